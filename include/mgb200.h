@@ -1,0 +1,188 @@
+/*
+ * mgb200.h -- C ABI of libmgb200.so, the B200 (sm_100a) multigrid V-cycle engine.
+ *
+ * The reference (claudiotomasi/LearnMultigrid) is pure Python; its "FFI" for the hot path is the set of
+ * native kernels it reaches through SciPy sparsetools, PyAMG amg_core and SuperLU from
+ * learn_multigrid/solvers/Multigrid.py.  Every entry point below names the reference call site it
+ * replaces.  Conventions:
+ *   - all pointers named d_* are DEVICE pointers (fp64 values, int32 column indices, int64 slice offsets);
+ *     h_* are HOST pointers; no torch types anywhere;
+ *   - every function returns 0 on success, a negative mg_status otherwise, never throws; the text of the
+ *     last failure on the calling thread is returned by mg_last_error();
+ *   - nothing allocates device memory: outputs and workspaces are passed in (sizes from the *_size calls);
+ *   - `stream` is a cudaStream_t passed as void*; work is enqueued, not synchronised, unless stated.
+ */
+#ifndef MGB200_H
+#define MGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    MG_OK = 0,
+    MG_ERR_INVALID = -1,   /* bad argument                                  */
+    MG_ERR_CUDA = -2,      /* a CUDA runtime call or launch failed          */
+    MG_ERR_UNSUPPORTED = -3,
+    MG_ERR_OVERFLOW = -4,  /* an index would not fit the int32 contract     */
+    MG_ERR_SINGULAR = -5   /* zero pivot in the coarsest-level inversion    */
+} mg_status;
+
+/* ------------------------------------------------------------------------------------------------ */
+/* library                                                                                          */
+int mg_version(void);
+const char *mg_last_error(void);
+/* fills sm_count / total global memory (bytes) / compute capability (e.g. 100) of the current device */
+int mg_device_info(int *sm_count, int64_t *global_mem, int *cc);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* CSR kernels (natural ordering).  CSR = (d_indptr[n+1], d_indices[nnz], d_values[nnz]).           */
+
+/* y = A x.   Replaces SciPy csr_matvec / csc_matvec:  Multigrid.py:62,90 (A.dot), :93 (i.T @ res, pass the
+ * CSR of Q^T), :115 (i @ u_coarse).  Row sums are accumulated in storage order with separate multiply and
+ * add (no FMA) so results are bit-identical to SciPy's. */
+int mg_spmv_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                const double *d_x, double *d_y, void *stream);
+/* r = b - A x.   Multigrid.py:62 and :90 (rhs - A.dot(u)). */
+int mg_residual_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                    const double *d_x, const double *d_b, double *d_r, void *stream);
+/* x_out = x + omega * (dinv * (b - A x)), out of place.  omega = 1 is Jacobi.py:35
+ * (self.solution += inv_d * self.residual_vector); the damped form is the smoother the commented dispatch at
+ * Multigrid.py:85-86,119-120 would call. */
+int mg_jacobi_sweep_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                        const double *d_dinv, const double *d_x, const double *d_b, double *d_x_out,
+                        double omega, void *stream);
+/* One multicolour Gauss-Seidel sweep, in place: for c in 0..ncolors-1, for every row i in
+ * d_color_rows[h_color_ptr[c] .. h_color_ptr[c+1]):  x_i = (b_i - sum_{j != i} A_ij x_j) / A_ii  (rows with a
+ * zero diagonal are skipped).  Per-row arithmetic is PyAMG amg_core::gauss_seidel's (call sites
+ * Multigrid.py:88,121); the row ORDER is the colour order instead of the index order. */
+int mg_gs_multicolor_sweep_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_indices,
+                               const double *d_values, double *d_x, const double *d_b,
+                               const int64_t *h_color_ptr, const int32_t *d_color_rows, int ncolors,
+                               void *stream);
+/* Exact lexicographic (index-order) Gauss-Seidel = PyAMG gauss_seidel(A, x, b, iterations, 'forward'),
+ * Multigrid.py:88,121, parallelised by dependency levels: rows of d_level_rows[h_level_ptr[l]..h_level_ptr[l+1])
+ * only depend on rows of earlier levels.  `iterations` full sweeps.  Bit-identical to the serial kernel. */
+int mg_gs_lex_sweep_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                        double *d_x, const double *d_b, const int64_t *d_level_ptr,
+                        const int32_t *d_level_rows, int64_t nlevels, int iterations, void *stream);
+/* u = u + Q e.   Multigrid.py:115 (u + i @ u_coarse): t = Q e from zero in storage order, then u + t. */
+int mg_prolong_correct_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_indices,
+                           const double *d_values, const double *d_e, double *d_u, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* SELL-32 kernels (the hot-path format).  A matrix is stored in slices of 32 consecutive rows; slice s
+ * holds len_s = (slice_ptr[s+1]-slice_ptr[s])/32 entries per row, column-major inside the slice:
+ * entry k of row r sits at slice_ptr[r/32] + 32*k + r%32.  Entries keep their CSR order; padding entries
+ * have value 0.0 and any valid column (the builder repeats the row's last column), so they add an exact
+ * zero to every row sum and are ignored by the diagonal detection of the Gauss-Seidel kernel.       */
+typedef struct {
+    int64_t nrows;
+    int64_t ncols;
+    int64_t nslices;            /* ceil(nrows/32)                                  */
+    const int64_t *d_slice_ptr; /* [nslices+1], entry offsets (multiples of 32)    */
+    const int32_t *d_cols;
+    const double *d_vals;
+} mg_sell;
+
+/* y = A x  (rows [row0,row1)) */
+int mg_sell_spmv(const mg_sell *A, const double *d_x, double *d_y, void *stream);
+/* r = b - A x */
+int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, double *d_r, void *stream);
+/* fused: *d_norm2 = sum_i (b - A x)_i^2 without storing r (outer loop Multigrid.py:62-63); d_partials is a
+ * workspace of mg_norm_workspace_size(nrows) doubles; deterministic two-stage reduction. */
+int mg_sell_residual_norm2(const mg_sell *A, const double *d_x, const double *d_b, double *d_partials,
+                           double *d_norm2, void *stream);
+int64_t mg_norm_workspace_size(int64_t n);
+/* x_out = x + omega*(dinv*(b - A x)) */
+int mg_sell_jacobi(const mg_sell *A, const double *d_dinv, const double *d_x, const double *d_b,
+                   double *d_x_out, double omega, void *stream);
+/* Gauss-Seidel update of the rows [row0,row1) in place (one colour of a colour-blocked ordering). */
+int mg_sell_gs_rows(const mg_sell *A, double *d_x, const double *d_b, int64_t row0, int64_t row1,
+                    void *stream);
+/* u_out = u + Q e  (u_out may alias u) */
+int mg_sell_prolong_correct(const mg_sell *Q, const double *d_e, const double *d_u, double *d_u_out,
+                            void *stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* vector kernels (Multigrid.py:63 np.linalg.norm; CG.py:30-48 dots and updates)                     */
+int mg_dot(int64_t n, const double *d_x, const double *d_y, double *d_partials, double *d_out, void *stream);
+int mg_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream);
+int mg_fill(int64_t n, double value, double *d_x, void *stream);
+/* out[i] = in[idx[i]] (permute into a level's ordering) and out[idx[i]] = in[i] (back) */
+int mg_gather(int64_t n, const int32_t *d_idx, const double *d_in, double *d_out, void *stream);
+int mg_scatter(int64_t n, const int32_t *d_idx, const double *d_in, double *d_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* coarsest level: dense direct solve.  Replaces spsolve(A_coarse, res_coarse) (SuperLU), Multigrid.py:106,
+ * which the reference refactorises in every cycle; here the inverse is formed once.                 */
+/* in: d_a row-major n x n (destroyed); out: d_ainv row-major n x n.  d_work: mg_dense_inverse_workspace(n)
+ * bytes.  Gauss-Jordan with partial pivoting, cooperative multi-CTA.  Synchronises the stream. */
+int mg_dense_inverse(int64_t n, double *d_a, double *d_ainv, void *d_work, void *stream);
+int64_t mg_dense_inverse_workspace(int64_t n);
+/* y = M x for a dense row-major n x m matrix (the coarse solve u = A^-1 r) */
+int mg_dense_gemv(int64_t n, int64_t m, const double *d_m, const double *d_x, double *d_y, void *stream);
+/* scatter a CSR matrix into a zeroed dense row-major n x n buffer */
+int mg_csr_to_dense(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                    double *d_dense, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* host-side (serial, HOST pointers) setup helpers                                                    */
+/* First-fit greedy colouring in index order on the symmetrised pattern of A; returns ncolors (>0) or <0.
+ * The colour order defines the multicolour Gauss-Seidel that replaces PyAMG's index-order sweep
+ * (Multigrid.py:88,121); the same colours are handed to the CPU oracle. */
+int mg_host_greedy_color(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_colors);
+/* dependency level of every row for an exact index-order sweep (see mg_gs_lex_sweep_csr); returns nlevels */
+int64_t mg_host_lex_levels(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_level);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* The V-cycle (Multigrid.v_cycle, Multigrid.py:77-124) over a prebuilt hierarchy.                   */
+enum { MG_SMOOTH_JACOBI = 0, MG_SMOOTH_MCGS = 1, MG_SMOOTH_LEXGS = 2 };
+enum { MG_COARSE_DENSE = 0, MG_COARSE_BCR = 1 };
+
+typedef struct {
+    int64_t n;                 /* rows on this level                                                     */
+    mg_sell A;                 /* operator in this level's ordering                                      */
+    const double *d_dinv;      /* 1/diag(A) (Jacobi)                                                     */
+    int32_t ncolors;           /* multicolour GS: colour c owns rows [h_color_ptr[c], h_color_ptr[c+1])  */
+    const int64_t *h_color_ptr;
+    /* exact lexicographic GS (parity mode): CSR + dependency levels, both in this level's ordering      */
+    const int32_t *d_csr_indptr, *d_csr_indices;
+    const double *d_csr_values;
+    const int64_t *d_lex_level_ptr;
+    const int32_t *d_lex_level_rows;
+    int64_t lex_nlevels;
+    mg_sell Q;                 /* n x n_coarse, prolongation  (absent on the coarsest level)             */
+    mg_sell QT;                /* n_coarse x n, restriction = explicit transpose                         */
+    double *d_x, *d_b, *d_r, *d_tmp;  /* level vectors; on level 0 d_x/d_b are the caller's                */
+    /* coarsest level only */
+    int32_t coarse_kind;
+    const double *d_coarse_inv;       /* MG_COARSE_DENSE: row-major n x n inverse                         */
+    const void *coarse_bcr;           /* MG_COARSE_BCR: handle from mg_bcr_create                         */
+} mg_level;
+
+typedef struct {
+    int32_t smoother;          /* MG_SMOOTH_*                                                            */
+    int32_t nu_pre, nu_post;   /* smooth_steps (the reference uses the same number before and after)     */
+    double omega;              /* Jacobi damping                                                         */
+    int32_t zero_guess_skip;   /* 1: skip A*0 work on coarse levels (results identical)                  */
+} mg_cycle_params;
+
+/* One V-cycle starting on levels[0]: pre-smooth, residual, restrict, recurse / coarsest solve,
+ * prolong + correct, post-smooth.  Launches only; capturable in a CUDA graph. */
+int mg_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, void *stream);
+/* number of kernels the last mg_vcycle call on this thread launched (bench.py's gpu_launches) */
+int64_t mg_last_launch_count(void);
+
+/* CUDA-graph helpers: capture whatever is enqueued on `stream` between begin and end. */
+int mg_graph_begin(void *stream);
+int mg_graph_end(void *stream, void **graph_exec_out);
+int mg_graph_launch(void *graph_exec, void *stream);
+int mg_graph_destroy(void *graph_exec);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB200_H */

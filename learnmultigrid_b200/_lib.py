@@ -1,0 +1,140 @@
+"""ctypes binding of libmgb200.so (C ABI declared in include/mgb200.h).
+
+The library is built in-tree by `learnmultigrid_b200._lib.build()` (nvcc, sm_100a only).  There is no CPU
+fallback: every compute entry point raises if the library is missing or no CUDA device is present.
+"""
+import ctypes
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmgb200.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+c_i32p = ctypes.c_void_p      # device pointers travel as integers
+c_f64p = ctypes.c_void_p
+c_i64 = ctypes.c_int64
+c_int = ctypes.c_int
+c_dbl = ctypes.c_double
+c_vp = ctypes.c_void_p
+
+MG_SMOOTH_JACOBI, MG_SMOOTH_MCGS, MG_SMOOTH_LEXGS = 0, 1, 2
+MG_COARSE_DENSE, MG_COARSE_BCR = 0, 1
+
+
+class MgError(RuntimeError):
+    pass
+
+
+class mg_sell(ctypes.Structure):
+    _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nslices", c_i64),
+                ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp)]
+
+
+class mg_level(ctypes.Structure):
+    _fields_ = [("n", c_i64), ("A", mg_sell), ("d_dinv", c_vp),
+                ("ncolors", ctypes.c_int32), ("h_color_ptr", ctypes.POINTER(c_i64)),
+                ("d_csr_indptr", c_vp), ("d_csr_indices", c_vp), ("d_csr_values", c_vp),
+                ("d_lex_level_ptr", c_vp), ("d_lex_level_rows", c_vp), ("lex_nlevels", c_i64),
+                ("Q", mg_sell), ("QT", mg_sell),
+                ("d_x", c_vp), ("d_b", c_vp), ("d_r", c_vp), ("d_tmp", c_vp),
+                ("coarse_kind", ctypes.c_int32), ("d_coarse_inv", c_vp), ("coarse_bcr", c_vp)]
+
+
+class mg_cycle_params(ctypes.Structure):
+    _fields_ = [("smoother", ctypes.c_int32), ("nu_pre", ctypes.c_int32), ("nu_post", ctypes.c_int32),
+                ("omega", c_dbl), ("zero_guess_skip", ctypes.c_int32)]
+
+
+# name -> (restype, argtypes).  tests/test_abi.py checks that every function declared in include/mgb200.h is
+# listed here and exported by the built library.
+_SIGNATURES = {
+    "mg_version": (c_int, []),
+    "mg_last_error": (ctypes.c_char_p, []),
+    "mg_device_info": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_i64), ctypes.POINTER(c_int)]),
+    "mg_spmv_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_residual_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_jacobi_sweep_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
+    "mg_gs_multicolor_sweep_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), c_vp,
+                                           c_int, c_vp]),
+    "mg_gs_lex_sweep_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
+    "mg_prolong_correct_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_sell_spmv": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
+    "mg_sell_residual": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
+    "mg_sell_residual_norm2": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_norm_workspace_size": (c_i64, [c_i64]),
+    "mg_sell_jacobi": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
+    "mg_sell_gs_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "mg_sell_prolong_correct": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
+    "mg_dot": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_axpby": (c_int, [c_i64, c_dbl, c_vp, c_dbl, c_vp, c_vp, c_vp]),
+    "mg_fill": (c_int, [c_i64, c_dbl, c_vp, c_vp]),
+    "mg_gather": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mg_scatter": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mg_dense_inverse": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mg_dense_inverse_workspace": (c_i64, [c_i64]),
+    "mg_dense_gemv": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mg_csr_to_dense": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_host_greedy_color": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
+    "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),
+    "mg_last_launch_count": (c_i64, []),
+    "mg_graph_begin": (c_int, [c_vp]),
+    "mg_graph_end": (c_int, [c_vp, ctypes.POINTER(c_vp)]),
+    "mg_graph_launch": (c_int, [c_vp, c_vp]),
+    "mg_graph_destroy": (c_int, [c_vp]),
+}
+
+_lib = None
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/*.cu for sm_100a into learnmultigrid_b200/libmgb200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", CSRC, "-j8"]
+    if force:
+        cmd.append("-B")
+    out = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if out.returncode != 0:
+        raise MgError("building libmgb200.so failed:\n" + out.stdout)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+def load():
+    """Load libmgb200.so and install the prototypes.  Fails loudly if it is missing: no fallback exists."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise MgError("libmgb200.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`"
+                      % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)      # AttributeError here = header / library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().mg_last_error().decode("utf-8", "replace")
+        raise MgError("libmgb200 %s failed (status %d): %s" % (what, rc, msg))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise MgError("learnmultigrid_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def ptr(t):
+    """device pointer of a torch tensor (or None -> NULL)"""
+    return None if t is None else t.data_ptr()
+
+
+def stream_handle(torch):
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,79 @@
+// common.cuh -- shared helpers of libmgb200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include "../../include/mgb200.h"
+
+namespace mgb {
+
+extern thread_local char g_last_error[512];
+extern thread_local int64_t g_launch_count;
+
+inline int set_error(int code, const char *what, const char *detail) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what, detail ? detail : "");
+    return code;
+}
+
+#define MG_CHECK_CUDA(expr)                                                                   \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) return mgb::set_error(MG_ERR_CUDA, #expr, cudaGetErrorString(_e)); \
+    } while (0)
+
+#define MG_CHECK_LAUNCH(name)                                                                 \
+    do {                                                                                      \
+        cudaError_t _e = cudaGetLastError();                                                  \
+        if (_e != cudaSuccess) return mgb::set_error(MG_ERR_CUDA, name, cudaGetErrorString(_e)); \
+        ++mgb::g_launch_count;                                                                \
+    } while (0)
+
+#define MG_REQUIRE(cond, msg)                                                                 \
+    do {                                                                                      \
+        if (!(cond)) return mgb::set_error(MG_ERR_INVALID, __func__, msg);                    \
+    } while (0)
+
+constexpr int kSlice = 32;      // SELL slice height = one warp
+constexpr int kBlock = 256;     // threads per CTA of the streaming kernels
+
+// IEEE multiply / add that the compiler may not contract into an FMA: the CPU oracle (gcc
+// -ffp-contract=off, SciPy, PyAMG) rounds the product and the sum separately and we match it bit for bit.
+__device__ __forceinline__ double mul_add_unfused(double acc, double a, double b) {
+    return __dadd_rn(acc, __dmul_rn(a, b));
+}
+
+// streaming (read-once) loads of the matrix arrays: do not pollute L1, which we want for the x gathers
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
+
+inline int sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&cached, cudaDevAttrMultiProcessorCount, dev);
+        if (cached <= 0) cached = 148;
+    }
+    return cached;
+}
+
+// deterministic block reduction (fixed tree), result valid in thread 0
+template <int BLOCK>
+__device__ __forceinline__ double block_sum(double v) {
+    __shared__ double sh[BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (l < BLOCK / 32) ? sh[l] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    }
+    __syncthreads();
+    return v;
+}
+
+}  // namespace mgb

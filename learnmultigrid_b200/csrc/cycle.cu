@@ -1,0 +1,181 @@
+// cycle.cu -- V-cycle orchestration over a prebuilt device hierarchy, CUDA-graph helpers, library globals.
+// Statement order follows Multigrid.v_cycle (learn_multigrid/solvers/Multigrid.py:77-124):
+//   pre-smooth (:88) -> residual (:90) -> restrict (:93) -> recurse (:102-104) or coarsest solve (:106)
+//   -> prolong + correct (:115) -> post-smooth (:121).
+// The Galerkin product (:97-98) and the coarse factorisation (:106), which the reference repeats in every
+// cycle, are hoisted to setup; the arithmetic of a cycle is unchanged.
+#include "common.cuh"
+
+namespace mgb {
+
+thread_local char g_last_error[512] = "";
+thread_local int64_t g_launch_count = 0;
+thread_local int64_t g_last_cycle_launches = 0;
+
+int sell_spmv(const mg_sell *, const double *, double *, cudaStream_t);
+int sell_residual(const mg_sell *, const double *, const double *, double *, cudaStream_t);
+int sell_jacobi(const mg_sell *, const double *, const double *, const double *, double *, double, cudaStream_t);
+int sell_gs_rows(const mg_sell *, double *, const double *, int64_t, int64_t, cudaStream_t);
+int sell_prolong(const mg_sell *, const double *, const double *, double *, cudaStream_t);
+int vec_axpby(int64_t, double, const double *, double, const double *, double *, cudaStream_t);
+int vec_fill(int64_t, double, double *, cudaStream_t);
+int vec_diag_scale(int64_t, double, const double *, const double *, double *, cudaStream_t);
+int dense_gemv(int64_t, int64_t, const double *, const double *, double *, cudaStream_t);
+int csr_gs_lex(const int32_t *, const int32_t *, const double *, double *, const double *, const int64_t *,
+               const int32_t *, int64_t, int64_t, int, cudaStream_t);
+int bcr_solve(const void *handle, const double *rhs, double *x, cudaStream_t st);
+
+#define MG_TRY(expr)            \
+    do {                        \
+        int _rc = (expr);       \
+        if (_rc) return _rc;    \
+    } while (0)
+
+// `steps` smoothing sweeps on level L.  cur points at the buffer holding the iterate and is updated
+// (Jacobi ping-pongs between d_x and d_tmp).  zero_guess: the iterate is known to be exactly zero and the
+// buffer has NOT been initialised.
+static int smooth(const mg_level &L, const mg_cycle_params &P, int steps, double **cur, double **alt,
+                  bool zero_guess, cudaStream_t st) {
+    if (steps <= 0) {
+        if (zero_guess) MG_TRY(vec_fill(L.n, 0.0, *cur, st));
+        return MG_OK;
+    }
+    if (P.smoother == MG_SMOOTH_JACOBI) {
+        int s = 0;
+        if (zero_guess) {
+            if (P.zero_guess_skip) {
+                // x1 = 0 + omega*(dinv*(b - A*0)) = omega*(dinv*b): same bits as a sweep on zeros, no matrix pass
+                MG_TRY(vec_diag_scale(L.n, P.omega, L.d_dinv, L.d_b, *alt, st));
+                double *t = *cur; *cur = *alt; *alt = t;
+                s = 1;
+            } else {
+                MG_TRY(vec_fill(L.n, 0.0, *cur, st));
+            }
+        }
+        for (; s < steps; ++s) {
+            MG_TRY(sell_jacobi(&L.A, L.d_dinv, *cur, L.d_b, *alt, P.omega, st));
+            double *t = *cur; *cur = *alt; *alt = t;
+        }
+        return MG_OK;
+    }
+    if (zero_guess) MG_TRY(vec_fill(L.n, 0.0, *cur, st));
+    if (P.smoother == MG_SMOOTH_MCGS) {
+        if (L.ncolors <= 0 || !L.h_color_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no colouring");
+        for (int s = 0; s < steps; ++s)
+            for (int c = 0; c < L.ncolors; ++c)
+                MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
+        return MG_OK;
+    }
+    if (P.smoother == MG_SMOOTH_LEXGS) {
+        if (!L.d_csr_indptr || !L.d_lex_level_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no lexicographic schedule");
+        return csr_gs_lex(L.d_csr_indptr, L.d_csr_indices, L.d_csr_values, *cur, L.d_b, L.d_lex_level_ptr,
+                          L.d_lex_level_rows, L.lex_nlevels, L.n, steps, st);
+    }
+    return set_error(MG_ERR_INVALID, "mg_vcycle", "unknown smoother");
+}
+
+static int vcycle_rec(const mg_level *levels, int nlevels, int l, const mg_cycle_params &P, cudaStream_t st) {
+    const mg_level &L = levels[l];
+    if (l == nlevels - 1) {   // coarsest: direct solve (Multigrid.py:106)
+        if (L.coarse_kind == MG_COARSE_DENSE) {
+            if (!L.d_coarse_inv) return set_error(MG_ERR_INVALID, "mg_vcycle", "coarsest level has no inverse");
+            return dense_gemv(L.n, L.n, L.d_coarse_inv, L.d_b, L.d_x, st);
+        }
+        if (L.coarse_kind == MG_COARSE_BCR) return bcr_solve(L.coarse_bcr, L.d_b, L.d_x, st);
+        return set_error(MG_ERR_INVALID, "mg_vcycle", "unknown coarse solver kind");
+    }
+    const mg_level &C = levels[l + 1];
+    const bool jac = P.smoother == MG_SMOOTH_JACOBI;
+    const bool zero_guess = l > 0;
+    double *cur = L.d_x, *alt = L.d_tmp;
+    bool prolong_flip = false;
+    if (jac) {
+        // Jacobi flips buffers once per sweep.  The result must end in d_x: on coarse levels choose the
+        // start buffer (the zero guess is virtual), on level 0 let the prolongation write out of place.
+        const int flips = P.nu_pre + P.nu_post;
+        if (flips & 1) {
+            if (zero_guess) { cur = L.d_tmp; alt = L.d_x; }
+            else prolong_flip = true;
+        }
+    }
+    MG_TRY(smooth(L, P, P.nu_pre, &cur, &alt, zero_guess, st));
+    MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));              // res = rhs - A u
+    MG_TRY(sell_spmv(&L.QT, L.d_r, C.d_b, st));                      // res_coarse = Q^T res
+    MG_TRY(vcycle_rec(levels, nlevels, l + 1, P, st));               // u_coarse
+    if (prolong_flip) {
+        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, alt, st));             // u = u + Q u_coarse (out of place)
+        double *t = cur; cur = alt; alt = t;
+    } else {
+        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, cur, st));
+    }
+    MG_TRY(smooth(L, P, P.nu_post, &cur, &alt, false, st));
+    if (cur != L.d_x) MG_TRY(vec_axpby(L.n, 1.0, cur, 0.0, nullptr, L.d_x, st));   // safety net; not reached
+    return MG_OK;
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+int mg_version(void) { return 100; }
+const char *mg_last_error(void) { return g_last_error; }
+
+int mg_device_info(int *sm, int64_t *mem, int *cc) {
+    int dev = 0;
+    MG_CHECK_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp p;
+    MG_CHECK_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (sm) *sm = p.multiProcessorCount;
+    if (mem) *mem = (int64_t)p.totalGlobalMem;
+    if (cc) *cc = p.major * 10 + p.minor;
+    return MG_OK;
+}
+
+int mg_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, void *stream) {
+    MG_REQUIRE(levels && params && nlevels >= 2, "need at least two levels (Multigrid.py:78,102: levels=1 is not handled by the reference either)");
+    MG_REQUIRE(params->nu_pre >= 0 && params->nu_post >= 0, "negative smoothing steps");
+    for (int l = 0; l < nlevels; ++l) {
+        MG_REQUIRE(levels[l].n > 0 && levels[l].d_x && levels[l].d_b, "level vectors missing");
+        if (l + 1 < nlevels) {
+            MG_REQUIRE(levels[l].d_r && levels[l].d_tmp, "level work vectors missing");
+            MG_REQUIRE(levels[l].A.nrows == levels[l].n && levels[l].Q.nrows == levels[l].n &&
+                           levels[l].QT.nrows == levels[l + 1].n && levels[l].Q.ncols == levels[l + 1].n,
+                       "inconsistent level shapes");
+        }
+    }
+    const int64_t before = g_launch_count;
+    int rc = vcycle_rec(levels, nlevels, 0, *params, (cudaStream_t)stream);
+    g_last_cycle_launches = g_launch_count - before;
+    return rc;
+}
+
+int64_t mg_last_launch_count(void) { return g_last_cycle_launches; }
+
+int mg_graph_begin(void *stream) {
+    MG_CHECK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+    return MG_OK;
+}
+int mg_graph_end(void *stream, void **graph_exec_out) {
+    MG_REQUIRE(graph_exec_out, "null output");
+    cudaGraph_t graph = nullptr;
+    MG_CHECK_CUDA(cudaStreamEndCapture((cudaStream_t)stream, &graph));
+    cudaGraphExec_t exec = nullptr;
+    cudaError_t e = cudaGraphInstantiate(&exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return set_error(MG_ERR_CUDA, "cudaGraphInstantiate", cudaGetErrorString(e));
+    *graph_exec_out = (void *)exec;
+    return MG_OK;
+}
+int mg_graph_launch(void *graph_exec, void *stream) {
+    MG_REQUIRE(graph_exec, "null graph");
+    MG_CHECK_CUDA(cudaGraphLaunch((cudaGraphExec_t)graph_exec, (cudaStream_t)stream));
+    return MG_OK;
+}
+int mg_graph_destroy(void *graph_exec) {
+    if (graph_exec) MG_CHECK_CUDA(cudaGraphExecDestroy((cudaGraphExec_t)graph_exec));
+    return MG_OK;
+}
+
+}  // extern "C"

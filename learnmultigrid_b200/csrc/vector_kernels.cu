@@ -1,0 +1,130 @@
+// vector_kernels.cu -- level-vector kernels: dot / norm (deterministic two-stage), axpby, fill, permute.
+// Reference call sites: np.linalg.norm at Multigrid.py:63; dots and updates of CG.py:30-48.
+#include "common.cuh"
+
+namespace mgb {
+
+__global__ void __launch_bounds__(kBlock)
+dot_partials_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
+                    double *__restrict__ partials) {
+    // each CTA owns a fixed contiguous chunk of 4*kBlock elements per pass -> fixed summation order
+    double s = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) s += x[i] * y[i];
+    s = block_sum<kBlock>(s);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024) reduce_partials_kernel2(const double *__restrict__ partials, int64_t n,
+                                                                double *__restrict__ out) {
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < n; i += 1024) s += partials[i];
+    s = block_sum<1024>(s);
+    if (threadIdx.x == 0) *out = s;
+}
+
+__global__ void __launch_bounds__(kBlock)
+axpby_kernel(int64_t n, double a, const double *x, double b, const double *y, double *out) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        // a*x + b*y with separately rounded products and sum; b == 0 skips y entirely (y may be null)
+        const double ax = __dmul_rn(a, x[i]);
+        out[i] = (b == 0.0) ? ax : __dadd_rn(ax, __dmul_rn(b, y[i]));
+    }
+}
+
+// out = omega * (dinv .* b): the first damped-Jacobi sweep from a zero iterate (no matrix pass needed)
+__global__ void __launch_bounds__(kBlock)
+diag_scale_kernel(int64_t n, double omega, const double *__restrict__ dinv, const double *__restrict__ b,
+                  double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
+        out[i] = __dadd_rn(0.0, __dmul_rn(omega, __dmul_rn(dinv[i], b[i])));
+}
+
+__global__ void __launch_bounds__(kBlock) fill_kernel(int64_t n, double v, double *x) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) x[i] = v;
+}
+
+__global__ void __launch_bounds__(kBlock)
+gather_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ in, double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) out[i] = in[idx[i]];
+}
+
+__global__ void __launch_bounds__(kBlock)
+scatter_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ in, double *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) out[idx[i]] = in[i];
+}
+
+static inline unsigned stream_grid(int64_t n) {
+    int64_t g = (n + kBlock - 1) / kBlock;
+    const int64_t cap = (int64_t)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (unsigned)g;
+}
+
+int vec_dot(int64_t n, const double *x, const double *y, double *partials, double *out, cudaStream_t st) {
+    const unsigned g = stream_grid(n);
+    dot_partials_kernel<<<g, kBlock, 0, st>>>(n, x, y, partials);
+    MG_CHECK_LAUNCH("dot_partials");
+    reduce_partials_kernel2<<<1, 1024, 0, st>>>(partials, g, out);
+    MG_CHECK_LAUNCH("reduce_partials");
+    return MG_OK;
+}
+int vec_axpby(int64_t n, double a, const double *x, double b, const double *y, double *out, cudaStream_t st) {
+    if (n <= 0) return MG_OK;
+    axpby_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, a, x, b, y, out);
+    MG_CHECK_LAUNCH("axpby");
+    return MG_OK;
+}
+int vec_diag_scale(int64_t n, double omega, const double *dinv, const double *b, double *out, cudaStream_t st) {
+    if (n <= 0) return MG_OK;
+    diag_scale_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, omega, dinv, b, out);
+    MG_CHECK_LAUNCH("diag_scale");
+    return MG_OK;
+}
+int vec_fill(int64_t n, double v, double *x, cudaStream_t st) {
+    if (n <= 0) return MG_OK;
+    fill_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, v, x);
+    MG_CHECK_LAUNCH("fill");
+    return MG_OK;
+}
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+int mg_dot(int64_t n, const double *d_x, const double *d_y, double *d_partials, double *d_out, void *stream) {
+    MG_REQUIRE(n >= 0, "negative size");
+    return vec_dot(n, d_x, d_y, d_partials, d_out, (cudaStream_t)stream);
+}
+int mg_axpby(int64_t n, double a, const double *d_x, double b, const double *d_y, double *d_out, void *stream) {
+    MG_REQUIRE(n >= 0, "negative size");
+    return vec_axpby(n, a, d_x, b, d_y, d_out, (cudaStream_t)stream);
+}
+int mg_fill(int64_t n, double value, double *d_x, void *stream) {
+    MG_REQUIRE(n >= 0, "negative size");
+    return vec_fill(n, value, d_x, (cudaStream_t)stream);
+}
+int mg_gather(int64_t n, const int32_t *d_idx, const double *d_in, double *d_out, void *stream) {
+    MG_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return MG_OK;
+    gather_kernel<<<stream_grid(n), kBlock, 0, (cudaStream_t)stream>>>(n, d_idx, d_in, d_out);
+    MG_CHECK_LAUNCH("gather");
+    return MG_OK;
+}
+int mg_scatter(int64_t n, const int32_t *d_idx, const double *d_in, double *d_out, void *stream) {
+    MG_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return MG_OK;
+    scatter_kernel<<<stream_grid(n), kBlock, 0, (cudaStream_t)stream>>>(n, d_idx, d_in, d_out);
+    MG_CHECK_LAUNCH("scatter");
+    return MG_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,324 @@
+"""Device multigrid hierarchy and V-cycle engine (host side of libmgb200).
+
+`DeviceHierarchy` owns, per level, the operator A_l, the transfer operators Q_l / Q_l^T (SELL-32, fp64 values,
+int32 columns), the level vectors and the smoother data, all resident in HBM, and replays one captured CUDA
+graph per V-cycle.  It is what `learnmultigrid_b200.solvers.Multigrid` drives; the arithmetic it performs is
+the reference's `Multigrid.v_cycle` (learn_multigrid/solvers/Multigrid.py:77-124) with the Galerkin product
+(:97-98) and the coarse factorisation (:106) hoisted out of the cycle.
+
+Orderings.  For multicolour Gauss-Seidel every level is stored colour-blocked (rows of colour 0 first, ...;
+natural order inside a colour; matrix columns and the transfer operators relabelled accordingly; entries keep
+their natural order inside every row), so that each colour's sweep streams one contiguous slab of the matrix
+and reads/writes x contiguously.  Vectors are permuted once on the way in and out.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+from . import formats as F
+from . import setup_device as SD
+
+DENSE_COARSE_MAX = 4096
+
+
+class DeviceSell:
+    """SELL-32 matrix in device memory."""
+
+    def __init__(self, torch, A_csr, device, sell=None):
+        slice_ptr, cols, vals = F.csr_to_sell(A_csr) if sell is None else sell
+        self.shape = A_csr.shape
+        self.nnz = int(A_csr.nnz)
+        self.padded = int(slice_ptr[-1])
+        self.slice_ptr = torch.from_numpy(slice_ptr).to(device)
+        self.cols = torch.from_numpy(cols).to(device)
+        self.vals = torch.from_numpy(vals).to(device)
+        self.struct = _lib.mg_sell(self.shape[0], self.shape[1], (self.shape[0] + 31) // 32,
+                                   self.slice_ptr.data_ptr(), self.cols.data_ptr(), self.vals.data_ptr())
+
+    @classmethod
+    def from_device(cls, shape, nnz, slice_ptr, cols, vals):
+        self = cls.__new__(cls)
+        self.shape = tuple(shape)
+        self.nnz = int(nnz)
+        self.padded = int(cols.numel())
+        self.slice_ptr, self.cols, self.vals = slice_ptr, cols, vals
+        self.struct = _lib.mg_sell(shape[0], shape[1], (shape[0] + 31) // 32,
+                                   slice_ptr.data_ptr(), cols.data_ptr(), vals.data_ptr())
+        return self
+
+    def bytes(self):
+        return self.padded * 12 + self.slice_ptr.numel() * 8
+
+
+class Level:
+    pass
+
+
+def algorithmic_bytes_csr(nnz, n):
+    """S(nnz, n) of SURVEY.md 8(d): 8 B value + 4 B column per entry, 4 B row pointer per row."""
+    return 12 * nnz + 4 * (n + 1)
+
+
+class DeviceHierarchy:
+    """Prebuilt multigrid hierarchy on one GPU.
+
+    A        : fine operator (anything SciPy accepts), n0 x n0
+    Q_list   : transfer operators [Q_0 (n0 x n1), Q_1, ...]; levels = len(Q_list) + 1
+    smoother : "jacobi" | "mcgs" (multicolour Gauss-Seidel) | "lexgs" (exact index-order Gauss-Seidel)
+    colors   : optional list of per-level colour arrays for "mcgs" (default: first-fit greedy colouring)
+    setup    : "device" (SpGEMM / transposes / SELL build by CUDA kernels) or "host" (NumPy/SciPy cross-check)
+    """
+
+    def __init__(self, A, Q_list, smoother="jacobi", colors=None, device=None, setup="host",
+                 dense_coarse_max=DENSE_COARSE_MAX, keep_host=True):
+        torch = _lib.require_cuda()
+        self.torch = torch
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if smoother not in ("jacobi", "mcgs", "lexgs"):
+            raise ValueError("unknown smoother %r" % (smoother,))
+        self.smoother = smoother
+        self.nlevels = len(Q_list) + 1
+        if self.nlevels < 2:
+            raise ValueError("need at least one transfer operator (levels >= 2)")
+        self.keep_host = keep_host
+        self._graphs = {}
+        self._keep = []          # tensors / ctypes buffers that must outlive the level structs
+        self.setup_kind = setup
+        if setup == "host":
+            self._setup_host(A, Q_list, colors, dense_coarse_max)
+        elif setup == "device":
+            SD.setup_device(self, A, Q_list, colors, dense_coarse_max)
+        else:
+            raise ValueError("setup must be 'device' or 'host'")
+        self._finish_structs()
+
+    # ------------------------------------------------------------------------------------------------
+    def _setup_host(self, A, Q_list, colors, dense_coarse_max):
+        """Hierarchy build with SciPy/NumPy on the host (formats.build_host_hierarchy), then upload."""
+        torch, dev = self.torch, self.device
+        L = self.nlevels
+        host = F.build_host_hierarchy(A, Q_list, self.smoother, colors, with_sell=True)
+        self.host_A = [d["A_nat"] for d in host] if self.keep_host else None
+        self.host_Q = [d.get("Q_nat") for d in host[:-1]] if self.keep_host else None
+        self.colors = [d["colors"] for d in host]
+        self.levels = []
+        for l, d in enumerate(host):
+            lev = Level()
+            lev.n = d["n"]
+            lev.perm = None if d["perm"] is None else torch.from_numpy(d["perm"]).to(dev)
+            lev.color_ptr = d["color_ptr"]
+            lev.nnz_A = d["nnz_A"]
+            if l < L - 1:
+                lev.A = DeviceSell(torch, d["A"], dev, d["A_sell"])
+                lev.dinv = torch.from_numpy(d["dinv"]).to(dev)
+                lev.Q = DeviceSell(torch, d["Q"], dev, d["Q_sell"])
+                lev.QT = DeviceSell(torch, d["QT"], dev, d["QT_sell"])
+                lev.nnz_Q = d["nnz_Q"]
+                if self.smoother == "lexgs":
+                    An = d["A_nat"]
+                    lev.csr = tuple(torch.from_numpy(a).to(dev) for a in (An.indptr, An.indices, An.data))
+                    lev.lex_ptr = torch.from_numpy(d["lex_ptr"]).to(dev)
+                    lev.lex_rows = torch.from_numpy(d["lex_rows"]).to(dev)
+                    lev.lex_nlevels = len(d["lex_ptr"]) - 1
+            else:
+                self._setup_coarsest(lev, d["A_nat"], dense_coarse_max)
+            self.levels.append(lev)
+
+    def _setup_coarsest(self, lev, A_csr, dense_coarse_max):
+        """Coarsest level: explicit dense inverse (replaces the per-cycle spsolve of Multigrid.py:106)."""
+        torch, dev = self.torch, self.device
+        n = A_csr.shape[0]
+        if n > dense_coarse_max:
+            raise _lib.MgError("coarsest level has %d unknowns (> %d): banded BCR solver required" % (n, dense_coarse_max))
+        ip = torch.from_numpy(A_csr.indptr).to(dev)
+        ix = torch.from_numpy(A_csr.indices).to(dev)
+        va = torch.from_numpy(A_csr.data).to(dev)
+        self._dense_coarse_from_device_csr(lev, n, ip, ix, va)
+
+    def _dense_coarse_from_device_csr(self, lev, n, ip, ix, va):
+        torch, dev = self.torch, self.device
+        st = _lib.stream_handle(torch)
+        dense = torch.empty(n * n, dtype=torch.float64, device=dev)
+        _lib.check(self.lib.mg_csr_to_dense(n, ip.data_ptr(), ix.data_ptr(), va.data_ptr(), dense.data_ptr(), st),
+                   "mg_csr_to_dense")
+        inv = torch.empty(n * n, dtype=torch.float64, device=dev)
+        work = torch.empty(int(self.lib.mg_dense_inverse_workspace(n)), dtype=torch.uint8, device=dev)
+        _lib.check(self.lib.mg_dense_inverse(n, dense.data_ptr(), inv.data_ptr(), work.data_ptr(), st),
+                   "mg_dense_inverse")
+        lev.coarse_kind = _lib.MG_COARSE_DENSE
+        lev.coarse_inv = inv
+        lev.coarse_bytes = n * n * 8
+
+    # ------------------------------------------------------------------------------------------------
+    def _finish_structs(self):
+        torch, dev = self.torch, self.device
+        L = self.nlevels
+        for lev in self.levels:
+            n = lev.n
+            lev.x = torch.zeros(n, dtype=torch.float64, device=dev)
+            lev.b = torch.zeros(n, dtype=torch.float64, device=dev)
+            lev.r = torch.zeros(n, dtype=torch.float64, device=dev)
+            lev.tmp = torch.zeros(n, dtype=torch.float64, device=dev)
+        n0 = self.levels[0].n
+        self.n = n0
+        self._stage = torch.zeros(n0, dtype=torch.float64, device=dev)       # natural-order staging
+        self._pinned = torch.zeros(n0, dtype=torch.float64).pin_memory()
+        self._norm_ws = torch.zeros(int(self.lib.mg_norm_workspace_size(n0)) + 4096, dtype=torch.float64, device=dev)
+        self._norm_out = torch.zeros(1, dtype=torch.float64, device=dev)
+        self._norm_host = torch.zeros(1, dtype=torch.float64).pin_memory()
+        arr = (_lib.mg_level * L)()
+        for l, lev in enumerate(self.levels):
+            s = arr[l]
+            s.n = lev.n
+            s.d_x, s.d_b, s.d_r, s.d_tmp = (t.data_ptr() for t in (lev.x, lev.b, lev.r, lev.tmp))
+            if l < L - 1:
+                s.A, s.Q, s.QT = lev.A.struct, lev.Q.struct, lev.QT.struct
+                s.d_dinv = lev.dinv.data_ptr()
+                if lev.color_ptr is not None:
+                    cp = (ctypes.c_int64 * len(lev.color_ptr))(*[int(v) for v in lev.color_ptr])
+                    self._keep.append(cp)
+                    s.ncolors = len(lev.color_ptr) - 1
+                    s.h_color_ptr = ctypes.cast(cp, ctypes.POINTER(ctypes.c_int64))
+                if getattr(lev, "csr", None) is not None and getattr(lev, "lex_ptr", None) is not None:
+                    s.d_csr_indptr, s.d_csr_indices, s.d_csr_values = (t.data_ptr() for t in lev.csr)
+                    s.d_lex_level_ptr = lev.lex_ptr.data_ptr()
+                    s.d_lex_level_rows = lev.lex_rows.data_ptr()
+                    s.lex_nlevels = lev.lex_nlevels
+            else:
+                s.coarse_kind = lev.coarse_kind
+                if lev.coarse_kind == _lib.MG_COARSE_DENSE:
+                    s.d_coarse_inv = lev.coarse_inv.data_ptr()
+                else:
+                    s.coarse_bcr = lev.coarse_bcr
+        self._level_structs = arr
+
+    # ------------------------------------------------------------------------------------------------
+    # vectors in and out (host NumPy <-> permuted device vectors)
+    def _to_level0(self, host_vec, dst):
+        torch = self.torch
+        v = np.ascontiguousarray(np.asarray(host_vec, dtype=np.float64).reshape(-1))
+        if v.size != self.n:
+            raise ValueError("vector has %d entries, operator has %d rows" % (v.size, self.n))
+        self._pinned.copy_(torch.from_numpy(v))
+        lev = self.levels[0]
+        if lev.perm is None:
+            dst.copy_(self._pinned, non_blocking=True)
+        else:
+            self._stage.copy_(self._pinned, non_blocking=True)
+            _lib.check(self.lib.mg_gather(self.n, lev.perm.data_ptr(), self._stage.data_ptr(), dst.data_ptr(),
+                                          _lib.stream_handle(torch)), "mg_gather")
+
+    def _from_level0(self, src):
+        torch = self.torch
+        lev = self.levels[0]
+        if lev.perm is None:
+            self._pinned.copy_(src, non_blocking=True)
+        else:
+            _lib.check(self.lib.mg_scatter(self.n, lev.perm.data_ptr(), src.data_ptr(), self._stage.data_ptr(),
+                                           _lib.stream_handle(torch)), "mg_scatter")
+            self._pinned.copy_(self._stage, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return self._pinned.numpy().copy().reshape(-1, 1)
+
+    def set_rhs(self, b):
+        self._to_level0(b, self.levels[0].b)
+
+    def set_x(self, x):
+        self._to_level0(x, self.levels[0].x)
+
+    def zero_x(self):
+        self.levels[0].x.zero_()
+
+    def get_x(self):
+        return self._from_level0(self.levels[0].x)
+
+    # ------------------------------------------------------------------------------------------------
+    def residual_norm(self):
+        """||b - A x||_2 on level 0, fused residual + norm (Multigrid.py:62-63), one D2H of 8 bytes."""
+        torch = self.torch
+        lev = self.levels[0]
+        st = _lib.stream_handle(torch)
+        _lib.check(self.lib.mg_sell_residual_norm2(ctypes.byref(lev.A.struct), lev.x.data_ptr(), lev.b.data_ptr(),
+                                                   self._norm_ws.data_ptr(), self._norm_out.data_ptr(), st),
+                   "mg_sell_residual_norm2")
+        self._norm_host.copy_(self._norm_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(np.sqrt(self._norm_host.item()))
+
+    def residual_vector(self):
+        lev = self.levels[0]
+        _lib.check(self.lib.mg_sell_residual(ctypes.byref(lev.A.struct), lev.x.data_ptr(), lev.b.data_ptr(),
+                                             lev.r.data_ptr(), _lib.stream_handle(self.torch)), "mg_sell_residual")
+        return self._from_level0(lev.r)
+
+    def make_params(self, nu_pre=1, nu_post=None, omega=1.0, zero_guess_skip=True):
+        sm = {"jacobi": _lib.MG_SMOOTH_JACOBI, "mcgs": _lib.MG_SMOOTH_MCGS, "lexgs": _lib.MG_SMOOTH_LEXGS}[self.smoother]
+        return _lib.mg_cycle_params(sm, int(nu_pre), int(nu_pre if nu_post is None else nu_post), float(omega),
+                                    1 if zero_guess_skip else 0)
+
+    def vcycle(self, params, nlevels=None, use_graph=True):
+        """One V-cycle on the level-0 vectors (x updated in place).  The launch sequence is captured into a CUDA
+        graph the first time a parameter set is used and replayed afterwards."""
+        torch = self.torch
+        L = self.nlevels if nlevels is None else int(nlevels)
+        st = _lib.stream_handle(torch)
+        if not use_graph or self.smoother == "lexgs":      # cooperative launches are not captured
+            _lib.check(self.lib.mg_vcycle(self._level_structs, L, ctypes.byref(params), st), "mg_vcycle")
+            self.last_launches = int(self.lib.mg_last_launch_count())
+            return
+        key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip)
+        g = self._graphs.get(key)
+        if g is None:
+            cap = torch.cuda.Stream(device=self.device)
+            cap.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(cap):
+                h = cap.cuda_stream
+                _lib.check(self.lib.mg_graph_begin(h), "mg_graph_begin")
+                rc = self.lib.mg_vcycle(self._level_structs, L, ctypes.byref(params), h)
+                launches = int(self.lib.mg_last_launch_count())
+                out = ctypes.c_void_p()
+                rc2 = self.lib.mg_graph_end(h, ctypes.byref(out))
+                _lib.check(rc, "mg_vcycle (capture)")
+                _lib.check(rc2, "mg_graph_end")
+            torch.cuda.current_stream().wait_stream(cap)
+            g = (out, launches)
+            self._graphs[key] = g
+        _lib.check(self.lib.mg_graph_launch(g[0], st), "mg_graph_launch")
+        self.last_launches = g[1]
+
+    def __del__(self):
+        try:
+            for g, _ in self._graphs.values():
+                self.lib.mg_graph_destroy(g)
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------------
+    def cycle_bytes(self, nu_pre, nu_post):
+        """Algorithmic bytes of one outer iteration (residual+norm, then one V(nu_pre,nu_post) cycle), exactly
+        the formula of SURVEY.md 8(d), from the ACTUAL nnz of the built hierarchy."""
+        S = algorithmic_bytes_csr
+        lv = self.levels
+        total = S(lv[0].nnz_A, lv[0].n) + 16 * lv[0].n
+        per_level = []
+        for l in range(self.nlevels - 1):
+            n, nc = lv[l].n, lv[l + 1].n
+            a, q = lv[l].nnz_A, lv[l].nnz_Q
+            b = (nu_pre + nu_post + 1) * (S(a, n) + 24 * n)           # sweeps + in-cycle residual
+            b += S(q, nc) + 8 * n + 8 * nc                            # restriction
+            b += S(q, n) + 8 * nc + 16 * n                            # prolongation + correction
+            per_level.append(b)
+            total += b
+        coarse = lv[-1].coarse_bytes + 16 * lv[-1].n
+        total += coarse
+        return {"total": total, "outer": S(lv[0].nnz_A, lv[0].n) + 16 * lv[0].n, "levels": per_level,
+                "coarse": coarse}
+
+    def level_matrix(self, l):
+        """A_l in natural ordering as a SciPy CSR (for pattern / value parity checks)."""
+        if self.host_A is not None and self.host_A[l] is not None:
+            return self.host_A[l]
+        return SD.download_level_matrix(self, l)

@@ -1,0 +1,220 @@
+"""Host-side sparse-format plumbing (NumPy, vectorised): canonical CSR, level permutations, SELL-32 layout.
+
+These routines only rearrange integers and copy values; all floating-point work happens in the CUDA kernels.
+They are also the host cross-check of the device setup kernels (tests compare the two).
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+
+from . import _lib
+
+SLICE = 32
+
+
+def canonical_csr(A):
+    """scipy CSR with sorted, duplicate-free int32 indices and float64 data (what SciPy hands to its kernels)."""
+    if not sp.issparse(A):
+        A = sp.csr_matrix(np.asarray(A, dtype=np.float64))
+    A = sp.csr_matrix(A, dtype=np.float64)
+    A.sum_duplicates()
+    A.sort_indices()
+    if A.nnz >= 2 ** 31 or max(A.shape) >= 2 ** 31:
+        raise OverflowError("matrix does not fit the int32 index contract")
+    A.indptr = A.indptr.astype(np.int32, copy=False)
+    A.indices = A.indices.astype(np.int32, copy=False)
+    return A
+
+
+def raw_csr(indptr, indices, data, shape):
+    """CSR container that never re-sorts or merges (entries keep the given order)."""
+    M = sp.csr_matrix(shape, dtype=np.float64)
+    M.indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    M.indices = np.ascontiguousarray(indices, dtype=np.int32)
+    M.data = np.ascontiguousarray(data, dtype=np.float64)
+    return M
+
+
+def permute_csr(A, row_perm=None, col_iperm=None):
+    """rows: new row i = old row row_perm[i]; columns relabelled old j -> col_iperm[j].
+    Entries keep their ORIGINAL order inside every row (so row sums round exactly as in natural ordering)."""
+    indptr, indices, data = A.indptr, A.indices, A.data
+    if row_perm is not None:
+        lens = np.diff(indptr)[row_perm]
+        new_ptr = np.zeros(len(row_perm) + 1, dtype=np.int64)
+        np.cumsum(lens, out=new_ptr[1:])
+        # source position of every new entry
+        src = np.repeat(indptr[:-1][row_perm].astype(np.int64) - new_ptr[:-1], lens) + np.arange(new_ptr[-1])
+        indices = indices[src]
+        data = data[src]
+        indptr = new_ptr
+        nrows = len(row_perm)
+    else:
+        nrows = A.shape[0]
+    if col_iperm is not None:
+        indices = np.asarray(col_iperm, dtype=np.int32)[indices]
+    return raw_csr(indptr, indices, data, (nrows, A.shape[1]))
+
+
+def transpose_csr(Q):
+    """CSR of Q^T whose row entries are in ascending original-row order (the order SciPy's csc_matvec adds
+    them in `i.T @ res`, Multigrid.py:93)."""
+    QT = sp.csr_matrix(sp.csc_matrix(Q).T) if not sp.isspmatrix_csr(Q) else Q.T.tocsr()
+    QT.sort_indices()
+    return canonical_csr(QT)
+
+
+def csr_to_sell(A):
+    """(slice_ptr int64[nslices+1], cols int32[total], vals float64[total]) of the SELL-32 layout."""
+    n = A.shape[0]
+    indptr = A.indptr.astype(np.int64)
+    indices, data = A.indices, A.data
+    lens = np.diff(indptr)
+    nsl = (n + SLICE - 1) // SLICE
+    lens_p = np.zeros(nsl * SLICE, dtype=np.int64)
+    lens_p[:n] = lens
+    sl_len = lens_p.reshape(nsl, SLICE).max(axis=1) if nsl else np.zeros(0, dtype=np.int64)
+    slice_ptr = np.zeros(nsl + 1, dtype=np.int64)
+    np.cumsum(sl_len * SLICE, out=slice_ptr[1:])
+    total = int(slice_ptr[-1])
+    lastcol = np.zeros(nsl * SLICE, dtype=np.int32)
+    nz = lens > 0
+    lastcol[:n][nz] = indices[indptr[1:][nz] - 1]
+    cols = np.repeat(lastcol.reshape(nsl, SLICE), sl_len, axis=0).reshape(-1)
+    cols = np.ascontiguousarray(cols, dtype=np.int32)
+    vals = np.zeros(total, dtype=np.float64)
+    if len(data):
+        rows = np.repeat(np.arange(n, dtype=np.int64), lens)
+        k = np.arange(len(data), dtype=np.int64) - indptr[rows]
+        dest = slice_ptr[rows >> 5] + k * SLICE + (rows & 31)
+        cols[dest] = indices
+        vals[dest] = data
+    return slice_ptr, cols, vals
+
+
+def sell_padding_ratio(A):
+    slice_ptr, _, _ = csr_to_sell(A) if not isinstance(A, tuple) else A
+    return float(slice_ptr[-1])
+
+
+def greedy_colors(A):
+    """First-fit colouring in index order on the symmetrised pattern (C helper in libmgb200, host code)."""
+    A = canonical_csr(A)
+    n = A.shape[0]
+    colors = np.empty(n, dtype=np.int32)
+    lib = _lib.load()
+    nc = lib.mg_host_greedy_color(n, A.indptr.ctypes.data, A.indices.ctypes.data, colors.ctypes.data)
+    if nc < 0:
+        _lib.check(nc, "mg_host_greedy_color")
+    return colors, int(nc)
+
+
+def lex_levels(A):
+    """(level_ptr int64[nlev+1], level_rows int32[n]) of the index-order Gauss-Seidel dependency levels."""
+    A = canonical_csr(A)
+    n = A.shape[0]
+    level = np.empty(n, dtype=np.int32)
+    lib = _lib.load()
+    nlev = lib.mg_host_lex_levels(n, A.indptr.ctypes.data, A.indices.ctypes.data, level.ctypes.data)
+    if nlev < 0:
+        _lib.check(int(nlev), "mg_host_lex_levels")
+    order = np.argsort(level, kind="stable").astype(np.int32)
+    counts = np.bincount(level, minlength=int(nlev))
+    level_ptr = np.zeros(int(nlev) + 1, dtype=np.int64)
+    np.cumsum(counts, out=level_ptr[1:])
+    return level_ptr, order
+
+
+def color_permutation(colors):
+    """perm (new -> old) that groups rows by colour, natural order inside a colour; colour offsets."""
+    colors = np.asarray(colors)
+    ncolors = int(colors.max()) + 1 if len(colors) else 0
+    perm = np.argsort(colors, kind="stable").astype(np.int32)
+    color_ptr = np.zeros(ncolors + 1, dtype=np.int64)
+    np.cumsum(np.bincount(colors, minlength=ncolors), out=color_ptr[1:])
+    return perm, color_ptr
+
+
+def inverse_permutation(perm):
+    iperm = np.empty(len(perm), dtype=np.int32)
+    iperm[perm] = np.arange(len(perm), dtype=np.int32)
+    return iperm
+
+
+def geometric_interpolator_csr(dimension):
+    """Sparse form of the reference's dense 1D linear interpolation (Multigrid.interpolator,
+    learn_multigrid/solvers/Multigrid.py:126-147): n x (floor((n-1)/2)+1), interior columns [1/2, 1, 1/2],
+    first column [1, 1/2], last column [1/2, 1]."""
+    rows_n = int(dimension)
+    cols_n = int(np.floor((rows_n - 1) / 2)) + 1
+    r, c, v = [0, 1], [0, 0], [1.0, 0.5]
+    j = np.arange(1, cols_n - 1)
+    i0 = 1 + 2 * (j - 1)
+    r += list(np.concatenate([i0, i0 + 1, i0 + 2]))
+    c += list(np.concatenate([j, j, j]))
+    v += [0.5] * len(j) + [1.0] * len(j) + [0.5] * len(j)
+    if cols_n >= 2 or rows_n >= 2:
+        r += [rows_n - 1, rows_n - 2]
+        c += [cols_n - 1, cols_n - 1]
+        v += [1.0, 0.5]
+    M = sp.coo_matrix((np.array(v), (np.array(r), np.array(c))), shape=(rows_n, cols_n))
+    # duplicates (tiny n) follow the dense assignment semantics: last write wins, so rebuild via dense then
+    if rows_n <= 4:
+        D = np.zeros((rows_n, cols_n))
+        ii = 1
+        for jj in range(1, cols_n - 1):
+            D[ii, jj] = 1; ii += 1
+            D[ii, jj] = 2; ii += 1
+            D[ii, jj] = 1
+        D[0, 0] = 2; D[1, 0] = 1; D[-1, -1] = 2; D[-2, -1] = 1
+        return canonical_csr(sp.csr_matrix(D / 2))
+    return canonical_csr(M.tocsr())
+
+
+def build_host_hierarchy(A, Q_list, smoother, colors=None, with_sell=True):
+    """Pure NumPy/SciPy construction of every level's data in the engine's orderings (no device work).
+
+    Returns a list of dicts (one per level) with: n, nnz_A, A_nat (canonical CSR, natural ordering), perm / iperm
+    (None = natural), colors, color_ptr, and for all but the coarsest level: A (permuted CSR, entries in natural
+    order inside rows), dinv, Q, QT (permuted CSR), Q_nat, nnz_Q, and with smoother == "lexgs" lex_ptr / lex_rows.
+    With with_sell=True the SELL-32 arrays of A, Q, QT are added as (slice_ptr, cols, vals) under *_sell.
+    The Galerkin products are SciPy's `csr_matrix(Q.T @ A @ Q)` (learn_multigrid/solvers/Multigrid.py:97-98).
+    """
+    L = len(Q_list) + 1
+    A_nat = [canonical_csr(sp.csc_matrix(A))]          # Solver.py:18 stores csc_matrix(matrix)
+    Q_nat = [canonical_csr(q) for q in Q_list]
+    for l in range(L - 1):
+        if Q_nat[l].shape[0] != A_nat[l].shape[0]:
+            raise ValueError("Q_%d has %d rows, level operator has %d" % (l, Q_nat[l].shape[0], A_nat[l].shape[0]))
+        A_nat.append(canonical_csr(sp.csr_matrix(Q_nat[l].T @ A_nat[l] @ Q_nat[l])))
+    levels = []
+    for l in range(L):
+        d = {"n": A_nat[l].shape[0], "nnz_A": int(A_nat[l].nnz), "A_nat": A_nat[l]}
+        if smoother == "mcgs" and l < L - 1:
+            if colors is not None and colors[l] is not None:
+                col = np.ascontiguousarray(colors[l], dtype=np.int32)
+            else:
+                col = greedy_colors(A_nat[l])[0]
+            d["colors"] = col
+            d["perm"], d["color_ptr"] = color_permutation(col)
+            d["iperm"] = inverse_permutation(d["perm"])
+        else:
+            d["colors"] = d["perm"] = d["iperm"] = d["color_ptr"] = None
+        levels.append(d)
+    for l in range(L - 1):
+        d, dc = levels[l], levels[l + 1]
+        d["A"] = permute_csr(A_nat[l], d["perm"], d["iperm"])
+        with np.errstate(divide="ignore"):
+            dinv = 1.0 / A_nat[l].diagonal()
+        d["dinv"] = np.ascontiguousarray(dinv if d["perm"] is None else dinv[d["perm"]])
+        d["Q_nat"] = Q_nat[l]
+        d["nnz_Q"] = int(Q_nat[l].nnz)
+        d["Q"] = permute_csr(Q_nat[l], d["perm"], dc["iperm"])
+        d["QT"] = permute_csr(transpose_csr(Q_nat[l]), dc["perm"], d["iperm"])
+        if smoother == "lexgs":
+            d["lex_ptr"], d["lex_rows"] = lex_levels(A_nat[l])
+        if with_sell:
+            for k in ("A", "Q", "QT"):
+                d[k + "_sell"] = csr_to_sell(d[k])
+    return levels

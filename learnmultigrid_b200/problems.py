@@ -1,0 +1,135 @@
+"""Synthetic P1 problems of BASELINE.json's configurations, generated with vectorised NumPy (host side).
+
+The structured 2D generators write the assembled operator directly (closed form of the reference's element
+loop on the right-triangle mesh) so that 16M / 64M-DOF inputs are produced in seconds; tests check them against
+the reference's own assembly on small meshes (tests/golden/assembly_2d.npz).
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from . import formats as F
+
+
+def structured_laplacian_2d(N, coefficient=None):
+    """P1 stiffness matrix of -div(k grad u) on the reference's structured mesh Mesh2D(N*N) ((N+1)^2 nodes, row
+    major), with boundary rows replaced by identity rows exactly as test/thesis_structured_2d.py:407-414.
+    k = 1 gives the 5-point stencil [-1,-1,4,-1,-1] (hypotenuse couplings are exact zeros and not stored);
+    `coefficient(x, y)` is evaluated at element centroids.  Returns canonical CSR."""
+    W = N + 1
+    n = W * W
+    if n * 5 >= 2 ** 31:
+        raise OverflowError("nnz does not fit int32")
+    iy, ix = np.divmod(np.arange(n, dtype=np.int64), W)
+    interior = (ix > 0) & (ix < N) & (iy > 0) & (iy < N)
+    counts = np.where(interior, 5, 1).astype(np.int64)
+    indptr = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    indices = np.empty(indptr[-1], dtype=np.int32)
+    data = np.empty(indptr[-1], dtype=np.float64)
+    b = np.flatnonzero(~interior)
+    indices[indptr[b]] = b
+    data[indptr[b]] = 1.0
+    r = np.flatnonzero(interior)
+    base = indptr[r]
+    if coefficient is None:
+        vals = (-1.0, -1.0, 4.0, -1.0, -1.0)
+        for k, off in enumerate((-W, -1, 0, 1, W)):
+            indices[base + k] = r + off
+            data[base + k] = vals[k]
+    else:
+        h = 1.0 / N
+        # element coefficients: lower triangle (type 1: [k,k+1,k+W+1]) and upper (type 2: [k,k+W+1,k+W]) of square (sx,sy)
+        def k1(sx, sy):
+            return coefficient((sx + 2.0 / 3.0) * h, (sy + 1.0 / 3.0) * h)
+
+        def k2(sx, sy):
+            return coefficient((sx + 1.0 / 3.0) * h, (sy + 2.0 / 3.0) * h)
+        x, y = ix[r], iy[r]
+        # horizontal edge (x,y)-(x+1,y): shared by type-1 of square (x,y) [legs] and type-2 of square (x,y-1)
+        east = -0.5 * (k1(x, y) + k2(x, y - 1))
+        west = -0.5 * (k1(x - 1, y) + k2(x - 1, y - 1))
+        # vertical edge (x,y)-(x,y+1): type-2 of square (x,y) and type-1 of square (x-1,y)
+        north = -0.5 * (k2(x, y) + k1(x - 1, y))
+        south = -0.5 * (k2(x, y - 1) + k1(x - 1, y - 1))
+        diag = -(east + west + north + south)
+        for k, (off, v) in enumerate(((-W, south), (-1, west), (0, diag), (1, east), (W, north))):
+            indices[base + k] = r + off
+            data[base + k] = v
+    return F.raw_csr(indptr.astype(np.int32), indices, data, (n, n))
+
+
+def structured_rhs_2d(N, f_value=-1.0):
+    """load vector of f = const on the structured mesh with Dirichlet rows zeroed: interior entries f*h^2
+    (six triangles of area h^2/2, each contributing f*area/3), thesis_structured_2d.py:17-19,403,414."""
+    W = N + 1
+    h = 1.0 / N
+    rhs = np.full((W, W), f_value * h * h)
+    rhs[0, :] = rhs[-1, :] = rhs[:, 0] = rhs[:, -1] = 0.0
+    return rhs.reshape(-1, 1)
+
+
+def linear_P_2d(Nf):
+    """linear interpolation from the nested coarse mesh Mesh2D((Nf/2)^2) to Mesh2D(Nf^2): coincident nodes 1,
+    edge midpoints 1/2 + 1/2 (horizontal, vertical and the lower-left/upper-right diagonal).  CSR."""
+    if Nf % 2:
+        raise ValueError("Nf must be even")
+    Wf, Wc = Nf + 1, Nf // 2 + 1
+    iy, ix = np.divmod(np.arange(Wf * Wf, dtype=np.int64), Wf)
+    cx, cy = ix // 2, iy // 2
+    ox, oy = ix % 2, iy % 2
+    two = (ox + oy) > 0
+    counts = np.where(two, 2, 1)
+    indptr = np.zeros(Wf * Wf + 1, dtype=np.int64)
+    np.cumsum(counts, out=indptr[1:])
+    indices = np.empty(indptr[-1], dtype=np.int32)
+    data = np.empty(indptr[-1], dtype=np.float64)
+    first = cy * Wc + cx
+    second = (cy + oy) * Wc + (cx + ox)
+    indices[indptr[:-1]] = first
+    data[indptr[:-1]] = np.where(two, 0.5, 1.0)
+    t = np.flatnonzero(two)
+    indices[indptr[t] + 1] = second[t]
+    data[indptr[t] + 1] = 0.5
+    return F.raw_csr(indptr.astype(np.int32), indices, data, (Wf * Wf, Wc * Wc))
+
+
+def structured_mass_2d(N):
+    """P1 mass matrix on Mesh2D(N*N) through the vectorised assembly (7-point pattern)."""
+    from .mesh.Mesh2D import Mesh2D
+    from .assembly.MassMatrix import MassMatrix
+    from .assembly.Quadrature import Quadrature2D
+    from .assembly.ShapeFunction import FunctionTriangle
+    return MassMatrix(Mesh2D(N * N)).compute_mass_2d(FunctionTriangle(1), Quadrature2D(3), format="csr")
+
+
+def quasi_l2_Q_2d(Nf):
+    """semi-geometric quasi-L2 transfer between the nested structured meshes: Q = rownormalise(M_h P)."""
+    P = linear_P_2d(Nf)
+    B = sp.csr_matrix(structured_mass_2d(Nf) @ P)
+    s = np.asarray(B.sum(axis=1)).ravel()
+    Q = sp.csr_matrix(sp.diags(1.0 / s) @ B)
+    Q.sort_indices()
+    return Q
+
+
+def structured_hierarchy_2d(N, levels, transfer="linear"):
+    """[Q_0, ..., Q_{levels-2}] for the nested structured meshes N, N/2, ..."""
+    qs = []
+    n = N
+    for _ in range(levels - 1):
+        if n % 2 or n < 2:
+            raise ValueError("mesh cannot be coarsened %d times" % (levels - 1))
+        qs.append(linear_P_2d(n) if transfer == "linear" else quasi_l2_Q_2d(n))
+        n //= 2
+    return qs
+
+
+def redblack_colors_2d(N):
+    W = N + 1
+    iy, ix = np.divmod(np.arange(W * W), W)
+    return ((ix + iy) % 2).astype(np.int32)
+
+
+def variable_coefficient(x, y):
+    """k(x,y) = 1 + 0.9 sin(2 pi x) sin(2 pi y)  """
+    return 1.0 + 0.9 * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y)

@@ -1,0 +1,66 @@
+"""Conjugate gradients with the reference's interface (learn_multigrid/solvers/CG.py:5-50) on the GPU, plus an
+optional V-cycle preconditioner (BASELINE.json configs[4]: MG-preconditioned CG)."""
+import numpy as np
+
+from .. import _lib
+from .Solver import IterativeSolver
+
+
+class CG(IterativeSolver):
+
+    def __init__(self, matrix, rhs):
+        super().__init__(matrix, rhs)
+        self.label = "CG"
+
+    def solve(self, max_iterations=1000, error=1e-08, initial_guess=None, preconditioner=None):
+        """Textbook CG (CG.py:12-50): history starts with the initial residual, absolute tolerance.
+        The reference evaluates `alpha * A @ p` (rescales A, second SpMV, CG.py:37); here A p is reused, which
+        changes results only in the last bits.  `preconditioner(r_dev, z_dev)` applies z = M^-1 r on device
+        vectors (see solvers.Multigrid.Multigrid.as_preconditioner)."""
+        d = self._device_csr()
+        torch, lib, n = d["torch"], d["lib"], d["n"]
+        st = _lib.stream_handle(torch)
+        if initial_guess is None:
+            x0 = np.zeros(shape=(self.get_dimension(), 1))
+        else:
+            x0 = initial_guess
+        x = self._upload(x0)
+        b = self._upload(self.rhs)
+        r = torch.empty_like(x)
+        Ap = torch.empty_like(x)
+        self._residual(x, b, r)
+        self.residual = self._norm(r)
+        track = [self.residual]
+        if preconditioner is None:
+            z = r
+        else:
+            z = torch.empty_like(x)
+            preconditioner(r, z)
+        p = z.clone()
+        rz = self._dot(r, z)
+
+        def axpby(a, xx, bb, yy, out):
+            _lib.check(lib.mg_axpby(n, float(a), xx.data_ptr(), float(bb), yy.data_ptr(), out.data_ptr(), st),
+                       "mg_axpby")
+
+        for _ in range(0, max_iterations):
+            self.iterations += 1
+            _lib.check(lib.mg_spmv_csr(n, d["indptr"].data_ptr(), d["indices"].data_ptr(), d["values"].data_ptr(),
+                                       p.data_ptr(), Ap.data_ptr(), st), "mg_spmv_csr")
+            pAp = self._dot(p, Ap)
+            alpha = rz / pAp
+            axpby(alpha, p, 1.0, x, x)            # x = x + alpha p
+            axpby(-alpha, Ap, 1.0, r, r)          # r = r - alpha A p
+            self.residual = self._norm(r)
+            track.append(self.residual)
+            if self.residual <= error:
+                break
+            if preconditioner is not None:
+                preconditioner(r, z)
+            rz_new = self._dot(r, z)
+            beta = rz_new / rz
+            rz = rz_new
+            axpby(beta, p, 1.0, z, p)             # p = z + beta p
+        self.solution = x.cpu().numpy().reshape(self.dim, 1)
+        self.residual_vector = r.cpu().numpy().reshape(self.dim, 1)
+        self.track_res = np.array(track, dtype=float).reshape(-1, 1)

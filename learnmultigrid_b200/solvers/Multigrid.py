@@ -1,0 +1,243 @@
+"""Multigrid drivers with the reference's interface (learn_multigrid/solvers/Multigrid.py) on the B200 engine.
+
+    Multigrid(matrix, rhs)                    Multigrid.py:26-161
+    GeometricMG(matrix, rhs)                  Multigrid.py:164-173
+    SemiGeometricMG(matrix, rhs, l2_proj)     Multigrid.py:176-197
+
+`solve()` keeps the reference's outer loop statement by statement (Multigrid.py:36-75): residual, 2-norm,
+the first-iteration sqrt(n) quirk (:64-66), history, ABSOLUTE tolerance test, one V-cycle.  The V-cycle itself
+(:77-124) runs on the device from a hierarchy that is built ONCE (the reference rebuilds Q^T A Q and refactorises
+the coarsest operator in every cycle, :97-98,106).
+
+Differences, all explicit:
+  * `smoother` is honoured.  The committed reference ignores it and always calls PyAMG's index-order
+    Gauss-Seidel (:88,121).  Here "GaussSeidel" selects multicolour Gauss-Seidel (`gs_order="multicolor"`,
+    default) or the exact index-order sweep (`gs_order="lexicographic"`, bit-for-bit the reference's smoother);
+    "Jacobi" selects damped Jacobi with `omega` (Jacobi.py:35 is omega=1, which does not smooth; default 2/3).
+  * `l2_proj` may be a list [Q_0, Q_1, ...] giving a transfer operator for every level.  Levels without one
+    use the reference's 1D linear interpolator (Multigrid.interpolator, :126-147), as the reference does
+    below the first level (:188-197).
+  * `initial_guess` is copied to the device, not mutated in place.
+"""
+import sys
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.sparse import csr_matrix
+
+from .. import _lib
+from .. import formats as F
+from ..engine import DeviceHierarchy
+from .Solver import IterativeSolver
+from .Jacobi import Jacobi
+from .CG import CG
+from .GaussSeidel import GaussSeidel
+
+
+class Multigrid(IterativeSolver):
+
+    def __init__(self, matrix, rhs):
+        super().__init__(matrix, rhs)
+        self.label = "Multigrid"
+        self._hier = None
+        self._hier_key = None
+        self._interp_cache = {}
+        self.verbose = False
+        self.setup = "host"
+
+    # ------------------------------------------------------------------------------------------------
+    def solve(self, levels=2, smoother="Jacobi", smooth_steps=1, max_iterations=100, error=1e-08,
+              initial_guess=None, cycle="V", first_call=False, *, omega=2.0 / 3.0, gs_order="multicolor",
+              colors=None, use_graph=True):
+        if initial_guess is None:
+            self.solution = np.zeros(shape=(self.get_dimension(), 1))
+        else:
+            self.solution = initial_guess
+        cycle_method = self.cycle_to_method(cycle)
+        if not callable(cycle_method):
+            print("Cycle type unknown, exit...")
+            sys.exit(0)                                            # Multigrid.py:55-57
+        h = self._hierarchy(levels, smoother, gs_order, colors, first_call)
+        params = h.make_params(nu_pre=smooth_steps, nu_post=smooth_steps, omega=omega)
+        h.set_rhs(self.rhs)
+        if initial_guess is None:
+            h.zero_x()
+        else:
+            h.set_x(self.solution)
+        track_res = np.ndarray(shape=(0, 1), dtype=float)
+        for _ in range(0, max_iterations):
+            self.iterations += 1
+            self.residual = h.residual_norm()                      # :62-63 fused residual + norm
+            if self.iterations <= 1:                               # :64-66
+                self.residual = float(np.sqrt(float(self.get_dimension())))
+                self._residual_is_ones = True
+            else:
+                self._residual_is_ones = False
+            track_res = np.vstack((track_res, self.residual))
+            if self.verbose:
+                print("It: ", self.iterations, self.residual)
+            if self.residual <= error:
+                break
+            h.vcycle(params, use_graph=use_graph)                  # :73
+        self.solution = h.get_x()
+        self.track_res = track_res
+        self._residual_dirty = True
+
+    def get_residual_vector(self):
+        if getattr(self, "_residual_dirty", False) and self._hier is not None:
+            if getattr(self, "_residual_is_ones", False):
+                self.residual_vector = np.ones(shape=self.solution.shape)      # :65
+            else:
+                self.residual_vector = self._hier.residual_vector()
+            self._residual_dirty = False
+        return self.residual_vector
+
+    # ------------------------------------------------------------------------------------------------
+    def v_cycle(self, A, u0, rhs, smoother, smooth_steps, error, levels, first_call=False, *, omega=2.0 / 3.0,
+                gs_order="multicolor", colors=None):
+        """One V-cycle for (A, rhs) starting from u0; returns the new iterate as an (n,1) array
+        (Multigrid.py:77-124).  The hierarchy is cached as long as the same matrix object is passed."""
+        if A is self.matrix:
+            h = self._hierarchy(levels, smoother, gs_order, colors, first_call)
+        else:
+            h = self._build(A, levels, smoother, gs_order, colors, first_call)
+        params = h.make_params(nu_pre=smooth_steps, nu_post=smooth_steps, omega=omega)
+        h.set_rhs(rhs)
+        h.set_x(u0)
+        h.vcycle(params)
+        return h.get_x()
+
+    def interpolator(self, dimension, _):
+        """Dense 1D linear interpolation, same values as Multigrid.py:126-147 (memoised per dimension)."""
+        key = int(dimension)
+        if key not in self._interp_cache:
+            self._interp_cache[key] = F.geometric_interpolator_csr(key).toarray()
+        return self._interp_cache[key]
+
+    def smoother_to_method(self, smoother):
+        switcher = {
+            "GaussSeidel": GaussSeidel,
+            "Jacobi": Jacobi,
+            "CG": CG,
+        }
+        return switcher.get(smoother, "Invalid smoother")
+
+    def cycle_to_method(self, cycle):
+        switcher = {
+            "V": self.v_cycle,
+        }
+        return switcher.get(cycle, "Invalid smoother")
+
+    # ------------------------------------------------------------------------------------------------
+    def _transfer_list(self, levels, first_call):
+        """[Q_0 ... Q_{levels-2}] in CSR; geometric 1D interpolation where none is supplied."""
+        given = self._given_transfers() if first_call else []
+        qs = []
+        n = self.matrix.shape[0]
+        for l in range(levels - 1):
+            if l < len(given):
+                q = F.canonical_csr(given[l])
+            else:
+                q = F.geometric_interpolator_csr(n)
+            if q.shape[0] != n:
+                raise ValueError("transfer operator %d has %d rows but the level has %d unknowns"
+                                 % (l, q.shape[0], n))
+            qs.append(q)
+            n = q.shape[1]
+        return qs
+
+    def _given_transfers(self):
+        return []
+
+    @staticmethod
+    def _smoother_kind(smoother, gs_order):
+        if smoother == "Jacobi":
+            return "jacobi"
+        if smoother == "GaussSeidel":
+            if gs_order == "multicolor":
+                return "mcgs"
+            if gs_order == "lexicographic":
+                return "lexgs"
+            raise ValueError("gs_order must be 'multicolor' or 'lexicographic'")
+        # the reference fails with "'str' object is not callable" for an unknown name (Multigrid.py:79-80)
+        raise TypeError("'str' object is not callable (unknown smoother %r)" % (smoother,))
+
+    def _build(self, A, levels, smoother, gs_order, colors, first_call):
+        if levels < 2:
+            raise ValueError("levels must be >= 2 (the reference recurses without bound for levels=1, "
+                             "Multigrid.py:78,102)")
+        kind = self._smoother_kind(smoother, gs_order)
+        save = self.matrix
+        try:
+            self.matrix = A
+            qs = self._transfer_list(levels, first_call)
+        finally:
+            self.matrix = save
+        return DeviceHierarchy(A, qs, smoother=kind, colors=colors, setup=self.setup)
+
+    def _hierarchy(self, levels, smoother, gs_order, colors, first_call):
+        key = (levels, smoother, gs_order, bool(first_call), id(self.matrix), None if colors is None else id(colors))
+        if self._hier is None or self._hier_key != key:
+            self._hier = self._build(self.matrix, levels, smoother, gs_order, colors, first_call)
+            self._hier_key = key
+        return self._hier
+
+    def get_hierarchy(self):
+        """The device hierarchy of the last solve (level matrices, colourings, byte counts)."""
+        return self._hier
+
+    def as_preconditioner(self, levels=2, smoother="GaussSeidel", smooth_steps=1, omega=2.0 / 3.0,
+                          gs_order="multicolor", first_call=True):
+        """z = M^-1 r by one V-cycle from a zero guess, on natural-order device vectors (for solvers.CG)."""
+        h = self._hierarchy(levels, smoother, gs_order, None, first_call)
+        params = h.make_params(nu_pre=smooth_steps, nu_post=smooth_steps, omega=omega)
+        lib, torch = h.lib, h.torch
+        lev = h.levels[0]
+
+        def apply(r, z):
+            st = _lib.stream_handle(torch)
+            if lev.perm is None:
+                lev.b.copy_(r)
+            else:
+                _lib.check(lib.mg_gather(h.n, lev.perm.data_ptr(), r.data_ptr(), lev.b.data_ptr(), st), "mg_gather")
+            lev.x.zero_()
+            h.vcycle(params)
+            if lev.perm is None:
+                z.copy_(lev.x)
+            else:
+                _lib.check(lib.mg_scatter(h.n, lev.perm.data_ptr(), lev.x.data_ptr(), z.data_ptr(), st), "mg_scatter")
+        return apply
+
+
+class GeometricMG(Multigrid):
+
+    def __init__(self, matrix, rhs):
+        super().__init__(matrix, rhs)
+        self.label = "GeometricMG"
+
+    def interpolator(self, dimension, _):
+        return super().interpolator(dimension, _)
+
+
+class SemiGeometricMG(Multigrid):
+
+    def __init__(self, matrix, rhs, l2_proj):
+        super().__init__(matrix, rhs)
+        self.label = "SemiGeometricMG"
+        if isinstance(l2_proj, (list, tuple)):
+            self.l_hierarchy = [csr_matrix(q) for q in l2_proj]     # one operator per level (extension)
+        else:
+            self.l_hierarchy = [csr_matrix(l2_proj)]               # Multigrid.py:182
+        self.l2_proj = self.l_hierarchy[0]
+
+    def solve(self, levels=2, smoother="Jacobi", smooth_steps=1, max_iterations=100, error=1e-08,
+              initial_guess=None, cycle="V", first_call=True, **kw):
+        super().solve(levels, smoother, smooth_steps, max_iterations, error, initial_guess, cycle, first_call, **kw)
+
+    def interpolator(self, dimension, first_call):
+        if first_call:
+            return self.l2_proj
+        return super().interpolator(dimension, first_call)
+
+    def _given_transfers(self):
+        return self.l_hierarchy

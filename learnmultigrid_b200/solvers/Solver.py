@@ -1,0 +1,143 @@
+"""Solver base classes with the reference's interface (learn_multigrid/solvers/Solver.py:8-84).
+
+State lives on the host exactly like the reference (`solution`, `residual_vector` are (n,1) float64 arrays,
+`track_res` is (k,1)); the compute behind `solve()` runs on the GPU through libmgb200.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+from scipy.sparse import csc_matrix
+
+from .. import _lib
+from .. import formats as F
+
+
+class Solver:
+    def __init__(self, matrix, rhs):
+        # Solver.py:14-21
+        self.dim = rhs.size
+        self.residual_vector = np.empty(shape=rhs.shape)
+        self.residual = 0.0
+        self.matrix = csc_matrix(matrix)
+        self.rhs = rhs
+        self.solution = np.empty(shape=rhs.shape)
+        self.track_res = np.ndarray(shape=(0, 1), dtype=float)
+        self._dev = None
+
+    # getters / setters, Solver.py:23-48
+    def set_matrix(self, matrix):
+        self.matrix = matrix
+        self._dev = None
+
+    def get_matrix(self):
+        return self.matrix
+
+    def get_residual_vector(self):
+        return self.residual_vector
+
+    def get_residual(self):
+        return self.residual
+
+    def set_rhs(self, rhs):
+        self.rhs = rhs
+
+    def get_rhs(self):
+        return self.rhs
+
+    def get_solution(self):
+        return self.solution
+
+    def get_dimension(self):
+        return self.dim
+
+    def get_track_res(self):
+        return self.track_res
+
+    # ---- device plumbing shared by the stationary solvers and CG (natural ordering, CSR kernels) ----------
+    def _device_csr(self):
+        if self._dev is None:
+            torch = _lib.require_cuda()
+            A = F.canonical_csr(self.matrix)
+            dev = torch.device("cuda", torch.cuda.current_device())
+            d = {"torch": torch, "lib": _lib.load(), "n": A.shape[0], "host": A, "dev": dev,
+                 "indptr": torch.from_numpy(A.indptr).to(dev), "indices": torch.from_numpy(A.indices).to(dev),
+                 "values": torch.from_numpy(A.data).to(dev)}
+            d["ws"] = torch.zeros(8192, dtype=torch.float64, device=dev)
+            d["out"] = torch.zeros(1, dtype=torch.float64, device=dev)
+            self._dev = d
+        return self._dev
+
+    def _upload(self, v):
+        d = self._device_csr()
+        v = np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(-1))
+        return d["torch"].from_numpy(v).to(d["dev"])
+
+    def _norm(self, t):
+        d = self._device_csr()
+        st = _lib.stream_handle(d["torch"])
+        _lib.check(d["lib"].mg_dot(t.numel(), t.data_ptr(), t.data_ptr(), d["ws"].data_ptr(), d["out"].data_ptr(), st),
+                   "mg_dot")
+        return float(np.sqrt(d["out"].item()))
+
+    def _dot(self, a, b):
+        d = self._device_csr()
+        st = _lib.stream_handle(d["torch"])
+        _lib.check(d["lib"].mg_dot(a.numel(), a.data_ptr(), b.data_ptr(), d["ws"].data_ptr(), d["out"].data_ptr(), st),
+                   "mg_dot")
+        return float(d["out"].item())
+
+    def _residual(self, x, b, r):
+        d = self._device_csr()
+        st = _lib.stream_handle(d["torch"])
+        _lib.check(d["lib"].mg_residual_csr(d["n"], d["indptr"].data_ptr(), d["indices"].data_ptr(),
+                                            d["values"].data_ptr(), x.data_ptr(), b.data_ptr(), r.data_ptr(), st),
+                   "mg_residual_csr")
+
+
+class DirectSolver(Solver):
+    """spsolve replacement (Solver.py:51-59): dense inverse on the device (n <= 4096)."""
+
+    def __init__(self, matrix, rhs):
+        super().__init__(matrix, rhs)
+
+    def solve(self):
+        d = self._device_csr()
+        torch, lib, n = d["torch"], d["lib"], d["n"]
+        if n > 4096:
+            raise _lib.MgError("DirectSolver: dense device solve is limited to 4096 unknowns")
+        st = _lib.stream_handle(torch)
+        dense = torch.empty(n * n, dtype=torch.float64, device=d["dev"])
+        _lib.check(lib.mg_csr_to_dense(n, d["indptr"].data_ptr(), d["indices"].data_ptr(), d["values"].data_ptr(),
+                                       dense.data_ptr(), st), "mg_csr_to_dense")
+        inv = torch.empty(n * n, dtype=torch.float64, device=d["dev"])
+        work = torch.empty(int(lib.mg_dense_inverse_workspace(n)), dtype=torch.uint8, device=d["dev"])
+        _lib.check(lib.mg_dense_inverse(n, dense.data_ptr(), inv.data_ptr(), work.data_ptr(), st), "mg_dense_inverse")
+        b = self._upload(self.rhs)
+        x = torch.empty_like(b)
+        _lib.check(lib.mg_dense_gemv(n, n, inv.data_ptr(), b.data_ptr(), x.data_ptr(), st), "mg_dense_gemv")
+        r = torch.empty_like(b)
+        self._residual(x, b, r)
+        self.solution = x.cpu().numpy().reshape(self.dim, 1)
+        self.residual_vector = r.cpu().numpy().reshape(self.dim, 1)
+        self.residual = self._norm(r)
+
+
+class IterativeSolver(Solver):
+    def __init__(self, matrix, rhs):
+        super().__init__(matrix, rhs)
+        self.iterations = 0          # Solver.py:72, never reset by the reference
+        self.label = "Iterative Solver"
+
+    def plot(self, scale="linear"):
+        """Residual plot (Solver.py:75-81); needs matplotlib, which is optional here."""
+        import matplotlib.pyplot as plt
+        plt.plot(self.track_res, label=self.label)
+        plt.yscale(scale)
+        plt.legend()
+        plt.title("Residual decreasing")
+        plt.ylabel('residual')
+        plt.xlabel('iterations')
+
+    def get_iterations(self):
+        return self.iterations

@@ -1,0 +1,63 @@
+"""The C-ABI library loads and exports exactly what include/mgb200.h declares (no compute calls: no GPU here)."""
+import ctypes
+import os
+import re
+
+from learnmultigrid_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "mgb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_are_exported_and_bound():
+    names = declared_functions()
+    assert len(names) >= 30
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(lib, n), "declared in mgb200.h but not exported: " + n
+        assert n in _lib._SIGNATURES, "declared in mgb200.h but not bound in _lib.py: " + n
+    for n in _lib._SIGNATURES:
+        assert n in names, "bound in _lib.py but not declared in mgb200.h: " + n
+
+
+def test_library_loads_and_reports_version():
+    lib = _lib.load()
+    assert lib.mg_version() == 100
+    assert lib.mg_last_error() is not None
+
+
+def test_struct_layouts_match_header_sizes():
+    # mg_sell: 3 x int64 + 3 pointers; mg_cycle_params: 3 x int32 (+pad) + double + int32 (+pad)
+    assert ctypes.sizeof(_lib.mg_sell) == 48
+    assert ctypes.sizeof(_lib.mg_cycle_params) == 32
+    assert ctypes.sizeof(_lib.mg_level) % 8 == 0
+
+
+def test_host_helpers_run_without_gpu():
+    import numpy as np
+    import scipy.sparse as sp
+    from learnmultigrid_b200 import formats as F
+    A = sp.csr_matrix(sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(9, 9)))
+    colors, nc = F.greedy_colors(A)
+    assert nc == 2 and list(colors) == [0, 1] * 4 + [0]
+    lp, lr = F.lex_levels(A)
+    assert len(lp) == 10 and list(lr) == list(range(9))
+
+
+def test_no_cpu_fallback_without_cuda():
+    import pytest
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    import numpy as np
+    import scipy.sparse as sp
+    from learnmultigrid_b200.solvers.Multigrid import SemiGeometricMG
+    A = sp.csr_matrix(sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(9, 9)))
+    mg = SemiGeometricMG(A, np.ones((9, 1)), sp.csr_matrix(np.ones((9, 5))))
+    with pytest.raises(_lib.MgError):
+        mg.solve(levels=2, smoother="Jacobi")

@@ -1,0 +1,159 @@
+"""Host-side logic of the engine (no GPU): formats, orderings, colourings, and the level data handed to the
+kernels, checked by emulating the kernels in NumPy (tests/helpers.py) against the CPU oracle."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+from scipy.sparse.linalg import spsolve
+
+from learnmultigrid_b200 import formats as F
+from oracle import kernels as K
+from oracle.vcycle import OracleMultigrid, geometric_interpolator
+from helpers import (bilinear_P, coo_from, emulate_vcycle, load_golden, poisson2d, sell_rowsum)
+
+
+def test_sell_layout_roundtrip_and_padding():
+    rng = np.random.default_rng(0)
+    for shape, dens in (((100, 80), 0.1), ((33, 33), 0.3), ((1, 5), 1.0), ((64, 64), 0.02), ((70, 3), 0.5)):
+        A = F.canonical_csr(sp.random(*shape, density=dens, random_state=1, format="csr"))
+        sell = F.csr_to_sell(A)
+        slice_ptr, cols, vals = sell
+        assert slice_ptr[0] == 0 and np.all(np.diff(slice_ptr) % 32 == 0)
+        assert len(slice_ptr) == (shape[0] + 31) // 32 + 1
+        assert cols.min() >= 0 and cols.max() < shape[1]          # padding columns are valid gathers
+        x = rng.standard_normal(shape[1])
+        assert np.array_equal(sell_rowsum(sell, shape[0], x), A @ x)
+        assert np.count_nonzero(vals) == np.count_nonzero(A.data)
+
+
+def test_empty_rows_and_ragged():
+    A = sp.lil_matrix((40, 40))
+    A[0, 0] = 2.0
+    A[5, :] = 1.0                      # one very long row in the first slice
+    A[39, 38] = -1.0
+    A = F.canonical_csr(A)
+    sell = F.csr_to_sell(A)
+    x = np.arange(40, dtype=float)
+    assert np.array_equal(sell_rowsum(sell, 40, x), A @ x)
+
+
+def test_permute_keeps_row_entry_order():
+    A = poisson2d(8)
+    colors, nc = F.greedy_colors(A)
+    assert nc == 2
+    perm, cptr = F.color_permutation(colors)
+    iperm = F.inverse_permutation(perm)
+    Ap = F.permute_csr(A, perm, iperm)
+    for newr in (0, 7, 40, 80):
+        oldr = perm[newr]
+        a0, a1 = A.indptr[oldr], A.indptr[oldr + 1]
+        p0, p1 = Ap.indptr[newr], Ap.indptr[newr + 1]
+        assert np.array_equal(perm[Ap.indices[p0:p1]], A.indices[a0:a1])     # same entries, same order
+        assert np.array_equal(Ap.data[p0:p1], A.data[a0:a1])
+
+
+def test_greedy_coloring_is_valid_on_nonsymmetric_pattern():
+    A = poisson2d(12)                              # row-replaced Dirichlet rows: structurally nonsymmetric
+    colors, nc = F.greedy_colors(A)
+    assert nc == 2                                 # red-black on the 5-point grid
+    S = sp.csr_matrix(A + A.T)
+    S.setdiag(0)
+    S.eliminate_zeros()
+    r, c = S.nonzero()
+    assert np.all(colors[r] != colors[c])
+    P = bilinear_P(12)
+    Ac = F.canonical_csr(sp.csr_matrix(P.T @ A @ P))
+    colors, nc = F.greedy_colors(Ac)
+    S = sp.csr_matrix(Ac + Ac.T)
+    S.setdiag(0)
+    S.eliminate_zeros()
+    r, c = S.nonzero()
+    assert np.all(colors[r] != colors[c]) and nc <= 6
+
+
+def test_lex_levels_respect_dependencies():
+    A = poisson2d(10)
+    lp, lr = F.lex_levels(A)
+    level = np.empty(A.shape[0], dtype=np.int64)
+    for l in range(len(lp) - 1):
+        level[lr[lp[l]:lp[l + 1]]] = l
+    S = sp.csr_matrix(A + A.T)
+    r, c = S.nonzero()
+    m = c < r
+    assert np.all(level[c[m]] < level[r[m]])
+    assert len(lp) - 1 == 2 * 11 - 1 - 2 or len(lp) - 1 <= 2 * 11      # anti-diagonal wavefronts
+    # emulate the level-scheduled sweep and compare with the serial kernel, bit for bit
+    rng = np.random.default_rng(1)
+    x = rng.standard_normal(A.shape[0])
+    b = rng.standard_normal(A.shape[0])
+    xs = x.copy()
+    K.gauss_seidel(A, xs, b, iterations=2)
+    xl = x.copy()
+    for _ in range(2):
+        for l in range(len(lp) - 1):
+            K.gauss_seidel_multicolor(A, xl, b, [lr[lp[l]:lp[l + 1]]])
+    assert np.array_equal(xs, xl)
+
+
+def test_geometric_interpolator_csr_equals_reference_dense():
+    for n in (3, 4, 5, 6, 9, 17, 33, 257, 1025):
+        assert np.array_equal(F.geometric_interpolator_csr(n).toarray(), geometric_interpolator(n))
+
+
+@pytest.mark.parametrize("smoother,omega", [("jacobi", 2.0 / 3.0), ("jacobi", 1.0), ("mcgs", 1.0)])
+@pytest.mark.parametrize("nu", [1, 2, 3])
+def test_emulated_device_cycle_matches_oracle_2d(smoother, omega, nu):
+    """The level data the engine uploads (permuted SELL operators, transfers, colour blocks), driven by a
+    NumPy mirror of cycle.cu, reproduces the oracle V-cycle on a 3-level 2D hierarchy."""
+    N = 16
+    A = poisson2d(N)
+    Qs = [bilinear_P(N), bilinear_P(N // 2)]
+    rng = np.random.default_rng(7)
+    b = rng.standard_normal(A.shape[0])
+    x0 = rng.standard_normal(A.shape[0])
+    host = F.build_host_hierarchy(A, Qs, smoother)
+    colors = [d["colors"] for d in host]
+    o = OracleMultigrid(A, b.reshape(-1, 1), Qs, smoother="mcgs" if smoother == "mcgs" else "jacobi",
+                        omega=omega, colors=colors, hoist_setup=True)
+    o.build_hierarchy(3)
+    want = o.v_cycle(o.matrix, x0.reshape(-1, 1).copy(), b.reshape(-1, 1), nu, 3).ravel()
+    perm = host[0]["perm"]
+    xin = x0 if perm is None else x0[perm]
+    bin_ = b if perm is None else b[perm]
+    got = emulate_vcycle(host, smoother, nu, nu, omega, xin, bin_,
+                         coarse_solve=lambda Ac, rc: spsolve(sp.csc_matrix(Ac), rc))
+    if perm is not None:
+        out = np.empty_like(got)
+        out[perm] = got
+        got = out
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-12 * np.linalg.norm(want))
+
+
+def test_emulated_cycle_matches_oracle_1d_c1():
+    c1 = load_golden("c1_1d_1024.npz")
+    A = coo_from(c1, "A")
+    Q0 = coo_from(c1, "Q_quasi")
+    Qs = [Q0, F.geometric_interpolator_csr(513)]
+    b = c1["rhs"].ravel()
+    host = F.build_host_hierarchy(A, Qs, "jacobi")
+    o = OracleMultigrid(A, b.reshape(-1, 1), Qs, smoother="jacobi", omega=2.0 / 3.0, hoist_setup=True)
+    o.build_hierarchy(3)
+    x = np.zeros(1025)
+    xo = np.zeros((1025, 1))
+    for _ in range(3):
+        x = emulate_vcycle(host, "jacobi", 1, 1, 2.0 / 3.0, x, b,
+                           coarse_solve=lambda Ac, rc: spsolve(sp.csc_matrix(Ac), rc))
+        xo = o.v_cycle(o.matrix, xo, b.reshape(-1, 1), 1, 3)
+        np.testing.assert_allclose(x, xo.ravel(), rtol=0, atol=1e-12 * np.linalg.norm(xo))
+
+
+def test_galerkin_pattern_matches_scipy_reference_semantics():
+    """host hierarchy = csr_matrix(Q.T @ A @ Q) (Multigrid.py:97-98): exact zeros pruned, sorted CSR."""
+    A = poisson2d(8)
+    P = bilinear_P(8)
+    host = F.build_host_hierarchy(A, [P], "jacobi", with_sell=False)
+    want = sp.csr_matrix(P.T @ sp.csc_matrix(A) @ P)
+    want.sort_indices()
+    got = host[1]["A_nat"]
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.array_equal(got.data, want.data)
+    assert np.all(got.data != 0.0)
