@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- V-cycle throughput of the B200 multigrid engine (BASELINE.json metric) + roofline + CPU baseline.
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm
+    python bench.py --impl reference --steps K --warmup W    # the reference's CPU path (oracle port) on host cores
+
+A "step" is one outer iteration of Multigrid.solve (learn_multigrid/solvers/Multigrid.py:59-73): fused
+residual + 2-norm on the fine level, then one V(nu,nu) cycle over the prebuilt hierarchy.  `value` is fine-grid
+DOF per second with everything resident in HBM; `e2e` is the same metric through the reference-facing API
+(SemiGeometricMG.solve with host rhs / host solution, H2D and D2H inside the timed region, `cycles_per_solve`
+V-cycles per call).  One JSON line is printed by rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "vcycle_fine_grid_dof_per_s"
+UNIT = "DOF/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=int(os.environ.get("MGB_BENCH_N", "4096")),
+                    help="elements per side of the structured mesh ((n+1)^2 DOF)")
+    ap.add_argument("--levels", type=int, default=int(os.environ.get("MGB_BENCH_LEVELS", "6")))
+    ap.add_argument("--transfer", default=os.environ.get("MGB_BENCH_TRANSFER", "linear"), choices=["linear", "quasi"])
+    ap.add_argument("--smoother", default=os.environ.get("MGB_BENCH_SMOOTHER", "GaussSeidel"),
+                    choices=["GaussSeidel", "Jacobi"])
+    ap.add_argument("--nu", type=int, default=1)
+    ap.add_argument("--coefficient", default="constant", choices=["constant", "variable"])
+    ap.add_argument("--cycles-per-solve", type=int, default=10)
+    ap.add_argument("--cpu-n", type=int, default=1024, help="mesh size of the bounded CPU sample")
+    ap.add_argument("--setup", default=os.environ.get("MGB_BENCH_SETUP", "host"), choices=["host", "device"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a, n):
+    return "2D structured P1 %s %dx%d grid (%d DOF), %d-level V(%d,%d), %s, %s transfers" % (
+        "Laplacian" if a.coefficient == "constant" else "variable-coefficient stiffness", n + 1, n + 1,
+        (n + 1) ** 2, a.levels, a.nu, a.nu,
+        "multicolour (red-black on the fine level) Gauss-Seidel" if a.smoother == "GaussSeidel" else "damped Jacobi (omega=2/3)",
+        a.transfer)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_problem(a, n):
+    from learnmultigrid_b200 import problems as P
+    coef = P.variable_coefficient if a.coefficient == "variable" else None
+    A = P.structured_laplacian_2d(n, coef)
+    rhs = P.structured_rhs_2d(n)
+    Qs = P.structured_hierarchy_2d(n, a.levels, transfer=a.transfer)
+    return A, rhs, Qs
+
+
+# ------------------------------------------------------------------------------------------------------------
+def cpu_cycle_rate(a, n, reference_style, budget_s=25.0, max_cycles=10):
+    """DOF/s of the oracle V-cycle (SciPy SpMV / transfers, PyAMG Gauss-Seidel kernel restated in C, SciPy
+    Galerkin, SuperLU) on one host core.  reference_style=True repeats the Galerkin products and the coarse
+    factorisation in every cycle exactly as the reference does (Multigrid.py:97-98,106)."""
+    from oracle.vcycle import OracleMultigrid
+    A, rhs, Qs = build_problem(a, n)
+    sm = "gs" if a.smoother == "GaussSeidel" else "jacobi"
+    o = OracleMultigrid(A, rhs, Qs, smoother=sm, omega=2.0 / 3.0, hoist_setup=not reference_style)
+    t_setup = 0.0
+    if not reference_style:
+        t0 = time.perf_counter()
+        o.build_hierarchy(a.levels)
+        t_setup = time.perf_counter() - t0
+    x = np.zeros_like(rhs)
+    Af = o.matrix
+    times = []
+    t_begin = time.perf_counter()
+    for _ in range(max_cycles):
+        t0 = time.perf_counter()
+        r = rhs - Af.dot(x)
+        np.linalg.norm(r)
+        x = o.v_cycle(Af, x, rhs, a.nu, a.levels)
+        times.append(time.perf_counter() - t0)
+        if time.perf_counter() - t_begin > budget_s:
+            break
+    per = float(np.median(times))
+    return (n + 1) ** 2 / per, per, len(times), t_setup
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = a.cpu_n
+    times = []
+    for _ in range(a.warmup + a.steps):
+        pass
+    # each step = one reference-style V-cycle iteration on the bounded sample; warm-up steps are cheap repeats
+    from oracle.vcycle import OracleMultigrid
+    A, rhs, Qs = build_problem(a, n)
+    sm = "gs" if a.smoother == "GaussSeidel" else "jacobi"
+    o = OracleMultigrid(A, rhs, Qs, smoother=sm, omega=2.0 / 3.0, hoist_setup=False)
+    x = np.zeros_like(rhs)
+    Af = o.matrix
+    budget = 150.0
+    t_begin = time.perf_counter()
+    done = 0
+    for it in range(a.warmup + a.steps):
+        t0 = time.perf_counter()
+        r = rhs - Af.dot(x)
+        np.linalg.norm(r)
+        x = o.v_cycle(Af, x, rhs, a.nu, a.levels)
+        dt = time.perf_counter() - t0
+        if it >= a.warmup:
+            times.append(dt)
+        done += 1
+        if time.perf_counter() - t_begin > budget and len(times) >= 1:
+            break
+    per = float(np.mean(times))
+    val = (n + 1) ** 2 / per
+    sample = ("%dx%d grid (%d DOF) of the same %d-level V(%d,%d) configuration, %d timed cycles, Galerkin products "
+              "and coarse LU repeated in every cycle as the reference does") % (n + 1, n + 1, (n + 1) ** 2, a.levels,
+                                                                                   a.nu, a.nu, len(times))
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(times),
+            "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(a, a.n), "sample": sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+    import torch.distributed as dist
+    from learnmultigrid_b200 import _lib
+    from learnmultigrid_b200.solvers.Multigrid import SemiGeometricMG
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = a.n
+    ndof = (n + 1) ** 2
+    t0 = time.perf_counter()
+    A, rhs, Qs = build_problem(a, n)
+    t_gen = time.perf_counter() - t0
+    mg = SemiGeometricMG(A, rhs, Qs)
+    mg.setup = a.setup
+    t0 = time.perf_counter()
+    kw = dict(levels=a.levels, smoother=a.smoother, smooth_steps=a.nu, omega=2.0 / 3.0)
+    h = mg._hierarchy(a.levels, a.smoother, "multicolor", None, True)
+    torch.cuda.synchronize()
+    t_setup = time.perf_counter() - t0
+    params = h.make_params(nu_pre=a.nu, nu_post=a.nu, omega=2.0 / 3.0)
+    lib = h.lib
+    import ctypes
+    h.set_rhs(rhs)
+    h.zero_x()
+    lev0 = h.levels[0]
+    st = _lib.stream_handle(torch)
+
+    def step():
+        _lib.check(lib.mg_sell_residual_norm2(ctypes.byref(lev0.A.struct), lev0.x.data_ptr(), lev0.b.data_ptr(),
+                                              h._norm_ws.data_ptr(), h._norm_out.data_ptr(), st))
+        h.vcycle(params)
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    launches_per_step = 2 + h.last_launches
+    h.zero_x()                       # time from a fresh start so the iterate stays meaningful
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+        t = torch.tensor([ms_total], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / a.steps
+    res_after = h.residual_norm()
+
+    # ---- dominant kernel: one fine-level smoothing sweep (sell_kernel<GS> per colour / sell_kernel<JACOBI>) ----
+    S = lev0.nnz_A * 12 + 4 * (lev0.n + 1)
+    sweep_bytes = S + 24 * lev0.n
+    reps = 20
+    nlaunch = lev0.A.struct.nrows and (len(lev0.color_ptr) - 1 if lev0.color_ptr is not None else 1)
+
+    def sweep():
+        if lev0.color_ptr is not None:
+            for c in range(len(lev0.color_ptr) - 1):
+                _lib.check(lib.mg_sell_gs_rows(ctypes.byref(lev0.A.struct), lev0.x.data_ptr(), lev0.b.data_ptr(),
+                                               int(lev0.color_ptr[c]), int(lev0.color_ptr[c + 1]), st))
+        else:
+            _lib.check(lib.mg_sell_jacobi(ctypes.byref(lev0.A.struct), lev0.dinv.data_ptr(), lev0.x.data_ptr(),
+                                          lev0.b.data_ptr(), lev0.tmp.data_ptr(), 2.0 / 3.0, st))
+    for _ in range(3):
+        sweep()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        sweep()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_sweep = e0.elapsed_time(e1) / reps
+    clocks = sampler.stop()
+    peak, peak_src = peaks()
+    ach = sweep_bytes / (ms_sweep * 1e-3) / 1e9
+    cyc = h.cycle_bytes(a.nu, a.nu)
+    cyc_gbs = cyc["total"] / (ms_step * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "sell_kernel<GS> (fine-level colour sweep)" if lev0.color_ptr is not None
+                else "sell_kernel<JACOBI> (fine-level sweep)",
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
+                "traffic": None, "bytes_per_launch": sweep_bytes / nlaunch, "launches_per_sweep": nlaunch,
+                "ms_per_launch": ms_sweep / nlaunch,
+                "cycle": {"algorithmic_bytes": cyc["total"], "achieved": cyc_gbs, "frac": cyc_gbs / peak,
+                          "frac_of_8TBps": cyc_gbs / 8000.0, "bytes_per_dof": cyc["total"] / ndof}}
+
+    # ---- end to end through the reference-facing API (host rhs -> solve -> host solution) -----------------------
+    e2e = None
+    if not a.no_e2e and rank == 0:
+        C = a.cycles_per_solve
+        pin = torch.from_numpy(np.ascontiguousarray(rhs.reshape(-1))).pin_memory()
+        mg.rhs = pin
+        mg.pinned_io = True
+        solve_kw = dict(kw, error=0.0, max_iterations=C, gs_order="multicolor")
+        mg.solve(**solve_kw)                                     # warm-up (graph already captured)
+        reps_e = 3
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(reps_e):
+            mg.solve(**solve_kw)
+            _ = float(mg.solution[ndof // 2, 0])
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps_e
+        e2e = {"value": ndof * C / dt, "unit": UNIT, "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8 + 8 * C,
+               "cycles_per_solve": C, "ms_per_solve": dt * 1e3,
+               "api": "learnmultigrid_b200.solvers.Multigrid.SemiGeometricMG.solve (pinned host rhs, host solution)"}
+
+    cpu = None
+    if not a.no_cpu_baseline and rank == 0:
+        v, per, ncyc, tset = cpu_cycle_rate(a, a.cpu_n, reference_style=False)
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": "%dx%d grid (%d DOF) of the same %d-level V(%d,%d) configuration, %d cycles, hierarchy built "
+                         "once (setup %.1f s excluded); SciPy sparsetools + C Gauss-Seidel are single-threaded; "
+                         "host has %d cores" % (a.cpu_n + 1, a.cpu_n + 1, (a.cpu_n + 1) ** 2, a.levels, a.nu, a.nu,
+                                                ncyc, tset, os.cpu_count()),
+               "ms_per_cycle": per * 1e3}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": ndof * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+                "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a, n), "l2": "inputs_exceed_l2 (%.1f GB of operators per cycle)"
+                           % (cyc["total"] / 1e9), "setup": a.setup, "levels_rows": [l.n for l in h.levels],
+                           "levels_nnz": [l.nnz_A for l in h.levels], "colors": [None if l.color_ptr is None else
+                                                                              len(l.color_ptr) - 1 for l in h.levels],
+                           "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2),
+                           "residual_after_timed_steps": res_after, "parallelism": "replicas" if world > 1 else "single"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
+                "clocks": clocks}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -199,19 +199,30 @@ class DeviceHierarchy:
     # vectors in and out (host NumPy <-> permuted device vectors)
     def _to_level0(self, host_vec, dst):
         torch = self.torch
-        v = np.ascontiguousarray(np.asarray(host_vec, dtype=np.float64).reshape(-1))
-        if v.size != self.n:
-            raise ValueError("vector has %d entries, operator has %d rows" % (v.size, self.n))
-        self._pinned.copy_(torch.from_numpy(v))
+        if isinstance(host_vec, torch.Tensor):
+            src = host_vec.reshape(-1)
+            if src.dtype != torch.float64 or src.numel() != self.n:
+                raise ValueError("tensor input must be float64 with %d entries" % self.n)
+            if not src.is_pinned() and not src.is_cuda:
+                self._pinned.copy_(src)
+                src = self._pinned
+        else:
+            v = np.ascontiguousarray(np.asarray(host_vec, dtype=np.float64).reshape(-1))
+            if v.size != self.n:
+                raise ValueError("vector has %d entries, operator has %d rows" % (v.size, self.n))
+            self._pinned.copy_(torch.from_numpy(v))
+            src = self._pinned
         lev = self.levels[0]
         if lev.perm is None:
-            dst.copy_(self._pinned, non_blocking=True)
+            dst.copy_(src, non_blocking=True)
         else:
-            self._stage.copy_(self._pinned, non_blocking=True)
+            self._stage.copy_(src, non_blocking=True)
             _lib.check(self.lib.mg_gather(self.n, lev.perm.data_ptr(), self._stage.data_ptr(), dst.data_ptr(),
                                           _lib.stream_handle(torch)), "mg_gather")
 
-    def _from_level0(self, src):
+    def _from_level0(self, src, view=False):
+        """device level-0 vector -> host (n,1) array in natural ordering.  view=True returns a view of the
+        engine's pinned buffer (valid until the next transfer) instead of a fresh copy."""
         torch = self.torch
         lev = self.levels[0]
         if lev.perm is None:
@@ -221,7 +232,8 @@ class DeviceHierarchy:
                                            _lib.stream_handle(torch)), "mg_scatter")
             self._pinned.copy_(self._stage, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return self._pinned.numpy().copy().reshape(-1, 1)
+        out = self._pinned.numpy()
+        return out.reshape(-1, 1) if view else out.copy().reshape(-1, 1)
 
     def set_rhs(self, b):
         self._to_level0(b, self.levels[0].b)
@@ -232,8 +244,8 @@ class DeviceHierarchy:
     def zero_x(self):
         self.levels[0].x.zero_()
 
-    def get_x(self):
-        return self._from_level0(self.levels[0].x)
+    def get_x(self, view=False):
+        return self._from_level0(self.levels[0].x, view)
 
     # ------------------------------------------------------------------------------------------------
     def residual_norm(self):

@@ -79,7 +79,7 @@ class Multigrid(IterativeSolver):
             if self.residual <= error:
                 break
             h.vcycle(params, use_graph=use_graph)                  # :73
-        self.solution = h.get_x()
+        self.solution = h.get_x(view=getattr(self, "pinned_io", False))
         self.track_res = track_res
         self._residual_dirty = True
 
