@@ -44,7 +44,7 @@ def parse_args():
     ap.add_argument("--coefficient", default="constant", choices=["constant", "variable"])
     ap.add_argument("--cycles-per-solve", type=int, default=10)
     ap.add_argument("--cpu-n", type=int, default=1024, help="mesh size of the bounded CPU sample")
-    ap.add_argument("--setup", default=os.environ.get("MGB_BENCH_SETUP", "host"), choices=["host", "device"])
+    ap.add_argument("--setup", default=os.environ.get("MGB_BENCH_SETUP", "device"), choices=["host", "device"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()

@@ -124,9 +124,82 @@ int mg_dense_inverse(int64_t n, double *d_a, double *d_ainv, void *d_work, void 
 int64_t mg_dense_inverse_workspace(int64_t n);
 /* y = M x for a dense row-major n x m matrix (the coarse solve u = A^-1 r) */
 int mg_dense_gemv(int64_t n, int64_t m, const double *d_m, const double *d_x, double *d_y, void *stream);
+/* Banded coarsest operators too large for an explicit inverse: block cyclic reduction with dense m x m blocks
+ * (m >= half bandwidth).  The host side forms all factors once with the three setup entry points below and
+ * fills an mg_bcr; mg_bcr_solve (also reached from mg_vcycle through mg_level.coarse_bcr) then performs
+ * x = A^-1 rhs in 2*nlevels+3 launches that stream the factors once.  Level s has na[s] active blocks;
+ * block position p of level s is original block p << s; odd positions are eliminated. */
+typedef struct {
+    int64_t n, n_pad, m, nb;      /* unknowns, padded unknowns (nb*m), block size, number of blocks          */
+    int32_t nlevels, pad_;
+    const double *d_GL[32], *d_GU[32];   /* per level: [ceil(na/2)][m][m]  f_p -= GL f_{p-1} + GU f_{p+1}     */
+    const double *d_Dinv[32], *d_HL[32], *d_HU[32]; /* per level: [na/2][m][m]  x_p = Dinv f_p - HL x_{p-1} - HU x_{p+1} */
+    int64_t na[32];
+    const double *d_last_inv;     /* inverse of the single remaining block                                     */
+    double *d_f, *d_x;            /* work vectors, n_pad doubles each                                          */
+} mg_bcr;
+int mg_bcr_blocks_from_csr(int64_t n, int64_t n_pad, int64_t m, const int32_t *d_indptr, const int32_t *d_indices,
+                           const double *d_values, double *d_D, double *d_L, double *d_U, int32_t *d_bad,
+                           void *stream);
+/* batch of dense inverses, one CTA per matrix (Gauss-Jordan, partial pivoting); d_work: batch*m*2m doubles */
+int mg_dense_inverse_batched(int64_t m, int64_t batch, const double *d_a, int64_t stride_a, double *d_out,
+                             int64_t stride_out, double *d_work, int32_t *d_singular, void *stream);
+/* C[b] = alpha*A[b]*B[b] + beta*C[b], m x m row-major, strides in elements */
+int mg_dense_gemm_batched(int64_t m, int64_t batch, const double *d_a, int64_t stride_a, const double *d_b,
+                          int64_t stride_b, double *d_c, int64_t stride_c, double alpha, double beta, void *stream);
+int mg_bcr_solve(const mg_bcr *bcr, const double *d_rhs, double *d_x, void *stream);
 /* scatter a CSR matrix into a zeroed dense row-major n x n buffer */
 int mg_csr_to_dense(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
                     double *d_dense, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ */
+/* hierarchy setup on the device.  Galerkin coarse operators A_c = Q^T A Q replace `csr_matrix(i.T @ A @ i)`
+ * (SciPy csr_matmat_maxnnz + csr_matmat twice + tocsr, Multigrid.py:97-98, repeated by the reference in every
+ * cycle).  The two-pass SpGEMM accumulates every output entry in SciPy's order without FMA and drops exact
+ * zeros, so values and sparsity patterns are bit-identical to SciPy's:  T = A^T Q,  C = Q^T T,  A_c = C^T. */
+int64_t mg_scan_workspace_size(int64_t n);
+/* d_out[0] = 0, d_out[i+1] = d_in[0..i] summed (int32 row pointer); *d_total (device int64) = total.
+ * Synchronises; MG_ERR_OVERFLOW if the total does not fit int32. */
+int mg_exclusive_scan_i32(int64_t n, const int32_t *d_in, int32_t *d_out, int64_t *d_total, void *d_temp,
+                          int64_t temp_bytes, void *stream);
+/* symbolic pass: d_row_count[i] = distinct columns of row i of A*B; group in {4,8,16,32} lanes per row;
+ * per-row hash table of 2^log2_table slots in shared memory; *d_overflow = 1 if a table filled up. */
+int mg_spgemm_symbolic(int64_t nrows, const int32_t *d_a_indptr, const int32_t *d_a_indices,
+                       const int32_t *d_b_indptr, const int32_t *d_b_indices, int group, int log2_table,
+                       int32_t *d_row_count, int32_t *d_overflow, void *stream);
+/* numeric pass: sorted columns + values into [d_c_indptr[i], d_c_indptr[i+1]); d_row_nonzeros[i] = entries != 0 */
+int mg_spgemm_numeric(int64_t nrows, const int32_t *d_a_indptr, const int32_t *d_a_indices, const double *d_a_values,
+                      const int32_t *d_b_indptr, const int32_t *d_b_indices, const double *d_b_values, int group,
+                      int log2_table, const int32_t *d_c_indptr, int32_t *d_c_indices, double *d_c_values,
+                      int32_t *d_row_nonzeros, int32_t *d_overflow, void *stream);
+/* prune exact zeros, keeping entry order (what SciPy's numeric pass does) */
+int mg_csr_compact_nonzeros(int64_t nrows, const int32_t *d_in_indptr, const int32_t *d_in_indices,
+                            const double *d_in_values, const int32_t *d_out_indptr, int32_t *d_out_indices,
+                            double *d_out_values, void *stream);
+int64_t mg_sort_workspace_size(int64_t n);
+/* stable argsort of int32 keys (LSD radix sort on key_bits bits): d_perm_out[i] = position of the i-th key */
+int mg_stable_argsort_i32(int64_t n, const int32_t *d_keys, int32_t *d_keys_sorted, int32_t *d_perm_out,
+                          int32_t *d_iota_tmp, int key_bits, void *d_temp, int64_t temp_bytes, void *stream);
+int64_t mg_csr_transpose_workspace(int64_t nnz);
+/* CSR of A^T with row entries in ascending original-row order (the order SciPy's csc kernels add them in,
+ * Multigrid.py:93 `i.T @ res`) */
+int mg_csr_transpose(int64_t nrows, int64_t ncols, int64_t nnz, const int32_t *d_indptr, const int32_t *d_indices,
+                     const double *d_values, int32_t *d_t_indptr, int32_t *d_t_indices, double *d_t_values,
+                     void *d_work, void *stream);
+int mg_invert_permutation(int64_t n, const int32_t *d_perm, int32_t *d_iperm, void *stream);
+int mg_csr_row_lengths(int64_t n, const int32_t *d_indptr, const int32_t *d_perm, int32_t *d_lens, void *stream);
+/* new row i = old row perm[i] (NULL = identity), column j -> col_iperm[j] (NULL = identity), entry order kept */
+int mg_csr_permute(int64_t n, const int32_t *d_in_indptr, const int32_t *d_in_indices, const double *d_in_values,
+                   const int32_t *d_perm, const int32_t *d_col_iperm, const int32_t *d_out_indptr,
+                   int32_t *d_out_indices, double *d_out_values, void *stream);
+/* SELL-32 build: layout (slice pointers, padded size returned on the host; synchronises) then fill */
+int mg_sell_layout(int64_t n, const int32_t *d_indptr, int32_t *d_slice_len_tmp, int64_t *d_slice_ptr,
+                   int64_t *h_total_out, void *d_temp, int64_t temp_bytes, void *stream);
+int mg_sell_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                 const int64_t *d_slice_ptr, int32_t *d_cols, double *d_vals, void *stream);
+/* d_dinv[i] = 1 / A[perm[i], perm[i]] (Jacobi.py:22-23 inverts the diagonal) */
+int mg_extract_dinv(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                    const int32_t *d_perm, double *d_dinv, void *stream);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* host-side (serial, HOST pointers) setup helpers                                                    */

@@ -31,6 +31,13 @@ class mg_sell(ctypes.Structure):
                 ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp)]
 
 
+class mg_bcr(ctypes.Structure):
+    _fields_ = [("n", c_i64), ("n_pad", c_i64), ("m", c_i64), ("nb", c_i64),
+                ("nlevels", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                ("d_GL", c_vp * 32), ("d_GU", c_vp * 32), ("d_Dinv", c_vp * 32), ("d_HL", c_vp * 32),
+                ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp)]
+
+
 class mg_level(ctypes.Structure):
     _fields_ = [("n", c_i64), ("A", mg_sell), ("d_dinv", c_vp),
                 ("ncolors", ctypes.c_int32), ("h_color_ptr", ctypes.POINTER(c_i64)),
@@ -74,7 +81,27 @@ _SIGNATURES = {
     "mg_dense_inverse": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mg_dense_inverse_workspace": (c_i64, [c_i64]),
     "mg_dense_gemv": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mg_bcr_blocks_from_csr": (c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_dense_inverse_batched": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
+    "mg_dense_gemm_batched": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp]),
+    "mg_bcr_solve": (c_int, [ctypes.POINTER(mg_bcr), c_vp, c_vp, c_vp]),
     "mg_csr_to_dense": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_scan_workspace_size": (c_i64, [c_i64]),
+    "mg_exclusive_scan_i32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "mg_spgemm_symbolic": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp]),
+    "mg_spgemm_numeric": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_vp, c_vp, c_vp, c_vp,
+                                  c_vp, c_vp]),
+    "mg_csr_compact_nonzeros": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_sort_workspace_size": (c_i64, [c_i64]),
+    "mg_stable_argsort_i32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_int, c_vp, c_i64, c_vp]),
+    "mg_csr_transpose_workspace": (c_i64, [c_i64]),
+    "mg_csr_transpose": (c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_invert_permutation": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "mg_csr_row_lengths": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mg_csr_permute": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_sell_layout": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), c_vp, c_i64, c_vp]),
+    "mg_sell_fill": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_extract_dinv": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_host_greedy_color": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
     "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),

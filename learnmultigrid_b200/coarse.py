@@ -1,0 +1,139 @@
+"""Coarsest-level direct solvers (replace the per-cycle SuperLU spsolve of Multigrid.py:106).
+
+  * dense : explicit inverse by cooperative Gauss-Jordan (csrc/dense_kernels.cu), solve = one GEMV;
+  * bcr   : block cyclic reduction for banded operators (csrc/bcr.cu); all dense factors formed once here with
+            the batched inverse / GEMM entry points, solve = 2*levels+3 launches streaming the factors once.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+
+def half_bandwidth(indptr, indices):
+    n = len(indptr) - 1
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    return int(np.abs(indices.astype(np.int64) - rows).max()) if len(indices) else 0
+
+
+class DenseCoarse:
+    kind = _lib.MG_COARSE_DENSE
+
+    def __init__(self, torch, dev, n, ip, ix, va):
+        lib = _lib.load()
+        st = _lib.stream_handle(torch)
+        dense = torch.empty(n * n, dtype=torch.float64, device=dev)
+        _lib.check(lib.mg_csr_to_dense(n, ip.data_ptr(), ix.data_ptr(), va.data_ptr(), dense.data_ptr(), st),
+                   "mg_csr_to_dense")
+        self.inv = torch.empty(n * n, dtype=torch.float64, device=dev)
+        work = torch.empty(int(lib.mg_dense_inverse_workspace(n)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.mg_dense_inverse(n, dense.data_ptr(), self.inv.data_ptr(), work.data_ptr(), st),
+                   "mg_dense_inverse")
+        self.n = n
+        self.bytes = n * n * 8
+        self.launches = 1
+
+
+class BcrCoarse:
+    kind = _lib.MG_COARSE_BCR
+
+    def __init__(self, torch, dev, n, ip, ix, va, half_bw, min_block=64):
+        lib = _lib.load()
+        st = _lib.stream_handle(torch)
+        f64 = torch.float64
+        m = max(int(half_bw), min_block, 1)
+        nb = (n + m - 1) // m
+        n_pad = nb * m
+        mm = m * m
+        self.n, self.m, self.nb = n, m, nb
+
+        def zeros(k):
+            return torch.zeros(max(k, 1) * mm, dtype=f64, device=dev)
+
+        D, L, U = zeros(nb), zeros(nb), zeros(nb)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        _lib.check(lib.mg_bcr_blocks_from_csr(n, n_pad, m, ip.data_ptr(), ix.data_ptr(), va.data_ptr(), D.data_ptr(),
+                                              L.data_ptr(), U.data_ptr(), bad.data_ptr(), st), "mg_bcr_blocks_from_csr")
+        if int(bad.item()):
+            raise _lib.MgError("BCR: matrix entries outside the block-tridiagonal band (half bandwidth > block size)")
+        sing = torch.zeros(1, dtype=torch.int32, device=dev)
+        work = torch.empty(max(nb // 2, 1) * m * 2 * m, dtype=f64, device=dev)
+        e = 8                       # bytes per double, for pointer arithmetic on data_ptr()
+
+        def inverse(src_ptr, stride, batch):
+            out = zeros(batch)
+            _lib.check(lib.mg_dense_inverse_batched(m, batch, src_ptr, stride, out.data_ptr(), mm, work.data_ptr(),
+                                                    sing.data_ptr(), st), "mg_dense_inverse_batched")
+            return out
+
+        def gemm(batch, a_ptr, sa, b_ptr, sb, c_ptr, sc, alpha, beta):
+            # grid.z is limited to 65535 batch members per launch
+            done = 0
+            while done < batch:
+                nb_ = min(batch - done, 65535)
+                _lib.check(lib.mg_dense_gemm_batched(m, nb_, a_ptr + done * sa * e, sa, b_ptr + done * sb * e, sb,
+                                                     c_ptr + done * sc * e, sc, float(alpha), float(beta), st),
+                           "mg_dense_gemm_batched")
+                done += nb_
+
+        self.levels = []
+        self.keep = []
+        na = nb
+        while na > 1:
+            nodd, nk = na // 2, (na + 1) // 2
+            Dinv = inverse(D.data_ptr() + mm * e, 2 * mm, nodd)
+            HL, HU = zeros(nodd), zeros(nodd)
+            gemm(nodd, Dinv.data_ptr(), mm, L.data_ptr() + mm * e, 2 * mm, HL.data_ptr(), mm, 1.0, 0.0)
+            gemm(nodd, Dinv.data_ptr(), mm, U.data_ptr() + mm * e, 2 * mm, HU.data_ptr(), mm, 1.0, 0.0)
+            GL, GU = zeros(nk), zeros(nk)
+            # GL[j] = L[2j] Dinv[j-1]  (j >= 1);  GU[j] = U[2j] Dinv[j]  (j < nodd)
+            gemm(nk - 1, L.data_ptr() + 2 * mm * e, 2 * mm, Dinv.data_ptr(), mm, GL.data_ptr() + mm * e, mm, 1.0, 0.0)
+            gemm(nodd, U.data_ptr(), 2 * mm, Dinv.data_ptr(), mm, GU.data_ptr(), mm, 1.0, 0.0)
+            # reduced system on the even positions
+            Dn = D.view(na, mm)[0::2].contiguous().view(-1)
+            Ln, Un = zeros(nk), zeros(nk)
+            gemm(nk - 1, GL.data_ptr() + mm * e, mm, U.data_ptr() + mm * e, 2 * mm, Dn.data_ptr() + mm * e, mm, -1.0, 1.0)
+            gemm(nodd, GU.data_ptr(), mm, L.data_ptr() + mm * e, 2 * mm, Dn.data_ptr(), mm, -1.0, 1.0)
+            gemm(nk - 1, GL.data_ptr() + mm * e, mm, L.data_ptr() + mm * e, 2 * mm, Ln.data_ptr() + mm * e, mm, -1.0, 0.0)
+            gemm(nodd, GU.data_ptr(), mm, U.data_ptr() + mm * e, 2 * mm, Un.data_ptr(), mm, -1.0, 0.0)
+            self.levels.append({"na": na, "GL": GL, "GU": GU, "Dinv": Dinv, "HL": HL, "HU": HU})
+            D, L, U = Dn, Ln, Un
+            na = nk
+        self.last_inv = inverse(D.data_ptr(), mm, 1)
+        torch.cuda.synchronize()
+        if int(sing.item()):
+            raise _lib.MgError("BCR: singular diagonal block in the coarsest operator")
+        self.f = torch.zeros(n_pad, dtype=f64, device=dev)
+        self.x = torch.zeros(n_pad, dtype=f64, device=dev)
+        h = _lib.mg_bcr()
+        h.n, h.n_pad, h.m, h.nb = n, n_pad, m, nb
+        h.nlevels = len(self.levels)
+        if h.nlevels > 32:
+            raise _lib.MgError("BCR: too many reduction levels")
+        for s, lv in enumerate(self.levels):
+            h.d_GL[s], h.d_GU[s] = lv["GL"].data_ptr(), lv["GU"].data_ptr()
+            h.d_Dinv[s], h.d_HL[s], h.d_HU[s] = lv["Dinv"].data_ptr(), lv["HL"].data_ptr(), lv["HU"].data_ptr()
+            h.na[s] = lv["na"]
+        h.d_last_inv = self.last_inv.data_ptr()
+        h.d_f, h.d_x = self.f.data_ptr(), self.x.data_ptr()
+        self.handle = h
+        self.bytes = sum((2 * ((lv["na"] + 1) // 2) + 3 * (lv["na"] // 2)) * mm * 8 for lv in self.levels) + mm * 8
+        self.launches = 2 * len(self.levels) + 3
+
+    def solve(self, torch, rhs, out):
+        _lib.check(_lib.load().mg_bcr_solve(ctypes.byref(self.handle), rhs.data_ptr(), out.data_ptr(),
+                                            _lib.stream_handle(torch)), "mg_bcr_solve")
+
+
+def build_coarse_solver(torch, dev, n, ip, ix, va, dense_max, host_pattern=None):
+    """pick dense inverse or BCR for the coarsest operator given as device CSR (ip, ix, va)"""
+    if n <= dense_max:
+        return DenseCoarse(torch, dev, n, ip, ix, va)
+    if host_pattern is None:
+        host_pattern = (ip.cpu().numpy(), ix.cpu().numpy())
+    bw = half_bandwidth(*host_pattern)
+    if (n + max(bw, 64) - 1) // max(bw, 64) < 4:
+        raise _lib.MgError("coarsest operator (%d unknowns, half bandwidth %d) is neither small enough for a dense "
+                           "inverse nor banded enough for block cyclic reduction; use more levels" % (n, bw))
+    return BcrCoarse(torch, dev, n, ip, ix, va, bw)

@@ -19,6 +19,7 @@ import scipy.sparse as sp
 from . import _lib
 from . import formats as F
 from . import setup_device as SD
+from .coarse import build_coarse_solver
 
 DENSE_COARSE_MAX = 4096
 
@@ -71,7 +72,7 @@ class DeviceHierarchy:
     setup    : "device" (SpGEMM / transposes / SELL build by CUDA kernels) or "host" (NumPy/SciPy cross-check)
     """
 
-    def __init__(self, A, Q_list, smoother="jacobi", colors=None, device=None, setup="host",
+    def __init__(self, A, Q_list, smoother="jacobi", colors=None, device=None, setup="device",
                  dense_coarse_max=DENSE_COARSE_MAX, keep_host=True):
         torch = _lib.require_cuda()
         self.torch = torch
@@ -128,29 +129,25 @@ class DeviceHierarchy:
             self.levels.append(lev)
 
     def _setup_coarsest(self, lev, A_csr, dense_coarse_max):
-        """Coarsest level: explicit dense inverse (replaces the per-cycle spsolve of Multigrid.py:106)."""
+        """Coarsest level from a host CSR: upload, then dense inverse or block cyclic reduction (coarse.py)."""
         torch, dev = self.torch, self.device
-        n = A_csr.shape[0]
-        if n > dense_coarse_max:
-            raise _lib.MgError("coarsest level has %d unknowns (> %d): banded BCR solver required" % (n, dense_coarse_max))
         ip = torch.from_numpy(A_csr.indptr).to(dev)
         ix = torch.from_numpy(A_csr.indices).to(dev)
         va = torch.from_numpy(A_csr.data).to(dev)
-        self._dense_coarse_from_device_csr(lev, n, ip, ix, va)
+        self._coarsest(lev, A_csr.shape[0], ip, ix, va, dense_coarse_max, (A_csr.indptr, A_csr.indices))
 
-    def _dense_coarse_from_device_csr(self, lev, n, ip, ix, va):
-        torch, dev = self.torch, self.device
-        st = _lib.stream_handle(torch)
-        dense = torch.empty(n * n, dtype=torch.float64, device=dev)
-        _lib.check(self.lib.mg_csr_to_dense(n, ip.data_ptr(), ix.data_ptr(), va.data_ptr(), dense.data_ptr(), st),
-                   "mg_csr_to_dense")
-        inv = torch.empty(n * n, dtype=torch.float64, device=dev)
-        work = torch.empty(int(self.lib.mg_dense_inverse_workspace(n)), dtype=torch.uint8, device=dev)
-        _lib.check(self.lib.mg_dense_inverse(n, dense.data_ptr(), inv.data_ptr(), work.data_ptr(), st),
-                   "mg_dense_inverse")
-        lev.coarse_kind = _lib.MG_COARSE_DENSE
-        lev.coarse_inv = inv
-        lev.coarse_bytes = n * n * 8
+    def _coarsest_from_device_csr(self, lev, A_dev, dense_coarse_max):
+        self._coarsest(lev, A_dev.shape[0], A_dev.indptr, A_dev.indices, A_dev.values, dense_coarse_max, None)
+
+    def _coarsest(self, lev, n, ip, ix, va, dense_coarse_max, host_pattern):
+        solver = build_coarse_solver(self.torch, self.device, n, ip, ix, va, dense_coarse_max, host_pattern)
+        lev.coarse = solver
+        lev.coarse_kind = solver.kind
+        lev.coarse_bytes = solver.bytes
+        if solver.kind == _lib.MG_COARSE_DENSE:
+            lev.coarse_inv = solver.inv
+        else:
+            lev.coarse_bcr = ctypes.cast(ctypes.pointer(solver.handle), ctypes.c_void_p)
 
     # ------------------------------------------------------------------------------------------------
     def _finish_structs(self):

@@ -1,11 +1,287 @@
-"""Device-side hierarchy setup (SpGEMM Galerkin products, transposes, colour permutation, SELL build).
-Filled in by the setup kernels of csrc/setup_kernels.cu."""
+"""Device-side hierarchy setup: Galerkin products by two-pass SpGEMM, transposes, colour-blocked permutation and
+SELL-32 build, all through the setup entry points of libmgb200 (csrc/setup_kernels.cu).  PyTorch only provides
+the device buffers.  The host path (formats.build_host_hierarchy) produces the same data with SciPy/NumPy and is
+what the GPU tests compare this against.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+
 from . import _lib
+from . import formats as F
+
+
+class DevCSR:
+    """CSR matrix in device memory (int32 indptr / indices, float64 values)."""
+
+    def __init__(self, shape, indptr, indices, values):
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.indptr, self.indices, self.values = indptr, indices, values
+        self.nnz = int(indices.numel())
+
+    def ptrs(self):
+        return self.indptr.data_ptr(), self.indices.data_ptr(), self.values.data_ptr()
+
+
+class DeviceSetup:
+    def __init__(self, torch, device):
+        self.torch = torch
+        self.dev = device
+        self.lib = _lib.load()
+        self._temp = None
+        self._total = torch.zeros(1, dtype=torch.int64, device=device)
+        self._flag = torch.zeros(1, dtype=torch.int32, device=device)
+
+    # ---- helpers ----------------------------------------------------------------------------------------
+    def st(self):
+        return _lib.stream_handle(self.torch)
+
+    def empty(self, n, dtype):
+        return self.torch.empty(max(int(n), 0), dtype=dtype, device=self.dev)
+
+    def temp(self, nbytes):
+        if self._temp is None or self._temp.numel() < nbytes:
+            self._temp = None
+            self._temp = self.torch.empty(int(nbytes), dtype=self.torch.uint8, device=self.dev)
+        return self._temp
+
+    def upload(self, A):
+        A = F.canonical_csr(A)
+        t = self.torch
+        return DevCSR(A.shape, t.from_numpy(A.indptr).to(self.dev), t.from_numpy(A.indices).to(self.dev),
+                      t.from_numpy(A.data).to(self.dev))
+
+    def download(self, A):
+        M = F.raw_csr(A.indptr.cpu().numpy(), A.indices.cpu().numpy(), A.values.cpu().numpy(), A.shape)
+        return M
+
+    def scan(self, counts, n):
+        """int32 row pointer (n+1) from int32 counts; returns (indptr tensor, total)"""
+        t = self.torch
+        out = self.empty(n + 1, t.int32)
+        nb = int(self.lib.mg_scan_workspace_size(max(n, 1)))
+        tmp = self.temp(nb)
+        _lib.check(self.lib.mg_exclusive_scan_i32(n, counts.data_ptr(), out.data_ptr(), self._total.data_ptr(),
+                                                  tmp.data_ptr(), nb, self.st()), "mg_exclusive_scan_i32")
+        return out, int(self._total.item())
+
+    # ---- kernels -------------------------------------------------------------------------------------------
+    def transpose(self, A):
+        t = self.torch
+        nr, nc = A.shape
+        ip = self.empty(nc + 1, t.int32)
+        ix = self.empty(A.nnz, t.int32)
+        va = self.empty(A.nnz, t.float64)
+        work = self.temp(int(self.lib.mg_csr_transpose_workspace(max(A.nnz, 1))))
+        _lib.check(self.lib.mg_csr_transpose(nr, nc, A.nnz, *A.ptrs(), ip.data_ptr(), ix.data_ptr(), va.data_ptr(),
+                                             work.data_ptr(), self.st()), "mg_csr_transpose")
+        return DevCSR((nc, nr), ip, ix, va)
+
+    @staticmethod
+    def _group_for(avg_b_row, log_t, numeric):
+        g = 4 if avg_b_row <= 4 else 8 if avg_b_row <= 12 else 16 if avg_b_row <= 24 else 32
+        while g < 32 and (256 // g) * (1 << log_t) * (12 if numeric else 4) > 200 * 1024:
+            g *= 2
+        if (256 // g) * (1 << log_t) * (12 if numeric else 4) > 200 * 1024:
+            raise _lib.MgError("SpGEMM row too long for the shared-memory hash table (2^%d slots)" % log_t)
+        return g
+
+    def spgemm(self, A, B):
+        """C = A @ B: sorted columns, values accumulated in SciPy's csr_matmat order, exact zeros pruned."""
+        t = self.torch
+        if A.shape[1] != B.shape[0]:
+            raise ValueError("dimension mismatch")
+        n = A.shape[0]
+        avg = B.nnz / max(B.shape[0], 1)
+        counts = self.empty(n, t.int32)
+        log_t = 7
+        while True:
+            g = self._group_for(avg, log_t, False)
+            self._flag.zero_()
+            _lib.check(self.lib.mg_spgemm_symbolic(n, A.indptr.data_ptr(), A.indices.data_ptr(), B.indptr.data_ptr(),
+                                                   B.indices.data_ptr(), g, log_t, counts.data_ptr(),
+                                                   self._flag.data_ptr(), self.st()), "mg_spgemm_symbolic")
+            if int(self._flag.item()) == 0:
+                break
+            log_t += 1
+            if log_t > 14:
+                raise _lib.MgError("SpGEMM symbolic pass: row exceeds 2^14 distinct columns")
+        max_row = int(counts.max().item()) if n else 0
+        cptr, total = self.scan(counts, n)
+        cidx = self.empty(total, t.int32)
+        cval = self.empty(total, t.float64)
+        log_n = max(4, int(np.ceil(np.log2(max(2 * max_row, 2)))))
+        g = self._group_for(avg, log_n, True)
+        nzc = self.empty(n, t.int32)
+        self._flag.zero_()
+        _lib.check(self.lib.mg_spgemm_numeric(n, *A.ptrs(), *B.ptrs(), g, log_n, cptr.data_ptr(), cidx.data_ptr(),
+                                              cval.data_ptr(), nzc.data_ptr(), self._flag.data_ptr(), self.st()),
+                   "mg_spgemm_numeric")
+        if int(self._flag.item()) != 0:
+            raise _lib.MgError("SpGEMM numeric pass overflowed its hash table")
+        optr, ototal = self.scan(nzc, n)
+        if ototal == total:
+            return DevCSR((n, B.shape[1]), cptr, cidx, cval)
+        oidx = self.empty(ototal, t.int32)
+        oval = self.empty(ototal, t.float64)
+        _lib.check(self.lib.mg_csr_compact_nonzeros(n, cptr.data_ptr(), cidx.data_ptr(), cval.data_ptr(),
+                                                    optr.data_ptr(), oidx.data_ptr(), oval.data_ptr(), self.st()),
+                   "mg_csr_compact_nonzeros")
+        return DevCSR((n, B.shape[1]), optr, oidx, oval)
+
+    def galerkin(self, A, Q, QT):
+        """A_c = Q^T A Q exactly as SciPy evaluates csr_matrix(i.T @ A @ i) (Multigrid.py:97-98):
+        T = A^T Q, C = Q^T T, A_c = C^T."""
+        AT = self.transpose(A)
+        T = self.spgemm(AT, Q)
+        del AT
+        C = self.spgemm(QT, T)
+        del T
+        return self.transpose(C)
+
+    def permute(self, A, perm, col_iperm):
+        t = self.torch
+        if perm is None and col_iperm is None:
+            return A
+        n = A.shape[0]
+        if perm is None:
+            optr = A.indptr
+        else:
+            lens = self.empty(n, t.int32)
+            _lib.check(self.lib.mg_csr_row_lengths(n, A.indptr.data_ptr(), perm.data_ptr(), lens.data_ptr(), self.st()),
+                       "mg_csr_row_lengths")
+            optr, total = self.scan(lens, n)
+            assert total == A.nnz
+        oidx = self.empty(A.nnz, t.int32)
+        oval = self.empty(A.nnz, t.float64)
+        _lib.check(self.lib.mg_csr_permute(n, *A.ptrs(), _lib.ptr(perm), _lib.ptr(col_iperm), optr.data_ptr(),
+                                           oidx.data_ptr(), oval.data_ptr(), self.st()), "mg_csr_permute")
+        return DevCSR(A.shape, optr, oidx, oval)
+
+    def to_sell(self, A):
+        from .engine import DeviceSell
+        t = self.torch
+        n = A.shape[0]
+        nsl = (n + 31) // 32
+        slen = self.empty(nsl, t.int32)
+        sptr = self.empty(nsl + 1, t.int64)
+        nb = int(self.lib.mg_scan_workspace_size(max(nsl, 1)))
+        tmp = self.temp(nb)
+        total = ctypes.c_int64(0)
+        _lib.check(self.lib.mg_sell_layout(n, A.indptr.data_ptr(), slen.data_ptr(), sptr.data_ptr(),
+                                           ctypes.byref(total), tmp.data_ptr(), nb, self.st()), "mg_sell_layout")
+        cols = self.empty(total.value, t.int32)
+        vals = self.empty(total.value, t.float64)
+        _lib.check(self.lib.mg_sell_fill(n, *A.ptrs(), sptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), self.st()),
+                   "mg_sell_fill")
+        return DeviceSell.from_device(A.shape, A.nnz, sptr, cols, vals)
+
+    def dinv(self, A, perm):
+        out = self.empty(A.shape[0], self.torch.float64)
+        _lib.check(self.lib.mg_extract_dinv(A.shape[0], *A.ptrs(), _lib.ptr(perm), out.data_ptr(), self.st()),
+                   "mg_extract_dinv")
+        return out
+
+    def color_perm(self, colors_host):
+        """device perm (new -> old, stable by colour), inverse perm, host colour offsets"""
+        t = self.torch
+        n = len(colors_host)
+        ncol = int(colors_host.max()) + 1 if n else 0
+        keys = t.from_numpy(np.ascontiguousarray(colors_host, dtype=np.int32)).to(self.dev)
+        ks = self.empty(n, t.int32)
+        perm = self.empty(n, t.int32)
+        iota = self.empty(n, t.int32)
+        nb = int(self.lib.mg_sort_workspace_size(max(n, 1)))
+        tmp = self.temp(nb)
+        bits = max(1, int(np.ceil(np.log2(max(ncol, 2)))))
+        _lib.check(self.lib.mg_stable_argsort_i32(n, keys.data_ptr(), ks.data_ptr(), perm.data_ptr(), iota.data_ptr(),
+                                                  bits, tmp.data_ptr(), nb, self.st()), "mg_stable_argsort_i32")
+        iperm = self.empty(n, t.int32)
+        _lib.check(self.lib.mg_invert_permutation(n, perm.data_ptr(), iperm.data_ptr(), self.st()),
+                   "mg_invert_permutation")
+        cptr = np.zeros(ncol + 1, dtype=np.int64)
+        np.cumsum(np.bincount(colors_host, minlength=ncol), out=cptr[1:])
+        return perm, iperm, cptr
 
 
 def setup_device(h, A, Q_list, colors, dense_coarse_max):
-    raise _lib.MgError("device setup kernels are not built yet; use setup='host'")
+    """Populate `h.levels` of a DeviceHierarchy with device-built data (same contents as the host path)."""
+    from .engine import Level
+    torch, dev = h.torch, h.device
+    S = DeviceSetup(torch, dev)
+    h._setup = S
+    L = h.nlevels
+    A_host0 = F.canonical_csr(sp.csc_matrix(A))            # Solver.py:18 stores csc_matrix(matrix)
+    A_nat = [S.upload(A_host0)]
+    Q_nat, QT_nat = [], []
+    for l in range(L - 1):
+        Q = S.upload(Q_list[l])
+        if Q.shape[0] != A_nat[l].shape[0]:
+            raise ValueError("Q_%d has %d rows, level operator has %d" % (l, Q.shape[0], A_nat[l].shape[0]))
+        QT = S.transpose(Q)
+        Q_nat.append(Q)
+        QT_nat.append(QT)
+        A_nat.append(S.galerkin(A_nat[l], Q, QT))
+    # orderings
+    perms, iperms, cptrs = [], [], []
+    h.colors = []
+    for l in range(L):
+        if h.smoother == "mcgs" and l < L - 1:
+            if colors is not None and colors[l] is not None:
+                col = np.ascontiguousarray(colors[l], dtype=np.int32)
+            else:
+                pat = A_host0 if l == 0 else F.raw_csr(A_nat[l].indptr.cpu().numpy(), A_nat[l].indices.cpu().numpy(),
+                                                       np.zeros(A_nat[l].nnz), A_nat[l].shape)
+                col = F.greedy_colors(pat)[0]
+            p, ip, cp = S.color_perm(col)
+            h.colors.append(col)
+        else:
+            p = ip = cp = None
+            h.colors.append(None)
+        perms.append(p)
+        iperms.append(ip)
+        cptrs.append(cp)
+    h.levels = []
+    for l in range(L):
+        lev = Level()
+        lev.n = A_nat[l].shape[0]
+        lev.perm = perms[l]
+        lev.color_ptr = cptrs[l]
+        lev.nnz_A = A_nat[l].nnz
+        if l < L - 1:
+            Ap = S.permute(A_nat[l], perms[l], iperms[l])
+            lev.A = S.to_sell(Ap)
+            del Ap
+            lev.dinv = S.dinv(A_nat[l], perms[l])
+            Qp = S.permute(Q_nat[l], perms[l], iperms[l + 1])
+            lev.Q = S.to_sell(Qp)
+            del Qp
+            QTp = S.permute(QT_nat[l], perms[l + 1], iperms[l])
+            lev.QT = S.to_sell(QTp)
+            del QTp
+            lev.nnz_Q = Q_nat[l].nnz
+            if h.smoother == "lexgs":
+                lev.csr = (A_nat[l].indptr, A_nat[l].indices, A_nat[l].values)
+                pat = A_host0 if l == 0 else S.download(A_nat[l])
+                lp, lr = F.lex_levels(pat)
+                lev.lex_ptr = torch.from_numpy(lp).to(dev)
+                lev.lex_rows = torch.from_numpy(lr).to(dev)
+                lev.lex_nlevels = len(lp) - 1
+        else:
+            h._coarsest_from_device_csr(lev, A_nat[l], dense_coarse_max)
+        h.levels.append(lev)
+    h.host_A = None
+    h.host_Q = None
+    if h.keep_host:
+        h._dev_A_nat = A_nat
+        h._dev_Q_nat = Q_nat
+    S._temp = None
+    torch.cuda.synchronize()
 
 
 def download_level_matrix(h, l):
-    raise _lib.MgError("level matrices were not kept on the host")
+    A = getattr(h, "_dev_A_nat", None)
+    if A is None:
+        raise _lib.MgError("level matrices were not kept (keep_host=False)")
+    return h._setup.download(A[l])

@@ -43,7 +43,7 @@ class Multigrid(IterativeSolver):
         self._hier_key = None
         self._interp_cache = {}
         self.verbose = False
-        self.setup = "host"
+        self.setup = "device"
 
     # ------------------------------------------------------------------------------------------------
     def solve(self, levels=2, smoother="Jacobi", smooth_steps=1, max_iterations=100, error=1e-08,
