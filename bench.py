@@ -34,7 +34,7 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("MGB_BENCH_N", "4096")),
+    ap.add_argument("--n", type=int, default=int(os.environ.get("MGB_BENCH_N", "8192")),
                     help="elements per side of the structured mesh ((n+1)^2 DOF)")
     ap.add_argument("--levels", type=int, default=int(os.environ.get("MGB_BENCH_LEVELS", "6")))
     ap.add_argument("--transfer", default=os.environ.get("MGB_BENCH_TRANSFER", "linear"), choices=["linear", "quasi"])
@@ -59,55 +59,60 @@ def workload_name(a, n):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled through NVML from a thread DURING the timed regions."""
 
-    def __init__(self, index=0):
-        self.lines = []
-        self.proc = None
-        self.index = index
+    def __init__(self, index=0, period=0.005):
+        self.index, self.period = index, period
+        self.samples = []
+        self.on = False
+        self.ok = False
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.ok = True
+        except Exception as e:   # pragma: no cover
+            self.err = repr(e)
+            return
+        self.on = True
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
-
-    def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, smax, reasons, power = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
+    def _run(self):
+        nv = self.nv
+        while self.on:
             try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-                power.append(float(f[3]))
-            except ValueError:
-                continue
-            for k, nm in enumerate(names):
-                if f[5 + k].lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), sm, rs, pw))
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self, windows=None):
+        """windows: list of (t0, t1) perf_counter intervals that count as 'under load'"""
+        if not self.ok:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "")]}
+        self.on = False
+        self.t.join(timeout=1)
+        nv = self.nv
+        smax = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+        sel = [s for s in self.samples if windows is None or any(a <= s[0] <= b for a, b in windows)]
+        if not sel:
+            sel = self.samples
+        bits = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+                "hw_power_brake": 0x80}
+        reasons = sorted(k for k, m in bits.items() if any(s[2] & m for s in sel))
+        return {"sm_mhz": float(np.median([s[1] for s in sel])) if sel else None, "sm_max_mhz": float(smax),
+                "power_w_max": max(s[3] for s in sel) if sel else None, "samples_under_load": len(sel),
+                "samples": len(self.samples), "reasons": reasons}
 
 
 def peaks():
@@ -248,14 +253,17 @@ def run_b200(a):
         dist.barrier()
     sampler = ClockSampler(local)
     sampler.start()
+    windows = []
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    tw = time.perf_counter()
     e0.record()
     for _ in range(a.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
+    windows.append((tw, time.perf_counter()))
     ms_total = e0.elapsed_time(e1)
     if world > 1:
         dist.barrier()
@@ -268,7 +276,7 @@ def run_b200(a):
     # ---- dominant kernel: one fine-level smoothing sweep (sell_kernel<GS> per colour / sell_kernel<JACOBI>) ----
     S = lev0.nnz_A * 12 + 4 * (lev0.n + 1)
     sweep_bytes = S + 24 * lev0.n
-    reps = 20
+    reps = 50
     nlaunch = lev0.A.struct.nrows and (len(lev0.color_ptr) - 1 if lev0.color_ptr is not None else 1)
 
     def sweep():
@@ -282,13 +290,15 @@ def run_b200(a):
     for _ in range(3):
         sweep()
     torch.cuda.synchronize()
+    tw = time.perf_counter()
     e0.record()
     for _ in range(reps):
         sweep()
     e1.record()
     torch.cuda.synchronize()
+    windows.append((tw, time.perf_counter()))
     ms_sweep = e0.elapsed_time(e1) / reps
-    clocks = sampler.stop()
+    clocks = sampler.stop(windows)
     peak, peak_src = peaks()
     ach = sweep_bytes / (ms_sweep * 1e-3) / 1e9
     cyc = h.cycle_bytes(a.nu, a.nu)

@@ -77,7 +77,8 @@ int mg_prolong_correct_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_
  * holds len_s = (slice_ptr[s+1]-slice_ptr[s])/32 entries per row, column-major inside the slice:
  * entry k of row r sits at slice_ptr[r/32] + 32*k + r%32.  Entries keep their CSR order; padding entries
  * have value 0.0 and any valid column (the builder repeats the row's last column), so they add an exact
- * zero to every row sum and are ignored by the diagonal detection of the Gauss-Seidel kernel.       */
+ * zero to every row sum and are ignored by the diagonal detection of the Gauss-Seidel kernel.  The builder pads
+ * all slices to the longest one ("uniform") when that costs <= 3 % extra entries (structured grids).      */
 typedef struct {
     int64_t nrows;
     int64_t ncols;
@@ -85,6 +86,9 @@ typedef struct {
     const int64_t *d_slice_ptr; /* [nslices+1], entry offsets (multiples of 32)    */
     const int32_t *d_cols;
     const double *d_vals;
+    int64_t max_slice_len;      /* longest slice (entries per row); 0 = unknown (generic kernel)           */
+    int64_t uniform_len;        /* > 0: EVERY slice has exactly this many entries per row (= max_slice_len), so
+                                   slice offsets are computed, not loaded; 0 = lengths vary, use d_slice_ptr */
 } mg_sell;
 
 /* y = A x  (rows [row0,row1)) */
@@ -96,6 +100,9 @@ int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, dou
 int mg_sell_residual_norm2(const mg_sell *A, const double *d_x, const double *d_b, double *d_partials,
                            double *d_norm2, void *stream);
 int64_t mg_norm_workspace_size(int64_t n);
+/* launches that cover at least `rows` rows use the bulk-async (TMA) staged kernel; 0 = never.  Returns the
+ * previous threshold (default 65536).  Both kernels give bit-identical results. */
+int64_t mg_set_tma_min_rows(int64_t rows);
 /* x_out = x + omega*(dinv*(b - A x)) */
 int mg_sell_jacobi(const mg_sell *A, const double *d_dinv, const double *d_x, const double *d_b,
                    double *d_x_out, double omega, void *stream);
@@ -194,7 +201,8 @@ int mg_csr_permute(int64_t n, const int32_t *d_in_indptr, const int32_t *d_in_in
                    int32_t *d_out_indices, double *d_out_values, void *stream);
 /* SELL-32 build: layout (slice pointers, padded size returned on the host; synchronises) then fill */
 int mg_sell_layout(int64_t n, const int32_t *d_indptr, int32_t *d_slice_len_tmp, int64_t *d_slice_ptr,
-                   int64_t *h_total_out, void *d_temp, int64_t temp_bytes, void *stream);
+                   int64_t *h_total_out, int64_t *h_max_len_out, int64_t *h_uniform_len_out, void *d_temp,
+                   int64_t temp_bytes, void *stream);
 int mg_sell_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
                  const int64_t *d_slice_ptr, int32_t *d_cols, double *d_vals, void *stream);
 /* d_dinv[i] = 1 / A[perm[i], perm[i]] (Jacobi.py:22-23 inverts the diagonal) */

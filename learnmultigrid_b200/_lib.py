@@ -28,7 +28,8 @@ class MgError(RuntimeError):
 
 class mg_sell(ctypes.Structure):
     _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nslices", c_i64),
-                ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp)]
+                ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp), ("max_slice_len", c_i64),
+                ("uniform_len", c_i64)]
 
 
 class mg_bcr(ctypes.Structure):
@@ -70,6 +71,7 @@ _SIGNATURES = {
     "mg_sell_residual": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
     "mg_sell_residual_norm2": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_norm_workspace_size": (c_i64, [c_i64]),
+    "mg_set_tma_min_rows": (c_i64, [c_i64]),
     "mg_sell_jacobi": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "mg_sell_gs_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_i64, c_i64, c_vp]),
     "mg_sell_prolong_correct": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
@@ -99,7 +101,8 @@ _SIGNATURES = {
     "mg_invert_permutation": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "mg_csr_row_lengths": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mg_csr_permute": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mg_sell_layout": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), c_vp, c_i64, c_vp]),
+    "mg_sell_layout": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.POINTER(c_i64), ctypes.POINTER(c_i64),
+                               ctypes.POINTER(c_i64), c_vp, c_i64, c_vp]),
     "mg_sell_fill": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_extract_dinv": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_host_greedy_color": (c_int, [c_i64, c_vp, c_vp, c_vp]),

@@ -9,8 +9,6 @@
 
 namespace mgb {
 
-enum SellMode { SPMV = 0, RESID = 1, RESNORM = 2, JACOBI = 3, GS = 4, PROLONG = 5 };
-
 struct SellArgs {
     const int64_t *__restrict__ slice_ptr;
     const int32_t *__restrict__ cols;
@@ -20,7 +18,37 @@ struct SellArgs {
     int64_t first_row;   // row of thread 0 of block 0 (row_begin rounded down to a slice)
 };
 
-template <int MODE>
+// accumulate CNT consecutive entries of a row: all cols/vals loads are issued first, then all x gathers, then the
+// sums in storage order.  Straight-line code: CNT*12 bytes per thread in flight at ~4 registers per entry.
+template <int MODE, int CNT>
+__device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const double *__restrict__ v,
+                                          const double *x, int64_t row, double &sum, double &diag) {
+    int32_t cc[CNT];
+    double vv[CNT], xx[CNT];
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+        cc[j] = ld_stream(c + j * kSlice);
+        vv[j] = ld_stream(v + j * kSlice);
+    }
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) xx[j] = x[cc[j]];
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+        if (MODE == GS) {
+            if (cc[j] == row) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
+        } else {
+            sum = mul_add_unfused(sum, vv[j], xx[j]);
+        }
+    }
+}
+
+// LEN   : the matrix' longest slice when it is <= 8 (fast path: slices of exactly LEN entries run one straight-line
+//         row_chunk<LEN>; shorter slices take a rolled loop), 0 for longer rows (chunks of 4 + rolled remainder).
+// UNIFORM: every slice of the matrix has exactly LEN entries, so the slice offset is computed instead of loaded.
+// The microbenchmark behind these choices is tools/sellbench.cu (profiles/r01_sellbench.log): occupancy x bytes in
+// flight per thread decides; at 32 registers and 60 B per thread the fine-level sweep reaches the DRAM limit
+// (6.8 TB/s algorithmic, ~7.1 TB/s of actual traffic), a rolled loop stays at 5.4 TB/s.
+template <int MODE, int LEN, bool UNIFORM>
 __global__ void __launch_bounds__(kBlock)
 sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
             double *y, double omega, double *__restrict__ partials) {
@@ -30,39 +58,25 @@ sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const dou
     if (row < A.row_end) {   // warp-uniform except in the last slice
         const int64_t slice = row >> 5;
         const int lane = (int)(row & 31);
-        const int64_t base = A.slice_ptr[slice];
-        const int len = (int)((A.slice_ptr[slice + 1] - base) >> 5);
+        int64_t base;
+        int len;
+        if (UNIFORM) {
+            base = slice * (int64_t)(kSlice * LEN);
+            len = LEN;
+        } else {
+            base = A.slice_ptr[slice];
+            len = (int)((A.slice_ptr[slice + 1] - base) >> 5);
+        }
         const double *__restrict__ v = A.vals + base + lane;
         const int32_t *__restrict__ c = A.cols + base + lane;
         double sum = 0.0, diag = 0.0;
-        int k = 0;
-        for (; k + 4 <= len; k += 4) {
-            const int32_t c0 = ld_stream(c + (k + 0) * kSlice), c1 = ld_stream(c + (k + 1) * kSlice),
-                          c2 = ld_stream(c + (k + 2) * kSlice), c3 = ld_stream(c + (k + 3) * kSlice);
-            const double v0 = ld_stream(v + (k + 0) * kSlice), v1 = ld_stream(v + (k + 1) * kSlice),
-                         v2 = ld_stream(v + (k + 2) * kSlice), v3 = ld_stream(v + (k + 3) * kSlice);
-            const double x0 = x[c0], x1 = x[c1], x2 = x[c2], x3 = x[c3];
-            if (MODE == GS) {
-                if (c0 == row) { if (v0 != 0.0) diag = v0; } else sum = mul_add_unfused(sum, v0, x0);
-                if (c1 == row) { if (v1 != 0.0) diag = v1; } else sum = mul_add_unfused(sum, v1, x1);
-                if (c2 == row) { if (v2 != 0.0) diag = v2; } else sum = mul_add_unfused(sum, v2, x2);
-                if (c3 == row) { if (v3 != 0.0) diag = v3; } else sum = mul_add_unfused(sum, v3, x3);
-            } else {
-                sum = mul_add_unfused(sum, v0, x0);
-                sum = mul_add_unfused(sum, v1, x1);
-                sum = mul_add_unfused(sum, v2, x2);
-                sum = mul_add_unfused(sum, v3, x3);
-            }
-        }
-        for (; k < len; ++k) {
-            const int32_t c0 = ld_stream(c + k * kSlice);
-            const double v0 = ld_stream(v + k * kSlice);
-            const double x0 = x[c0];
-            if (MODE == GS) {
-                if (c0 == row) { if (v0 != 0.0) diag = v0; } else sum = mul_add_unfused(sum, v0, x0);
-            } else {
-                sum = mul_add_unfused(sum, v0, x0);
-            }
+        if (LEN > 0 && (UNIFORM || len == LEN)) {
+            row_chunk<MODE, (LEN > 0 ? LEN : 1)>(c, v, x, row, sum, diag);
+        } else {
+            int k = 0;
+            if (LEN == 0)
+                for (; k + 4 <= len; k += 4) row_chunk<MODE, 4>(c + k * kSlice, v + k * kSlice, x, row, sum, diag);
+            for (; k < len; ++k) row_chunk<MODE, 1>(c + k * kSlice, v + k * kSlice, x, row, sum, diag);
         }
         if (active) {
             if (MODE == SPMV) {
@@ -98,10 +112,26 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__r
 }
 
 template <int MODE>
+int launch_sell_tma(const mg_sell *M, int64_t max_len, const double *x, const double *b, const double *aux, double *y,
+                    double omega, double *partials, int64_t row0, int64_t row1, int *grid_out, cudaStream_t st,
+                    const char *name);
+
+// rows per launch from which the bulk-async staged kernel (sell_tma.cu) is used; 0 disables it
+static int64_t g_tma_min_rows = 0;   // off by default: the register-staged kernel is as fast (see sell_tma.cu)
+
+template <int MODE>
 static int launch_sell(const mg_sell *A, const double *x, const double *b, const double *aux, double *y,
                        double omega, double *partials, int64_t row0, int64_t row1, cudaStream_t st,
-                       const char *name) {
+                       const char *name, int *nblocks_out = nullptr) {
     if (row1 <= row0) return MG_OK;
+    if (g_tma_min_rows > 0 && row1 - row0 >= g_tma_min_rows && A->max_slice_len > 0) {
+        int grid = 0;
+        const int rc = launch_sell_tma<MODE>(A, A->max_slice_len, x, b, aux, y, omega, partials, row0, row1, &grid, st, name);
+        if (rc <= 0) {
+            if (nblocks_out) *nblocks_out = grid;
+            return rc;
+        }
+    }
     SellArgs a;
     a.slice_ptr = A->d_slice_ptr;
     a.cols = A->d_cols;
@@ -112,8 +142,28 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     const int64_t nthreads = row1 - a.first_row;
     const int64_t grid = (nthreads + kBlock - 1) / kBlock;
     if (grid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
-    sell_kernel<MODE><<<(unsigned)grid, kBlock, 0, st>>>(a, x, b, aux, y, omega, partials);
+    const int64_t ml = A->max_slice_len;
+    const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
+#define MG_SELL_CASE(L)                                                                                      \
+    do {                                                                                                     \
+        if (uni) sell_kernel<MODE, L, true><<<(unsigned)grid, kBlock, 0, st>>>(a, x, b, aux, y, omega, partials); \
+        else sell_kernel<MODE, L, false><<<(unsigned)grid, kBlock, 0, st>>>(a, x, b, aux, y, omega, partials);     \
+    } while (0)
+    switch (ml) {
+        case 1: MG_SELL_CASE(1); break;
+        case 2: MG_SELL_CASE(2); break;
+        case 3: MG_SELL_CASE(3); break;
+        case 4: MG_SELL_CASE(4); break;
+        case 5: MG_SELL_CASE(5); break;
+        case 6: MG_SELL_CASE(6); break;
+        case 7: MG_SELL_CASE(7); break;
+        case 8: MG_SELL_CASE(8); break;
+        default:   // long rows, or length unknown (0)
+            sell_kernel<MODE, 0, false><<<(unsigned)grid, kBlock, 0, st>>>(a, x, b, aux, y, omega, partials);
+    }
+#undef MG_SELL_CASE
     MG_CHECK_LAUNCH(name);
+    if (nblocks_out) *nblocks_out = (int)grid;
     return MG_OK;
 }
 
@@ -125,9 +175,9 @@ int sell_residual(const mg_sell *A, const double *x, const double *b, double *r,
 }
 int sell_residual_norm2(const mg_sell *A, const double *x, const double *b, double *partials, double *out,
                         cudaStream_t st) {
-    const int64_t nblocks = (A->nrows + kBlock - 1) / kBlock;
+    int nblocks = 0;
     int rc = launch_sell<RESNORM>(A, x, b, nullptr, nullptr, 0.0, partials, 0, A->nrows, st,
-                                  "sell_residual_norm2");
+                                  "sell_residual_norm2", &nblocks);
     if (rc) return rc;
     reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, nblocks, out);
     MG_CHECK_LAUNCH("reduce_partials");
@@ -167,6 +217,12 @@ int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, dou
     return sell_residual(A, d_x, d_b, d_r, (cudaStream_t)stream);
 }
 int64_t mg_norm_workspace_size(int64_t n) { return (n + kBlock - 1) / kBlock + 1; }
+/* rows per launch from which the bulk-async staged SELL kernel is used (0 = never); returns the old value */
+int64_t mg_set_tma_min_rows(int64_t rows) {
+    const int64_t old = g_tma_min_rows;
+    g_tma_min_rows = rows;
+    return old;
+}
 int mg_sell_residual_norm2(const mg_sell *A, const double *d_x, const double *d_b, double *d_partials,
                            double *d_norm2, void *stream) {
     if (int rc = check_sell(A)) return rc;

@@ -281,9 +281,12 @@ int64_t mg_scan_workspace_size(int64_t n) {
     cub::DeviceScan::InclusiveSum(nullptr, a, (const int32_t *)nullptr, (int32_t *)nullptr, n);
     cub::DeviceReduce::Sum(nullptr, b, it64, (int64_t *)nullptr, n);
     cub::DeviceScan::InclusiveSum(nullptr, c, it32, (int64_t *)nullptr, n);
+    size_t d = 0;
+    cub::DeviceReduce::Max(nullptr, d, (const int32_t *)nullptr, (int32_t *)nullptr, n);
     size_t m = a > b ? a : b;
     if (c > m) m = c;
-    return (int64_t)m + 256;
+    if (d > m) m = d;
+    return (int64_t)m + 1024;
 }
 
 /* d_out[0] = 0, d_out[i+1] = d_in[0] + ... + d_in[i]  (int32 row pointer); *d_total = the same sum in int64.
@@ -428,11 +431,21 @@ int mg_csr_permute(int64_t n, const int32_t *d_in_indptr, const int32_t *d_in_in
     return MG_OK;
 }
 
-/* SELL-32 build, step 1: d_slice_ptr[nslices+1] (int64 entry offsets); *h_total_out = padded entry count.
- * d_slice_len_tmp: nslices int32.  Synchronises the stream. */
+__global__ void __launch_bounds__(kBlock) fill_i32_kernel(int64_t n, int32_t v, int32_t *out) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
+/* SELL-32 build, step 1: d_slice_ptr[nslices+1] (int64 entry offsets); on the host: padded entry count, longest
+ * slice, and the uniform length (all slices are padded to the longest one when that costs <= 3 % extra entries;
+ * 0 otherwise).  d_slice_len_tmp: nslices int32.  Synchronises the stream. */
 int mg_sell_layout(int64_t n, const int32_t *d_indptr, int32_t *d_slice_len_tmp, int64_t *d_slice_ptr,
-                   int64_t *h_total_out, void *d_temp, int64_t temp_bytes, void *stream) {
-    MG_REQUIRE(n >= 0 && d_slice_ptr && h_total_out, "bad argument");
+                   int64_t *h_total_out, int64_t *h_max_len_out, int64_t *h_uniform_len_out, void *d_temp,
+                   int64_t temp_bytes, void *stream) {
+    MG_REQUIRE(n >= 0 && d_slice_ptr && h_total_out && h_max_len_out && h_uniform_len_out && temp_bytes > 512,
+               "bad argument");
+    *h_max_len_out = 0;
+    *h_uniform_len_out = 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nslices = (n + kSlice - 1) / kSlice;
     MG_CHECK_CUDA(cudaMemsetAsync(d_slice_ptr, 0, sizeof(int64_t), st));
@@ -440,12 +453,33 @@ int mg_sell_layout(int64_t n, const int32_t *d_indptr, int32_t *d_slice_len_tmp,
     if (nslices == 0) return MG_OK;
     slice_lengths_kernel<<<(unsigned)((nslices * kSlice + kBlock - 1) / kBlock), kBlock, 0, st>>>(n, d_indptr, d_slice_len_tmp);
     MG_CHECK_LAUNCH("slice_lengths");
+    // the first 256 bytes of the workspace hold the reduction results, the rest is CUB scratch
+    int32_t *d_max = (int32_t *)d_temp;
+    int64_t *d_sum = (int64_t *)((char *)d_temp + 64);
+    void *cub_temp = (void *)((char *)d_temp + 256);
+    size_t bytes = (size_t)temp_bytes - 256;
+    MG_CHECK_CUDA(cub::DeviceReduce::Max(cub_temp, bytes, d_slice_len_tmp, d_max, nslices, st));
+    cub::TransformInputIterator<int64_t, ToI64, const int32_t *> it64(d_slice_len_tmp, ToI64());
+    bytes = (size_t)temp_bytes - 256;
+    MG_CHECK_CUDA(cub::DeviceReduce::Sum(cub_temp, bytes, it64, d_sum, nslices, st));
+    int32_t h_max = 0;
+    int64_t h_sum = 0;
+    MG_CHECK_CUDA(cudaMemcpyAsync(&h_max, d_max, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MG_CHECK_CUDA(cudaMemcpyAsync(&h_sum, d_sum, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
+    MG_CHECK_CUDA(cudaStreamSynchronize(st));
+    const bool uniform = h_max > 0 && nslices * (int64_t)h_max * 100 <= 103 * h_sum;
+    if (uniform) {
+        fill_i32_kernel<<<(unsigned)((nslices + kBlock - 1) / kBlock), kBlock, 0, st>>>(nslices, h_max, d_slice_len_tmp);
+        MG_CHECK_LAUNCH("fill_i32");
+    }
     cub::TransformInputIterator<int64_t, Times32, const int32_t *> it(d_slice_len_tmp, Times32());
-    size_t bytes = (size_t)temp_bytes;
-    MG_CHECK_CUDA(cub::DeviceScan::InclusiveSum(d_temp, bytes, it, d_slice_ptr + 1, nslices, st));
-    ++g_launch_count;
+    bytes = (size_t)temp_bytes - 256;
+    MG_CHECK_CUDA(cub::DeviceScan::InclusiveSum(cub_temp, bytes, it, d_slice_ptr + 1, nslices, st));
+    g_launch_count += 3;
     MG_CHECK_CUDA(cudaMemcpyAsync(h_total_out, d_slice_ptr + nslices, sizeof(int64_t), cudaMemcpyDeviceToHost, st));
     MG_CHECK_CUDA(cudaStreamSynchronize(st));
+    *h_max_len_out = h_max;
+    *h_uniform_len_out = uniform ? h_max : 0;
     return MG_OK;
 }
 

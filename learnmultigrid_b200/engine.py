@@ -35,18 +35,25 @@ class DeviceSell:
         self.slice_ptr = torch.from_numpy(slice_ptr).to(device)
         self.cols = torch.from_numpy(cols).to(device)
         self.vals = torch.from_numpy(vals).to(device)
+        d = np.diff(slice_ptr) // 32
+        self.max_len = int(d.max()) if len(d) else 0
+        self.uniform_len = self.max_len if len(d) and int(d.min()) == self.max_len else 0
         self.struct = _lib.mg_sell(self.shape[0], self.shape[1], (self.shape[0] + 31) // 32,
-                                   self.slice_ptr.data_ptr(), self.cols.data_ptr(), self.vals.data_ptr())
+                                   self.slice_ptr.data_ptr(), self.cols.data_ptr(), self.vals.data_ptr(),
+                                   self.max_len, self.uniform_len)
 
     @classmethod
-    def from_device(cls, shape, nnz, slice_ptr, cols, vals):
+    def from_device(cls, shape, nnz, slice_ptr, cols, vals, max_len=0, uniform_len=0):
         self = cls.__new__(cls)
         self.shape = tuple(shape)
         self.nnz = int(nnz)
         self.padded = int(cols.numel())
         self.slice_ptr, self.cols, self.vals = slice_ptr, cols, vals
+        self.max_len = int(max_len)
+        self.uniform_len = int(uniform_len)
         self.struct = _lib.mg_sell(shape[0], shape[1], (shape[0] + 31) // 32,
-                                   slice_ptr.data_ptr(), cols.data_ptr(), vals.data_ptr())
+                                   slice_ptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), self.max_len,
+                                   self.uniform_len)
         return self
 
     def bytes(self):

@@ -65,6 +65,11 @@ def transpose_csr(Q):
     return canonical_csr(QT)
 
 
+def sell_is_uniform(max_len, sum_len, nslices):
+    """pad all slices to the longest one when that costs at most 3 % extra entries (same rule as mg_sell_layout)"""
+    return max_len > 0 and nslices * max_len * 100 <= 103 * sum_len
+
+
 def csr_to_sell(A):
     """(slice_ptr int64[nslices+1], cols int32[total], vals float64[total]) of the SELL-32 layout."""
     n = A.shape[0]
@@ -75,6 +80,8 @@ def csr_to_sell(A):
     lens_p = np.zeros(nsl * SLICE, dtype=np.int64)
     lens_p[:n] = lens
     sl_len = lens_p.reshape(nsl, SLICE).max(axis=1) if nsl else np.zeros(0, dtype=np.int64)
+    if nsl and sell_is_uniform(int(sl_len.max()), int(sl_len.sum()), nsl):
+        sl_len = np.full(nsl, sl_len.max(), dtype=np.int64)      # pad every slice to the longest one
     slice_ptr = np.zeros(nsl + 1, dtype=np.int64)
     np.cumsum(sl_len * SLICE, out=slice_ptr[1:])
     total = int(slice_ptr[-1])

@@ -169,13 +169,16 @@ class DeviceSetup:
         nb = int(self.lib.mg_scan_workspace_size(max(nsl, 1)))
         tmp = self.temp(nb)
         total = ctypes.c_int64(0)
+        maxlen = ctypes.c_int64(0)
+        unilen = ctypes.c_int64(0)
         _lib.check(self.lib.mg_sell_layout(n, A.indptr.data_ptr(), slen.data_ptr(), sptr.data_ptr(),
-                                           ctypes.byref(total), tmp.data_ptr(), nb, self.st()), "mg_sell_layout")
+                                           ctypes.byref(total), ctypes.byref(maxlen), ctypes.byref(unilen),
+                                           tmp.data_ptr(), nb, self.st()), "mg_sell_layout")
         cols = self.empty(total.value, t.int32)
         vals = self.empty(total.value, t.float64)
         _lib.check(self.lib.mg_sell_fill(n, *A.ptrs(), sptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), self.st()),
                    "mg_sell_fill")
-        return DeviceSell.from_device(A.shape, A.nnz, sptr, cols, vals)
+        return DeviceSell.from_device(A.shape, A.nnz, sptr, cols, vals, maxlen.value, unilen.value)
 
     def dinv(self, A, perm):
         out = self.empty(A.shape[0], self.torch.float64)

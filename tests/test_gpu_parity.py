@@ -142,8 +142,72 @@ def sell_struct(env, A):
     return DeviceSell(env["torch"], A, env["dev"])
 
 
+@pytest.fixture(params=["plain", "tma"])
+def sell_path(request, env):
+    """run the SELL tests through the plain kernel and through the bulk-async (TMA) staged kernel"""
+    old = env["lib"].mg_set_tma_min_rows(1 if request.param == "tma" else 0)
+    yield request.param
+    env["lib"].mg_set_tma_min_rows(old)
+
+
+@pytest.mark.parametrize("n,per_row", [(5000, 2), (70000, 5), (33000, 9), (4100, 40), (600, 700)])
+def test_sell_tma_all_modes_and_stage_geometries(env, n, per_row):
+    """max slice length 2 / 5 / ~10 / ~40 / > 500 exercises the G = 4, 2, 1 stage geometries and the fallback for
+    very long rows; row ranges that start and end inside a slice exercise the colour-block masking"""
+    from learnmultigrid_b200 import formats as F
+    L, lib, torch = env["L"], env["lib"], env["torch"]
+    rng = np.random.default_rng(n)
+    rows = np.repeat(np.arange(n), per_row)
+    cols = (rows + rng.integers(-3 * per_row, 3 * per_row + 1, size=rows.size)) % n
+    A = F.canonical_csr(sp.csr_matrix((rng.standard_normal(rows.size), (rows, cols)), shape=(n, n)) + 4.0 * sp.eye(n))
+    S = sell_struct(env, A)
+    x, b = rng.standard_normal(n), rng.standard_normal(n)
+    dx, db = up(env, x), up(env, b)
+    old = lib.mg_set_tma_min_rows(1)
+    try:
+        out = torch.empty(n, dtype=torch.float64, device=env["dev"])
+        L.check(lib.mg_sell_spmv(ctypes.byref(S.struct), dx.data_ptr(), out.data_ptr(), stream(env)))
+        assert np.array_equal(out.cpu().numpy(), K.spmv(A, x))
+        L.check(lib.mg_sell_residual(ctypes.byref(S.struct), dx.data_ptr(), db.data_ptr(), out.data_ptr(), stream(env)))
+        r = K.residual(A, x, b)
+        assert np.array_equal(out.cpu().numpy(), r)
+        ws = torch.zeros(int(lib.mg_norm_workspace_size(n)) + 8, dtype=torch.float64, device=env["dev"])
+        nrm = torch.zeros(1, dtype=torch.float64, device=env["dev"])
+        L.check(lib.mg_sell_residual_norm2(ctypes.byref(S.struct), dx.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                           nrm.data_ptr(), stream(env)))
+        np.testing.assert_allclose(np.sqrt(nrm.item()), np.linalg.norm(r), rtol=1e-13)
+        dinv = 1.0 / A.diagonal()
+        dd = up(env, dinv)
+        L.check(lib.mg_sell_jacobi(ctypes.byref(S.struct), dd.data_ptr(), dx.data_ptr(), db.data_ptr(), out.data_ptr(),
+                                   0.8, stream(env)))
+        assert np.array_equal(out.cpu().numpy(), K.jacobi(A, x, b, dinv, 0.8, 1))
+        # Gauss-Seidel on an arbitrary row range [r0, r1) (Jacobi-style inside the range, like one colour block)
+        r0, r1 = 37, n - 45
+        want = x.copy()
+        Ao = A.copy()
+        acc = b[r0:r1] - (A[r0:r1] @ x - A.diagonal()[r0:r1] * x[r0:r1])
+        dxs = up(env, x.copy())
+        L.check(lib.mg_sell_gs_rows(ctypes.byref(S.struct), dxs.data_ptr(), db.data_ptr(), r0, r1, stream(env)))
+        got = dxs.cpu().numpy()
+        assert np.array_equal(got[:r0], x[:r0]) and np.array_equal(got[r1:], x[r1:])
+        # rows inside the range may read rows of the same range that were already updated only if coupled; compare
+        # against the oracle on the decoupled reference: one row at a time with the ORIGINAL x (what a valid colour sees)
+        ref = x.copy()
+        for i in (r0, r0 + 1, (r0 + r1) // 2, r1 - 1):
+            xi = x.copy()
+            K.gauss_seidel_multicolor(A, xi, b, [np.array([i], dtype=np.int32)])
+            ref[i] = xi[i]
+            if not np.any((A[i].indices >= r0) & (A[i].indices < r1) & (A[i].indices != i)):
+                assert got[i] == ref[i]
+        du = up(env, b.copy())
+        L.check(lib.mg_sell_prolong_correct(ctypes.byref(S.struct), dx.data_ptr(), du.data_ptr(), du.data_ptr(), stream(env)))
+        assert np.array_equal(du.cpu().numpy(), K.prolong_correct(A, x, b))
+    finally:
+        lib.mg_set_tma_min_rows(old)
+
+
 @pytest.mark.parametrize("shape,density", [((1, 1), 1.0), ((33, 20), 0.3), ((1000, 1000), 0.01), ((4100, 900), 0.004)])
-def test_sell_kernels_bit_exact(env, shape, density):
+def test_sell_kernels_bit_exact(env, sell_path, shape, density):
     from learnmultigrid_b200 import formats as F
     L, lib, torch = env["L"], env["lib"], env["torch"]
     rng = np.random.default_rng(shape[0])
@@ -162,7 +226,7 @@ def test_sell_kernels_bit_exact(env, shape, density):
 
 
 @pytest.mark.parametrize("n,density", [(1, 1.0), (64, 0.1), (1500, 0.01)])
-def test_sell_square_kernels_bit_exact(env, n, density):
+def test_sell_square_kernels_bit_exact(env, sell_path, n, density):
     from learnmultigrid_b200 import formats as F
     L, lib, torch = env["L"], env["lib"], env["torch"]
     A, x, b = random_system(n, density, 100 + n)
@@ -281,7 +345,7 @@ def _cycle_case(env, A, Qs, smoother, omega, nu, use_graph, seed=0):
 
 @pytest.mark.parametrize("smoother,omega", [("jacobi", 2.0 / 3.0), ("jacobi", 1.0), ("mcgs", 1.0), ("lexgs", 1.0)])
 @pytest.mark.parametrize("nu", [1, 2, 3])
-def test_vcycle_2d_three_levels(env, smoother, omega, nu):
+def test_vcycle_2d_three_levels(env, sell_path, smoother, omega, nu):
     N = 32
     A = poisson2d(N)
     Qs = [bilinear_P(N), bilinear_P(N // 2)]
@@ -289,7 +353,7 @@ def test_vcycle_2d_three_levels(env, smoother, omega, nu):
 
 
 @pytest.mark.parametrize("smoother", ["jacobi", "mcgs"])
-def test_vcycle_2d_quasi_l2_transfers(env, smoother):
+def test_vcycle_2d_quasi_l2_transfers(env, sell_path, smoother):
     from learnmultigrid_b200 import problems as P
     N = 32
     A = P.structured_laplacian_2d(N)
