@@ -303,10 +303,14 @@ def run_b200(a):
     ach = sweep_bytes / (ms_sweep * 1e-3) / 1e9
     cyc = h.cycle_bytes(a.nu, a.nu)
     cyc_gbs = cyc["total"] / (ms_step * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_gs_traffic.json")
+    if lev0.color_ptr is not None and n == 8192 and a.coefficient == "constant" and os.path.exists(tpath):
+        traffic = json.load(open(tpath))["traffic_per_launch"]      # ncu --set full capture of this kernel / config
     roofline = {"bound": "hbm", "kernel": "sell_kernel<GS> (fine-level colour sweep)" if lev0.color_ptr is not None
                 else "sell_kernel<JACOBI> (fine-level sweep)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                "traffic": None, "bytes_per_launch": sweep_bytes / nlaunch, "launches_per_sweep": nlaunch,
+                "traffic": traffic, "bytes_per_launch": sweep_bytes / nlaunch, "launches_per_sweep": nlaunch,
                 "ms_per_launch": ms_sweep / nlaunch,
                 "cycle": {"algorithmic_bytes": cyc["total"], "achieved": cyc_gbs, "frac": cyc_gbs / peak,
                           "frac_of_8TBps": cyc_gbs / 8000.0, "bytes_per_dof": cyc["total"] / ndof}}
