@@ -210,6 +210,26 @@ int mg_extract_dinv(int64_t n, const int32_t *d_indptr, const int32_t *d_indices
                     const int32_t *d_perm, double *d_dinv, void *stream);
 
 /* ------------------------------------------------------------------------------------------------ */
+/* multi-GPU: halo exchange over peer-mapped memory (no reference counterpart; contract in SURVEY.md 8e).
+ * Each rank owns an arena (mg_comm_alloc) exported by CUDA IPC; neighbours map it and write boundary values directly
+ * into its staging area, then publish a sequence number (release, system scope); the owner's consumer kernel waits
+ * for it (acquire) and unpacks into the halo part of its level vector.  Expected sequence numbers are
+ * *d_seq_base + site, so that a captured V-cycle graph can be replayed (mg_seq_advance at its end). */
+int mg_comm_alloc(int64_t bytes, void **d_ptr_out);
+int mg_comm_free(void *d_ptr);
+int mg_comm_export(void *d_ptr, unsigned char *h_handle64);
+int mg_comm_import(const unsigned char *h_handle64, void **d_peer_ptr_out);
+int mg_comm_unmap(void *d_peer_ptr);
+int mg_halo_push(const double *d_src, const int32_t *d_idx, int64_t count, double *d_peer_dst, void *d_peer_flag,
+                 const void *d_seq_base, int64_t site, void *d_done, void *stream);
+int mg_halo_wait_unpack(const void *d_flag, const void *d_seq_base, int64_t site, const double *d_staging,
+                        double *d_dst, int64_t count, void *stream);
+int mg_seq_advance(void *d_seq_base, int64_t delta, void *stream);
+/* relabel the columns of a row block: c in [c0,c1) -> d_own_iperm[c-c0] (NULL: c-c0), else n_own + d_slot_of[c] */
+int mg_csr_remap_cols(int64_t nnz, const int32_t *d_cols_in, int64_t c0, int64_t c1, const int32_t *d_own_iperm,
+                      int64_t n_own, const int32_t *d_slot_of, int32_t *d_cols_out, int32_t *d_missing, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* host-side (serial, HOST pointers) setup helpers                                                    */
 /* First-fit greedy colouring in index order on the symmetrised pattern of A; returns ncolors (>0) or <0.
  * The colour order defines the multicolour Gauss-Seidel that replaces PyAMG's index-order sweep

@@ -105,6 +105,15 @@ _SIGNATURES = {
                                ctypes.POINTER(c_i64), c_vp, c_i64, c_vp]),
     "mg_sell_fill": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_extract_dinv": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_comm_alloc": (c_int, [c_i64, ctypes.POINTER(c_vp)]),
+    "mg_comm_free": (c_int, [c_vp]),
+    "mg_comm_export": (c_int, [c_vp, ctypes.c_char_p]),
+    "mg_comm_import": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
+    "mg_comm_unmap": (c_int, [c_vp]),
+    "mg_halo_push": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "mg_halo_wait_unpack": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
+    "mg_seq_advance": (c_int, [c_vp, c_i64, c_vp]),
+    "mg_csr_remap_cols": (c_int, [c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mg_host_greedy_color": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
     "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),

@@ -54,11 +54,8 @@ def _f64(a):
 
 
 def _csr(A):
-    """Canonical CSR view (what PyAMG does first: `A = csr_matrix(A)` if not CSR)."""
-    A = sp.csr_matrix(A)
-    if not A.has_sorted_indices:
-        A = A.sorted_indices()
-    return A
+    """CSR view (what PyAMG does first: `A = csr_matrix(A)` if not CSR); entries keep their storage order."""
+    return sp.csr_matrix(A)
 
 
 def gauss_seidel(A, x, b, iterations=1, sweep="forward"):
