@@ -34,6 +34,9 @@ typedef enum {
 /* library                                                                                          */
 int mg_version(void);
 const char *mg_last_error(void);
+/* sizeof of the ABI structs as compiled (0 mg_sell, 1 mg_level, 2 mg_cycle_params, 3 mg_bcr, 4 mg_comm, 5 mg_xfer,
+ * 6 mg_dist_level): lets a binding verify its own layout */
+int64_t mg_struct_size(int which);
 /* fills sm_count / total global memory (bytes) / compute capability (e.g. 100) of the current device */
 int mg_device_info(int *sm_count, int64_t *global_mem, int *cc);
 
@@ -210,24 +213,76 @@ int mg_extract_dinv(int64_t n, const int32_t *d_indptr, const int32_t *d_indices
                     const int32_t *d_perm, double *d_dinv, void *stream);
 
 /* ------------------------------------------------------------------------------------------------ */
-/* multi-GPU: halo exchange over peer-mapped memory (no reference counterpart; contract in SURVEY.md 8e).
- * Each rank owns an arena (mg_comm_alloc) exported by CUDA IPC; neighbours map it and write boundary values directly
- * into its staging area, then publish a sequence number (release, system scope); the owner's consumer kernel waits
- * for it (acquire) and unpacks into the halo part of its level vector.  Expected sequence numbers are
- * *d_seq_base + site, so that a captured V-cycle graph can be replayed (mg_seq_advance at its end). */
-int mg_comm_alloc(int64_t bytes, void **d_ptr_out);
+/* multi-GPU: exchanges between the row blocks of a distributed level over peer-mapped memory (NVLink / NVSwitch).
+ * No reference counterpart (the reference is single-process); the contract is SURVEY.md 8e.
+ *
+ * Every rank owns an ARENA (mg_comm_alloc, exported with CUDA IPC and mapped by its peers):
+ *     [0]    u64 epoch | u32 error | ... | u32 done[MG_MAX_RANKS] at byte 64        (header, 4096 bytes)
+ *     [4096] u64 flags[world][max_sites]          flags[q][s]: written by rank q when its message for site s landed
+ *     [...]  staging[world][2][region_bytes]      data from rank q, double-buffered by epoch parity
+ * A PROGRAM is the launch sequence between mg_comm_begin and mg_comm_end (e.g. one V-cycle; capturable in a CUDA
+ * graph).  Every rank enqueues the same sequence of exchange SITES.  One fused kernel per site: gather the
+ * outgoing values, store them straight into each peer's staging area, publish the epoch into the peer's flag with a
+ * system-scope release store, then spin (acquire) on the own flags and unpack what the peers wrote.  Pushes never
+ * wait, so no ordering of the ranks can deadlock; a wait longer than timeout_s sets the error word instead of hanging.
+ * Peer sets must be symmetric at every site (zero-length messages are fine).  Every program contains at least one
+ * site at which all pairs of ranks talk (mg_comm_end appends an empty one if none occurred): together with the parity
+ * double-buffering this is what makes it safe for a rank to run ahead into the next program.
+ * Several ranks inside ONE process (virtual ranks on one device, used by the tests): CUDA loads kernels lazily and a
+ * first-time load can wait for the device to drain, which never happens while another rank's exchange kernel spins on
+ * a message this thread has yet to launch.  Run every program once with dry_run = 1 (all kernels get loaded, exchanges
+ * neither push nor wait, the epoch stands still) before the first real one. */
+#define MG_MAX_RANKS 8
+typedef struct {
+    int32_t rank, world;
+    int32_t max_sites, dry_run;        /* dry_run != 0: exchanges are launched as no-ops (kernel warm-up, below)  */
+    int64_t region_bytes;              /* staging bytes per (sender, parity)                                     */
+    void *d_arena[MG_MAX_RANKS];       /* every rank's arena as mapped into THIS process ([rank] = the own one)  */
+    double timeout_s;                  /* <= 0: 10 s                                                             */
+    /* running state of the program being enqueued (host side; reset by mg_comm_begin) */
+    int32_t site, all_pairs;           /* all_pairs: an all-ranks site occurred (else mg_comm_end adds a fence)  */
+    int64_t bump_send[MG_MAX_RANKS], bump_recv[MG_MAX_RANKS];
+} mg_comm;
+/* one exchange site: for peer k, send src[d_send_idx[k][i]] (NULL: src[send_off[k]+i]), i < send_cnt[k], and
+ * receive recv_cnt[k] values into dst[d_recv_idx[k][i]] (NULL: dst[recv_off[k]+i]) */
+typedef struct {
+    int32_t npeers, pad_;
+    int32_t peer[MG_MAX_RANKS];
+    const int32_t *d_send_idx[MG_MAX_RANKS];
+    int64_t send_off[MG_MAX_RANKS], send_cnt[MG_MAX_RANKS];
+    const int32_t *d_recv_idx[MG_MAX_RANKS];
+    int64_t recv_off[MG_MAX_RANKS], recv_cnt[MG_MAX_RANKS];
+} mg_xfer;
+int64_t mg_comm_arena_bytes(int32_t world, int32_t max_sites, int64_t region_bytes);
+int mg_comm_alloc(int64_t bytes, void **d_ptr_out);          /* cudaMalloc'ed (IPC needs a whole allocation), zeroed */
 int mg_comm_free(void *d_ptr);
-int mg_comm_export(void *d_ptr, unsigned char *h_handle64);
+int mg_comm_export(void *d_ptr, unsigned char *h_handle64);  /* 64-byte CUDA IPC handle                              */
 int mg_comm_import(const unsigned char *h_handle64, void **d_peer_ptr_out);
 int mg_comm_unmap(void *d_peer_ptr);
-int mg_halo_push(const double *d_src, const int32_t *d_idx, int64_t count, double *d_peer_dst, void *d_peer_flag,
-                 const void *d_seq_base, int64_t site, void *d_done, void *stream);
-int mg_halo_wait_unpack(const void *d_flag, const void *d_seq_base, int64_t site, const double *d_staging,
-                        double *d_dst, int64_t count, void *stream);
-int mg_seq_advance(void *d_seq_base, int64_t delta, void *stream);
+int mg_comm_init(mg_comm *comm, void *stream);               /* epoch = 1, error = 0 in the own arena                */
+int mg_comm_begin(mg_comm *comm);
+int mg_comm_exchange(mg_comm *comm, const mg_xfer *xfer, const double *d_src, double *d_dst, void *stream);
+/* *d_out = sum over ranks of *d_value, added in rank order (identical bits on every rank); d_slots: world doubles */
+int mg_comm_allreduce_sum(mg_comm *comm, const double *d_value, double *d_slots, double *d_out, void *stream);
+int mg_comm_end(mg_comm *comm, void *stream);                /* epoch += 1                                           */
+/* synchronises the stream; *h_error = 0, or 1 + the first site whose wait timed out */
+int mg_comm_error(mg_comm *comm, int32_t *h_error, void *stream);
 /* relabel the columns of a row block: c in [c0,c1) -> d_own_iperm[c-c0] (NULL: c-c0), else n_own + d_slot_of[c] */
 int mg_csr_remap_cols(int64_t nnz, const int32_t *d_cols_in, int64_t c0, int64_t c1, const int32_t *d_own_iperm,
                       int64_t n_own, const int32_t *d_slot_of, int32_t *d_cols_out, int32_t *d_missing, void *stream);
+/* what a distributed level adds to mg_level (mg_level.dist): level vectors are laid out [owned rows | halo] */
+typedef struct {
+    int64_t n_halo;
+    int32_t ncolors, pad_;
+    const mg_xfer *xfer_color;          /* [ncolors] boundary values of one colour (multicolour Gauss-Seidel)       */
+    const mg_xfer *xfer_all;            /* all boundary values                                                      */
+    /* hand-off to the replicated coarse levels (set on the LAST distributed level only): the restriction writes the
+     * owned block of the coarse right-hand side to d_gather_tmp, which is then gathered into every rank's full vector */
+    const mg_xfer *xfer_gather;
+    double *d_gather_tmp;
+    const int32_t *d_gather_self_idx;   /* positions of the own block in the full coarse vector                     */
+    int64_t n_gather_own;
+} mg_dist_level;
 
 /* ------------------------------------------------------------------------------------------------ */
 /* host-side (serial, HOST pointers) setup helpers                                                    */
@@ -262,6 +317,8 @@ typedef struct {
     int32_t coarse_kind;
     const double *d_coarse_inv;       /* MG_COARSE_DENSE: row-major n x n inverse                         */
     const void *coarse_bcr;           /* MG_COARSE_BCR: handle from mg_bcr_create                         */
+    /* row-partitioned level (multi-GPU): n = OWNED rows, vectors hold n + dist->n_halo entries; NULL otherwise */
+    const mg_dist_level *dist;
 } mg_level;
 
 typedef struct {
@@ -274,6 +331,18 @@ typedef struct {
 /* One V-cycle starting on levels[0]: pre-smooth, residual, restrict, recurse / coarsest solve,
  * prolong + correct, post-smooth.  Launches only; capturable in a CUDA graph. */
 int mg_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, void *stream);
+/* The same cycle over a hierarchy whose first levels are row-partitioned across the ranks of `comm` (levels with
+ * mg_level.dist set) and whose remaining levels are replicated.  Enqueues ONE program (mg_comm_begin .. mg_comm_end):
+ * if `norm` is given, first the fused residual + squared 2-norm of level 0 summed over all ranks into *d_norm2 (the
+ * outer loop of Multigrid.solve, Multigrid.py:62-63); then, if `params` is given, the V-cycle. */
+typedef struct {
+    double *d_partials;        /* mg_norm_workspace_size(owned rows) doubles                                */
+    double *d_local;           /* 1 double: this rank's sum of squares                                      */
+    double *d_slots;           /* MG_MAX_RANKS doubles: the other ranks' sums land here                     */
+    double *d_norm2;           /* 1 double: the global sum, identical bits on every rank                    */
+} mg_dist_norm;
+int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_cycle_params *params,
+                   const mg_dist_norm *norm, void *stream);
 /* number of kernels the last mg_vcycle call on this thread launched (bench.py's gpu_launches) */
 int64_t mg_last_launch_count(void);
 

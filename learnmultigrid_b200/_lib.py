@@ -39,6 +39,34 @@ class mg_bcr(ctypes.Structure):
                 ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp)]
 
 
+MG_MAX_RANKS = 8
+
+
+class mg_comm(ctypes.Structure):
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("max_sites", ctypes.c_int32),
+                ("dry_run", ctypes.c_int32), ("region_bytes", c_i64), ("d_arena", c_vp * MG_MAX_RANKS),
+                ("timeout_s", c_dbl), ("site", ctypes.c_int32), ("all_pairs", ctypes.c_int32),
+                ("bump_send", c_i64 * MG_MAX_RANKS), ("bump_recv", c_i64 * MG_MAX_RANKS)]
+
+
+class mg_xfer(ctypes.Structure):
+    _fields_ = [("npeers", ctypes.c_int32), ("pad_", ctypes.c_int32), ("peer", ctypes.c_int32 * MG_MAX_RANKS),
+                ("d_send_idx", c_vp * MG_MAX_RANKS), ("send_off", c_i64 * MG_MAX_RANKS),
+                ("send_cnt", c_i64 * MG_MAX_RANKS), ("d_recv_idx", c_vp * MG_MAX_RANKS),
+                ("recv_off", c_i64 * MG_MAX_RANKS), ("recv_cnt", c_i64 * MG_MAX_RANKS)]
+
+
+class mg_dist_level(ctypes.Structure):
+    _fields_ = [("n_halo", c_i64), ("ncolors", ctypes.c_int32), ("pad_", ctypes.c_int32),
+                ("xfer_color", ctypes.POINTER(mg_xfer)), ("xfer_all", ctypes.POINTER(mg_xfer)),
+                ("xfer_gather", ctypes.POINTER(mg_xfer)), ("d_gather_tmp", c_vp), ("d_gather_self_idx", c_vp),
+                ("n_gather_own", c_i64)]
+
+
+class mg_dist_norm(ctypes.Structure):
+    _fields_ = [("d_partials", c_vp), ("d_local", c_vp), ("d_slots", c_vp), ("d_norm2", c_vp)]
+
+
 class mg_level(ctypes.Structure):
     _fields_ = [("n", c_i64), ("A", mg_sell), ("d_dinv", c_vp),
                 ("ncolors", ctypes.c_int32), ("h_color_ptr", ctypes.POINTER(c_i64)),
@@ -46,7 +74,8 @@ class mg_level(ctypes.Structure):
                 ("d_lex_level_ptr", c_vp), ("d_lex_level_rows", c_vp), ("lex_nlevels", c_i64),
                 ("Q", mg_sell), ("QT", mg_sell),
                 ("d_x", c_vp), ("d_b", c_vp), ("d_r", c_vp), ("d_tmp", c_vp),
-                ("coarse_kind", ctypes.c_int32), ("d_coarse_inv", c_vp), ("coarse_bcr", c_vp)]
+                ("coarse_kind", ctypes.c_int32), ("d_coarse_inv", c_vp), ("coarse_bcr", c_vp),
+                ("dist", ctypes.POINTER(mg_dist_level))]
 
 
 class mg_cycle_params(ctypes.Structure):
@@ -59,6 +88,7 @@ class mg_cycle_params(ctypes.Structure):
 _SIGNATURES = {
     "mg_version": (c_int, []),
     "mg_last_error": (ctypes.c_char_p, []),
+    "mg_struct_size": (c_i64, [c_int]),
     "mg_device_info": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_i64), ctypes.POINTER(c_int)]),
     "mg_spmv_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_residual_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -110,13 +140,19 @@ _SIGNATURES = {
     "mg_comm_export": (c_int, [c_vp, ctypes.c_char_p]),
     "mg_comm_import": (c_int, [ctypes.c_char_p, ctypes.POINTER(c_vp)]),
     "mg_comm_unmap": (c_int, [c_vp]),
-    "mg_halo_push": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
-    "mg_halo_wait_unpack": (c_int, [c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp]),
-    "mg_seq_advance": (c_int, [c_vp, c_i64, c_vp]),
+    "mg_comm_arena_bytes": (c_i64, [ctypes.c_int32, ctypes.c_int32, c_i64]),
+    "mg_comm_init": (c_int, [ctypes.POINTER(mg_comm), c_vp]),
+    "mg_comm_begin": (c_int, [ctypes.POINTER(mg_comm)]),
+    "mg_comm_exchange": (c_int, [ctypes.POINTER(mg_comm), ctypes.POINTER(mg_xfer), c_vp, c_vp, c_vp]),
+    "mg_comm_allreduce_sum": (c_int, [ctypes.POINTER(mg_comm), c_vp, c_vp, c_vp, c_vp]),
+    "mg_comm_end": (c_int, [ctypes.POINTER(mg_comm), c_vp]),
+    "mg_comm_error": (c_int, [ctypes.POINTER(mg_comm), ctypes.POINTER(ctypes.c_int32), c_vp]),
     "mg_csr_remap_cols": (c_int, [c_i64, c_vp, c_i64, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mg_host_greedy_color": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
     "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),
+    "mg_vcycle_dist": (c_int, [ctypes.POINTER(mg_comm), ctypes.POINTER(mg_level), c_int,
+                               ctypes.POINTER(mg_cycle_params), ctypes.POINTER(mg_dist_norm), c_vp]),
     "mg_last_launch_count": (c_i64, []),
     "mg_graph_begin": (c_int, [c_vp]),
     "mg_graph_end": (c_int, [c_vp, ctypes.POINTER(c_vp)]),

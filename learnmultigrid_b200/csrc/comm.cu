@@ -1,15 +1,19 @@
-// comm.cu -- halo exchange between the row blocks of a distributed level over peer-mapped memory (NVLink/NVSwitch).
+// comm.cu -- exchanges between the row blocks of a distributed level over peer-mapped memory (NVLink/NVSwitch).
 //
 // There is no reference counterpart (the reference is single-process); the contract is SURVEY 8e.
-// Mechanism: every rank owns a communication arena allocated with cudaMalloc and exported with CUDA IPC; peers map
-// it and WRITE the boundary values the owner needs straight into its staging area (st.global over NVLink), then
-// publish a sequence number with a system-scope release store.  The owner's consumer kernel spins on its local flag
-// with acquire loads and unpacks the staging area into the halo part of its level vector.  Both kernels are ordinary
-// stream work, so a whole V-cycle including its exchanges is captured in one CUDA graph; the sequence number expected
-// by each exchange site is read from a device counter that the graph advances at its end.
+// Mechanism (arena layout and protocol: include/mgb200.h): every rank owns an arena allocated with cudaMalloc and
+// exported with CUDA IPC; peers map it.  One fused kernel per exchange site gathers the boundary values, WRITES them
+// straight into each peer's staging area (st.global over NVLink), publishes the program's epoch into the peer's
+// flag with a system-scope release store, then spins on its own flags with acquire loads and unpacks what the peers
+// wrote.  It is ordinary stream work, so a whole V-cycle including its exchanges is captured in one CUDA graph; the
+// epoch is a device counter the program advances at its end, staging is double-buffered by epoch parity so a rank
+// that runs ahead into the next program never overwrites data its peer has not consumed yet.
 #include "common.cuh"
 
 namespace mgb {
+
+constexpr int64_t kHeaderBytes = 4096;
+constexpr int kMaxCtasPerPeer = 16;
 
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -19,44 +23,96 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
-// gather src[idx[i]] (idx == NULL: src[i]) into the peer's staging area, then publish seq_base[0] + site.
-// The last CTA to finish (counted in *done, which it resets) performs the release store.
-__global__ void __launch_bounds__(kBlock)
-halo_push_kernel(const double *__restrict__ src, const int32_t *__restrict__ idx, int64_t count,
-                 double *__restrict__ peer_dst, unsigned long long *peer_flag,
-                 const unsigned long long *__restrict__ seq_base, unsigned long long site, unsigned int *done) {
-    const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += stride)
-        peer_dst[i] = idx ? src[idx[i]] : src[i];
+struct ExPeer {
+    const int32_t *send_idx;
+    int64_t send_off, send_cnt;
+    double *peer_stage;                 // in the PEER's arena: where my message lands (parity 0)
+    unsigned long long *peer_flag;      // in the PEER's arena: flags[my rank][site]
+    const double *my_stage;             // in MY arena: where the peer's message lands (parity 0)
+    const unsigned long long *my_flag;  // in MY arena: flags[peer][site]
+    const int32_t *recv_idx;
+    int64_t recv_off, recv_cnt;
+};
+struct ExArgs {
+    int npeers, ctas_per_peer;
+    const double *src;
+    double *dst;
+    const unsigned long long *epoch;
+    unsigned int *done;                 // [MG_MAX_RANKS], zero between kernels
+    unsigned int *err;
+    int64_t parity_stride;              // doubles between the two staging buffers of a region
+    unsigned long long timeout_ns;
+    unsigned int site;
+    int dry;                            // warm-up launch: do nothing
+    ExPeer p[MG_MAX_RANKS];
+};
+
+__global__ void __launch_bounds__(kBlock) exchange_kernel(const ExArgs a) {
+    if (a.dry) return;
+    const int p = blockIdx.x / a.ctas_per_peer, chunk = blockIdx.x % a.ctas_per_peer;
+    const ExPeer &P = a.p[p];
+    const unsigned long long epoch = *a.epoch;
+    const int64_t par = (int64_t)(epoch & 1ull) * a.parity_stride;
+    const int64_t stride = (int64_t)a.ctas_per_peer * kBlock;
+    // ---- push: never waits for anybody
+    double *out = P.peer_stage + par;
+    for (int64_t i = (int64_t)chunk * kBlock + threadIdx.x; i < P.send_cnt; i += stride)
+        out[i] = P.send_idx ? a.src[P.send_idx[i]] : a.src[P.send_off + i];
     __threadfence_system();
     __syncthreads();
+    __shared__ int ok;
     if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(done, 1u);
-        if (prev == gridDim.x - 1) {
-            *done = 0;
+        const unsigned int prev = atomicAdd(a.done + p, 1u);
+        if (prev == (unsigned)a.ctas_per_peer - 1u) {      // last CTA of this peer: everything is written
+            a.done[p] = 0;
             __threadfence_system();
-            st_release_sys(peer_flag, seq_base[0] + site);
+            st_release_sys(P.peer_flag, epoch);
         }
-    }
-}
-
-// wait until *flag >= seq_base[0] + site (written by the peer), then dst[i] = staging[i]
-__global__ void __launch_bounds__(kBlock)
-halo_wait_unpack_kernel(const unsigned long long *flag, const unsigned long long *__restrict__ seq_base,
-                        unsigned long long site, const double *staging, double *__restrict__ dst, int64_t count) {
-    if (threadIdx.x == 0) {
-        const unsigned long long want = seq_base[0] + site;
-        while (ld_acquire_sys(flag) < want) { __nanosleep(64); }
+        // ---- wait for the peer's message of the same site and epoch
+        int good = 1;
+        if (ld_acquire_sys(P.my_flag) < epoch) {
+            const unsigned long long t0 = global_timer_ns();
+            unsigned int spins = 0;
+            while (ld_acquire_sys(P.my_flag) < epoch) {
+                __nanosleep(32);
+                if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { good = 0; break; }
+            }
+        }
+        if (!good) atomicCAS(a.err, 0u, a.site + 1u);
+        ok = good;
     }
     __syncthreads();
-    const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < count; i += stride)
-        dst[i] = __ldcv(staging + i);      // volatile load: never served from a stale L1 line
+    if (!ok) return;
+    const double *in = P.my_stage + par;
+    for (int64_t i = (int64_t)chunk * kBlock + threadIdx.x; i < P.recv_cnt; i += stride) {
+        const double v = __ldcv(in + i);                     // never served from a stale L1 line
+        if (P.recv_idx) a.dst[P.recv_idx[i]] = v;
+        else a.dst[P.recv_off + i] = v;
+    }
 }
 
-__global__ void seq_advance_kernel(unsigned long long *seq_base, unsigned long long delta) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) seq_base[0] += delta;
+__global__ void comm_init_kernel(unsigned long long *hdr) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        hdr[0] = 1ull;
+        ((unsigned int *)hdr)[2] = 0u;
+    }
+}
+__global__ void epoch_advance_kernel(unsigned long long *epoch, unsigned long long delta) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) epoch[0] += delta;
+}
+// out = sum_q (q == rank ? *value : slots[q]) in rank order
+__global__ void sum_slots_kernel(const double *value, const double *slots, int rank, int world, double *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int q = 0; q < world; ++q) s += (q == rank) ? *value : slots[q];
+        *out = s;
+    }
 }
 
 // column relabelling of a row block: global column -> local [owned (permuted) | halo] index through a lookup table:
@@ -79,11 +135,74 @@ remap_cols_table_kernel(int64_t nnz, const int32_t *__restrict__ cols_in, int64_
     }
 }
 
-static inline unsigned small_grid(int64_t n) {
-    int64_t g = (n + kBlock - 1) / kBlock;
-    if (g > 64) g = 64;          // halos are small: a few CTAs keep the barrier cheap
-    if (g < 1) g = 1;
-    return (unsigned)g;
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+static inline int64_t flags_offset() { return kHeaderBytes; }
+static inline int64_t staging_offset(int world, int max_sites) {
+    return align_up(kHeaderBytes + (int64_t)world * max_sites * 8, 4096);
+}
+
+int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, cudaStream_t st) {
+    if (!c || !x) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "null argument");
+    if (c->site >= c->max_sites) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "program has more exchange sites than the arena has flags");
+    const int site = c->site++;
+    if (c->dry_run) {
+        ExArgs a;
+        memset(&a, 0, sizeof(a));
+        a.dry = 1;
+        a.ctas_per_peer = 1;
+        exchange_kernel<<<1, kBlock, 0, st>>>(a);
+        MG_CHECK_LAUNCH("exchange (dry run)");
+        return MG_OK;
+    }
+    if (x->npeers == 0) return MG_OK;
+    if (x->npeers == c->world - 1) c->all_pairs = 1;
+    if (x->npeers < 0 || x->npeers > MG_MAX_RANKS) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "bad peer count");
+    ExArgs a;
+    memset(&a, 0, sizeof(a));
+    char *mine = (char *)c->d_arena[c->rank];
+    a.npeers = x->npeers;
+    a.src = src;
+    a.dst = dst;
+    a.epoch = (const unsigned long long *)mine;
+    a.err = (unsigned int *)(mine + 8);
+    a.done = (unsigned int *)(mine + 64);
+    a.parity_stride = c->region_bytes / 8;
+    a.timeout_ns = (unsigned long long)((c->timeout_s > 0 ? c->timeout_s : 10.0) * 1e9);
+    a.site = (unsigned)site;
+    const int64_t stg = staging_offset(c->world, c->max_sites);
+    int64_t longest = 1;
+    for (int k = 0; k < x->npeers; ++k) {
+        const int q = x->peer[k];
+        if (q < 0 || q >= c->world || q == c->rank || !c->d_arena[q])
+            return set_error(MG_ERR_INVALID, "mg_comm_exchange", "bad peer rank");
+        if (x->send_cnt[k] < 0 || x->recv_cnt[k] < 0) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "negative count");
+        if ((c->bump_send[q] + x->send_cnt[k]) * 8 > c->region_bytes || (c->bump_recv[q] + x->recv_cnt[k]) * 8 > c->region_bytes)
+            return set_error(MG_ERR_INVALID, "mg_comm_exchange", "staging region too small for this program");
+        char *theirs = (char *)c->d_arena[q];
+        ExPeer &P = a.p[k];
+        P.send_idx = x->d_send_idx[k];
+        P.send_off = x->send_off[k];
+        P.send_cnt = x->send_cnt[k];
+        P.peer_stage = (double *)(theirs + stg + (int64_t)c->rank * 2 * c->region_bytes) + c->bump_send[q];
+        P.peer_flag = (unsigned long long *)(theirs + flags_offset()) + (int64_t)c->rank * c->max_sites + site;
+        P.my_stage = (const double *)(mine + stg + (int64_t)q * 2 * c->region_bytes) + c->bump_recv[q];
+        P.my_flag = (const unsigned long long *)(mine + flags_offset()) + (int64_t)q * c->max_sites + site;
+        P.recv_idx = x->d_recv_idx[k];
+        P.recv_off = x->recv_off[k];
+        P.recv_cnt = x->recv_cnt[k];
+        c->bump_send[q] += (x->send_cnt[k] + 15) / 16 * 16;       // keep messages 128-byte aligned
+        c->bump_recv[q] += (x->recv_cnt[k] + 15) / 16 * 16;
+        if (x->send_cnt[k] > longest) longest = x->send_cnt[k];
+        if (x->recv_cnt[k] > longest) longest = x->recv_cnt[k];
+    }
+    int cpp = (int)((longest + 4 * kBlock - 1) / (4 * kBlock));
+    if (cpp > kMaxCtasPerPeer) cpp = kMaxCtasPerPeer;
+    if (cpp < 1) cpp = 1;
+    a.ctas_per_peer = cpp;
+    exchange_kernel<<<(unsigned)(cpp * x->npeers), kBlock, 0, st>>>(a);
+    MG_CHECK_LAUNCH("exchange");
+    return MG_OK;
 }
 
 }  // namespace mgb
@@ -92,11 +211,16 @@ using namespace mgb;
 
 extern "C" {
 
+int64_t mg_comm_arena_bytes(int32_t world, int32_t max_sites, int64_t region_bytes) {
+    if (world < 1 || world > MG_MAX_RANKS || max_sites < 1 || region_bytes < 0 || region_bytes % 128) return -1;
+    return staging_offset(world, max_sites) + (int64_t)world * 2 * region_bytes;
+}
 /* communication arena: cudaMalloc'ed (IPC needs a whole allocation), zero-initialised */
 int mg_comm_alloc(int64_t bytes, void **d_ptr_out) {
     MG_REQUIRE(bytes > 0 && d_ptr_out, "bad argument");
     MG_CHECK_CUDA(cudaMalloc(d_ptr_out, (size_t)bytes));
     MG_CHECK_CUDA(cudaMemset(*d_ptr_out, 0, (size_t)bytes));
+    MG_CHECK_CUDA(cudaDeviceSynchronize());
     return MG_OK;
 }
 int mg_comm_free(void *d_ptr) {
@@ -124,32 +248,62 @@ int mg_comm_unmap(void *d_peer_ptr) {
     if (d_peer_ptr) MG_CHECK_CUDA(cudaIpcCloseMemHandle(d_peer_ptr));
     return MG_OK;
 }
-
-/* peer_dst[i] = src[idx[i]] (idx NULL: src[i]) for i < count, then *peer_flag = *d_seq_base + site (release, system
- * scope).  d_done: one zero-initialised uint32 of scratch per concurrent push. */
-int mg_halo_push(const double *d_src, const int32_t *d_idx, int64_t count, double *d_peer_dst, void *d_peer_flag,
-                 const void *d_seq_base, int64_t site, void *d_done, void *stream) {
-    MG_REQUIRE(count >= 0 && d_peer_flag && d_seq_base && d_done, "null argument");
-    halo_push_kernel<<<small_grid(count), kBlock, 0, (cudaStream_t)stream>>>(
-        d_src, d_idx, count, d_peer_dst, (unsigned long long *)d_peer_flag, (const unsigned long long *)d_seq_base,
-        (unsigned long long)site, (unsigned int *)d_done);
-    MG_CHECK_LAUNCH("halo_push");
+int mg_comm_init(mg_comm *comm, void *stream) {
+    MG_REQUIRE(comm && comm->world >= 1 && comm->world <= MG_MAX_RANKS && comm->rank >= 0 && comm->rank < comm->world &&
+                   comm->d_arena[comm->rank] && comm->max_sites > 0 && comm->region_bytes % 128 == 0, "bad communicator");
+    comm_init_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)comm->d_arena[comm->rank]);
+    MG_CHECK_LAUNCH("comm_init");
+    return mg_comm_begin(comm);
+}
+int mg_comm_begin(mg_comm *comm) {
+    MG_REQUIRE(comm, "null communicator");
+    comm->site = 0;
+    comm->all_pairs = 0;
+    for (int q = 0; q < MG_MAX_RANKS; ++q) comm->bump_send[q] = comm->bump_recv[q] = 0;
     return MG_OK;
 }
-/* spin until *d_flag >= *d_seq_base + site, then d_dst[i] = d_staging[i] */
-int mg_halo_wait_unpack(const void *d_flag, const void *d_seq_base, int64_t site, const double *d_staging,
-                        double *d_dst, int64_t count, void *stream) {
-    MG_REQUIRE(count >= 0 && d_flag && d_seq_base, "null argument");
-    halo_wait_unpack_kernel<<<small_grid(count), kBlock, 0, (cudaStream_t)stream>>>(
-        (const unsigned long long *)d_flag, (const unsigned long long *)d_seq_base, (unsigned long long)site,
-        d_staging, d_dst, count);
-    MG_CHECK_LAUNCH("halo_wait_unpack");
+int mg_comm_exchange(mg_comm *comm, const mg_xfer *xfer, const double *d_src, double *d_dst, void *stream) {
+    return comm_exchange(comm, xfer, d_src, d_dst, (cudaStream_t)stream);
+}
+int mg_comm_allreduce_sum(mg_comm *comm, const double *d_value, double *d_slots, double *d_out, void *stream) {
+    MG_REQUIRE(comm && d_value && d_slots && d_out, "null argument");
+    mg_xfer x;
+    memset(&x, 0, sizeof(x));
+    for (int q = 0; q < comm->world; ++q) {
+        if (q == comm->rank) continue;
+        const int k = x.npeers++;
+        x.peer[k] = q;
+        x.send_cnt[k] = 1;
+        x.recv_off[k] = q;
+        x.recv_cnt[k] = 1;
+    }
+    int rc = comm_exchange(comm, &x, d_value, d_slots, (cudaStream_t)stream);
+    if (rc) return rc;
+    sum_slots_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_value, d_slots, comm->rank, comm->world, d_out);
+    MG_CHECK_LAUNCH("sum_slots");
     return MG_OK;
 }
-int mg_seq_advance(void *d_seq_base, int64_t delta, void *stream) {
-    MG_REQUIRE(d_seq_base, "null argument");
-    seq_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)d_seq_base, (unsigned long long)delta);
-    MG_CHECK_LAUNCH("seq_advance");
+int mg_comm_end(mg_comm *comm, void *stream) {
+    MG_REQUIRE(comm && comm->d_arena[comm->rank], "null communicator");
+    if (!comm->all_pairs && comm->world > 1) {      // fence: an empty all-pairs site (see mgb200.h)
+        mg_xfer x;
+        memset(&x, 0, sizeof(x));
+        for (int q = 0; q < comm->world; ++q)
+            if (q != comm->rank) x.peer[x.npeers++] = q;
+        int rc = comm_exchange(comm, &x, nullptr, nullptr, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    epoch_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)comm->d_arena[comm->rank],
+                                                             comm->dry_run ? 0ull : 1ull);
+    MG_CHECK_LAUNCH("epoch_advance");
+    return MG_OK;
+}
+int mg_comm_error(mg_comm *comm, int32_t *h_error, void *stream) {
+    MG_REQUIRE(comm && h_error && comm->d_arena[comm->rank], "null argument");
+    MG_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    unsigned int e = 0;
+    MG_CHECK_CUDA(cudaMemcpy(&e, (char *)comm->d_arena[comm->rank] + 8, 4, cudaMemcpyDeviceToHost));
+    *h_error = (int32_t)e;
     return MG_OK;
 }
 /* relabel the columns of a row block: c in [c0,c1) -> d_own_iperm[c-c0] (NULL: c-c0), otherwise n_own + d_slot_of[c] */

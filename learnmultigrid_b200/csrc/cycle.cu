@@ -14,6 +14,7 @@ thread_local int64_t g_last_cycle_launches = 0;
 
 int sell_spmv(const mg_sell *, const double *, double *, cudaStream_t);
 int sell_residual(const mg_sell *, const double *, const double *, double *, cudaStream_t);
+int sell_residual_norm2(const mg_sell *, const double *, const double *, double *, double *, cudaStream_t);
 int sell_jacobi(const mg_sell *, const double *, const double *, const double *, double *, double, cudaStream_t);
 int sell_gs_rows(const mg_sell *, double *, const double *, int64_t, int64_t, cudaStream_t);
 int sell_prolong(const mg_sell *, const double *, const double *, double *, cudaStream_t);
@@ -24,6 +25,8 @@ int dense_gemv(int64_t, int64_t, const double *, const double *, double *, cudaS
 int csr_gs_lex(const int32_t *, const int32_t *, const double *, double *, const double *, const int64_t *,
                const int32_t *, int64_t, int64_t, int, cudaStream_t);
 int bcr_solve(const void *handle, const double *rhs, double *x, cudaStream_t st);
+int vec_scatter(int64_t, const int32_t *, const double *, double *, cudaStream_t);
+int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStream_t);
 
 #define MG_TRY(expr)            \
     do {                        \
@@ -31,13 +34,23 @@ int bcr_solve(const void *handle, const double *rhs, double *x, cudaStream_t st)
         if (_rc) return _rc;    \
     } while (0)
 
+// Row-partitioned levels (mg_level.dist != NULL): L.n counts the OWNED rows, the level vectors carry
+// dist->n_halo more entries behind them, and every kernel that changes a vector other ranks read is followed by an
+// exchange of the boundary values.  Invariant: the halo of the iterate is current on entry to and on return from
+// vcycle_rec, and after every smoothing step.
+static inline int64_t vec_len(const mg_level &L) { return L.n + (L.dist ? L.dist->n_halo : 0); }
+static inline int halo_all(mg_comm *comm, const mg_level &L, double *v, cudaStream_t st) {
+    if (!L.dist) return MG_OK;
+    return comm_exchange(comm, L.dist->xfer_all, v, v, st);
+}
+
 // `steps` smoothing sweeps on level L.  cur points at the buffer holding the iterate and is updated
 // (Jacobi ping-pongs between d_x and d_tmp).  zero_guess: the iterate is known to be exactly zero and the
 // buffer has NOT been initialised.
-static int smooth(const mg_level &L, const mg_cycle_params &P, int steps, double **cur, double **alt,
+static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, int steps, double **cur, double **alt,
                   bool zero_guess, cudaStream_t st) {
     if (steps <= 0) {
-        if (zero_guess) MG_TRY(vec_fill(L.n, 0.0, *cur, st));
+        if (zero_guess) MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
         return MG_OK;
     }
     if (P.smoother == MG_SMOOTH_JACOBI) {
@@ -46,27 +59,33 @@ static int smooth(const mg_level &L, const mg_cycle_params &P, int steps, double
             if (P.zero_guess_skip) {
                 // x1 = 0 + omega*(dinv*(b - A*0)) = omega*(dinv*b): same bits as a sweep on zeros, no matrix pass
                 MG_TRY(vec_diag_scale(L.n, P.omega, L.d_dinv, L.d_b, *alt, st));
+                MG_TRY(halo_all(comm, L, *alt, st));
                 double *t = *cur; *cur = *alt; *alt = t;
                 s = 1;
             } else {
-                MG_TRY(vec_fill(L.n, 0.0, *cur, st));
+                MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
             }
         }
         for (; s < steps; ++s) {
             MG_TRY(sell_jacobi(&L.A, L.d_dinv, *cur, L.d_b, *alt, P.omega, st));
+            MG_TRY(halo_all(comm, L, *alt, st));
             double *t = *cur; *cur = *alt; *alt = t;
         }
         return MG_OK;
     }
-    if (zero_guess) MG_TRY(vec_fill(L.n, 0.0, *cur, st));
+    if (zero_guess) MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
     if (P.smoother == MG_SMOOTH_MCGS) {
         if (L.ncolors <= 0 || !L.h_color_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no colouring");
+        if (L.dist && L.dist->ncolors != L.ncolors) return set_error(MG_ERR_INVALID, "mg_vcycle", "halo plan and colouring disagree");
         for (int s = 0; s < steps; ++s)
-            for (int c = 0; c < L.ncolors; ++c)
+            for (int c = 0; c < L.ncolors; ++c) {
                 MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
+                if (L.dist) MG_TRY(comm_exchange(comm, L.dist->xfer_color + c, *cur, *cur, st));
+            }
         return MG_OK;
     }
     if (P.smoother == MG_SMOOTH_LEXGS) {
+        if (L.dist) return set_error(MG_ERR_UNSUPPORTED, "mg_vcycle", "index-order Gauss-Seidel is serial across row blocks; not available on partitioned levels");
         if (!L.d_csr_indptr || !L.d_lex_level_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no lexicographic schedule");
         return csr_gs_lex(L.d_csr_indptr, L.d_csr_indices, L.d_csr_values, *cur, L.d_b, L.d_lex_level_ptr,
                           L.d_lex_level_rows, L.lex_nlevels, L.n, steps, st);
@@ -74,7 +93,8 @@ static int smooth(const mg_level &L, const mg_cycle_params &P, int steps, double
     return set_error(MG_ERR_INVALID, "mg_vcycle", "unknown smoother");
 }
 
-static int vcycle_rec(const mg_level *levels, int nlevels, int l, const mg_cycle_params &P, cudaStream_t st) {
+static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l, const mg_cycle_params &P,
+                      cudaStream_t st) {
     const mg_level &L = levels[l];
     if (l == nlevels - 1) {   // coarsest: direct solve (Multigrid.py:106)
         if (L.coarse_kind == MG_COARSE_DENSE) {
@@ -98,18 +118,54 @@ static int vcycle_rec(const mg_level *levels, int nlevels, int l, const mg_cycle
             else prolong_flip = true;
         }
     }
-    MG_TRY(smooth(L, P, P.nu_pre, &cur, &alt, zero_guess, st));
+    MG_TRY(smooth(comm, L, P, P.nu_pre, &cur, &alt, zero_guess, st));
     MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));              // res = rhs - A u
-    MG_TRY(sell_spmv(&L.QT, L.d_r, C.d_b, st));                      // res_coarse = Q^T res
-    MG_TRY(vcycle_rec(levels, nlevels, l + 1, P, st));               // u_coarse
+    if (L.dist && L.dist->xfer_gather) {
+        // last partitioned level: restrict into the owned block of the coarse rhs, then gather it into every
+        // rank's full vector (the coarse levels below are replicated)
+        const mg_dist_level &D = *L.dist;
+        MG_TRY(halo_all(comm, L, L.d_r, st));
+        MG_TRY(sell_spmv(&L.QT, L.d_r, D.d_gather_tmp, st));         // res_coarse = Q^T res (owned rows)
+        MG_TRY(vec_scatter(D.n_gather_own, D.d_gather_self_idx, D.d_gather_tmp, C.d_b, st));
+        MG_TRY(comm_exchange(comm, D.xfer_gather, D.d_gather_tmp, C.d_b, st));
+    } else {
+        MG_TRY(halo_all(comm, L, L.d_r, st));
+        MG_TRY(sell_spmv(&L.QT, L.d_r, C.d_b, st));                  // res_coarse = Q^T res
+    }
+    MG_TRY(vcycle_rec(comm, levels, nlevels, l + 1, P, st));         // u_coarse
     if (prolong_flip) {
         MG_TRY(sell_prolong(&L.Q, C.d_x, cur, alt, st));             // u = u + Q u_coarse (out of place)
         double *t = cur; cur = alt; alt = t;
     } else {
         MG_TRY(sell_prolong(&L.Q, C.d_x, cur, cur, st));
     }
-    MG_TRY(smooth(L, P, P.nu_post, &cur, &alt, false, st));
-    if (cur != L.d_x) MG_TRY(vec_axpby(L.n, 1.0, cur, 0.0, nullptr, L.d_x, st));   // safety net; not reached
+    MG_TRY(halo_all(comm, L, cur, st));
+    MG_TRY(smooth(comm, L, P, P.nu_post, &cur, &alt, false, st));
+    if (cur != L.d_x) MG_TRY(vec_axpby(vec_len(L), 1.0, cur, 0.0, nullptr, L.d_x, st));   // safety net; not reached
+    return MG_OK;
+}
+
+static int check_levels(const mg_level *levels, int nlevels, const mg_cycle_params *params, bool dist_ok) {
+    MG_REQUIRE(levels && params && nlevels >= 2, "need at least two levels (Multigrid.py:78,102: levels=1 is not handled by the reference either)");
+    MG_REQUIRE(params->nu_pre >= 0 && params->nu_post >= 0, "negative smoothing steps");
+    for (int l = 0; l < nlevels; ++l) {
+        MG_REQUIRE(levels[l].n > 0 && levels[l].d_x && levels[l].d_b, "level vectors missing");
+        MG_REQUIRE(dist_ok || !levels[l].dist, "partitioned level passed to mg_vcycle; use mg_vcycle_dist");
+        if (l + 1 < nlevels) {
+            const mg_level &L = levels[l], &C = levels[l + 1];
+            MG_REQUIRE(L.d_r && L.d_tmp, "level work vectors missing");
+            MG_REQUIRE(!(C.dist && !L.dist), "a partitioned level below a replicated one");
+            const int64_t lenL = L.n + (L.dist ? L.dist->n_halo : 0), lenC = C.n + (C.dist ? C.dist->n_halo : 0);
+            if (L.dist && !C.dist) {
+                MG_REQUIRE(L.dist->xfer_gather && L.dist->d_gather_tmp && L.dist->d_gather_self_idx &&
+                               L.QT.nrows == L.dist->n_gather_own, "last partitioned level has no coarse hand-off");
+            } else {
+                MG_REQUIRE(L.QT.nrows == C.n, "inconsistent level shapes");
+            }
+            MG_REQUIRE(L.A.nrows == L.n && L.A.ncols == lenL && L.Q.nrows == L.n && L.Q.ncols == lenC && L.QT.ncols == lenL,
+                       "inconsistent level shapes");
+        }
+    }
     return MG_OK;
 }
 
@@ -120,6 +176,18 @@ using namespace mgb;
 extern "C" {
 
 int mg_version(void) { return 100; }
+int64_t mg_struct_size(int which) {
+    switch (which) {
+        case 0: return sizeof(mg_sell);
+        case 1: return sizeof(mg_level);
+        case 2: return sizeof(mg_cycle_params);
+        case 3: return sizeof(mg_bcr);
+        case 4: return sizeof(mg_comm);
+        case 5: return sizeof(mg_xfer);
+        case 6: return sizeof(mg_dist_level);
+        default: return -1;
+    }
+}
 const char *mg_last_error(void) { return g_last_error; }
 
 int mg_device_info(int *sm, int64_t *mem, int *cc) {
@@ -134,19 +202,30 @@ int mg_device_info(int *sm, int64_t *mem, int *cc) {
 }
 
 int mg_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, void *stream) {
-    MG_REQUIRE(levels && params && nlevels >= 2, "need at least two levels (Multigrid.py:78,102: levels=1 is not handled by the reference either)");
-    MG_REQUIRE(params->nu_pre >= 0 && params->nu_post >= 0, "negative smoothing steps");
-    for (int l = 0; l < nlevels; ++l) {
-        MG_REQUIRE(levels[l].n > 0 && levels[l].d_x && levels[l].d_b, "level vectors missing");
-        if (l + 1 < nlevels) {
-            MG_REQUIRE(levels[l].d_r && levels[l].d_tmp, "level work vectors missing");
-            MG_REQUIRE(levels[l].A.nrows == levels[l].n && levels[l].Q.nrows == levels[l].n &&
-                           levels[l].QT.nrows == levels[l + 1].n && levels[l].Q.ncols == levels[l + 1].n,
-                       "inconsistent level shapes");
-        }
-    }
+    MG_TRY(check_levels(levels, nlevels, params, false));
     const int64_t before = g_launch_count;
-    int rc = vcycle_rec(levels, nlevels, 0, *params, (cudaStream_t)stream);
+    int rc = vcycle_rec(nullptr, levels, nlevels, 0, *params, (cudaStream_t)stream);
+    g_last_cycle_launches = g_launch_count - before;
+    return rc;
+}
+
+int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_cycle_params *params,
+                   const mg_dist_norm *norm, void *stream) {
+    MG_REQUIRE(comm, "null communicator");
+    MG_REQUIRE(params || norm, "nothing to do");
+    if (params) MG_TRY(check_levels(levels, nlevels, params, true));
+    else MG_REQUIRE(levels && nlevels >= 1, "no level");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t before = g_launch_count;
+    MG_TRY(mg_comm_begin(comm));
+    int rc = MG_OK;
+    if (norm) {   // outer loop of Multigrid.solve (:62-63): ||b - A x||^2 over all row blocks
+        MG_REQUIRE(norm->d_partials && norm->d_local && norm->d_slots && norm->d_norm2, "norm workspace missing");
+        rc = sell_residual_norm2(&levels[0].A, levels[0].d_x, levels[0].d_b, norm->d_partials, norm->d_local, st);
+        if (!rc) rc = mg_comm_allreduce_sum(comm, norm->d_local, norm->d_slots, norm->d_norm2, stream);
+    }
+    if (!rc && params) rc = vcycle_rec(comm, levels, nlevels, 0, *params, st);
+    if (!rc) rc = mg_comm_end(comm, stream);
     g_last_cycle_launches = g_launch_count - before;
     return rc;
 }

@@ -94,6 +94,13 @@ int vec_fill(int64_t n, double v, double *x, cudaStream_t st) {
     return MG_OK;
 }
 
+int vec_scatter(int64_t n, const int32_t *idx, const double *in, double *out, cudaStream_t st) {
+    if (n <= 0) return MG_OK;
+    scatter_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, idx, in, out);
+    MG_CHECK_LAUNCH("scatter");
+    return MG_OK;
+}
+
 }  // namespace mgb
 
 using namespace mgb;
@@ -121,10 +128,7 @@ int mg_gather(int64_t n, const int32_t *d_idx, const double *d_in, double *d_out
 }
 int mg_scatter(int64_t n, const int32_t *d_idx, const double *d_in, double *d_out, void *stream) {
     MG_REQUIRE(n >= 0, "negative size");
-    if (n == 0) return MG_OK;
-    scatter_kernel<<<stream_grid(n), kBlock, 0, (cudaStream_t)stream>>>(n, d_idx, d_in, d_out);
-    MG_CHECK_LAUNCH("scatter");
-    return MG_OK;
+    return vec_scatter(n, d_idx, d_in, d_out, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -161,7 +161,7 @@ class DeviceHierarchy:
         torch, dev = self.torch, self.device
         L = self.nlevels
         for lev in self.levels:
-            n = lev.n
+            n = getattr(lev, "n_vec", lev.n)          # partitioned levels: owned entries + halo
             lev.x = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.b = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.r = torch.zeros(n, dtype=torch.float64, device=dev)
@@ -178,6 +178,8 @@ class DeviceHierarchy:
             s = arr[l]
             s.n = lev.n
             s.d_x, s.d_b, s.d_r, s.d_tmp = (t.data_ptr() for t in (lev.x, lev.b, lev.r, lev.tmp))
+            if getattr(lev, "dist_struct", None) is not None:
+                s.dist = ctypes.pointer(lev.dist_struct)
             if l < L - 1:
                 s.A, s.Q, s.QT = lev.A.struct, lev.Q.struct, lev.QT.struct
                 s.d_dinv = lev.dinv.data_ptr()
@@ -218,7 +220,7 @@ class DeviceHierarchy:
             src = self._pinned
         lev = self.levels[0]
         if lev.perm is None:
-            dst.copy_(src, non_blocking=True)
+            dst[:self.n].copy_(src, non_blocking=True)
         else:
             self._stage.copy_(src, non_blocking=True)
             _lib.check(self.lib.mg_gather(self.n, lev.perm.data_ptr(), self._stage.data_ptr(), dst.data_ptr(),
@@ -230,7 +232,7 @@ class DeviceHierarchy:
         torch = self.torch
         lev = self.levels[0]
         if lev.perm is None:
-            self._pinned.copy_(src, non_blocking=True)
+            self._pinned.copy_(src[:self.n], non_blocking=True)
         else:
             _lib.check(self.lib.mg_scatter(self.n, lev.perm.data_ptr(), src.data_ptr(), self._stage.data_ptr(),
                                            _lib.stream_handle(torch)), "mg_scatter")

@@ -208,13 +208,10 @@ class DeviceSetup:
         return perm, iperm, cptr
 
 
-def setup_device(h, A, Q_list, colors, dense_coarse_max):
-    """Populate `h.levels` of a DeviceHierarchy with device-built data (same contents as the host path)."""
-    from .engine import Level
-    torch, dev = h.torch, h.device
-    S = DeviceSetup(torch, dev)
-    h._setup = S
-    L = h.nlevels
+def build_natural(S, A, Q_list):
+    """Upload A and the transfer operators and form the Galerkin hierarchy in natural ordering on the device.
+    Returns (A_host0, A_nat, Q_nat, QT_nat)."""
+    L = len(Q_list) + 1
     A_host0 = F.canonical_csr(sp.csc_matrix(A))            # Solver.py:18 stores csc_matrix(matrix)
     A_nat = [S.upload(A_host0)]
     Q_nat, QT_nat = [], []
@@ -226,54 +223,80 @@ def setup_device(h, A, Q_list, colors, dense_coarse_max):
         Q_nat.append(Q)
         QT_nat.append(QT)
         A_nat.append(S.galerkin(A_nat[l], Q, QT))
-    # orderings
-    perms, iperms, cptrs = [], [], []
-    h.colors = []
+    return A_host0, A_nat, Q_nat, QT_nat
+
+
+def level_colors(S, smoother, colors, A_host0, A_nat):
+    """Per level: host colour array (or None) for multicolour Gauss-Seidel; the coarsest level is never coloured."""
+    L = len(A_nat)
+    out = []
     for l in range(L):
-        if h.smoother == "mcgs" and l < L - 1:
+        if smoother == "mcgs" and l < L - 1:
             if colors is not None and colors[l] is not None:
                 col = np.ascontiguousarray(colors[l], dtype=np.int32)
             else:
                 pat = A_host0 if l == 0 else F.raw_csr(A_nat[l].indptr.cpu().numpy(), A_nat[l].indices.cpu().numpy(),
                                                        np.zeros(A_nat[l].nnz), A_nat[l].shape)
                 col = F.greedy_colors(pat)[0]
-            p, ip, cp = S.color_perm(col)
-            h.colors.append(col)
+            out.append(col)
+        else:
+            out.append(None)
+    return out
+
+
+def build_replicated_level(h, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, iperms, cptrs, dense_coarse_max):
+    """One level held in full on this GPU (colour-blocked ordering, SELL-32)."""
+    from .engine import Level
+    torch, dev = h.torch, h.device
+    lev = Level()
+    lev.n = A_nat[l].shape[0]
+    lev.perm = perms[l]
+    lev.color_ptr = cptrs[l]
+    lev.nnz_A = A_nat[l].nnz
+    if l < L - 1:
+        Ap = S.permute(A_nat[l], perms[l], iperms[l])
+        lev.A = S.to_sell(Ap)
+        del Ap
+        lev.dinv = S.dinv(A_nat[l], perms[l])
+        Qp = S.permute(Q_nat[l], perms[l], iperms[l + 1])
+        lev.Q = S.to_sell(Qp)
+        del Qp
+        QTp = S.permute(QT_nat[l], perms[l + 1], iperms[l])
+        lev.QT = S.to_sell(QTp)
+        del QTp
+        lev.nnz_Q = Q_nat[l].nnz
+        if h.smoother == "lexgs":
+            lev.csr = (A_nat[l].indptr, A_nat[l].indices, A_nat[l].values)
+            pat = A_host0 if l == 0 else S.download(A_nat[l])
+            lp, lr = F.lex_levels(pat)
+            lev.lex_ptr = torch.from_numpy(lp).to(dev)
+            lev.lex_rows = torch.from_numpy(lr).to(dev)
+            lev.lex_nlevels = len(lp) - 1
+    else:
+        h._coarsest_from_device_csr(lev, A_nat[l], dense_coarse_max)
+    return lev
+
+
+def setup_device(h, A, Q_list, colors, dense_coarse_max):
+    """Populate `h.levels` of a DeviceHierarchy with device-built data (same contents as the host path)."""
+    torch, dev = h.torch, h.device
+    S = DeviceSetup(torch, dev)
+    h._setup = S
+    L = h.nlevels
+    A_host0, A_nat, Q_nat, QT_nat = build_natural(S, A, Q_list)
+    # orderings
+    h.colors = level_colors(S, h.smoother, colors, A_host0, A_nat)
+    perms, iperms, cptrs = [], [], []
+    for l in range(L):
+        if h.colors[l] is not None:
+            p, ip, cp = S.color_perm(h.colors[l])
         else:
             p = ip = cp = None
-            h.colors.append(None)
         perms.append(p)
         iperms.append(ip)
         cptrs.append(cp)
-    h.levels = []
-    for l in range(L):
-        lev = Level()
-        lev.n = A_nat[l].shape[0]
-        lev.perm = perms[l]
-        lev.color_ptr = cptrs[l]
-        lev.nnz_A = A_nat[l].nnz
-        if l < L - 1:
-            Ap = S.permute(A_nat[l], perms[l], iperms[l])
-            lev.A = S.to_sell(Ap)
-            del Ap
-            lev.dinv = S.dinv(A_nat[l], perms[l])
-            Qp = S.permute(Q_nat[l], perms[l], iperms[l + 1])
-            lev.Q = S.to_sell(Qp)
-            del Qp
-            QTp = S.permute(QT_nat[l], perms[l + 1], iperms[l])
-            lev.QT = S.to_sell(QTp)
-            del QTp
-            lev.nnz_Q = Q_nat[l].nnz
-            if h.smoother == "lexgs":
-                lev.csr = (A_nat[l].indptr, A_nat[l].indices, A_nat[l].values)
-                pat = A_host0 if l == 0 else S.download(A_nat[l])
-                lp, lr = F.lex_levels(pat)
-                lev.lex_ptr = torch.from_numpy(lp).to(dev)
-                lev.lex_rows = torch.from_numpy(lr).to(dev)
-                lev.lex_nlevels = len(lp) - 1
-        else:
-            h._coarsest_from_device_csr(lev, A_nat[l], dense_coarse_max)
-        h.levels.append(lev)
+    h.levels = [build_replicated_level(h, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, iperms, cptrs,
+                                       dense_coarse_max) for l in range(L)]
     h.host_A = None
     h.host_Q = None
     if h.keep_host:

@@ -44,6 +44,20 @@ class Multigrid(IterativeSolver):
         self._interp_cache = {}
         self.verbose = False
         self.setup = "device"
+        self.fabric = None           # set by distribute(): run the V-cycle row-partitioned over several GPUs
+        self.dist_options = {}
+
+    def distribute(self, fabric=None, **options):
+        """Row-partition the fine levels over the ranks of `fabric` (default: the torch.distributed world, one
+        process per GPU) -- no reference counterpart, see learnmultigrid_b200/distributed.py.  Every rank must
+        construct the solver with the same global (matrix, rhs, transfers) and make the same calls."""
+        if fabric is None:
+            from ..distributed import TorchFabric
+            fabric = TorchFabric()
+        self.fabric = fabric
+        self.dist_options = dict(options)
+        self._hier = None
+        return self
 
     # ------------------------------------------------------------------------------------------------
     def solve(self, levels=2, smoother="Jacobi", smooth_steps=1, max_iterations=100, error=1e-08,
@@ -173,6 +187,9 @@ class Multigrid(IterativeSolver):
             qs = self._transfer_list(levels, first_call)
         finally:
             self.matrix = save
+        if self.fabric is not None and self.fabric.world > 1:
+            from ..distributed import DistributedHierarchy
+            return DistributedHierarchy(A, qs, self.fabric, smoother=kind, colors=colors, **self.dist_options)
         return DeviceHierarchy(A, qs, smoother=kind, colors=colors, setup=self.setup)
 
     def _hierarchy(self, levels, smoother, gs_order, colors, first_call):

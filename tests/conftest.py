@@ -3,6 +3,9 @@ import sys
 
 import pytest
 
+# virtual-rank tests run several spinning exchange kernels from one process: load all kernels up front
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
