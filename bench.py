@@ -47,6 +47,13 @@ def parse_args():
     ap.add_argument("--setup", default=os.environ.get("MGB_BENCH_SETUP", "device"), choices=["host", "device"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--multi", default=os.environ.get("MGB_BENCH_MULTI", "partitioned"),
+                    choices=["partitioned", "replicas"],
+                    help="N>1: row-partition ONE problem over the GPUs (strong scaling, SURVEY 8e) or run N replicas")
+    ap.add_argument("--colors", default=os.environ.get("MGB_BENCH_COLORS", "structured"), choices=["structured", "greedy"],
+                    help="structured: (ix+iy)%%2 / %%3 colourings of the 5-/7-point operators (linear transfers only); "
+                         "greedy: first-fit on the matrix graph")
+    ap.add_argument("--min-rows-per-rank", type=int, default=int(os.environ.get("MGB_MIN_ROWS", "65536")))
     return ap.parse_args()
 
 
@@ -225,9 +232,17 @@ def run_b200(a):
     t_gen = time.perf_counter() - t0
     mg = SemiGeometricMG(A, rhs, Qs)
     mg.setup = a.setup
+    part = world > 1 and a.multi == "partitioned"
+    if part:
+        mg.distribute(min_rows_per_rank=a.min_rows_per_rank, timeout_s=30.0)
+        mg.local_solution = True
     t0 = time.perf_counter()
     kw = dict(levels=a.levels, smoother=a.smoother, smooth_steps=a.nu, omega=2.0 / 3.0)
-    h = mg._hierarchy(a.levels, a.smoother, "multicolor", None, True)
+    from learnmultigrid_b200 import problems as P
+    colors = None
+    if a.colors == "structured" and a.transfer == "linear" and a.smoother == "GaussSeidel":
+        colors = P.structured_colors_2d(n, a.levels)
+    h = mg._hierarchy(a.levels, a.smoother, "multicolor", colors, True)
     torch.cuda.synchronize()
     t_setup = time.perf_counter() - t0
     params = h.make_params(nu_pre=a.nu, nu_post=a.nu, omega=2.0 / 3.0)
@@ -238,15 +253,19 @@ def run_b200(a):
     lev0 = h.levels[0]
     st = _lib.stream_handle(torch)
 
-    def step():
-        _lib.check(lib.mg_sell_residual_norm2(ctypes.byref(lev0.A.struct), lev0.x.data_ptr(), lev0.b.data_ptr(),
-                                              h._norm_ws.data_ptr(), h._norm_out.data_ptr(), st))
-        h.vcycle(params)
+    if part:
+        def step():                  # one program / one graph: fused residual norm + all-reduce + V-cycle
+            h.vcycle(params, with_norm=True)
+    else:
+        def step():
+            _lib.check(lib.mg_sell_residual_norm2(ctypes.byref(lev0.A.struct), lev0.x.data_ptr(), lev0.b.data_ptr(),
+                                                  h._norm_ws.data_ptr(), h._norm_out.data_ptr(), st))
+            h.vcycle(params)
 
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    launches_per_step = 2 + h.last_launches
+    launches_per_step = h.last_launches if part else 2 + h.last_launches
     h.zero_x()                       # time from a fresh start so the iterate stays meaningful
     torch.cuda.synchronize()
     if world > 1:
@@ -272,9 +291,27 @@ def run_b200(a):
         ms_total = float(t.item())
     ms_step = ms_total / a.steps
     res_after = h.residual_norm()
+    ms_dry = None
+    if part:
+        h.check()                    # no exchange timed out
+        # the same program with its exchange kernels launched as no-ops: kernel time without waiting for peers
+        for _ in range(3):
+            h.vcycle(params, with_norm=True, dry=True)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0.record()
+        for _ in range(a.steps):
+            h.vcycle(params, with_norm=True, dry=True)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / a.steps], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_dry = float(t.item())
+        h.zero_x()
+        dist.barrier()
 
     # ---- dominant kernel: one fine-level smoothing sweep (sell_kernel<GS> per colour / sell_kernel<JACOBI>) ----
-    S = lev0.nnz_A * 12 + 4 * (lev0.n + 1)
+    S = getattr(lev0, "local_nnz_A", lev0.nnz_A) * 12 + 4 * (lev0.n + 1)      # this rank's rows
     sweep_bytes = S + 24 * lev0.n
     reps = 50
     nlaunch = lev0.A.struct.nrows and (len(lev0.color_ptr) - 1 if lev0.color_ptr is not None else 1)
@@ -317,24 +354,33 @@ def run_b200(a):
 
     # ---- end to end through the reference-facing API (host rhs -> solve -> host solution) -----------------------
     e2e = None
-    if not a.no_e2e and rank == 0:
+    if not a.no_e2e and (rank == 0 or part):
         C = a.cycles_per_solve
         pin = torch.from_numpy(np.ascontiguousarray(rhs.reshape(-1))).pin_memory()
         mg.rhs = pin
         mg.pinned_io = True
-        solve_kw = dict(kw, error=0.0, max_iterations=C, gs_order="multicolor")
+        solve_kw = dict(kw, error=0.0, max_iterations=C, gs_order="multicolor", colors=colors)
         mg.solve(**solve_kw)                                     # warm-up (graph already captured)
         reps_e = 3
         torch.cuda.synchronize()
+        if part:
+            dist.barrier()
         t0 = time.perf_counter()
         for _ in range(reps_e):
             mg.solve(**solve_kw)
-            _ = float(mg.solution[ndof // 2, 0])
+            _ = float(mg.solution[mg.solution.shape[0] // 2, 0])
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / reps_e
-        e2e = {"value": ndof * C / dt, "unit": UNIT, "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8 + 8 * C,
+        if part:
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+            h.check()
+        # partitioned: every rank copies its own row block of the rhs in and of the solution out (bytes summed over ranks)
+        e2e = {"value": ndof * C / dt, "unit": UNIT, "h2d_bytes_per_step": ndof * 8, "d2h_bytes_per_step": ndof * 8 + 8 * C * (world if part else 1),
                "cycles_per_solve": C, "ms_per_solve": dt * 1e3,
-               "api": "learnmultigrid_b200.solvers.Multigrid.SemiGeometricMG.solve (pinned host rhs, host solution)"}
+               "api": "learnmultigrid_b200.solvers.Multigrid.SemiGeometricMG.solve (pinned host rhs, host solution"
+                      + ("; each rank moves its own row block)" if part else ")")}
 
     cpu = None
     if not a.no_cpu_baseline and rank == 0:
@@ -347,15 +393,18 @@ def run_b200(a):
                "ms_per_cycle": per * 1e3}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": ndof * world / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
+        line = {"metric": METRIC, "value": ndof * (1 if part else world) / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if part else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(a, n), "l2": "inputs_exceed_l2 (%.1f GB of operators per cycle)"
-                           % (cyc["total"] / 1e9), "setup": a.setup, "levels_rows": [l.n for l in h.levels],
+                           % (cyc["total"] / 1e9), "setup": a.setup, "levels_rows": list(getattr(h, "_global_n", [l.n for l in h.levels])),
                            "levels_nnz": [l.nnz_A for l in h.levels], "colors": [None if l.color_ptr is None else
                                                                               len(l.color_ptr) - 1 for l in h.levels],
                            "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2),
-                           "residual_after_timed_steps": res_after, "parallelism": "replicas" if world > 1 else "single"},
+                           "residual_after_timed_steps": res_after,
+                           "ms_per_step_without_exchange_waits": ms_dry, "parallelism": ("row-partitioned x%d, levels 0..%d partitioned, %d replicated, halo exchange by peer-memory "
+                                           "stores over NVLink inside the cycle graph" % (world, h.n_dist - 1, a.levels - h.n_dist))
+                           if part else ("replicas" if world > 1 else "single")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
                 "clocks": clocks}
         print(json.dumps(line))

@@ -217,14 +217,16 @@ int mg_extract_dinv(int64_t n, const int32_t *d_indptr, const int32_t *d_indices
  * No reference counterpart (the reference is single-process); the contract is SURVEY.md 8e.
  *
  * Every rank owns an ARENA (mg_comm_alloc, exported with CUDA IPC and mapped by its peers):
- *     [0]    u64 epoch | u32 error | ... | u32 done[MG_MAX_RANKS] at byte 64        (header, 4096 bytes)
- *     [4096] u64 flags[world][max_sites]          flags[q][s]: written by rank q when its message for site s landed
- *     [...]  staging[world][2][region_bytes]      data from rank q, double-buffered by epoch parity
+ *     [0]    u64 epoch | u32 error                                                   (header, 4096 bytes)
+ *     [4096] u64 flags[world][max_sites]          flags[q][s]: handshake word of rank q for site s (empty messages)
+ *     [...]  staging[world][2][region_bytes]      packets from rank q, double-buffered by epoch parity
  * A PROGRAM is the launch sequence between mg_comm_begin and mg_comm_end (e.g. one V-cycle; capturable in a CUDA
  * graph).  Every rank enqueues the same sequence of exchange SITES.  One fused kernel per site: gather the
- * outgoing values, store them straight into each peer's staging area, publish the epoch into the peer's flag with a
- * system-scope release store, then spin (acquire) on the own flags and unpack what the peers wrote.  Pushes never
- * wait, so no ordering of the ranks can deadlock; a wait longer than timeout_s sets the error word instead of hanging.
+ * outgoing values and store them straight into each peer's staging area as 16-byte packets (every double split into
+ * two 8-byte words, each carrying 4 data bytes and the epoch as a tag), then poll the own staging area until the
+ * peers' packets carry this program's tag and unpack them.  An aligned 8-byte store is atomic, so no fence and no
+ * separate flag is needed: one NVLink traversal of latency per site.  Pushes never wait, so no ordering of the
+ * ranks can deadlock; a wait longer than timeout_s sets the error word instead of hanging.
  * Peer sets must be symmetric at every site (zero-length messages are fine).  Every program contains at least one
  * site at which all pairs of ranks talk (mg_comm_end appends an empty one if none occurred): together with the parity
  * double-buffering this is what makes it safe for a rank to run ahead into the next program.

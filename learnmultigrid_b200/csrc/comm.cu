@@ -3,9 +3,8 @@
 // There is no reference counterpart (the reference is single-process); the contract is SURVEY 8e.
 // Mechanism (arena layout and protocol: include/mgb200.h): every rank owns an arena allocated with cudaMalloc and
 // exported with CUDA IPC; peers map it.  One fused kernel per exchange site gathers the boundary values, WRITES them
-// straight into each peer's staging area (st.global over NVLink), publishes the program's epoch into the peer's
-// flag with a system-scope release store, then spins on its own flags with acquire loads and unpacks what the peers
-// wrote.  It is ordinary stream work, so a whole V-cycle including its exchanges is captured in one CUDA graph; the
+// straight into each peer's staging area (st.global over NVLink) as self-validating packets tagged with the
+// program's epoch, then polls its own staging area until the peers' packets carry the same tag and unpacks them.  It is ordinary stream work, so a whole V-cycle including its exchanges is captured in one CUDA graph; the
 // epoch is a device counter the program advances at its end, staging is double-buffered by epoch parity so a rank
 // that runs ahead into the next program never overwrites data its peer has not consumed yet.
 #include "common.cuh"
@@ -29,12 +28,17 @@ __device__ __forceinline__ unsigned long long global_timer_ns() {
     return t;
 }
 
+// Wire format ("LL", as in low-latency collectives): every double travels as two 8-byte words, each holding 4 data
+// bytes and the low 32 bits of the program's epoch as a tag.  An aligned 8-byte store lands atomically, so the
+// receiver simply polls each word until its tag matches: no fence, no separate flag, one NVLink traversal of latency.
+// Staging slots written two programs ago (same parity buffer) carry an older tag and can never match.  Messages of
+// length zero still shake hands through the flag word, which keeps the run-ahead argument of mgb200.h intact.
 struct ExPeer {
     const int32_t *send_idx;
     int64_t send_off, send_cnt;
-    double *peer_stage;                 // in the PEER's arena: where my message lands (parity 0)
+    ulonglong2 *peer_stage;             // in the PEER's arena: where my message lands (parity 0)
     unsigned long long *peer_flag;      // in the PEER's arena: flags[my rank][site]
-    const double *my_stage;             // in MY arena: where the peer's message lands (parity 0)
+    const ulonglong2 *my_stage;         // in MY arena: where the peer's message lands (parity 0)
     const unsigned long long *my_flag;  // in MY arena: flags[peer][site]
     const int32_t *recv_idx;
     int64_t recv_off, recv_cnt;
@@ -44,57 +48,75 @@ struct ExArgs {
     const double *src;
     double *dst;
     const unsigned long long *epoch;
-    unsigned int *done;                 // [MG_MAX_RANKS], zero between kernels
     unsigned int *err;
-    int64_t parity_stride;              // doubles between the two staging buffers of a region
+    int64_t parity_stride;              // 16-byte packets between the two staging buffers of a region
     unsigned long long timeout_ns;
     unsigned int site;
     int dry;                            // warm-up launch: do nothing
     ExPeer p[MG_MAX_RANKS];
 };
 
+__device__ __forceinline__ void st_packet(ulonglong2 *p, unsigned long long w0, unsigned long long w1) {
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ld_packet(const ulonglong2 *p, unsigned long long &w0, unsigned long long &w1) {
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __global__ void __launch_bounds__(kBlock) exchange_kernel(const ExArgs a) {
     if (a.dry) return;
     const int p = blockIdx.x / a.ctas_per_peer, chunk = blockIdx.x % a.ctas_per_peer;
     const ExPeer &P = a.p[p];
     const unsigned long long epoch = *a.epoch;
+    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
     const int64_t par = (int64_t)(epoch & 1ull) * a.parity_stride;
     const int64_t stride = (int64_t)a.ctas_per_peer * kBlock;
+    const int64_t first = (int64_t)chunk * kBlock + threadIdx.x;
     // ---- push: never waits for anybody
-    double *out = P.peer_stage + par;
-    for (int64_t i = (int64_t)chunk * kBlock + threadIdx.x; i < P.send_cnt; i += stride)
-        out[i] = P.send_idx ? a.src[P.send_idx[i]] : a.src[P.send_off + i];
-    __threadfence_system();
-    __syncthreads();
-    __shared__ int ok;
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(a.done + p, 1u);
-        if (prev == (unsigned)a.ctas_per_peer - 1u) {      // last CTA of this peer: everything is written
-            a.done[p] = 0;
-            __threadfence_system();
-            st_release_sys(P.peer_flag, epoch);
-        }
-        // ---- wait for the peer's message of the same site and epoch
-        int good = 1;
-        if (ld_acquire_sys(P.my_flag) < epoch) {
+    ulonglong2 *out = P.peer_stage + par;
+    for (int64_t i = first; i < P.send_cnt; i += stride) {
+        const unsigned long long bits =
+            (unsigned long long)__double_as_longlong(P.send_idx ? a.src[P.send_idx[i]] : a.src[P.send_off + i]);
+        st_packet(out + i, (bits & 0xffffffffull) | tag, (bits >> 32) | tag);
+    }
+    if (P.send_cnt == 0 && first == 0) st_relaxed_sys(P.peer_flag, epoch);
+    // ---- receive: poll every packet until both words carry this program's tag
+    const ulonglong2 *in = P.my_stage + par;
+    bool timed_out = false;
+    for (int64_t i = first; i < P.recv_cnt; i += stride) {
+        unsigned long long w0, w1;
+        ld_packet(in + i, w0, w1);
+        if ((w0 & 0xffffffff00000000ull) != tag || (w1 & 0xffffffff00000000ull) != tag) {
             const unsigned long long t0 = global_timer_ns();
             unsigned int spins = 0;
-            while (ld_acquire_sys(P.my_flag) < epoch) {
-                __nanosleep(32);
-                if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { good = 0; break; }
+            for (;;) {
+                ld_packet(in + i, w0, w1);
+                if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
+                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { timed_out = true; break; }
             }
+            if (timed_out) break;
         }
-        if (!good) atomicCAS(a.err, 0u, a.site + 1u);
-        ok = good;
-    }
-    __syncthreads();
-    if (!ok) return;
-    const double *in = P.my_stage + par;
-    for (int64_t i = (int64_t)chunk * kBlock + threadIdx.x; i < P.recv_cnt; i += stride) {
-        const double v = __ldcv(in + i);                     // never served from a stale L1 line
+        const double v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
         if (P.recv_idx) a.dst[P.recv_idx[i]] = v;
         else a.dst[P.recv_off + i] = v;
     }
+    if (P.recv_cnt == 0 && first == 0) {
+        const unsigned long long t0 = global_timer_ns();
+        unsigned int spins = 0;
+        while (ld_relaxed_sys(P.my_flag) < epoch) {
+            __nanosleep(20);
+            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { timed_out = true; break; }
+        }
+    }
+    if (timed_out) atomicCAS(a.err, 0u, a.site + 1u);
 }
 
 __global__ void comm_init_kernel(unsigned long long *hdr) {
@@ -166,8 +188,7 @@ int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, 
     a.dst = dst;
     a.epoch = (const unsigned long long *)mine;
     a.err = (unsigned int *)(mine + 8);
-    a.done = (unsigned int *)(mine + 64);
-    a.parity_stride = c->region_bytes / 8;
+    a.parity_stride = c->region_bytes / 16;
     a.timeout_ns = (unsigned long long)((c->timeout_s > 0 ? c->timeout_s : 10.0) * 1e9);
     a.site = (unsigned)site;
     const int64_t stg = staging_offset(c->world, c->max_sites);
@@ -177,26 +198,26 @@ int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, 
         if (q < 0 || q >= c->world || q == c->rank || !c->d_arena[q])
             return set_error(MG_ERR_INVALID, "mg_comm_exchange", "bad peer rank");
         if (x->send_cnt[k] < 0 || x->recv_cnt[k] < 0) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "negative count");
-        if ((c->bump_send[q] + x->send_cnt[k]) * 8 > c->region_bytes || (c->bump_recv[q] + x->recv_cnt[k]) * 8 > c->region_bytes)
+        if ((c->bump_send[q] + x->send_cnt[k]) * 16 > c->region_bytes || (c->bump_recv[q] + x->recv_cnt[k]) * 16 > c->region_bytes)
             return set_error(MG_ERR_INVALID, "mg_comm_exchange", "staging region too small for this program");
         char *theirs = (char *)c->d_arena[q];
         ExPeer &P = a.p[k];
         P.send_idx = x->d_send_idx[k];
         P.send_off = x->send_off[k];
         P.send_cnt = x->send_cnt[k];
-        P.peer_stage = (double *)(theirs + stg + (int64_t)c->rank * 2 * c->region_bytes) + c->bump_send[q];
+        P.peer_stage = (ulonglong2 *)(theirs + stg + (int64_t)c->rank * 2 * c->region_bytes) + c->bump_send[q];
         P.peer_flag = (unsigned long long *)(theirs + flags_offset()) + (int64_t)c->rank * c->max_sites + site;
-        P.my_stage = (const double *)(mine + stg + (int64_t)q * 2 * c->region_bytes) + c->bump_recv[q];
+        P.my_stage = (const ulonglong2 *)(mine + stg + (int64_t)q * 2 * c->region_bytes) + c->bump_recv[q];
         P.my_flag = (const unsigned long long *)(mine + flags_offset()) + (int64_t)q * c->max_sites + site;
         P.recv_idx = x->d_recv_idx[k];
         P.recv_off = x->recv_off[k];
         P.recv_cnt = x->recv_cnt[k];
-        c->bump_send[q] += (x->send_cnt[k] + 15) / 16 * 16;       // keep messages 128-byte aligned
-        c->bump_recv[q] += (x->recv_cnt[k] + 15) / 16 * 16;
+        c->bump_send[q] += (x->send_cnt[k] + 7) / 8 * 8;          // keep messages 128-byte aligned
+        c->bump_recv[q] += (x->recv_cnt[k] + 7) / 8 * 8;
         if (x->send_cnt[k] > longest) longest = x->send_cnt[k];
         if (x->recv_cnt[k] > longest) longest = x->recv_cnt[k];
     }
-    int cpp = (int)((longest + 4 * kBlock - 1) / (4 * kBlock));
+    int cpp = (int)((longest + 2 * kBlock - 1) / (2 * kBlock));
     if (cpp > kMaxCtasPerPeer) cpp = kMaxCtasPerPeer;
     if (cpp < 1) cpp = 1;
     a.ctas_per_peer = cpp;

@@ -526,9 +526,11 @@ class DistributedHierarchy(DeviceHierarchy):
         parts = self.fabric.allgather(self._from_level0(lev.r).reshape(-1))
         return np.concatenate(parts).reshape(-1, 1)
 
-    def vcycle(self, params, nlevels=None, use_graph=True, with_norm=False):
+    def vcycle(self, params, nlevels=None, use_graph=True, with_norm=False, dry=False):
         """One V-cycle (optionally preceded by the fused residual norm of the outer loop) as one program.  Every
-        rank must make the same call.  Captured into a CUDA graph per parameter set."""
+        rank must make the same call.  Captured into a CUDA graph per parameter set.  dry=True captures the program
+        with its exchanges disabled (results are meaningless; bench.py times it to separate kernel time from
+        exchange time)."""
         torch = self.torch
         if nlevels is not None and int(nlevels) != self.nlevels:
             raise ValueError("a partitioned hierarchy runs all of its levels")
@@ -541,7 +543,8 @@ class DistributedHierarchy(DeviceHierarchy):
                        "mg_vcycle_dist")
             self.last_launches = int(self.lib.mg_last_launch_count())
             return
-        key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip, bool(with_norm))
+        key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip, bool(with_norm),
+               bool(dry))
         g = self._graphs.get(key)
         if g is None:
             cap = torch.cuda.Stream(device=self.device)
@@ -549,7 +552,11 @@ class DistributedHierarchy(DeviceHierarchy):
             with torch.cuda.stream(cap):
                 h = cap.cuda_stream
                 _lib.check(self.lib.mg_graph_begin(h), "mg_graph_begin")
-                rc = self.lib.mg_vcycle_dist(comm, self._level_structs, L, ctypes.byref(params), norm, h)
+                self.comm.struct.dry_run = 1 if dry else 0
+                try:
+                    rc = self.lib.mg_vcycle_dist(comm, self._level_structs, L, ctypes.byref(params), norm, h)
+                finally:
+                    self.comm.struct.dry_run = 0
                 launches = int(self.lib.mg_last_launch_count())
                 out = ctypes.c_void_p()
                 rc2 = self.lib.mg_graph_end(h, ctypes.byref(out))

@@ -130,6 +130,29 @@ def redblack_colors_2d(N):
     return ((ix + iy) % 2).astype(np.int32)
 
 
+def structured_colors_2d(N, levels):
+    """Per-level colourings for the structured hierarchy with LINEAR transfers: red-black (ix+iy)%2 for the 5-point
+    fine operator, (ix+iy)%3 for the 7-point Galerkin operators (stencil offsets (+-1,0), (0,+-1), +-(1,1) never
+    differ by a multiple of 3).  One colour fewer than first-fit greedy on the coarse levels, i.e. one launch and one
+    halo exchange fewer per sweep; the last (coarsest) level is solved directly and gets None."""
+    out = []
+    n = N
+    for l in range(levels - 1):
+        W = n + 1
+        iy, ix = np.divmod(np.arange(W * W), W)
+        out.append(((ix + iy) % (2 if l == 0 else 3)).astype(np.int32))
+        n //= 2
+    out.append(None)
+    return out
+
+
+def coloring_is_valid(A, colors):
+    """no off-diagonal entry of A joins two rows of the same colour"""
+    A = sp.coo_matrix(A)
+    off = A.row != A.col
+    return not np.any(colors[A.row[off]] == colors[A.col[off]])
+
+
 def variable_coefficient(x, y):
     """k(x,y) = 1 + 0.9 sin(2 pi x) sin(2 pi y)  """
     return 1.0 + 0.9 * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y)

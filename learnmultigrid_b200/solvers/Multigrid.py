@@ -93,7 +93,10 @@ class Multigrid(IterativeSolver):
             if self.residual <= error:
                 break
             h.vcycle(params, use_graph=use_graph)                  # :73
-        self.solution = h.get_x(view=getattr(self, "pinned_io", False))
+        if self.fabric is not None and getattr(self, "local_solution", False) and hasattr(h, "get_x_local"):
+            self.solution = h.get_x_local(view=getattr(self, "pinned_io", False))     # this rank's row block only
+        else:
+            self.solution = h.get_x(view=getattr(self, "pinned_io", False))
         self.track_res = track_res
         self._residual_dirty = True
 

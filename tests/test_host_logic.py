@@ -157,3 +157,19 @@ def test_galerkin_pattern_matches_scipy_reference_semantics():
     assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
     assert np.array_equal(got.data, want.data)
     assert np.all(got.data != 0.0)
+
+
+def test_structured_colorings_are_valid_on_the_galerkin_hierarchy():
+    """(ix+iy)%2 on the 5-point fine operator, (ix+iy)%3 on the 7-point Galerkin operators of linear transfers"""
+    import scipy.sparse as sp
+    from learnmultigrid_b200 import problems as P
+    for coef in (None, P.variable_coefficient):
+        N, L = 32, 4
+        A = P.structured_laplacian_2d(N, coef)
+        Qs = P.structured_hierarchy_2d(N, L, transfer="linear")
+        cols = P.structured_colors_2d(N, L)
+        assert cols[-1] is None
+        for l in range(L - 1):
+            assert cols[l].max() == (1 if l == 0 else 2)
+            assert P.coloring_is_valid(A, cols[l]), "level %d" % l
+            A = sp.csr_matrix(Qs[l].T @ A @ Qs[l])
