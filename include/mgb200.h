@@ -35,7 +35,7 @@ typedef enum {
 int mg_version(void);
 const char *mg_last_error(void);
 /* sizeof of the ABI structs as compiled (0 mg_sell, 1 mg_level, 2 mg_cycle_params, 3 mg_bcr, 4 mg_comm, 5 mg_xfer,
- * 6 mg_dist_level): lets a binding verify its own layout */
+ * 6 mg_dist_level, 7 mg_bcr_dist, 8 mg_dist_norm): lets a binding verify its own layout */
 int64_t mg_struct_size(int which);
 /* fills sm_count / total global memory (bytes) / compute capability (e.g. 100) of the current device */
 int mg_device_info(int *sm_count, int64_t *global_mem, int *cc);
@@ -138,15 +138,18 @@ int mg_dense_gemv(int64_t n, int64_t m, const double *d_m, const double *d_x, do
  * (m >= half bandwidth).  The host side forms all factors once with the three setup entry points below and
  * fills an mg_bcr; mg_bcr_solve (also reached from mg_vcycle through mg_level.coarse_bcr) then performs
  * x = A^-1 rhs in 2*nlevels+3 launches that stream the factors once.  Level s has na[s] active blocks;
- * block position p of level s is original block p << s; odd positions are eliminated. */
+ * block position p of level s is original block p << s; odd positions are eliminated.  The reduction stops when
+ * tail_na blocks are left; that small block-tridiagonal system is solved through its dense inverse (one launch
+ * instead of a chain of latency-bound ones). */
 typedef struct {
     int64_t n, n_pad, m, nb;      /* unknowns, padded unknowns (nb*m), block size, number of blocks          */
     int32_t nlevels, pad_;
     const double *d_GL[32], *d_GU[32];   /* per level: [ceil(na/2)][m][m]  f_p -= GL f_{p-1} + GU f_{p+1}     */
     const double *d_Dinv[32], *d_HL[32], *d_HU[32]; /* per level: [na/2][m][m]  x_p = Dinv f_p - HL x_{p-1} - HU x_{p+1} */
     int64_t na[32];
-    const double *d_last_inv;     /* inverse of the single remaining block                                     */
+    const double *d_last_inv;     /* dense inverse of what is left after nlevels reductions: (tail_na*m)^2     */
     double *d_f, *d_x;            /* work vectors, n_pad doubles each                                          */
+    int64_t tail_na;              /* blocks left after the reductions (<= 1: a single block)                   */
 } mg_bcr;
 int mg_bcr_blocks_from_csr(int64_t n, int64_t n_pad, int64_t m, const int32_t *d_indptr, const int32_t *d_indices,
                            const double *d_values, double *d_D, double *d_L, double *d_U, int32_t *d_bad,
@@ -272,6 +275,20 @@ int mg_comm_error(mg_comm *comm, int32_t *h_error, void *stream);
 /* relabel the columns of a row block: c in [c0,c1) -> d_own_iperm[c-c0] (NULL: c-c0), else n_own + d_slot_of[c] */
 int mg_csr_remap_cols(int64_t nnz, const int32_t *d_cols_in, int64_t c0, int64_t c1, const int32_t *d_own_iperm,
                       int64_t n_own, const int32_t *d_slot_of, int32_t *d_cols_out, int32_t *d_missing, void *stream);
+/* Coarsest-level BCR solve with its large steps split over the ranks (the level itself is replicated): rank r
+ * computes the block rows [j0,j1) of a reduction level / the rows [i0,i1) of the dense tail, then all ranks gather
+ * what the others computed (xfer: an all-pairs site with index lists into the padded work vectors).  xfer == NULL:
+ * the step runs replicated.  Same per-row arithmetic as the replicated solve, hence the same bits. */
+typedef struct {
+    int64_t fwd_j0[32], fwd_j1[32];
+    const mg_xfer *fwd_xfer[32];
+    int64_t bwd_j0[32], bwd_j1[32];
+    const mg_xfer *bwd_xfer[32];
+    int64_t tail_i0, tail_i1;
+    const mg_xfer *tail_xfer;
+} mg_bcr_dist;
+int mg_bcr_solve_dist(mg_comm *comm, const mg_bcr *bcr, const mg_bcr_dist *dist, const double *d_rhs, double *d_x,
+                      void *stream);
 /* what a distributed level adds to mg_level (mg_level.dist): level vectors are laid out [owned rows | halo] */
 typedef struct {
     int64_t n_halo;
@@ -321,6 +338,7 @@ typedef struct {
     const void *coarse_bcr;           /* MG_COARSE_BCR: handle from mg_bcr_create                         */
     /* row-partitioned level (multi-GPU): n = OWNED rows, vectors hold n + dist->n_halo entries; NULL otherwise */
     const mg_dist_level *dist;
+    const mg_bcr_dist *coarse_bcr_dist;   /* optional: split the BCR solve over the ranks (mg_vcycle_dist only)      */
 } mg_level;
 
 typedef struct {

@@ -36,7 +36,7 @@ class mg_bcr(ctypes.Structure):
     _fields_ = [("n", c_i64), ("n_pad", c_i64), ("m", c_i64), ("nb", c_i64),
                 ("nlevels", ctypes.c_int32), ("pad_", ctypes.c_int32),
                 ("d_GL", c_vp * 32), ("d_GU", c_vp * 32), ("d_Dinv", c_vp * 32), ("d_HL", c_vp * 32),
-                ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp)]
+                ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp), ("tail_na", c_i64)]
 
 
 MG_MAX_RANKS = 8
@@ -63,6 +63,12 @@ class mg_dist_level(ctypes.Structure):
                 ("n_gather_own", c_i64)]
 
 
+class mg_bcr_dist(ctypes.Structure):
+    _fields_ = [("fwd_j0", c_i64 * 32), ("fwd_j1", c_i64 * 32), ("fwd_xfer", ctypes.POINTER(mg_xfer) * 32),
+                ("bwd_j0", c_i64 * 32), ("bwd_j1", c_i64 * 32), ("bwd_xfer", ctypes.POINTER(mg_xfer) * 32),
+                ("tail_i0", c_i64), ("tail_i1", c_i64), ("tail_xfer", ctypes.POINTER(mg_xfer))]
+
+
 class mg_dist_norm(ctypes.Structure):
     _fields_ = [("d_partials", c_vp), ("d_local", c_vp), ("d_slots", c_vp), ("d_norm2", c_vp)]
 
@@ -75,7 +81,7 @@ class mg_level(ctypes.Structure):
                 ("Q", mg_sell), ("QT", mg_sell),
                 ("d_x", c_vp), ("d_b", c_vp), ("d_r", c_vp), ("d_tmp", c_vp),
                 ("coarse_kind", ctypes.c_int32), ("d_coarse_inv", c_vp), ("coarse_bcr", c_vp),
-                ("dist", ctypes.POINTER(mg_dist_level))]
+                ("dist", ctypes.POINTER(mg_dist_level)), ("coarse_bcr_dist", ctypes.POINTER(mg_bcr_dist))]
 
 
 class mg_cycle_params(ctypes.Structure):
@@ -117,6 +123,8 @@ _SIGNATURES = {
     "mg_dense_inverse_batched": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_vp, c_vp]),
     "mg_dense_gemm_batched": (c_int, [c_i64, c_i64, c_vp, c_i64, c_vp, c_i64, c_vp, c_i64, c_dbl, c_dbl, c_vp]),
     "mg_bcr_solve": (c_int, [ctypes.POINTER(mg_bcr), c_vp, c_vp, c_vp]),
+    "mg_bcr_solve_dist": (c_int, [ctypes.POINTER(mg_comm), ctypes.POINTER(mg_bcr), ctypes.POINTER(mg_bcr_dist), c_vp,
+                                  c_vp, c_vp]),
     "mg_csr_to_dense": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_scan_workspace_size": (c_i64, [c_i64]),
     "mg_exclusive_scan_i32": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),

@@ -38,7 +38,7 @@ class DenseCoarse:
 class BcrCoarse:
     kind = _lib.MG_COARSE_BCR
 
-    def __init__(self, torch, dev, n, ip, ix, va, half_bw, min_block=64):
+    def __init__(self, torch, dev, n, ip, ix, va, half_bw, min_block=64, tail_blocks=16):
         lib = _lib.load()
         st = _lib.stream_handle(torch)
         f64 = torch.float64
@@ -80,7 +80,7 @@ class BcrCoarse:
         self.levels = []
         self.keep = []
         na = nb
-        while na > 1:
+        while na > max(int(tail_blocks), 1):
             nodd, nk = na // 2, (na + 1) // 2
             Dinv = inverse(D.data_ptr() + mm * e, 2 * mm, nodd)
             HL, HU = zeros(nodd), zeros(nodd)
@@ -100,7 +100,26 @@ class BcrCoarse:
             self.levels.append({"na": na, "GL": GL, "GU": GU, "Dinv": Dinv, "HL": HL, "HU": HU})
             D, L, U = Dn, Ln, Un
             na = nk
-        self.last_inv = inverse(D.data_ptr(), mm, 1)
+        self.tail_na = na
+        if na == 1:
+            self.last_inv = inverse(D.data_ptr(), mm, 1)
+        else:
+            # what is left is a small block-tridiagonal system: assemble it densely and invert it once, so that the
+            # solve replaces a chain of latency-bound reduction levels by one matrix-vector product
+            nt = na * m
+            R = torch.zeros(nt, nt, dtype=f64, device=dev)
+            Dv, Lv, Uv = D.view(-1, m, m), L.view(-1, m, m), U.view(-1, m, m)
+            for p in range(na):
+                R[p * m:(p + 1) * m, p * m:(p + 1) * m] = Dv[p]
+                if p >= 1:
+                    R[p * m:(p + 1) * m, (p - 1) * m:p * m] = Lv[p]
+                if p + 1 < na:
+                    R[p * m:(p + 1) * m, (p + 1) * m:(p + 2) * m] = Uv[p]
+            self.last_inv = torch.empty(nt * nt, dtype=f64, device=dev)
+            wk = torch.empty(int(lib.mg_dense_inverse_workspace(nt)), dtype=torch.uint8, device=dev)
+            _lib.check(lib.mg_dense_inverse(nt, R.data_ptr(), self.last_inv.data_ptr(), wk.data_ptr(), st),
+                       "mg_dense_inverse (BCR tail)")
+            del R, wk
         torch.cuda.synchronize()
         if int(sing.item()):
             raise _lib.MgError("BCR: singular diagonal block in the coarsest operator")
@@ -117,9 +136,65 @@ class BcrCoarse:
             h.na[s] = lv["na"]
         h.d_last_inv = self.last_inv.data_ptr()
         h.d_f, h.d_x = self.f.data_ptr(), self.x.data_ptr()
+        h.tail_na = self.tail_na
         self.handle = h
-        self.bytes = sum((2 * ((lv["na"] + 1) // 2) + 3 * (lv["na"] // 2)) * mm * 8 for lv in self.levels) + mm * 8
+        self.bytes = (sum((2 * ((lv["na"] + 1) // 2) + 3 * (lv["na"] // 2)) * mm * 8 for lv in self.levels)
+                      + self.tail_na * self.tail_na * mm * 8)
         self.launches = 2 * len(self.levels) + 3
+        self.torch, self.dev = torch, dev
+        self.dist = None
+
+    def make_dist(self, rank, world, min_blocks=32):
+        """mg_bcr_dist: split the reduction levels with at least `min_blocks` block rows, and the dense tail, over the
+        ranks; each split step is followed by an all-gather (index lists into the padded work vectors)."""
+        torch, dev = self.torch, self.dev
+        m = self.m
+        d = _lib.mg_bcr_dist()
+        self._dist_keep = []
+
+        def offsets(k):
+            return [(k * r) // world for r in range(world + 1)]
+
+        def gather_xfer(pos_of_rank):
+            """all-gather site: rank q contributes the entries pos_of_rank[q] (int64 numpy positions)"""
+            idx = [torch.from_numpy(np.ascontiguousarray(p, dtype=np.int32)).to(dev) for p in pos_of_rank]
+            x = _lib.mg_xfer()
+            for q in range(world):
+                if q == rank:
+                    continue
+                k = x.npeers
+                x.npeers += 1
+                x.peer[k] = q
+                x.d_send_idx[k] = idx[rank].data_ptr() if idx[rank].numel() else None
+                x.send_cnt[k] = idx[rank].numel()
+                x.d_recv_idx[k] = idx[q].data_ptr() if idx[q].numel() else None
+                x.recv_cnt[k] = idx[q].numel()
+            self._dist_keep.append((idx, x))
+            return ctypes.pointer(x)
+
+        ar = np.arange(m, dtype=np.int64)
+        for s, lv in enumerate(self.levels):
+            na = lv["na"]
+            nk, nodd = (na + 1) // 2, na // 2
+            if world > 1 and nk >= min_blocks:
+                o = offsets(nk)
+                d.fwd_j0[s], d.fwd_j1[s] = o[rank], o[rank + 1]
+                d.fwd_xfer[s] = gather_xfer([(((2 * np.arange(o[q], o[q + 1], dtype=np.int64)) << s) * m)[:, None]
+                                             + ar[None, :] for q in range(world)])
+            if world > 1 and nodd >= min_blocks:
+                o = offsets(nodd)
+                d.bwd_j0[s], d.bwd_j1[s] = o[rank], o[rank + 1]
+                d.bwd_xfer[s] = gather_xfer([(((2 * np.arange(o[q], o[q + 1], dtype=np.int64) + 1) << s) * m)[:, None]
+                                             + ar[None, :] for q in range(world)])
+        S = len(self.levels)
+        nt = max(self.tail_na, 1) * m
+        if world > 1 and self.tail_na > 1:
+            o = offsets(nt)
+            d.tail_i0, d.tail_i1 = o[rank], o[rank + 1]
+            rows = [np.arange(o[q], o[q + 1], dtype=np.int64) for q in range(world)]
+            d.tail_xfer = gather_xfer([((i // m) << S) * m + i % m for i in rows])
+        self.dist = d
+        return d
 
     def solve(self, torch, rhs, out):
         _lib.check(_lib.load().mg_bcr_solve(ctypes.byref(self.handle), rhs.data_ptr(), out.data_ptr(),

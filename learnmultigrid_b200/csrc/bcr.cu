@@ -21,6 +21,7 @@ struct BcrHandle {            // mirrors mg_bcr in include/mgb200.h
     int64_t na[32];
     const double *last_inv;
     double *f, *x;
+    int64_t tail_na;          // blocks left after the reductions (0/1: one block); last_inv is (tail_na*m)^2
 };
 
 // ---- setup kernels -------------------------------------------------------------------------------------------
@@ -181,14 +182,14 @@ bcr_load_kernel(int64_t n, int64_t n_pad, const double *__restrict__ b, double *
     if (i < n_pad) f[i] = (i < n) ? b[i] : 0.0;
 }
 
-// level s forward: kept blocks j' (position p = 2j', original block p << s)
+// level s forward: kept blocks j in [j0, j0+nk) (position p = 2j, original block p << s)
 __global__ void __launch_bounds__(kBlock)
-bcr_forward_kernel(int m, int s, int64_t na, int64_t nk, const double *__restrict__ GL,
+bcr_forward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nk, const double *__restrict__ GL,
                    const double *__restrict__ GU, double *f) {
     const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= nk * m) return;
-    const int64_t j = wid / m;
+    const int64_t j = j0 + wid / m;
     const int r = (int)(wid % m);
     const int64_t p = 2 * j;
     double acc = 0.0;
@@ -199,26 +200,32 @@ bcr_forward_kernel(int m, int s, int64_t na, int64_t nk, const double *__restric
     if (lane == 0) f[(p << s) * m + r] -= acc;
 }
 
+// the system left after s reduction levels (tail_na blocks at positions p << s) through its dense inverse:
+// rows [i0, i0+ni) of x_tail = inv * f_tail
 __global__ void __launch_bounds__(kBlock)
-bcr_last_kernel(int m, const double *__restrict__ Dinv, const double *__restrict__ f, double *__restrict__ x) {
+bcr_tail_kernel(int m, int s, int64_t tail_na, int64_t i0, int64_t ni, const double *__restrict__ inv,
+                const double *__restrict__ f, double *__restrict__ x) {
     const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (wid >= m) return;
-    double acc = warp_row_dot(Dinv + wid * (int64_t)m, f, m, lane);
+    if (wid >= ni) return;
+    const int64_t i = i0 + wid;
+    const double *row = inv + i * (tail_na * m);
+    double acc = 0.0;
+    for (int64_t p = 0; p < tail_na; ++p) acc += warp_row_dot(row + p * m, f + (p << s) * m, m, lane);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) x[wid] = acc;
+    if (lane == 0) x[((i / m) << s) * m + i % m] = acc;
 }
 
-// level s backward: eliminated blocks j (position p = 2j+1)
+// level s backward: eliminated blocks j in [j0, j0+nodd) (position p = 2j+1)
 __global__ void __launch_bounds__(kBlock)
-bcr_backward_kernel(int m, int s, int64_t na, int64_t nodd, const double *__restrict__ Dinv,
+bcr_backward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nodd, const double *__restrict__ Dinv,
                     const double *__restrict__ HL, const double *__restrict__ HU, const double *__restrict__ f,
                     double *x) {
     const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= nodd * m) return;
-    const int64_t j = wid / m;
+    const int64_t j = j0 + wid / m;
     const int r = (int)(wid % m);
     const int64_t p = 2 * j + 1;
     const int64_t ro = (j * m + r) * (int64_t)m;
@@ -238,24 +245,58 @@ bcr_store_kernel(int64_t n, const double *__restrict__ x, double *__restrict__ o
 
 static inline unsigned warps_grid(int64_t nwarps) { return (unsigned)((nwarps * 32 + kBlock - 1) / kBlock); }
 
-int bcr_solve(const void *handle, const double *rhs, double *x, cudaStream_t st) {
+int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStream_t);
+
+// x = A^-1 rhs.  With `dist` (and `comm`) the block rows of the large reduction levels and the rows of the dense tail
+// are split over the ranks and every such step is followed by an all-gather of what the ranks computed, so f and x
+// stay complete on every rank; the per-row arithmetic, hence the result, is the same as in the replicated solve.
+int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const double *rhs, double *x,
+              cudaStream_t st) {
     const BcrHandle *H = (const BcrHandle *)handle;
     if (!H || H->m <= 0 || H->nlevels < 0 || H->nlevels > 32) return set_error(MG_ERR_INVALID, "bcr_solve", "bad handle");
+    if (dist && !comm) dist = nullptr;
     const int m = (int)H->m;
     bcr_load_kernel<<<(unsigned)((H->n_pad + kBlock - 1) / kBlock), kBlock, 0, st>>>(H->n, H->n_pad, rhs, H->f);
     MG_CHECK_LAUNCH("bcr_load");
     for (int s = 0; s < H->nlevels; ++s) {
         const int64_t na = H->na[s], nk = (na + 1) / 2;
-        bcr_forward_kernel<<<warps_grid(nk * m), kBlock, 0, st>>>(m, s, na, nk, H->GL[s], H->GU[s], H->f);
-        MG_CHECK_LAUNCH("bcr_forward");
+        const bool split = dist && dist->fwd_xfer[s];
+        const int64_t j0 = split ? dist->fwd_j0[s] : 0, j1 = split ? dist->fwd_j1[s] : nk;
+        if (j1 > j0) {
+            bcr_forward_kernel<<<warps_grid((j1 - j0) * m), kBlock, 0, st>>>(m, s, na, j0, j1 - j0, H->GL[s], H->GU[s], H->f);
+            MG_CHECK_LAUNCH("bcr_forward");
+        }
+        if (split) {
+            int rc = comm_exchange(comm, dist->fwd_xfer[s], H->f, H->f, st);
+            if (rc) return rc;
+        }
     }
-    bcr_last_kernel<<<warps_grid(m), kBlock, 0, st>>>(m, H->last_inv, H->f, H->x);
-    MG_CHECK_LAUNCH("bcr_last");
+    {
+        const int64_t tna = H->tail_na > 1 ? H->tail_na : 1;
+        const bool split = dist && dist->tail_xfer;
+        const int64_t i0 = split ? dist->tail_i0 : 0, i1 = split ? dist->tail_i1 : tna * m;
+        if (i1 > i0) {
+            bcr_tail_kernel<<<warps_grid(i1 - i0), kBlock, 0, st>>>(m, H->nlevels, tna, i0, i1 - i0, H->last_inv, H->f, H->x);
+            MG_CHECK_LAUNCH("bcr_tail");
+        }
+        if (split) {
+            int rc = comm_exchange(comm, dist->tail_xfer, H->x, H->x, st);
+            if (rc) return rc;
+        }
+    }
     for (int s = H->nlevels - 1; s >= 0; --s) {
         const int64_t na = H->na[s], nodd = na / 2;
-        bcr_backward_kernel<<<warps_grid(nodd * m), kBlock, 0, st>>>(m, s, na, nodd, H->Dinv[s], H->HL[s], H->HU[s],
-                                                                      H->f, H->x);
-        MG_CHECK_LAUNCH("bcr_backward");
+        const bool split = dist && dist->bwd_xfer[s];
+        const int64_t j0 = split ? dist->bwd_j0[s] : 0, j1 = split ? dist->bwd_j1[s] : nodd;
+        if (j1 > j0) {
+            bcr_backward_kernel<<<warps_grid((j1 - j0) * m), kBlock, 0, st>>>(m, s, na, j0, j1 - j0, H->Dinv[s], H->HL[s],
+                                                                              H->HU[s], H->f, H->x);
+            MG_CHECK_LAUNCH("bcr_backward");
+        }
+        if (split) {
+            int rc = comm_exchange(comm, dist->bwd_xfer[s], H->x, H->x, st);
+            if (rc) return rc;
+        }
     }
     bcr_store_kernel<<<(unsigned)((H->n + kBlock - 1) / kBlock), kBlock, 0, st>>>(H->n, H->x, x);
     MG_CHECK_LAUNCH("bcr_store");
@@ -306,7 +347,17 @@ int mg_dense_gemm_batched(int64_t m, int64_t batch, const double *d_a, int64_t s
 /* x = A^-1 rhs with the factors of `bcr` (an mg_bcr filled by the host side) */
 int mg_bcr_solve(const mg_bcr *bcr, const double *d_rhs, double *d_x, void *stream) {
     MG_REQUIRE(bcr && d_rhs && d_x, "null argument");
-    return bcr_solve((const void *)bcr, d_rhs, d_x, (cudaStream_t)stream);
+    return bcr_solve((const void *)bcr, nullptr, nullptr, d_rhs, d_x, (cudaStream_t)stream);
+}
+
+/* the same solve with the large steps split over the ranks of `comm` (one program of its own) */
+int mg_bcr_solve_dist(mg_comm *comm, const mg_bcr *bcr, const mg_bcr_dist *dist, const double *d_rhs, double *d_x,
+                      void *stream) {
+    MG_REQUIRE(comm && bcr && dist && d_rhs && d_x, "null argument");
+    int rc = mg_comm_begin(comm);
+    if (!rc) rc = bcr_solve((const void *)bcr, dist, comm, d_rhs, d_x, (cudaStream_t)stream);
+    if (!rc) rc = mg_comm_end(comm, stream);
+    return rc;
 }
 
 }  // extern "C"

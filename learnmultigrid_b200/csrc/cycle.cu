@@ -24,7 +24,7 @@ int vec_diag_scale(int64_t, double, const double *, const double *, double *, cu
 int dense_gemv(int64_t, int64_t, const double *, const double *, double *, cudaStream_t);
 int csr_gs_lex(const int32_t *, const int32_t *, const double *, double *, const double *, const int64_t *,
                const int32_t *, int64_t, int64_t, int, cudaStream_t);
-int bcr_solve(const void *handle, const double *rhs, double *x, cudaStream_t st);
+int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const double *rhs, double *x, cudaStream_t st);
 int vec_scatter(int64_t, const int32_t *, const double *, double *, cudaStream_t);
 int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStream_t);
 
@@ -101,7 +101,7 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
             if (!L.d_coarse_inv) return set_error(MG_ERR_INVALID, "mg_vcycle", "coarsest level has no inverse");
             return dense_gemv(L.n, L.n, L.d_coarse_inv, L.d_b, L.d_x, st);
         }
-        if (L.coarse_kind == MG_COARSE_BCR) return bcr_solve(L.coarse_bcr, L.d_b, L.d_x, st);
+        if (L.coarse_kind == MG_COARSE_BCR) return bcr_solve(L.coarse_bcr, L.coarse_bcr_dist, comm, L.d_b, L.d_x, st);
         return set_error(MG_ERR_INVALID, "mg_vcycle", "unknown coarse solver kind");
     }
     const mg_level &C = levels[l + 1];
@@ -185,6 +185,8 @@ int64_t mg_struct_size(int which) {
         case 4: return sizeof(mg_comm);
         case 5: return sizeof(mg_xfer);
         case 6: return sizeof(mg_dist_level);
+        case 7: return sizeof(mg_bcr_dist);
+        case 8: return sizeof(mg_dist_norm);
         default: return -1;
     }
 }

@@ -190,12 +190,15 @@ class DistributedHierarchy(DeviceHierarchy):
     fabric                      : TorchFabric() (one process per GPU) or a ThreadFabric view (virtual ranks)
     min_rows_per_rank           : levels with fewer rows per rank are replicated (latency-bound anyway)
     n_dist                      : force the number of partitioned levels (1 <= n_dist <= levels-1)
+    split_coarse_solve          : split the large steps of a block-cyclic-reduction coarsest solve over the ranks
     """
 
     def __init__(self, A, Q_list, fabric, smoother="jacobi", colors=None, device=None, min_rows_per_rank=65536,
                  n_dist=None, dense_coarse_max=DENSE_COARSE_MAX, keep_host=False, region_bytes=16 << 20,
-                 max_sites=512, timeout_s=10.0):
+                 max_sites=512, timeout_s=10.0, split_coarse_solve=True, bcr_split_min_blocks=32):
         torch = _lib.require_cuda()
+        self.split_coarse_solve = bool(split_coarse_solve)
+        self.bcr_split_min_blocks = int(bcr_split_min_blocks)
         self.torch = torch
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -389,6 +392,9 @@ class DistributedHierarchy(DeviceHierarchy):
         for l in range(Lp, L):
             self.levels.append(SD.build_replicated_level(self, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, iperms,
                                                          cptrs, dense_coarse_max))
+        last = self.levels[-1]
+        if last.coarse_kind == _lib.MG_COARSE_BCR and self.split_coarse_solve:
+            last.coarse_bcr_dist = last.coarse.make_dist(rank, W, self.bcr_split_min_blocks)
         self.host_A = None
         self.host_Q = None
         if self.keep_host:

@@ -199,6 +199,8 @@ class DeviceHierarchy:
                     s.d_coarse_inv = lev.coarse_inv.data_ptr()
                 else:
                     s.coarse_bcr = lev.coarse_bcr
+                    if getattr(lev, "coarse_bcr_dist", None) is not None:
+                        s.coarse_bcr_dist = ctypes.pointer(lev.coarse_bcr_dist)
         self._level_structs = arr
 
     # ------------------------------------------------------------------------------------------------

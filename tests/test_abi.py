@@ -38,7 +38,7 @@ def test_struct_layouts_match_header_sizes():
     assert ctypes.sizeof(_lib.mg_level) % 8 == 0
     lib = _lib.load()
     for which, st in enumerate((_lib.mg_sell, _lib.mg_level, _lib.mg_cycle_params, _lib.mg_bcr, _lib.mg_comm,
-                                _lib.mg_xfer, _lib.mg_dist_level)):
+                                _lib.mg_xfer, _lib.mg_dist_level, _lib.mg_bcr_dist, _lib.mg_dist_norm)):
         assert lib.mg_struct_size(which) == ctypes.sizeof(st), st.__name__
 
 

@@ -171,6 +171,98 @@ def test_partitioned_quasi_l2_wide_halos_and_eager_mode(torch_mod):
         np.testing.assert_allclose(norms, norms1, rtol=1e-12)
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_split_bcr_coarse_solve_is_bit_identical(torch_mod, world):
+    """block cyclic reduction with its reduction levels and dense tail split over the ranks + all-gathers"""
+    import scipy.sparse as sp
+    torch = torch_mod
+    from learnmultigrid_b200 import _lib, problems as P, formats as F, setup_device as SD
+    from learnmultigrid_b200.coarse import BcrCoarse, half_bandwidth
+    from learnmultigrid_b200.distributed import PeerComm, run_virtual_ranks
+    lib = _lib.load()
+    A = P.structured_laplacian_2d(80)
+    Q = P.structured_hierarchy_2d(80, 2, transfer="linear")[0]
+    Ac = F.canonical_csr(sp.csr_matrix(Q.T @ sp.csc_matrix(A) @ Q))
+    n = Ac.shape[0]
+    bw = half_bandwidth(Ac.indptr, Ac.indices)
+    rhs = np.random.default_rng(1).standard_normal(n)
+
+    def body(fab):
+        dev = torch.device("cuda", 0)
+        S = SD.DeviceSetup(torch, dev)
+        Ad = S.upload(Ac)
+        bcr = BcrCoarse(torch, dev, n, Ad.indptr, Ad.indices, Ad.values, bw, min_block=1, tail_blocks=5)
+        d = bcr.make_dist(fab.rank, fab.world, min_blocks=4)
+        assert sum(1 for s in range(32) if d.fwd_xfer[s]) >= 2 and d.tail_xfer
+        comm = PeerComm(fab, torch, region_bytes=1 << 20, max_sites=64, timeout_s=30.0)
+        d_rhs = torch.from_numpy(rhs).to(dev)
+        x_rep = torch.zeros(n, dtype=torch.float64, device=dev)
+        x_split = torch.zeros(n, dtype=torch.float64, device=dev)
+        st = _lib.stream_handle(torch)
+        _lib.check(lib.mg_bcr_solve(ctypes.byref(bcr.handle), d_rhs.data_ptr(), x_rep.data_ptr(), st))
+        comm.struct.dry_run = 1                     # load the kernels before anybody spins (mgb200.h, mg_comm)
+        _lib.check(lib.mg_bcr_solve_dist(ctypes.byref(comm.struct), ctypes.byref(bcr.handle), ctypes.byref(d),
+                                         d_rhs.data_ptr(), x_split.data_ptr(), st))
+        comm.struct.dry_run = 0
+        torch.cuda.current_stream().synchronize()
+        fab.barrier()
+        for _ in range(3):
+            x_split.zero_()
+            _lib.check(lib.mg_bcr_solve_dist(ctypes.byref(comm.struct), ctypes.byref(bcr.handle), ctypes.byref(d),
+                                             d_rhs.data_ptr(), x_split.data_ptr(), st))
+            torch.cuda.current_stream().synchronize()
+            assert torch.equal(x_rep, x_split)
+        comm.check()
+        out = x_split.cpu().numpy()
+        comm.close()
+        return out
+
+    res = run_virtual_ranks(world, body)
+    from scipy.sparse.linalg import spsolve
+    want = spsolve(sp.csc_matrix(Ac), rhs)
+    for got in res:
+        np.testing.assert_allclose(got, want, rtol=0, atol=1e-11 * np.linalg.norm(want))
+
+
+def test_partitioned_cycle_with_split_bcr_coarsest_level(torch_mod):
+    from learnmultigrid_b200 import problems as P
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
+    N = 64
+    A = P.structured_laplacian_2d(N)
+    Qs = P.structured_hierarchy_2d(N, 2, transfer="linear")          # coarsest = 33^2 = 1089 unknowns -> BCR
+    rng = np.random.default_rng(0)
+    b, x0 = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+    h1 = DeviceHierarchy(A, Qs, smoother="mcgs", dense_coarse_max=500)
+    assert h1.levels[-1].coarse_kind == 1
+    h1.set_rhs(b)
+    h1.set_x(x0)
+    p1 = h1.make_params(nu_pre=1, nu_post=1)
+    want = []
+    for _ in range(3):
+        h1.vcycle(p1)
+        want.append(h1.get_x().copy())
+
+    def body(fab):
+        h = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h1.colors, n_dist=1, dense_coarse_max=500,
+                                 bcr_split_min_blocks=2, region_bytes=1 << 20, timeout_s=30.0)
+        assert h.levels[-1].coarse_bcr_dist is not None
+        h.set_rhs(b)
+        h.set_x(x0)
+        p = h.make_params(nu_pre=1, nu_post=1)
+        got = []
+        for _ in range(3):
+            h.vcycle(p)
+            got.append(h.get_x().copy())
+        h.check()
+        h.close()
+        return got
+
+    for got in run_virtual_ranks(3, body):
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+
+
 def test_partitioned_api_solve_matches_oracle_history(torch_mod):
     """SemiGeometricMG.solve on a partitioned hierarchy: same iteration count and history as the CPU oracle"""
     from learnmultigrid_b200 import problems as P

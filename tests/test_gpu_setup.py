@@ -204,9 +204,9 @@ def test_bcr_solver_matches_direct_solve(S, N, transfer):
     n = Ac.shape[0]
     bw = half_bandwidth(Ac.indptr, Ac.indices)
     Ad = S.upload(Ac)
-    for min_block in (1, 64):
-        bcr = BcrCoarse(S.torch, S.dev, n, Ad.indptr, Ad.indices, Ad.values, bw, min_block=min_block)
-        assert bcr.nb >= 4
+    for min_block, tail in ((1, 1), (1, 5), (1, 16), (64, 1), (64, 16)):
+        bcr = BcrCoarse(S.torch, S.dev, n, Ad.indptr, Ad.indices, Ad.values, bw, min_block=min_block, tail_blocks=tail)
+        assert bcr.nb >= 4 and 1 <= bcr.tail_na <= max(tail, 1)
         rng = np.random.default_rng(3)
         rhs = rng.standard_normal(n)
         d_rhs = S.torch.from_numpy(rhs).to(S.dev)
