@@ -47,10 +47,12 @@ def parse_args():
     ap.add_argument("--setup", default=os.environ.get("MGB_BENCH_SETUP", "device"), choices=["host", "device"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="bracket ONE extra step with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--multi", default=os.environ.get("MGB_BENCH_MULTI", "partitioned"),
                     choices=["partitioned", "replicas"],
                     help="N>1: row-partition ONE problem over the GPUs (strong scaling, SURVEY 8e) or run N replicas")
-    ap.add_argument("--colors", default=os.environ.get("MGB_BENCH_COLORS", "structured"), choices=["structured", "greedy"],
+    ap.add_argument("--colors", default=os.environ.get("MGB_BENCH_COLORS", "greedy"), choices=["structured", "greedy"],
                     help="structured: (ix+iy)%%2 / %%3 colourings of the 5-/7-point operators (linear transfers only); "
                          "greedy: first-fit on the matrix graph")
     ap.add_argument("--min-rows-per-rank", type=int, default=int(os.environ.get("MGB_MIN_ROWS", "65536")))
@@ -290,6 +292,12 @@ def run_b200(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_step = ms_total / a.steps
+    if a.profile_step:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.start()
+        step()
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     res_after = h.residual_norm()
     ms_dry = None
     if part:

@@ -150,6 +150,7 @@ typedef struct {
     const double *d_last_inv;     /* dense inverse of what is left after nlevels reductions: (tail_na*m)^2     */
     double *d_f, *d_x;            /* work vectors, n_pad doubles each                                          */
     int64_t tail_na;              /* blocks left after the reductions (<= 1: a single block)                   */
+    double *d_tail;               /* work vector, max(tail_na,1)*m doubles                                     */
 } mg_bcr;
 int mg_bcr_blocks_from_csr(int64_t n, int64_t n_pad, int64_t m, const int32_t *d_indptr, const int32_t *d_indices,
                            const double *d_values, double *d_D, double *d_L, double *d_U, int32_t *d_bad,

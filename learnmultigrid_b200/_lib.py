@@ -36,7 +36,7 @@ class mg_bcr(ctypes.Structure):
     _fields_ = [("n", c_i64), ("n_pad", c_i64), ("m", c_i64), ("nb", c_i64),
                 ("nlevels", ctypes.c_int32), ("pad_", ctypes.c_int32),
                 ("d_GL", c_vp * 32), ("d_GU", c_vp * 32), ("d_Dinv", c_vp * 32), ("d_HL", c_vp * 32),
-                ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp), ("tail_na", c_i64)]
+                ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp), ("tail_na", c_i64), ("d_tail", c_vp)]
 
 
 MG_MAX_RANKS = 8

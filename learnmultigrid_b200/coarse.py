@@ -137,6 +137,8 @@ class BcrCoarse:
         h.d_last_inv = self.last_inv.data_ptr()
         h.d_f, h.d_x = self.f.data_ptr(), self.x.data_ptr()
         h.tail_na = self.tail_na
+        self.tail = torch.zeros(max(self.tail_na, 1) * m, dtype=f64, device=dev)
+        h.d_tail = self.tail.data_ptr()
         self.handle = h
         self.bytes = (sum((2 * ((lv["na"] + 1) // 2) + 3 * (lv["na"] // 2)) * mm * 8 for lv in self.levels)
                       + self.tail_na * self.tail_na * mm * 8)

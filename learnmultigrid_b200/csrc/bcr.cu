@@ -22,6 +22,7 @@ struct BcrHandle {            // mirrors mg_bcr in include/mgb200.h
     const double *last_inv;
     double *f, *x;
     int64_t tail_na;          // blocks left after the reductions (0/1: one block); last_inv is (tail_na*m)^2
+    double *tail;             // tail_na*m doubles: contiguous right-hand side of the tail system
 };
 
 // ---- setup kernels -------------------------------------------------------------------------------------------
@@ -200,21 +201,12 @@ bcr_forward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nk, const doubl
     if (lane == 0) f[(p << s) * m + r] -= acc;
 }
 
-// the system left after s reduction levels (tail_na blocks at positions p << s) through its dense inverse:
-// rows [i0, i0+ni) of x_tail = inv * f_tail
+// the system left after s reduction levels (tail_na blocks at positions p << s): gather its right-hand side into a
+// contiguous vector; the dense inverse is then applied by gemv_rows (dense_kernels.cu), which scatters the result back
 __global__ void __launch_bounds__(kBlock)
-bcr_tail_kernel(int m, int s, int64_t tail_na, int64_t i0, int64_t ni, const double *__restrict__ inv,
-                const double *__restrict__ f, double *__restrict__ x) {
-    const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wid >= ni) return;
-    const int64_t i = i0 + wid;
-    const double *row = inv + i * (tail_na * m);
-    double acc = 0.0;
-    for (int64_t p = 0; p < tail_na; ++p) acc += warp_row_dot(row + p * m, f + (p << s) * m, m, lane);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) x[((i / m) << s) * m + i % m] = acc;
+bcr_tail_gather_kernel(int m, int s, int64_t nt, const double *__restrict__ f, double *__restrict__ g) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < nt) g[i] = f[((i / m) << s) * m + i % m];
 }
 
 // level s backward: eliminated blocks j in [j0, j0+nodd) (position p = 2j+1)
@@ -246,6 +238,8 @@ bcr_store_kernel(int64_t n, const double *__restrict__ x, double *__restrict__ o
 static inline unsigned warps_grid(int64_t nwarps) { return (unsigned)((nwarps * 32 + kBlock - 1) / kBlock); }
 
 int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStream_t);
+int gemv_rows(int64_t total_rows, int64_t row0, int64_t nrows, int64_t m, const double *M, const double *x, double *y,
+              int64_t bm, int shift, cudaStream_t st);
 
 // x = A^-1 rhs.  With `dist` (and `comm`) the block rows of the large reduction levels and the rows of the dense tail
 // are split over the ranks and every such step is followed by an all-gather of what the ranks computed, so f and x
@@ -275,10 +269,12 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
         const int64_t tna = H->tail_na > 1 ? H->tail_na : 1;
         const bool split = dist && dist->tail_xfer;
         const int64_t i0 = split ? dist->tail_i0 : 0, i1 = split ? dist->tail_i1 : tna * m;
-        if (i1 > i0) {
-            bcr_tail_kernel<<<warps_grid(i1 - i0), kBlock, 0, st>>>(m, H->nlevels, tna, i0, i1 - i0, H->last_inv, H->f, H->x);
-            MG_CHECK_LAUNCH("bcr_tail");
-        }
+        if (!H->tail) return set_error(MG_ERR_INVALID, "bcr_solve", "handle has no tail work vector");
+        const int64_t nt = tna * m;
+        bcr_tail_gather_kernel<<<(unsigned)((nt + kBlock - 1) / kBlock), kBlock, 0, st>>>(m, H->nlevels, nt, H->f, H->tail);
+        MG_CHECK_LAUNCH("bcr_tail_gather");
+        int rc = gemv_rows(nt, i0, i1 - i0, nt, H->last_inv, H->tail, H->x, m, H->nlevels, st);
+        if (rc) return rc;
         if (split) {
             int rc = comm_exchange(comm, dist->tail_xfer, H->x, H->x, st);
             if (rc) return rc;

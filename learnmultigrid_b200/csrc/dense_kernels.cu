@@ -108,19 +108,48 @@ build_augmented_kernel(int64_t n, const double *__restrict__ A, double *__restri
         W[r * 2 * n + c] = (c < n) ? A[r * n + c] : ((c - n == r) ? 1.0 : 0.0);
 }
 
-// y = M x, M row-major n x m: one warp per row, lanes stride the row (coalesced), fixed-order tree sum
+// y = M x for the rows [row0, row0+nrows) of a row-major matrix with m columns.  T threads share a row (kBlock/T rows
+// per CTA), each keeps four independent loads in flight; partial sums are combined in a fixed order (four
+// accumulators, warp tree, then the row's warps in order), so the result depends on T only.  The output index of
+// row i is i, or ((i / bm) << shift) * bm + i % bm when bm > 0 (block-strided vectors of the BCR tail solve).
+template <int T>
 __global__ void __launch_bounds__(kBlock)
-dense_gemv_kernel(int64_t n, int64_t m, const double *__restrict__ M, const double *__restrict__ x,
-                  double *__restrict__ y) {
-    const int64_t row = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (row >= n) return;
-    const double *mr = M + row * m;
-    double s = 0.0;
-    for (int64_t c = lane; c < m; c += 32) s += mr[c] * x[c];
+gemv_rows_kernel(int64_t row0, int64_t nrows, int64_t m, const double *__restrict__ M, const double *__restrict__ x,
+                 double *__restrict__ y, int64_t bm, int shift) {
+    constexpr int RPC = kBlock / T;
+    __shared__ double part[kBlock / 32];
+    const int sub = threadIdx.x / T, t = threadIdx.x % T;
+    const int64_t r = (int64_t)blockIdx.x * RPC + sub;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (r < nrows) {
+        const double *mr = M + (row0 + r) * m;
+        int64_t c = t;
+        for (; c + 3 * T < m; c += 4 * T) {
+            const double v0 = __ldcs(mr + c), v1 = __ldcs(mr + c + T), v2 = __ldcs(mr + c + 2 * T),
+                         v3 = __ldcs(mr + c + 3 * T);
+            a0 += v0 * x[c];
+            a1 += v1 * x[c + T];
+            a2 += v2 * x[c + 2 * T];
+            a3 += v3 * x[c + 3 * T];
+        }
+        for (; c < m; c += T) a0 += __ldcs(mr + c) * x[c];
+    }
+    double s = (a0 + a1) + (a2 + a3);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if (lane == 0) y[row] = s;
+    if (T > 32) {
+        const int w = threadIdx.x >> 5;
+        if ((threadIdx.x & 31) == 0) part[w] = s;
+        __syncthreads();
+        if (t == 0) {
+            s = 0.0;
+            for (int k = 0; k < T / 32; ++k) s += part[sub * (T / 32) + k];
+        }
+    }
+    if (t == 0 && r < nrows) {
+        const int64_t i = row0 + r;
+        y[bm > 0 ? ((i / bm) << shift) * bm + i % bm : i] = s;
+    }
 }
 
 __global__ void __launch_bounds__(kBlock)
@@ -131,12 +160,24 @@ csr_to_dense_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32_t
     for (int32_t p = indptr[row]; p < indptr[row + 1]; ++p) D[row * n + indices[p]] += values[p];
 }
 
-int dense_gemv(int64_t n, int64_t m, const double *M, const double *x, double *y, cudaStream_t st) {
-    if (n <= 0) return MG_OK;
-    const int64_t grid = (n * 32 + kBlock - 1) / kBlock;
-    dense_gemv_kernel<<<(unsigned)grid, kBlock, 0, st>>>(n, m, M, x, y);
-    MG_CHECK_LAUNCH("dense_gemv");
+// rows [row0,row0+nrows) of y = M x; `total_rows` (the whole matrix) picks the threads per row, so that a row block
+// computed on its own (split solve) gets the same bits as in the full product
+int gemv_rows(int64_t total_rows, int64_t row0, int64_t nrows, int64_t m, const double *M, const double *x, double *y,
+              int64_t bm, int shift, cudaStream_t st) {
+    if (nrows <= 0) return MG_OK;
+    const int64_t want = (int64_t)sm_count() * 2048;          // threads that fill the device
+    const int T = (total_rows * 32 >= want) ? 32 : (total_rows * 128 >= want) ? 128 : 256;
+    const int64_t rpc = kBlock / T;
+    const unsigned grid = (unsigned)((nrows + rpc - 1) / rpc);
+    if (T == 32) gemv_rows_kernel<32><<<grid, kBlock, 0, st>>>(row0, nrows, m, M, x, y, bm, shift);
+    else if (T == 128) gemv_rows_kernel<128><<<grid, kBlock, 0, st>>>(row0, nrows, m, M, x, y, bm, shift);
+    else gemv_rows_kernel<256><<<grid, kBlock, 0, st>>>(row0, nrows, m, M, x, y, bm, shift);
+    MG_CHECK_LAUNCH("gemv_rows");
     return MG_OK;
+}
+
+int dense_gemv(int64_t n, int64_t m, const double *M, const double *x, double *y, cudaStream_t st) {
+    return gemv_rows(n, 0, n, m, M, x, y, 0, 0, st);
 }
 
 }  // namespace mgb
