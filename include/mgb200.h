@@ -37,6 +37,10 @@ const char *mg_last_error(void);
 /* sizeof of the ABI structs as compiled (0 mg_sell, 1 mg_level, 2 mg_cycle_params, 3 mg_bcr, 4 mg_comm, 5 mg_xfer,
  * 6 mg_dist_level, 7 mg_bcr_dist, 8 mg_dist_norm): lets a binding verify its own layout */
 int64_t mg_struct_size(int which);
+/* 1 (default): the kernels of the cycle are launched with programmatic stream serialization (each kernel waits for
+ * its predecessor with griddepcontrol.wait and lets its successor be scheduled early); 0: plain stream order.
+ * Affects launches (and graph captures) made afterwards; returns the previous setting.  Results are identical. */
+int mg_set_pdl(int enabled);
 /* fills sm_count / total global memory (bytes) / compute capability (e.g. 100) of the current device */
 int mg_device_info(int *sm_count, int64_t *global_mem, int *cc);
 
@@ -106,6 +110,10 @@ int64_t mg_norm_workspace_size(int64_t n);
 /* launches that cover at least `rows` rows use the bulk-async (TMA) staged kernel; 0 = never.  Returns the
  * previous threshold (default 65536).  Both kernels give bit-identical results. */
 int64_t mg_set_tma_min_rows(int64_t rows);
+/* matrices whose longest slice has at least `len` entries per row (and at most 64) run the four-warps-per-slice
+ * kernel: loads of a row spread over four warps, products added in storage order (same bits); 0 = never.  Returns
+ * the previous threshold (default 9: the 19- and 37-point Galerkin stencils of quasi-L2 transfers). */
+int64_t mg_set_wide_min_len(int64_t len);
 /* x_out = x + omega*(dinv*(b - A x)) */
 int mg_sell_jacobi(const mg_sell *A, const double *d_dinv, const double *d_x, const double *d_b,
                    double *d_x_out, double omega, void *stream);

@@ -95,6 +95,7 @@ _SIGNATURES = {
     "mg_version": (c_int, []),
     "mg_last_error": (ctypes.c_char_p, []),
     "mg_struct_size": (c_i64, [c_int]),
+    "mg_set_pdl": (c_int, [c_int]),
     "mg_device_info": (c_int, [ctypes.POINTER(c_int), ctypes.POINTER(c_i64), ctypes.POINTER(c_int)]),
     "mg_spmv_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_residual_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -108,6 +109,7 @@ _SIGNATURES = {
     "mg_sell_residual_norm2": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_norm_workspace_size": (c_i64, [c_i64]),
     "mg_set_tma_min_rows": (c_i64, [c_i64]),
+    "mg_set_wide_min_len": (c_i64, [c_i64]),
     "mg_sell_jacobi": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "mg_sell_gs_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_i64, c_i64, c_vp]),
     "mg_sell_prolong_correct": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
@@ -197,6 +199,10 @@ def load():
         fn = getattr(lib, name)      # AttributeError here = header / library mismatch
         fn.restype = res
         fn.argtypes = args
+    if os.environ.get("MGB_PDL", "1") == "0":
+        lib.mg_set_pdl(0)
+    if "MGB_WIDE_MIN_LEN" in os.environ:
+        lib.mg_set_wide_min_len(int(os.environ["MGB_WIDE_MIN_LEN"]))
     _lib = lib
     return lib
 

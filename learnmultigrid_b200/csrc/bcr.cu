@@ -179,6 +179,7 @@ __device__ __forceinline__ double warp_row_dot(const double *__restrict__ row, c
 
 __global__ void __launch_bounds__(kBlock)
 bcr_load_kernel(int64_t n, int64_t n_pad, const double *__restrict__ b, double *__restrict__ f) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i < n_pad) f[i] = (i < n) ? b[i] : 0.0;
 }
@@ -187,6 +188,7 @@ bcr_load_kernel(int64_t n, int64_t n_pad, const double *__restrict__ b, double *
 __global__ void __launch_bounds__(kBlock)
 bcr_forward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nk, const double *__restrict__ GL,
                    const double *__restrict__ GU, double *f) {
+    pdl_prologue();
     const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= nk * m) return;
@@ -205,6 +207,7 @@ bcr_forward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nk, const doubl
 // contiguous vector; the dense inverse is then applied by gemv_rows (dense_kernels.cu), which scatters the result back
 __global__ void __launch_bounds__(kBlock)
 bcr_tail_gather_kernel(int m, int s, int64_t nt, const double *__restrict__ f, double *__restrict__ g) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i < nt) g[i] = f[((i / m) << s) * m + i % m];
 }
@@ -214,6 +217,7 @@ __global__ void __launch_bounds__(kBlock)
 bcr_backward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nodd, const double *__restrict__ Dinv,
                     const double *__restrict__ HL, const double *__restrict__ HU, const double *__restrict__ f,
                     double *x) {
+    pdl_prologue();
     const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (wid >= nodd * m) return;
@@ -231,6 +235,7 @@ bcr_backward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nodd, const do
 
 __global__ void __launch_bounds__(kBlock)
 bcr_store_kernel(int64_t n, const double *__restrict__ x, double *__restrict__ out) {
+    pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
     if (i < n) out[i] = x[i];
 }
@@ -250,14 +255,14 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
     if (!H || H->m <= 0 || H->nlevels < 0 || H->nlevels > 32) return set_error(MG_ERR_INVALID, "bcr_solve", "bad handle");
     if (dist && !comm) dist = nullptr;
     const int m = (int)H->m;
-    bcr_load_kernel<<<(unsigned)((H->n_pad + kBlock - 1) / kBlock), kBlock, 0, st>>>(H->n, H->n_pad, rhs, H->f);
+    launch_k(bcr_load_kernel, (unsigned)((unsigned)((H->n_pad + kBlock - 1) / kBlock)), (unsigned)kBlock, st, H->n, H->n_pad, rhs, H->f);
     MG_CHECK_LAUNCH("bcr_load");
     for (int s = 0; s < H->nlevels; ++s) {
         const int64_t na = H->na[s], nk = (na + 1) / 2;
         const bool split = dist && dist->fwd_xfer[s];
         const int64_t j0 = split ? dist->fwd_j0[s] : 0, j1 = split ? dist->fwd_j1[s] : nk;
         if (j1 > j0) {
-            bcr_forward_kernel<<<warps_grid((j1 - j0) * m), kBlock, 0, st>>>(m, s, na, j0, j1 - j0, H->GL[s], H->GU[s], H->f);
+            launch_k(bcr_forward_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->GL[s], H->GU[s], H->f);
             MG_CHECK_LAUNCH("bcr_forward");
         }
         if (split) {
@@ -271,7 +276,7 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
         const int64_t i0 = split ? dist->tail_i0 : 0, i1 = split ? dist->tail_i1 : tna * m;
         if (!H->tail) return set_error(MG_ERR_INVALID, "bcr_solve", "handle has no tail work vector");
         const int64_t nt = tna * m;
-        bcr_tail_gather_kernel<<<(unsigned)((nt + kBlock - 1) / kBlock), kBlock, 0, st>>>(m, H->nlevels, nt, H->f, H->tail);
+        launch_k(bcr_tail_gather_kernel, (unsigned)((unsigned)((nt + kBlock - 1) / kBlock)), (unsigned)kBlock, st, m, H->nlevels, nt, H->f, H->tail);
         MG_CHECK_LAUNCH("bcr_tail_gather");
         int rc = gemv_rows(nt, i0, i1 - i0, nt, H->last_inv, H->tail, H->x, m, H->nlevels, st);
         if (rc) return rc;
@@ -285,7 +290,7 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
         const bool split = dist && dist->bwd_xfer[s];
         const int64_t j0 = split ? dist->bwd_j0[s] : 0, j1 = split ? dist->bwd_j1[s] : nodd;
         if (j1 > j0) {
-            bcr_backward_kernel<<<warps_grid((j1 - j0) * m), kBlock, 0, st>>>(m, s, na, j0, j1 - j0, H->Dinv[s], H->HL[s],
+            launch_k(bcr_backward_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->Dinv[s], H->HL[s],
                                                                               H->HU[s], H->f, H->x);
             MG_CHECK_LAUNCH("bcr_backward");
         }
@@ -294,7 +299,7 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
             if (rc) return rc;
         }
     }
-    bcr_store_kernel<<<(unsigned)((H->n + kBlock - 1) / kBlock), kBlock, 0, st>>>(H->n, H->x, x);
+    launch_k(bcr_store_kernel, (unsigned)((unsigned)((H->n + kBlock - 1) / kBlock)), (unsigned)kBlock, st, H->n, H->x, x);
     MG_CHECK_LAUNCH("bcr_store");
     return MG_OK;
 }

@@ -72,6 +72,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long
 }
 
 __global__ void __launch_bounds__(kBlock) exchange_kernel(const ExArgs a) {
+    pdl_prologue();
     if (a.dry) return;
     const int p = blockIdx.x / a.ctas_per_peer, chunk = blockIdx.x % a.ctas_per_peer;
     const ExPeer &P = a.p[p];
@@ -126,10 +127,12 @@ __global__ void comm_init_kernel(unsigned long long *hdr) {
     }
 }
 __global__ void epoch_advance_kernel(unsigned long long *epoch, unsigned long long delta) {
+    pdl_prologue();
     if (threadIdx.x == 0 && blockIdx.x == 0) epoch[0] += delta;
 }
 // out = sum_q (q == rank ? *value : slots[q]) in rank order
 __global__ void sum_slots_kernel(const double *value, const double *slots, int rank, int world, double *out) {
+    pdl_prologue();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         double s = 0.0;
         for (int q = 0; q < world; ++q) s += (q == rank) ? *value : slots[q];
@@ -173,7 +176,7 @@ int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, 
         memset(&a, 0, sizeof(a));
         a.dry = 1;
         a.ctas_per_peer = 1;
-        exchange_kernel<<<1, kBlock, 0, st>>>(a);
+        launch_k(exchange_kernel, (unsigned)(1), (unsigned)kBlock, st, a);
         MG_CHECK_LAUNCH("exchange (dry run)");
         return MG_OK;
     }
@@ -221,7 +224,7 @@ int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, 
     if (cpp > kMaxCtasPerPeer) cpp = kMaxCtasPerPeer;
     if (cpp < 1) cpp = 1;
     a.ctas_per_peer = cpp;
-    exchange_kernel<<<(unsigned)(cpp * x->npeers), kBlock, 0, st>>>(a);
+    launch_k(exchange_kernel, (unsigned)((unsigned)(cpp * x->npeers)), (unsigned)kBlock, st, a);
     MG_CHECK_LAUNCH("exchange");
     return MG_OK;
 }
@@ -300,7 +303,7 @@ int mg_comm_allreduce_sum(mg_comm *comm, const double *d_value, double *d_slots,
     }
     int rc = comm_exchange(comm, &x, d_value, d_slots, (cudaStream_t)stream);
     if (rc) return rc;
-    sum_slots_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_value, d_slots, comm->rank, comm->world, d_out);
+    launch_k(sum_slots_kernel, (unsigned)(1), (unsigned)32, (cudaStream_t)stream, d_value, d_slots, comm->rank, comm->world, d_out);
     MG_CHECK_LAUNCH("sum_slots");
     return MG_OK;
 }
@@ -314,7 +317,7 @@ int mg_comm_end(mg_comm *comm, void *stream) {
         int rc = comm_exchange(comm, &x, nullptr, nullptr, (cudaStream_t)stream);
         if (rc) return rc;
     }
-    epoch_advance_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((unsigned long long *)comm->d_arena[comm->rank],
+    launch_k(epoch_advance_kernel, (unsigned)(1), (unsigned)32, (cudaStream_t)stream, (unsigned long long *)comm->d_arena[comm->rank],
                                                              comm->dry_run ? 0ull : 1ull);
     MG_CHECK_LAUNCH("epoch_advance");
     return MG_OK;

@@ -49,6 +49,35 @@ __device__ __forceinline__ double mul_add_unfused(double acc, double a, double b
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
 
+// ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
+// The V-cycle is a long chain of short dependent kernels (60-150 per cycle, many of a few microseconds on the coarse
+// levels and between exchange sites).  Every kernel of the chain starts with pdl_prologue(): it waits until the
+// preceding grid has completed and flushed (griddepcontrol.wait) and then allows the NEXT kernel of the stream to
+// be scheduled early (griddepcontrol.launch_dependents), so that its launch latency overlaps this kernel's
+// execution; launch_k() marks the launch accordingly.  Since every kernel of the chain waits unconditionally, a grid
+// can never complete before all of its predecessors have, which keeps the ordering transitive.  Stream capture turns
+// these launches into programmatic graph edges.  mg_set_pdl(0) falls back to plain stream order.
+extern int g_pdl;
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), unsigned grid, unsigned block, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(block, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);     // errors are picked up by MG_CHECK_LAUNCH
+}
+
 inline int sm_count() {
     static int cached = 0;
     if (!cached) {

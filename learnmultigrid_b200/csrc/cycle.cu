@@ -11,6 +11,7 @@ namespace mgb {
 thread_local char g_last_error[512] = "";
 thread_local int64_t g_launch_count = 0;
 thread_local int64_t g_last_cycle_launches = 0;
+int g_pdl = 1;
 
 int sell_spmv(const mg_sell *, const double *, double *, cudaStream_t);
 int sell_residual(const mg_sell *, const double *, const double *, double *, cudaStream_t);
@@ -176,6 +177,11 @@ using namespace mgb;
 extern "C" {
 
 int mg_version(void) { return 100; }
+int mg_set_pdl(int enabled) {
+    const int prev = g_pdl;
+    g_pdl = enabled ? 1 : 0;
+    return prev;
+}
 int64_t mg_struct_size(int which) {
     switch (which) {
         case 0: return sizeof(mg_sell);

@@ -116,6 +116,7 @@ template <int T>
 __global__ void __launch_bounds__(kBlock)
 gemv_rows_kernel(int64_t row0, int64_t nrows, int64_t m, const double *__restrict__ M, const double *__restrict__ x,
                  double *__restrict__ y, int64_t bm, int shift) {
+    pdl_prologue();
     constexpr int RPC = kBlock / T;
     __shared__ double part[kBlock / 32];
     const int sub = threadIdx.x / T, t = threadIdx.x % T;
@@ -169,9 +170,9 @@ int gemv_rows(int64_t total_rows, int64_t row0, int64_t nrows, int64_t m, const 
     const int T = (total_rows * 32 >= want) ? 32 : (total_rows * 128 >= want) ? 128 : 256;
     const int64_t rpc = kBlock / T;
     const unsigned grid = (unsigned)((nrows + rpc - 1) / rpc);
-    if (T == 32) gemv_rows_kernel<32><<<grid, kBlock, 0, st>>>(row0, nrows, m, M, x, y, bm, shift);
-    else if (T == 128) gemv_rows_kernel<128><<<grid, kBlock, 0, st>>>(row0, nrows, m, M, x, y, bm, shift);
-    else gemv_rows_kernel<256><<<grid, kBlock, 0, st>>>(row0, nrows, m, M, x, y, bm, shift);
+    if (T == 32) launch_k(gemv_rows_kernel<32>, (unsigned)(grid), (unsigned)kBlock, st, row0, nrows, m, M, x, y, bm, shift);
+    else if (T == 128) launch_k(gemv_rows_kernel<128>, (unsigned)(grid), (unsigned)kBlock, st, row0, nrows, m, M, x, y, bm, shift);
+    else launch_k(gemv_rows_kernel<256>, (unsigned)(grid), (unsigned)kBlock, st, row0, nrows, m, M, x, y, bm, shift);
     MG_CHECK_LAUNCH("gemv_rows");
     return MG_OK;
 }

@@ -16,6 +16,7 @@ struct SellArgs {
     int64_t row_begin;   // first row this launch touches
     int64_t row_end;     // one past the last row
     int64_t first_row;   // row of thread 0 of block 0 (row_begin rounded down to a slice)
+    int64_t nrows;       // rows of the matrix (rows of the last slice beyond it hold no data)
 };
 
 // accumulate CNT consecutive entries of a row: all cols/vals loads are issued first, then all x gathers, then the
@@ -52,6 +53,7 @@ template <int MODE, int LEN, bool UNIFORM>
 __global__ void __launch_bounds__(kBlock)
 sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
             double *y, double omega, double *__restrict__ partials) {
+    pdl_prologue();
     const int64_t row = A.first_row + (int64_t)blockIdx.x * kBlock + threadIdx.x;
     const bool active = row >= A.row_begin && row < A.row_end;
     double contrib = 0.0;
@@ -102,9 +104,102 @@ sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const dou
     }
 }
 
+// ---- long rows: four warps per slice ---------------------------------------------------------------------------------
+// With 19- / 37-point Galerkin stencils (quasi-L2 transfers) one thread walking a whole row is a chain of dependent
+// (column -> x gather) round trips: ~15 us per launch however small, and half the DRAM rate on large levels.  Here
+// the four warps of a slice take every fourth entry each, issue all their loads up front, and park the separately
+// rounded products v*x in shared memory; one warp then adds them in STORAGE ORDER, so the row sums keep the oracle's
+// bits (the additions are the only order-sensitive part, and they are a few hundred cycles of shared-memory reads).
+constexpr int kWps = 4;            // warps per slice
+constexpr int kWideU = 5;          // entries per warp and pass: 20 entries per pass per slice
+constexpr int kWideMaxLen = 64;    // products kept in shared memory: 2 slices x 64 entries x 32 rows
+
+template <int MODE>
+__global__ void __launch_bounds__(kBlock)
+sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__restrict__ b, const double *aux,
+                 double *y, double omega, double *__restrict__ partials) {
+    pdl_prologue();
+    __shared__ double prod[kBlock / 32 / kWps][kWideMaxLen][kSlice];
+    __shared__ unsigned char skip[kBlock / 32 / kWps][kWideMaxLen][kSlice];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = warp / kWps, w = warp % kWps;
+    const int64_t slice = (A.first_row >> 5) + (int64_t)blockIdx.x * (kBlock / 32 / kWps) + sl;
+    const int64_t row = slice * kSlice + lane;
+    int len = 0;
+    int64_t base = 0;
+    if (slice * kSlice < A.row_end && row < A.nrows) {
+        if (uniform_len > 0) {
+            base = slice * (int64_t)kSlice * uniform_len;
+            len = uniform_len;
+        } else {
+            base = A.slice_ptr[slice];
+            len = (int)((A.slice_ptr[slice + 1] - base) >> 5);
+        }
+    }
+    const double *__restrict__ v = A.vals + base + lane;
+    const int32_t *__restrict__ c = A.cols + base + lane;
+    for (int k0 = w; k0 < len; k0 += kWps * kWideU) {
+        int32_t cc[kWideU];
+        double vv[kWideU], xx[kWideU];
+#pragma unroll
+        for (int j = 0; j < kWideU; ++j) {
+            const int k = k0 + j * kWps;
+            if (k < len) {
+                cc[j] = ld_stream(c + (int64_t)k * kSlice);
+                vv[j] = ld_stream(v + (int64_t)k * kSlice);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kWideU; ++j)
+            if (k0 + j * kWps < len) xx[j] = x[cc[j]];
+#pragma unroll
+        for (int j = 0; j < kWideU; ++j) {
+            const int k = k0 + j * kWps;
+            if (k < len) {
+                const bool is_diag = (MODE == GS) && cc[j] == row;
+                prod[sl][k][lane] = is_diag ? vv[j] : __dmul_rn(vv[j], xx[j]);
+                if (MODE == GS) skip[sl][k][lane] = is_diag ? 1 : 0;
+            }
+        }
+    }
+    __syncthreads();
+    double contrib = 0.0;
+    if (w == 0 && row >= A.row_begin && row < A.row_end) {
+        double sum = 0.0, diag = 0.0;
+        for (int k = 0; k < len; ++k) {
+            const double p = prod[sl][k][lane];
+            if (MODE == GS && skip[sl][k][lane]) { if (p != 0.0) diag = p; }
+            else sum = __dadd_rn(sum, p);
+        }
+        if (MODE == SPMV) {
+            y[row] = sum;
+        } else if (MODE == RESID) {
+            y[row] = __dsub_rn(b[row], sum);
+        } else if (MODE == RESNORM) {
+            const double r = __dsub_rn(b[row], sum);
+            contrib = r * r;
+        } else if (MODE == JACOBI) {
+            const double r = __dsub_rn(b[row], sum);
+            y[row] = __dadd_rn(x[row], __dmul_rn(omega, __dmul_rn(aux[row], r)));
+        } else if (MODE == GS) {
+            if (diag != 0.0) y[row] = __ddiv_rn(__dsub_rn(b[row], sum), diag);
+        } else if (MODE == PROLONG) {
+            y[row] = __dadd_rn(aux[row], sum);
+        }
+    }
+    if (MODE == RESNORM) {
+        const double s = block_sum<kBlock>(contrib);
+        if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    }
+}
+
+// slices at least this long use sell_wide_kernel (0 = never)
+static int64_t g_wide_min_len = 9;
+
 // second stage of the deterministic norm / dot: one CTA sums the per-block partials in a fixed order
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int64_t n,
                                                                double *__restrict__ out) {
+    pdl_prologue();
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += 1024) s += partials[i];
     s = block_sum<1024>(s);
@@ -139,15 +234,26 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     a.row_begin = row0;
     a.row_end = row1;
     a.first_row = row0 & ~(int64_t)(kSlice - 1);
+    a.nrows = A->nrows;
     const int64_t nthreads = row1 - a.first_row;
-    const int64_t grid = (nthreads + kBlock - 1) / kBlock;
-    if (grid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
     const int64_t ml = A->max_slice_len;
     const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
+    if (g_wide_min_len > 0 && ml >= g_wide_min_len && ml <= kWideMaxLen) {
+        constexpr int spc = kBlock / 32 / kWps;                       // slices per CTA
+        const int64_t nsl = (nthreads + kSlice - 1) / kSlice;
+        const int64_t wgrid = (nsl + spc - 1) / spc;
+        if (wgrid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
+        launch_k(sell_wide_kernel<MODE>, (unsigned)wgrid, kBlock, st, a, (int)(uni ? ml : 0), x, b, aux, y, omega, partials);
+        MG_CHECK_LAUNCH(name);
+        if (nblocks_out) *nblocks_out = (int)wgrid;
+        return MG_OK;
+    }
+    const int64_t grid = (nthreads + kBlock - 1) / kBlock;
+    if (grid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
 #define MG_SELL_CASE(L)                                                                                      \
     do {                                                                                                     \
-        if (uni) sell_kernel<MODE, L, true><<<(unsigned)grid, kBlock, 0, st>>>(a, x, b, aux, y, omega, partials); \
-        else sell_kernel<MODE, L, false><<<(unsigned)grid, kBlock, 0, st>>>(a, x, b, aux, y, omega, partials);     \
+        if (uni) launch_k(sell_kernel<MODE, L, true>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials); \
+        else launch_k(sell_kernel<MODE, L, false>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);     \
     } while (0)
     switch (ml) {
         case 1: MG_SELL_CASE(1); break;
@@ -159,7 +265,7 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
         case 7: MG_SELL_CASE(7); break;
         case 8: MG_SELL_CASE(8); break;
         default:   // long rows, or length unknown (0)
-            sell_kernel<MODE, 0, false><<<(unsigned)grid, kBlock, 0, st>>>(a, x, b, aux, y, omega, partials);
+            launch_k(sell_kernel<MODE, 0, false>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);
     }
 #undef MG_SELL_CASE
     MG_CHECK_LAUNCH(name);
@@ -179,7 +285,7 @@ int sell_residual_norm2(const mg_sell *A, const double *x, const double *b, doub
     int rc = launch_sell<RESNORM>(A, x, b, nullptr, nullptr, 0.0, partials, 0, A->nrows, st,
                                   "sell_residual_norm2", &nblocks);
     if (rc) return rc;
-    reduce_partials_kernel<<<1, 1024, 0, st>>>(partials, nblocks, out);
+    launch_k(reduce_partials_kernel, 1u, 1024u, st, (const double *)partials, (int64_t)nblocks, out);
     MG_CHECK_LAUNCH("reduce_partials");
     return MG_OK;
 }
@@ -218,6 +324,11 @@ int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, dou
 }
 int64_t mg_norm_workspace_size(int64_t n) { return (n + kBlock - 1) / kBlock + 1; }
 /* rows per launch from which the bulk-async staged SELL kernel is used (0 = never); returns the old value */
+int64_t mg_set_wide_min_len(int64_t len) {
+    const int64_t prev = g_wide_min_len;
+    g_wide_min_len = len < 0 ? 0 : len;
+    return prev;
+}
 int64_t mg_set_tma_min_rows(int64_t rows) {
     const int64_t old = g_tma_min_rows;
     g_tma_min_rows = rows;

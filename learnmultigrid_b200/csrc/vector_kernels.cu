@@ -7,6 +7,7 @@ namespace mgb {
 __global__ void __launch_bounds__(kBlock)
 dot_partials_kernel(int64_t n, const double *__restrict__ x, const double *__restrict__ y,
                     double *__restrict__ partials) {
+    pdl_prologue();
     // each CTA owns a fixed contiguous chunk of 4*kBlock elements per pass -> fixed summation order
     double s = 0.0;
     const int64_t stride = (int64_t)gridDim.x * kBlock;
@@ -17,6 +18,7 @@ dot_partials_kernel(int64_t n, const double *__restrict__ x, const double *__res
 
 __global__ void __launch_bounds__(1024) reduce_partials_kernel2(const double *__restrict__ partials, int64_t n,
                                                                 double *__restrict__ out) {
+    pdl_prologue();
     double s = 0.0;
     for (int64_t i = threadIdx.x; i < n; i += 1024) s += partials[i];
     s = block_sum<1024>(s);
@@ -25,6 +27,7 @@ __global__ void __launch_bounds__(1024) reduce_partials_kernel2(const double *__
 
 __global__ void __launch_bounds__(kBlock)
 axpby_kernel(int64_t n, double a, const double *x, double b, const double *y, double *out) {
+    pdl_prologue();
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
         // a*x + b*y with separately rounded products and sum; b == 0 skips y entirely (y may be null)
@@ -37,24 +40,28 @@ axpby_kernel(int64_t n, double a, const double *x, double b, const double *y, do
 __global__ void __launch_bounds__(kBlock)
 diag_scale_kernel(int64_t n, double omega, const double *__restrict__ dinv, const double *__restrict__ b,
                   double *__restrict__ out) {
+    pdl_prologue();
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
         out[i] = __dadd_rn(0.0, __dmul_rn(omega, __dmul_rn(dinv[i], b[i])));
 }
 
 __global__ void __launch_bounds__(kBlock) fill_kernel(int64_t n, double v, double *x) {
+    pdl_prologue();
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) x[i] = v;
 }
 
 __global__ void __launch_bounds__(kBlock)
 gather_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ in, double *__restrict__ out) {
+    pdl_prologue();
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) out[i] = in[idx[i]];
 }
 
 __global__ void __launch_bounds__(kBlock)
 scatter_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restrict__ in, double *__restrict__ out) {
+    pdl_prologue();
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) out[idx[i]] = in[i];
 }
@@ -69,34 +76,34 @@ static inline unsigned stream_grid(int64_t n) {
 
 int vec_dot(int64_t n, const double *x, const double *y, double *partials, double *out, cudaStream_t st) {
     const unsigned g = stream_grid(n);
-    dot_partials_kernel<<<g, kBlock, 0, st>>>(n, x, y, partials);
+    launch_k(dot_partials_kernel, (unsigned)(g), (unsigned)kBlock, st, n, x, y, partials);
     MG_CHECK_LAUNCH("dot_partials");
-    reduce_partials_kernel2<<<1, 1024, 0, st>>>(partials, g, out);
+    launch_k(reduce_partials_kernel2, (unsigned)(1), (unsigned)1024, st, partials, g, out);
     MG_CHECK_LAUNCH("reduce_partials");
     return MG_OK;
 }
 int vec_axpby(int64_t n, double a, const double *x, double b, const double *y, double *out, cudaStream_t st) {
     if (n <= 0) return MG_OK;
-    axpby_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, a, x, b, y, out);
+    launch_k(axpby_kernel, (unsigned)(stream_grid(n)), (unsigned)kBlock, st, n, a, x, b, y, out);
     MG_CHECK_LAUNCH("axpby");
     return MG_OK;
 }
 int vec_diag_scale(int64_t n, double omega, const double *dinv, const double *b, double *out, cudaStream_t st) {
     if (n <= 0) return MG_OK;
-    diag_scale_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, omega, dinv, b, out);
+    launch_k(diag_scale_kernel, (unsigned)(stream_grid(n)), (unsigned)kBlock, st, n, omega, dinv, b, out);
     MG_CHECK_LAUNCH("diag_scale");
     return MG_OK;
 }
 int vec_fill(int64_t n, double v, double *x, cudaStream_t st) {
     if (n <= 0) return MG_OK;
-    fill_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, v, x);
+    launch_k(fill_kernel, (unsigned)(stream_grid(n)), (unsigned)kBlock, st, n, v, x);
     MG_CHECK_LAUNCH("fill");
     return MG_OK;
 }
 
 int vec_scatter(int64_t n, const int32_t *idx, const double *in, double *out, cudaStream_t st) {
     if (n <= 0) return MG_OK;
-    scatter_kernel<<<stream_grid(n), kBlock, 0, st>>>(n, idx, in, out);
+    launch_k(scatter_kernel, (unsigned)(stream_grid(n)), (unsigned)kBlock, st, n, idx, in, out);
     MG_CHECK_LAUNCH("scatter");
     return MG_OK;
 }
@@ -122,7 +129,7 @@ int mg_fill(int64_t n, double value, double *d_x, void *stream) {
 int mg_gather(int64_t n, const int32_t *d_idx, const double *d_in, double *d_out, void *stream) {
     MG_REQUIRE(n >= 0, "negative size");
     if (n == 0) return MG_OK;
-    gather_kernel<<<stream_grid(n), kBlock, 0, (cudaStream_t)stream>>>(n, d_idx, d_in, d_out);
+    launch_k(gather_kernel, (unsigned)(stream_grid(n)), (unsigned)kBlock, (cudaStream_t)stream, n, d_idx, d_in, d_out);
     MG_CHECK_LAUNCH("gather");
     return MG_OK;
 }
