@@ -110,10 +110,13 @@ int64_t mg_norm_workspace_size(int64_t n);
 /* launches that cover at least `rows` rows use the bulk-async (TMA) staged kernel; 0 = never.  Returns the
  * previous threshold (default 65536).  Both kernels give bit-identical results. */
 int64_t mg_set_tma_min_rows(int64_t rows);
-/* matrices whose longest slice has at least `len` entries per row (and at most 64) run the four-warps-per-slice
- * kernel: loads of a row spread over four warps, products added in storage order (same bits); 0 = never.  Returns
+/* matrices whose longest slice has at least `len` entries per row (and at most 64) run the warps-per-slice
+ * kernel: loads of a row spread over four or eight warps, products added in storage order (same bits); 0 = never.  Returns
  * the previous threshold (default 9: the 19- and 37-point Galerkin stencils of quasi-L2 transfers). */
 int64_t mg_set_wide_min_len(int64_t len);
+/* ... and only for launches of at most `rows` rows (default 2^18): larger launches keep enough rows in flight for the
+ * thread-per-row kernel, which then streams at the DRAM limit.  Returns the previous value. */
+int64_t mg_set_wide_max_rows(int64_t rows);
 /* x_out = x + omega*(dinv*(b - A x)) */
 int mg_sell_jacobi(const mg_sell *A, const double *d_dinv, const double *d_x, const double *d_b,
                    double *d_x_out, double omega, void *stream);

@@ -110,6 +110,7 @@ _SIGNATURES = {
     "mg_norm_workspace_size": (c_i64, [c_i64]),
     "mg_set_tma_min_rows": (c_i64, [c_i64]),
     "mg_set_wide_min_len": (c_i64, [c_i64]),
+    "mg_set_wide_max_rows": (c_i64, [c_i64]),
     "mg_sell_jacobi": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
     "mg_sell_gs_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_i64, c_i64, c_vp]),
     "mg_sell_prolong_correct": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
@@ -203,6 +204,8 @@ def load():
         lib.mg_set_pdl(0)
     if "MGB_WIDE_MIN_LEN" in os.environ:
         lib.mg_set_wide_min_len(int(os.environ["MGB_WIDE_MIN_LEN"]))
+    if "MGB_WIDE_MAX_ROWS" in os.environ:
+        lib.mg_set_wide_max_rows(int(os.environ["MGB_WIDE_MAX_ROWS"]))
     _lib = lib
     return lib
 

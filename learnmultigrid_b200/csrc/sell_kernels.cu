@@ -110,20 +110,22 @@ sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const dou
 // the four warps of a slice take every fourth entry each, issue all their loads up front, and park the separately
 // rounded products v*x in shared memory; one warp then adds them in STORAGE ORDER, so the row sums keep the oracle's
 // bits (the additions are the only order-sensitive part, and they are a few hundred cycles of shared-memory reads).
-constexpr int kWps = 4;            // warps per slice
-constexpr int kWideU = 5;          // entries per warp and pass: 20 entries per pass per slice
-constexpr int kWideMaxLen = 64;    // products kept in shared memory: 2 slices x 64 entries x 32 rows
+constexpr int kWideU = 5;          // entries per warp and pass
+constexpr int kWideMaxLen = 64;    // products kept in shared memory: 64 entries x 32 rows per slice
 
-template <int MODE>
+// WPS warps share one slice (kBlock/32/WPS slices per CTA); WPS*kWideU entries per pass: 4 warps cover the 19-point
+// stencil in one pass, 8 warps the 37-point one.
+template <int MODE, int WPS>
 __global__ void __launch_bounds__(kBlock)
 sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__restrict__ b, const double *aux,
                  double *y, double omega, double *__restrict__ partials) {
     pdl_prologue();
-    __shared__ double prod[kBlock / 32 / kWps][kWideMaxLen][kSlice];
-    __shared__ unsigned char skip[kBlock / 32 / kWps][kWideMaxLen][kSlice];
+    constexpr int SPC = kBlock / 32 / WPS;
+    __shared__ double prod[SPC][kWideMaxLen][kSlice];
+    __shared__ unsigned char skip[SPC][kWideMaxLen][kSlice];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int sl = warp / kWps, w = warp % kWps;
-    const int64_t slice = (A.first_row >> 5) + (int64_t)blockIdx.x * (kBlock / 32 / kWps) + sl;
+    const int sl = warp / WPS, w = warp % WPS;
+    const int64_t slice = (A.first_row >> 5) + (int64_t)blockIdx.x * SPC + sl;
     const int64_t row = slice * kSlice + lane;
     int len = 0;
     int64_t base = 0;
@@ -136,14 +138,21 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
             len = (int)((A.slice_ptr[slice + 1] - base) >> 5);
         }
     }
+    // the warp that will finish the rows fetches their vector entries now, under the shadow of the matrix loads
+    const bool finisher = w == 0 && row >= A.row_begin && row < A.row_end;
+    double bv = 0.0, av = 0.0;
+    if (finisher) {
+        if (MODE == RESID || MODE == RESNORM || MODE == JACOBI || MODE == GS) bv = b[row];
+        if (MODE == JACOBI || MODE == PROLONG) av = aux[row];
+    }
     const double *__restrict__ v = A.vals + base + lane;
     const int32_t *__restrict__ c = A.cols + base + lane;
-    for (int k0 = w; k0 < len; k0 += kWps * kWideU) {
+    for (int k0 = w; k0 < len; k0 += WPS * kWideU) {
         int32_t cc[kWideU];
         double vv[kWideU], xx[kWideU];
 #pragma unroll
         for (int j = 0; j < kWideU; ++j) {
-            const int k = k0 + j * kWps;
+            const int k = k0 + j * WPS;
             if (k < len) {
                 cc[j] = ld_stream(c + (int64_t)k * kSlice);
                 vv[j] = ld_stream(v + (int64_t)k * kSlice);
@@ -151,10 +160,10 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
         }
 #pragma unroll
         for (int j = 0; j < kWideU; ++j)
-            if (k0 + j * kWps < len) xx[j] = x[cc[j]];
+            if (k0 + j * WPS < len) xx[j] = x[cc[j]];
 #pragma unroll
         for (int j = 0; j < kWideU; ++j) {
-            const int k = k0 + j * kWps;
+            const int k = k0 + j * WPS;
             if (k < len) {
                 const bool is_diag = (MODE == GS) && cc[j] == row;
                 prod[sl][k][lane] = is_diag ? vv[j] : __dmul_rn(vv[j], xx[j]);
@@ -162,9 +171,11 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
             }
         }
     }
+    double xr = 0.0;
+    if (MODE == JACOBI && finisher) xr = x[row];
     __syncthreads();
     double contrib = 0.0;
-    if (w == 0 && row >= A.row_begin && row < A.row_end) {
+    if (finisher) {
         double sum = 0.0, diag = 0.0;
         for (int k = 0; k < len; ++k) {
             const double p = prod[sl][k][lane];
@@ -174,17 +185,17 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
         if (MODE == SPMV) {
             y[row] = sum;
         } else if (MODE == RESID) {
-            y[row] = __dsub_rn(b[row], sum);
+            y[row] = __dsub_rn(bv, sum);
         } else if (MODE == RESNORM) {
-            const double r = __dsub_rn(b[row], sum);
+            const double r = __dsub_rn(bv, sum);
             contrib = r * r;
         } else if (MODE == JACOBI) {
-            const double r = __dsub_rn(b[row], sum);
-            y[row] = __dadd_rn(x[row], __dmul_rn(omega, __dmul_rn(aux[row], r)));
+            const double r = __dsub_rn(bv, sum);
+            y[row] = __dadd_rn(xr, __dmul_rn(omega, __dmul_rn(av, r)));
         } else if (MODE == GS) {
-            if (diag != 0.0) y[row] = __ddiv_rn(__dsub_rn(b[row], sum), diag);
+            if (diag != 0.0) y[row] = __ddiv_rn(__dsub_rn(bv, sum), diag);
         } else if (MODE == PROLONG) {
-            y[row] = __dadd_rn(aux[row], sum);
+            y[row] = __dadd_rn(av, sum);
         }
     }
     if (MODE == RESNORM) {
@@ -195,6 +206,9 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
 
 // slices at least this long use sell_wide_kernel (0 = never)
 static int64_t g_wide_min_len = 9;
+// ... for launches of at most this many rows; larger launches have enough rows in flight for the thread-per-row kernel,
+// which then streams at the DRAM limit (measured: profiles/r01_launches_c3_quasi_*.txt)
+static int64_t g_wide_max_rows = 1 << 18;
 
 // second stage of the deterministic norm / dot: one CTA sums the per-block partials in a fixed order
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int64_t n,
@@ -238,12 +252,16 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     const int64_t nthreads = row1 - a.first_row;
     const int64_t ml = A->max_slice_len;
     const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
-    if (g_wide_min_len > 0 && ml >= g_wide_min_len && ml <= kWideMaxLen) {
-        constexpr int spc = kBlock / 32 / kWps;                       // slices per CTA
+    if (g_wide_min_len > 0 && ml >= g_wide_min_len && ml <= kWideMaxLen && row1 - row0 <= g_wide_max_rows) {
+        const int wps = ml <= 4 * kWideU ? 4 : 8;
+        const int spc = kBlock / 32 / wps;                            // slices per CTA
         const int64_t nsl = (nthreads + kSlice - 1) / kSlice;
         const int64_t wgrid = (nsl + spc - 1) / spc;
         if (wgrid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
-        launch_k(sell_wide_kernel<MODE>, (unsigned)wgrid, kBlock, st, a, (int)(uni ? ml : 0), x, b, aux, y, omega, partials);
+        if (wps == 4)
+            launch_k(sell_wide_kernel<MODE, 4>, (unsigned)wgrid, kBlock, st, a, (int)(uni ? ml : 0), x, b, aux, y, omega, partials);
+        else
+            launch_k(sell_wide_kernel<MODE, 8>, (unsigned)wgrid, kBlock, st, a, (int)(uni ? ml : 0), x, b, aux, y, omega, partials);
         MG_CHECK_LAUNCH(name);
         if (nblocks_out) *nblocks_out = (int)wgrid;
         return MG_OK;
@@ -327,6 +345,11 @@ int64_t mg_norm_workspace_size(int64_t n) { return (n + kBlock - 1) / kBlock + 1
 int64_t mg_set_wide_min_len(int64_t len) {
     const int64_t prev = g_wide_min_len;
     g_wide_min_len = len < 0 ? 0 : len;
+    return prev;
+}
+int64_t mg_set_wide_max_rows(int64_t rows) {
+    const int64_t prev = g_wide_max_rows;
+    g_wide_max_rows = rows < 0 ? 0 : rows;
     return prev;
 }
 int64_t mg_set_tma_min_rows(int64_t rows) {
