@@ -358,6 +358,8 @@ typedef struct {
     int32_t nu_pre, nu_post;   /* smooth_steps (the reference uses the same number before and after)     */
     double omega;              /* Jacobi damping                                                         */
     int32_t zero_guess_skip;   /* 1: skip A*0 work on coarse levels (results identical)                  */
+    int32_t reverse_post;      /* 1: multicolour post-smoothing visits the colours in reverse order, which makes
+                                  the V-cycle a symmetric operator (preconditioner for CG); 0: reference order  */
 } mg_cycle_params;
 
 /* One V-cycle starting on levels[0]: pre-smooth, residual, restrict, recurse / coarsest solve,

@@ -86,7 +86,7 @@ class mg_level(ctypes.Structure):
 
 class mg_cycle_params(ctypes.Structure):
     _fields_ = [("smoother", ctypes.c_int32), ("nu_pre", ctypes.c_int32), ("nu_post", ctypes.c_int32),
-                ("omega", c_dbl), ("zero_guess_skip", ctypes.c_int32)]
+                ("omega", c_dbl), ("zero_guess_skip", ctypes.c_int32), ("reverse_post", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes).  tests/test_abi.py checks that every function declared in include/mgb200.h is

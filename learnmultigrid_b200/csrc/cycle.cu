@@ -49,7 +49,7 @@ static inline int halo_all(mg_comm *comm, const mg_level &L, double *v, cudaStre
 // (Jacobi ping-pongs between d_x and d_tmp).  zero_guess: the iterate is known to be exactly zero and the
 // buffer has NOT been initialised.
 static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, int steps, double **cur, double **alt,
-                  bool zero_guess, cudaStream_t st) {
+                  bool zero_guess, bool reverse, cudaStream_t st) {
     if (steps <= 0) {
         if (zero_guess) MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
         return MG_OK;
@@ -79,7 +79,8 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
         if (L.ncolors <= 0 || !L.h_color_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no colouring");
         if (L.dist && L.dist->ncolors != L.ncolors) return set_error(MG_ERR_INVALID, "mg_vcycle", "halo plan and colouring disagree");
         for (int s = 0; s < steps; ++s)
-            for (int c = 0; c < L.ncolors; ++c) {
+            for (int cc = 0; cc < L.ncolors; ++cc) {
+                const int c = reverse ? L.ncolors - 1 - cc : cc;
                 MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
                 if (L.dist) MG_TRY(comm_exchange(comm, L.dist->xfer_color + c, *cur, *cur, st));
             }
@@ -119,7 +120,7 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
             else prolong_flip = true;
         }
     }
-    MG_TRY(smooth(comm, L, P, P.nu_pre, &cur, &alt, zero_guess, st));
+    MG_TRY(smooth(comm, L, P, P.nu_pre, &cur, &alt, zero_guess, false, st));
     MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));              // res = rhs - A u
     if (L.dist && L.dist->xfer_gather) {
         // last partitioned level: restrict into the owned block of the coarse rhs, then gather it into every
@@ -141,7 +142,7 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
         MG_TRY(sell_prolong(&L.Q, C.d_x, cur, cur, st));
     }
     MG_TRY(halo_all(comm, L, cur, st));
-    MG_TRY(smooth(comm, L, P, P.nu_post, &cur, &alt, false, st));
+    MG_TRY(smooth(comm, L, P, P.nu_post, &cur, &alt, false, P.reverse_post != 0, st));
     if (cur != L.d_x) MG_TRY(vec_axpby(vec_len(L), 1.0, cur, 0.0, nullptr, L.d_x, st));   // safety net; not reached
     return MG_OK;
 }

@@ -549,8 +549,8 @@ class DistributedHierarchy(DeviceHierarchy):
                        "mg_vcycle_dist")
             self.last_launches = int(self.lib.mg_last_launch_count())
             return
-        key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip, bool(with_norm),
-               bool(dry))
+        key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip,
+               params.reverse_post, bool(with_norm), bool(dry))
         g = self._graphs.get(key)
         if g is None:
             cap = torch.cuda.Stream(device=self.device)

@@ -274,10 +274,10 @@ class DeviceHierarchy:
                                              lev.r.data_ptr(), _lib.stream_handle(self.torch)), "mg_sell_residual")
         return self._from_level0(lev.r)
 
-    def make_params(self, nu_pre=1, nu_post=None, omega=1.0, zero_guess_skip=True):
+    def make_params(self, nu_pre=1, nu_post=None, omega=1.0, zero_guess_skip=True, reverse_post=False):
         sm = {"jacobi": _lib.MG_SMOOTH_JACOBI, "mcgs": _lib.MG_SMOOTH_MCGS, "lexgs": _lib.MG_SMOOTH_LEXGS}[self.smoother]
         return _lib.mg_cycle_params(sm, int(nu_pre), int(nu_pre if nu_post is None else nu_post), float(omega),
-                                    1 if zero_guess_skip else 0)
+                                    1 if zero_guess_skip else 0, 1 if reverse_post else 0)
 
     def vcycle(self, params, nlevels=None, use_graph=True):
         """One V-cycle on the level-0 vectors (x updated in place).  The launch sequence is captured into a CUDA
@@ -289,7 +289,8 @@ class DeviceHierarchy:
             _lib.check(self.lib.mg_vcycle(self._level_structs, L, ctypes.byref(params), st), "mg_vcycle")
             self.last_launches = int(self.lib.mg_last_launch_count())
             return
-        key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip)
+        key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip,
+               params.reverse_post)
         g = self._graphs.get(key)
         if g is None:
             cap = torch.cuda.Stream(device=self.device)
@@ -308,6 +309,62 @@ class DeviceHierarchy:
             self._graphs[key] = g
         _lib.check(self.lib.mg_graph_launch(g[0], st), "mg_graph_launch")
         self.last_launches = g[1]
+
+    # ------------------------------------------------------------------------------------------------
+    def pcg(self, rhs, params, error=1e-8, max_iterations=1000):
+        """Conjugate gradients preconditioned by one V-cycle per iteration (BASELINE.json configs[4]), entirely in
+        the level-0 ordering of this hierarchy: A p by the SELL kernel, z = M^-1 r by replaying the captured cycle on
+        (x_0, b_0) = (0, r) -- the residual LIVES in the level's right-hand-side buffer, so nothing is copied or
+        permuted per iteration.  Statement order = solvers/CG.py (the reference's CG.py:12-50 plus the
+        preconditioner).  Returns (solution (n,1) natural order, history list, iterations)."""
+        torch, lib = self.torch, self.lib
+        lev = self.levels[0]
+        n = self.n
+        if getattr(lev, "n_halo", 0):
+            raise _lib.MgError("pcg() runs on a single-GPU hierarchy")
+        st = _lib.stream_handle(torch)
+        if getattr(self, "_cg", None) is None:
+            self._cg = [torch.zeros(n, dtype=torch.float64, device=self.device) for _ in range(3)]
+        x, p, Ap = self._cg
+        r, z = lev.b, lev.x
+
+        def dot(a, b):
+            _lib.check(lib.mg_dot(n, a.data_ptr(), b.data_ptr(), self._norm_ws.data_ptr(), self._norm_out.data_ptr(), st),
+                       "mg_dot")
+            self._norm_host.copy_(self._norm_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return float(self._norm_host.item())
+
+        def axpby(a, xx, b, yy, out):
+            _lib.check(lib.mg_axpby(n, float(a), xx.data_ptr(), float(b), yy.data_ptr(), out.data_ptr(), st), "mg_axpby")
+
+        def precondition():
+            z.zero_()
+            self.vcycle(params)
+
+        self.set_rhs(rhs)                      # r = b - A*0 = b
+        x.zero_()
+        track = [float(np.sqrt(dot(r, r)))]
+        precondition()
+        p.copy_(z)
+        rz = dot(r, z)
+        its = 0
+        for _ in range(max_iterations):
+            its += 1
+            _lib.check(lib.mg_sell_spmv(ctypes.byref(lev.A.struct), p.data_ptr(), Ap.data_ptr(), st), "mg_sell_spmv")
+            alpha = rz / dot(p, Ap)
+            axpby(alpha, p, 1.0, x, x)
+            axpby(-alpha, Ap, 1.0, r, r)
+            res = float(np.sqrt(dot(r, r)))
+            track.append(res)
+            if res <= error:
+                break
+            precondition()
+            rz_new = dot(r, z)
+            beta = rz_new / rz
+            rz = rz_new
+            axpby(beta, p, 1.0, z, p)
+        return self._from_level0(x), track, its
 
     def __del__(self):
         try:

@@ -10,6 +10,26 @@ import scipy.sparse as sp
 from . import formats as F
 
 
+def symmetric_dirichlet(A, boundary):
+    """Zero the columns of the Dirichlet nodes in the other rows (their values are 0, so the solution is unchanged):
+    the operator becomes symmetric, as MG-preconditioned CG needs (the 1D scripts do the same: `A[1,0]=0;
+    A[-2,-1]=0`, test/test_NN.py:176-177).  Explicit zeros are dropped."""
+    A = sp.csr_matrix(A)
+    keep = np.ones(A.shape[0])
+    keep[boundary] = 0.0
+    D = sp.diags(keep)
+    B = sp.csr_matrix(A @ D + sp.diags(1.0 - keep) @ sp.diags(A.diagonal()))
+    B.eliminate_zeros()
+    B.sort_indices()
+    return F.raw_csr(B.indptr.astype(np.int32), B.indices.astype(np.int32), B.data, B.shape)
+
+
+def boundary_nodes_2d(N):
+    W = N + 1
+    iy, ix = np.divmod(np.arange(W * W, dtype=np.int64), W)
+    return np.flatnonzero((ix == 0) | (ix == N) | (iy == 0) | (iy == N))
+
+
 def structured_laplacian_2d(N, coefficient=None):
     """P1 stiffness matrix of -div(k grad u) on the reference's structured mesh Mesh2D(N*N) ((N+1)^2 nodes, row
     major), with boundary rows replaced by identity rows exactly as test/thesis_structured_2d.py:407-414.

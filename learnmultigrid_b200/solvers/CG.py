@@ -17,6 +17,19 @@ class CG(IterativeSolver):
         The reference evaluates `alpha * A @ p` (rescales A, second SpMV, CG.py:37); here A p is reused, which
         changes results only in the last bits.  `preconditioner(r_dev, z_dev)` applies z = M^-1 r on device
         vectors (see solvers.Multigrid.Multigrid.as_preconditioner)."""
+        h = getattr(preconditioner, "hierarchy", None)
+        if (h is not None and initial_guess is None and getattr(preconditioner, "matrix", None) is not None
+                and preconditioner.matrix.shape == self.matrix.shape and preconditioner.matrix.nnz == self.matrix.nnz
+                and not getattr(h.levels[0], "n_halo", 0)):
+            # the preconditioner's hierarchy already holds this operator on the device (SELL, level-0 ordering): run
+            # the whole iteration there (engine.DeviceHierarchy.pcg) instead of uploading a second copy of the matrix
+            x, track, its = h.pcg(self.rhs, preconditioner.params, error=error, max_iterations=max_iterations)
+            self.iterations += its
+            self.solution = x
+            self.residual = track[-1]
+            self.track_res = np.array(track, dtype=float).reshape(-1, 1)
+            self.residual_vector = h._from_level0(h.levels[0].b)      # the residual lives in the level-0 rhs buffer
+            return
         d = self._device_csr()
         torch, lib, n = d["torch"], d["lib"], d["n"]
         st = _lib.stream_handle(torch)

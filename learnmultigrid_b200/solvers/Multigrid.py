@@ -207,10 +207,13 @@ class Multigrid(IterativeSolver):
         return self._hier
 
     def as_preconditioner(self, levels=2, smoother="GaussSeidel", smooth_steps=1, omega=2.0 / 3.0,
-                          gs_order="multicolor", first_call=True):
-        """z = M^-1 r by one V-cycle from a zero guess, on natural-order device vectors (for solvers.CG)."""
-        h = self._hierarchy(levels, smoother, gs_order, None, first_call)
-        params = h.make_params(nu_pre=smooth_steps, nu_post=smooth_steps, omega=omega)
+                          gs_order="multicolor", first_call=True, symmetric=True, colors=None):
+        """z = M^-1 r by one V-cycle from a zero guess, on natural-order device vectors (for solvers.CG).
+        symmetric=True runs the multicolour post-smoothing in reverse colour order, so that M is symmetric for a
+        symmetric A (Galerkin coarse operators, restriction = Q^T); damped Jacobi is symmetric as it is."""
+        h = self._hierarchy(levels, smoother, gs_order, colors, first_call)
+        params = h.make_params(nu_pre=smooth_steps, nu_post=smooth_steps, omega=omega,
+                               reverse_post=bool(symmetric) and smoother == "GaussSeidel")
         lib, torch = h.lib, h.torch
         lev = h.levels[0]
 
@@ -226,6 +229,9 @@ class Multigrid(IterativeSolver):
                 z.copy_(lev.x)
             else:
                 _lib.check(lib.mg_scatter(h.n, lev.perm.data_ptr(), lev.x.data_ptr(), z.data_ptr(), st), "mg_scatter")
+        apply.hierarchy = h            # solvers.CG runs the whole iteration inside the hierarchy when it sees these
+        apply.params = params
+        apply.matrix = self.matrix
         return apply
 
 

@@ -63,7 +63,8 @@ class OracleMultigrid:
     """Restated `Multigrid` / `SemiGeometricMG` (Multigrid.py:26-197) with an explicit hierarchy."""
 
     def __init__(self, A, rhs, Q_list=None, smoother="gs", omega=1.0, colors=None,
-                 hoist_setup=False, geometric_below=False):
+                 hoist_setup=False, geometric_below=False, reverse_post=False):
+        self.reverse_post = reverse_post         # multicolour post-smoothing in reverse colour order (engine option)
         # Solver.__init__ (Solver.py:14-21)
         self.dim = rhs.size
         self.matrix = csc_matrix(A)
@@ -91,7 +92,7 @@ class OracleMultigrid:
             return geometric_interpolator(n)     # dense ndarray, as in the reference
         raise ValueError("no transfer operator for level %d" % level)
 
-    def _smooth(self, A, u, rhs, steps, level):
+    def _smooth(self, A, u, rhs, steps, level, post=False):
         """pre/post smoothing (Multigrid.py:88,121); returns the smoothed vector (may alias u)."""
         if self.smoother == "gs":
             K.gauss_seidel(A, u, rhs, iterations=steps)
@@ -105,7 +106,10 @@ class OracleMultigrid:
                 self._color_rows = {}
             if level not in self._color_rows:
                 self._color_rows[level] = color_rows_from_colors(self.colors[level])
-            K.gauss_seidel_multicolor(A, u, rhs, self._color_rows[level], iterations=steps)
+            rows = self._color_rows[level]
+            if post and self.reverse_post:
+                rows = rows[::-1]
+            K.gauss_seidel_multicolor(A, u, rhs, rows, iterations=steps)
             return u
         raise ValueError("unknown smoother %r" % (self.smoother,))
 
@@ -143,7 +147,7 @@ class OracleMultigrid:
                 u_coarse = np.reshape(spsolve(A_coarse, res_coarse, use_umfpack=False),
                                       (A_coarse.shape[0], 1))
         u = u + i @ u_coarse                                          # :115
-        u = self._smooth(A, u, rhs, smooth_steps, level)              # :121
+        u = self._smooth(A, u, rhs, smooth_steps, level, post=True)   # :121
         return u
 
     # -- Multigrid.solve (Multigrid.py:36-75) -----------------------------------------------------
@@ -232,4 +236,34 @@ def cg_solve(A, rhs, max_iterations=1000, error=1e-08, initial_guess=None):
             break
         beta = (r.T @ r).item() / r2
         p = r + beta * p
+    return x, np.array(track).reshape(-1, 1), it
+
+
+def pcg_solve(A, rhs, precond, max_iterations=1000, error=1e-08):
+    """Preconditioned CG in the statement order of learnmultigrid_b200/solvers/CG.py (the reference's CG.py:12-50 has
+    no preconditioner; BASELINE.json configs[4] asks for MG-preconditioned CG).  precond(r) -> z."""
+    A = csc_matrix(A)
+    rhs = np.asarray(rhs, dtype=np.float64).reshape(-1, 1)
+    x = np.zeros_like(rhs)
+    r = rhs - A.dot(x)
+    track = [np.linalg.norm(r)]
+    z = precond(r)
+    p = z.copy()
+    rz = (r.T @ z).item()
+    it = 0
+    for _ in range(max_iterations):
+        it += 1
+        Ap = A.dot(p)
+        alpha = rz / (p.T @ Ap).item()
+        x = x + alpha * p
+        r = r - alpha * Ap
+        res = np.linalg.norm(r)
+        track.append(res)
+        if res <= error:
+            break
+        z = precond(r)
+        rz_new = (r.T @ z).item()
+        beta = rz_new / rz
+        rz = rz_new
+        p = z + beta * p
     return x, np.array(track).reshape(-1, 1), it

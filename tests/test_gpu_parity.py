@@ -519,3 +519,32 @@ def test_api_edge_cases(env):
     mg0 = SemiGeometricMG(A, np.zeros((1025, 1)), Q)
     mg0.solve(levels=2, smoother="GaussSeidel", error=1e-12, max_iterations=5)
     assert mg0.get_iterations() == 2 and mg0.track_res[1, 0] == 0.0
+
+
+def test_mg_preconditioned_cg_matches_oracle(env):
+    """BASELINE configs[4]: CG preconditioned by one symmetric V(1,1) cycle (multicolour GS, post-smoothing in reverse
+    colour order) against the same algorithm on the CPU oracle: same iteration count, same history"""
+    from learnmultigrid_b200 import problems as P
+    from learnmultigrid_b200.solvers.CG import CG
+    from learnmultigrid_b200.solvers.Multigrid import SemiGeometricMG
+    from oracle.vcycle import pcg_solve
+    N, L = 64, 4
+    A = P.symmetric_dirichlet(P.structured_laplacian_2d(N, P.variable_coefficient), P.boundary_nodes_2d(N))
+    rhs = P.structured_rhs_2d(N)
+    Qs = P.structured_hierarchy_2d(N, L, transfer="linear")
+    mg = SemiGeometricMG(A, rhs, Qs)
+    pre = mg.as_preconditioner(levels=L, smoother="GaussSeidel", smooth_steps=1)
+    cg = CG(A, rhs)
+    cg.solve(max_iterations=60, error=1e-10, preconditioner=pre)
+    o = OracleMultigrid(A, rhs, Qs, smoother="mcgs", colors=mg.get_hierarchy().colors, hoist_setup=True,
+                        reverse_post=True)
+    o.build_hierarchy(L)
+    n = A.shape[0]
+    x, hist, its = pcg_solve(A, rhs, lambda r: o.v_cycle(o.matrix, np.zeros((n, 1)), r, 1, L), 60, 1e-10)
+    assert cg.get_iterations() == its and its < 15
+    np.testing.assert_allclose(cg.track_res, hist, rtol=1e-6)
+    np.testing.assert_allclose(cg.get_solution(), x, rtol=0, atol=1e-9 * np.linalg.norm(x))
+    # plain CG needs many more iterations on the same problem
+    cg0 = CG(A, rhs)
+    cg0.solve(max_iterations=400, error=1e-10)
+    assert cg0.get_iterations() > 5 * its

@@ -173,3 +173,30 @@ def test_structured_colorings_are_valid_on_the_galerkin_hierarchy():
             assert cols[l].max() == (1 if l == 0 else 2)
             assert P.coloring_is_valid(A, cols[l]), "level %d" % l
             A = sp.csr_matrix(Qs[l].T @ A @ Qs[l])
+
+
+def test_reverse_post_smoothing_makes_the_cycle_symmetric():
+    """V(1,1) with multicolour GS forward before and REVERSED after the coarse correction is a symmetric operator on a
+    symmetric problem (what MG-preconditioned CG needs); the reference order is not"""
+    from learnmultigrid_b200 import problems as P, formats as F
+    from oracle.vcycle import OracleMultigrid
+    N, L = 16, 3
+    A = P.symmetric_dirichlet(P.structured_laplacian_2d(N, P.variable_coefficient), P.boundary_nodes_2d(N))
+    assert abs(A - A.T).max() == 0.0
+    Qs = P.structured_hierarchy_2d(N, L, transfer="linear")
+    n = A.shape[0]
+    rng = np.random.default_rng(0)
+    r1, r2 = rng.standard_normal((n, 1)), rng.standard_normal((n, 1))
+    import scipy.sparse as sp
+    cols, Al = [], A
+    for l in range(L - 1):
+        cols.append(F.greedy_colors(F.canonical_csr(Al))[0])
+        Al = sp.csr_matrix(Qs[l].T @ Al @ Qs[l])
+    cols.append(None)
+    asym = {}
+    for rev in (False, True):
+        o = OracleMultigrid(A, r1, Qs, smoother="mcgs", colors=cols, hoist_setup=True, reverse_post=rev)
+        o.build_hierarchy(L)
+        M = lambda r: o.v_cycle(o.matrix, np.zeros((n, 1)), r, 1, L)
+        asym[rev] = abs((M(r1).T @ r2).item() - (r1.T @ M(r2)).item()) / abs((M(r1).T @ r2).item())
+    assert asym[True] < 1e-12 < asym[False]
