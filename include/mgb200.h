@@ -316,6 +316,49 @@ typedef struct {
 } mg_dist_level;
 
 /* ------------------------------------------------------------------------------------------------ */
+/* NN-predicted transfer operators in 2D: the device form of NeuralMG_2D.define_hierarchy and its helpers
+ * (learn_multigrid/solvers/Multigrid.py:401-765; csrc/nn_kernels.cu).  CSR inputs with sorted columns, int32 ids.
+ * Supported regime: at most 6 positive off-diagonal entries per row (MG_ERR_UNSUPPORTED otherwise, no fallback). */
+/* coarsening (:401-426): lexicographically first maximal independent set; input = CSR of M^T; d_state: 1 coarse /
+ * 2 fine; d_work: n+1 int32; synchronises; returns the number of rounds or a negative status */
+int mg_nn_coarsen(int64_t n, const int32_t *d_t_indptr, const int32_t *d_t_indices, const double *d_t_values,
+                  int32_t *d_state, int32_t *d_work, void *stream);
+/* map_coarse (:679-684): with d_scan = exclusive scan of (state == 1): cmap[i] = coarse id or -1, clist[k] = node */
+int mg_nn_compact(int64_t n, const int32_t *d_state, const int32_t *d_scan, int32_t *d_cmap, int32_t *d_clist,
+                  void *stream);
+/* extract_patches (:591-677): [nc][43] features and [nc][31] fill indices (-1 padded); synchronises */
+int mg_nn_extract_patches(int64_t nc, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                          const int32_t *d_cmap, const int32_t *d_clist, double *d_patches, int32_t *d_fill,
+                          int32_t *d_err, void *stream);
+/* fill_B (:687-732) in three steps: contributions [np][31] in application order (unused: row = unused_row >= rows)
+ * + d_neighs table [ncoarse][6]; fold of the runs of equal (row, col) given the stable (row, col) sort order with the
+ * reference's running mean (d_head marks run heads with a non-zero result); emission of the COO triplets of B */
+int mg_nn_contributions(int64_t np_, const int32_t *d_fill, const double *d_pred, const int32_t *d_cmap,
+                        int32_t unused_row, int32_t *d_rows, int32_t *d_cols, double *d_vals, int32_t *d_dneigh,
+                        void *stream);
+int mg_nn_fold(int64_t m, int32_t unused_row, const int32_t *d_rows, const int32_t *d_cols, const double *d_vals,
+               const int32_t *d_order, int32_t *d_head, double *d_folded, void *stream);
+int mg_nn_emit(int64_t m, const int32_t *d_rows, const int32_t *d_cols, const int32_t *d_order, const int32_t *d_head,
+               const int32_t *d_slot, const double *d_folded, int32_t *d_out_rows, int32_t *d_out_cols,
+               double *d_out_vals, void *stream);
+/* Q = B / rowsum(B) in place (:758-759) */
+int mg_nn_row_normalise(int64_t n, const int32_t *d_indptr, double *d_values, void *stream);
+/* pre_process (:735-739): keep of row i the diagonal and the columns d_dneigh[i][0..5]; count pass, scan, fill pass */
+int mg_nn_cut_count(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                    const int32_t *d_dneigh, int32_t *d_keep, int32_t *d_count, void *stream);
+int mg_nn_cut_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                   const int32_t *d_keep, const int32_t *d_out_indptr, int32_t *d_out_indices, double *d_out_values,
+                   void *stream);
+/* the same per-node code run serially on HOST arrays: lets the CPU test-suite check the extraction and contribution
+ * logic against the reference's golden vectors without a GPU; not called by the product */
+int mg_host_nn_coarsen(int64_t n, const int32_t *h_t_indptr, const int32_t *h_t_indices, const double *h_t_values,
+                       int32_t *h_cmap, int32_t *h_clist);
+int mg_host_nn_extract_patches(int64_t nc, const int32_t *h_indptr, const int32_t *h_indices, const double *h_values,
+                               const int32_t *h_cmap, const int32_t *h_clist, double *h_patches, int32_t *h_fill);
+int mg_host_nn_contributions(int64_t np_, const int32_t *h_fill, const double *h_pred, const int32_t *h_cmap,
+                             int32_t unused_row, int32_t *h_rows, int32_t *h_cols, double *h_vals, int32_t *h_dneigh);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* host-side (serial, HOST pointers) setup helpers                                                    */
 /* First-fit greedy colouring in index order on the symmetrised pattern of A; returns ncolors (>0) or <0.
  * The colour order defines the multicolour Gauss-Seidel that replaces PyAMG's index-order sweep

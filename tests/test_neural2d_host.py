@@ -1,0 +1,110 @@
+"""The per-node logic of the NN transfer-operator builder (csrc/nn_kernels.cu: coarsening, patch extraction, fill_B
+contributions), run serially on host arrays through the mg_host_nn_* entry points, against the golden vectors the
+REFERENCE's own NeuralMG_2D methods produced (tests/golden/make_golden_neural.py -> neural_2d_cases.npz).
+The CUDA kernels run the same __host__ __device__ functions; tests/test_gpu_neural2d.py checks them on the GPU."""
+import ctypes
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from learnmultigrid_b200 import _lib
+from helpers import load_golden
+
+CASES = ["s81", "r77", "s289", "i81", "i289"]
+
+
+def level_data(g, case, l):
+    key = "%s__l%d_" % (case, l)
+    if key + "C" not in g.files:
+        return None
+    M = sp.csr_matrix((g[key + "M_data"], (g[key + "M_row"], g[key + "M_col"])), shape=tuple(g[key + "M_shape"]))
+    M.sort_indices()
+    return {"M": M, "C": g[key + "C"], "patches": g[key + "patches"], "fill": g[key + "fill"], "pred": g[key + "pred"],
+            "B": g[key + "B"], "Q": g[key + "Q"], "dn": g[key + "dn"]}
+
+
+def levels_of(g, case):
+    out, l = [], 0
+    while True:
+        d = level_data(g, case, l)
+        if d is None:
+            return out
+        out.append(d)
+        l += 1
+
+
+def ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def host_coarsen(M):
+    lib = _lib.load()
+    MT = sp.csr_matrix(M.T)
+    MT.sort_indices()
+    n = M.shape[0]
+    ip, ix, va = MT.indptr.astype(np.int32), MT.indices.astype(np.int32), MT.data.astype(np.float64)
+    cmap = np.empty(n, dtype=np.int32)
+    clist = np.empty(n, dtype=np.int32)
+    nc = lib.mg_host_nn_coarsen(n, ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist))
+    assert nc > 0
+    return cmap, clist[:nc].copy()
+
+
+def fold_reference_rule(rows, cols, vals, n, nc, unused):
+    """the running mean of fill_B applied in contribution order (tiny cases: plain Python)"""
+    B = np.zeros((n, nc))
+    for r, c, v in zip(rows.ravel(), cols.ravel(), vals.ravel()):
+        if r >= unused:
+            continue
+        B[r, c] = v if B[r, c] == 0 else (B[r, c] + v) / 2.0
+    return B
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_coarsening_extraction_and_fill_match_the_reference(case):
+    lib = _lib.load()
+    g = load_golden("neural_2d_cases.npz")
+    for d in levels_of(g, case):
+        M = d["M"]
+        n = M.shape[0]
+        cmap, clist = host_coarsen(M)
+        assert np.array_equal(clist, d["C"])                         # same coarse nodes, same order
+        nc = len(clist)
+        ip, ix, va = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64)
+        patches = np.empty((nc, 43))
+        fill = np.empty((nc, 31), dtype=np.int32)
+        _lib.check(lib.mg_host_nn_extract_patches(nc, ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches),
+                                                  ptr(fill)), "mg_host_nn_extract_patches")
+        assert d["patches"].shape == patches.shape                   # no extra patch variants in these cases
+        assert np.array_equal(fill, d["fill"])
+        assert np.array_equal(patches, d["patches"])                 # bit for bit
+        pred = np.ascontiguousarray(d["pred"])
+        rows = np.empty((nc, 31), dtype=np.int32)
+        cols = np.empty((nc, 31), dtype=np.int32)
+        vals = np.empty((nc, 31))
+        dn = -np.ones((nc, 6), dtype=np.int32)
+        _lib.check(lib.mg_host_nn_contributions(nc, ptr(fill), ptr(pred), ptr(cmap), n, ptr(rows), ptr(cols), ptr(vals),
+                                                ptr(dn)), "mg_host_nn_contributions")
+        assert np.array_equal(dn, d["dn"])
+        B = fold_reference_rule(rows, cols, vals, n, nc, n)
+        assert np.array_equal(B, d["B"])                             # bit for bit, order-dependent means included
+        Q = B / B.sum(axis=1)[:, None]
+        assert np.array_equal(Q, d["Q"])
+
+
+def test_unsupported_degree_is_reported_not_worked_around():
+    lib = _lib.load()
+    n = 9
+    A = sp.lil_matrix((n, n))
+    A.setdiag(4.0)
+    A[0, 1:9] = 1.0
+    A[1:9, 0] = 1.0
+    M = sp.csr_matrix(A)
+    M.sort_indices()
+    cmap, clist = host_coarsen(M)
+    ip, ix, va = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64)
+    patches = np.empty((len(clist), 43))
+    fill = np.empty((len(clist), 31), dtype=np.int32)
+    rc = lib.mg_host_nn_extract_patches(len(clist), ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches), ptr(fill))
+    assert rc == -3 and b"more than 6 neighbours" in lib.mg_last_error()
