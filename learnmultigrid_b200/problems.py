@@ -173,6 +173,41 @@ def coloring_is_valid(A, colors):
     return not np.any(colors[A.row[off]] == colors[A.col[off]])
 
 
+def irregular_p1_2d(N, seed=42, f_value=-1.0):
+    """BASELINE configs[1] (C2): the reference's own notion of an unstructured mesh -- Mesh2D((N/2)^2) followed by one
+    irregular red refinement (Mesh2D.refine(regular=False): new edge points at r in [0.3, 0.7] along each edge,
+    Mesh2D.py:110-135; parents are numbered first, edge nodes in element-edge discovery order) -- with P1 stiffness,
+    mass and load (f = const) and row-replaced Dirichlet rows (thesis_structured_2d.py:407-414).  (N+1)^2 nodes.
+    Returns dict(A, M, rhs, boundary, mesh)."""
+    from .mesh.Mesh2D import Mesh2D
+    from .assembly.MassMatrix import MassMatrix
+    from .assembly.StiffnessMatrix import StiffnessMatrix
+    from .assembly.LoadVector import LoadVector
+    from .assembly.Quadrature import Quadrature2D
+    from .assembly.ShapeFunction import FunctionTriangle, GradientTriangle
+    if N % 2:
+        raise ValueError("N must be even")
+    np.random.seed(seed)
+    mesh = Mesh2D((N // 2) ** 2)
+    mesh.refine(regular=False)
+    q = Quadrature2D(3)
+    A = StiffnessMatrix(mesh).compute_stiffness_2d(GradientTriangle(1), q, format="csr")
+    M = MassMatrix(mesh).compute_mass_2d(FunctionTriangle(1), q, format="csr")
+    from .assembly.LoadFunction import LoadFunction
+    rhs = LoadVector(mesh).compute_rhs_2d(LoadFunction(lambda pts: f_value), FunctionTriangle(1), q)
+    p = np.asarray(mesh.get_points())
+    eps = 1e-12
+    boundary = np.flatnonzero((p[:, 0] < eps) | (p[:, 0] > 1 - eps) | (p[:, 1] < eps) | (p[:, 1] > 1 - eps))
+    A = sp.lil_matrix(A)
+    for i in boundary:                      # A[nodes,:] = I[nodes,:]
+        A.rows[i] = [int(i)]
+        A.data[i] = [1.0]
+    A = F.canonical_csr(sp.csr_matrix(A))
+    rhs = np.asarray(rhs, dtype=np.float64).reshape(-1, 1).copy()
+    rhs[boundary] = 0.0
+    return {"A": A, "M": F.canonical_csr(sp.csr_matrix(M)), "rhs": rhs, "boundary": boundary, "mesh": mesh}
+
+
 def variable_coefficient(x, y):
     """k(x,y) = 1 + 0.9 sin(2 pi x) sin(2 pi y)  """
     return 1.0 + 0.9 * np.sin(2 * np.pi * x) * np.sin(2 * np.pi * y)

@@ -267,3 +267,110 @@ class SemiGeometricMG(Multigrid):
 
     def _given_transfers(self):
         return self.l_hierarchy
+
+
+class NeuralMG_2D(Multigrid):
+    """NeuralMG_2D(matrix, rhs, model, M, std, mean) -- Multigrid.py:373-765.  `define_hierarchy(levels)` builds the
+    transfer operators from the mass matrix M with the predictor `model` (anything with `.predict(X) -> (len(X), 31)`,
+    the Keras interface the reference uses, or `.predict_device`), on the device (learnmultigrid_b200/neural2d.py).
+
+    Differences, all explicit: the reference stores the hierarchy in `l_hierarchy` but its `solve` never uses it
+    (no `interpolator` override: it falls through to the 1D geometric interpolator); here `solve`
+    runs the V-cycle with `l_hierarchy`.  `fill_B` returns B as a SciPy CSR matrix instead of a dense n x n_C array.
+    Nodes with more than 6 neighbours (extra patch variants, :645-663) are not supported (MgError, no fallback)."""
+
+    def __init__(self, matrix, rhs, model, M, std, mean):
+        super().__init__(matrix, rhs)
+        self.label = "NeuralMG"
+        self.model = model
+        self.M = M
+        self.std = std
+        self.mean = mean
+        self.l_hierarchy = []
+        self._builder = None
+
+    def _nb(self):
+        if self._builder is None:
+            from ..neural2d import NeuralBuilder
+            self._builder = NeuralBuilder()
+        return self._builder
+
+    @staticmethod
+    def diff(first, second):
+        second = set(second)
+        return [item for item in first if item not in second]
+
+    @staticmethod
+    def scaling_vnodes(_neighs):
+        switcher = {2: [6, 1], 3: [3, 2], 4: [2, 3], 5: [1.5, 4]}
+        return switcher.get(_neighs, "Invalid month")
+
+    @staticmethod
+    def map_coarse(_C):
+        return dict(zip(_C, range(len(_C))))
+
+    def coarsening(self, _conn):
+        """(CC, FF, CC_neighs, FF_neighs) as Multigrid.py:401-426; CC in selection (= ascending) order"""
+        nb = self._nb()
+        Mh = F.canonical_csr(sp.csr_matrix(_conn))
+        cmap, clist, nc = nb.coarsen(nb.upload(Mh))
+        CC = [int(v) for v in clist.cpu().numpy()]
+        is_c = cmap.cpu().numpy() >= 0
+        FF = [int(i) for i in np.flatnonzero(~is_c)]
+        offd = Mh.copy()
+        offd.setdiag(0)
+        offd.eliminate_zeros()
+
+        def neighs(i):
+            r = offd.getrow(i)
+            return r.indices[r.data > 0]
+        return CC, FF, {i: neighs(i) for i in CC}, {i: neighs(i) for i in FF}
+
+    def extract_patches(self, CC, _mat):
+        nb = self._nb()
+        torch = nb.torch
+        Mh = F.canonical_csr(sp.csr_matrix(_mat))
+        n = Mh.shape[0]
+        cmap = -np.ones(n, dtype=np.int32)
+        cmap[np.asarray(CC, dtype=np.int64)] = np.arange(len(CC), dtype=np.int32)
+        clist = torch.from_numpy(np.asarray(CC, dtype=np.int32)).to(nb.dev)
+        patches, fill = nb.extract(nb.upload(Mh), torch.from_numpy(cmap).to(nb.dev), clist)
+        return patches.cpu().numpy(), fill.cpu().numpy().astype(int)
+
+    def fill_B(self, _res, _idx_fill, total_size, mapping, CC):
+        nb = self._nb()
+        torch = nb.torch
+        cmap = -np.ones(total_size, dtype=np.int32)
+        for k, v in mapping.items():
+            cmap[int(k)] = int(v)
+        pred = torch.from_numpy(np.ascontiguousarray(_res, dtype=np.float64)).to(nb.dev)
+        fill = torch.from_numpy(np.ascontiguousarray(_idx_fill, dtype=np.int32)).to(nb.dev)
+        B, dn = nb.fill_B(pred, fill, torch.from_numpy(cmap).to(nb.dev), total_size, len(CC))
+        dn = dn.cpu().numpy()
+        return nb.download(B), {k: dn[k][dn[k] >= 0].astype(int) for k in range(len(CC))}
+
+    def pre_process(self, mass, d_neighs):
+        nb = self._nb()
+        torch = nb.torch
+        Mh = F.canonical_csr(sp.csr_matrix(mass))
+        dn = -np.ones((Mh.shape[0], 6), dtype=np.int32)
+        for k, v in d_neighs.items():
+            dn[int(k), :len(v)] = v
+        return nb.download(nb.cut(nb.upload(Mh), torch.from_numpy(dn).to(nb.dev)))
+
+    def define_hierarchy(self, levels=2):
+        if levels == 1:
+            print("Coarse grid correction not required")
+            return
+        nb = self._nb()
+        Qs = nb.define_hierarchy(F.canonical_csr(sp.csr_matrix(self.M)), self.model, self.mean, self.std, levels)
+        self.l_hierarchy = [nb.download(Q) for Q in Qs]
+
+    def solve(self, levels=2, smoother="Jacobi", smooth_steps=1, max_iterations=100, error=1e-08,
+              initial_guess=None, cycle="V", first_call=True, **kw):
+        if len(self.l_hierarchy) < levels - 1:
+            self.define_hierarchy(levels)
+        super().solve(levels, smoother, smooth_steps, max_iterations, error, initial_guess, cycle, first_call, **kw)
+
+    def _given_transfers(self):
+        return self.l_hierarchy
