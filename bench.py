@@ -37,7 +37,11 @@ def parse_args():
     ap.add_argument("--n", type=int, default=int(os.environ.get("MGB_BENCH_N", "8192")),
                     help="elements per side of the structured mesh ((n+1)^2 DOF)")
     ap.add_argument("--levels", type=int, default=int(os.environ.get("MGB_BENCH_LEVELS", "6")))
-    ap.add_argument("--transfer", default=os.environ.get("MGB_BENCH_TRANSFER", "linear"), choices=["linear", "quasi"])
+    ap.add_argument("--transfer", default=os.environ.get("MGB_BENCH_TRANSFER", "linear"), choices=["linear", "quasi", "nn"],
+                    help="nn: transfer operators from the mass matrix through NeuralMG_2D.define_hierarchy (device "
+                         "builder, mass-surrogate predictor: the reference's trained weights are not shipped)")
+    ap.add_argument("--mesh", default=os.environ.get("MGB_BENCH_MESH", "structured"), choices=["structured", "irregular"],
+                    help="irregular: Mesh2D((n/2)^2) + one irregular red refinement, parents numbered first (configs[1])")
     ap.add_argument("--smoother", default=os.environ.get("MGB_BENCH_SMOOTHER", "GaussSeidel"),
                     choices=["GaussSeidel", "Jacobi"])
     ap.add_argument("--nu", type=int, default=1)
@@ -60,10 +64,12 @@ def parse_args():
 
 
 def workload_name(a, n):
-    return "2D structured P1 %s %dx%d grid (%d DOF), %d-level V(%d,%d), %s, %s transfers" % (
+    return "2D %s P1 %s %dx%d grid (%d DOF), %d-level V(%d,%d), %s, %s transfers" % (
+        "structured" if a.mesh == "structured" else "irregularly refined (unstructured numbering)",
         "Laplacian" if a.coefficient == "constant" else "variable-coefficient stiffness", n + 1, n + 1,
         (n + 1) ** 2, a.levels, a.nu, a.nu,
-        "multicolour (red-black on the fine level) Gauss-Seidel" if a.smoother == "GaussSeidel" else "damped Jacobi (omega=2/3)",
+        ("multicolour Gauss-Seidel (greedy colouring)" if a.mesh == "irregular" else
+         "multicolour (red-black on the fine level) Gauss-Seidel") if a.smoother == "GaussSeidel" else "damped Jacobi (omega=2/3)",
         a.transfer)
 
 
@@ -132,8 +138,24 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+NN_BUILD = {}
+
+
 def build_problem(a, n):
     from learnmultigrid_b200 import problems as P
+    if a.mesh == "irregular" or a.transfer == "nn":
+        if a.mesh != "irregular" or a.transfer != "nn":
+            raise SystemExit("--mesh irregular and --transfer nn go together (BASELINE configs[1])")
+        from learnmultigrid_b200.neural2d import MassSurrogate
+        from learnmultigrid_b200.solvers.Multigrid import NeuralMG_2D
+        pb = P.irregular_p1_2d(n, seed=42)
+        nmg = NeuralMG_2D(pb["A"], pb["rhs"], MassSurrogate(), pb["M"], np.ones(43), np.zeros(43))
+        t0 = time.perf_counter()
+        nmg.define_hierarchy(a.levels)
+        NN_BUILD[n] = {"define_hierarchy_s": round(time.perf_counter() - t0, 3),
+                       "coarse_nodes": [int(q.shape[1]) for q in nmg.l_hierarchy],
+                       "nnz_Q": [int(q.nnz) for q in nmg.l_hierarchy]}
+        return pb["A"], pb["rhs"], nmg.l_hierarchy
     coef = P.variable_coefficient if a.coefficient == "variable" else None
     A = P.structured_laplacian_2d(n, coef)
     rhs = P.structured_rhs_2d(n)
@@ -408,7 +430,7 @@ def run_b200(a):
                            % (cyc["total"] / 1e9), "setup": a.setup, "levels_rows": list(getattr(h, "_global_n", [l.n for l in h.levels])),
                            "levels_nnz": [l.nnz_A for l in h.levels], "colors": [None if l.color_ptr is None else
                                                                               len(l.color_ptr) - 1 for l in h.levels],
-                           "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2),
+                           "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2), "nn_builder": NN_BUILD.get(n),
                            "residual_after_timed_steps": res_after,
                            "ms_per_step_without_exchange_waits": ms_dry, "parallelism": ("row-partitioned x%d, levels 0..%d partitioned, %d replicated, halo exchange by peer-memory "
                                            "stores over NVLink inside the cycle graph" % (world, h.n_dist - 1, a.levels - h.n_dist))
