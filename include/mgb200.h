@@ -316,6 +316,28 @@ typedef struct {
 } mg_dist_level;
 
 /* ------------------------------------------------------------------------------------------------ */
+/* P1 assembly on the device (csrc/assembly_kernels.cu).  Replaces the per-element Python loops of
+ * MassMatrix.compute_mass_2d (MassMatrix.py:21-35), StiffnessMatrix.compute_stiffness_2d (StiffnessMatrix.py:21-36),
+ * LoadVector.compute_rhs_2d (LoadVector.py:20-51) and the Dirichlet row replacement thesis_structured_2d.py:407-414. */
+/* nine (row, col, value) contributions per element, element-major.  kind 0 mass: h_const = c[3][3]; kind 1 stiffness:
+ * h_const = g[3][2], w[3], number of quadrature points (10 doubles); d_coef optional per-element coefficient */
+int mg_assemble_p1_2d(int64_t ne, const double *d_points, const int32_t *d_conn, int kind, const double *h_const,
+                      const double *d_coef, int32_t *d_rows, int32_t *d_cols, double *d_vals, void *stream);
+int mg_assemble_load_p1_2d(int64_t ne, const double *d_points, const int32_t *d_conn, const double *h_c3,
+                           int32_t *d_nodes, double *d_vals, void *stream);
+/* sum the runs of equal (row, col) of contributions sorted stably by (row, col), in order (= element order, the order
+ * of the reference's `+=`); runs whose sum is exactly 0 are dropped (d_head = 0).  mg_nn_emit writes the triplets. */
+int mg_coo_fold_sum(int64_t m, const int32_t *d_rows, const int32_t *d_cols, const double *d_vals,
+                    const int32_t *d_order, int32_t *d_head, double *d_folded, void *stream);
+int mg_vector_from_runs(int64_t m, const int32_t *d_rows, const int32_t *d_order, const int32_t *d_head,
+                        const double *d_folded, double *d_out, void *stream);
+/* A[nodes,:] = I[nodes,:] for the rows flagged in d_flag: count pass, scan, fill pass */
+int mg_csr_dirichlet_count(int64_t n, const int32_t *d_indptr, const int32_t *d_flag, int32_t *d_count, void *stream);
+int mg_csr_dirichlet_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                          const int32_t *d_flag, const int32_t *d_out_indptr, int32_t *d_out_indices,
+                          double *d_out_values, void *stream);
+
+/* ------------------------------------------------------------------------------------------------ */
 /* NN-predicted transfer operators in 2D: the device form of NeuralMG_2D.define_hierarchy and its helpers
  * (learn_multigrid/solvers/Multigrid.py:401-765; csrc/nn_kernels.cu).  CSR inputs with sorted columns, int32 ids.
  * Supported regime: at most 6 positive off-diagonal entries per row (MG_ERR_UNSUPPORTED otherwise, no fallback). */

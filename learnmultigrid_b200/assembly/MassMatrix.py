@@ -25,7 +25,13 @@ class MassMatrix:
         self.M = lil_matrix([])
 
     def compute_mass_2d(self, phi, q, format="lil"):
-        """loc_M[i,j] = detJ * sum_k phi_i(p_k) phi_j(p_k) w_k  (MassMatrix.py:21-35, 52-59)"""
+        """loc_M[i,j] = detJ * sum_k phi_i(p_k) phi_j(p_k) w_k  (MassMatrix.py:21-35, 52-59).
+        format="device": assembled by CUDA kernels (assembly_device.py), returns a device CSR (setup_device.DevCSR)."""
+        if format == "device":
+            from ..assembly_device import DeviceAssembler
+            asm = DeviceAssembler()
+            self.M = asm.mass(*asm.mesh_to_device(self.mesh), phi, q)
+            return self.M
         n_p = self.mesh.get_np()
         p = self.mesh.get_points()
         conn = np.asarray(self.mesh.get_connections())

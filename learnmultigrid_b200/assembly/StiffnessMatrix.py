@@ -28,6 +28,11 @@ class StiffnessMatrix:
     def compute_stiffness_2d(self, d_phi, q, format="lil", coefficient=None):
         """loc_A[i,j] = detJ * sum_k ((J^-T g_i)^T J^-T) g_j * w[i]   (StiffnessMatrix.py:21-36, 53-59 and
         Quadrature2D.compute_grad, Quadrature.py:72-82, same association of the products)."""
+        if format == "device":             # CUDA kernels (assembly_device.py); returns a device CSR (setup_device.DevCSR)
+            from ..assembly_device import DeviceAssembler
+            asm = DeviceAssembler()
+            self.A = asm.stiffness(*asm.mesh_to_device(self.mesh), d_phi, q, coefficient)
+            return self.A
         n_p = self.mesh.get_np()
         p = self.mesh.get_points()
         conn = np.asarray(self.mesh.get_connections())

@@ -1,0 +1,246 @@
+// assembly_kernels.cu -- P1 finite-element assembly on the device.
+//
+// Reference: MassMatrix.compute_mass_2d (learn_multigrid/assembly/MassMatrix.py:21-35, 52-59),
+// StiffnessMatrix.compute_stiffness_2d (StiffnessMatrix.py:21-36, 53-59; Quadrature2D.compute_grad, Quadrature.py:72-82),
+// LoadVector.compute_rhs_2d (LoadVector.py:20-51) and the Dirichlet row replacement of the drivers
+// (test/thesis_structured_2d.py:407-414).  The reference loops over the elements in Python (~1 ms per element) and adds
+// each 3x3 block into a lil_matrix; here one thread per element writes its nine (row, col, value) contributions, which
+// are then sorted stably by (row, col) and summed run by run IN ELEMENT ORDER (the order the reference's `+=` sees
+// them), exact zeros dropped as lil_matrix does.  The element arithmetic is the product's vectorised host assembly
+// (learnmultigrid_b200/assembly/*.py) operation for operation without FMA contraction, so device and host results are
+// bit-identical; both differ from the reference in the last bit of detJ (np.linalg.det goes through a pivoted LU).
+#include "common.cuh"
+
+namespace mgb {
+
+__device__ __forceinline__ void element_jacobian(const double *__restrict__ p, const int32_t *__restrict__ conn,
+                                                 int64_t e, int32_t node[3], double &J00, double &J01, double &J10,
+                                                 double &J11, double &det) {
+    node[0] = conn[3 * e];
+    node[1] = conn[3 * e + 1];
+    node[2] = conn[3 * e + 2];
+    const double x0 = p[2 * (int64_t)node[0]], y0 = p[2 * (int64_t)node[0] + 1];
+    const double x1 = p[2 * (int64_t)node[1]], y1 = p[2 * (int64_t)node[1] + 1];
+    const double x2 = p[2 * (int64_t)node[2]], y2 = p[2 * (int64_t)node[2] + 1];
+    J00 = __dsub_rn(x1, x0);
+    J01 = __dsub_rn(x2, x0);
+    J10 = __dsub_rn(y1, y0);
+    J11 = __dsub_rn(y2, y0);
+    det = __dsub_rn(__dmul_rn(J00, J11), __dmul_rn(J01, J10));      // signed, like the reference (MassMatrix.py:31)
+}
+
+struct MassConst { double c[9]; };
+struct StiffConst { double g[6]; double w[3]; int npts; };
+struct LoadConst { double c[3]; };
+
+// loc_M[i,j] = detJ * c[i][j],   c[i][j] = sum_k phi_i(p_k) phi_j(p_k) w_k (evaluated once on the host)
+__global__ void __launch_bounds__(kBlock)
+assemble_mass_kernel(int64_t ne, const double *__restrict__ p, const int32_t *__restrict__ conn, MassConst K,
+                     int32_t *__restrict__ rows, int32_t *__restrict__ cols, double *__restrict__ vals) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= ne) return;
+    int32_t nd[3];
+    double J00, J01, J10, J11, det;
+    element_jacobian(p, conn, e, nd, J00, J01, J10, J11, det);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int64_t o = 9 * e + 3 * i + j;
+            rows[o] = nd[i];
+            cols[o] = nd[j];
+            vals[o] = __dmul_rn(det, K.c[3 * i + j]);
+        }
+}
+
+// loc_A[i,j] = detJ * sum_k ((J^-T g_i)^T J^-T) g_j * w[i]  (the reference indexes w by i, Quadrature.py:80), times an
+// optional per-element coefficient
+__global__ void __launch_bounds__(kBlock)
+assemble_stiffness_kernel(int64_t ne, const double *__restrict__ p, const int32_t *__restrict__ conn, StiffConst K,
+                          const double *__restrict__ coef, int32_t *__restrict__ rows, int32_t *__restrict__ cols,
+                          double *__restrict__ vals) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= ne) return;
+    int32_t nd[3];
+    double J00, J01, J10, J11, det;
+    element_jacobian(p, conn, e, nd, J00, J01, J10, J11, det);
+    const double T00 = __ddiv_rn(J11, det), T01 = __ddiv_rn(-J10, det);
+    const double T10 = __ddiv_rn(-J01, det), T11 = __ddiv_rn(J00, det);
+    const double ke = coef ? coef[e] : 1.0;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double a0 = __dadd_rn(__dmul_rn(T00, K.g[2 * i]), __dmul_rn(T01, K.g[2 * i + 1]));
+        const double a1 = __dadd_rn(__dmul_rn(T10, K.g[2 * i]), __dmul_rn(T11, K.g[2 * i + 1]));
+        const double t0 = __dadd_rn(__dmul_rn(a0, T00), __dmul_rn(a1, T10));
+        const double t1 = __dadd_rn(__dmul_rn(a0, T01), __dmul_rn(a1, T11));
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const double s = __dmul_rn(__dadd_rn(__dmul_rn(t0, K.g[2 * j]), __dmul_rn(t1, K.g[2 * j + 1])), K.w[i]);
+            double res = 0.0;
+            for (int k = 0; k < K.npts; ++k) res = __dadd_rn(res, s);
+            double v = __dmul_rn(det, res);
+            if (coef) v = __dmul_rn(v, ke);
+            const int64_t o = 9 * e + 3 * i + j;
+            rows[o] = nd[i];
+            cols[o] = nd[j];
+            vals[o] = v;
+        }
+    }
+}
+
+// loc_rhs[i] = detJ * c[i]
+__global__ void __launch_bounds__(kBlock)
+assemble_load_kernel(int64_t ne, const double *__restrict__ p, const int32_t *__restrict__ conn, LoadConst K,
+                     int32_t *__restrict__ nodes, double *__restrict__ vals) {
+    const int64_t e = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (e >= ne) return;
+    int32_t nd[3];
+    double J00, J01, J10, J11, det;
+    element_jacobian(p, conn, e, nd, J00, J01, J10, J11, det);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        nodes[3 * e + i] = nd[i];
+        vals[3 * e + i] = __dmul_rn(det, K.c[i]);
+    }
+}
+
+// contributions sorted stably by (row, col): the first element of a run adds the run up in order
+__global__ void __launch_bounds__(kBlock)
+coo_fold_sum_kernel(int64_t m, const int32_t *__restrict__ rows, const int32_t *__restrict__ cols,
+                    const double *__restrict__ vals, const int32_t *__restrict__ order, int32_t *__restrict__ head,
+                    double *__restrict__ folded) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= m) return;
+    const int32_t o = order[i];
+    const int32_t r = rows[o], c = cols ? cols[o] : 0;
+    head[i] = 0;
+    if (i > 0) {
+        const int32_t po = order[i - 1];
+        if (rows[po] == r && (cols ? cols[po] : 0) == c) return;
+    }
+    double s = 0.0;
+    for (int64_t k = i; k < m; ++k) {
+        const int32_t ok = order[k];
+        if (rows[ok] != r || (cols ? cols[ok] : 0) != c) break;
+        s = __dadd_rn(s, vals[ok]);
+    }
+    head[i] = s != 0.0 ? 1 : 0;
+    folded[i] = s;
+}
+
+__global__ void __launch_bounds__(kBlock)
+vector_from_runs_kernel(int64_t m, const int32_t *__restrict__ rows, const int32_t *__restrict__ order,
+                        const int32_t *__restrict__ head, const double *__restrict__ folded, double *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= m || !head[i]) return;
+    out[rows[order[i]]] = folded[i];
+}
+
+// A[nodes,:] = I[nodes,:]
+__global__ void __launch_bounds__(kBlock)
+dirichlet_count_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32_t *__restrict__ flag,
+                       int32_t *__restrict__ count) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) count[i] = flag[i] ? 1 : indptr[i + 1] - indptr[i];
+}
+__global__ void __launch_bounds__(kBlock)
+dirichlet_fill_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                      const double *__restrict__ values, const int32_t *__restrict__ flag,
+                      const int32_t *__restrict__ out_indptr, int32_t *__restrict__ out_indices,
+                      double *__restrict__ out_values) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= n) return;
+    int32_t o = out_indptr[i];
+    if (flag[i]) {
+        out_indices[o] = (int32_t)i;
+        out_values[o] = 1.0;
+        return;
+    }
+    for (int32_t p = indptr[i]; p < indptr[i + 1]; ++p, ++o) {
+        out_indices[o] = indices[p];
+        out_values[o] = values[p];
+    }
+}
+
+static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
+
+}  // namespace mgb
+
+using namespace mgb;
+
+extern "C" {
+
+/* the nine (row, col, value) contributions of every P1 element, element-major ([ne][3][3]).
+ * kind 0: mass, h_const = c[3][3] with c[i][j] = sum_k phi_i(p_k) phi_j(p_k) w_k (MassMatrix.py:52-59);
+ * kind 1: stiffness, h_const = g[3][2] (reference gradients) followed by w[3] and the number of quadrature points
+ *         (StiffnessMatrix.py:53-59, Quadrature.py:72-82); d_coef: optional per-element coefficient (NULL: 1).
+ * d_points: [np][2] doubles, d_conn: [ne][3] int32. */
+int mg_assemble_p1_2d(int64_t ne, const double *d_points, const int32_t *d_conn, int kind, const double *h_const,
+                      const double *d_coef, int32_t *d_rows, int32_t *d_cols, double *d_vals, void *stream) {
+    MG_REQUIRE(ne > 0 && d_points && d_conn && h_const && d_rows && d_cols && d_vals, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (kind == 0) {
+        MassConst K;
+        for (int i = 0; i < 9; ++i) K.c[i] = h_const[i];
+        assemble_mass_kernel<<<grid_for(ne), kBlock, 0, st>>>(ne, d_points, d_conn, K, d_rows, d_cols, d_vals);
+    } else if (kind == 1) {
+        StiffConst K;
+        for (int i = 0; i < 6; ++i) K.g[i] = h_const[i];
+        for (int i = 0; i < 3; ++i) K.w[i] = h_const[6 + i];
+        K.npts = (int)h_const[9];
+        assemble_stiffness_kernel<<<grid_for(ne), kBlock, 0, st>>>(ne, d_points, d_conn, K, d_coef, d_rows, d_cols, d_vals);
+    } else {
+        return set_error(MG_ERR_INVALID, "mg_assemble_p1_2d", "kind must be 0 (mass) or 1 (stiffness)");
+    }
+    MG_CHECK_LAUNCH("assemble_p1_2d");
+    return MG_OK;
+}
+
+/* load vector contributions ([ne][3] nodes / values), h_c3[i] = sum_k phi_i(p_k) f(p_k) w_k (LoadVector.py:45-51) */
+int mg_assemble_load_p1_2d(int64_t ne, const double *d_points, const int32_t *d_conn, const double *h_c3,
+                           int32_t *d_nodes, double *d_vals, void *stream) {
+    MG_REQUIRE(ne > 0 && d_points && d_conn && h_c3 && d_nodes && d_vals, "null argument");
+    LoadConst K;
+    for (int i = 0; i < 3; ++i) K.c[i] = h_c3[i];
+    assemble_load_kernel<<<grid_for(ne), kBlock, 0, (cudaStream_t)stream>>>(ne, d_points, d_conn, K, d_nodes, d_vals);
+    MG_CHECK_LAUNCH("assemble_load");
+    return MG_OK;
+}
+
+/* with d_order = the stable (row, col) sort order of the contributions: d_head[i] = 1 where a run starts and its sum
+ * (added in order) is not exactly zero, d_folded[i] = that sum.  d_cols may be NULL (vectors).  mg_nn_emit writes
+ * the triplets. */
+int mg_coo_fold_sum(int64_t m, const int32_t *d_rows, const int32_t *d_cols, const double *d_vals,
+                    const int32_t *d_order, int32_t *d_head, double *d_folded, void *stream) {
+    MG_REQUIRE(m > 0 && d_rows && d_vals && d_order && d_head && d_folded, "null argument");
+    coo_fold_sum_kernel<<<grid_for(m), kBlock, 0, (cudaStream_t)stream>>>(m, d_rows, d_cols, d_vals, d_order, d_head, d_folded);
+    MG_CHECK_LAUNCH("coo_fold_sum");
+    return MG_OK;
+}
+/* d_out[row of run] = sum of the run, for runs marked by mg_coo_fold_sum (d_out zero-initialised by the caller) */
+int mg_vector_from_runs(int64_t m, const int32_t *d_rows, const int32_t *d_order, const int32_t *d_head,
+                        const double *d_folded, double *d_out, void *stream) {
+    MG_REQUIRE(m > 0 && d_rows && d_order && d_head && d_folded && d_out, "null argument");
+    vector_from_runs_kernel<<<grid_for(m), kBlock, 0, (cudaStream_t)stream>>>(m, d_rows, d_order, d_head, d_folded, d_out);
+    MG_CHECK_LAUNCH("vector_from_runs");
+    return MG_OK;
+}
+
+/* Dirichlet rows (thesis_structured_2d.py:407-414: A[nodes,:] = I[nodes,:]): rows with d_flag != 0 become (i, 1.0).
+ * Two passes around a scan of d_count. */
+int mg_csr_dirichlet_count(int64_t n, const int32_t *d_indptr, const int32_t *d_flag, int32_t *d_count, void *stream) {
+    MG_REQUIRE(n > 0 && d_indptr && d_flag && d_count, "null argument");
+    dirichlet_count_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(n, d_indptr, d_flag, d_count);
+    MG_CHECK_LAUNCH("dirichlet_count");
+    return MG_OK;
+}
+int mg_csr_dirichlet_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                          const int32_t *d_flag, const int32_t *d_out_indptr, int32_t *d_out_indices,
+                          double *d_out_values, void *stream) {
+    MG_REQUIRE(n > 0 && d_indptr && d_indices && d_values && d_flag && d_out_indptr && d_out_indices && d_out_values, "null argument");
+    dirichlet_fill_kernel<<<grid_for(n), kBlock, 0, (cudaStream_t)stream>>>(n, d_indptr, d_indices, d_values, d_flag, d_out_indptr, d_out_indices, d_out_values);
+    MG_CHECK_LAUNCH("dirichlet_fill");
+    return MG_OK;
+}
+
+}  // extern "C"

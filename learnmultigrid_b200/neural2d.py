@@ -132,18 +132,6 @@ class NeuralBuilder:
             raise ValueError("the predictor must return (n_patches, 31) values, got %r" % (tuple(res.shape),))
         return res.to(t.float64).contiguous()
 
-    def _argsort(self, keys, bits):
-        t, S = self.torch, self.S
-        n = keys.numel()
-        ks = S.empty(n, t.int32)
-        perm = S.empty(n, t.int32)
-        iota = S.empty(n, t.int32)
-        nb = int(self.lib.mg_sort_workspace_size(max(n, 1)))
-        tmp = S.temp(nb)
-        _lib.check(self.lib.mg_stable_argsort_i32(n, keys.data_ptr(), ks.data_ptr(), perm.data_ptr(), iota.data_ptr(),
-                                                  int(bits), tmp.data_ptr(), nb, self.st()), "mg_stable_argsort_i32")
-        return perm
-
     # fill_B (:687-732) -> (B as device CSR n x nc, d_neighs table nc x 6)
     def fill_B(self, pred, fill, cmap, n, nc):
         t, S = self.torch, self.S
@@ -155,11 +143,7 @@ class NeuralBuilder:
         _lib.check(self.lib.mg_nn_contributions(np_, fill.data_ptr(), pred.data_ptr(), cmap.data_ptr(), n,
                                                 rows.data_ptr(), cols.data_ptr(), vals.data_ptr(), dneigh.data_ptr(),
                                                 self.st()), "mg_nn_contributions")
-        bits_c = max(1, int(np.ceil(np.log2(max(nc, 2)))))
-        bits_r = max(1, int(np.ceil(np.log2(n + 2))))
-        o1 = self._argsort(cols, bits_c)                                  # stable by column ...
-        o2 = self._argsort(rows[o1.long()].contiguous(), bits_r)         # ... then stable by row
-        order = o1[o2.long()].contiguous()
+        order = S.row_col_order(rows, cols, n + 1, nc)        # stable by column, then stably by row (unused: row n)
         head = S.empty(m, t.int32)
         folded = S.empty(m, t.float64)
         _lib.check(self.lib.mg_nn_fold(m, n, rows.data_ptr(), cols.data_ptr(), vals.data_ptr(), order.data_ptr(),

@@ -66,6 +66,27 @@ class DeviceSetup:
                                                   tmp.data_ptr(), nb, self.st()), "mg_exclusive_scan_i32")
         return out, int(self._total.item())
 
+    def argsort_i32(self, keys, bits):
+        """stable argsort of non-negative int32 keys on their low `bits` bits (LSD radix sort)"""
+        t = self.torch
+        n = keys.numel()
+        ks, perm, iota = self.empty(n, t.int32), self.empty(n, t.int32), self.empty(n, t.int32)
+        nb = int(self.lib.mg_sort_workspace_size(max(n, 1)))
+        tmp = self.temp(nb)
+        _lib.check(self.lib.mg_stable_argsort_i32(n, keys.data_ptr(), ks.data_ptr(), perm.data_ptr(), iota.data_ptr(),
+                                                  int(bits), tmp.data_ptr(), nb, self.st()), "mg_stable_argsort_i32")
+        return perm
+
+    def row_col_order(self, rows, cols, n_rows, n_cols):
+        """stable sort order of (row, col) pairs: by column, then stably by row"""
+        bits_c = max(1, int(np.ceil(np.log2(max(n_cols, 2)))))
+        bits_r = max(1, int(np.ceil(np.log2(max(n_rows, 2)))))
+        if cols is None:
+            return self.argsort_i32(rows, bits_r)
+        o1 = self.argsort_i32(cols, bits_c)
+        o2 = self.argsort_i32(rows[o1.long()].contiguous(), bits_r)
+        return o1[o2.long()].contiguous()
+
     # ---- kernels -------------------------------------------------------------------------------------------
     def transpose(self, A):
         t = self.torch
@@ -212,11 +233,15 @@ def build_natural(S, A, Q_list):
     """Upload A and the transfer operators and form the Galerkin hierarchy in natural ordering on the device.
     Returns (A_host0, A_nat, Q_nat, QT_nat)."""
     L = len(Q_list) + 1
-    A_host0 = F.canonical_csr(sp.csc_matrix(A))            # Solver.py:18 stores csc_matrix(matrix)
-    A_nat = [S.upload(A_host0)]
+    if isinstance(A, DevCSR):                              # already on the device (assembly_device / neural2d)
+        A_host0 = None
+        A_nat = [A]
+    else:
+        A_host0 = F.canonical_csr(sp.csc_matrix(A))        # Solver.py:18 stores csc_matrix(matrix)
+        A_nat = [S.upload(A_host0)]
     Q_nat, QT_nat = [], []
     for l in range(L - 1):
-        Q = S.upload(Q_list[l])
+        Q = Q_list[l] if isinstance(Q_list[l], DevCSR) else S.upload(Q_list[l])
         if Q.shape[0] != A_nat[l].shape[0]:
             raise ValueError("Q_%d has %d rows, level operator has %d" % (l, Q.shape[0], A_nat[l].shape[0]))
         QT = S.transpose(Q)
@@ -235,8 +260,8 @@ def level_colors(S, smoother, colors, A_host0, A_nat):
             if colors is not None and colors[l] is not None:
                 col = np.ascontiguousarray(colors[l], dtype=np.int32)
             else:
-                pat = A_host0 if l == 0 else F.raw_csr(A_nat[l].indptr.cpu().numpy(), A_nat[l].indices.cpu().numpy(),
-                                                       np.zeros(A_nat[l].nnz), A_nat[l].shape)
+                pat = A_host0 if (l == 0 and A_host0 is not None) else F.raw_csr(
+                    A_nat[l].indptr.cpu().numpy(), A_nat[l].indices.cpu().numpy(), np.zeros(A_nat[l].nnz), A_nat[l].shape)
                 col = F.greedy_colors(pat)[0]
             out.append(col)
         else:
@@ -267,7 +292,7 @@ def build_replicated_level(h, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, ipe
         lev.nnz_Q = Q_nat[l].nnz
         if h.smoother == "lexgs":
             lev.csr = (A_nat[l].indptr, A_nat[l].indices, A_nat[l].values)
-            pat = A_host0 if l == 0 else S.download(A_nat[l])
+            pat = A_host0 if (l == 0 and A_host0 is not None) else S.download(A_nat[l])
             lp, lr = F.lex_levels(pat)
             lev.lex_ptr = torch.from_numpy(lp).to(dev)
             lev.lex_rows = torch.from_numpy(lr).to(dev)

@@ -94,6 +94,8 @@ def run_case(mesh, levels, mean, std):
         out["final_M_data"], out["final_M_shape"] = Mc.data.astype(np.float64), np.array(Mc.shape)
         Ac = sp.coo_matrix(sp.csr_matrix(A))
         out["A_row"], out["A_col"], out["A_data"] = Ac.row.astype(np.int32), Ac.col.astype(np.int32), Ac.data
+        out["mesh_p"] = np.asarray(mesh.get_points(), dtype=np.float64)          # inputs of the reference's assembly
+        out["mesh_conn"] = np.asarray(mesh.get_connections(), dtype=np.int64)
     return out
 
 
