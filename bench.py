@@ -149,10 +149,33 @@ def build_problem(a, n):
         from learnmultigrid_b200.neural2d import MassSurrogate
         from learnmultigrid_b200.solvers.Multigrid import NeuralMG_2D
         pb = P.irregular_p1_2d(n, seed=42)
+        asm_ms = None
+        try:                         # the same operators by the device assembler, timed (informational)
+            import torch
+            from learnmultigrid_b200.assembly_device import DeviceAssembler
+            from learnmultigrid_b200.assembly.LoadFunction import LoadFunction
+            from learnmultigrid_b200.assembly.Quadrature import Quadrature2D
+            from learnmultigrid_b200.assembly.ShapeFunction import FunctionTriangle, GradientTriangle
+            asm = DeviceAssembler()
+            q = Quadrature2D(3)
+            for rep in range(2):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                m = asm.mesh_to_device(pb["mesh"])
+                Ad = asm.stiffness(*m, GradientTriangle(1), q)
+                Md = asm.mass(*m, FunctionTriangle(1), q)
+                bd = asm.load(*m, LoadFunction(lambda pts: -1.0), FunctionTriangle(1), q)
+                Ad = asm.dirichlet(Ad, pb["boundary"], bd)
+                torch.cuda.synchronize()
+                asm_ms = (time.perf_counter() - t0) * 1e3
+            assert Ad.nnz == pb["A"].nnz and Md.nnz == pb["M"].nnz
+            del Ad, Md, bd, asm
+        except ImportError:
+            pass
         nmg = NeuralMG_2D(pb["A"], pb["rhs"], MassSurrogate(), pb["M"], np.ones(43), np.zeros(43))
         t0 = time.perf_counter()
         nmg.define_hierarchy(a.levels)
-        NN_BUILD[n] = {"define_hierarchy_s": round(time.perf_counter() - t0, 3),
+        NN_BUILD[n] = {"define_hierarchy_s": round(time.perf_counter() - t0, 3), "device_assembly_A_M_rhs_ms": asm_ms,
                        "coarse_nodes": [int(q.shape[1]) for q in nmg.l_hierarchy],
                        "nnz_Q": [int(q.nnz) for q in nmg.l_hierarchy]}
         return pb["A"], pb["rhs"], nmg.l_hierarchy
