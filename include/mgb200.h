@@ -313,7 +313,17 @@ typedef struct {
     double *d_gather_tmp;
     const int32_t *d_gather_self_idx;   /* positions of the own block in the full coarse vector                     */
     int64_t n_gather_own;
+    /* per slice of A / Q / Q^T: 1 if the slice reads halo columns (mg_sell_halo_mask).  With these, an exchange is not
+     * launched on its own but rides on the next SELL kernel that reads the exchanged vector (mg_set_fused_exchange):
+     * extra CTAs in front push / poll / unpack, the compute CTAs of masked slices wait for them, all others overlap
+     * the exchange.  NULL: every slice waits. */
+    const unsigned char *d_mask_A, *d_mask_Q, *d_mask_QT;
 } mg_dist_level;
+/* d_mask[s] = 1 if slice s of the SELL matrix holds a column >= first_halo_col */
+int mg_sell_halo_mask(const mg_sell *A, int64_t first_halo_col, unsigned char *d_mask, void *stream);
+/* 1 (default): in mg_vcycle_dist with multicolour Gauss-Seidel the halo exchanges ride on the following SELL kernel
+ * (see mg_dist_level); 0: every exchange is a kernel of its own.  Same results.  Returns the previous setting. */
+int mg_set_fused_exchange(int enabled);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* P1 assembly on the device (csrc/assembly_kernels.cu).  Replaces the per-element Python loops of

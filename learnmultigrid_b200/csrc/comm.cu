@@ -7,7 +7,7 @@
 // program's epoch, then polls its own staging area until the peers' packets carry the same tag and unpacks them.  It is ordinary stream work, so a whole V-cycle including its exchanges is captured in one CUDA graph; the
 // epoch is a device counter the program advances at its end, staging is double-buffered by epoch parity so a rank
 // that runs ahead into the next program never overwrites data its peer has not consumed yet.
-#include "common.cuh"
+#include "exchange.cuh"
 
 namespace mgb {
 
@@ -22,102 +22,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ unsigned long long global_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-
-// Wire format ("LL", as in low-latency collectives): every double travels as two 8-byte words, each holding 4 data
-// bytes and the low 32 bits of the program's epoch as a tag.  An aligned 8-byte store lands atomically, so the
-// receiver simply polls each word until its tag matches: no fence, no separate flag, one NVLink traversal of latency.
-// Staging slots written two programs ago (same parity buffer) carry an older tag and can never match.  Messages of
-// length zero still shake hands through the flag word, which keeps the run-ahead argument of mgb200.h intact.
-struct ExPeer {
-    const int32_t *send_idx;
-    int64_t send_off, send_cnt;
-    ulonglong2 *peer_stage;             // in the PEER's arena: where my message lands (parity 0)
-    unsigned long long *peer_flag;      // in the PEER's arena: flags[my rank][site]
-    const ulonglong2 *my_stage;         // in MY arena: where the peer's message lands (parity 0)
-    const unsigned long long *my_flag;  // in MY arena: flags[peer][site]
-    const int32_t *recv_idx;
-    int64_t recv_off, recv_cnt;
-};
-struct ExArgs {
-    int npeers, ctas_per_peer;
-    const double *src;
-    double *dst;
-    const unsigned long long *epoch;
-    unsigned int *err;
-    int64_t parity_stride;              // 16-byte packets between the two staging buffers of a region
-    unsigned long long timeout_ns;
-    unsigned int site;
-    int dry;                            // warm-up launch: do nothing
-    ExPeer p[MG_MAX_RANKS];
-};
-
-__device__ __forceinline__ void st_packet(ulonglong2 *p, unsigned long long w0, unsigned long long w1) {
-    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(w0), "l"(w1) : "memory");
-}
-__device__ __forceinline__ void ld_packet(const ulonglong2 *p, unsigned long long &w0, unsigned long long &w1) {
-    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(p) : "memory");
-}
-__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 
 __global__ void __launch_bounds__(kBlock) exchange_kernel(const ExArgs a) {
     pdl_prologue();
     if (a.dry) return;
-    const int p = blockIdx.x / a.ctas_per_peer, chunk = blockIdx.x % a.ctas_per_peer;
-    const ExPeer &P = a.p[p];
-    const unsigned long long epoch = *a.epoch;
-    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
-    const int64_t par = (int64_t)(epoch & 1ull) * a.parity_stride;
-    const int64_t stride = (int64_t)a.ctas_per_peer * kBlock;
-    const int64_t first = (int64_t)chunk * kBlock + threadIdx.x;
-    // ---- push: never waits for anybody
-    ulonglong2 *out = P.peer_stage + par;
-    for (int64_t i = first; i < P.send_cnt; i += stride) {
-        const unsigned long long bits =
-            (unsigned long long)__double_as_longlong(P.send_idx ? a.src[P.send_idx[i]] : a.src[P.send_off + i]);
-        st_packet(out + i, (bits & 0xffffffffull) | tag, (bits >> 32) | tag);
-    }
-    if (P.send_cnt == 0 && first == 0) st_relaxed_sys(P.peer_flag, epoch);
-    // ---- receive: poll every packet until both words carry this program's tag
-    const ulonglong2 *in = P.my_stage + par;
-    bool timed_out = false;
-    for (int64_t i = first; i < P.recv_cnt; i += stride) {
-        unsigned long long w0, w1;
-        ld_packet(in + i, w0, w1);
-        if ((w0 & 0xffffffff00000000ull) != tag || (w1 & 0xffffffff00000000ull) != tag) {
-            const unsigned long long t0 = global_timer_ns();
-            unsigned int spins = 0;
-            for (;;) {
-                ld_packet(in + i, w0, w1);
-                if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
-                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { timed_out = true; break; }
-            }
-            if (timed_out) break;
-        }
-        const double v = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-        if (P.recv_idx) a.dst[P.recv_idx[i]] = v;
-        else a.dst[P.recv_off + i] = v;
-    }
-    if (P.recv_cnt == 0 && first == 0) {
-        const unsigned long long t0 = global_timer_ns();
-        unsigned int spins = 0;
-        while (ld_relaxed_sys(P.my_flag) < epoch) {
-            __nanosleep(20);
-            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { timed_out = true; break; }
-        }
-    }
-    if (timed_out) atomicCAS(a.err, 0u, a.site + 1u);
+    exchange_role(a, (int)blockIdx.x);
 }
 
 __global__ void comm_init_kernel(unsigned long long *hdr) {
@@ -167,33 +76,36 @@ static inline int64_t staging_offset(int world, int max_sites) {
     return align_up(kHeaderBytes + (int64_t)world * max_sites * 8, 4096);
 }
 
-int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, cudaStream_t st) {
+// Book the next site of the program for `x` and fill the kernel arguments.  *grid_out = number of exchange CTAs
+// (0: nothing to launch, e.g. no peers).  Returns MG_OK or an error.
+int comm_prepare(mg_comm *c, const mg_xfer *x, const double *src, double *dst, ExArgs *out, int *grid_out) {
+    *grid_out = 0;
     if (!c || !x) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "null argument");
     if (c->site >= c->max_sites) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "program has more exchange sites than the arena has flags");
     const int site = c->site++;
+    ExArgs &a = *out;
+    memset(&a, 0, sizeof(a));
+    char *mine = (char *)c->d_arena[c->rank];
+    a.epoch = (const unsigned long long *)mine;
+    a.err = (unsigned int *)(mine + 8);
+    a.done = (unsigned int *)(mine + 16);
+    a.ready = (unsigned long long *)(mine + 24);
+    a.timeout_ns = (unsigned long long)((c->timeout_s > 0 ? c->timeout_s : 10.0) * 1e9);
+    a.site = (unsigned)site;
     if (c->dry_run) {
-        ExArgs a;
-        memset(&a, 0, sizeof(a));
         a.dry = 1;
+        a.npeers = 1;
         a.ctas_per_peer = 1;
-        launch_k(exchange_kernel, (unsigned)(1), (unsigned)kBlock, st, a);
-        MG_CHECK_LAUNCH("exchange (dry run)");
+        *grid_out = 1;
         return MG_OK;
     }
     if (x->npeers == 0) return MG_OK;
     if (x->npeers == c->world - 1) c->all_pairs = 1;
     if (x->npeers < 0 || x->npeers > MG_MAX_RANKS) return set_error(MG_ERR_INVALID, "mg_comm_exchange", "bad peer count");
-    ExArgs a;
-    memset(&a, 0, sizeof(a));
-    char *mine = (char *)c->d_arena[c->rank];
     a.npeers = x->npeers;
     a.src = src;
     a.dst = dst;
-    a.epoch = (const unsigned long long *)mine;
-    a.err = (unsigned int *)(mine + 8);
     a.parity_stride = c->region_bytes / 16;
-    a.timeout_ns = (unsigned long long)((c->timeout_s > 0 ? c->timeout_s : 10.0) * 1e9);
-    a.site = (unsigned)site;
     const int64_t stg = staging_offset(c->world, c->max_sites);
     int64_t longest = 1;
     for (int k = 0; k < x->npeers; ++k) {
@@ -224,7 +136,16 @@ int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, 
     if (cpp > kMaxCtasPerPeer) cpp = kMaxCtasPerPeer;
     if (cpp < 1) cpp = 1;
     a.ctas_per_peer = cpp;
-    launch_k(exchange_kernel, (unsigned)((unsigned)(cpp * x->npeers)), (unsigned)kBlock, st, a);
+    *grid_out = cpp * x->npeers;
+    return MG_OK;
+}
+
+int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, cudaStream_t st) {
+    ExArgs a;
+    int grid = 0;
+    int rc = comm_prepare(c, x, src, dst, &a, &grid);
+    if (rc || grid == 0) return rc;
+    launch_k(exchange_kernel, (unsigned)grid, (unsigned)kBlock, st, a);
     MG_CHECK_LAUNCH("exchange");
     return MG_OK;
 }

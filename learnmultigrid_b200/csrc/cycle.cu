@@ -4,9 +4,22 @@
 //   -> prolong + correct (:115) -> post-smooth (:121).
 // The Galerkin product (:97-98) and the coarse factorisation (:106), which the reference repeats in every
 // cycle, are hoisted to setup; the arithmetic of a cycle is unchanged.
-#include "common.cuh"
+#include "exchange.cuh"
 
 namespace mgb {
+
+struct SellFuse {          // mirrors sell_kernels.cu
+    ExArgs ex;
+    int nex;
+    const unsigned char *mask;
+};
+int comm_prepare(mg_comm *, const mg_xfer *, const double *, double *, ExArgs *, int *);
+bool sell_fusable(const mg_sell *, int64_t, int64_t);
+int sell_spmv_fused(const mg_sell *, const double *, double *, const SellFuse *, cudaStream_t);
+int sell_residual_fused(const mg_sell *, const double *, const double *, double *, const SellFuse *, cudaStream_t);
+int sell_gs_rows_fused(const mg_sell *, double *, const double *, int64_t, int64_t, const SellFuse *, cudaStream_t);
+int sell_prolong_fused(const mg_sell *, const double *, const double *, double *, const SellFuse *, cudaStream_t);
+int g_fused_exchange = 1;
 
 thread_local char g_last_error[512] = "";
 thread_local int64_t g_launch_count = 0;
@@ -34,6 +47,49 @@ int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStre
         int _rc = (expr);       \
         if (_rc) return _rc;    \
     } while (0)
+
+// Deferred exchange: with multicolour Gauss-Seidel an exchange of a level vector is not launched when it is issued
+// but handed to the next SELL kernel that gathers from that vector, which carries it as extra CTAs (sell_kernel_fused).
+// Anything else that needs the halo first calls flush_pending().
+struct Pending {
+    const mg_xfer *x = nullptr;
+    double *vec = nullptr;
+};
+static thread_local Pending g_pend;
+
+static int flush_pending(mg_comm *comm, cudaStream_t st) {
+    if (!g_pend.x) return MG_OK;
+    const mg_xfer *x = g_pend.x;
+    double *v = g_pend.vec;
+    g_pend.x = nullptr;
+    return comm_exchange(comm, x, v, v, st);
+}
+// issue an exchange of vector v: deferred if allowed, immediate otherwise
+static int issue_exchange(mg_comm *comm, const mg_xfer *x, double *v, bool may_defer, cudaStream_t st) {
+    MG_TRY(flush_pending(comm, st));
+    if (!may_defer || !g_fused_exchange) return comm_exchange(comm, x, v, v, st);
+    g_pend.x = x;
+    g_pend.vec = v;
+    return MG_OK;
+}
+// before a SELL launch that gathers from `xop` over rows [row0,row1) of M: take the pending exchange along if it is on
+// that vector and the launch can carry it; otherwise flush it.  *use tells whether `f` was filled.
+static int take_pending(mg_comm *comm, const double *xop, const mg_sell *M, int64_t row0, int64_t row1,
+                        const unsigned char *mask, SellFuse *f, bool *use, cudaStream_t st) {
+    *use = false;
+    if (!g_pend.x) return MG_OK;
+    if (g_pend.vec != xop || !sell_fusable(M, row0, row1)) return flush_pending(comm, st);
+    const mg_xfer *x = g_pend.x;
+    double *v = g_pend.vec;
+    g_pend.x = nullptr;
+    int grid = 0;
+    MG_TRY(comm_prepare(comm, x, v, v, &f->ex, &grid));
+    if (grid == 0) return MG_OK;
+    f->nex = grid;
+    f->mask = mask;
+    *use = true;
+    return MG_OK;
+}
 
 // Row-partitioned levels (mg_level.dist != NULL): L.n counts the OWNED rows, the level vectors carry
 // dist->n_halo more entries behind them, and every kernel that changes a vector other ranks read is followed by an
@@ -81,8 +137,16 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
         for (int s = 0; s < steps; ++s)
             for (int cc = 0; cc < L.ncolors; ++cc) {
                 const int c = reverse ? L.ncolors - 1 - cc : cc;
-                MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
-                if (L.dist) MG_TRY(comm_exchange(comm, L.dist->xfer_color + c, *cur, *cur, st));
+                if (L.dist) {
+                    SellFuse f;
+                    bool use;
+                    MG_TRY(take_pending(comm, *cur, &L.A, L.h_color_ptr[c], L.h_color_ptr[c + 1], L.dist->d_mask_A, &f, &use, st));
+                    if (use) MG_TRY(sell_gs_rows_fused(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], &f, st));
+                    else MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
+                    MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
+                } else {
+                    MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
+                }
             }
         return MG_OK;
     }
@@ -120,28 +184,46 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
             else prolong_flip = true;
         }
     }
+    if (!L.dist) MG_TRY(flush_pending(comm, st));                    // replicated level: nothing may be in flight
+    const bool defer = P.smoother == MG_SMOOTH_MCGS;                 // exchanges ride on the next SELL kernel
+    SellFuse f;
+    bool use = false;
     MG_TRY(smooth(comm, L, P, P.nu_pre, &cur, &alt, zero_guess, false, st));
-    MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));              // res = rhs - A u
-    if (L.dist && L.dist->xfer_gather) {
+    if (L.dist) {
+        const mg_dist_level &D = *L.dist;
+        MG_TRY(take_pending(comm, cur, &L.A, 0, L.A.nrows, D.d_mask_A, &f, &use, st));
+        if (use) MG_TRY(sell_residual_fused(&L.A, cur, L.d_b, L.d_r, &f, st));       // res = rhs - A u
+        else MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));
+        MG_TRY(issue_exchange(comm, D.xfer_all, L.d_r, defer, st));                  // the restriction reads halo rows
         // last partitioned level: restrict into the owned block of the coarse rhs, then gather it into every
         // rank's full vector (the coarse levels below are replicated)
-        const mg_dist_level &D = *L.dist;
-        MG_TRY(halo_all(comm, L, L.d_r, st));
-        MG_TRY(sell_spmv(&L.QT, L.d_r, D.d_gather_tmp, st));         // res_coarse = Q^T res (owned rows)
-        MG_TRY(vec_scatter(D.n_gather_own, D.d_gather_self_idx, D.d_gather_tmp, C.d_b, st));
-        MG_TRY(comm_exchange(comm, D.xfer_gather, D.d_gather_tmp, C.d_b, st));
+        double *rc = D.xfer_gather ? D.d_gather_tmp : C.d_b;
+        MG_TRY(take_pending(comm, L.d_r, &L.QT, 0, L.QT.nrows, D.d_mask_QT, &f, &use, st));
+        if (use) MG_TRY(sell_spmv_fused(&L.QT, L.d_r, rc, &f, st));                  // res_coarse = Q^T res (owned rows)
+        else MG_TRY(sell_spmv(&L.QT, L.d_r, rc, st));
+        if (D.xfer_gather) {
+            MG_TRY(vec_scatter(D.n_gather_own, D.d_gather_self_idx, D.d_gather_tmp, C.d_b, st));
+            MG_TRY(comm_exchange(comm, D.xfer_gather, D.d_gather_tmp, C.d_b, st));
+        }
     } else {
-        MG_TRY(halo_all(comm, L, L.d_r, st));
+        MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));          // res = rhs - A u
         MG_TRY(sell_spmv(&L.QT, L.d_r, C.d_b, st));                  // res_coarse = Q^T res
     }
     MG_TRY(vcycle_rec(comm, levels, nlevels, l + 1, P, st));         // u_coarse
-    if (prolong_flip) {
-        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, alt, st));             // u = u + Q u_coarse (out of place)
-        double *t = cur; cur = alt; alt = t;
+    double *out = prolong_flip ? alt : cur;                          // u = u + Q u_coarse (out of place when flipping)
+    if (L.dist) {
+        // a partitioned coarse level leaves the exchange of its last sweep pending on C.d_x
+        MG_TRY(take_pending(comm, C.d_x, &L.Q, 0, L.Q.nrows, L.dist->d_mask_Q, &f, &use, st));
+        if (use) MG_TRY(sell_prolong_fused(&L.Q, C.d_x, cur, out, &f, st));
+        else MG_TRY(sell_prolong(&L.Q, C.d_x, cur, out, st));
     } else {
-        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, cur, st));
+        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, out, st));
     }
-    MG_TRY(halo_all(comm, L, cur, st));
+    if (prolong_flip) { double *t = cur; cur = alt; alt = t; }
+    // every boundary value changed.  Deferred, this exchange rides on the first post-smoothing sweep, which rewrites
+    // its own colour while the values are being sent: harmless, a colour never reads itself and is sent again right
+    // after its sweep.
+    if (L.dist) MG_TRY(issue_exchange(comm, L.dist->xfer_all, cur, defer, st));
     MG_TRY(smooth(comm, L, P, P.nu_post, &cur, &alt, false, P.reverse_post != 0, st));
     if (cur != L.d_x) MG_TRY(vec_axpby(vec_len(L), 1.0, cur, 0.0, nullptr, L.d_x, st));   // safety net; not reached
     return MG_OK;
@@ -178,6 +260,11 @@ using namespace mgb;
 extern "C" {
 
 int mg_version(void) { return 100; }
+int mg_set_fused_exchange(int enabled) {
+    const int prev = g_fused_exchange;
+    g_fused_exchange = enabled ? 1 : 0;
+    return prev;
+}
 int mg_set_pdl(int enabled) {
     const int prev = g_pdl;
     g_pdl = enabled ? 1 : 0;
@@ -227,6 +314,7 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t before = g_launch_count;
     MG_TRY(mg_comm_begin(comm));
+    g_pend.x = nullptr;
     int rc = MG_OK;
     if (norm) {   // outer loop of Multigrid.solve (:62-63): ||b - A x||^2 over all row blocks
         MG_REQUIRE(norm->d_partials && norm->d_local && norm->d_slots && norm->d_norm2, "norm workspace missing");
@@ -234,6 +322,8 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
         if (!rc) rc = mg_comm_allreduce_sum(comm, norm->d_local, norm->d_slots, norm->d_norm2, stream);
     }
     if (!rc && params) rc = vcycle_rec(comm, levels, nlevels, 0, *params, st);
+    if (!rc) rc = flush_pending(comm, st);      // the halo of the iterate is current when the program ends
+    g_pend.x = nullptr;
     if (!rc) rc = mg_comm_end(comm, stream);
     g_last_cycle_launches = g_launch_count - before;
     return rc;

@@ -5,7 +5,7 @@
 // gathers go through L1/L2, which hold the few grid lines a structured stencil touches.
 // Every kernel is HBM-bound: algorithmic bytes per row = 12*nnz_row + 4 (CSR yardstick of SURVEY 8d) plus
 // the vector traffic listed at each launcher.
-#include "common.cuh"
+#include "exchange.cuh"
 
 namespace mgb {
 
@@ -49,17 +49,19 @@ __device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const d
 // The microbenchmark behind these choices is tools/sellbench.cu (profiles/r01_sellbench.log): occupancy x bytes in
 // flight per thread decides; at 32 registers and 60 B per thread the fine-level sweep reaches the DRAM limit
 // (6.8 TB/s algorithmic, ~7.1 TB/s of actual traffic), a rolled loop stays at 5.4 TB/s.
-template <int MODE, int LEN, bool UNIFORM>
-__global__ void __launch_bounds__(kBlock)
-sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
-            double *y, double omega, double *__restrict__ partials) {
-    pdl_prologue();
-    const int64_t row = A.first_row + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+template <int MODE, int LEN, bool UNIFORM, bool FUSED>
+__device__ __forceinline__ void
+sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
+          double *__restrict__ partials, int64_t bid, const ExArgs *fx, const unsigned char *__restrict__ mask) {
+    const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
     const bool active = row >= A.row_begin && row < A.row_end;
     double contrib = 0.0;
     if (row < A.row_end) {   // warp-uniform except in the last slice
         const int64_t slice = row >> 5;
         const int lane = (int)(row & 31);
+        if (FUSED) {      // this slice reads halo columns: wait until the exchange CTAs of this launch have unpacked them
+            if (!mask || mask[slice]) fused_wait_ready(*fx);
+        }
         int64_t base;
         int len;
         if (UNIFORM) {
@@ -100,8 +102,33 @@ sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const dou
     }
     if (MODE == RESNORM) {
         const double s = block_sum<kBlock>(contrib);
-        if (threadIdx.x == 0) partials[blockIdx.x] = s;
+        if (threadIdx.x == 0) partials[bid] = s;
     }
+}
+
+template <int MODE, int LEN, bool UNIFORM>
+__global__ void __launch_bounds__(kBlock)
+sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
+            double *y, double omega, double *__restrict__ partials) {
+    pdl_prologue();
+    sell_body<MODE, LEN, UNIFORM, false>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
+}
+
+// The same kernel carrying an exchange site (multi-GPU, csrc/comm.cu): the first npeers*ctas_per_peer CTAs push the
+// boundary values the previous kernel produced, poll for the peers' packets and unpack them into the halo of x; the
+// compute CTAs whose slice reads halo columns (mask) wait for that, all others start at once.  The exchange latency
+// (NVLink flight + polling) is hidden behind the interior rows, and the site costs no launch of its own.
+template <int MODE, int LEN, bool UNIFORM>
+__global__ void __launch_bounds__(kBlock)
+sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
+                  double *__restrict__ partials, const ExArgs fx, const unsigned char *__restrict__ mask) {
+    pdl_prologue();
+    const int nex = fx.npeers * fx.ctas_per_peer;
+    if ((int)blockIdx.x < nex) {
+        fused_exchange_cta(fx, (int)blockIdx.x);
+        return;
+    }
+    sell_body<MODE, LEN, UNIFORM, true>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
 }
 
 // ---- long rows: four warps per slice ---------------------------------------------------------------------------------
@@ -210,6 +237,21 @@ static int64_t g_wide_min_len = 9;
 // which then streams at the DRAM limit (measured: profiles/r01_launches_c3_quasi_*.txt)
 static int64_t g_wide_max_rows = 1 << 18;
 
+// mask[s] = 1 if slice s holds a column >= first_halo_col (one warp per slice)
+__global__ void __launch_bounds__(kBlock)
+sell_halo_mask_kernel(int64_t nslices, const int64_t *__restrict__ slice_ptr, int64_t uniform_len,
+                      const int32_t *__restrict__ cols, int64_t first_halo_col, unsigned char *__restrict__ mask) {
+    const int64_t s = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (s >= nslices) return;
+    const int64_t base = uniform_len > 0 ? s * kSlice * uniform_len : slice_ptr[s];
+    const int64_t end = uniform_len > 0 ? base + kSlice * uniform_len : slice_ptr[s + 1];
+    int hit = 0;
+    for (int64_t p = base + lane; p < end; p += 32) hit |= cols[p] >= first_halo_col;
+    hit = __any_sync(0xffffffffu, hit);
+    if (lane == 0) mask[s] = hit ? 1 : 0;
+}
+
 // second stage of the deterministic norm / dot: one CTA sums the per-block partials in a fixed order
 __global__ void __launch_bounds__(1024) reduce_partials_kernel(const double *__restrict__ partials, int64_t n,
                                                                double *__restrict__ out) {
@@ -228,10 +270,26 @@ int launch_sell_tma(const mg_sell *M, int64_t max_len, const double *x, const do
 // rows per launch from which the bulk-async staged kernel (sell_tma.cu) is used; 0 disables it
 static int64_t g_tma_min_rows = 0;   // off by default: the register-staged kernel is as fast (see sell_tma.cu)
 
+// an exchange site riding on a SELL launch (prepared by comm_prepare)
+struct SellFuse {
+    ExArgs ex;
+    int nex;                       // exchange CTAs in front of the compute CTAs
+    const unsigned char *mask;     // per slice of the matrix: reads halo columns (NULL: assume every slice does)
+};
+
+// which launches can carry an exchange site: the thread-per-row kernel only
+bool sell_fusable(const mg_sell *A, int64_t row0, int64_t row1) {
+    if (row1 <= row0 || g_tma_min_rows > 0) return false;
+    const int64_t ml = A->max_slice_len;
+    if (g_wide_min_len > 0 && ml >= g_wide_min_len && ml <= kWideMaxLen && row1 - row0 <= g_wide_max_rows) return false;
+    return true;
+}
+
 template <int MODE>
 static int launch_sell(const mg_sell *A, const double *x, const double *b, const double *aux, double *y,
                        double omega, double *partials, int64_t row0, int64_t row1, cudaStream_t st,
-                       const char *name, int *nblocks_out = nullptr) {
+                       const char *name, int *nblocks_out = nullptr, const SellFuse *fuse = nullptr) {
+    if (fuse && !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot carry an exchange site");
     if (row1 <= row0) return MG_OK;
     if (g_tma_min_rows > 0 && row1 - row0 >= g_tma_min_rows && A->max_slice_len > 0) {
         int grid = 0;
@@ -270,7 +328,10 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     if (grid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
 #define MG_SELL_CASE(L)                                                                                      \
     do {                                                                                                     \
-        if (uni) launch_k(sell_kernel<MODE, L, true>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials); \
+        if (fuse) {                                                                                          \
+            if (uni) launch_k(sell_kernel_fused<MODE, L, true>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
+            else launch_k(sell_kernel_fused<MODE, L, false>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask);     \
+        } else if (uni) launch_k(sell_kernel<MODE, L, true>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials); \
         else launch_k(sell_kernel<MODE, L, false>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);     \
     } while (0)
     switch (ml) {
@@ -283,7 +344,8 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
         case 7: MG_SELL_CASE(7); break;
         case 8: MG_SELL_CASE(8); break;
         default:   // long rows, or length unknown (0)
-            launch_k(sell_kernel<MODE, 0, false>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);
+            if (fuse) launch_k(sell_kernel_fused<MODE, 0, false>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask);
+            else launch_k(sell_kernel<MODE, 0, false>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);
     }
 #undef MG_SELL_CASE
     MG_CHECK_LAUNCH(name);
@@ -296,6 +358,20 @@ int sell_spmv(const mg_sell *A, const double *x, double *y, cudaStream_t st) {
 }
 int sell_residual(const mg_sell *A, const double *x, const double *b, double *r, cudaStream_t st) {
     return launch_sell<RESID>(A, x, b, nullptr, r, 0.0, nullptr, 0, A->nrows, st, "sell_residual");
+}
+// variants carrying an exchange site
+int sell_spmv_fused(const mg_sell *A, const double *x, double *y, const SellFuse *f, cudaStream_t st) {
+    return launch_sell<SPMV>(A, x, nullptr, nullptr, y, 0.0, nullptr, 0, A->nrows, st, "sell_spmv", nullptr, f);
+}
+int sell_residual_fused(const mg_sell *A, const double *x, const double *b, double *r, const SellFuse *f, cudaStream_t st) {
+    return launch_sell<RESID>(A, x, b, nullptr, r, 0.0, nullptr, 0, A->nrows, st, "sell_residual", nullptr, f);
+}
+int sell_gs_rows_fused(const mg_sell *A, double *x, const double *b, int64_t row0, int64_t row1, const SellFuse *f,
+                       cudaStream_t st) {
+    return launch_sell<GS>(A, x, b, nullptr, x, 0.0, nullptr, row0, row1, st, "sell_gs_rows", nullptr, f);
+}
+int sell_prolong_fused(const mg_sell *Q, const double *e, const double *u, double *uo, const SellFuse *f, cudaStream_t st) {
+    return launch_sell<PROLONG>(Q, e, nullptr, u, uo, 0.0, nullptr, 0, Q->nrows, st, "sell_prolong", nullptr, f);
 }
 int sell_residual_norm2(const mg_sell *A, const double *x, const double *b, double *partials, double *out,
                         cudaStream_t st) {
@@ -342,6 +418,14 @@ int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, dou
 }
 int64_t mg_norm_workspace_size(int64_t n) { return (n + kBlock - 1) / kBlock + 1; }
 /* rows per launch from which the bulk-async staged SELL kernel is used (0 = never); returns the old value */
+int mg_sell_halo_mask(const mg_sell *A, int64_t first_halo_col, unsigned char *d_mask, void *stream) {
+    MG_REQUIRE(A && d_mask && A->nrows > 0, "null argument");
+    const int64_t ns = A->nslices;
+    sell_halo_mask_kernel<<<(unsigned)((ns * 32 + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        ns, A->d_slice_ptr, A->uniform_len, A->d_cols, first_halo_col, d_mask);
+    MG_CHECK_LAUNCH("sell_halo_mask");
+    return MG_OK;
+}
 int64_t mg_set_wide_min_len(int64_t len) {
     const int64_t prev = g_wide_min_len;
     g_wide_min_len = len < 0 ? 0 : len;

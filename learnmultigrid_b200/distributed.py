@@ -386,6 +386,15 @@ class DistributedHierarchy(DeviceHierarchy):
             lev.QT = S.to_sell(S.permute(loc, cperm, None))
             del blk, loc
             self._build_xfers(lev, l, everyone, offs, iperms, Lp)
+            # which slices of A / Q / Q^T read halo columns (lets an exchange ride on the kernel that needs it)
+            lev.masks = []
+            for Msell, first_halo in ((lev.A, p.n_own), (lev.Q, lays[l + 1].n_own), (lev.QT, p.n_own)):
+                mk = torch.zeros(max(int(Msell.struct.nslices), 1), dtype=torch.uint8, device=dev)
+                _lib.check(self.lib.mg_sell_halo_mask(ctypes.byref(Msell.struct), int(first_halo), mk.data_ptr(),
+                                                      S.st()), "mg_sell_halo_mask")
+                lev.masks.append(mk)
+            d = lev.dist_struct
+            d.d_mask_A, d.d_mask_Q, d.d_mask_QT = (m.data_ptr() for m in lev.masks)
             self.levels.append(lev)
         del lays
         # ---- replicated levels
