@@ -21,9 +21,12 @@ struct SellArgs {
 
 // accumulate CNT consecutive entries of a row: all cols/vals loads are issued first, then all x gathers, then the
 // sums in storage order.  Straight-line code: CNT*12 bytes per thread in flight at ~4 registers per entry.
+// `halo_wait` (fused launches only): this slice reads halo columns, so between the matrix loads (which do not depend on
+// the halo and are already in flight) and the x gathers, wait until the launch's exchange CTAs have unpacked it.
 template <int MODE, int CNT>
 __device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const double *__restrict__ v,
-                                          const double *x, int64_t row, double &sum, double &diag) {
+                                          const double *x, int64_t row, double &sum, double &diag,
+                                          unsigned char halo_wait = 0, const ExArgs *fx = nullptr) {
     int32_t cc[CNT];
     double vv[CNT], xx[CNT];
 #pragma unroll
@@ -31,6 +34,7 @@ __device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const d
         cc[j] = ld_stream(c + j * kSlice);
         vv[j] = ld_stream(v + j * kSlice);
     }
+    if (halo_wait) fused_wait_ready(*fx);
 #pragma unroll
     for (int j = 0; j < CNT; ++j) xx[j] = x[cc[j]];
 #pragma unroll
@@ -59,9 +63,8 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
     if (row < A.row_end) {   // warp-uniform except in the last slice
         const int64_t slice = row >> 5;
         const int lane = (int)(row & 31);
-        if (FUSED) {      // this slice reads halo columns: wait until the exchange CTAs of this launch have unpacked them
-            if (!mask || mask[slice]) fused_wait_ready(*fx);
-        }
+        unsigned char hw = 0;      // fused launch: does this slice read halo columns? (load issued now, used in row_chunk)
+        if (FUSED) hw = mask ? mask[slice] : 1;
         int64_t base;
         int len;
         if (UNIFORM) {
@@ -75,12 +78,18 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
         const int32_t *__restrict__ c = A.cols + base + lane;
         double sum = 0.0, diag = 0.0;
         if (LEN > 0 && (UNIFORM || len == LEN)) {
-            row_chunk<MODE, (LEN > 0 ? LEN : 1)>(c, v, x, row, sum, diag);
+            row_chunk<MODE, (LEN > 0 ? LEN : 1)>(c, v, x, row, sum, diag, hw, fx);
         } else {
             int k = 0;
             if (LEN == 0)
-                for (; k + 4 <= len; k += 4) row_chunk<MODE, 4>(c + k * kSlice, v + k * kSlice, x, row, sum, diag);
-            for (; k < len; ++k) row_chunk<MODE, 1>(c + k * kSlice, v + k * kSlice, x, row, sum, diag);
+                for (; k + 4 <= len; k += 4) {
+                    row_chunk<MODE, 4>(c + k * kSlice, v + k * kSlice, x, row, sum, diag, hw, fx);
+                    hw = 0;
+                }
+            for (; k < len; ++k) {
+                row_chunk<MODE, 1>(c + k * kSlice, v + k * kSlice, x, row, sum, diag, hw, fx);
+                hw = 0;
+            }
         }
         if (active) {
             if (MODE == SPMV) {
