@@ -269,6 +269,85 @@ class SemiGeometricMG(Multigrid):
         return self.l_hierarchy
 
 
+class NeuralMG(Multigrid):
+    """NeuralMG(matrix, rhs, model, M, std, mean) -- the 1D NN multigrid of Multigrid.py:200-370.
+
+    `transfer_op(M)` builds the transfer operator of one level from its mass matrix exactly as the reference does:
+    seven mass entries per interior coarse node (`prepare_nn_input`, :313-334), `model.predict` on the normalised
+    features, `construct_B` (:336-370: entries [2], [4:7], [8] of each prediction, boundary rows from the
+    partition-of-unity constraint rowsum(B) = rowsum(M)), Q = B / rowsum(B).  The reference re-predicts Q and
+    recomputes Q^T A Q, Q^T M Q on every level of every cycle (:262-275); here the hierarchy is built once per solve
+    and the V-cycle (:246-301, the same statement order as Multigrid.v_cycle) runs on the device.  The reference's
+    smoother is PyAMG's index-order Gauss-Seidel whatever `smoother` says (:257,299): pass gs_order="lexicographic"
+    to reproduce its histories, the default is multicolour Gauss-Seidel / damped Jacobi as for the other classes."""
+
+    def __init__(self, matrix, rhs, model, M, std, mean):
+        super().__init__(matrix, rhs)
+        self.label = "NeuralMG"
+        self.model = model
+        self.M = M
+        self.std = std
+        self.mean = mean
+        self.l_hierarchy = []
+
+    @staticmethod
+    def _dense(M):
+        return np.asarray(M.todense() if sp.issparse(M) else M, dtype=np.float64)
+
+    def prepare_nn_input(self, mass):
+        """(n_c - 2, 7): [M[i,i-1], M[i,i], M[i,i+1], M[i+1,i+1], M[i+1,i+2], M[i+2,i+2], M[i+2,i+3]] for odd i"""
+        M = sp.csr_matrix(mass)
+        dim = M.shape[0]
+        i = np.arange(1, dim - 2, 2)
+        rows = np.stack([i, i, i, i + 1, i + 1, i + 2, i + 2], axis=1)
+        cols = np.stack([i - 1, i, i + 1, i + 1, i + 2, i + 2, i + 3], axis=1)
+        return np.asarray(M[rows.ravel(), cols.ravel()]).reshape(-1, 7)[:int((dim - 1) / 2) - 1]
+
+    def construct_B(self, data_M, M):
+        dim = M.shape[0]
+        nc = int((dim - 1) / 2) + 1
+        res = np.asarray(self.model.predict(data_M), dtype=np.float64)
+        k = np.arange(res.shape[0])
+        r = np.concatenate([2 * k + 2, 2 * k + 1, 2 * k + 2, 2 * k + 3, 2 * k + 2])
+        c = np.concatenate([k, k + 1, k + 1, k + 1, k + 2])
+        v = np.concatenate([res[:, 2], res[:, 4], res[:, 5], res[:, 6], res[:, 8]])
+        B = sp.lil_matrix(sp.csr_matrix((v, (r, c)), shape=(dim, nc)))      # every (row, col) is written once
+        Ms = sp.csr_matrix(M)
+        diff = np.asarray(Ms.sum(axis=1)).ravel() - np.asarray(B.sum(axis=1)).ravel()
+        B[0, 0], B[1, 0] = diff[0], diff[1]
+        B[dim - 2, nc - 1], B[dim - 1, nc - 1] = diff[-2], diff[-1]
+        B = sp.csr_matrix(B)
+        row_sums = np.asarray(B.sum(axis=1)).ravel()
+        Q = sp.csr_matrix(sp.diags(1.0 / row_sums) @ B)
+        Q.sort_indices()
+        return Q
+
+    def transfer_op(self, M):
+        """Q of one level (Multigrid.py:306-311); dense ndarray for a dense M (like the reference), CSR otherwise"""
+        data_M = (self.prepare_nn_input(M) - self.mean) / self.std
+        Q = self.construct_B(data_M, M)
+        return Q.toarray() if not sp.issparse(M) else Q
+
+    def define_hierarchy(self, levels=2):
+        """the transfer operators of all levels, M coarsened by Q^T M Q between them (:269-275)"""
+        M = sp.csr_matrix(self.M)
+        qs = []
+        for _ in range(levels - 1):
+            Q = sp.csr_matrix(self.transfer_op(M))
+            qs.append(Q)
+            M = sp.csr_matrix(Q.T @ M @ Q)
+        self.l_hierarchy = qs
+
+    def solve(self, levels=2, smoother="Jacobi", smooth_steps=1, max_iterations=100, error=1e-08,
+              initial_guess=None, cycle="V", first_call=True, **kw):
+        if len(self.l_hierarchy) != levels - 1:
+            self.define_hierarchy(levels)
+        super().solve(levels, smoother, smooth_steps, max_iterations, error, initial_guess, cycle, True, **kw)
+
+    def _given_transfers(self):
+        return self.l_hierarchy
+
+
 class NeuralMG_2D(Multigrid):
     """NeuralMG_2D(matrix, rhs, model, M, std, mean) -- Multigrid.py:373-765.  `define_hierarchy(levels)` builds the
     transfer operators from the mass matrix M with the predictor `model` (anything with `.predict(X) -> (len(X), 31)`,

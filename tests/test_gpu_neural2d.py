@@ -124,3 +124,23 @@ def test_torch_mlp_predictor_runs_on_device(nb):
         Qh = nb.download(Q)
         np.testing.assert_allclose(np.asarray(Qh.sum(axis=1)).ravel(), 1.0, atol=1e-13)
         assert Qh.data.min() > 0
+
+
+@pytest.mark.parametrize("name", ["reg64", "irr128"])
+def test_api_neuralmg_1d_reproduces_reference_history(name):
+    """1D NeuralMG.solve (Multigrid.py:211-301) with the reference's smoother (index-order Gauss-Seidel): the
+    reference's own residual history, iteration count and solution (tests/golden/neural_1d.npz)"""
+    from test_neural1d_host import make
+    g = load_golden("neural_1d.npz")
+    mg = make(g, name)
+    levels, steps = (int(v) for v in g[name + "_par"])
+    mg.solve(levels=levels, smoother="GaussSeidel", smooth_steps=steps, error=1e-10, max_iterations=40,
+             initial_guess=np.zeros((g[name + "_A"].shape[0], 1)), gs_order="lexicographic")
+    want = g[name + "_hist"]
+    assert mg.get_iterations() == len(want)
+    assert_history_close(mg.track_res, want, g[name + "_A"], g[name + "_sol"])
+    np.testing.assert_allclose(mg.get_solution(), g[name + "_sol"], rtol=0, atol=1e-11 * np.linalg.norm(g[name + "_sol"]))
+    # and the default (multicolour) smoother converges as well
+    mg2 = make(g, name)
+    mg2.solve(levels=levels, smoother="GaussSeidel", smooth_steps=steps, error=1e-10, max_iterations=40)
+    assert mg2.get_iterations() <= len(want) + 3
