@@ -207,6 +207,17 @@ class DeviceHierarchy:
     # vectors in and out (host NumPy <-> permuted device vectors)
     def _to_level0(self, host_vec, dst):
         torch = self.torch
+        # the pinned staging buffer is reused by every transfer: wait until the previous H2D copy has read it
+        evt = getattr(self, "_pin_evt", None)
+        if evt is not None:
+            evt.synchronize()
+        self._to_level0_enqueue(host_vec, dst)
+        if evt is None:
+            evt = self._pin_evt = torch.cuda.Event()
+        evt.record(torch.cuda.current_stream())
+
+    def _to_level0_enqueue(self, host_vec, dst):
+        torch = self.torch
         if isinstance(host_vec, torch.Tensor):
             src = host_vec.reshape(-1)
             if src.dtype != torch.float64 or src.numel() != self.n:

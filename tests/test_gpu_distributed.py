@@ -303,3 +303,49 @@ def test_two_process_torchrun_over_cuda_ipc(torch_mod):
            "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"), "--size", "128"]
     out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "DIST_CHECK_OK" in out.stdout, out.stdout[-4000:]
+
+
+def test_partitioned_cycle_is_bit_identical_at_4m_dof(torch_mod):
+    """larger blocks (interior CTAs really overlap the riding exchanges), automatic choice of the partitioned levels,
+    structured 2/3-colourings, fused residual norm: 2049^2, 5 levels, 4 virtual ranks"""
+    from learnmultigrid_b200 import problems as P
+    N, L = 2048, 5
+    A = P.structured_laplacian_2d(N, P.variable_coefficient)
+    Qs = P.structured_hierarchy_2d(N, L, transfer="linear")
+    cols = P.structured_colors_2d(N, L)
+    rng = np.random.default_rng(4)
+    n = A.shape[0]
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
+    h1 = DeviceHierarchy(A, Qs, smoother="mcgs", colors=cols)
+    h1.set_rhs(b)
+    h1.set_x(x0)
+    p1 = h1.make_params(nu_pre=1, nu_post=1)
+    want, norms1 = [], []
+    for _ in range(3):
+        norms1.append(h1.residual_norm())
+        h1.vcycle(p1)
+        want.append(h1.get_x().copy())
+    del h1
+
+    def body(fab):
+        h = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=cols, timeout_s=30.0)
+        h.set_rhs(b)
+        h.set_x(x0)
+        p = h.make_params(nu_pre=1, nu_post=1)
+        got, norms = [], []
+        for _ in range(3):
+            h.vcycle(p, with_norm=True)
+            norms.append(h.last_norm())
+            got.append(h.get_x_local().copy())
+        h.check()
+        o = (int(h.levels[0].plan.o0), int(h.levels[0].plan.o1), h.n_dist)
+        h.close()
+        return got, norms, o
+
+    for got, norms, (o0, o1, nd) in run_virtual_ranks(4, body):
+        assert nd == 3                                  # 4.2 M / 1.05 M / 263 k rows: >= 65536 per rank; 66 k: replicated
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w[o0:o1])
+        np.testing.assert_allclose(norms, norms1, rtol=1e-12)
