@@ -56,11 +56,12 @@ def parse_args():
     ap.add_argument("--multi", default=os.environ.get("MGB_BENCH_MULTI", "partitioned"),
                     choices=["partitioned", "replicas"],
                     help="N>1: row-partition ONE problem over the GPUs (strong scaling, SURVEY 8e) or run N replicas")
-    ap.add_argument("--colors", default=os.environ.get("MGB_BENCH_COLORS", "auto"), choices=["auto", "structured", "greedy"],
-                    help="structured: (ix+iy)%%2 / %%3 colourings of the 5-/7-point operators (linear transfers only); "
-                         "greedy: first-fit on the matrix graph; auto: greedy on one GPU (4 colours on the coarse levels "
-                         "stream 1%% faster), structured when partitioned (one exchange site and one launch fewer per "
-                         "coarse-level sweep: 3%% faster at 8 GPUs)")
+    ap.add_argument("--colors", default=os.environ.get("MGB_BENCH_COLORS", "greedy"), choices=["structured", "greedy"],
+                    help="greedy (default, at every GPU count): first-fit colouring of the matrix graph, 2 colours on the "
+                         "5-point level and 4 on the 7-point Galerkin levels; structured: (ix+iy)%%2 / %%3 (linear "
+                         "transfers only) -- one launch and one exchange site fewer per coarse sweep (3%% faster per "
+                         "cycle at 8 GPUs) but a worse smoother: V(1,1) convergence factor 0.23 instead of 0.20 "
+                         "(profiles/r01_convergence_factors.txt), so it loses on time to solution")
     ap.add_argument("--min-rows-per-rank", type=int, default=int(os.environ.get("MGB_MIN_ROWS", "65536")))
     return ap.parse_args()
 
@@ -287,8 +288,7 @@ def run_b200(a):
     kw = dict(levels=a.levels, smoother=a.smoother, smooth_steps=a.nu, omega=2.0 / 3.0)
     from learnmultigrid_b200 import problems as P
     colors = None
-    want_structured = a.colors == "structured" or (a.colors == "auto" and part)
-    if want_structured and a.transfer == "linear" and a.mesh == "structured" and a.smoother == "GaussSeidel":
+    if a.colors == "structured" and a.transfer == "linear" and a.mesh == "structured" and a.smoother == "GaussSeidel":
         colors = P.structured_colors_2d(n, a.levels)
     h = mg._hierarchy(a.levels, a.smoother, "multicolor", colors, True)
     torch.cuda.synchronize()
