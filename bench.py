@@ -254,7 +254,9 @@ def run_reference(a):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(times),
             "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(a, a.n), "sample": sample},
+            "config": {"workload": workload_name(a, a.n), "sample": sample,
+                       "smoother": ("index-order Gauss-Seidel (PyAMG's sweep restated in C: what the reference runs whatever "
+                                    "`smoother` says, Multigrid.py:88,121)" if a.smoother == "GaussSeidel" else "damped Jacobi")},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
