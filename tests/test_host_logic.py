@@ -200,3 +200,26 @@ def test_reverse_post_smoothing_makes_the_cycle_symmetric():
         M = lambda r: o.v_cycle(o.matrix, np.zeros((n, 1)), r, 1, L)
         asym[rev] = abs((M(r1).T @ r2).item() - (r1.T @ M(r2)).item()) / abs((M(r1).T @ r2).item())
     assert asym[True] < 1e-12 < asym[False]
+
+
+@pytest.mark.parametrize("transfer,expect", [("linear", [2, 3, 3]), ("quasi", None)])
+def test_lattice_colorings_are_valid_and_smaller_than_greedy(transfer, expect):
+    """colour = (alpha*ix + beta*iy) mod m from the stencil offsets of a small model hierarchy, applied to a larger one"""
+    import scipy.sparse as sp
+    from learnmultigrid_b200 import problems as P, formats as F
+    N, L = 64, 4
+    for coef in (None, P.variable_coefficient):
+        A = sp.csr_matrix(P.structured_laplacian_2d(N, coef))
+        Qs = P.structured_hierarchy_2d(N, L, transfer=transfer)
+        cols = P.lattice_colors_2d(N, L, transfer=transfer, coefficient=coef, model_N=32)
+        counts = []
+        for l in range(L - 1):
+            assert P.coloring_is_valid(A, cols[l]), "level %d" % l
+            counts.append(int(cols[l].max()) + 1)
+            greedy = int(F.greedy_colors(F.canonical_csr(A))[1])
+            assert counts[-1] <= greedy
+            A = sp.csr_matrix(Qs[l].T @ A @ Qs[l])
+        if expect is not None:
+            assert counts == expect
+        else:
+            assert counts[0] == 2 and counts[1] <= 8 and counts[2] <= 14     # 19- and 37-point stencils
