@@ -102,3 +102,19 @@ def external_columns(indptr, indices, r0, r1, c0, c1):
     cols = np.asarray(indices[indptr[r0]:indptr[r1]], dtype=np.int64)
     ext = cols[(cols < c0) | (cols >= c1)]
     return np.unique(ext)
+
+
+def level_external_columns(A, QT, Q_prev, offs, offs_next, offs_prev, rank):
+    """The halo of a rank's level vector: the columns outside its row block that its rows of A_l (smoothing, residual),
+    its rows of Q_l^T (restriction: rows = the coarse rows it owns, columns = this level) and its rows of Q_{l-1}
+    (prolongation from this level: rows = the finer rows it owns) refer to.  CSR inputs in natural ordering; QT /
+    Q_prev may be None.  distributed.DistributedHierarchy computes the same set on the device."""
+    o0, o1 = int(offs[rank]), int(offs[rank + 1])
+    parts = [external_columns(A.indptr, A.indices, o0, o1, o0, o1)]
+    if QT is not None:
+        c0, c1 = int(offs_next[rank]), int(offs_next[rank + 1])
+        parts.append(external_columns(QT.indptr, QT.indices, c0, c1, o0, o1))
+    if Q_prev is not None:
+        f0, f1 = int(offs_prev[rank]), int(offs_prev[rank + 1])
+        parts.append(external_columns(Q_prev.indptr, Q_prev.indices, f0, f1, o0, o1))
+    return np.unique(np.concatenate(parts))

@@ -170,3 +170,142 @@ def test_two_process_gloo_halo_exchange(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
     assert "PARTITION_OK" in out.stdout, out.stdout[-3000:]
+
+
+VCYCLE_WORKER = r'''
+import os, sys
+import numpy as np
+import scipy.sparse as sp
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.environ["MGB_ROOT"])
+sys.path.insert(0, os.path.join(os.environ["MGB_ROOT"], "tests"))
+from learnmultigrid_b200 import formats as F, partition as PT, problems as P
+from oracle import kernels as K
+from oracle.vcycle import OracleMultigrid
+
+dist.init_process_group("gloo")
+rank, W = dist.get_rank(), dist.get_world_size()
+N, L, ND, NU = 16, 4, 2, 1                      # levels 0,1 partitioned; 2,3 replicated
+A0 = P.structured_laplacian_2d(N, P.variable_coefficient)
+Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, L, transfer="linear")]
+As = [F.canonical_csr(A0)]
+for q in Qs:
+    As.append(F.canonical_csr(sp.csr_matrix(q.T @ sp.csc_matrix(As[-1]) @ q)))
+QTs = [F.transpose_csr(q) for q in Qs]
+cols = [F.greedy_colors(a)[0] for a in As[:-1]] + [None]
+offs = [PT.block_offsets(a.shape[0], W) for a in As]
+
+def plan_of(l, r):
+    ext = PT.level_external_columns(As[l], QTs[l], Qs[l - 1] if l else None, offs[l], offs[l + 1],
+                                    offs[l - 1] if l else None, r)
+    return PT.RankPlan(offs[l], r, ext, cols[l])
+
+plans = [plan_of(l, rank) for l in range(ND)]
+nbrs = [{p: plan_of(l, p) for p in range(W) if p != rank} for l in range(ND)]
+
+def local(M, rows_g, colmap):
+    B = M[rows_g]
+    return F.raw_csr(B.indptr, colmap[B.indices].astype(np.int32), B.data, (len(rows_g), int(colmap.max()) + 1))
+
+def colmap_of(l):
+    if l < ND:
+        g = plans[l].gather_indices()
+        m = -np.ones(As[l].shape[0], dtype=np.int64); m[g] = np.arange(len(g)); return m, len(g)
+    return np.arange(As[l].shape[0], dtype=np.int64), As[l].shape[0]      # replicated: natural ordering
+
+lev = []
+for l in range(ND):
+    p = plans[l]
+    g = p.gather_indices()
+    cm, nv = colmap_of(l)
+    cmn, nvn = colmap_of(l + 1)
+    own_next = (plans[l + 1].gather_indices()[:plans[l + 1].n_own] if l + 1 < ND
+                else np.arange(offs[l + 1][rank], offs[l + 1][rank + 1]))
+    Al = local(As[l], g[:p.n_own], cm); Al = F.raw_csr(Al.indptr, Al.indices, Al.data, (p.n_own, nv))
+    Ql = local(Qs[l], g[:p.n_own], cmn); Ql = F.raw_csr(Ql.indptr, Ql.indices, Ql.data, (p.n_own, nvn))
+    QTl = local(QTs[l], own_next, cm); QTl = F.raw_csr(QTl.indptr, QTl.indices, QTl.data, (len(own_next), nv))
+    lev.append({"A": Al, "Q": Ql, "QT": QTl, "p": p, "nv": nv, "own_next": own_next})
+
+def exchange(l, v, color=None):
+    p = lev[l]["p"]; reqs, recv = [], {}
+    for q in sorted(set(p.neighbours) | {r for r, pl in nbrs[l].items() if rank in pl.seg}):
+        pl = nbrs[l][q]
+        idx, ptr = p.send_indices(pl)
+        a, b = (0, len(idx)) if color is None else (ptr[color], ptr[color + 1])
+        out = torch.from_numpy(np.ascontiguousarray(v[idx[a:b]]))
+        if q in p.seg:
+            s0, s1 = p.seg[q] if color is None else p.seg_color[(q, color)]
+        else:
+            s0 = s1 = 0
+        recv[q] = (s0, torch.empty(s1 - s0, dtype=torch.float64))
+        if out.numel(): reqs.append(dist.isend(out, q))
+        if s1 > s0: reqs.append(dist.irecv(recv[q][1], q))
+    for r_ in reqs: r_.wait()
+    for q, (s0, t) in recv.items():
+        v[p.n_own + s0: p.n_own + s0 + t.numel()] = t.numpy()
+
+oracle = OracleMultigrid(A0, np.zeros((As[0].shape[0], 1)), Qs, smoother="mcgs", colors=cols, hoist_setup=True)
+oracle.build_hierarchy(L)
+
+def smooth(l, x, b):
+    d = lev[l]; p = d["p"]
+    Asq = sp.vstack([d["A"], sp.csr_matrix((p.n_halo, d["nv"]))]).tocsr()
+    Asq = F.raw_csr(Asq.indptr, Asq.indices, Asq.data, Asq.shape)
+    bb = np.concatenate([b, np.zeros(p.n_halo)])
+    for s in range(NU):
+        for c in range(p.ncolors):
+            rows = np.arange(p.color_ptr[c], p.color_ptr[c + 1], dtype=np.int32)
+            K.gauss_seidel_multicolor(Asq, x, bb, [rows])
+            exchange(l, x, c)
+
+def vcycle(l, x, b):
+    """x: local vector (own | halo) with a current halo; b: own rows"""
+    d = lev[l]; p = d["p"]
+    smooth(l, x, b)
+    r = np.zeros(d["nv"]); r[:p.n_own] = K.residual(d["A"], x, b)
+    exchange(l, r)
+    rc = K.spmv(d["QT"], r)
+    if l + 1 < ND:
+        pc = lev[l + 1]["p"]
+        e = np.zeros(lev[l + 1]["nv"])
+        vcycle(l + 1, e, rc)
+    else:
+        sizes = [int(offs[l + 1][q + 1] - offs[l + 1][q]) for q in range(W)]
+        mine = torch.zeros(max(sizes), dtype=torch.float64); mine[:len(rc)] = torch.from_numpy(np.ascontiguousarray(rc))
+        parts = [torch.empty(max(sizes), dtype=torch.float64) for q in range(W)]      # gloo wants equal sizes
+        dist.all_gather(parts, mine)
+        bc = np.concatenate([t.numpy()[:k] for t, k in zip(parts, sizes)]).reshape(-1, 1)
+        e = oracle.v_cycle(oracle._A_levels[l + 1], np.zeros_like(bc), bc, NU, L - (l + 1), level=l + 1).ravel()
+    x[:p.n_own] = K.prolong_correct(d["Q"], e, x[:p.n_own])
+    exchange(l, x)
+    smooth(l, x, b)
+
+rng = np.random.default_rng(1)
+n0 = As[0].shape[0]
+xg, bg = rng.standard_normal(n0), rng.standard_normal(n0)
+g0 = plans[0].gather_indices()
+x = xg[g0].copy(); b = bg[g0[:plans[0].n_own]].copy()
+want = xg.reshape(-1, 1).copy()
+ok = True
+for cyc in range(2):
+    vcycle(0, x, b)
+    want = oracle.v_cycle(oracle.matrix, want, bg.reshape(-1, 1), NU, L)
+    ok = ok and np.array_equal(x[:plans[0].n_own], want.ravel()[g0[:plans[0].n_own]])
+t = torch.tensor([1 if ok else 0]); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0: print("VCYCLE_PARTITION_OK" if int(t.item()) == 1 else "VCYCLE_PARTITION_MISMATCH")
+dist.destroy_process_group()
+'''
+
+
+def test_two_process_gloo_partitioned_vcycle(tmp_path):
+    """the whole partitioned V-cycle of learnmultigrid_b200/distributed.py (halo per colour, residual halo for the
+    restriction, all-gather hand-off to the replicated levels, prolongation, halo refresh) as two gloo processes with
+    the oracle's kernels: bit-identical to the single-process oracle cycle"""
+    script = tmp_path / "vworker.py"
+    script.write_text(VCYCLE_WORKER)
+    env = dict(os.environ, MGB_ROOT=ROOT, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert "VCYCLE_PARTITION_OK" in out.stdout, out.stdout[-4000:]
