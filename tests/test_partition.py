@@ -6,6 +6,7 @@ import subprocess
 import sys
 
 import numpy as np
+import pytest
 import scipy.sparse as sp
 
 from learnmultigrid_b200 import formats as F
@@ -309,3 +310,48 @@ def test_two_process_gloo_partitioned_vcycle(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert "VCYCLE_PARTITION_OK" in out.stdout, out.stdout[-4000:]
+
+
+@pytest.mark.parametrize("seed,size", [(0, 2), (1, 3), (2, 5), (3, 8)])
+def test_partitioned_sweeps_on_random_unstructured_graphs(seed, size):
+    """random symmetric sparsity (no grid structure, long-range couplings: every rank can neighbour every other),
+    random world sizes: plans are consistent and the emulated per-colour exchange reproduces the global sweep"""
+    from oracle import kernels as K
+    rng = np.random.default_rng(seed)
+    n = 97 + 13 * seed
+    S = sp.random(n, n, density=0.04, random_state=seed, format="csr")
+    S = S + S.T + sp.diags(np.full(n, 8.0))
+    A = F.canonical_csr(sp.csr_matrix(S))
+    colors, nc = F.greedy_colors(A)
+    offs, plans = plans_for(A, size, colors)
+    x, b = rng.standard_normal(n), rng.standard_normal(n)
+    perm, cptr = F.color_permutation(colors)
+    want = x.copy()
+    K.gauss_seidel_multicolor(A, want, b, [perm[cptr[c]:cptr[c + 1]] for c in range(nc)], iterations=1)
+    loc = []
+    for p in plans:
+        g = p.gather_indices()
+        assert len(set(g)) == len(g)
+        slot = -np.ones(n, dtype=np.int64)
+        slot[g] = np.arange(len(g))
+        Ab = A[g[:p.n_own]]
+        assert slot[Ab.indices].min() >= 0                      # every referenced column is owned or in the halo
+        Asq = sp.vstack([F.raw_csr(Ab.indptr, slot[Ab.indices], Ab.data, (p.n_own, len(g))),
+                         sp.csr_matrix((p.n_halo, len(g)))]).tocsr()
+        loc.append({"A": F.raw_csr(Asq.indptr, Asq.indices, Asq.data, Asq.shape), "x": x[g].copy(),
+                    "b": np.concatenate([b[g[:p.n_own]], np.zeros(p.n_halo)]), "g": g})
+    for c in range(nc):
+        for p, d in zip(plans, loc):
+            rows = np.arange(p.color_ptr[c], p.color_ptr[c + 1], dtype=np.int32)
+            if len(rows):
+                K.gauss_seidel_multicolor(d["A"], d["x"], d["b"], [rows])
+        for r, dr in zip(plans, loc):
+            for s, ds in zip(plans, loc):
+                if s.rank in r.seg:
+                    idx, ptr = s.send_indices(r)
+                    a = r.seg[s.rank][0]
+                    dr["x"][r.n_own + a + ptr[c]: r.n_own + a + ptr[c + 1]] = ds["x"][idx[ptr[c]:ptr[c + 1]]]
+    got = np.empty(n)
+    for p, d in zip(plans, loc):
+        got[d["g"][:p.n_own]] = d["x"][:p.n_own]
+    assert np.array_equal(got, want)
