@@ -47,3 +47,9 @@ class CouplingOperator:
         shape = (self.fine_mesh.get_np(), self.coarse_mesh.get_np())
         B = sp.coo_matrix((loc.reshape(-1), (rows, cols)), shape=shape).tocsr()
         return B if sparse else B.toarray()
+
+    def compute_b_2d(self):
+        """B[f, c] = int phi_f phi_c on the triangle-triangle intersections (no reference counterpart: the 2D path of
+        the reference is a stub; see coupling2d.py).  CSR."""
+        from .coupling2d import coupling_operator_2d
+        return coupling_operator_2d(self.fine_mesh, self.coarse_mesh)

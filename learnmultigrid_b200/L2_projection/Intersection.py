@@ -23,7 +23,17 @@ class Intersection:
     def get_intersections(self):
         return self.intersections
 
-    def find_intersections2d(self):
+    def find_intersections2d(self, geometric=False):
+        """geometric=False: the reference's stub (nested child map, Intersection.py:19-34).  geometric=True: all
+        (fine, coarse) element pairs that overlap with positive area, for arbitrary mesh pairs (coupling2d.py);
+        `int_coord` then holds the overlap areas."""
+        if geometric:
+            from .coupling2d import coupling_operator_2d
+            _, pairs, area = coupling_operator_2d(self.fine_mesh, self.coarse_mesh, return_pairs=True)
+            order = np.lexsort((pairs[:, 1], pairs[:, 0]))
+            self.intersections = pairs[order].astype(int)
+            self.int_coord = area[order]
+            return
         conn = self.fine_mesh.get_connections()
         c_conn = self.coarse_mesh.get_connections()
         intersected = np.zeros((conn.shape[0], 2), dtype=int)

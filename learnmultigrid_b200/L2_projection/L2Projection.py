@@ -53,18 +53,29 @@ class L2Projection:
         return L, timeL
 
     def compute_transfer_2d(self, P=None):
-        """Q (CSR) between nested P1 triangle meshes: Q = rownormalise(M_h P) ("quasi") or
-        diag(colsum M_h)^-1 M_h P ("pseudo"); P = linear interpolation coarse -> fine (n_f x n_c CSR)."""
-        if P is None:
-            raise ValueError("compute_transfer_2d needs the nested interpolation matrix P (see problems.linear_P_2d)")
+        """Q (CSR) between two P1 triangle meshes of the same domain.
+        With P (the linear interpolation coarse -> fine of NESTED meshes, n_f x n_c) the coupling operator is
+        B_h = M_h P -- one sparse product.  Without it B_h is integrated on the triangle-triangle
+        intersections (coupling2d.coupling_operator_2d), which works for non-nested meshes as well.
+        "quasi": Q = B / rowsum(B); "pseudo": Q = diag(colsum M)^-1 B; "L2": Q = M^-1 B (sparse solve, dense result:
+        small meshes only), as in 1D (:67-90)."""
         M = MassMatrix(self.fine_mesh).compute_mass_2d(FunctionTriangle(1), Quadrature2D(3), format="csr")
-        B = sp.csr_matrix(M @ sp.csr_matrix(P))
+        if P is not None:
+            B = sp.csr_matrix(M @ sp.csr_matrix(P))
+        else:
+            from .coupling2d import coupling_operator_2d
+            B = coupling_operator_2d(self.fine_mesh, self.coarse_mesh)
         if self.type == "quasi":
             s = np.asarray(B.sum(axis=1)).ravel()
         elif self.type == "pseudo":
             s = np.asarray(M.sum(axis=0)).ravel()
+        elif self.type == "L2":
+            from scipy.sparse.linalg import splu
+            Q = sp.csr_matrix(splu(sp.csc_matrix(M)).solve(B.toarray()))
+            Q.sort_indices()
+            return Q
         else:
-            raise ValueError("2D transfer supports 'quasi' and 'pseudo'")
+            raise ValueError("unknown projection type %r" % (self.type,))
         Q = sp.csr_matrix(sp.diags(1.0 / s) @ B)
         Q.sort_indices()
         return Q
