@@ -548,3 +548,26 @@ def test_mg_preconditioned_cg_matches_oracle(env):
     cg0 = CG(A, rhs)
     cg0.solve(max_iterations=400, error=1e-10)
     assert cg0.get_iterations() > 5 * its
+
+
+def test_api_semigeometric_mg_on_non_nested_2d_meshes(env):
+    """the README's headline use: a transfer operator from the semi-geometric L2 projection between an irregular fine
+    mesh and an unrelated (non-nested) coarse mesh (L2_projection/coupling2d.py), used by SemiGeometricMG exactly as in
+    the 2D scripts (levels=2, Gauss-Seidel x3, thesis_structured_2d.py:457-458); history against the CPU oracle"""
+    from learnmultigrid_b200 import problems as P
+    from learnmultigrid_b200.L2_projection.L2Projection import L2Projection
+    from learnmultigrid_b200.mesh.Mesh2D import Mesh2D
+    from learnmultigrid_b200.solvers.Multigrid import SemiGeometricMG
+    pb = P.irregular_p1_2d(32, seed=6)
+    coarse = Mesh2D(13 * 13)
+    Q = L2Projection("quasi", pb["mesh"], coarse).compute_transfer_2d()
+    pc = np.asarray(coarse.get_points())
+    inner = np.flatnonzero((pc[:, 0] > 1e-12) & (pc[:, 0] < 1 - 1e-12) & (pc[:, 1] > 1e-12) & (pc[:, 1] < 1 - 1e-12))
+    Q = sp.csr_matrix(Q[:, inner])
+    mg = SemiGeometricMG(pb["A"], pb["rhs"], Q)
+    mg.solve(levels=2, smoother="GaussSeidel", smooth_steps=3, error=1e-9, max_iterations=40)
+    o = OracleMultigrid(pb["A"], pb["rhs"], [Q], smoother="mcgs", colors=mg.get_hierarchy().colors, hoist_setup=True)
+    o.solve(levels=2, smooth_steps=3, error=1e-9, max_iterations=40)
+    assert mg.get_iterations() == len(o.track_res) < 40
+    assert_history_close(mg.track_res, o.track_res, pb["A"], o.solution)
+    np.testing.assert_allclose(mg.get_solution(), o.solution, rtol=0, atol=1e-12 * np.linalg.norm(o.solution))
