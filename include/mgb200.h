@@ -341,6 +341,16 @@ int mg_coo_fold_sum(int64_t m, const int32_t *d_rows, const int32_t *d_cols, con
                     const int32_t *d_order, int32_t *d_head, double *d_folded, void *stream);
 int mg_vector_from_runs(int64_t m, const int32_t *d_rows, const int32_t *d_order, const int32_t *d_head,
                         const double *d_folded, double *d_out, void *stream);
+/* Semi-geometric coupling operator B[f,c] = int phi_f phi_c between two P1 triangle meshes, integrated on the
+ * triangle-triangle intersections (finishes the reference's 2D stub L2Projection.py:17-24 along the 1D recipe
+ * CouplingOperator.py:31-69): nine contributions per candidate pair of elements (+ the overlap area, optional).
+ * Fold with mg_coo_fold_sum.  The mg_host_ variant runs the same per-pair code serially on host arrays (CPU tests). */
+int mg_coupling_pairs_p1_2d(int64_t npairs, const int32_t *d_pair_f, const int32_t *d_pair_c, const double *d_pf,
+                            const int32_t *d_tf, const double *d_pc, const int32_t *d_tc, int32_t *d_rows,
+                            int32_t *d_cols, double *d_vals, double *d_area, void *stream);
+int mg_host_coupling_pairs_p1_2d(int64_t npairs, const int32_t *h_pair_f, const int32_t *h_pair_c, const double *h_pf,
+                                 const int32_t *h_tf, const double *h_pc, const int32_t *h_tc, int32_t *h_rows,
+                                 int32_t *h_cols, double *h_vals, double *h_area);
 /* A[nodes,:] = I[nodes,:] for the rows flagged in d_flag: count pass, scan, fill pass */
 int mg_csr_dirichlet_count(int64_t n, const int32_t *d_indptr, const int32_t *d_flag, int32_t *d_count, void *stream);
 int mg_csr_dirichlet_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,

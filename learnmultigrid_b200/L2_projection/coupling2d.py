@@ -102,8 +102,67 @@ def _barycentric(p, tri, elem, x):
     return np.stack([1.0 - l1 - l2, l1, l2], axis=1)
 
 
+def _pair_kernel_inputs(pf, tf, pc, tc, f, c):
+    return (np.ascontiguousarray(f, dtype=np.int32), np.ascontiguousarray(c, dtype=np.int32),
+            np.ascontiguousarray(pf, dtype=np.float64), np.ascontiguousarray(tf, dtype=np.int32),
+            np.ascontiguousarray(pc, dtype=np.float64), np.ascontiguousarray(tc, dtype=np.int32))
+
+
+def coupling_operator_2d_native(fine_mesh, coarse_mesh, where="device"):
+    """The same operator through libmgb200 (csrc/assembly_kernels.cu: one thread per candidate pair clips, triangulates
+    and integrates; runs of equal (row, col) summed by the assembly fold).  where="device": CUDA kernels, returns a
+    device CSR (setup_device.DevCSR); where="host": the same per-pair C code run serially on the host (CPU tests),
+    returns SciPy CSR.  Candidate pairs come from the host binning in both cases."""
+    import ctypes
+    from .. import _lib
+    pf = np.asarray(fine_mesh.get_points(), dtype=np.float64)
+    tf = np.asarray(fine_mesh.get_connections(), dtype=np.int64)
+    pc = np.asarray(coarse_mesh.get_points(), dtype=np.float64)
+    tc = np.asarray(coarse_mesh.get_connections(), dtype=np.int64)
+    f, c = candidate_pairs(pf, tf, pc, tc)
+    hf, hc, hpf, htf, hpc, htc = _pair_kernel_inputs(pf, tf, pc, tc, f, c)
+    K = len(hf)
+    lib = _lib.load()
+    if where == "host":
+        rows, cols = np.empty(9 * K, dtype=np.int32), np.empty(9 * K, dtype=np.int32)
+        vals = np.empty(9 * K)
+        ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(lib.mg_host_coupling_pairs_p1_2d(K, ptr(hf), ptr(hc), ptr(hpf), ptr(htf), ptr(hpc), ptr(htc), ptr(rows),
+                                                    ptr(cols), ptr(vals), None), "mg_host_coupling_pairs_p1_2d")
+        B = sp.coo_matrix((vals, (rows, cols)), shape=(len(pf), len(pc))).tocsr()
+        B.sum_duplicates()
+        B.data[np.abs(B.data) < 1e-13 * np.abs(B.data).max()] = 0.0
+        B.eliminate_zeros()
+        B.sort_indices()
+        return B
+    from .. import setup_device as SD
+    torch = _lib.require_cuda()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    S = SD.DeviceSetup(torch, dev)
+    d = [torch.from_numpy(a).to(dev) for a in (hf, hc, hpf, htf, hpc, htc)]
+    rows, cols, vals = S.empty(9 * K, torch.int32), S.empty(9 * K, torch.int32), S.empty(9 * K, torch.float64)
+    st = _lib.stream_handle(torch)
+    _lib.check(lib.mg_coupling_pairs_p1_2d(K, *[t.data_ptr() for t in d], rows.data_ptr(), cols.data_ptr(),
+                                           vals.data_ptr(), None, st), "mg_coupling_pairs_p1_2d")
+    m = 9 * K
+    order = S.row_col_order(rows, cols, len(pf), len(pc))
+    head, folded = S.empty(m, torch.int32), S.empty(m, torch.float64)
+    _lib.check(lib.mg_coo_fold_sum(m, rows.data_ptr(), cols.data_ptr(), vals.data_ptr(), order.data_ptr(),
+                                   head.data_ptr(), folded.data_ptr(), st), "mg_coo_fold_sum")
+    live = head.bool()
+    thr = 1e-13 * float(folded[live].abs().max().item())
+    head[live & (folded.abs() < thr)] = 0                       # slivers between triangles that merely touch
+    slot, nnz = S.scan(head, m)
+    orow, ocol, oval = S.empty(nnz, torch.int32), S.empty(nnz, torch.int32), S.empty(nnz, torch.float64)
+    _lib.check(lib.mg_nn_emit(m, rows.data_ptr(), cols.data_ptr(), order.data_ptr(), head.data_ptr(), slot.data_ptr(),
+                              folded.data_ptr(), orow.data_ptr(), ocol.data_ptr(), oval.data_ptr(), st), "mg_nn_emit")
+    indptr = torch.searchsorted(orow, torch.arange(len(pf) + 1, dtype=torch.int32, device=dev)).to(torch.int32)
+    return SD.DevCSR((len(pf), len(pc)), indptr, ocol, oval)
+
+
 def coupling_operator_2d(fine_mesh, coarse_mesh, return_pairs=False):
-    """B (n_fine x n_coarse CSR) with B[f, c] = int phi_f phi_c; meshes expose get_points() / get_connections()"""
+    """B (n_fine x n_coarse CSR) with B[f, c] = int phi_f phi_c; meshes expose get_points() / get_connections().
+    NumPy model of the kernel in csrc/assembly_kernels.cu (coupling_operator_2d_native)."""
     pf = np.asarray(fine_mesh.get_points(), dtype=np.float64)
     tf = np.asarray(fine_mesh.get_connections(), dtype=np.int64)
     pc = np.asarray(coarse_mesh.get_points(), dtype=np.float64)

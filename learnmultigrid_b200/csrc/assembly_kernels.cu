@@ -162,6 +162,108 @@ dirichlet_fill_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32
     }
 }
 
+// ---- semi-geometric coupling operator B[f,c] = int phi_f phi_c on triangle-triangle intersections -------------------
+// (no reference counterpart: L2Projection.compute_transfer_2d is a stub, L2Projection.py:17-24; the recipe is the 1D
+// one, CouplingOperator.py:31-69.  Host model: learnmultigrid_b200/L2_projection/coupling2d.py.)
+// One candidate pair: clip the fine triangle by the three half-planes of the (counter-clockwise) coarse triangle
+// (Sutherland-Hodgman), fan-triangulate the polygon, integrate the products of the two P1 bases with the edge-midpoint
+// rule (exact for quadratics).  loc[i][j] (9 doubles) and the overlap area are returned; all zero if the triangles do
+// not overlap.
+__host__ __device__ inline void bary2(const double *t, double x, double y, double *l) {
+    const double ax = t[0], ay = t[1], bx = t[2], by = t[3], cx = t[4], cy = t[5];
+    const double det = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);
+    const double l1 = ((x - ax) * (cy - ay) - (y - ay) * (cx - ax)) / det;
+    const double l2 = ((bx - ax) * (y - ay) - (by - ay) * (x - ax)) / det;
+    l[0] = 1.0 - l1 - l2;
+    l[1] = l1;
+    l[2] = l2;
+}
+
+__host__ __device__ inline void coupling_pair(const double *tf, const double *tc_in, double *loc, double *area_out) {
+    for (int i = 0; i < 9; ++i) loc[i] = 0.0;
+    *area_out = 0.0;
+    double tc[6];
+    for (int i = 0; i < 6; ++i) tc[i] = tc_in[i];
+    const double orient = (tc[2] - tc[0]) * (tc[5] - tc[1]) - (tc[3] - tc[1]) * (tc[4] - tc[0]);
+    if (orient < 0) {            // clip against a counter-clockwise triangle: swap vertices 1 and 2
+        double t;
+        t = tc[2]; tc[2] = tc[4]; tc[4] = t;
+        t = tc[3]; tc[3] = tc[5]; tc[5] = t;
+    }
+    double px[8], py[8], qx[8], qy[8];
+    int n = 3;
+    for (int i = 0; i < 3; ++i) { px[i] = tf[2 * i]; py[i] = tf[2 * i + 1]; }
+    for (int e = 0; e < 3 && n > 0; ++e) {
+        const double ax = tc[2 * e], ay = tc[2 * e + 1];
+        const double ex = tc[2 * ((e + 1) % 3)] - ax, ey = tc[2 * ((e + 1) % 3) + 1] - ay;
+        int m = 0;
+        for (int k = 0; k < n; ++k) {
+            const int kn = (k + 1 < n) ? k + 1 : 0;
+            const double d = ex * (py[k] - ay) - ey * (px[k] - ax);
+            const double dn = ex * (py[kn] - ay) - ey * (px[kn] - ax);
+            const bool in = d >= 0, inn = dn >= 0;
+            if (in && m < 8) { qx[m] = px[k]; qy[m] = py[k]; ++m; }
+            if (in != inn && m < 8) {
+                const double t = d / (d - dn);
+                qx[m] = px[k] + t * (px[kn] - px[k]);
+                qy[m] = py[k] + t * (py[kn] - py[k]);
+                ++m;
+            }
+        }
+        n = m;
+        for (int k = 0; k < n; ++k) { px[k] = qx[k]; py[k] = qy[k]; }
+    }
+    double total = 0.0;
+    for (int i = 1; i + 1 < n; ++i) {
+        const double x0 = px[0], y0 = py[0], x1 = px[i], y1 = py[i], x2 = px[i + 1], y2 = py[i + 1];
+        double area = 0.5 * ((x1 - x0) * (y2 - y0) - (y1 - y0) * (x2 - x0));
+        if (area < 0) area = -area;
+        if (!(area > 0)) continue;
+        total += area;
+        const double mx[3] = {0.5 * (x0 + x1), 0.5 * (x1 + x2), 0.5 * (x2 + x0)};
+        const double my[3] = {0.5 * (y0 + y1), 0.5 * (y1 + y2), 0.5 * (y2 + y0)};
+        double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int q = 0; q < 3; ++q) {
+            double lf[3], lc[3];
+            bary2(tf, mx[q], my[q], lf);
+            bary2(tc_in, mx[q], my[q], lc);
+            for (int a = 0; a < 3; ++a)
+                for (int b2 = 0; b2 < 3; ++b2) acc[3 * a + b2] += lf[a] * lc[b2];
+        }
+        const double w = area / 3.0;
+        for (int a = 0; a < 9; ++a) loc[a] += w * acc[a];
+    }
+    *area_out = total;
+}
+
+__global__ void __launch_bounds__(kBlock)
+coupling_pairs_kernel(int64_t npairs, const int32_t *__restrict__ pair_f, const int32_t *__restrict__ pair_c,
+                      const double *__restrict__ pf, const int32_t *__restrict__ tf, const double *__restrict__ pc,
+                      const int32_t *__restrict__ tc, int32_t *__restrict__ rows, int32_t *__restrict__ cols,
+                      double *__restrict__ vals, double *__restrict__ area) {
+    const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (k >= npairs) return;
+    const int64_t f = pair_f[k], c = pair_c[k];
+    double a[6], b[6], loc[9], ar;
+    int32_t nf[3], nc[3];
+    for (int i = 0; i < 3; ++i) {
+        nf[i] = tf[3 * f + i];
+        nc[i] = tc[3 * c + i];
+        a[2 * i] = pf[2 * (int64_t)nf[i]];
+        a[2 * i + 1] = pf[2 * (int64_t)nf[i] + 1];
+        b[2 * i] = pc[2 * (int64_t)nc[i]];
+        b[2 * i + 1] = pc[2 * (int64_t)nc[i] + 1];
+    }
+    coupling_pair(a, b, loc, &ar);
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            rows[9 * k + 3 * i + j] = nf[i];
+            cols[9 * k + 3 * i + j] = nc[j];
+            vals[9 * k + 3 * i + j] = loc[3 * i + j];
+        }
+    if (area) area[k] = ar;
+}
+
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
 }  // namespace mgb
@@ -223,6 +325,44 @@ int mg_vector_from_runs(int64_t m, const int32_t *d_rows, const int32_t *d_order
     MG_REQUIRE(m > 0 && d_rows && d_order && d_head && d_folded && d_out, "null argument");
     vector_from_runs_kernel<<<grid_for(m), kBlock, 0, (cudaStream_t)stream>>>(m, d_rows, d_order, d_head, d_folded, d_out);
     MG_CHECK_LAUNCH("vector_from_runs");
+    return MG_OK;
+}
+
+/* Semi-geometric coupling operator between two P1 triangle meshes (coupling2d.py is the host model): for every
+ * candidate pair (fine element d_pair_f[k], coarse element d_pair_c[k]) the nine contributions
+ * (fine node i, coarse node j, int_{overlap} phi_i phi_j) and, optionally, the overlap area.  Sum the runs with
+ * mg_coo_fold_sum / mg_nn_emit. */
+int mg_coupling_pairs_p1_2d(int64_t npairs, const int32_t *d_pair_f, const int32_t *d_pair_c, const double *d_pf,
+                            const int32_t *d_tf, const double *d_pc, const int32_t *d_tc, int32_t *d_rows,
+                            int32_t *d_cols, double *d_vals, double *d_area, void *stream) {
+    MG_REQUIRE(npairs > 0 && d_pair_f && d_pair_c && d_pf && d_tf && d_pc && d_tc && d_rows && d_cols && d_vals, "null argument");
+    coupling_pairs_kernel<<<grid_for(npairs), kBlock, 0, (cudaStream_t)stream>>>(npairs, d_pair_f, d_pair_c, d_pf, d_tf, d_pc, d_tc, d_rows, d_cols, d_vals, d_area);
+    MG_CHECK_LAUNCH("coupling_pairs");
+    return MG_OK;
+}
+/* the same per-pair code on HOST arrays (serial), for the CPU test-suite */
+int mg_host_coupling_pairs_p1_2d(int64_t npairs, const int32_t *h_pair_f, const int32_t *h_pair_c, const double *h_pf,
+                                 const int32_t *h_tf, const double *h_pc, const int32_t *h_tc, int32_t *h_rows,
+                                 int32_t *h_cols, double *h_vals, double *h_area) {
+    MG_REQUIRE(npairs > 0 && h_pair_f && h_pair_c && h_pf && h_tf && h_pc && h_tc && h_rows && h_cols && h_vals, "null argument");
+    for (int64_t k = 0; k < npairs; ++k) {
+        const int64_t f = h_pair_f[k], c = h_pair_c[k];
+        double a[6], b[6], loc[9], ar;
+        for (int i = 0; i < 3; ++i) {
+            a[2 * i] = h_pf[2 * (int64_t)h_tf[3 * f + i]];
+            a[2 * i + 1] = h_pf[2 * (int64_t)h_tf[3 * f + i] + 1];
+            b[2 * i] = h_pc[2 * (int64_t)h_tc[3 * c + i]];
+            b[2 * i + 1] = h_pc[2 * (int64_t)h_tc[3 * c + i] + 1];
+        }
+        coupling_pair(a, b, loc, &ar);
+        for (int i = 0; i < 3; ++i)
+            for (int j = 0; j < 3; ++j) {
+                h_rows[9 * k + 3 * i + j] = h_tf[3 * f + i];
+                h_cols[9 * k + 3 * i + j] = h_tc[3 * c + j];
+                h_vals[9 * k + 3 * i + j] = loc[3 * i + j];
+            }
+        if (h_area) h_area[k] = ar;
+    }
     return MG_OK;
 }
 

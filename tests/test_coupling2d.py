@@ -81,3 +81,15 @@ def test_two_level_cycle_converges_on_non_nested_meshes():
     h = o.track_res.ravel()
     assert len(h) < 40 and h[-1] <= 1e-9
     assert np.all(h[2:] < 0.8 * h[1:-1])
+
+
+@pytest.mark.parametrize("fine,coarse", [("irr16", "s36"), ("s64", "s16")])
+def test_per_pair_c_code_matches_numpy_model(fine, coarse):
+    """csrc/assembly_kernels.cu::coupling_pair run serially on the host (the CUDA kernel runs the same function)"""
+    from learnmultigrid_b200.L2_projection.coupling2d import coupling_operator_2d_native
+    meshes = {"irr16": lambda: irregular(64, 1), "s36": lambda: Mesh2D(36), "s64": lambda: Mesh2D(64), "s16": lambda: Mesh2D(16)}
+    mf, mc = meshes[fine](), meshes[coarse]()
+    B = coupling_operator_2d(mf, mc)
+    Bn = coupling_operator_2d_native(mf, mc, where="host")
+    assert np.array_equal(B.indptr, Bn.indptr) and np.array_equal(B.indices, Bn.indices)
+    np.testing.assert_allclose(Bn.data, B.data, rtol=1e-12, atol=1e-17)

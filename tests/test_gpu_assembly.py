@@ -117,3 +117,23 @@ def test_device_resident_pipeline_equals_host_fed_pipeline(asm):
         h_host.vcycle(p)
         assert np.array_equal(h_dev.get_x(), h_host.get_x())
     assert h_dev.residual_norm() < 0.2 * np.linalg.norm(pb["rhs"])        # three V(2,2) cycles
+
+
+def test_device_coupling_operator_on_triangle_intersections(asm):
+    """B[f,c] = int phi_f phi_c between non-nested meshes by the per-pair CUDA kernel: against the NumPy model and the
+    exact properties (partition of unity of both bases)"""
+    from learnmultigrid_b200 import problems as P
+    from learnmultigrid_b200.L2_projection.coupling2d import coupling_operator_2d, coupling_operator_2d_native
+    from learnmultigrid_b200.mesh.Mesh2D import Mesh2D
+    from learnmultigrid_b200.assembly.MassMatrix import MassMatrix
+    from learnmultigrid_b200.assembly.Quadrature import Quadrature2D
+    from learnmultigrid_b200.assembly.ShapeFunction import FunctionTriangle
+    pb = P.irregular_p1_2d(32, seed=8)
+    for coarse in (Mesh2D(13 * 13), Mesh2D(16 * 16)):          # unrelated and (for 16x16 parents) nested
+        Bd = asm.S.download(coupling_operator_2d_native(pb["mesh"], coarse))
+        Bh = coupling_operator_2d(pb["mesh"], coarse)
+        assert np.array_equal(Bd.indptr, Bh.indptr) and np.array_equal(Bd.indices, Bh.indices)
+        np.testing.assert_allclose(Bd.data, Bh.data, rtol=1e-12, atol=1e-17)
+        Mc = MassMatrix(coarse).compute_mass_2d(FunctionTriangle(1), Quadrature2D(3), format="csr")
+        np.testing.assert_allclose(np.asarray(Bd.sum(axis=1)).ravel(), np.asarray(pb["M"].sum(axis=1)).ravel(), rtol=1e-12)
+        np.testing.assert_allclose(np.asarray(Bd.sum(axis=0)).ravel(), np.asarray(Mc.sum(axis=1)).ravel(), rtol=1e-12)
