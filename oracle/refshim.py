@@ -8,7 +8,11 @@ Shims:
   1. no-op `matplotlib`, `matplotlib.pyplot` (Solver.py:5, Mesh1D.py:4, Mesh2D.py:4-5 import them);
   2. `pyamg.relaxation.relaxation.gauss_seidel` = oracle.kernels.gauss_seidel, the restated PyAMG
      kernel (PyAMG is not installed and cannot be: no network);
-  3. `np.asscalar` for CG.py:30,32,47; `np.int` for Mesh2D.refine.
+  3. `np.asscalar` for CG.py:30,32,47; `np.int` for Mesh2D.refine;
+  4. (opt-in, `patch_refine()`) Mesh2D.refine builds its per-element scratch as `np.zeros((3, 1))`, whose
+     elements NumPy >= 1.24 no longer accepts inside the list assignments of Mesh2D.py:149-156; the module's `np`
+     is replaced by a proxy that hands out `np.zeros(3)` for exactly that shape.  Nothing else changes, the
+     reference's statements run as they stand.
 """
 import contextlib
 import io
@@ -69,3 +73,21 @@ def quiet():
     """The reference prints on every constructor and iteration (Multigrid.py:32,61,68)."""
     with contextlib.redirect_stdout(io.StringIO()):
         yield
+
+
+def patch_refine():
+    """shim 4: let the reference's own Mesh2D.refine run under NumPy >= 1.24 (call after install())"""
+    import learn_multigrid.mesh.Mesh2D as ref_mesh
+
+    class _NumpyProxy:
+        def __getattr__(self, name):
+            return getattr(np, name)
+
+        @staticmethod
+        def zeros(shape, *args, **kwargs):
+            if shape == (3, 1):
+                shape = (3,)
+            return np.zeros(shape, *args, **kwargs)
+
+    ref_mesh.np = _NumpyProxy()
+    return ref_mesh
