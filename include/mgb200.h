@@ -368,16 +368,26 @@ int mg_nn_coarsen(int64_t n, const int32_t *d_t_indptr, const int32_t *d_t_indic
 /* map_coarse (:679-684): with d_scan = exclusive scan of (state == 1): cmap[i] = coarse id or -1, clist[k] = node */
 int mg_nn_compact(int64_t n, const int32_t *d_state, const int32_t *d_scan, int32_t *d_cmap, int32_t *d_clist,
                   void *stream);
-/* extract_patches (:591-677): [nc][43] features and [nc][31] fill indices (-1 padded); synchronises */
+/* extract_patches (:591-677): [nc][43] features and [nc][31] fill indices (-1 padded); synchronises.  For a coarse node
+ * with more than 6 neighbours this is patch variant 0 (the 6 largest mass entries kept) */
 int mg_nn_extract_patches(int64_t nc, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
                           const int32_t *d_cmap, const int32_t *d_clist, double *d_patches, int32_t *d_fill,
                           int32_t *d_err, void *stream);
+/* extra patch variants of coarse nodes with 6 + a neighbours (:631-663): d_extra[k] = a; with d_extra_ptr = exclusive
+ * scan of d_extra (nc + 1 entries, total T) variants 1..a of every such node go to rows nc .. nc+T-1 of d_patches /
+ * d_fill (node order), and d_not_last ([nc + T], zeroed by the caller) is set for every patch of such a node but its
+ * last variant, whose d_neighs row is the one fill_B keeps.  a <= 6.  mg_nn_extract_variants synchronises. */
+int mg_nn_count_variants(int64_t nc, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                         const int32_t *d_clist, int32_t *d_extra, void *stream);
+int mg_nn_extract_variants(int64_t nc, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                           const int32_t *d_cmap, const int32_t *d_clist, const int32_t *d_extra_ptr,
+                           double *d_patches, int32_t *d_fill, int32_t *d_not_last, int32_t *d_err, void *stream);
 /* fill_B (:687-732) in three steps: contributions [np][31] in application order (unused: row = unused_row >= rows)
  * + d_neighs table [ncoarse][6]; fold of the runs of equal (row, col) given the stable (row, col) sort order with the
  * reference's running mean (d_head marks run heads with a non-zero result); emission of the COO triplets of B */
 int mg_nn_contributions(int64_t np_, const int32_t *d_fill, const double *d_pred, const int32_t *d_cmap,
-                        int32_t unused_row, int32_t *d_rows, int32_t *d_cols, double *d_vals, int32_t *d_dneigh,
-                        void *stream);
+                        const int32_t *d_not_last /* nullable */, int32_t unused_row, int32_t *d_rows, int32_t *d_cols,
+                        double *d_vals, int32_t *d_dneigh, void *stream);
 int mg_nn_fold(int64_t m, int32_t unused_row, const int32_t *d_rows, const int32_t *d_cols, const double *d_vals,
                const int32_t *d_order, int32_t *d_head, double *d_folded, void *stream);
 int mg_nn_emit(int64_t m, const int32_t *d_rows, const int32_t *d_cols, const int32_t *d_order, const int32_t *d_head,
@@ -395,6 +405,7 @@ int mg_nn_cut_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices,
  * logic against the reference's golden vectors without a GPU; not called by the product */
 int mg_host_nn_coarsen(int64_t n, const int32_t *h_t_indptr, const int32_t *h_t_indices, const double *h_t_values,
                        int32_t *h_cmap, int32_t *h_clist);
+/* returns the number of patch rows = nc + extra variants (outputs may be null to only count), or a negative status */
 int mg_host_nn_extract_patches(int64_t nc, const int32_t *h_indptr, const int32_t *h_indices, const double *h_values,
                                const int32_t *h_cmap, const int32_t *h_clist, double *h_patches, int32_t *h_fill);
 int mg_host_nn_contributions(int64_t np_, const int32_t *h_fill, const double *h_pred, const int32_t *h_cmap,

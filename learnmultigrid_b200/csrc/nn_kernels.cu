@@ -12,14 +12,16 @@
 // Here: one thread per coarse node / prediction, CSR input, no dense matrix.  The per-node logic is written once as
 // __host__ __device__ functions; the mg_host_nn_* entry points run the same code serially on host arrays, which is how
 // the CPU test-suite checks it against the golden vectors produced by the reference itself
-// (tests/golden/neural_2d_cases.npz).  Supported regime: every row of M has at most 6 positive off-diagonal entries
-// (true for P1 meshes from Mesh2D and for every coarser level, whose rows pre_process cuts to 6); a node with more
-// neighbours makes the reference emit extra patch variants (:645-663) -- reported as MG_ERR_UNSUPPORTED, no fallback.
+// (tests/golden/neural_2d_cases.npz).  A coarse node with 6 + a neighbours (a > 0; never the case for Mesh2D meshes or
+// for coarser levels, whose rows pre_process cuts to 6) gets a + 1 patch variants as in the reference (:645-663):
+// variant v drops the neighbours ranked v .. v+a-1 by ascending mass entry; variant 0 sits in the node's own slot, the
+// others are appended behind all regular patches in node order.  a <= 6 (beyond that the reference itself fails).
 #include "common.cuh"
 
 namespace mgb {
 
 constexpr int kMaxRow = 16;        // longest row (entries incl. diagonal) the extraction accepts
+constexpr int kMaxDegree = 12;     // most neighbours of a coarse node: 6 kept + up to 6 dropped per variant
 constexpr int kPatch = 43, kFill = 31;
 enum NnError { NN_OK = 0, NN_DEGREE = 1, NN_NEGATIVE = 2, NN_ISOLATED = 3, NN_LONG_ROW = 4 };
 
@@ -54,14 +56,26 @@ __host__ __device__ inline bool nn_contains(const int32_t *a, int n, int32_t x) 
     return false;
 }
 
-// single_extraction (Multigrid.py:545-589) for a coarse node with at most 6 neighbours.  Returns an NnError.
+// number of patch variants beyond the first for coarse node c: max(0, positive off-diagonal entries - 6)
+// (Multigrid.py:606-614, 631-632)
+__host__ __device__ inline int nn_extra_variants(const int32_t *indptr, const int32_t *indices, const double *values,
+                                                 int32_t c) {
+    int deg = 0;
+    for (int32_t p = indptr[c]; p < indptr[c + 1]; ++p)
+        if (indices[p] != c && values[p] > 0.0) ++deg;
+    return deg > 6 ? deg - 6 : 0;
+}
+
+// single_extraction (Multigrid.py:545-589) for patch variant `variant` of coarse node c (0 for a node with at most 6
+// neighbours).  Returns an NnError.
 __host__ __device__ inline int nn_extract_one(const int32_t *indptr, const int32_t *indices, const double *values,
-                                              const int32_t *cmap, int32_t c, double *patch, int32_t *fill) {
+                                              const int32_t *cmap, int32_t c, int variant, double *patch,
+                                              int32_t *fill) {
     for (int i = 0; i < kPatch; ++i) patch[i] = -1.0;
     for (int i = 0; i < kFill; ++i) fill[i] = -1;
     // row of c: `where` = columns of the nonzero entries other than c, `row` = the positive values (:622-629)
-    int32_t where[6];
-    double row[6];
+    int32_t where[kMaxDegree];
+    double row[kMaxDegree];
     int nnb = 0;
     double node_M = 0.0;
     for (int32_t p = indptr[c]; p < indptr[c + 1]; ++p) {
@@ -70,10 +84,29 @@ __host__ __device__ inline int nn_extract_one(const int32_t *indptr, const int32
         if (j == c) { node_M = v; continue; }
         if (v == 0.0) continue;
         if (v < 0.0) return NN_NEGATIVE;
-        if (nnb >= 6) return NN_DEGREE;
+        if (nnb >= kMaxDegree) return NN_DEGREE;
         where[nnb] = j;
         row[nnb] = v;
         ++nnb;
+    }
+    if (nnb > 6) {
+        // `ordered = argsort(row)`; variant v deletes positions ordered[v : v + additional] (:636-644).  Ties are ranked
+        // by position (NumPy's default sort does not promise an order for equal keys).
+        const int additional = nnb - 6;
+        if (variant < 0 || variant > additional) return NN_DEGREE;
+        bool drop[kMaxDegree];
+        for (int i = 0; i < nnb; ++i) {
+            int rank = 0;
+            for (int k = 0; k < nnb; ++k)
+                if (row[k] < row[i] || (row[k] == row[i] && k < i)) ++rank;
+            drop[i] = rank >= variant && rank < variant + additional;
+        }
+        int kept = 0;
+        for (int i = 0; i < nnb; ++i)
+            if (!drop[i]) { where[kept] = where[i]; row[kept] = row[i]; ++kept; }
+        nnb = kept;
+    } else if (variant != 0) {
+        return NN_DEGREE;
     }
     double up = 0.0, down = 1.0;
     if (nnb < 6 && !nn_scaling(nnb, up, down)) return NN_ISOLATED;
@@ -256,16 +289,51 @@ nn_extract_kernel(int64_t nc, const int32_t *__restrict__ indptr, const int32_t 
     if (k >= nc) return;
     double patch[kPatch];
     int32_t fi[kFill];
-    const int rc = nn_extract_one(indptr, indices, values, cmap, clist[k], patch, fi);
+    const int rc = nn_extract_one(indptr, indices, values, cmap, clist[k], 0, patch, fi);
     if (rc != NN_OK) atomicCAS(err, 0, rc);
     for (int i = 0; i < kPatch; ++i) patches[k * kPatch + i] = patch[i];
     for (int i = 0; i < kFill; ++i) fill[k * kFill + i] = fi[i];
 }
 
+__global__ void __launch_bounds__(kBlock)
+nn_count_variants_kernel(int64_t nc, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                         const double *__restrict__ values, const int32_t *__restrict__ clist,
+                         int32_t *__restrict__ extra) {
+    const int64_t k = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (k >= nc) return;
+    extra[k] = nn_extra_variants(indptr, indices, values, clist[k]);
+}
+
+// variants 1 .. a of the coarse nodes that have them, written behind the nc regular patches in node order;
+// not_last[j] = 1 for every patch of such a node except its last variant (whose d_neighs entry is the one fill_B keeps)
+__global__ void __launch_bounds__(128)
+nn_extract_variants_kernel(int64_t nc, const int32_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                           const double *__restrict__ values, const int32_t *__restrict__ cmap,
+                           const int32_t *__restrict__ clist, const int32_t *__restrict__ extra_ptr,
+                           double *__restrict__ patches, int32_t *__restrict__ fill, int32_t *__restrict__ not_last,
+                           int32_t *__restrict__ err) {
+    const int64_t k = (int64_t)blockIdx.x * 128 + threadIdx.x;
+    if (k >= nc) return;
+    const int32_t first = extra_ptr[k], additional = extra_ptr[k + 1] - first;
+    if (additional == 0) return;
+    not_last[k] = 1;
+    double patch[kPatch];
+    int32_t fi[kFill];
+    for (int v = 1; v <= additional; ++v) {
+        const int rc = nn_extract_one(indptr, indices, values, cmap, clist[k], v, patch, fi);
+        if (rc != NN_OK) atomicCAS(err, 0, rc);
+        const int64_t j = nc + first + (v - 1);
+        for (int i = 0; i < kPatch; ++i) patches[j * kPatch + i] = patch[i];
+        for (int i = 0; i < kFill; ++i) fill[j * kFill + i] = fi[i];
+        not_last[j] = v < additional ? 1 : 0;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 nn_contrib_kernel(int64_t np_, const int32_t *__restrict__ fill, const double *__restrict__ pred,
-                  const int32_t *__restrict__ cmap, int32_t unused_row, int32_t *__restrict__ rows, int32_t *__restrict__ cols,
-                  double *__restrict__ vals, int32_t *__restrict__ dneigh) {
+                  const int32_t *__restrict__ cmap, const int32_t *__restrict__ not_last, int32_t unused_row,
+                  int32_t *__restrict__ rows, int32_t *__restrict__ cols, double *__restrict__ vals,
+                  int32_t *__restrict__ dneigh) {
     const int64_t j = (int64_t)blockIdx.x * 128 + threadIdx.x;
     if (j >= np_) return;
     int32_t r[kFill], c[kFill], dn[6];
@@ -276,6 +344,7 @@ nn_contrib_kernel(int64_t np_, const int32_t *__restrict__ fill, const double *_
         cols[j * kFill + i] = c[i];
         vals[j * kFill + i] = v[i];
     }
+    if (not_last && not_last[j]) return;       // d_neighs[node] is overwritten by every patch of the node: the last one stays
     const int32_t ncoarse = cmap[fill[j * kFill]];
     for (int i = 0; i < 6; ++i) dneigh[(int64_t)ncoarse * 6 + i] = dn[i];
 }
@@ -368,7 +437,7 @@ nn_cut_fill_kernel(int64_t n, const int32_t *__restrict__ indptr, const int32_t 
 
 static const char *nn_error_text(int rc) {
     switch (rc) {
-        case NN_DEGREE: return "a node has more than 6 neighbours: the reference emits extra patch variants there (Multigrid.py:645-663), which the device builder does not support";
+        case NN_DEGREE: return "a coarse node has more than 12 neighbours (more than 6 dropped per patch variant, Multigrid.py:636-644: the reference fails there too)";
         case NN_NEGATIVE: return "negative off-diagonal entry in the mass matrix";
         case NN_ISOLATED: return "a node has fewer than 2 neighbours (scaling_vnodes has no entry; the reference fails too)";
         case NN_LONG_ROW: return "a row has more than 16 entries";
@@ -441,12 +510,41 @@ int mg_nn_extract_patches(int64_t nc, const int32_t *d_indptr, const int32_t *d_
     return MG_OK;
 }
 
+/* Patch variants of coarse nodes with more than 6 neighbours (Multigrid.py:631-663).  mg_nn_count_variants:
+ * d_extra[k] = max(0, neighbours of clist[k] - 6).  With d_extra_ptr = its exclusive scan (nc + 1 entries, total = T),
+ * mg_nn_extract_variants writes variants 1.. of those nodes to rows nc .. nc+T-1 of d_patches / d_fill (rows 0..nc-1 =
+ * variant 0, written by mg_nn_extract_patches) and sets d_not_last ([nc + T], zero-initialised by the caller) for every
+ * patch that is not its node's last one.  Synchronises. */
+int mg_nn_count_variants(int64_t nc, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                         const int32_t *d_clist, int32_t *d_extra, void *stream) {
+    MG_REQUIRE(nc > 0 && d_indptr && d_indices && d_values && d_clist && d_extra, "null argument");
+    nn_count_variants_kernel<<<(unsigned)((nc + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(nc, d_indptr, d_indices, d_values, d_clist, d_extra);
+    MG_CHECK_LAUNCH("nn_count_variants");
+    return MG_OK;
+}
+int mg_nn_extract_variants(int64_t nc, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
+                           const int32_t *d_cmap, const int32_t *d_clist, const int32_t *d_extra_ptr,
+                           double *d_patches, int32_t *d_fill, int32_t *d_not_last, int32_t *d_err, void *stream) {
+    MG_REQUIRE(nc > 0 && d_indptr && d_indices && d_values && d_cmap && d_clist && d_extra_ptr && d_patches && d_fill && d_not_last && d_err, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    MG_CHECK_CUDA(cudaMemsetAsync(d_err, 0, sizeof(int32_t), st));
+    nn_extract_variants_kernel<<<(unsigned)((nc + 127) / 128), 128, 0, st>>>(nc, d_indptr, d_indices, d_values, d_cmap, d_clist, d_extra_ptr, d_patches, d_fill, d_not_last, d_err);
+    MG_CHECK_LAUNCH("nn_extract_variants");
+    int32_t e = 0;
+    MG_CHECK_CUDA(cudaMemcpyAsync(&e, d_err, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MG_CHECK_CUDA(cudaStreamSynchronize(st));
+    if (e) return set_error(MG_ERR_UNSUPPORTED, "mg_nn_extract_variants", nn_error_text(e));
+    return MG_OK;
+}
+
 /* fill_B step 1: the (row, col, value) contributions of every prediction in application order ([np][31] each, row =
- * unused_row (>= number of fine rows) where unused) and the d_neighs table ([ncoarse][6], -1 padded) */
+ * unused_row (>= number of fine rows) where unused) and the d_neighs table ([ncoarse][6], -1 padded).  d_not_last
+ * (may be null: no patch variants) marks the patches that must not write d_neighs (see mg_nn_extract_variants). */
 int mg_nn_contributions(int64_t np_, const int32_t *d_fill, const double *d_pred, const int32_t *d_cmap,
-                        int32_t unused_row, int32_t *d_rows, int32_t *d_cols, double *d_vals, int32_t *d_dneigh, void *stream) {
+                        const int32_t *d_not_last, int32_t unused_row, int32_t *d_rows, int32_t *d_cols, double *d_vals,
+                        int32_t *d_dneigh, void *stream) {
     MG_REQUIRE(np_ > 0 && d_fill && d_pred && d_cmap && d_rows && d_cols && d_vals && d_dneigh, "null argument");
-    nn_contrib_kernel<<<(unsigned)((np_ + 127) / 128), 128, 0, (cudaStream_t)stream>>>(np_, d_fill, d_pred, d_cmap, unused_row, d_rows, d_cols, d_vals, d_dneigh);
+    nn_contrib_kernel<<<(unsigned)((np_ + 127) / 128), 128, 0, (cudaStream_t)stream>>>(np_, d_fill, d_pred, d_cmap, d_not_last, unused_row, d_rows, d_cols, d_vals, d_dneigh);
     MG_CHECK_LAUNCH("nn_contrib");
     return MG_OK;
 }
@@ -513,14 +611,22 @@ int mg_host_nn_coarsen(int64_t n, const int32_t *h_t_indptr, const int32_t *h_t_
     }
     return nc;
 }
+/* h_patches / h_fill hold nc + (sum of extra variants) rows; returns that row count (>= nc) or a negative status.
+ * Pass null output pointers to only count. */
 int mg_host_nn_extract_patches(int64_t nc, const int32_t *h_indptr, const int32_t *h_indices, const double *h_values,
                                const int32_t *h_cmap, const int32_t *h_clist, double *h_patches, int32_t *h_fill) {
-    MG_REQUIRE(nc > 0 && h_indptr && h_indices && h_values && h_cmap && h_clist && h_patches && h_fill, "null argument");
+    MG_REQUIRE(nc > 0 && h_indptr && h_indices && h_values && h_cmap && h_clist, "null argument");
+    int64_t next = nc;
     for (int64_t k = 0; k < nc; ++k) {
-        const int rc = nn_extract_one(h_indptr, h_indices, h_values, h_cmap, h_clist[k], h_patches + k * kPatch, h_fill + k * kFill);
-        if (rc != NN_OK) return set_error(MG_ERR_UNSUPPORTED, "mg_host_nn_extract_patches", nn_error_text(rc));
+        const int additional = nn_extra_variants(h_indptr, h_indices, h_values, h_clist[k]);
+        for (int v = 0; v <= additional; ++v) {
+            const int64_t j = v == 0 ? k : next++;
+            if (!h_patches || !h_fill) continue;
+            const int rc = nn_extract_one(h_indptr, h_indices, h_values, h_cmap, h_clist[k], v, h_patches + j * kPatch, h_fill + j * kFill);
+            if (rc != NN_OK) return set_error(MG_ERR_UNSUPPORTED, "mg_host_nn_extract_patches", nn_error_text(rc));
+        }
     }
-    return MG_OK;
+    return (int)next;
 }
 int mg_host_nn_contributions(int64_t np_, const int32_t *h_fill, const double *h_pred, const int32_t *h_cmap,
                              int32_t unused_row, int32_t *h_rows, int32_t *h_cols, double *h_vals, int32_t *h_dneigh) {

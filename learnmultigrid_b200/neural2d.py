@@ -107,16 +107,28 @@ class NeuralBuilder:
         self.last_rounds = int(rounds)
         return cmap, clist, nc
 
-    # extract_patches (:591-677)
+    # extract_patches (:591-677); rows nc.. hold the extra patch variants of nodes with more than 6 neighbours (:631-663)
     def extract(self, M, cmap, clist):
         t, S = self.torch, self.S
         nc = clist.numel()
-        patches = S.empty(nc * 43, t.float64)
-        fill = S.empty(nc * 31, t.int32)
+        extra = S.empty(nc, t.int32)
+        _lib.check(self.lib.mg_nn_count_variants(nc, *M.ptrs(), clist.data_ptr(), extra.data_ptr(), self.st()),
+                   "mg_nn_count_variants")
+        extra_ptr, total = S.scan(extra, nc)
+        rows = nc + total
+        patches = S.empty(rows * 43, t.float64)
+        fill = S.empty(rows * 31, t.int32)
         _lib.check(self.lib.mg_nn_extract_patches(nc, *M.ptrs(), cmap.data_ptr(), clist.data_ptr(), patches.data_ptr(),
                                                   fill.data_ptr(), S._flag.data_ptr(), self.st()),
                    "mg_nn_extract_patches")
-        return patches.view(nc, 43), fill.view(nc, 31)
+        self.not_last = None
+        if total:
+            self.not_last = t.zeros(rows, dtype=t.int32, device=self.dev)
+            _lib.check(self.lib.mg_nn_extract_variants(nc, *M.ptrs(), cmap.data_ptr(), clist.data_ptr(),
+                                                       extra_ptr.data_ptr(), patches.data_ptr(), fill.data_ptr(),
+                                                       self.not_last.data_ptr(), S._flag.data_ptr(), self.st()),
+                       "mg_nn_extract_variants")
+        return patches.view(rows, 43), fill.view(rows, 31)
 
     # (patches - mean) / std ; model.predict (:755-756)
     def predict(self, model, patches, mean, std):
@@ -133,14 +145,22 @@ class NeuralBuilder:
         return res.to(t.float64).contiguous()
 
     # fill_B (:687-732) -> (B as device CSR n x nc, d_neighs table nc x 6)
-    def fill_B(self, pred, fill, cmap, n, nc):
+    def fill_B(self, pred, fill, cmap, n, nc, not_last=None):
+        """not_last: int32 flag per patch, set for all but the last patch of a node that has several (`extract` leaves it
+        in self.not_last); None = derive it here from the fill indices (any patch followed by one of the same node)"""
         t, S = self.torch, self.S
         np_ = fill.shape[0]
+        if not_last is None and np_ > nc:
+            node = fill[:, 0].to(t.int64)
+            last = t.full((int(cmap.numel()),), -1, dtype=t.int64, device=self.dev)
+            last.scatter_reduce_(0, node, t.arange(np_, device=self.dev), reduce="amax")
+            not_last = (last[node] != t.arange(np_, device=self.dev)).to(t.int32).contiguous()
         m = np_ * 31
         rows, cols = S.empty(m, t.int32), S.empty(m, t.int32)
         vals = S.empty(m, t.float64)
         dneigh = t.full((nc * 6,), -1, dtype=t.int32, device=self.dev)
-        _lib.check(self.lib.mg_nn_contributions(np_, fill.data_ptr(), pred.data_ptr(), cmap.data_ptr(), n,
+        _lib.check(self.lib.mg_nn_contributions(np_, fill.data_ptr(), pred.data_ptr(), cmap.data_ptr(),
+                                                not_last.data_ptr() if not_last is not None else None, n,
                                                 rows.data_ptr(), cols.data_ptr(), vals.data_ptr(), dneigh.data_ptr(),
                                                 self.st()), "mg_nn_contributions")
         order = S.row_col_order(rows, cols, n + 1, nc)        # stable by column, then stably by row (unused: row n)
@@ -190,7 +210,7 @@ class NeuralBuilder:
             cmap, clist, nc = self.coarsen(mass)
             patches, fill = self.extract(mass, cmap, clist)
             pred = self.predict(model, patches, mean, std)
-            B, dneigh = self.fill_B(pred, fill, cmap, mass.shape[0], nc)
+            B, dneigh = self.fill_B(pred, fill, cmap, mass.shape[0], nc, not_last=self.not_last)
             if keep_intermediates:
                 trace.append({"M": mass, "cmap": cmap, "clist": clist, "patches": patches, "fill": fill, "pred": pred,
                               "B": SD.DevCSR(B.shape, B.indptr, B.indices, B.values.clone()), "dneigh": dneigh,

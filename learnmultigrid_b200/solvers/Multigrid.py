@@ -356,7 +356,8 @@ class NeuralMG_2D(Multigrid):
     Differences, all explicit: the reference stores the hierarchy in `l_hierarchy` but its `solve` never uses it
     (no `interpolator` override: it falls through to the 1D geometric interpolator); here `solve`
     runs the V-cycle with `l_hierarchy`.  `fill_B` returns B as a SciPy CSR matrix instead of a dense n x n_C array.
-    Nodes with more than 6 neighbours (extra patch variants, :645-663) are not supported (MgError, no fallback)."""
+    Coarse nodes with 7..12 neighbours get the reference's extra patch variants (:631-663; rows appended behind the
+    regular patches); more than 12 is an MgError (the reference fails there too)."""
 
     def __init__(self, matrix, rhs, model, M, std, mean):
         super().__init__(matrix, rhs)

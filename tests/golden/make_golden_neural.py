@@ -54,6 +54,27 @@ def irregular_mesh(ne, seed):
     return Mesh2D(p=np.array(m.p), conn=np.array(m.conn))
 
 
+def flipped_mesh(nsq, flips, seed, jitter=0.15):
+    """nsq x nsq squares; the diagonal of the listed squares (ix, iy) runs from the lower-right to the upper-left corner
+    instead (so the node that is the lower-right corner of one flipped square and the upper-left corner of another has 8
+    neighbours, 7 with one flip); interior nodes are moved by up to `jitter` * h so that no two mass entries are equal
+    (the reference ranks a node's neighbours with np.argsort, whose order of equal keys is unspecified)"""
+    with refshim.quiet():
+        m = Mesh2D(nsq * nsq)
+    p, conn = np.array(m.p), np.array(m.conn)
+    W = nsq + 1
+    for ix, iy in flips:
+        k, e = iy * W + ix, 2 * (iy * nsq + ix)
+        assert list(conn[e]) == [k, k + 1, k + W + 1] and list(conn[e + 1]) == [k, k + W + 1, k + W]
+        conn[e] = [k, k + 1, k + W]
+        conn[e + 1] = [k + 1, k + W + 1, k + W]
+    rng = np.random.default_rng(seed)
+    interior = (p[:, 0] > 0) & (p[:, 0] < 1) & (p[:, 1] > 0) & (p[:, 1] < 1)
+    p[interior] += (rng.random((int(interior.sum()), 2)) - 0.5) * 2 * jitter / nsq
+    with refshim.quiet():
+        return Mesh2D(p=p, conn=conn)
+
+
 def run_case(mesh, levels, mean, std):
     q = Quadrature2D(3)
     with refshim.quiet():
@@ -113,6 +134,10 @@ def main():
     cases["s289"] = run_case(big, 4, mean, std)
     cases["i81"] = run_case(irregular_mesh(16, 42), 3, mean, std)        # 4x4 squares refined irregularly: 81 nodes
     cases["i289"] = run_case(irregular_mesh(64, 7), 3, mean2, std2)     # 8x8 refined: 289 nodes, parents numbered first
+    # coarse nodes with 7 and 8 neighbours: extra patch variants (Multigrid.py:631-663)
+    cases["f81"] = run_case(flipped_mesh(8, [(1, 2), (2, 1), (3, 4), (5, 2), (6, 1), (6, 5)], 3), 3, mean, std)
+    cases["f169"] = run_case(flipped_mesh(12, [(1, 2), (2, 1), (3, 4), (5, 2), (6, 1), (6, 5), (9, 8), (8, 9), (3, 8),
+                                               (4, 7), (9, 2), (7, 10)], 11), 3, mean2, std2)
     flat = {"mean2": mean2, "std2": std2}
     for name, d in cases.items():
         for k, v in d.items():
@@ -121,7 +146,7 @@ def main():
     np.savez_compressed(path, **flat)
     print(path, os.path.getsize(path))
     for name, d in cases.items():
-        print(name, [d[k].shape for k in d if k.endswith("_Q")])
+        print(name, [d[k].shape for k in d if k.endswith("_Q")], [d[k].shape[0] for k in d if k.endswith("_patches")])
 
 
 if __name__ == "__main__":

@@ -46,8 +46,13 @@ def test_device_builder_matches_reference_level_by_level(nb, case):
         assert np.array_equal(fill.cpu().numpy(), d["fill"])
         assert np.array_equal(patches.cpu().numpy(), d["patches"])
         pred = torch.from_numpy(np.ascontiguousarray(d["pred"])).to(nb.dev)
-        B, dn = nb.fill_B(pred, fill, cmap, n, nc)
+        B, dn = nb.fill_B(pred, fill, cmap, n, nc, not_last=nb.not_last)      # flags from the variant kernel
         assert np.array_equal(dn.cpu().numpy(), d["dn"])
+        if fill.shape[0] > nc:                                                  # patch variants (cases f81, f169)
+            assert int(nb.not_last.sum()) == fill.shape[0] - nc                 # a node with a extra variants: a flags
+            B2, dn2 = nb.fill_B(pred, fill, cmap, n, nc)                        # flags derived from the fill indices
+            assert np.array_equal(dn2.cpu().numpy(), d["dn"])
+            assert np.array_equal(nb.download(B2).toarray(), d["B"])
         Bh = nb.download(B)
         assert np.array_equal(Bh.toarray(), d["B"])
         assert Bh.nnz == np.count_nonzero(d["B"]) and Bh.has_sorted_indices
@@ -60,7 +65,7 @@ def test_device_builder_matches_reference_level_by_level(nb, case):
 def test_device_define_hierarchy_matches_reference(nb, case):
     g = load_golden("neural_2d_cases.npz")
     lv = levels_of(g, case)
-    mean, std = (g["mean2"], g["std2"]) if case in ("r77", "i289") else (np.zeros(43), np.ones(43))
+    mean, std = (g["mean2"], g["std2"]) if case in ("r77", "i289", "f169") else (np.zeros(43), np.ones(43))
     Qs = nb.define_hierarchy(lv[0]["M"], Stub(), mean, std, len(lv) + 1, keep_intermediates=True)
     assert len(Qs) == len(lv)
     for l, (Q, d) in enumerate(zip(Qs, lv)):

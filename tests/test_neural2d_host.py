@@ -11,7 +11,8 @@ import scipy.sparse as sp
 from learnmultigrid_b200 import _lib
 from helpers import load_golden
 
-CASES = ["s81", "r77", "s289", "i81", "i289"]
+CASES = ["s81", "r77", "s289", "i81", "i289", "f81", "f169"]
+VARIANTS = {"f81": 6, "f169": 12}      # extra patch variants on the fine level (coarse nodes with 7 / 8 neighbours)
 
 
 def level_data(g, case, l):
@@ -65,27 +66,32 @@ def fold_reference_rule(rows, cols, vals, n, nc, unused):
 def test_coarsening_extraction_and_fill_match_the_reference(case):
     lib = _lib.load()
     g = load_golden("neural_2d_cases.npz")
-    for d in levels_of(g, case):
+    for l, d in enumerate(levels_of(g, case)):
         M = d["M"]
         n = M.shape[0]
         cmap, clist = host_coarsen(M)
         assert np.array_equal(clist, d["C"])                         # same coarse nodes, same order
         nc = len(clist)
         ip, ix, va = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64)
-        patches = np.empty((nc, 43))
-        fill = np.empty((nc, 31), dtype=np.int32)
-        _lib.check(lib.mg_host_nn_extract_patches(nc, ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches),
-                                                  ptr(fill)), "mg_host_nn_extract_patches")
-        assert d["patches"].shape == patches.shape                   # no extra patch variants in these cases
+        rows_p = lib.mg_host_nn_extract_patches(nc, ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), None, None)
+        assert rows_p == d["patches"].shape[0]                       # nc + extra patch variants (Multigrid.py:631-663)
+        if l == 0:
+            assert rows_p - nc == VARIANTS.get(case, 0)
+        else:
+            assert rows_p == nc                                      # pre_process cuts coarse rows to 6 neighbours
+        patches = np.empty((rows_p, 43))
+        fill = np.empty((rows_p, 31), dtype=np.int32)
+        assert lib.mg_host_nn_extract_patches(nc, ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches),
+                                              ptr(fill)) == rows_p, lib.mg_last_error()
         assert np.array_equal(fill, d["fill"])
         assert np.array_equal(patches, d["patches"])                 # bit for bit
         pred = np.ascontiguousarray(d["pred"])
-        rows = np.empty((nc, 31), dtype=np.int32)
-        cols = np.empty((nc, 31), dtype=np.int32)
-        vals = np.empty((nc, 31))
+        rows = np.empty((rows_p, 31), dtype=np.int32)
+        cols = np.empty((rows_p, 31), dtype=np.int32)
+        vals = np.empty((rows_p, 31))
         dn = -np.ones((nc, 6), dtype=np.int32)
-        _lib.check(lib.mg_host_nn_contributions(nc, ptr(fill), ptr(pred), ptr(cmap), n, ptr(rows), ptr(cols), ptr(vals),
-                                                ptr(dn)), "mg_host_nn_contributions")
+        _lib.check(lib.mg_host_nn_contributions(rows_p, ptr(fill), ptr(pred), ptr(cmap), n, ptr(rows), ptr(cols),
+                                                ptr(vals), ptr(dn)), "mg_host_nn_contributions")
         assert np.array_equal(dn, d["dn"])
         B = fold_reference_rule(rows, cols, vals, n, nc, n)
         assert np.array_equal(B, d["B"])                             # bit for bit, order-dependent means included
@@ -93,18 +99,46 @@ def test_coarsening_extraction_and_fill_match_the_reference(case):
         assert np.array_equal(Q, d["Q"])
 
 
-def test_unsupported_degree_is_reported_not_worked_around():
-    lib = _lib.load()
-    n = 9
+def star(arms):
+    n = arms + 1
     A = sp.lil_matrix((n, n))
     A.setdiag(4.0)
-    A[0, 1:9] = 1.0
-    A[1:9, 0] = 1.0
+    A[0, 1:n] = 1.0 + 0.01 * np.arange(arms)
+    A[1:n, 0] = 1.0
+    for i in range(1, n):                 # a ring, so that no neighbour is left with fewer than 2 neighbours
+        A[i, 1 + i % arms] = 0.5
+        A[1 + i % arms, i] = 0.5
     M = sp.csr_matrix(A)
     M.sort_indices()
+    return M
+
+
+def test_variants_drop_a_sliding_window_of_the_smallest_entries():
+    """a hub with 9 neighbours of increasing mass entry: variant v keeps all but the entries ranked v..v+2"""
+    lib = _lib.load()
+    M = star(9)
+    cmap, clist = host_coarsen(M)
+    assert clist[0] == 0
+    ip, ix, va = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64)
+    rows_p = lib.mg_host_nn_extract_patches(len(clist), ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), None, None)
+    assert rows_p == len(clist) + 3
+    patches = np.empty((rows_p, 43))
+    fill = np.empty((rows_p, 31), dtype=np.int32)
+    assert lib.mg_host_nn_extract_patches(len(clist), ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches),
+                                          ptr(fill)) == rows_p
+    variants = [0] + list(range(len(clist), rows_p))
+    for v, j in enumerate(variants):
+        kept = [k for k in range(1, 10) if not (v <= k - 1 < v + 3)]
+        assert list(fill[j, :7]) == [0] + kept
+        np.testing.assert_array_equal(patches[j, 1:7], 1.0 + 0.01 * (np.array(kept) - 1))
+
+
+def test_more_than_twelve_neighbours_is_reported_not_worked_around():
+    lib = _lib.load()
+    M = star(13)
     cmap, clist = host_coarsen(M)
     ip, ix, va = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64)
-    patches = np.empty((len(clist), 43))
-    fill = np.empty((len(clist), 31), dtype=np.int32)
+    patches = np.empty((len(clist) + 7, 43))
+    fill = np.empty((len(clist) + 7, 31), dtype=np.int32)
     rc = lib.mg_host_nn_extract_patches(len(clist), ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches), ptr(fill))
-    assert rc == -3 and b"more than 6 neighbours" in lib.mg_last_error()
+    assert rc == -3 and b"more than 12 neighbours" in lib.mg_last_error()
