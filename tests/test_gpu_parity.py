@@ -473,6 +473,28 @@ def test_api_2d_two_level_reference_answers(env):
         np.testing.assert_allclose(mg.get_solution()[8 * 17 + 8, 0], -7.3445766e-02, rtol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["N16_quasi", "N16_linear", "N32_quasi"])
+def test_api_2d_two_level_reference_histories(env, name):
+    """SURVEY 8c, 2D two-level answers: the reference's own residual histories, iteration counts and solutions
+    (tests/golden/solve_2d.npz, thesis_structured_2d.py:457-458) through the drop-in API with the reference's
+    index-order Gauss-Seidel"""
+    from learnmultigrid_b200.solvers.Multigrid import SemiGeometricMG
+    g = load_golden("solve_2d.npz")
+    A, Q, rhs = coo_from(g, name + "_A"), coo_from(g, name + "_Q"), g[name + "_rhs"]
+    mg = SemiGeometricMG(A, rhs, Q)
+    mg.solve(levels=2, smoother="GaussSeidel", smooth_steps=3, error=1e-09, max_iterations=20,
+             gs_order="lexicographic")
+    want, x_ref = g[name + "_track"], g[name + "_x"]
+    assert mg.get_iterations() == int(g[name + "_its"]) == 7
+    assert_history_close(mg.track_res, want, A, x_ref)
+    np.testing.assert_allclose(mg.get_solution(), x_ref, rtol=0, atol=1e-12 * np.linalg.norm(x_ref))
+    # multicolour Gauss-Seidel (the engine's default smoother) converges at least as fast on this problem
+    mc = SemiGeometricMG(A, rhs, Q)
+    mc.solve(levels=2, smoother="GaussSeidel", smooth_steps=3, error=1e-09, max_iterations=20)
+    assert mc.get_iterations() <= 8
+    np.testing.assert_allclose(mc.get_solution(), x_ref, rtol=0, atol=1e-8)
+
+
 def test_api_stationary_solvers_cg_direct(env):
     from learnmultigrid_b200.solvers.Jacobi import Jacobi
     from learnmultigrid_b200.solvers.GaussSeidel import GaussSeidel
