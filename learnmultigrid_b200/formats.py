@@ -13,6 +13,15 @@ from . import _lib
 SLICE = 32
 
 
+def solver_csr(A):
+    """The CSR form of what the reference's Solver holds, `csc_matrix(matrix)` (Solver.py:18).  A CSR matrix that is
+    already canonical (sorted, duplicate-free) comes back from the CSR -> CSC -> CSR round trip unchanged, so it is
+    taken as it is (the round trip costs seconds at 10^8 entries)."""
+    if sp.isspmatrix_csr(A) and A.dtype == np.float64 and A.has_canonical_format:
+        return canonical_csr(A)
+    return canonical_csr(sp.csc_matrix(A))
+
+
 def canonical_csr(A):
     """scipy CSR with sorted, duplicate-free int32 indices and float64 data (what SciPy hands to its kernels)."""
     if not sp.issparse(A):
@@ -189,7 +198,7 @@ def build_host_hierarchy(A, Q_list, smoother, colors=None, with_sell=True):
     The Galerkin products are SciPy's `csr_matrix(Q.T @ A @ Q)` (learn_multigrid/solvers/Multigrid.py:97-98).
     """
     L = len(Q_list) + 1
-    A_nat = [canonical_csr(sp.csc_matrix(A))]          # Solver.py:18 stores csc_matrix(matrix)
+    A_nat = [solver_csr(A)]                            # Solver.py:18 stores csc_matrix(matrix)
     Q_nat = [canonical_csr(q) for q in Q_list]
     for l in range(L - 1):
         if Q_nat[l].shape[0] != A_nat[l].shape[0]:

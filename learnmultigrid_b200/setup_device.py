@@ -237,7 +237,7 @@ def build_natural(S, A, Q_list):
         A_host0 = None
         A_nat = [A]
     else:
-        A_host0 = F.canonical_csr(sp.csc_matrix(A))        # Solver.py:18 stores csc_matrix(matrix)
+        A_host0 = F.solver_csr(A)                          # Solver.py:18 stores csc_matrix(matrix)
         A_nat = [S.upload(A_host0)]
     Q_nat, QT_nat = [], []
     for l in range(L - 1):
