@@ -475,6 +475,29 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
                    const mg_dist_norm *norm, void *stream);
 /* number of kernels the last mg_vcycle call on this thread launched (bench.py's gpu_launches) */
 int64_t mg_last_launch_count(void);
+/* Tail program (csrc/tail.cu; off by default).  In mg_vcycle / mg_vcycle_dist, from the first replicated level with at
+ * most `rows` rows downwards, the operations of the cycle (smoothing sweeps, residual, restriction, prolongation,
+ * fills) are not launched one by one but recorded and run by ONE persistent cooperative kernel per stretch -- the way
+ * down to the coarsest solve, the way back up -- whose CTAs walk the record and separate dependent operations by a
+ * grid barrier.  The record travels in the kernel's parameter space (<= 40 operations per launch), so the launch is
+ * capturable in a CUDA graph like any other.  Same per-row arithmetic as the SELL kernels: bit-identical results.
+ * Levels smoothed by index-order Gauss-Seidel are never recorded.  Returns the previous threshold (0 = off). */
+int64_t mg_set_tail_max_rows(int64_t rows);
+/* resident CTAs per SM of that kernel (default 2, clamped to what fits); returns the previous value */
+int mg_set_tail_ctas_per_sm(int ctas);
+/* incremented by the two setters above: a captured graph of the cycle is valid for one value of it */
+int64_t mg_tail_config_epoch(void);
+/* of the last mg_vcycle / mg_vcycle_dist / mg_host_tail_vcycle call on this thread: operations recorded, grid
+ * barriers placed between them, cooperative launches made */
+int mg_tail_last_stats(int64_t *ops, int64_t *barriers, int64_t *launches);
+/* HOST emulation for the CPU test-suite (every pointer in `levels` is a host pointer; Jacobi or multicolour
+ * Gauss-Seidel; dense coarsest inverse): the whole cycle is recorded as a tail program and executed serially with the
+ * same per-row code; shuffle != 0 runs the rows of every barrier-free group of operations in a pseudo-random order,
+ * which is legal exactly if the barriers are placed correctly.  Not called by the product. */
+int mg_host_tail_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, uint64_t shuffle);
+/* TEST HOOK: on != 0 removes every barrier inside a stretch (wrong on purpose), so that the test-suite can show that
+ * the shuffled host execution above does detect a missing barrier.  Returns the previous setting. */
+int mg_tail_debug_drop_barriers(int on);
 
 /* CUDA-graph helpers: capture whatever is enqueued on `stream` between begin and end. */
 int mg_graph_begin(void *stream);

@@ -111,6 +111,12 @@ _SIGNATURES = {
     "mg_set_tma_min_rows": (c_i64, [c_i64]),
     "mg_sell_halo_mask": (c_int, [ctypes.POINTER(mg_sell), c_i64, c_vp, c_vp]),
     "mg_set_fused_exchange": (c_int, [c_int]),
+    "mg_set_tail_max_rows": (c_i64, [c_i64]),
+    "mg_set_tail_ctas_per_sm": (c_int, [c_int]),
+    "mg_tail_config_epoch": (c_i64, []),
+    "mg_tail_last_stats": (c_int, [c_vp, c_vp, c_vp]),
+    "mg_host_tail_vcycle": (c_int, [c_vp, c_int, c_vp, ctypes.c_uint64]),
+    "mg_tail_debug_drop_barriers": (c_int, [c_int]),
     "mg_set_wide_min_len": (c_i64, [c_i64]),
     "mg_set_wide_max_rows": (c_i64, [c_i64]),
     "mg_sell_jacobi": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
@@ -230,6 +236,8 @@ def load():
         lib.mg_set_fused_exchange(0)
     if "MGB_WIDE_MIN_LEN" in os.environ:
         lib.mg_set_wide_min_len(int(os.environ["MGB_WIDE_MIN_LEN"]))
+    if "MGB_TAIL_MAX_ROWS" in os.environ:
+        lib.mg_set_tail_max_rows(int(os.environ["MGB_TAIL_MAX_ROWS"]))
     if "MGB_WIDE_MAX_ROWS" in os.environ:
         lib.mg_set_wide_max_rows(int(os.environ["MGB_WIDE_MAX_ROWS"]))
     _lib = lib

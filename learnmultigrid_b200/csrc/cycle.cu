@@ -48,6 +48,60 @@ int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStre
         if (_rc) return _rc;    \
     } while (0)
 
+// ---- tail program (tail.cu): on small replicated levels the operations are recorded and run by one persistent
+// cooperative kernel instead of one launch each.  The op_* wrappers below are what the cycle calls on levels that may
+// be recorded; outside a recording they are the plain launches.
+enum TailKind { T_SELL = 0, T_FILL = 1, T_DIAG_SCALE = 2, T_COPY = 3 };
+bool tail_recording();
+bool tail_host_mode();
+int64_t tail_max_rows();
+void tail_begin(bool host, uint64_t shuffle);
+void tail_end();
+int tail_flush(cudaStream_t st);
+void tail_stats_reset();
+void tail_record_sell(int mode, const mg_sell *A, const double *x, const double *b, const double *aux, double *y,
+                      double omega, int64_t row0, int64_t row1);
+void tail_record_vector(int kind, int64_t n, double value, const double *src, const double *b, const double *aux,
+                        double *y);
+struct TailScope {          // ends a recording on every exit path of the frame that began it
+    bool on = false;
+    ~TailScope() { if (on) tail_end(); }
+};
+
+static int op_gs_rows(const mg_sell *A, double *x, const double *b, int64_t r0, int64_t r1, cudaStream_t st) {
+    if (tail_recording()) { tail_record_sell(GS, A, x, b, nullptr, x, 0.0, r0, r1); return MG_OK; }
+    return sell_gs_rows(A, x, b, r0, r1, st);
+}
+static int op_jacobi(const mg_sell *A, const double *dinv, const double *x, const double *b, double *xo, double omega,
+                     cudaStream_t st) {
+    if (tail_recording()) { tail_record_sell(JACOBI, A, x, b, dinv, xo, omega, 0, A->nrows); return MG_OK; }
+    return sell_jacobi(A, dinv, x, b, xo, omega, st);
+}
+static int op_residual(const mg_sell *A, const double *x, const double *b, double *r, cudaStream_t st) {
+    if (tail_recording()) { tail_record_sell(RESID, A, x, b, nullptr, r, 0.0, 0, A->nrows); return MG_OK; }
+    return sell_residual(A, x, b, r, st);
+}
+static int op_spmv(const mg_sell *A, const double *x, double *y, cudaStream_t st) {
+    if (tail_recording()) { tail_record_sell(SPMV, A, x, nullptr, nullptr, y, 0.0, 0, A->nrows); return MG_OK; }
+    return sell_spmv(A, x, y, st);
+}
+static int op_prolong(const mg_sell *Q, const double *e, const double *u, double *uo, cudaStream_t st) {
+    if (tail_recording()) { tail_record_sell(PROLONG, Q, e, nullptr, u, uo, 0.0, 0, Q->nrows); return MG_OK; }
+    return sell_prolong(Q, e, u, uo, st);
+}
+static int op_fill(int64_t n, double v, double *x, cudaStream_t st) {
+    if (tail_recording()) { tail_record_vector(T_FILL, n, v, nullptr, nullptr, nullptr, x); return MG_OK; }
+    return vec_fill(n, v, x, st);
+}
+static int op_diag_scale(int64_t n, double omega, const double *dinv, const double *b, double *out, cudaStream_t st) {
+    if (tail_recording()) { tail_record_vector(T_DIAG_SCALE, n, omega, nullptr, b, dinv, out); return MG_OK; }
+    return vec_diag_scale(n, omega, dinv, b, out, st);
+}
+static int op_copy(int64_t n, const double *src, double *dst, cudaStream_t st) {
+    if (tail_recording()) { tail_record_vector(T_COPY, n, 0.0, src, nullptr, nullptr, dst); return MG_OK; }
+    return vec_axpby(n, 1.0, src, 0.0, nullptr, dst, st);
+}
+
 // Deferred exchange: with multicolour Gauss-Seidel an exchange of a level vector is not launched when it is issued
 // but handed to the next SELL kernel that gathers from that vector, which carries it as extra CTAs (sell_kernel_fused).
 // Anything else that needs the halo first calls flush_pending().
@@ -107,7 +161,7 @@ static inline int halo_all(mg_comm *comm, const mg_level &L, double *v, cudaStre
 static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, int steps, double **cur, double **alt,
                   bool zero_guess, bool reverse, cudaStream_t st) {
     if (steps <= 0) {
-        if (zero_guess) MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
+        if (zero_guess) MG_TRY(op_fill(vec_len(L), 0.0, *cur, st));
         return MG_OK;
     }
     if (P.smoother == MG_SMOOTH_JACOBI) {
@@ -115,22 +169,22 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
         if (zero_guess) {
             if (P.zero_guess_skip) {
                 // x1 = 0 + omega*(dinv*(b - A*0)) = omega*(dinv*b): same bits as a sweep on zeros, no matrix pass
-                MG_TRY(vec_diag_scale(L.n, P.omega, L.d_dinv, L.d_b, *alt, st));
+                MG_TRY(op_diag_scale(L.n, P.omega, L.d_dinv, L.d_b, *alt, st));
                 MG_TRY(halo_all(comm, L, *alt, st));
                 double *t = *cur; *cur = *alt; *alt = t;
                 s = 1;
             } else {
-                MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
+                MG_TRY(op_fill(vec_len(L), 0.0, *cur, st));
             }
         }
         for (; s < steps; ++s) {
-            MG_TRY(sell_jacobi(&L.A, L.d_dinv, *cur, L.d_b, *alt, P.omega, st));
+            MG_TRY(op_jacobi(&L.A, L.d_dinv, *cur, L.d_b, *alt, P.omega, st));
             MG_TRY(halo_all(comm, L, *alt, st));
             double *t = *cur; *cur = *alt; *alt = t;
         }
         return MG_OK;
     }
-    if (zero_guess) MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
+    if (zero_guess) MG_TRY(op_fill(vec_len(L), 0.0, *cur, st));
     if (P.smoother == MG_SMOOTH_MCGS) {
         if (L.ncolors <= 0 || !L.h_color_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no colouring");
         if (L.dist && L.dist->ncolors != L.ncolors) return set_error(MG_ERR_INVALID, "mg_vcycle", "halo plan and colouring disagree");
@@ -145,12 +199,13 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
                     else MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
                     MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
                 } else {
-                    MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
+                    MG_TRY(op_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
                 }
             }
         return MG_OK;
     }
     if (P.smoother == MG_SMOOTH_LEXGS) {
+        if (tail_recording()) return set_error(MG_ERR_UNSUPPORTED, "mg_vcycle", "index-order Gauss-Seidel cannot be part of a tail program");
         if (L.dist) return set_error(MG_ERR_UNSUPPORTED, "mg_vcycle", "index-order Gauss-Seidel is serial across row blocks; not available on partitioned levels");
         if (!L.d_csr_indptr || !L.d_lex_level_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no lexicographic schedule");
         return csr_gs_lex(L.d_csr_indptr, L.d_csr_indices, L.d_csr_values, *cur, L.d_b, L.d_lex_level_ptr,
@@ -163,6 +218,16 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
                       cudaStream_t st) {
     const mg_level &L = levels[l];
     if (l == nlevels - 1) {   // coarsest: direct solve (Multigrid.py:106)
+        MG_TRY(tail_flush(st));                                      // a recorded tail runs before the solve's own kernels
+        if (tail_host_mode()) {                                      // CPU test-suite: dense inverse applied on the host
+            if (L.coarse_kind != MG_COARSE_DENSE || !L.d_coarse_inv) return set_error(MG_ERR_UNSUPPORTED, "mg_host_tail_vcycle", "host mode needs a dense coarsest inverse");
+            for (int64_t i = 0; i < L.n; ++i) {
+                double acc = 0.0;
+                for (int64_t j = 0; j < L.n; ++j) acc += L.d_coarse_inv[i * L.n + j] * L.d_b[j];
+                L.d_x[i] = acc;
+            }
+            return MG_OK;
+        }
         if (L.coarse_kind == MG_COARSE_DENSE) {
             if (!L.d_coarse_inv) return set_error(MG_ERR_INVALID, "mg_vcycle", "coarsest level has no inverse");
             return dense_gemv(L.n, L.n, L.d_coarse_inv, L.d_b, L.d_x, st);
@@ -185,6 +250,14 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
         }
     }
     if (!L.dist) MG_TRY(flush_pending(comm, st));                    // replicated level: nothing may be in flight
+    // from the first level that is small enough (and replicated, like everything below it) the operations are recorded
+    // into a tail program; the frame that starts the recording flushes and ends it
+    TailScope tail;
+    if (!tail_recording() && tail_max_rows() > 0 && !L.dist && L.n <= tail_max_rows() &&
+        (P.smoother == MG_SMOOTH_JACOBI || P.smoother == MG_SMOOTH_MCGS)) {
+        tail_begin(false, 0);
+        tail.on = true;
+    }
     const bool defer = P.smoother == MG_SMOOTH_MCGS;                 // exchanges ride on the next SELL kernel
     SellFuse f;
     bool use = false;
@@ -206,8 +279,8 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
             MG_TRY(comm_exchange(comm, D.xfer_gather, D.d_gather_tmp, C.d_b, st));
         }
     } else {
-        MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));          // res = rhs - A u
-        MG_TRY(sell_spmv(&L.QT, L.d_r, C.d_b, st));                  // res_coarse = Q^T res
+        MG_TRY(op_residual(&L.A, cur, L.d_b, L.d_r, st));            // res = rhs - A u
+        MG_TRY(op_spmv(&L.QT, L.d_r, C.d_b, st));                    // res_coarse = Q^T res
     }
     MG_TRY(vcycle_rec(comm, levels, nlevels, l + 1, P, st));         // u_coarse
     double *out = prolong_flip ? alt : cur;                          // u = u + Q u_coarse (out of place when flipping)
@@ -217,7 +290,7 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
         if (use) MG_TRY(sell_prolong_fused(&L.Q, C.d_x, cur, out, &f, st));
         else MG_TRY(sell_prolong(&L.Q, C.d_x, cur, out, st));
     } else {
-        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, out, st));
+        MG_TRY(op_prolong(&L.Q, C.d_x, cur, out, st));
     }
     if (prolong_flip) { double *t = cur; cur = alt; alt = t; }
     // every boundary value changed.  Deferred, this exchange rides on the first post-smoothing sweep, which rewrites
@@ -225,7 +298,8 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
     // after its sweep.
     if (L.dist) MG_TRY(issue_exchange(comm, L.dist->xfer_all, cur, defer, st));
     MG_TRY(smooth(comm, L, P, P.nu_post, &cur, &alt, false, P.reverse_post != 0, st));
-    if (cur != L.d_x) MG_TRY(vec_axpby(vec_len(L), 1.0, cur, 0.0, nullptr, L.d_x, st));   // safety net; not reached
+    if (cur != L.d_x) MG_TRY(op_copy(vec_len(L), cur, L.d_x, st));   // safety net; not reached
+    if (tail.on) MG_TRY(tail_flush(st));
     return MG_OK;
 }
 
@@ -300,6 +374,7 @@ int mg_device_info(int *sm, int64_t *mem, int *cc) {
 int mg_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, void *stream) {
     MG_TRY(check_levels(levels, nlevels, params, false));
     const int64_t before = g_launch_count;
+    tail_stats_reset();
     int rc = vcycle_rec(nullptr, levels, nlevels, 0, *params, (cudaStream_t)stream);
     g_last_cycle_launches = g_launch_count - before;
     return rc;
@@ -313,6 +388,7 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     else MG_REQUIRE(levels && nlevels >= 1, "no level");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t before = g_launch_count;
+    tail_stats_reset();
     MG_TRY(mg_comm_begin(comm));
     g_pend.x = nullptr;
     int rc = MG_OK;
@@ -330,6 +406,23 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
 }
 
 int64_t mg_last_launch_count(void) { return g_last_cycle_launches; }
+
+/* The V-cycle with EVERY level recorded into a tail program and executed serially on the HOST (all pointers of the
+ * mg_level array are host pointers; multicolour Gauss-Seidel or Jacobi; dense coarsest inverse).  This is how the CPU
+ * test-suite checks the recorder, the placement of the grid barriers (shuffle != 0: the rows of every barrier-free
+ * group of operations run in a pseudo-random order) and the per-row arithmetic of tail.cu without a GPU.  Not called
+ * by the product. */
+int mg_host_tail_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, uint64_t shuffle) {
+    MG_TRY(check_levels(levels, nlevels, params, false));
+    MG_REQUIRE(params->smoother == MG_SMOOTH_JACOBI || params->smoother == MG_SMOOTH_MCGS, "Jacobi or multicolour Gauss-Seidel only");
+    tail_stats_reset();
+    tail_begin(true, shuffle);
+    TailScope scope;
+    scope.on = true;
+    int rc = vcycle_rec(nullptr, levels, nlevels, 0, *params, nullptr);
+    if (!rc) rc = tail_flush(nullptr);
+    return rc;
+}
 
 int mg_graph_begin(void *stream) {
     MG_CHECK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));

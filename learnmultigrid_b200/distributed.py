@@ -559,7 +559,7 @@ class DistributedHierarchy(DeviceHierarchy):
             self.last_launches = int(self.lib.mg_last_launch_count())
             return
         key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip,
-               params.reverse_post, bool(with_norm), bool(dry))
+               params.reverse_post, bool(with_norm), bool(dry), int(self.lib.mg_tail_config_epoch()))
         g = self._graphs.get(key)
         if g is None:
             cap = torch.cuda.Stream(device=self.device)
