@@ -69,3 +69,15 @@ def test_embedded_mass_matrix_fills_boundary_patches():
     h2 = (1.0 / 8) ** 2
     np.testing.assert_allclose(rows.diagonal(), h2 / 2, rtol=1e-12)
     np.testing.assert_allclose(np.asarray(rows.sum(axis=1)).ravel(), h2, rtol=1e-12)
+
+
+@pytest.mark.parametrize("ne,key", [(16, "N4"), (256, "N16"), (12, "rect12")])
+def test_structured_mesh_construction_equals_reference(ne, key):
+    """Mesh2D(ne): node coordinates and element list of the reference (Mesh2D.py:41-93), including the rectangular
+    4 x 3 split that find_balanced_couple picks for ne = 12 (tests/golden/assembly_2d.npz)"""
+    from learnmultigrid_b200.mesh.Mesh2D import Mesh2D
+    d = load_golden("assembly_2d.npz")
+    m = Mesh2D(ne)
+    assert np.array_equal(m.get_points(), d[key + "_p"])
+    assert np.array_equal(m.get_connections(), d[key + "_conn"])
+    assert m.get_np() == len(d[key + "_p"]) and m.get_ne() == len(d[key + "_conn"])

@@ -142,3 +142,50 @@ def test_more_than_twelve_neighbours_is_reported_not_worked_around():
     fill = np.empty((len(clist) + 7, 31), dtype=np.int32)
     rc = lib.mg_host_nn_extract_patches(len(clist), ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches), ptr(fill))
     assert rc == -3 and b"more than 12 neighbours" in lib.mg_last_error()
+
+
+def test_first_reference_run_with_the_stub_predictor():
+    """tests/golden/neural_2d_stub.npz: the reference's NeuralMG_2D on Mesh2D(64) (SURVEY 8c probe: the 25 coarse nodes
+    (2j, 2k), patches (25, 43), Q shapes (81, 25) and (25, 9))"""
+    lib = _lib.load()
+    g = load_golden("neural_2d_stub.npz")
+    M = sp.csr_matrix((g["M_data"], (g["M_row"], g["M_col"])), shape=tuple(g["M_shape"]))
+    M.sort_indices()
+    cmap, clist = host_coarsen(M)
+    assert np.array_equal(clist, g["C_order"]) and np.array_equal(np.sort(clist), g["C"])
+    assert np.array_equal(clist, [9 * (2 * j) + 2 * k for j in range(5) for k in range(5)])
+    ip, ix, va = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64)
+    patches = np.empty((25, 43))
+    fill = np.empty((25, 31), dtype=np.int32)
+    assert lib.mg_host_nn_extract_patches(25, ptr(ip), ptr(ix), ptr(va), ptr(cmap), ptr(clist), ptr(patches),
+                                          ptr(fill)) == 25
+    assert np.array_equal(patches, g["patches"]) and np.array_equal(fill, g["fill"])
+    h2 = (1.0 / 8) ** 2                                                   # interior patch of SURVEY 8c
+    k = list(clist).index(40)
+    np.testing.assert_allclose(patches[k], [h2 / 2] + [h2 / 12] * 6 + ([h2 / 2] + [h2 / 12] * 5) * 6, rtol=1e-12)
+    assert list(fill[k, :13]) == [40, 30, 31, 39, 41, 49, 50, 20, 22, 38, 42, 58, 60]
+    assert g["Q0"].shape == (81, 25) and g["Q1"].shape == (25, 9)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_next_level_mass_matrix_is_the_galerkin_product(case):
+    """define_hierarchy's `mass = Q^T mass Q` (Multigrid.py:763): the stored next-level / final matrices are the SciPy
+    products of the stored Q and M, pattern and values (what the device SpGEMM is checked against on the GPU)"""
+    g = load_golden("neural_2d_cases.npz")
+    lv = levels_of(g, case)
+    for l, d in enumerate(lv):
+        Q = sp.csr_matrix(d["Q"])
+        prod = sp.csr_matrix(Q.T @ d["M"] @ Q)
+        prod.sort_indices()
+        if l + 1 < len(lv):
+            # the next level's stored matrix is the product after pre_process cut its rows to the predicted neighbours
+            nxt = lv[l + 1]["M"]
+            dense = prod.toarray()
+            keep = nxt.toarray() != 0
+            assert np.all(dense[keep] != 0)
+            np.testing.assert_allclose(nxt.toarray()[keep], dense[keep], rtol=1e-13)
+            assert np.all(np.diff(nxt.indptr) <= 7)                  # diagonal + at most 6 predicted neighbours
+        else:
+            key = "%s__final_M_" % case
+            fin = sp.csr_matrix((g[key + "data"], (g[key + "row"], g[key + "col"])), shape=tuple(g[key + "shape"]))
+            np.testing.assert_allclose(fin.toarray(), prod.toarray(), rtol=1e-13, atol=1e-300)
