@@ -5,6 +5,7 @@
 // The Galerkin product (:97-98) and the coarse factorisation (:106), which the reference repeats in every
 // cycle, are hoisted to setup; the arithmetic of a cycle is unchanged.
 #include "exchange.cuh"
+#include "tail.cuh"
 
 namespace mgb {
 
@@ -51,18 +52,6 @@ int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStre
 // ---- tail program (tail.cu): on small replicated levels the operations are recorded and run by one persistent
 // cooperative kernel instead of one launch each.  The op_* wrappers below are what the cycle calls on levels that may
 // be recorded; outside a recording they are the plain launches.
-enum TailKind { T_SELL = 0, T_FILL = 1, T_DIAG_SCALE = 2, T_COPY = 3 };
-bool tail_recording();
-bool tail_host_mode();
-int64_t tail_max_rows();
-void tail_begin(bool host, uint64_t shuffle);
-void tail_end();
-int tail_flush(cudaStream_t st);
-void tail_stats_reset();
-void tail_record_sell(int mode, const mg_sell *A, const double *x, const double *b, const double *aux, double *y,
-                      double omega, int64_t row0, int64_t row1);
-void tail_record_vector(int kind, int64_t n, double value, const double *src, const double *b, const double *aux,
-                        double *y);
 struct TailScope {          // ends a recording on every exit path of the frame that began it
     bool on = false;
     ~TailScope() { if (on) tail_end(); }

@@ -18,13 +18,11 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <vector>
-#include "common.cuh"
+#include "tail.cuh"
 
 namespace cg = cooperative_groups;
 
 namespace mgb {
-
-enum TailKind { T_SELL = 0, T_FILL = 1, T_DIAG_SCALE = 2, T_COPY = 3 };
 
 struct TailOp {
     const int64_t *slice_ptr;   // SELL matrix (T_SELL)
