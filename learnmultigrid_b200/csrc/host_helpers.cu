@@ -13,35 +13,46 @@ extern "C" {
 // Returns the number of colours (>0) or a negative status.
 int mg_host_greedy_color(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_colors) {
     MG_REQUIRE(n >= 0 && h_indptr && h_colors, "null argument");
-    std::vector<uint64_t> forbidden_lo((size_t)n, 0), forbidden_hi((size_t)n, 0);
+    // forbidden[i]: colours already taken by neighbours that were coloured BEFORE row i and reach it only through their
+    // own row (entry (j,i) without (i,j): the pattern need not be symmetric).  One 64-bit word per row; the second word
+    // (colours 64..127) is only allocated if a 65th colour is ever needed.
+    std::vector<uint64_t> forbidden_lo((size_t)n, 0), forbidden_hi;
+    std::vector<int64_t> deferred;                 // rows with nothing but a diagonal entry, coloured last
     for (int64_t i = 0; i < n; ++i) h_colors[i] = -1;
     int ncolors = 0;
-    for (int pass = 0; pass < 2; ++pass) {
-        for (int64_t i = 0; i < n; ++i) {
-            bool has_offdiag = false;
-            for (int32_t p = h_indptr[i]; p < h_indptr[i + 1]; ++p)
-                if (h_indices[p] != i) { has_offdiag = true; break; }
-            if (has_offdiag != (pass == 0)) continue;
-            uint64_t lo = forbidden_lo[i], hi = forbidden_hi[i];
-            for (int32_t p = h_indptr[i]; p < h_indptr[i + 1]; ++p) {
-                const int32_t j = h_indices[p];
-                const int32_t c = (j != i) ? h_colors[j] : -1;
-                if (c >= 0) { if (c < 64) lo |= (1ull << c); else hi |= (1ull << (c - 64)); }
-            }
-            int c;
-            if (~lo) c = __builtin_ctzll(~lo);
-            else if (~hi) c = 64 + __builtin_ctzll(~hi);
-            else return set_error(MG_ERR_UNSUPPORTED, "mg_host_greedy_color", "more than 128 colours needed");
-            h_colors[i] = c;
-            if (c + 1 > ncolors) ncolors = c + 1;
-            for (int32_t p = h_indptr[i]; p < h_indptr[i + 1]; ++p) {
-                const int32_t j = h_indices[p];
-                if (j != i && h_colors[j] < 0) {
-                    if (c < 64) forbidden_lo[j] |= (1ull << c); else forbidden_hi[j] |= (1ull << (c - 64));
-                }
+    auto color_row = [&](int64_t i) -> int {
+        const int32_t p0 = h_indptr[i], p1 = h_indptr[i + 1];
+        uint64_t lo = forbidden_lo[i], hi = forbidden_hi.empty() ? 0 : forbidden_hi[i];
+        for (int32_t p = p0; p < p1; ++p) {
+            const int32_t j = h_indices[p];
+            if (j == i) continue;
+            const int32_t c = h_colors[j];
+            if (c >= 0) { if (c < 64) lo |= (1ull << c); else hi |= (1ull << (c - 64)); }
+        }
+        int c;
+        if (~lo) c = __builtin_ctzll(~lo);
+        else if (~hi) c = 64 + __builtin_ctzll(~hi);
+        else return -1;
+        h_colors[i] = c;
+        if (c + 1 > ncolors) ncolors = c + 1;
+        if (c >= 64 && forbidden_hi.empty()) forbidden_hi.assign((size_t)n, 0);
+        for (int32_t p = p0; p < p1; ++p) {
+            const int32_t j = h_indices[p];
+            if (j != i && h_colors[j] < 0) {
+                if (c < 64) forbidden_lo[j] |= (1ull << c); else forbidden_hi[j] |= (1ull << (c - 64));
             }
         }
+        return c;
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t p0 = h_indptr[i], p1 = h_indptr[i + 1];
+        const bool diag_only = p1 == p0 || (p1 - p0 == 1 && h_indices[p0] == i) ||
+                               [&] { for (int32_t p = p0; p < p1; ++p) if (h_indices[p] != i) return false; return true; }();
+        if (diag_only) { deferred.push_back(i); continue; }
+        if (color_row(i) < 0) return set_error(MG_ERR_UNSUPPORTED, "mg_host_greedy_color", "more than 128 colours needed");
     }
+    for (int64_t i : deferred)
+        if (color_row(i) < 0) return set_error(MG_ERR_UNSUPPORTED, "mg_host_greedy_color", "more than 128 colours needed");
     return ncolors;
 }
 
