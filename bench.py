@@ -413,6 +413,31 @@ def run_b200(a):
                 "cycle": {"algorithmic_bytes": cyc["total"], "achieved": cyc_gbs, "frac": cyc_gbs / peak,
                           "frac_of_8TBps": cyc_gbs / 8000.0, "bytes_per_dof": cyc["total"] / ndof}}
 
+    # ---- SpMV per level (the metric's second half): y = A_l x on every smoothed level, algorithmic bytes
+    # S(nnz, n) + 16 n over the CUDA-event time of back-to-back launches; this rank's rows when partitioned.
+    # Informational: a failure here must not cost the headline numbers.
+    try:
+        per_level = []
+        for l, lev in enumerate(h.levels[:-1]):
+            nnz_l = getattr(lev, "local_nnz_A", lev.nnz_A)
+            bytes_l = 12 * nnz_l + 4 * (lev.n + 1) + 16 * lev.n
+            reps_l = 20 if lev.n > (1 << 20) else 100
+            for _ in range(3):
+                _lib.check(lib.mg_sell_spmv(ctypes.byref(lev.A.struct), lev.x.data_ptr(), lev.r.data_ptr(), st))
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(reps_l):
+                _lib.check(lib.mg_sell_spmv(ctypes.byref(lev.A.struct), lev.x.data_ptr(), lev.r.data_ptr(), st))
+            e1.record()
+            torch.cuda.synchronize()
+            ms_l = e0.elapsed_time(e1) / reps_l
+            gbs_l = bytes_l / (ms_l * 1e-3) / 1e9
+            per_level.append({"level": l, "rows": int(lev.n), "nnz": int(nnz_l), "us_per_launch": round(ms_l * 1e3, 2),
+                              "gbs": round(gbs_l, 1), "frac": round(gbs_l / peak, 4)})
+        roofline["spmv_per_level"] = per_level
+    except Exception as exc:         # pragma: no cover
+        roofline["spmv_per_level"] = {"error": repr(exc)}
+
     # ---- end to end through the reference-facing API (host rhs -> solve -> host solution) -----------------------
     e2e = None
     if not a.no_e2e and (rank == 0 or part):
