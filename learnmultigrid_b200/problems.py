@@ -30,27 +30,33 @@ def boundary_nodes_2d(N):
     return np.flatnonzero((ix == 0) | (ix == N) | (iy == 0) | (iy == N))
 
 
-def structured_laplacian_2d(N, coefficient=None):
+def structured_laplacian_2d(N, coefficient=None, rows=None):
     """P1 stiffness matrix of -div(k grad u) on the reference's structured mesh Mesh2D(N*N) ((N+1)^2 nodes, row
     major), with boundary rows replaced by identity rows exactly as test/thesis_structured_2d.py:407-414.
     k = 1 gives the 5-point stencil [-1,-1,4,-1,-1] (hypotenuse couplings are exact zeros and not stored);
-    `coefficient(x, y)` is evaluated at element centroids.  Returns canonical CSR."""
+    `coefficient(x, y)` is evaluated at element centroids.  Returns canonical CSR.
+    rows=(r0, r1): only that row block (global column ids) -- what one rank of a row-partitioned run generates, so
+    that no process ever holds the global operator (partition_setup.py)."""
     W = N + 1
     n = W * W
-    if n * 5 >= 2 ** 31:
+    r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
+    if not 0 <= r0 <= r1 <= n:
+        raise ValueError("row block outside the matrix")
+    if (r1 - r0) * 5 >= 2 ** 31 or n >= 2 ** 31:
         raise OverflowError("nnz does not fit int32")
-    iy, ix = np.divmod(np.arange(n, dtype=np.int64), W)
+    iy, ix = np.divmod(np.arange(r0, r1, dtype=np.int64), W)
     interior = (ix > 0) & (ix < N) & (iy > 0) & (iy < N)
     counts = np.where(interior, 5, 1).astype(np.int64)
-    indptr = np.zeros(n + 1, dtype=np.int64)
+    indptr = np.zeros(r1 - r0 + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     indices = np.empty(indptr[-1], dtype=np.int32)
     data = np.empty(indptr[-1], dtype=np.float64)
     b = np.flatnonzero(~interior)
-    indices[indptr[b]] = b
+    indices[indptr[b]] = b + r0
     data[indptr[b]] = 1.0
-    r = np.flatnonzero(interior)
-    base = indptr[r]
+    loc = np.flatnonzero(interior)
+    r = loc + r0                                   # global row ids of the interior rows of the block
+    base = indptr[loc]
     if coefficient is None:
         vals = (-1.0, -1.0, 4.0, -1.0, -1.0)
         for k, off in enumerate((-W, -1, 0, 1, W)):
@@ -64,7 +70,7 @@ def structured_laplacian_2d(N, coefficient=None):
 
         def k2(sx, sy):
             return coefficient((sx + 1.0 / 3.0) * h, (sy + 2.0 / 3.0) * h)
-        x, y = ix[r], iy[r]
+        x, y = ix[loc], iy[loc]
         # horizontal edge (x,y)-(x+1,y): shared by type-1 of square (x,y) [legs] and type-2 of square (x,y-1)
         east = -0.5 * (k1(x, y) + k2(x, y - 1))
         west = -0.5 * (k1(x - 1, y) + k2(x - 1, y - 1))
@@ -75,7 +81,7 @@ def structured_laplacian_2d(N, coefficient=None):
         for k, (off, v) in enumerate(((-W, south), (-1, west), (0, diag), (1, east), (W, north))):
             indices[base + k] = r + off
             data[base + k] = v
-    return F.raw_csr(indptr.astype(np.int32), indices, data, (n, n))
+    return F.raw_csr(indptr.astype(np.int32), indices, data, (r1 - r0, n))
 
 
 def structured_rhs_2d(N, f_value=-1.0):
@@ -88,18 +94,22 @@ def structured_rhs_2d(N, f_value=-1.0):
     return rhs.reshape(-1, 1)
 
 
-def linear_P_2d(Nf):
+def linear_P_2d(Nf, rows=None):
     """linear interpolation from the nested coarse mesh Mesh2D((Nf/2)^2) to Mesh2D(Nf^2): coincident nodes 1,
-    edge midpoints 1/2 + 1/2 (horizontal, vertical and the lower-left/upper-right diagonal).  CSR."""
+    edge midpoints 1/2 + 1/2 (horizontal, vertical and the lower-left/upper-right diagonal).  CSR.
+    rows=(r0, r1): only that block of fine rows (global coarse column ids)."""
     if Nf % 2:
         raise ValueError("Nf must be even")
     Wf, Wc = Nf + 1, Nf // 2 + 1
-    iy, ix = np.divmod(np.arange(Wf * Wf, dtype=np.int64), Wf)
+    r0, r1 = (0, Wf * Wf) if rows is None else (int(rows[0]), int(rows[1]))
+    if not 0 <= r0 <= r1 <= Wf * Wf:
+        raise ValueError("row block outside the matrix")
+    iy, ix = np.divmod(np.arange(r0, r1, dtype=np.int64), Wf)
     cx, cy = ix // 2, iy // 2
     ox, oy = ix % 2, iy % 2
     two = (ox + oy) > 0
     counts = np.where(two, 2, 1)
-    indptr = np.zeros(Wf * Wf + 1, dtype=np.int64)
+    indptr = np.zeros(r1 - r0 + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
     indices = np.empty(indptr[-1], dtype=np.int32)
     data = np.empty(indptr[-1], dtype=np.float64)
@@ -110,7 +120,7 @@ def linear_P_2d(Nf):
     t = np.flatnonzero(two)
     indices[indptr[t] + 1] = second[t]
     data[indptr[t] + 1] = 0.5
-    return F.raw_csr(indptr.astype(np.int32), indices, data, (Wf * Wf, Wc * Wc))
+    return F.raw_csr(indptr.astype(np.int32), indices, data, (r1 - r0, Wc * Wc))
 
 
 def structured_mass_2d(N):

@@ -1,0 +1,217 @@
+"""Strip-local hierarchy setup (learnmultigrid_b200/partition_setup.py): every rank holds only its row blocks of A_l and
+Q_l, fetches the few remote rows it needs and forms its rows of A_{l+1} = Q^T A Q.  Checked against the single-process
+product -- SciPy's `csr_matrix(Q.T @ A @ Q)` with A held as CSC, which is what the reference computes
+(Multigrid.py:97-98, Solver.py:18) and what the device SpGEMM reproduces -- BIT FOR BIT, values and sparsity patterns,
+on virtual ranks (threads) and in a world_size-2 gloo run."""
+import os
+import subprocess
+import sys
+import threading
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from learnmultigrid_b200 import formats as F
+from learnmultigrid_b200 import partition as PT
+from learnmultigrid_b200 import partition_setup as PS
+from learnmultigrid_b200 import problems as P
+from helpers import coo_from, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_ranks(world, fn):
+    """fn(fabric_view) on `world` threads (the ThreadFabric of the virtual-rank GPU tests, without a device)"""
+    from learnmultigrid_b200.distributed import ThreadFabric
+    fab = ThreadFabric(world)
+    out, err = [None] * world, [None] * world
+
+    def work(r):
+        try:
+            out[r] = fn(fab.view(r))
+        except BaseException as e:       # noqa: BLE001
+            err[r] = e
+            fab.abort()
+    ts = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in err:
+        if e is not None and not isinstance(e, threading.BrokenBarrierError):
+            raise e
+    return out
+
+
+def global_hierarchy(A, Qs):
+    """single-process reference: the reference's expression, level by level"""
+    As = [F.canonical_csr(A)]
+    cur = sp.csc_matrix(A)
+    for Q in Qs:
+        Q = F.canonical_csr(Q)
+        cur = sp.csr_matrix(Q.T @ cur @ Q)
+        cur.sort_indices()
+        As.append(F.canonical_csr(cur))
+    return As
+
+
+def same(got, want):
+    got, want = sp.csr_matrix(got), sp.csr_matrix(want)
+    got.sort_indices()
+    want.sort_indices()
+    assert got.shape == want.shape
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)   # pattern exact
+    assert np.array_equal(got.data, want.data)                                                    # values bit for bit
+
+
+def strip_run(A, Qs, world):
+    A = F.canonical_csr(A)
+    Qs = [F.canonical_csr(Q) for Q in Qs]
+    ns = [A.shape[0]] + [Q.shape[1] for Q in Qs]
+    offs = [PT.block_offsets(n, world) for n in ns]
+
+    def body(fab):
+        r = fab.rank
+        A_blk = A[offs[0][r]:offs[0][r + 1]]
+        Q_blks = [Q[offs[l][r]:offs[l][r + 1]] for l, Q in enumerate(Qs)]
+        return PS.build_strip_hierarchy(fab, A_blk, Q_blks, offs)
+    return offs, run_ranks(world, body)
+
+
+CASES = {
+    "lap2d_linear": lambda: (P.structured_laplacian_2d(32), P.structured_hierarchy_2d(32, 4, "linear")),
+    "varcoef2d_quasi": lambda: (P.structured_laplacian_2d(32, P.variable_coefficient),
+                                P.structured_hierarchy_2d(32, 4, "quasi")),
+}
+
+
+@pytest.mark.parametrize("case", sorted(CASES))
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_strip_hierarchy_equals_the_global_product(case, world):
+    A, Qs = CASES[case]()
+    want = global_hierarchy(A, Qs)
+    offs, res = strip_run(A, Qs, world)
+    for l in range(len(want)):
+        same(sp.vstack([res[r][0][l] for r in range(world)], format="csr"), want[l])
+    for l, Q in enumerate(Qs):
+        QT = sp.csr_matrix(F.canonical_csr(Q).T)
+        QT.sort_indices()
+        same(sp.vstack([res[r][1][l] for r in range(world)], format="csr"), QT)
+
+
+def test_strip_galerkin_1d_c1_three_transfer_types():
+    c1 = load_golden("c1_1d_1024.npz")
+    A = coo_from(c1, "A")
+    for Q in (coo_from(c1, "Q_quasi"), coo_from(c1, "Q_pseudo"), sp.csr_matrix(c1["Q_L2_dense"])):
+        want = global_hierarchy(A, [Q])
+        offs, res = strip_run(A, [Q], 4)
+        same(sp.vstack([res[r][0][1] for r in range(4)], format="csr"), want[1])
+
+
+def test_fetch_rows_and_more_ranks_than_rows():
+    """a rank may own no rows at all (5 rows over 8 ranks) and may need rows from several owners"""
+    rng = np.random.default_rng(1)
+    M = F.canonical_csr(sp.random(5, 9, density=0.6, random_state=3, format="csr"))
+    offs = PT.block_offsets(5, 8)
+
+    def body(fab):
+        r = fab.rank
+        wanted = np.unique(rng.integers(0, 5, size=4)) if r % 2 == 0 else np.zeros(0, dtype=np.int64)
+        wanted = np.array([0, 2, 4]) if r == 3 else wanted
+        got = PS.fetch_rows(fab, offs, M[offs[r]:offs[r + 1]], wanted)
+        return wanted, got
+    for wanted, got in run_ranks(8, body):
+        same(got, M[wanted])
+
+
+def test_only_a_few_grid_lines_are_fetched():
+    """the exchange is a halo, not a gather: on a 65^2 grid cut into 4 strips a rank fetches rows of at most two grid
+    lines of A and four of Q per neighbour"""
+    N = 64
+    A = F.canonical_csr(P.structured_laplacian_2d(N))
+    Q = F.canonical_csr(P.linear_P_2d(N))
+    world = 4
+    offs_f, offs_c = PT.block_offsets(A.shape[0], world), PT.block_offsets(Q.shape[1], world)
+    W = N + 1
+    for r in range(world):
+        QT_blk = sp.csr_matrix(Q.T)[offs_c[r]:offs_c[r + 1]]
+        F1 = np.unique(QT_blk.indices)
+        F2 = np.unique(A[F1].indices)
+        for Fset, lines in ((F1, 2), (F2, 4)):
+            remote = Fset[(Fset < offs_f[r]) | (Fset >= offs_f[r + 1])]
+            assert len(remote) <= 2 * lines * W
+
+
+WORKER = r"""
+import os, sys
+import numpy as np, scipy.sparse as sp, torch.distributed as dist
+sys.path.insert(0, {root!r})
+from learnmultigrid_b200 import formats as F, partition as PT, partition_setup as PS, problems as P
+from learnmultigrid_b200.distributed import TorchFabric
+dist.init_process_group("gloo")
+fab = TorchFabric()
+A = F.canonical_csr(P.structured_laplacian_2d(16, P.variable_coefficient))
+Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(16, 3, "quasi")]
+ns = [A.shape[0]] + [q.shape[1] for q in Qs]
+offs = [PT.block_offsets(n, fab.world) for n in ns]
+r = fab.rank
+A_blks, QT_blks = PS.build_strip_hierarchy(fab, A[offs[0][r]:offs[0][r + 1]],
+                                           [q[offs[l][r]:offs[l][r + 1]] for l, q in enumerate(Qs)], offs)
+cur = sp.csc_matrix(A)
+ok = True
+for l, q in enumerate(Qs):
+    cur = sp.csr_matrix(q.T @ cur @ q); cur.sort_indices()
+    want = F.canonical_csr(cur)[offs[l + 1][r]:offs[l + 1][r + 1]]
+    got = sp.csr_matrix(A_blks[l + 1]); got.sort_indices()
+    ok = ok and np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices) \
+        and np.array_equal(got.data, want.data)
+print("RANK", r, "OK" if ok else "MISMATCH", flush=True)
+dist.destroy_process_group()
+"""
+
+
+def test_two_process_gloo_strip_setup(tmp_path):
+    import socket
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    with socket.socket() as sock:                  # a free port: back-to-back runs must not collide in TIME_WAIT
+        sock.bind(("127.0.0.1", 0))
+        port = str(sock.getsockname()[1])
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT=port, CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", port, str(script)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "RANK 0 OK" in out.stdout and "RANK 1 OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_row_block_generators_equal_slices_of_the_global_operators():
+    for N in (8, 16):
+        for coef in (None, P.variable_coefficient):
+            A = P.structured_laplacian_2d(N, coef)
+            n = A.shape[0]
+            for r0, r1 in ((0, n), (0, 0), (5, 40), (n - 17, n), (N + 1, 3 * (N + 1))):
+                same(P.structured_laplacian_2d(N, coef, rows=(r0, r1)), A[r0:r1])
+        Pm = P.linear_P_2d(N)
+        for r0, r1 in ((0, Pm.shape[0]), (3, 50), (Pm.shape[0] - 9, Pm.shape[0])):
+            same(P.linear_P_2d(N, rows=(r0, r1)), Pm[r0:r1])
+
+
+def test_hierarchy_from_generated_strips_without_any_global_matrix():
+    """every rank generates ITS rows of A_0 and of every P_l, nothing else: the assembled hierarchy equals the global
+    one (the precondition for problems larger than one GPU's memory)"""
+    N, levels, world = 32, 4, 4
+    ns = [(N >> l) + 1 for l in range(levels)]
+    offs = [PT.block_offsets(w * w, world) for w in ns]
+
+    def body(fab):
+        r = fab.rank
+        A_blk = P.structured_laplacian_2d(N, P.variable_coefficient, rows=(offs[0][r], offs[0][r + 1]))
+        Q_blks = [P.linear_P_2d(N >> l, rows=(offs[l][r], offs[l][r + 1])) for l in range(levels - 1)]
+        return PS.build_strip_hierarchy(fab, A_blk, Q_blks, offs)
+    res = run_ranks(world, body)
+    want = global_hierarchy(P.structured_laplacian_2d(N, P.variable_coefficient),
+                            P.structured_hierarchy_2d(N, levels, "linear"))
+    for l in range(levels):
+        same(sp.vstack([res[r][0][l] for r in range(world)], format="csr"), want[l])
