@@ -22,6 +22,9 @@ class RankPlan:
     """halo plan of one rank on one level"""
 
     def __init__(self, offsets, rank, ext_cols, colors=None):
+        """colors: None, the GLOBAL colour array of the level, or -- for a setup in which no rank holds global data
+        (partition_setup.py) -- a tuple (colours of the owned rows, colours of the sorted unique external columns,
+        number of colours of the level)."""
         self.offsets = np.asarray(offsets, dtype=np.int64)
         self.rank = int(rank)
         self.o0, self.o1 = int(self.offsets[rank]), int(self.offsets[rank + 1])
@@ -30,14 +33,26 @@ class RankPlan:
         if len(ext) and (np.any((ext >= self.o0) & (ext < self.o1))):
             raise ValueError("external column set contains owned columns")
         owner = owner_of(self.offsets, ext) if len(ext) else np.zeros(0, dtype=np.int64)
-        if colors is not None:
-            colors = np.asarray(colors)
-            own_col = colors[self.o0:self.o1]
-            self.ncolors = int(colors.max()) + 1 if len(colors) else 0
+        if isinstance(colors, tuple):
+            own_col, hcol_in, ncolors = colors
+            own_col, hcol_in = np.asarray(own_col), np.asarray(hcol_in)
+            if len(own_col) != self.n_own or len(hcol_in) != len(ext):
+                raise ValueError("local colour arrays do not match the row block / the external column set")
+            colors = None
+            local_colors = True
+        else:
+            local_colors = False
+        if local_colors or colors is not None:
+            if not local_colors:
+                colors = np.asarray(colors)
+                own_col = colors[self.o0:self.o1]
+                ncolors = int(colors.max()) + 1 if len(colors) else 0
+                hcol_in = colors[ext] if len(ext) else np.zeros(0, dtype=np.int64)
+            self.ncolors = int(ncolors)
             self.perm = np.argsort(own_col, kind="stable").astype(np.int32)          # new -> old (block-local)
             self.color_ptr = np.zeros(self.ncolors + 1, dtype=np.int64)
             np.cumsum(np.bincount(own_col, minlength=self.ncolors), out=self.color_ptr[1:])
-            hcol = colors[ext] if len(ext) else np.zeros(0, dtype=np.int64)
+            hcol = np.asarray(hcol_in, dtype=np.int64) if len(ext) else np.zeros(0, dtype=np.int64)
         else:
             self.ncolors = 0
             self.perm = None

@@ -88,6 +88,45 @@ def fetch_rows(fabric, offsets, block, wanted):
     return out
 
 
+def fetch_values(fabric, offsets, own_values, wanted):
+    """entries `wanted` (sorted unique global ids) of a vector whose block [offsets[r], offsets[r+1]) lives on rank r
+    (colours of the halo nodes, for instance).  Collective."""
+    rank, world = fabric.rank, fabric.world
+    wanted = np.asarray(wanted, dtype=np.int64)
+    own_values = np.asarray(own_values)
+    o0 = int(offsets[rank])
+    owner = PT.owner_of(offsets, wanted) if len(wanted) else np.zeros(0, dtype=np.int64)
+    everyone = fabric.allgather({int(q): wanted[owner == q] for q in np.unique(owner) if int(q) != rank})
+    answers = fabric.allgather({p: own_values[np.asarray(everyone[p][rank], dtype=np.int64) - o0]
+                                for p in range(world) if p != rank and rank in everyone[p]})
+    out = np.empty(len(wanted), dtype=own_values.dtype)
+    for q in np.unique(owner):
+        sel = owner == q
+        out[sel] = own_values[wanted[sel] - o0] if int(q) == rank else answers[int(q)][rank]
+    return out
+
+
+def rank_plan_from_blocks(fabric, offs, offs_next, offs_prev, A_blk, QT_blk, Q_prev_blk, own_colors, ncolors):
+    """partition.RankPlan of this rank on one level from its own row blocks only: the external columns of its rows of
+    A_l, of Q_l^T (coarse rows it owns) and of Q_{l-1} (finer rows it owns), and the colours of those halo nodes fetched
+    from their owners.  own_colors None = no colouring (Jacobi).  Collective."""
+    rank = fabric.rank
+    o0, o1 = int(offs[rank]), int(offs[rank + 1])
+    parts = []
+    for blk in (A_blk, QT_blk, Q_prev_blk):
+        if blk is None:
+            continue
+        cols = np.asarray(_canon(blk).indices, dtype=np.int64)
+        parts.append(np.unique(cols[(cols < o0) | (cols >= o1)]))
+    ext = np.unique(np.concatenate(parts)) if parts else np.zeros(0, dtype=np.int64)
+    if own_colors is None:
+        fabric.allgather(None)                       # keep the collective sequence identical on every rank
+        fabric.allgather(None)
+        return PT.RankPlan(offs, rank, ext, None)
+    ext_colors = fetch_values(fabric, offs, np.asarray(own_colors), ext)
+    return PT.RankPlan(offs, rank, ext, (np.asarray(own_colors), ext_colors, int(ncolors)))
+
+
 def _compress_columns(M, keep):
     """columns `keep` (sorted unique) of M renumbered 0..len(keep)-1; all of M's columns must be in `keep`"""
     M = _canon(M)

@@ -215,3 +215,36 @@ def test_hierarchy_from_generated_strips_without_any_global_matrix():
                             P.structured_hierarchy_2d(N, levels, "linear"))
     for l in range(levels):
         same(sp.vstack([res[r][0][l] for r in range(world)], format="csr"), want[l])
+
+
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_halo_plans_from_local_blocks_equal_the_plans_from_global_data(world):
+    """partition.RankPlan built from a rank's own row blocks + fetched halo colours = the plan built from the global
+    matrices and the global colour array (what DistributedHierarchy uses today), attribute by attribute"""
+    N = 16
+    A, Qs = P.structured_laplacian_2d(N), P.structured_hierarchy_2d(N, 3, "quasi")
+    As = global_hierarchy(A, Qs)
+    Qs = [F.canonical_csr(q) for q in Qs]
+    QTs = [F.canonical_csr(sp.csr_matrix(q.T)) for q in Qs]
+    l = 1                                                                  # a level with a finer and a coarser one
+    colors, nc = F.greedy_colors(As[l])
+    offs = [PT.block_offsets(a.shape[0], world) for a in As]
+
+    def body(fab):
+        r = fab.rank
+        A_blk = As[l][offs[l][r]:offs[l][r + 1]]
+        QT_blk = QTs[l][offs[l + 1][r]:offs[l + 1][r + 1]]
+        Qp_blk = Qs[l - 1][offs[l - 1][r]:offs[l - 1][r + 1]]
+        plan = PS.rank_plan_from_blocks(fab, offs[l], offs[l + 1], offs[l - 1], A_blk, QT_blk, Qp_blk,
+                                        colors[offs[l][r]:offs[l][r + 1]], nc)
+        jac = PS.rank_plan_from_blocks(fab, offs[l], offs[l + 1], offs[l - 1], A_blk, QT_blk, Qp_blk, None, 0)
+        return plan, jac
+    for r, (got, jac) in enumerate(run_ranks(world, body)):
+        ext = PT.level_external_columns(As[l], QTs[l], Qs[l - 1], offs[l], offs[l + 1], offs[l - 1], r)
+        want = PT.RankPlan(offs[l], r, ext, colors)
+        for name in ("halo_gid", "halo_owner", "halo_color", "perm", "iperm", "color_ptr"):
+            assert np.array_equal(getattr(got, name), getattr(want, name)), name
+        assert (got.n_own, got.n_halo, got.ncolors, got.neighbours, got.seg, got.seg_color) == \
+            (want.n_own, want.n_halo, want.ncolors, want.neighbours, want.seg, want.seg_color)
+        wj = PT.RankPlan(offs[l], r, ext, None)
+        assert np.array_equal(jac.halo_gid, wj.halo_gid) and jac.seg == wj.seg and jac.perm is None
