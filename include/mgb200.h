@@ -417,6 +417,16 @@ int mg_host_nn_contributions(int64_t np_, const int32_t *h_fill, const double *h
  * The colour order defines the multicolour Gauss-Seidel that replaces PyAMG's index-order sweep
  * (Multigrid.py:88,121); the same colours are handed to the CPU oracle. */
 int mg_host_greedy_color(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_colors);
+/* The same colouring on a ROW BLOCK, one phase per call, for a setup in which no process holds the global pattern
+ * (learnmultigrid_b200/partition_setup.py drives the blocks in rank order and gets the colours of the call above).
+ * Columns are block-local: own rows 0..n_own-1, external node k at n_own + k with colour h_ext_color[k] (-1 = not
+ * coloured yet).  h_forbidden_lo / _hi: n_own + n_ext words each, bit c = colour c (lo) / 64 + c (hi) is taken by a
+ * coloured row that reaches the node through its own row only; in for the own rows, out for the external nodes.
+ * phase 0: rows with off-diagonal entries (h_colors is reset to -1 first); phase 1: the remaining rows.
+ * Returns the largest colour used in the block + 1 (0 if none) or a negative status. */
+int mg_host_greedy_color_block(int64_t n_own, int64_t n_ext, const int32_t *h_indptr, const int32_t *h_indices,
+                               const int32_t *h_ext_color, uint64_t *h_forbidden_lo, uint64_t *h_forbidden_hi,
+                               int32_t *h_colors, int phase);
 /* dependency level of every row for an exact index-order sweep (see mg_gs_lex_sweep_csr); returns nlevels */
 int64_t mg_host_lex_levels(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_level);
 

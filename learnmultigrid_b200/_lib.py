@@ -190,6 +190,7 @@ _SIGNATURES = {
     "mg_host_nn_extract_patches": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_host_nn_contributions": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp]),
     "mg_host_greedy_color": (c_int, [c_i64, c_vp, c_vp, c_vp]),
+    "mg_host_greedy_color_block": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
     "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
     "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),
     "mg_vcycle_dist": (c_int, [ctypes.POINTER(mg_comm), ctypes.POINTER(mg_level), c_int,

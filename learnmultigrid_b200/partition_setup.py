@@ -106,6 +106,68 @@ def fetch_values(fabric, offsets, own_values, wanted):
     return out
 
 
+def greedy_colors_distributed(fabric, offsets, A_blk):
+    """The first-fit colouring of formats.greedy_colors (index order on the symmetrised pattern, rows with only a
+    diagonal entry last) of a row-partitioned matrix: returns (colours of the own rows, number of colours of the whole
+    matrix), identical to the single-process result.  The colouring is sequential by nature, so the blocks are coloured
+    in rank order (world rounds, one all-gather each): a rank receives the colours of the lower ranks' rows it refers to
+    and the colours those ranks' rows forbid for its own rows, colours its rows with off-diagonal entries, and publishes
+    the same for the others; the rows with only a diagonal entry are coloured locally at the end.  Collective."""
+    import ctypes
+    from . import _lib
+    lib = _lib.load()
+    rank, world = fabric.rank, fabric.world
+    A_blk = _canon(A_blk)
+    o0, o1 = int(offsets[rank]), int(offsets[rank + 1])
+    n_own = o1 - o0
+    cols = np.asarray(A_blk.indices, dtype=np.int64)
+    ext = np.unique(cols[(cols < o0) | (cols >= o1)])
+    n_ext = len(ext)
+    local = np.where((cols >= o0) & (cols < o1), cols - o0, n_own + np.searchsorted(ext, cols)).astype(np.int32)
+    indptr = np.ascontiguousarray(A_blk.indptr, dtype=np.int32)
+    ext_color = -np.ones(max(n_ext, 1), dtype=np.int32)
+    lo = np.zeros(n_own + n_ext + 1, dtype=np.uint64)
+    hi = np.zeros(n_own + n_ext + 1, dtype=np.uint64)
+    colors = -np.ones(max(n_own, 1), dtype=np.int32)
+    ext_owner = PT.owner_of(offsets, ext) if n_ext else np.zeros(0, dtype=np.int64)
+    wanted_by = fabric.allgather(ext)                          # wanted_by[p] = global ids rank p refers to
+
+    def vp(a):
+        return a.ctypes.data_as(ctypes.c_void_p)
+
+    def run(phase):
+        rc = lib.mg_host_greedy_color_block(n_own, n_ext, vp(indptr), vp(local), vp(ext_color), vp(lo), vp(hi),
+                                            vp(colors), phase)
+        if rc < 0:
+            _lib.check(rc, "mg_host_greedy_color_block")
+
+    for turn in range(world):
+        payload = None
+        if turn == rank:
+            run(0)
+            # for every other rank: the colours of my rows it refers to, and what my rows forbid for its rows
+            payload = {}
+            for p in range(world):
+                if p == rank:
+                    continue
+                ids = wanted_by[p]
+                mine = ids[(ids >= o0) & (ids < o1)]
+                sel = np.flatnonzero(ext_owner == p)
+                push = sel[(lo[n_own + sel] != 0) | (hi[n_own + sel] != 0)]
+                payload[p] = (mine, colors[mine - o0].copy(), ext[push], lo[n_own + push].copy(), hi[n_own + push].copy())
+        got = fabric.allgather(payload)[turn]
+        if turn != rank and got is not None and rank in got:
+            ids, cs, pushed, plo, phi = got[rank]
+            if len(ids):
+                ext_color[np.searchsorted(ext, ids)] = cs          # -1 for rows the owner colours in its last phase
+            if len(pushed):
+                lo[pushed - o0] |= plo
+                hi[pushed - o0] |= phi
+    run(1)
+    ncolors = max(fabric.allgather(int(colors[:n_own].max()) + 1 if n_own else 0))
+    return colors[:n_own].copy(), int(ncolors)
+
+
 def rank_plan_from_blocks(fabric, offs, offs_next, offs_prev, A_blk, QT_blk, Q_prev_blk, own_colors, ncolors):
     """partition.RankPlan of this rank on one level from its own row blocks only: the external columns of its rows of
     A_l, of Q_l^T (coarse rows it owns) and of Q_{l-1} (finer rows it owns), and the colours of those halo nodes fetched

@@ -248,3 +248,23 @@ def test_halo_plans_from_local_blocks_equal_the_plans_from_global_data(world):
             (want.n_own, want.n_halo, want.ncolors, want.neighbours, want.seg, want.seg_color)
         wj = PT.RankPlan(offs[l], r, ext, None)
         assert np.array_equal(jac.halo_gid, wj.halo_gid) and jac.seg == wj.seg and jac.perm is None
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_distributed_first_fit_colouring_equals_the_global_one(world):
+    """blocks coloured in rank order with the forbidden-colour masks passed along: the colours of
+    formats.greedy_colors, for symmetric and unsymmetric patterns, with Dirichlet (diagonal-only) rows, with 19- and
+    37-point stencils, and on a random sparse matrix whose couplings cross several blocks"""
+    N = 16
+    A = P.structured_laplacian_2d(N)
+    Qs = P.structured_hierarchy_2d(N, 3, "quasi")
+    mats = global_hierarchy(A, Qs)                                     # 5-point + identity rows, 19- and 37-point
+    R = sp.random(120, 120, density=0.08, random_state=5, format="csr") + sp.diags((np.arange(120) % 3 > 0) * 1.0)
+    mats.append(F.canonical_csr(R))                                    # unsymmetric, long-range, some empty diagonals
+    for M in mats:
+        want, nc = F.greedy_colors(M)
+        offs = PT.block_offsets(M.shape[0], world)
+        res = run_ranks(world, lambda fab: PS.greedy_colors_distributed(fab, offs, M[offs[fab.rank]:offs[fab.rank + 1]]))
+        got = np.concatenate([r[0] for r in res])
+        assert np.array_equal(got, want)
+        assert all(r[1] == nc for r in res)
