@@ -260,3 +260,66 @@ def build_strip_hierarchy(fabric, A_blk, Q_blks, offsets, ops=ScipyOps):
         QT_blks.append(QT)
         A_blks.append(galerkin_row_block(fabric, offsets[l], offsets[l + 1], A_blks[l], Q_blk, QT, ops))
     return A_blks, QT_blks
+
+
+def gather_row_blocks(fabric, block, n_cols=None):
+    """The row blocks of all ranks stacked in rank order = the global matrix, on every rank (the first replicated
+    level of a partitioned hierarchy and the transfer operators below it are small: DistributedHierarchy keeps them in
+    full on every GPU).  Collective."""
+    block = _canon(block)
+    parts = fabric.allgather((block.indptr.astype(np.int64), block.indices.astype(np.int64),
+                              block.data.astype(np.float64), block.shape))
+    n_cols = block.shape[1] if n_cols is None else int(n_cols)
+    mats = [sp.csr_matrix((va, ix, ip), shape=(shape[0], n_cols)) for ip, ix, va, shape in parts]
+    out = sp.vstack(mats, format="csr")
+    out.sort_indices()
+    return out
+
+
+class StripLevel:
+    """what one rank holds of a partitioned level after strip_local_setup: its rows of A_l and Q_l (fine rows it owns),
+    its rows of Q_l^T (coarse rows it owns) -- global column ids --, the colours of its rows and its halo plan"""
+
+    def __init__(self, A, Q, QT, colors, ncolors, plan):
+        self.A, self.Q, self.QT, self.colors, self.ncolors, self.plan = A, Q, QT, colors, ncolors, plan
+
+
+def strip_local_setup(fabric, A_blk, Q_blks, offsets, n_dist, smoother="mcgs", colors=None, ops=ScipyOps):
+    """The whole host side of a partitioned hierarchy setup from this rank's row blocks only.
+
+    A_blk    : rows [offsets[0][rank], offsets[0][rank+1]) of A_0 (global column ids)
+    Q_blks   : rows [offsets[l][rank], offsets[l][rank+1]) of every Q_l
+    offsets  : block offsets per level (partition.block_offsets), len = number of levels
+    n_dist   : levels 0..n_dist-1 stay partitioned, level n_dist and below are replicated
+    colors   : optional per-level colours of the OWN rows (e.g. a structured colouring evaluated on the own rows);
+               default for "mcgs": the first-fit colouring, coloured block by block in rank order
+    Returns (levels, A_rep, Q_rep): `levels[l]` a StripLevel for l < n_dist; `A_rep` = A_{n_dist} in full and `Q_rep` =
+    [Q_l in full for l >= n_dist], gathered once -- the inputs of the replicated tail, whose remaining Galerkin
+    products are small and formed redundantly on every rank as before.  Everything equals what DistributedHierarchy
+    derives from the global operators today (tests/test_partition_setup.py).  Collective."""
+    L = len(Q_blks) + 1
+    if len(offsets) != L:
+        raise ValueError("one offsets array per level expected")
+    if not 1 <= n_dist <= L - 1:
+        raise ValueError("n_dist must be between 1 and levels-1")
+    if smoother not in ("jacobi", "mcgs"):
+        raise ValueError("partitioned levels support 'jacobi' and 'mcgs'")
+    Q_blks = [_canon(Q) for Q in Q_blks]
+    A_blks, QT_blks = build_strip_hierarchy(fabric, A_blk, Q_blks[:n_dist], offsets, ops)
+    levels = []
+    for l in range(n_dist):
+        own_col, nc = None, 0
+        if smoother == "mcgs":
+            if colors is not None and colors[l] is not None:
+                own_col = np.ascontiguousarray(colors[l], dtype=np.int32)
+                if len(own_col) != A_blks[l].shape[0]:
+                    raise ValueError("level %d: one colour per own row expected" % l)
+                nc = max(fabric.allgather(int(own_col.max()) + 1 if len(own_col) else 0))
+            else:
+                own_col, nc = greedy_colors_distributed(fabric, offsets[l], A_blks[l])
+        plan = rank_plan_from_blocks(fabric, offsets[l], offsets[l + 1], offsets[l - 1] if l else None, A_blks[l],
+                                     QT_blks[l], Q_blks[l - 1] if l else None, own_col, nc)
+        levels.append(StripLevel(A_blks[l], Q_blks[l], QT_blks[l], own_col, nc, plan))
+    A_rep = gather_row_blocks(fabric, A_blks[n_dist], int(offsets[n_dist][-1]))
+    Q_rep = [gather_row_blocks(fabric, Q_blks[l], int(offsets[l + 1][-1])) for l in range(n_dist, L - 1)]
+    return levels, A_rep, Q_rep

@@ -166,6 +166,14 @@ for l, q in enumerate(Qs):
     got = sp.csr_matrix(A_blks[l + 1]); got.sort_indices()
     ok = ok and np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices) \
         and np.array_equal(got.data, want.data)
+# the composed setup (blocks, first-fit colours coloured in rank order, halo plan, gathered replicated level)
+levs, A_rep, Q_rep = PS.strip_local_setup(fab, A[offs[0][r]:offs[0][r + 1]],
+                                          [q[offs[l][r]:offs[l][r + 1]] for l, q in enumerate(Qs)], offs, 1, "mcgs")
+col, nc = F.greedy_colors(A)
+A1 = sp.csr_matrix(Qs[0].T @ sp.csc_matrix(A) @ Qs[0]); A1.sort_indices()
+ok = ok and np.array_equal(levs[0].colors, col[offs[0][r]:offs[0][r + 1]]) and levs[0].ncolors == nc \
+    and np.array_equal(A_rep.indices, A1.indices) and np.array_equal(A_rep.data, A1.data) \
+    and (Q_rep[0] != Qs[1]).nnz == 0
 print("RANK", r, "OK" if ok else "MISMATCH", flush=True)
 dist.destroy_process_group()
 """
@@ -268,3 +276,65 @@ def test_distributed_first_fit_colouring_equals_the_global_one(world):
         got = np.concatenate([r[0] for r in res])
         assert np.array_equal(got, want)
         assert all(r[1] == nc for r in res)
+
+
+@pytest.mark.parametrize("smoother", ["mcgs", "jacobi"])
+@pytest.mark.parametrize("world", [2, 4])
+def test_whole_strip_local_setup_equals_what_the_replicated_setup_derives(world, smoother):
+    """strip_local_setup (row blocks in, nothing global held): per partitioned level the operator blocks, first-fit
+    colours and halo plans of the replicated setup; below, the gathered first replicated operator and transfers"""
+    N, levels, n_dist = 32, 5, 3
+    A = P.structured_laplacian_2d(N, P.variable_coefficient)
+    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, "linear")]
+    As = global_hierarchy(A, Qs)
+    QTs = [F.canonical_csr(sp.csr_matrix(q.T)) for q in Qs]
+    offs = [PT.block_offsets(a.shape[0], world) for a in As]
+
+    def body(fab):
+        r = fab.rank
+        A_blk = P.structured_laplacian_2d(N, P.variable_coefficient, rows=(offs[0][r], offs[0][r + 1]))
+        Q_blks = [P.linear_P_2d(N >> l, rows=(offs[l][r], offs[l][r + 1])) for l in range(levels - 1)]
+        return PS.strip_local_setup(fab, A_blk, Q_blks, offs, n_dist, smoother)
+    res = run_ranks(world, body)
+    for r, (levs, A_rep, Q_rep) in enumerate(res):
+        assert len(levs) == n_dist and len(Q_rep) == levels - 1 - n_dist
+        same(A_rep, As[n_dist])
+        for k, Q in enumerate(Q_rep):
+            same(Q, Qs[n_dist + k])
+        for l, lv in enumerate(levs):
+            same(lv.A, As[l][offs[l][r]:offs[l][r + 1]])
+            same(lv.Q, Qs[l][offs[l][r]:offs[l][r + 1]])
+            same(lv.QT, QTs[l][offs[l + 1][r]:offs[l + 1][r + 1]])
+            colors = F.greedy_colors(As[l])[0] if smoother == "mcgs" else None
+            ext = PT.level_external_columns(As[l], QTs[l], Qs[l - 1] if l else None, offs[l], offs[l + 1],
+                                            offs[l - 1] if l else None, r)
+            want = PT.RankPlan(offs[l], r, ext, colors)
+            for name in ("halo_gid", "halo_owner", "halo_color", "perm", "iperm", "color_ptr"):
+                a, b = getattr(lv.plan, name, None), getattr(want, name, None)
+                assert (a is None and b is None) or np.array_equal(a, b), (l, name)
+            assert (lv.plan.n_own, lv.plan.n_halo, lv.plan.ncolors, lv.plan.seg, lv.plan.seg_color) == \
+                (want.n_own, want.n_halo, want.ncolors, want.seg, want.seg_color)
+            if smoother == "mcgs":
+                assert np.array_equal(lv.colors, colors[offs[l][r]:offs[l][r + 1]])
+
+
+def test_strip_local_setup_with_row_local_structured_colours():
+    """colours given per own row (a structured colouring needs no exchange at all)"""
+    N, levels, world = 16, 3, 2
+    A = P.structured_laplacian_2d(N)
+    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, "linear")]
+    As = global_hierarchy(A, Qs)
+    offs = [PT.block_offsets(a.shape[0], world) for a in As]
+    full = [F.greedy_colors(a)[0] for a in As[:-1]]
+
+    def body(fab):
+        r = fab.rank
+        own = [full[l][offs[l][r]:offs[l][r + 1]] for l in range(levels - 1)]
+        return PS.strip_local_setup(fab, A[offs[0][r]:offs[0][r + 1]],
+                                    [q[offs[l][r]:offs[l][r + 1]] for l, q in enumerate(Qs)], offs, 1, "mcgs", own)
+    for r, (levs, A_rep, Q_rep) in enumerate(run_ranks(world, body)):
+        ext = PT.level_external_columns(As[0], F.canonical_csr(sp.csr_matrix(Qs[0].T)), None, offs[0], offs[1], None, r)
+        want = PT.RankPlan(offs[0], r, ext, full[0])
+        assert np.array_equal(levs[0].plan.perm, want.perm) and levs[0].plan.seg_color == want.seg_color
+        same(A_rep, As[1])
+        same(Q_rep[0], Qs[1])
