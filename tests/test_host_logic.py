@@ -223,3 +223,49 @@ def test_lattice_colorings_are_valid_and_smaller_than_greedy(transfer, expect):
             assert counts == expect
         else:
             assert counts[0] == 2 and counts[1] <= 8 and counts[2] <= 14     # 19- and 37-point stencils
+
+
+def _first_fit_python(A):
+    """the definition: symmetrised pattern, rows with off-diagonal entries in index order, then the rows with nothing
+    but a diagonal entry; each takes the smallest colour no coloured neighbour has"""
+    A = F.canonical_csr(A)
+    n = A.shape[0]
+    S = sp.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape)
+    S = sp.csr_matrix(S + S.T)
+    off = np.array([np.any(A.indices[A.indptr[i]:A.indptr[i + 1]] != i) for i in range(n)], dtype=bool)
+    colors = -np.ones(n, dtype=np.int64)
+    for i in list(np.flatnonzero(off)) + list(np.flatnonzero(~off)):
+        nb = S.indices[S.indptr[i]:S.indptr[i + 1]]
+        used = set(colors[nb[nb != i]].tolist())
+        c = 0
+        while c in used:
+            c += 1
+        colors[i] = c
+    return colors
+
+
+def test_greedy_coloring_equals_the_python_definition_including_more_than_64_colours():
+    rng = np.random.default_rng(11)
+    mats = [poisson2d(9), sp.random(150, 150, density=0.05, random_state=2, format="csr") + sp.eye(150)]
+    C = sp.lil_matrix((100, 100))
+    C[:70, :70] = 1.0                               # a 70-clique: colours 0..69 cross the 64-bit mask boundary
+    C[70:, 3] = 1.0                                 # one-directional couplings into the clique
+    C.setdiag(1.0)
+    C[95, :] = 0.0
+    C[95, 95] = 1.0                                 # a diagonal-only row that others do not reference
+    mats.append(C.tocsr())
+    mats.append(sp.csr_matrix(rng.random((40, 40)) < 0.5) * 1.0 + sp.eye(40))
+    for M in mats:
+        M = F.canonical_csr(M)
+        got, nc = F.greedy_colors(M)
+        want = _first_fit_python(M)
+        assert np.array_equal(got, want)
+        assert nc == want.max() + 1
+    assert F.greedy_colors(mats[2])[1] >= 70
+
+
+def test_greedy_coloring_refuses_more_than_128_colours():
+    from learnmultigrid_b200 import _lib
+    full = F.canonical_csr(sp.csr_matrix(np.ones((130, 130))))
+    with pytest.raises(_lib.MgError):
+        F.greedy_colors(full)

@@ -269,6 +269,11 @@ def test_distributed_first_fit_colouring_equals_the_global_one(world):
     mats = global_hierarchy(A, Qs)                                     # 5-point + identity rows, 19- and 37-point
     R = sp.random(120, 120, density=0.08, random_state=5, format="csr") + sp.diags((np.arange(120) % 3 > 0) * 1.0)
     mats.append(F.canonical_csr(R))                                    # unsymmetric, long-range, some empty diagonals
+    C = sp.lil_matrix((100, 100))
+    C[:70, :70] = 1.0                                                  # a 70-clique across the blocks: > 64 colours
+    C[70:, 3] = 1.0
+    C.setdiag(1.0)
+    mats.append(F.canonical_csr(C.tocsr()))
     for M in mats:
         want, nc = F.greedy_colors(M)
         offs = PT.block_offsets(M.shape[0], world)
