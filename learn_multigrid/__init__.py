@@ -10,7 +10,7 @@ _SUBMODULES = [
     "assembly", "assembly.MassMatrix", "assembly.StiffnessMatrix", "assembly.LoadVector", "assembly.LoadFunction",
     "assembly.Quadrature", "assembly.ShapeFunction", "assembly.MapReferenceElement",
     "mesh", "mesh.Mesh1D", "mesh.Mesh2D", "mesh.Element1D",
-    "utilities", "utilities.laplacian",
+    "utilities", "utilities.laplacian", "utilities.plots",
 ]
 
 for _name in _SUBMODULES:

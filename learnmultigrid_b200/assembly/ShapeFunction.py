@@ -29,24 +29,40 @@ class ShapeFunction(ABC):
 class Function(ShapeFunction):
     def __init__(self, order):
         super().__init__(order)
-        self.phi = {2: np.array([lambda x: 1 - x, lambda x: x])}.get(order, "Invalid order")
+        self.phi = self.order_to_function(order)
+
+    @staticmethod
+    def order_to_function(order):
+        return {2: np.array([lambda x: 1 - x, lambda x: x])}.get(order, "Invalid order")
 
 
 class Gradient(ShapeFunction):
     def __init__(self, order):
         super().__init__(order)
-        self.phi = {2: np.array([lambda x: -1, lambda x: 1])}.get(order, "Invalid order")
+        self.phi = self.order_to_gradient(order)
+
+    @staticmethod
+    def order_to_gradient(order):
+        return {2: np.array([lambda x: -1, lambda x: 1])}.get(order, "Invalid order")
 
 
 class FunctionTriangle(ShapeFunction):
     def __init__(self, order):
         super().__init__(order)
-        self.phi = {1: np.array([lambda p: 1 - p[0] - p[1], lambda p: p[0], lambda p: p[1]])}.get(order, "Invalid order")
+        self.phi = self.order_to_function(order)
+
+    @staticmethod
+    def order_to_function(order):
+        return {1: np.array([lambda p: 1 - p[0] - p[1], lambda p: p[0], lambda p: p[1]])}.get(order, "Invalid order")
 
 
 class GradientTriangle(ShapeFunction):
     def __init__(self, order):
         super().__init__(order)
-        self.phi = {1: np.array([lambda p: np.array([np.array([-1, -1])]).T,
-                                 lambda p: np.array([np.array([1, 0])]).T,
-                                 lambda p: np.array([np.array([0, 1])]).T])}.get(order, "Invalid order")
+        self.phi = self.order_to_gradient(order)
+
+    @staticmethod
+    def order_to_gradient(order):
+        return {1: np.array([lambda p: np.array([np.array([-1, -1])]).T,
+                             lambda p: np.array([np.array([1, 0])]).T,
+                             lambda p: np.array([np.array([0, 1])]).T])}.get(order, "Invalid order")

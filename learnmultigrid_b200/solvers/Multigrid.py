@@ -344,6 +344,16 @@ class NeuralMG(Multigrid):
             self.define_hierarchy(levels)
         super().solve(levels, smoother, smooth_steps, max_iterations, error, initial_guess, cycle, True, **kw)
 
+    def v_cycle(self, A, M, u0, rhs, smoother, smooth_steps, error, levels, first_call=False, **kw):
+        """One V-cycle with the reference's argument list (Multigrid.py:246: the level's mass matrix M comes second).
+        The transfer operators are predicted from M for all levels at once (define_hierarchy) and kept while the same
+        M object and level count are passed; the cycle itself is Multigrid.v_cycle on the device."""
+        if M is not self.M or len(self.l_hierarchy) != levels - 1:
+            self.M = M
+            self.define_hierarchy(levels)
+            self._hier = None
+        return super().v_cycle(A, u0, rhs, smoother, smooth_steps, error, levels, True, **kw)
+
     def _given_transfers(self):
         return self.l_hierarchy
 
@@ -388,6 +398,32 @@ class NeuralMG_2D(Multigrid):
     @staticmethod
     def map_coarse(_C):
         return dict(zip(_C, range(len(_C))))
+
+    @staticmethod
+    def get_conn(mat):
+        """dense 0/1 adjacency of the positive off-diagonal entries (Multigrid.py:391-398); unlike the reference's
+        `mat[:]`, which is a view for some SciPy formats, the argument is left untouched"""
+        Mh = sp.csr_matrix(mat, copy=True)
+        Mh.setdiag(0)
+        Mh.eliminate_zeros()
+        out = Mh.toarray()
+        out[out > 0] = 1
+        return out
+
+    def create_virtual_nodes(self, row, node_M):
+        """(virtual_neighs, row) of Multigrid.py:438-454: a node with fewer than 6 neighbours gets 6 - k virtual ones
+        worth node_M / down each, and every virtual neighbour a patch row [node_M * up, 5 x node_M / down], with
+        (up, down) = scaling_vnodes(k).  The per-node steps that follow in the reference (direct_neighs,
+        intersecting_rows, single_extraction) are one CUDA thread per coarse node here (csrc/nn_kernels.cu, reached
+        through extract_patches)."""
+        row = np.asarray(row, dtype=np.float64)
+        k = len(row)
+        if k >= 6:
+            return [], row
+        up, down = self.scaling_vnodes(k)
+        row = np.concatenate([row, np.full(6 - k, node_M / down)])
+        virtual = np.tile(np.concatenate([[node_M * up], np.full(5, node_M / down)]), 6 - k)
+        return virtual, row
 
     def coarsening(self, _conn):
         """(CC, FF, CC_neighs, FF_neighs) as Multigrid.py:401-426; CC in selection (= ascending) order"""

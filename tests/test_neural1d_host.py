@@ -47,3 +47,44 @@ def test_features_and_transfer_operators_match_reference(name):
         M = want.T @ M @ want                                # the reference's own coarse mass for the next level
     mg.define_hierarchy(levels)
     assert [q.shape for q in mg.l_hierarchy] == [g["%s_Q%d" % (name, l)].shape for l in range(levels - 1)]
+
+
+def test_v_cycle_takes_the_reference_argument_list(monkeypatch):
+    """NeuralMG.v_cycle(A, M, u0, rhs, ...) (Multigrid.py:246): the mass matrix comes second; the transfer operators
+    handed to the engine are the ones predicted from THAT M.  The device part is replaced by a recorder here."""
+    from learnmultigrid_b200.solvers import Multigrid as MGmod
+    g = load_golden("neural_1d.npz")
+    mg = make(g, "reg64")
+    levels = int(g["reg64_par"][0])
+    seen = {}
+
+    class FakeHierarchy:
+        def make_params(self, **kw):
+            return kw
+
+        def set_rhs(self, b):
+            seen["rhs"] = b
+
+        def set_x(self, x):
+            seen["x"] = x
+
+        def vcycle(self, params):
+            seen["params"] = params
+
+        def get_x(self):
+            return seen["x"]
+
+    def fake_build(self, A, lv, smoother, gs_order, colors, first_call):
+        seen["Q"] = self._transfer_list(lv, first_call)
+        return FakeHierarchy()
+    monkeypatch.setattr(MGmod.Multigrid, "_build", fake_build)
+    A, M = g["reg64_A"], g["reg64_M"]
+    u0, rhs = np.zeros((A.shape[0], 1)), g["reg64_rhs"]
+    out = mg.v_cycle(A, M, u0, rhs, "GaussSeidel", 3, 1e-10, levels)
+    assert out is u0 and seen["params"]["nu_pre"] == 3 and seen["rhs"] is rhs
+    assert len(seen["Q"]) == levels - 1
+    for l, Q in enumerate(seen["Q"]):
+        np.testing.assert_allclose(Q.toarray(), g["reg64_Q%d" % l], rtol=1e-14, atol=0)
+    M2 = 2.0 * M                                            # another mass matrix: the operators are rebuilt from it
+    mg.v_cycle(A, M2, u0, rhs, "GaussSeidel", 1, 1e-10, levels)
+    assert mg.M is M2 and len(mg.l_hierarchy) == levels - 1

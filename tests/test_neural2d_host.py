@@ -189,3 +189,33 @@ def test_next_level_mass_matrix_is_the_galerkin_product(case):
             key = "%s__final_M_" % case
             fin = sp.csr_matrix((g[key + "data"], (g[key + "row"], g[key + "col"])), shape=tuple(g[key + "shape"]))
             np.testing.assert_allclose(fin.toarray(), prod.toarray(), rtol=1e-13, atol=1e-300)
+
+
+def test_virtual_nodes_and_connectivity_helpers_against_the_reference_patches():
+    """NeuralMG_2D.create_virtual_nodes / get_conn (Multigrid.py:391-398, 438-454): for every coarse node of the
+    structured golden case with fewer than 6 neighbours, the padded neighbour entries and the virtual patch rows the
+    helper returns are the ones in the patch the REFERENCE extracted"""
+    from learnmultigrid_b200.solvers.Multigrid import NeuralMG_2D
+    g = load_golden("neural_2d_cases.npz")
+    d = level_data(g, "s81", 0)
+    M = d["M"]
+    nmg = NeuralMG_2D.__new__(NeuralMG_2D)                  # the helpers use no state
+    conn = NeuralMG_2D.get_conn(M)
+    off = M.toarray() - np.diag(M.diagonal())
+    assert np.array_equal(conn, (off > 0).astype(float)) and M.diagonal().min() > 0      # argument untouched
+    seen = set()
+    for k, c in enumerate(d["C"]):
+        nb = np.flatnonzero(conn[c])
+        vals = np.sort(off[c, nb])[::-1]                    # the reference orders a node's neighbours by mass entry
+        node_M = M[c, c]
+        virt, row = nmg.create_virtual_nodes(vals, node_M)
+        patch = d["patches"][k]
+        assert patch[0] == node_M and len(row) == 6
+        assert np.array_equal(np.sort(row)[::-1], np.sort(patch[1:7])[::-1])
+        if len(nb) < 6:
+            assert len(virt) == 6 * (6 - len(nb))
+            assert np.array_equal(patch[43 - len(virt):], virt)
+            seen.add(len(nb))
+        else:
+            assert len(virt) == 0
+    assert seen >= {2, 3, 4}                                # corners of both kinds and edge nodes
