@@ -1,0 +1,91 @@
+"""GPU tests of distributed_strip.StripHierarchy (partitioned hierarchy built from row blocks only): iterates and
+residual norms bit-identical to the single-GPU hierarchy, local products on the device SpGEMM identical to SciPy's.
+
+Written at the end of round 1 with no GPU time left: NOT YET RUN on a B200, therefore skipped unless MGB_UNVERIFIED=1
+(first thing to run in the next round: MGB_UNVERIFIED=1 python -m pytest tests/test_gpu_strip.py -m gpu)."""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("MGB_UNVERIFIED") != "1",
+                                 reason="not yet verified on a GPU (set MGB_UNVERIFIED=1 to run)")]
+
+
+@pytest.fixture(scope="module")
+def torch_mod():
+    import torch
+    assert torch.cuda.is_available()
+    torch.cuda.set_device(0)
+    return torch
+
+
+def test_device_ops_equal_scipy_ops(torch_mod):
+    from learnmultigrid_b200 import formats as F, partition_setup as PS, problems as P, setup_device as SD
+    from learnmultigrid_b200.distributed_strip import DeviceOps
+    torch = torch_mod
+    ops = DeviceOps(SD.DeviceSetup(torch, torch.device("cuda", 0)))
+    A = F.canonical_csr(P.structured_laplacian_2d(16, P.variable_coefficient))
+    Q = F.canonical_csr(P.structured_hierarchy_2d(16, 2, "quasi")[0])
+    for X, Y in ((sp.csr_matrix(A.T), Q), (sp.csr_matrix(Q.T), A), (A[3:40], Q)):
+        got, want = ops.spgemm(X, Y), PS.ScipyOps.spgemm(X, Y)
+        got.sort_indices()
+        assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+        assert np.array_equal(got.data, want.data)
+    got, want = ops.transpose(Q[5:77]), PS.ScipyOps.transpose(Q[5:77])
+    assert np.array_equal(got.indptr, want.indptr) and np.array_equal(got.indices, want.indices)
+    assert np.array_equal(got.data, want.data)
+    assert ops.spgemm(sp.csr_matrix((0, 5)), sp.csr_matrix((5, 3))).shape == (0, 3)
+    assert ops.transpose(sp.csr_matrix((4, 0))).shape == (0, 4)
+
+
+@pytest.mark.parametrize("smoother,transfer,world,n_dist", [("mcgs", "linear", 2, 2), ("mcgs", "quasi", 4, 2),
+                                                            ("jacobi", "linear", 3, 1), ("mcgs", "linear", 4, 3)])
+def test_strip_hierarchy_is_bit_identical_to_the_single_gpu_cycle(torch_mod, smoother, transfer, world, n_dist):
+    from learnmultigrid_b200 import formats as F, partition as PT, problems as P
+    from learnmultigrid_b200.distributed import run_virtual_ranks
+    from learnmultigrid_b200.distributed_strip import StripHierarchy
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    N, levels, nu, cycles = 64, 4, 2, 3
+    A = F.canonical_csr(P.structured_laplacian_2d(N, P.variable_coefficient))
+    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, transfer)]
+    b = P.structured_rhs_2d(N)
+    rng = np.random.default_rng(3)
+    x0 = rng.standard_normal((A.shape[0], 1))
+    ns = [A.shape[0]] + [q.shape[1] for q in Qs]
+    offs = [PT.block_offsets(n, world) for n in ns]
+
+    h = DeviceHierarchy(A, Qs, smoother=smoother)
+    h.set_rhs(b)
+    h.set_x(x0)
+    params = h.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
+    want_x, want_n = [], []
+    for _ in range(cycles):
+        want_n.append(h.residual_norm())
+        h.vcycle(params)
+        want_x.append(h.get_x().copy())
+
+    def body(fab):
+        r = fab.rank
+        hs = StripHierarchy(A[offs[0][r]:offs[0][r + 1]], [q[offs[l][r]:offs[l][r + 1]] for l, q in enumerate(Qs)],
+                            offs, fab, n_dist, smoother=smoother, region_bytes=1 << 20, max_sites=256, timeout_s=30.0)
+        hs.set_rhs(b[offs[0][r]:offs[0][r + 1]])                      # the owned block is enough
+        hs.set_x(x0)
+        p = hs.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
+        xs, norms = [], []
+        for _ in range(cycles):
+            norms.append(hs.residual_norm())
+            hs.vcycle(p)
+            xs.append(hs.get_x().copy())
+        hs.check()
+        nnz = (list(hs._global_nnzA), list(hs._global_nnzQ))
+        hs.close()
+        return xs, norms, nnz
+
+    for xs, norms, nnz in run_virtual_ranks(world, body):
+        for got, want in zip(xs, want_x):
+            assert np.array_equal(got, want)                           # bit for bit
+        np.testing.assert_allclose(norms, want_n, rtol=1e-13)         # blockwise sum of the squares
+        assert nnz[0] == [lv.nnz_A for lv in h.levels] and nnz[1] == [lv.nnz_Q for lv in h.levels[:-1]]
