@@ -252,7 +252,8 @@ def run_reference(a):
               "and coarse LU repeated in every cycle as the reference does") % (n + 1, n + 1, (n + 1) ** 2, a.levels,
                                                                                    a.nu, a.nu, len(times))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": len(times),
-            "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak",
+            "warmup": a.warmup, "ms_per_step": per * 1e3, "higher_is_better": True,
+            "scaling": "strong" if a.multi == "partitioned" else "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(a, a.n), "sample": sample,
                        "smoother": ("index-order Gauss-Seidel (PyAMG's sweep restated in C: what the reference runs whatever "
@@ -481,7 +482,7 @@ def run_b200(a):
     if rank == 0:
         line = {"metric": METRIC, "value": ndof * (1 if part else world) / (ms_step * 1e-3), "unit": UNIT, "n_gpus": world,
                 "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
-                "scaling": "strong" if part else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if a.multi == "partitioned" else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": workload_name(a, n), "l2": "inputs_exceed_l2 (%.1f GB of operators per cycle)"
                            % (cyc["total"] / 1e9), "setup": a.setup, "levels_rows": list(getattr(h, "_global_n", [l.n for l in h.levels])),
                            "levels_nnz": [l.nnz_A for l in h.levels], "colors": [None if l.color_ptr is None else
