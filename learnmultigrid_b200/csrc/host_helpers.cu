@@ -66,12 +66,50 @@ static int greedy_color_worker(int64_t n_own, int64_t n_ext, const int32_t *h_in
     return ncolors;
 }
 
+// The whole-matrix colouring while 64 colours suffice (no external nodes, one mask word per row): the same rule as the
+// worker above with the row's two loops stripped of everything that case does not need.  Returns -1 as soon as a 65th
+// colour would be needed; the caller then starts over with the general worker and two mask words.
+static int greedy_color_whole_64(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, uint64_t *forbidden,
+                                 int32_t *h_colors) {
+    std::vector<int64_t> deferred;
+    for (int64_t i = 0; i < n; ++i) h_colors[i] = -1;
+    uint64_t used = 0;
+    auto color_row = [&](int64_t i, int32_t p0, int32_t p1, uint64_t mask) -> bool {
+        if (!~mask) return false;
+        const int c = __builtin_ctzll(~mask);
+        h_colors[i] = c;
+        used |= 1ull << c;
+        const uint64_t bit = 1ull << c;
+        for (int32_t p = p0; p < p1; ++p) {
+            const int32_t j = h_indices[p];
+            if (h_colors[j] < 0) forbidden[j] |= bit;          // j == i is coloured by now
+        }
+        return true;
+    };
+    for (int64_t i = 0; i < n; ++i) {
+        const int32_t p0 = h_indptr[i], p1 = h_indptr[i + 1];
+        uint64_t mask = forbidden[i];
+        bool offdiag = false;
+        for (int32_t p = p0; p < p1; ++p) {
+            const int32_t j = h_indices[p];
+            const int32_t c = h_colors[j];                      // -1 for j == i (not coloured yet) and for later rows
+            offdiag |= j != i;
+            mask |= (uint64_t)(c >= 0) << (c & 63);
+        }
+        if (!offdiag) { deferred.push_back(i); continue; }
+        if (!color_row(i, p0, p1, mask)) return -1;
+    }
+    for (int64_t i : deferred)
+        if (!color_row(i, h_indptr[i], h_indptr[i + 1], forbidden[i])) return -1;
+    return used ? 64 - __builtin_clzll(used) : 0;
+}
+
 // Returns the number of colours (>0) or a negative status.
 int mg_host_greedy_color(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_colors) {
     MG_REQUIRE(n >= 0 && h_indptr && h_colors, "null argument");
     // one 64-bit word per row; the second word (colours 64..127) only if a 65th colour is ever needed
     std::vector<uint64_t> lo((size_t)n, 0), hi;
-    int nc = greedy_color_worker(n, 0, h_indptr, h_indices, nullptr, lo.data(), nullptr, h_colors, 3, true);
+    int nc = greedy_color_whole_64(n, h_indptr, h_indices, lo.data(), h_colors);
     if (nc < 0) {
         std::fill(lo.begin(), lo.end(), 0);
         hi.assign((size_t)n, 0);
