@@ -1,19 +1,12 @@
 """Load vector with the reference's interface (learn_multigrid/assembly/LoadVector.py:4-62), vectorised."""
 import numpy as np
 
-from ._element import element_jacobians
+from ._element import element_jacobians, triangle_jacobian
 
 
 class LoadVector:
 
-    @staticmethod
-    def jacobian(x, y):
-        J = np.zeros((2, 2))
-        J[0, 0] = x[1] - x[0]
-        J[0, 1] = x[2] - x[0]
-        J[1, 0] = y[1] - y[0]
-        J[1, 1] = y[2] - y[0]
-        return J
+    jacobian = staticmethod(triangle_jacobian)
 
     def __init__(self, mesh):
         self.mesh = mesh
@@ -30,13 +23,12 @@ class LoadVector:
         c = np.array([q.compute_single(phi, i, fun) for i in range(3)], dtype=float)
         rhs = np.zeros(n_p)
         loc = det[:, None] * c[None, :]
-        for i in range(3):                       # element order inside each local index
-            np.add.at(rhs, conn[:, i], loc[:, i])
+        np.add.at(rhs, conn.reshape(-1), loc.reshape(-1))      # element by element, like the reference's loop (:25-33)
         self.rhs = rhs.reshape(n_p, 1)
         return self.rhs
 
     def save(self, path="../data/matrices/rhs"):
-        np.save(path, self.rhs)
+        np.save(path, self.rhs)                  # .npy, as the reference writes it (LoadVector.py:36-43)
 
     def load(self, path):
         self.rhs = np.load(path)
@@ -44,10 +36,7 @@ class LoadVector:
 
     @staticmethod
     def loc_rhs_2d(d_J, fun, phi, q):
-        locRHS = np.zeros(shape=(3, 1))
-        for i in range(0, 3):
-            locRHS[i] = d_J * q.compute_single(phi, i, fun)
-        return locRHS
+        return np.array([[d_J * q.compute_single(phi, i, fun)] for i in range(3)], dtype=float)
 
     def compute_rhs_1d(self, f):
         """per-element trapezoid rule (LoadVector.py:53-62)"""

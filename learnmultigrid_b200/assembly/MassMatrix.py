@@ -3,21 +3,15 @@ over elements.  1D returns a dense (n,n) array like the reference (or CSR with s
 lil_matrix like the reference (or CSR with format="csr")."""
 import numpy as np
 import scipy.sparse as sp
-from scipy.sparse import coo_matrix, lil_matrix
+from scipy.sparse import lil_matrix
 
-from ._element import element_jacobians, scatter_elements
+from ._element import (element_jacobians, load_triplets, local_matrix, save_triplets, scatter_elements,
+                       triangle_jacobian)
 
 
 class MassMatrix:
 
-    @staticmethod
-    def jacobian(x, y):
-        J = np.zeros((2, 2))
-        J[0, 0] = x[1] - x[0]
-        J[0, 1] = x[2] - x[0]
-        J[1, 0] = y[1] - y[0]
-        J[1, 1] = y[2] - y[0]
-        return J
+    jacobian = staticmethod(triangle_jacobian)
 
     def __init__(self, mesh):
         self.mesh = mesh
@@ -42,23 +36,15 @@ class MassMatrix:
         return self.M
 
     def save(self, path="../data/matrices/M"):
-        x_coo = sp.coo_matrix(self.M)
-        np.savez(path, row=x_coo.row, col=x_coo.col, data=x_coo.data, shape=x_coo.shape)
+        save_triplets(path, self.M)
 
     def load(self, path):
-        y = np.load(path)
-        z = coo_matrix((y['data'], (y['row'], y['col'])), shape=y['shape'])
-        z = lil_matrix(z)
-        self.M = z
-        return z
+        self.M = load_triplets(path)
+        return self.M
 
     @staticmethod
     def loc_m_2d(d_J, phi, q):
-        locM = np.zeros(shape=(3, 3))
-        for i in range(0, 3):
-            for j in range(0, 3):
-                locM[i, j] = d_J * q.compute(phi, np.array([i, j]))
-        return locM
+        return local_matrix(3, d_J, lambda i, j: q.compute(phi, np.array([i, j])))
 
     def compute_mass_1d(self, phi, q, sparse=False):
         """loc_M[i,j] = (right-left) * sum_k phi_i phi_j w_k  (MassMatrix.py:61-82)"""
@@ -70,11 +56,7 @@ class MassMatrix:
 
     @staticmethod
     def loc_m_1d(phi, q, left, right):
-        locM = np.zeros(shape=(2, 2))
-        for i in range(0, 2):
-            for j in range(0, 2):
-                locM[i, j] = (right - left) * q.compute(phi, np.array([i, j]))
-        return locM
+        return local_matrix(2, right - left, lambda i, j: q.compute(phi, np.array([i, j])))
 
 
 def _assemble_1d(loc, n_points, sparse):

@@ -3,22 +3,16 @@ vectorised over elements.  `coefficient` (optional, new: the reference has no va
 test/thesis_variableCoeff_stiff.py is empty) is a callable k(x, y) evaluated at element centroids."""
 import numpy as np
 import scipy.sparse as sp
-from scipy.sparse import coo_matrix, lil_matrix
+from scipy.sparse import lil_matrix
 
-from ._element import element_jacobians, scatter_elements
+from ._element import (element_jacobians, load_triplets, local_matrix, save_triplets, scatter_elements,
+                       triangle_jacobian)
 from .MassMatrix import _assemble_1d
 
 
 class StiffnessMatrix:
 
-    @staticmethod
-    def jacobian(x, y):
-        J = np.zeros((2, 2))
-        J[0, 0] = x[1] - x[0]
-        J[0, 1] = x[2] - x[0]
-        J[1, 0] = y[1] - y[0]
-        J[1, 1] = y[2] - y[0]
-        return J
+    jacobian = staticmethod(triangle_jacobian)
 
     def __init__(self, mesh):
         self.mesh = mesh
@@ -66,23 +60,15 @@ class StiffnessMatrix:
         return self.A
 
     def save(self, path="../data/matrices/A"):
-        x_coo = sp.coo_matrix(self.A)
-        np.savez(path, row=x_coo.row, col=x_coo.col, data=x_coo.data, shape=x_coo.shape)
+        save_triplets(path, self.A)
 
     def load(self, path):
-        y = np.load(path)
-        z = coo_matrix((y['data'], (y['row'], y['col'])), shape=y['shape'])
-        z = lil_matrix(z)
-        self.A = z
-        return z
+        self.A = load_triplets(path)
+        return self.A
 
     @staticmethod
     def loc_a_2d(d_J, jac_inv, d_phi, q):
-        loc_A = np.zeros((3, 3))
-        for i in range(0, 3):
-            for j in range(0, 3):
-                loc_A[i, j] = d_J * q.compute_grad(d_phi, jac_inv, np.array([i, j]))
-        return loc_A
+        return local_matrix(3, d_J, lambda i, j: q.compute_grad(d_phi, jac_inv, np.array([i, j])))
 
     def compute_stiffness_1d(self, dphi, q, sparse=False):
         """loc_A[i,j] = 1/(right-left) * sum_k dphi_i dphi_j w_k  (StiffnessMatrix.py:61-82)"""
@@ -94,8 +80,4 @@ class StiffnessMatrix:
 
     @staticmethod
     def loc_a_1d(dphi, q, left, right):
-        locA = np.zeros(shape=(2, 2))
-        for i in range(0, 2):
-            for j in range(0, 2):
-                locA[i, j] = 1 / (right - left) * q.compute(dphi, np.array([i, j]))
-        return locA
+        return local_matrix(2, 1 / (right - left), lambda i, j: q.compute(dphi, np.array([i, j])))

@@ -30,3 +30,28 @@ def scatter_elements(conn, loc, n, fmt):
     if fmt == "csr":
         return M
     raise ValueError("format must be 'lil' or 'csr'")
+
+
+def triangle_jacobian(x, y):
+    """Jacobian of the affine map from the unit triangle to the triangle with vertex coordinates x[0..2], y[0..2]:
+    its columns are the edge vectors from vertex 0 (MassMatrix.jacobian, MassMatrix.py:8-14)."""
+    return np.array([[x[1] - x[0], x[2] - x[0]],
+                     [y[1] - y[0], y[2] - y[0]]], dtype=float)
+
+
+def local_matrix(n, scale, entry):
+    """n x n element matrix  scale * entry(i, j)  (the reference's loc_* helpers)"""
+    return np.array([[scale * entry(i, j) for j in range(n)] for i in range(n)], dtype=float)
+
+
+def save_triplets(path, M):
+    """matrix as COO triplets in an .npz file (the layout of the reference's save(), MassMatrix.py:37-43)"""
+    coo = sp.coo_matrix(M)
+    np.savez(path, row=coo.row, col=coo.col, data=coo.data, shape=coo.shape)
+
+
+def load_triplets(path):
+    """lil_matrix from a file written by save_triplets / by the reference's save()"""
+    with np.load(path) as z:
+        return sp.coo_matrix((z["data"], (z["row"], z["col"])), shape=tuple(z["shape"])).tolil()
+

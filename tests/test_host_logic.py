@@ -269,3 +269,33 @@ def test_greedy_coloring_refuses_more_than_128_colours():
     full = F.canonical_csr(sp.csr_matrix(np.ones((130, 130))))
     with pytest.raises(_lib.MgError):
         F.greedy_colors(full)
+
+
+def test_interface_helpers_of_the_assembly_and_mesh_mirror():
+    """small pieces behind the reference's names: affine interval map, element table, rule tables, invalid orders"""
+    from learnmultigrid_b200.assembly.MapReferenceElement import IntervalMap, g_function, inv_g_function
+    from learnmultigrid_b200.assembly.Quadrature import Quadrature, Quadrature2D
+    from learnmultigrid_b200.assembly.ShapeFunction import Function, GradientTriangle
+    from learnmultigrid_b200.assembly.LoadFunction import LoadFunction
+    from learnmultigrid_b200.mesh.Mesh1D import Mesh1D, Mesh1DRefinement
+    m = IntervalMap(0.25, 0.75)
+    assert m.to_physical(0.5) == 0.5 and m.to_reference(0.5) == 0.5
+    assert g_function(0.2, 1.0, 3.0) == 1.0 + 0.2 * (3.0 - 1.0) and inv_g_function(1.4, 1.0, 3.0) == (1.4 - 1.0) / (3.0 - 1.0)
+    q = Quadrature(3)
+    assert np.array_equal(q.get_points(), [0.11270166537926, 0.5, 0.88729833462074])      # 14-digit constants
+    assert np.array_equal(q.get_weights(), [0.27777777777778, 0.44444444444444, 0.27777777777778])
+    assert Quadrature.order_to_points(2) == "Invalid order" and Quadrature2D.order_to_weights(1) == "Invalid order"
+    assert np.array_equal(Quadrature2D(3).get_weights(), [1 / 6] * 3) and Quadrature2D(3).get_points().shape == (3, 2)
+    phi = Function(2)
+    assert q.compute(phi, (0, 1)) == q.compute(phi, np.array([1, 0]))
+    assert abs(q.compute(phi, (0, 0)) - 1 / 3) < 1e-13 and abs(q.compute_single(phi, 1, LoadFunction(lambda x: 1.0)) - 0.5) < 1e-13
+    assert GradientTriangle(1).evaluate(None, 2).tolist() == [[0], [1]]
+    with pytest.raises(TypeError):
+        LoadFunction(3.0)
+    mesh = Mesh1D(True, 4)
+    mesh.construct()
+    els = mesh.elements()
+    assert [e.index for e in els] == [0, 1, 2, 3] and els[2].left == 0.5 and els[2].length == 0.25
+    fine = Mesh1DRefinement(3, 2)
+    fine.construct()
+    assert fine.get_ne() == 12 and fine.get_np() == 13 and fine.get_connections().shape == (12, 2)
