@@ -18,88 +18,86 @@ from ..assembly.Quadrature import Quadrature, Quadrature2D
 from ..assembly.ShapeFunction import Function, FunctionTriangle
 
 
+def _scaling(kind, B, M):
+    """the diagonal a sparse coupling operator is divided by: its row sums ("quasi") or the lumped mass ("pseudo")"""
+    if kind == "quasi":
+        return np.asarray(B.sum(axis=1)).ravel()
+    if kind == "pseudo":
+        return np.asarray(M.sum(axis=0)).ravel()
+    raise ValueError("unknown projection type %r" % (kind,))
+
+
+def _row_scaled(B, s):
+    Q = sp.csr_matrix(sp.diags(1.0 / s) @ B)
+    Q.sort_indices()
+    return Q
+
+
 class L2Projection:
+    KINDS = ("L2", "pseudo", "quasi")
 
     def __init__(self, type, fine_mesh, coarse_mesh):
         self.type = type
         self.fine_mesh = fine_mesh
         self.coarse_mesh = coarse_mesh
 
+    # ---- 1D (dense like the reference, :26-90) -------------------------------------------------------------
     def compute_transfer_1d(self, sparse=False):
-        """returns (Q, seconds spent in the intersection search) like the reference (:26-57)"""
-        fine_mesh = self.fine_mesh
-        coarse_mesh = self.coarse_mesh
-        inter = Intersection(fine_mesh, coarse_mesh)
-        start = time.time()
-        inter.find_intersections1d()
-        timeL = time.time() - start
-        q = Quadrature(3)
-        phi = Function(2)
-        coup_op = CouplingOperator(inter, fine_mesh, coarse_mesh)
+        """(Q, seconds spent in the intersection search).  sparse=True builds "quasi" / "pseudo" operators in CSR
+        without the dense n x n detour."""
         method = self.type_to_method(self.type)
         if not callable(method):
             raise ValueError("unknown projection type %r" % (self.type,))
-        if sparse and self.type in ("quasi", "pseudo"):
-            B = coup_op.compute_b_1d(q, phi, sparse=True)
-            M = MassMatrix(fine_mesh).compute_mass_1d(phi, q, sparse=True)
-            if self.type == "quasi":
-                s = np.asarray(B.sum(axis=1)).ravel()
-            else:
-                s = np.asarray(M.sum(axis=0)).ravel()
-            return sp.csr_matrix(sp.diags(1.0 / s) @ B), timeL
-        B = coup_op.compute_b_1d(q, phi)
-        M = MassMatrix(fine_mesh).compute_mass_1d(phi, q)
-        L = method(B, M)
-        return L, timeL
+        inter = Intersection(self.fine_mesh, self.coarse_mesh)
+        t0 = time.time()
+        inter.find_intersections1d()
+        seconds = time.time() - t0
+        rule, hat = Quadrature(3), Function(2)
+        coupling = CouplingOperator(inter, self.fine_mesh, self.coarse_mesh)
+        mass = MassMatrix(self.fine_mesh)
+        if sparse and self.type != "L2":
+            B = coupling.compute_b_1d(rule, hat, sparse=True)
+            M = mass.compute_mass_1d(hat, rule, sparse=True)
+            return _row_scaled(B, _scaling(self.type, B, M)), seconds
+        return method(coupling.compute_b_1d(rule, hat), mass.compute_mass_1d(hat, rule)), seconds
 
+    def type_to_method(self, type):
+        return getattr(self, "compute_%s_1d" % type.lower(), "Invalid order") if type in self.KINDS else "Invalid order"
+
+    @staticmethod
+    def compute_l2_1d(B, M):
+        """Q = M^-1 B through the explicit inverse, as the reference forms it (:67-71; same LAPACK calls, same bits)"""
+        return np.dot(np.linalg.inv(M), B)
+
+    @staticmethod
+    def compute_pseudo_1d(B, M):
+        """Q = diag(column sums of M)^-1 B by a dense solve with the diagonal matrix (:73-81)"""
+        return np.linalg.solve(np.diag(np.sum(M, axis=0)), B)
+
+    @staticmethod
+    def compute_quasi_1d(B, _):
+        """Q = B with every row divided by its sum (:83-90)"""
+        return B / B.sum(axis=1)[:, np.newaxis]
+
+    # ---- 2D ------------------------------------------------------------------------------------------------
     def compute_transfer_2d(self, P=None):
         """Q (CSR) between two P1 triangle meshes of the same domain.
         With P (the linear interpolation coarse -> fine of NESTED meshes, n_f x n_c) the coupling operator is
         B_h = M_h P -- one sparse product.  Without it B_h is integrated on the triangle-triangle
         intersections (coupling2d.coupling_operator_2d), which works for non-nested meshes as well.
         "quasi": Q = B / rowsum(B); "pseudo": Q = diag(colsum M)^-1 B; "L2": Q = M^-1 B (sparse solve, dense result:
-        small meshes only), as in 1D (:67-90)."""
+        small meshes only), as in 1D."""
+        if self.type not in self.KINDS:
+            raise ValueError("unknown projection type %r" % (self.type,))
         M = MassMatrix(self.fine_mesh).compute_mass_2d(FunctionTriangle(1), Quadrature2D(3), format="csr")
         if P is not None:
             B = sp.csr_matrix(M @ sp.csr_matrix(P))
         else:
             from .coupling2d import coupling_operator_2d
             B = coupling_operator_2d(self.fine_mesh, self.coarse_mesh)
-        if self.type == "quasi":
-            s = np.asarray(B.sum(axis=1)).ravel()
-        elif self.type == "pseudo":
-            s = np.asarray(M.sum(axis=0)).ravel()
-        elif self.type == "L2":
+        if self.type == "L2":
             from scipy.sparse.linalg import splu
             Q = sp.csr_matrix(splu(sp.csc_matrix(M)).solve(B.toarray()))
             Q.sort_indices()
             return Q
-        else:
-            raise ValueError("unknown projection type %r" % (self.type,))
-        Q = sp.csr_matrix(sp.diags(1.0 / s) @ B)
-        Q.sort_indices()
-        return Q
-
-    def type_to_method(self, type):
-        switcher = {
-            "L2": self.compute_l2_1d,
-            "pseudo": self.compute_pseudo_1d,
-            "quasi": self.compute_quasi_1d,
-        }
-        return switcher.get(type, "Invalid order")
-
-    @staticmethod
-    def compute_l2_1d(B, M):
-        inv_M = np.linalg.inv(M)
-        return np.dot(inv_M, B)
-
-    @staticmethod
-    def compute_pseudo_1d(B, M):
-        row_sum = np.sum(M, axis=0)
-        diag = np.diag(row_sum)
-        return np.linalg.solve(diag, B)
-
-    @staticmethod
-    def compute_quasi_1d(B, _):
-        row_sums = B.sum(axis=1)
-        return B / row_sums[:, np.newaxis]
+        return _row_scaled(B, _scaling(self.type, B, M))

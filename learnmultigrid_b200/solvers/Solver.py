@@ -25,34 +25,13 @@ class Solver:
         self.track_res = np.ndarray(shape=(0, 1), dtype=float)
         self._dev = None
 
-    # getters / setters, Solver.py:23-48
+    # accessors of Solver.py:23-48 (read access is generated from the table below the class)
     def set_matrix(self, matrix):
         self.matrix = matrix
-        self._dev = None
-
-    def get_matrix(self):
-        return self.matrix
-
-    def get_residual_vector(self):
-        return self.residual_vector
-
-    def get_residual(self):
-        return self.residual
+        self._dev = None                 # the device copy belongs to the old matrix
 
     def set_rhs(self, rhs):
         self.rhs = rhs
-
-    def get_rhs(self):
-        return self.rhs
-
-    def get_solution(self):
-        return self.solution
-
-    def get_dimension(self):
-        return self.dim
-
-    def get_track_res(self):
-        return self.track_res
 
     # ---- device plumbing shared by the stationary solvers and CG (natural ordering, CSR kernels) ----------
     def _device_csr(self):
@@ -93,6 +72,20 @@ class Solver:
         _lib.check(d["lib"].mg_residual_csr(d["n"], d["indptr"].data_ptr(), d["indices"].data_ptr(),
                                             d["values"].data_ptr(), x.data_ptr(), b.data_ptr(), r.data_ptr(), st),
                    "mg_residual_csr")
+
+
+def _reader(attribute):
+    def read(self):
+        return getattr(self, attribute)
+    read.__name__ = read.__qualname__ = "get_" + attribute
+    read.__doc__ = "the solver's `%s`" % attribute
+    return read
+
+
+for _name, _attribute in (("get_matrix", "matrix"), ("get_rhs", "rhs"), ("get_solution", "solution"),
+                          ("get_residual", "residual"), ("get_residual_vector", "residual_vector"),
+                          ("get_dimension", "dim"), ("get_track_res", "track_res")):
+    setattr(Solver, _name, _reader(_attribute))
 
 
 class DirectSolver(Solver):
