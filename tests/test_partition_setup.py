@@ -343,3 +343,146 @@ def test_strip_local_setup_with_row_local_structured_colours():
         assert np.array_equal(levs[0].plan.perm, want.perm) and levs[0].plan.seg_color == want.seg_color
         same(A_rep, As[1])
         same(Q_rep[0], Qs[1])
+
+
+@pytest.mark.parametrize("world,n_dist", [(2, 2), (3, 2), (4, 1), (2, 3)])
+def test_partitioned_vcycle_driven_by_the_strip_setup_equals_the_global_oracle(world, n_dist):
+    """End to end without any global operator on the ranks: every rank generates its rows, strip_local_setup gives it
+    blocks, colours, plans and the replicated tail; the partitioned V-cycle (halo per colour, residual halo, hand-off
+    gather, prolongation, halo refresh -- the steps of csrc/cycle.cu, here with the oracle's kernels and send lists
+    exchanged the way DistributedHierarchy does) reproduces the single-process oracle cycle BIT FOR BIT.  This is the
+    host-side twin of distributed_strip.StripHierarchy."""
+    from oracle import kernels as K
+    from oracle.vcycle import OracleMultigrid
+    N, L, NU = 16, 4, 1
+    ns = [((N >> l) + 1) ** 2 for l in range(L)]
+    offs = [PT.block_offsets(n, world) for n in ns]
+    # the global oracle: verification only
+    A0 = P.structured_laplacian_2d(N, P.variable_coefficient)
+    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, L, "linear")]
+    As = global_hierarchy(A0, Qs)
+    cols = [F.greedy_colors(a)[0] for a in As[:-1]] + [None]
+    oracle = OracleMultigrid(A0, np.zeros((ns[0], 1)), Qs, smoother="mcgs", colors=cols, hoist_setup=True)
+    oracle.build_hierarchy(L)
+    rng = np.random.default_rng(1)
+    xg, bg = rng.standard_normal(ns[0]), rng.standard_normal(ns[0])
+    want, cur = [], xg.reshape(-1, 1).copy()
+    for _ in range(2):
+        cur = oracle.v_cycle(oracle.matrix, cur, bg.reshape(-1, 1), NU, L)
+        want.append(cur.ravel().copy())
+
+    def body(fab):
+        r = fab.rank
+        A_blk = P.structured_laplacian_2d(N, P.variable_coefficient, rows=(offs[0][r], offs[0][r + 1]))
+        Q_blks = [P.linear_P_2d(N >> l, rows=(offs[l][r], offs[l][r + 1])) for l in range(L - 1)]
+        strip, A_rep, Q_rep = PS.strip_local_setup(fab, A_blk, Q_blks, offs, n_dist, "mcgs")
+        plans = [s.plan for s in strip]
+        # send lists, as in DistributedHierarchy: everyone tells the others which rows it reads, in its halo order
+        mine = []
+        for p in plans:
+            d = {}
+            for q in p.neighbours:
+                s, e = p.seg[q]
+                d[q] = (p.halo_gid[s:e], [p.seg_color[(q, c)][0] - s for c in range(p.ncolors)] + [e - s])
+            mine.append(d)
+        everyone = fab.allgather(mine)
+        sends = [{q: (plans[l].local_of_owned(everyone[q][l][r][0]), everyone[q][l][r][1])
+                  for q in range(world) if q != r and r in everyone[q][l]} for l in range(n_dist)]
+
+        def positions(l):
+            """global id -> position in this rank's level-l vector (partitioned: [own | halo]; replicated: natural)"""
+            if l >= n_dist:
+                return lambda gid: np.asarray(gid, dtype=np.int64), ns[l]
+            g = plans[l].gather_indices()
+            order = np.argsort(g)
+
+            def pos(gid):
+                k = np.searchsorted(g[order], gid)
+                assert np.array_equal(g[order][k], gid)          # every referenced column is owned or in the halo
+                return order[k]
+            return pos, len(g)
+
+        lev = []
+        for l in range(n_dist):
+            p, s = plans[l], strip[l]
+            pos, nv = positions(l)
+            posn, nvn = positions(l + 1)
+            own = p.gather_indices()[:p.n_own] - p.o0                       # block rows in colour-blocked order
+            if l + 1 < n_dist:
+                pn = plans[l + 1]
+                own_next = pn.gather_indices()[:pn.n_own] - pn.o0
+            else:
+                own_next = np.arange(offs[l + 1][r + 1] - offs[l + 1][r])
+
+            def local(M, rows, colpos, ncols):
+                B = sp.csr_matrix(M)[rows]
+                B.sort_indices()
+                return F.raw_csr(B.indptr, colpos(B.indices.astype(np.int64)).astype(np.int32), B.data,
+                                 (len(rows), ncols))
+            lev.append({"A": local(s.A, own, pos, nv), "Q": local(s.Q, own, posn, nvn),
+                        "QT": local(s.QT, own_next, pos, nv), "p": p, "nv": nv})
+
+        def exchange(l, v, color=None):
+            p = lev[l]["p"]
+            out = {}
+            for q, (idx, ptr) in sends[l].items():
+                a, b = (0, len(idx)) if color is None else (ptr[color], ptr[color + 1])
+                out[q] = v[idx[a:b]].copy()
+            got = fab.allgather(out)
+            for q in p.neighbours:
+                s0, s1 = p.seg[q] if color is None else p.seg_color[(q, color)]
+                v[p.n_own + s0:p.n_own + s1] = got[q][r]
+
+        tail_colors = [F.greedy_colors(A_rep)[0]]
+        tail = OracleMultigrid(A_rep, np.zeros((ns[n_dist], 1)), Q_rep, smoother="mcgs", colors=tail_colors,
+                               hoist_setup=True)
+        for a in tail.build_hierarchy(L - n_dist)[1:-1]:
+            tail_colors.append(F.greedy_colors(F.canonical_csr(a))[0])
+
+        def smooth(l, x, b):
+            d = lev[l]
+            p = d["p"]
+            Asq = sp.vstack([d["A"], sp.csr_matrix((p.n_halo, d["nv"]))]).tocsr()
+            Asq = F.raw_csr(Asq.indptr, Asq.indices, Asq.data, Asq.shape)
+            bb = np.concatenate([b, np.zeros(p.n_halo)])
+            for _ in range(NU):
+                for c in range(p.ncolors):
+                    K.gauss_seidel_multicolor(Asq, x, bb, [np.arange(p.color_ptr[c], p.color_ptr[c + 1], dtype=np.int32)])
+                    exchange(l, x, c)
+
+        def vcycle(l, x, b):
+            d = lev[l]
+            p = d["p"]
+            smooth(l, x, b)
+            res = np.zeros(d["nv"])
+            res[:p.n_own] = K.residual(d["A"], x, b)
+            exchange(l, res)
+            rc = K.spmv(d["QT"], res)
+            if l + 1 < n_dist:
+                e = np.zeros(lev[l + 1]["nv"])
+                vcycle(l + 1, e, rc)
+            else:
+                bc = np.concatenate(fab.allgather(rc)).reshape(-1, 1)       # hand-off: every rank gets the full rhs
+                if L - (l + 1) >= 2:
+                    e = tail.v_cycle(tail.matrix, np.zeros_like(bc), bc, NU, L - (l + 1)).ravel()
+                else:
+                    e = tail._lu.solve(bc.ravel())                          # the tail is the coarsest level alone
+            x[:p.n_own] = K.prolong_correct(d["Q"], e, x[:p.n_own])
+            exchange(l, x)
+            smooth(l, x, b)
+
+        g0 = plans[0].gather_indices()
+        x, b = xg[g0].copy(), bg[g0[:plans[0].n_own]].copy()
+        out = []
+        for _ in range(2):
+            vcycle(0, x, b)
+            out.append((g0[:plans[0].n_own].copy(), x[:plans[0].n_own].copy()))
+        return out
+
+    res = run_ranks(world, body)
+    for cyc in range(2):
+        got = np.empty(ns[0])
+        for rank_out in res:
+            gid, val = rank_out[cyc]
+            got[gid] = val
+        assert np.array_equal(got, want[cyc])
