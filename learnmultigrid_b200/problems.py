@@ -30,22 +30,25 @@ def boundary_nodes_2d(N):
     return np.flatnonzero((ix == 0) | (ix == N) | (iy == 0) | (iy == N))
 
 
-def structured_laplacian_2d(N, coefficient=None, rows=None):
+def structured_laplacian_2d(N, coefficient=None, rows=None, Ny=None):
     """P1 stiffness matrix of -div(k grad u) on the reference's structured mesh Mesh2D(N*N) ((N+1)^2 nodes, row
     major), with boundary rows replaced by identity rows exactly as test/thesis_structured_2d.py:407-414.
     k = 1 gives the 5-point stencil [-1,-1,4,-1,-1] (hypotenuse couplings are exact zeros and not stored);
     `coefficient(x, y)` is evaluated at element centroids.  Returns canonical CSR.
     rows=(r0, r1): only that row block (global column ids) -- what one rank of a row-partitioned run generates, so
-    that no process ever holds the global operator (partition_setup.py)."""
+    that no process ever holds the global operator (partition_setup.py).
+    Ny: number of squares in y (default N): the domain is [0, 1] x [0, Ny/N] with the same square cells of side 1/N --
+    the stacked strips of a weak-scaling run (one N x N square per GPU)."""
+    Ny = N if Ny is None else int(Ny)
     W = N + 1
-    n = W * W
+    n = W * (Ny + 1)
     r0, r1 = (0, n) if rows is None else (int(rows[0]), int(rows[1]))
     if not 0 <= r0 <= r1 <= n:
         raise ValueError("row block outside the matrix")
     if (r1 - r0) * 5 >= 2 ** 31 or n >= 2 ** 31:
         raise OverflowError("nnz does not fit int32")
     iy, ix = np.divmod(np.arange(r0, r1, dtype=np.int64), W)
-    interior = (ix > 0) & (ix < N) & (iy > 0) & (iy < N)
+    interior = (ix > 0) & (ix < N) & (iy > 0) & (iy < Ny)
     counts = np.where(interior, 5, 1).astype(np.int64)
     indptr = np.zeros(r1 - r0 + 1, dtype=np.int64)
     np.cumsum(counts, out=indptr[1:])
@@ -84,25 +87,31 @@ def structured_laplacian_2d(N, coefficient=None, rows=None):
     return F.raw_csr(indptr.astype(np.int32), indices, data, (r1 - r0, n))
 
 
-def structured_rhs_2d(N, f_value=-1.0):
+def structured_rhs_2d(N, f_value=-1.0, rows=None, Ny=None):
     """load vector of f = const on the structured mesh with Dirichlet rows zeroed: interior entries f*h^2
-    (six triangles of area h^2/2, each contributing f*area/3), thesis_structured_2d.py:17-19,403,414."""
+    (six triangles of area h^2/2, each contributing f*area/3), thesis_structured_2d.py:17-19,403,414.
+    rows / Ny as in structured_laplacian_2d."""
+    Ny = N if Ny is None else int(Ny)
     W = N + 1
     h = 1.0 / N
-    rhs = np.full((W, W), f_value * h * h)
-    rhs[0, :] = rhs[-1, :] = rhs[:, 0] = rhs[:, -1] = 0.0
-    return rhs.reshape(-1, 1)
+    r0, r1 = (0, W * (Ny + 1)) if rows is None else (int(rows[0]), int(rows[1]))
+    iy, ix = np.divmod(np.arange(r0, r1, dtype=np.int64), W)
+    interior = (ix > 0) & (ix < N) & (iy > 0) & (iy < Ny)
+    return np.where(interior, f_value * h * h, 0.0).reshape(-1, 1)
 
 
-def linear_P_2d(Nf, rows=None):
+def linear_P_2d(Nf, rows=None, Nyf=None):
     """linear interpolation from the nested coarse mesh Mesh2D((Nf/2)^2) to Mesh2D(Nf^2): coincident nodes 1,
     edge midpoints 1/2 + 1/2 (horizontal, vertical and the lower-left/upper-right diagonal).  CSR.
-    rows=(r0, r1): only that block of fine rows (global coarse column ids)."""
-    if Nf % 2:
+    rows=(r0, r1): only that block of fine rows (global coarse column ids).
+    Nyf: squares in y of the fine mesh (default Nf), for the rectangular meshes of structured_laplacian_2d(Ny=)."""
+    Nyf = Nf if Nyf is None else int(Nyf)
+    if Nf % 2 or Nyf % 2:
         raise ValueError("Nf must be even")
     Wf, Wc = Nf + 1, Nf // 2 + 1
-    r0, r1 = (0, Wf * Wf) if rows is None else (int(rows[0]), int(rows[1]))
-    if not 0 <= r0 <= r1 <= Wf * Wf:
+    nf, nc = Wf * (Nyf + 1), Wc * (Nyf // 2 + 1)
+    r0, r1 = (0, nf) if rows is None else (int(rows[0]), int(rows[1]))
+    if not 0 <= r0 <= r1 <= nf:
         raise ValueError("row block outside the matrix")
     iy, ix = np.divmod(np.arange(r0, r1, dtype=np.int64), Wf)
     cx, cy = ix // 2, iy // 2
@@ -120,7 +129,7 @@ def linear_P_2d(Nf, rows=None):
     t = np.flatnonzero(two)
     indices[indptr[t] + 1] = second[t]
     data[indptr[t] + 1] = 0.5
-    return F.raw_csr(indptr.astype(np.int32), indices, data, (r1 - r0, Wc * Wc))
+    return F.raw_csr(indptr.astype(np.int32), indices, data, (r1 - r0, nc))
 
 
 def structured_mass_2d(N):
@@ -142,15 +151,18 @@ def quasi_l2_Q_2d(Nf):
     return Q
 
 
-def structured_hierarchy_2d(N, levels, transfer="linear"):
-    """[Q_0, ..., Q_{levels-2}] for the nested structured meshes N, N/2, ..."""
+def structured_hierarchy_2d(N, levels, transfer="linear", Ny=None):
+    """[Q_0, ..., Q_{levels-2}] for the nested structured meshes N, N/2, ...  (Ny: squares in y, linear transfers only)"""
+    if Ny is not None and transfer != "linear":
+        raise ValueError("rectangular meshes: linear transfers only")
     qs = []
-    n = N
+    n, ny = N, (N if Ny is None else int(Ny))
     for _ in range(levels - 1):
-        if n % 2 or n < 2:
+        if n % 2 or n < 2 or ny % 2 or ny < 2:
             raise ValueError("mesh cannot be coarsened %d times" % (levels - 1))
-        qs.append(linear_P_2d(n) if transfer == "linear" else quasi_l2_Q_2d(n))
+        qs.append(linear_P_2d(n, Nyf=ny) if transfer == "linear" else quasi_l2_Q_2d(n))
         n //= 2
+        ny //= 2
     return qs
 
 

@@ -486,3 +486,59 @@ def test_partitioned_vcycle_driven_by_the_strip_setup_equals_the_global_oracle(w
             gid, val = rank_out[cyc]
             got[gid] = val
         assert np.array_equal(got, want[cyc])
+
+
+def _rect_mesh(Nx, Ny):
+    """Nx x Ny square cells of side 1/Nx with the reference's node numbering and triangle split (Mesh2D.py:63-93)"""
+    from learnmultigrid_b200.mesh.Mesh2D import Mesh2D
+    W, h = Nx + 1, 1.0 / Nx
+    iy, ix = np.divmod(np.arange(W * (Ny + 1)), W)
+    k = (np.arange(Ny)[:, None] * W + np.arange(Nx)[None, :]).reshape(-1)
+    conn = np.stack([np.stack([k, k + 1, k + W + 1], axis=1), np.stack([k, k + W + 1, k + W], axis=1)], axis=1)
+    return Mesh2D(p=np.stack([ix * h, iy * h], axis=1), conn=conn.reshape(-1, 3))
+
+
+@pytest.mark.parametrize("Nx,Ny", [(4, 8), (8, 4)])
+def test_rectangular_strip_generators_match_the_assembly(Nx, Ny):
+    """structured_laplacian_2d / structured_rhs_2d / linear_P_2d with Ny != N (the stacked strips of a weak-scaling
+    run): the operator and load vector equal the P1 assembly on that mesh, row blocks equal slices, the transfer
+    reproduces linear functions, and the strip-local Galerkin hierarchy equals the global one"""
+    from learnmultigrid_b200.assembly.StiffnessMatrix import StiffnessMatrix
+    from learnmultigrid_b200.assembly.LoadVector import LoadVector
+    from learnmultigrid_b200.assembly.LoadFunction import LoadFunction
+    from learnmultigrid_b200.assembly.Quadrature import Quadrature2D
+    from learnmultigrid_b200.assembly.ShapeFunction import GradientTriangle, FunctionTriangle
+    mesh = _rect_mesh(Nx, Ny)
+    W = Nx + 1
+    n = W * (Ny + 1)
+    iy, ix = np.divmod(np.arange(n), W)
+    bnd = np.flatnonzero((ix == 0) | (ix == Nx) | (iy == 0) | (iy == Ny))
+    for coef in (None, P.variable_coefficient):
+        As = sp.lil_matrix(StiffnessMatrix(mesh).compute_stiffness_2d(GradientTriangle(1), Quadrature2D(3), format="csr",
+                                                                      coefficient=coef))
+        for b in bnd:
+            As[b, :] = 0
+            As[b, b] = 1.0
+        As = sp.csr_matrix(As)
+        As.data[abs(As.data) < 1e-13] = 0          # hypotenuse couplings: exact zeros in the generator
+        As.eliminate_zeros()
+        As.sort_indices()
+        G = P.structured_laplacian_2d(Nx, coef, Ny=Ny)
+        assert np.array_equal(As.indptr, G.indptr) and np.array_equal(As.indices, G.indices)
+        np.testing.assert_allclose(G.data, As.data, rtol=1e-13, atol=1e-14)
+        for r0, r1 in ((0, n), (3, 29), (n - 11, n)):
+            same(P.structured_laplacian_2d(Nx, coef, rows=(r0, r1), Ny=Ny), G[r0:r1])
+    rhs = LoadVector(mesh).compute_rhs_2d(LoadFunction(lambda q: -1.0), FunctionTriangle(1), Quadrature2D(3))
+    rhs[bnd] = 0
+    np.testing.assert_allclose(P.structured_rhs_2d(Nx, Ny=Ny), rhs, rtol=1e-13, atol=1e-18)
+    assert np.array_equal(P.structured_rhs_2d(Nx, rows=(5, 31), Ny=Ny), P.structured_rhs_2d(Nx, Ny=Ny)[5:31])
+    Pm = P.linear_P_2d(Nx, Nyf=Ny)
+    Wc = Nx // 2 + 1
+    cy, cx = np.divmod(np.arange(Wc * (Ny // 2 + 1)), Wc)
+    np.testing.assert_allclose(Pm @ (3.0 + 2.0 * cx - 5.0 * cy), 3.0 + ix - 2.5 * iy, rtol=0, atol=1e-13)
+    same(P.linear_P_2d(Nx, rows=(7, 33), Nyf=Ny), Pm[7:33])
+    Qs = P.structured_hierarchy_2d(Nx, 3, "linear", Ny=Ny)
+    want = global_hierarchy(G, Qs)
+    offs, res = strip_run(G, Qs, 3)
+    for l in range(3):
+        same(sp.vstack([res[r][0][l] for r in range(3)], format="csr"), want[l])
