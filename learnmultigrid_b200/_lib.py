@@ -60,7 +60,9 @@ class mg_dist_level(ctypes.Structure):
     _fields_ = [("n_halo", c_i64), ("ncolors", ctypes.c_int32), ("pad_", ctypes.c_int32),
                 ("xfer_color", ctypes.POINTER(mg_xfer)), ("xfer_all", ctypes.POINTER(mg_xfer)),
                 ("xfer_gather", ctypes.POINTER(mg_xfer)), ("d_gather_tmp", c_vp), ("d_gather_self_idx", c_vp),
-                ("n_gather_own", c_i64), ("d_mask_A", c_vp), ("d_mask_Q", c_vp), ("d_mask_QT", c_vp)]
+                ("n_gather_own", c_i64), ("d_mask_A", c_vp), ("d_mask_Q", c_vp), ("d_mask_QT", c_vp),
+                ("h_push_ptr", ctypes.POINTER(c_i64)), ("d_push_row", c_vp), ("d_push_peer", c_vp), ("d_push_pos", c_vp),
+                ("d_push_mask", c_vp), ("h_push_tail", ctypes.POINTER(c_i64))]
 
 
 class mg_bcr_dist(ctypes.Structure):
@@ -111,6 +113,7 @@ _SIGNATURES = {
     "mg_set_tma_min_rows": (c_i64, [c_i64]),
     "mg_sell_halo_mask": (c_int, [ctypes.POINTER(mg_sell), c_i64, c_vp, c_vp]),
     "mg_set_fused_exchange": (c_int, [c_int]),
+    "mg_set_push_exchange": (c_int, [c_int]),
     "mg_set_tail_max_rows": (c_i64, [c_i64]),
     "mg_set_tail_ctas_per_sm": (c_int, [c_int]),
     "mg_tail_config_epoch": (c_i64, []),
@@ -235,6 +238,8 @@ def load():
         lib.mg_set_pdl(0)
     if os.environ.get("MGB_FUSED_EXCHANGE", "1") == "0":
         lib.mg_set_fused_exchange(0)
+    if os.environ.get("MGB_PUSH_EXCHANGE", "0") == "1":
+        lib.mg_set_push_exchange(1)
     if "MGB_WIDE_MIN_LEN" in os.environ:
         lib.mg_set_wide_min_len(int(os.environ["MGB_WIDE_MIN_LEN"]))
     if "MGB_TAIL_MAX_ROWS" in os.environ:

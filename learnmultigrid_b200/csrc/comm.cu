@@ -140,6 +140,15 @@ int comm_prepare(mg_comm *c, const mg_xfer *x, const double *src, double *dst, E
     return MG_OK;
 }
 
+// stand-alone launch of a site that was booked earlier (comm_prepare) -- the receiving half of a pushed exchange that
+// no SELL kernel could carry
+int comm_launch_prepared(const ExArgs &a, int grid, cudaStream_t st) {
+    if (grid <= 0) return MG_OK;
+    launch_k(exchange_kernel, (unsigned)grid, (unsigned)kBlock, st, a);
+    MG_CHECK_LAUNCH("exchange (prepared)");
+    return MG_OK;
+}
+
 int comm_exchange(mg_comm *c, const mg_xfer *x, const double *src, double *dst, cudaStream_t st) {
     ExArgs a;
     int grid = 0;

@@ -20,7 +20,10 @@ int sell_spmv_fused(const mg_sell *, const double *, double *, const SellFuse *,
 int sell_residual_fused(const mg_sell *, const double *, const double *, double *, const SellFuse *, cudaStream_t);
 int sell_gs_rows_fused(const mg_sell *, double *, const double *, int64_t, int64_t, const SellFuse *, cudaStream_t);
 int sell_prolong_fused(const mg_sell *, const double *, const double *, double *, const SellFuse *, cudaStream_t);
+int sell_gs_rows_push(const mg_sell *, double *, const double *, int64_t, int64_t, const SellFuse *, const SellPush *, cudaStream_t);
+int comm_launch_prepared(const ExArgs &, int, cudaStream_t);
 int g_fused_exchange = 1;
+int g_push_exchange = 0;     // producer-driven colour exchanges (mg_set_push_exchange); off by default
 
 thread_local char g_last_error[512] = "";
 thread_local int64_t g_launch_count = 0;
@@ -94,9 +97,14 @@ static int op_copy(int64_t n, const double *src, double *dst, cudaStream_t st) {
 // Deferred exchange: with multicolour Gauss-Seidel an exchange of a level vector is not launched when it is issued
 // but handed to the next SELL kernel that gathers from that vector, which carries it as extra CTAs (sell_kernel_fused).
 // Anything else that needs the halo first calls flush_pending().
+// A pending exchange whose values were already PUSHED by the kernel that produced them (producer-driven mode) has its
+// site booked: `prepared` holds the receiving half (recv_only) and the number of exchange CTAs.
 struct Pending {
     const mg_xfer *x = nullptr;
     double *vec = nullptr;
+    bool prepared = false;
+    int grid = 0;
+    ExArgs ex;
 };
 static thread_local Pending g_pend;
 
@@ -105,6 +113,10 @@ static int flush_pending(mg_comm *comm, cudaStream_t st) {
     const mg_xfer *x = g_pend.x;
     double *v = g_pend.vec;
     g_pend.x = nullptr;
+    if (g_pend.prepared) {
+        g_pend.prepared = false;
+        return comm_launch_prepared(g_pend.ex, g_pend.grid, st);
+    }
     return comm_exchange(comm, x, v, v, st);
 }
 // issue an exchange of vector v: deferred if allowed, immediate otherwise
@@ -113,6 +125,7 @@ static int issue_exchange(mg_comm *comm, const mg_xfer *x, double *v, bool may_d
     if (!may_defer || !g_fused_exchange) return comm_exchange(comm, x, v, v, st);
     g_pend.x = x;
     g_pend.vec = v;
+    g_pend.prepared = false;
     return MG_OK;
 }
 // before a SELL launch that gathers from `xop` over rows [row0,row1) of M: take the pending exchange along if it is on
@@ -126,7 +139,13 @@ static int take_pending(mg_comm *comm, const double *xop, const mg_sell *M, int6
     double *v = g_pend.vec;
     g_pend.x = nullptr;
     int grid = 0;
-    MG_TRY(comm_prepare(comm, x, v, v, &f->ex, &grid));
+    if (g_pend.prepared) {          // pushed by its producer: the site is booked, only the receiving half is left
+        g_pend.prepared = false;
+        f->ex = g_pend.ex;
+        grid = g_pend.grid;
+    } else {
+        MG_TRY(comm_prepare(comm, x, v, v, &f->ex, &grid));
+    }
     if (grid == 0) return MG_OK;
     f->nex = grid;
     f->mask = mask;
@@ -142,6 +161,13 @@ static inline int64_t vec_len(const mg_level &L) { return L.n + (L.dist ? L.dist
 static inline int halo_all(mg_comm *comm, const mg_level &L, double *v, cudaStream_t st) {
     if (!L.dist) return MG_OK;
     return comm_exchange(comm, L.dist->xfer_all, v, v, st);
+}
+
+// may the colour sweep over rows [r0,r1) of a partitioned level push its own boundary values?
+static inline bool can_push(const mg_level &L, int64_t r0, int64_t r1) {
+    const mg_dist_level *D = L.dist;
+    return g_push_exchange && g_fused_exchange && D && D->h_push_ptr && D->d_push_mask && D->d_push_row && D->d_push_peer &&
+           D->d_push_pos && r1 > r0 && sell_fusable(&L.A, r0, r1);
 }
 
 // `steps` smoothing sweeps on level L.  cur points at the buffer holding the iterate and is updated
@@ -183,9 +209,39 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
                 if (L.dist) {
                     SellFuse f;
                     bool use;
-                    MG_TRY(take_pending(comm, *cur, &L.A, L.h_color_ptr[c], L.h_color_ptr[c + 1], L.dist->d_mask_A, &f, &use, st));
-                    if (use) MG_TRY(sell_gs_rows_fused(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], &f, st));
-                    else MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
+                    const int64_t r0 = L.h_color_ptr[c], r1 = L.h_color_ptr[c + 1];
+                    MG_TRY(take_pending(comm, *cur, &L.A, r0, r1, L.dist->d_mask_A, &f, &use, st));
+                    if (can_push(L, r0, r1)) {
+                        // producer-driven: book this colour's site now (after the carried one, so that sites are
+                        // consumed in the order they were booked); the kernel below stores the boundary values into
+                        // the peers' staging slots itself and the next consumer only polls and unpacks
+                        const mg_dist_level &D = *L.dist;
+                        SellPush push;
+                        int grid = 0;
+                        MG_TRY(comm_prepare(comm, D.xfer_color + c, *cur, *cur, &push.ex, &grid));
+                        if (grid > 0) {
+                            push.mask = D.d_push_mask;
+                            push.rows = D.d_push_row + D.h_push_ptr[c];
+                            push.peer = D.d_push_peer + D.h_push_ptr[c];
+                            push.pos = D.d_push_pos + D.h_push_ptr[c];
+                            push.n = (int32_t)(D.h_push_ptr[c + 1] - D.h_push_ptr[c]);
+                            push.tail_first = D.h_push_tail ? (int32_t)D.h_push_tail[c] : 0;
+                            MG_TRY(sell_gs_rows_push(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, &push, st));
+                            g_pend.x = D.xfer_color + c;
+                            g_pend.vec = *cur;
+                            g_pend.prepared = true;
+                            g_pend.grid = grid;
+                            g_pend.ex = push.ex;
+                            g_pend.ex.recv_only = 1;
+                            continue;
+                        }
+                        // no peers on this site: nothing to push or to receive
+                        if (use) MG_TRY(sell_gs_rows_fused(&L.A, *cur, L.d_b, r0, r1, &f, st));
+                        else MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, st));
+                        continue;
+                    }
+                    if (use) MG_TRY(sell_gs_rows_fused(&L.A, *cur, L.d_b, r0, r1, &f, st));
+                    else MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, st));
                     MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
                 } else {
                     MG_TRY(op_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
@@ -328,6 +384,11 @@ int mg_set_fused_exchange(int enabled) {
     g_fused_exchange = enabled ? 1 : 0;
     return prev;
 }
+int mg_set_push_exchange(int enabled) {
+    const int prev = g_push_exchange;
+    g_push_exchange = enabled ? 1 : 0;
+    return prev;
+}
 int mg_set_pdl(int enabled) {
     const int prev = g_pdl;
     g_pdl = enabled ? 1 : 0;
@@ -380,6 +441,7 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     tail_stats_reset();
     MG_TRY(mg_comm_begin(comm));
     g_pend.x = nullptr;
+    g_pend.prepared = false;
     int rc = MG_OK;
     if (norm) {   // outer loop of Multigrid.solve (:62-63): ||b - A x||^2 over all row blocks
         MG_REQUIRE(norm->d_partials && norm->d_local && norm->d_slots && norm->d_norm2, "norm workspace missing");
@@ -389,6 +451,7 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     if (!rc && params) rc = vcycle_rec(comm, levels, nlevels, 0, *params, st);
     if (!rc) rc = flush_pending(comm, st);      // the halo of the iterate is current when the program ends
     g_pend.x = nullptr;
+    g_pend.prepared = false;
     if (!rc) rc = mg_comm_end(comm, stream);
     g_last_cycle_launches = g_launch_count - before;
     return rc;

@@ -140,6 +140,29 @@ sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, con
     sell_body<MODE, LEN, UNIFORM, true>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
 }
 
+// Colour sweep of a partitioned level that PUSHES its own boundary values (producer-driven exchange, exchange.cuh):
+// the compute CTAs run the rows next to the upper neighbour first (tail_first), every thread whose row is in the
+// colour's send table stores its new value straight into the peer's staging slot, and the NVLink flight overlaps the
+// interior rows of this very kernel.  CARRY: the launch also carries the previous site as extra CTAs, exactly like
+// sell_kernel_fused.  Opt-in (mg_set_push_exchange); same values, same packets, same receiving code.
+template <int LEN, bool UNIFORM, bool CARRY>
+__global__ void __launch_bounds__(kBlock)
+sell_gs_push_kernel(SellArgs A, double *x, const double *__restrict__ b, const ExArgs fx,
+                    const unsigned char *__restrict__ mask, const SellPush push) {
+    pdl_prologue();
+    const int nex = CARRY ? fx.npeers * fx.ctas_per_peer : 0;
+    if (CARRY && (int)blockIdx.x < nex) {
+        fused_exchange_cta(fx, (int)blockIdx.x);
+        return;
+    }
+    const int64_t nb = (int64_t)gridDim.x - nex;
+    int64_t bid = (int64_t)blockIdx.x - nex;
+    bid = bid < push.tail_first ? nb - 1 - bid : bid - push.tail_first;
+    sell_body<GS, LEN, UNIFORM, CARRY>(A, x, b, nullptr, x, 0.0, nullptr, bid, &fx, mask);
+    const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
+    if (row >= A.row_begin && row < A.row_end && !push.ex.dry && push.mask[row >> 5]) push_row_if_listed(push, row, x);
+}
+
 // ---- long rows: four warps per slice ---------------------------------------------------------------------------------
 // With 19- / 37-point Galerkin stencils (quasi-L2 transfers) one thread walking a whole row is a chain of dependent
 // (column -> x gather) round trips: ~15 us per launch however small, and half the DRAM rate on large levels.  Here
@@ -378,6 +401,56 @@ int sell_residual_fused(const mg_sell *A, const double *x, const double *b, doub
 int sell_gs_rows_fused(const mg_sell *A, double *x, const double *b, int64_t row0, int64_t row1, const SellFuse *f,
                        cudaStream_t st) {
     return launch_sell<GS>(A, x, b, nullptr, x, 0.0, nullptr, row0, row1, st, "sell_gs_rows", nullptr, f);
+}
+// colour sweep that pushes its own boundary values (carry: the previous site riding along, or NULL)
+int sell_gs_rows_push(const mg_sell *A, double *x, const double *b, int64_t row0, int64_t row1, const SellFuse *carry,
+                      const SellPush *push, cudaStream_t st) {
+    const char *name = "sell_gs_rows_push";
+    if (!push || !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot push an exchange site");
+    SellArgs a;
+    a.slice_ptr = A->d_slice_ptr;
+    a.cols = A->d_cols;
+    a.vals = A->d_vals;
+    a.row_begin = row0;
+    a.row_end = row1;
+    a.first_row = row0 & ~(int64_t)(kSlice - 1);
+    a.nrows = A->nrows;
+    const int64_t ml = A->max_slice_len;
+    const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
+    const int64_t grid = (row1 - a.first_row + kBlock - 1) / kBlock;
+    const int nex = carry ? carry->nex : 0;
+    if (grid + nex > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
+    SellPush p = *push;
+    if (p.tail_first < 0 || p.tail_first > grid / 2) p.tail_first = 0;
+    ExArgs none;
+    memset(&none, 0, sizeof(none));
+    const ExArgs &fx = carry ? carry->ex : none;
+    const unsigned char *mask = carry ? carry->mask : nullptr;
+#define MG_PUSH_CASE(L, U)                                                                                              \
+    do {                                                                                                                \
+        if (carry) launch_k(sell_gs_push_kernel<L, U, true>, (unsigned)(grid + nex), kBlock, st, a, x, b, fx, mask, p); \
+        else launch_k(sell_gs_push_kernel<L, U, false>, (unsigned)grid, kBlock, st, a, x, b, fx, mask, p);              \
+    } while (0)
+#define MG_PUSH_LEN(L)                  \
+    do {                                \
+        if (uni) MG_PUSH_CASE(L, true); \
+        else MG_PUSH_CASE(L, false);    \
+    } while (0)
+    switch (ml) {
+        case 1: MG_PUSH_LEN(1); break;
+        case 2: MG_PUSH_LEN(2); break;
+        case 3: MG_PUSH_LEN(3); break;
+        case 4: MG_PUSH_LEN(4); break;
+        case 5: MG_PUSH_LEN(5); break;
+        case 6: MG_PUSH_LEN(6); break;
+        case 7: MG_PUSH_LEN(7); break;
+        case 8: MG_PUSH_LEN(8); break;
+        default: MG_PUSH_CASE(0, false);
+    }
+#undef MG_PUSH_LEN
+#undef MG_PUSH_CASE
+    MG_CHECK_LAUNCH(name);
+    return MG_OK;
 }
 int sell_prolong_fused(const mg_sell *Q, const double *e, const double *u, double *uo, const SellFuse *f, cudaStream_t st) {
     return launch_sell<PROLONG>(Q, e, nullptr, u, uo, 0.0, nullptr, 0, Q->nrows, st, "sell_prolong", nullptr, f);

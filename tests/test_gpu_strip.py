@@ -89,3 +89,51 @@ def test_strip_hierarchy_is_bit_identical_to_the_single_gpu_cycle(torch_mod, smo
             assert np.array_equal(got, want)                           # bit for bit
         np.testing.assert_allclose(norms, want_n, rtol=1e-13)         # blockwise sum of the squares
         assert nnz[0] == [lv.nnz_A for lv in h.levels] and nnz[1] == [lv.nnz_Q for lv in h.levels[:-1]]
+
+
+@pytest.mark.parametrize("world,n_dist,use_graph", [(2, 2, True), (4, 2, True), (3, 1, False), (4, 3, True)])
+def test_producer_driven_exchange_is_bit_identical(torch_mod, world, n_dist, use_graph):
+    """mg_set_push_exchange(1) + send tables (DistributedHierarchy(push_exchange=True)): the colour sweeps store their
+    boundary values into the peers' staging slots themselves; iterates must equal the single-GPU cycle bit for bit,
+    over several programs (epoch parity), eagerly and from the captured graph"""
+    from learnmultigrid_b200 import _lib, formats as F, problems as P
+    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    lib = _lib.load()
+    N, levels, nu, cycles = 64, 4, 2, 4
+    A = F.canonical_csr(P.structured_laplacian_2d(N, P.variable_coefficient))
+    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, "linear")]
+    b = P.structured_rhs_2d(N)
+    x0 = np.random.default_rng(5).standard_normal((A.shape[0], 1))
+    h = DeviceHierarchy(A, Qs, smoother="mcgs")
+    h.set_rhs(b)
+    h.set_x(x0)
+    params = h.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
+    want = []
+    for _ in range(cycles):
+        h.vcycle(params)
+        want.append(h.get_x().copy())
+
+    def body(fab):
+        hd = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h.colors, n_dist=n_dist, region_bytes=1 << 20,
+                                  max_sites=256, timeout_s=30.0, push_exchange=True)
+        assert hd.levels[0].dist_struct.h_push_ptr and hd.levels[0].dist_struct.d_push_mask
+        hd.set_rhs(b)
+        hd.set_x(x0)
+        p = hd.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
+        xs = []
+        for _ in range(cycles):
+            hd.vcycle(p, use_graph=use_graph, with_norm=True)
+            xs.append(hd.get_x().copy())
+        hd.check()
+        hd.close()
+        return xs
+
+    prev = lib.mg_set_push_exchange(1)
+    try:
+        res = run_virtual_ranks(world, body)
+    finally:
+        lib.mg_set_push_exchange(prev)
+    for xs in res:
+        for got, w in zip(xs, want):
+            assert np.array_equal(got, w)
