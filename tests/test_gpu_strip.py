@@ -137,3 +137,51 @@ def test_producer_driven_exchange_is_bit_identical(torch_mod, world, n_dist, use
     for xs in res:
         for got, w in zip(xs, want):
             assert np.array_equal(got, w)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_producer_driven_exchange_with_split_bcr_coarsest_level(torch_mod, world):
+    """the split reduction levels of the block-cyclic-reduction coarsest solve push their all-gather messages from the
+    forward / backward kernels (bcr_*_push_kernel): same iterates as the single-GPU cycle, bit for bit"""
+    from learnmultigrid_b200 import _lib, problems as P
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
+    lib = _lib.load()
+    N = 64
+    A = P.structured_laplacian_2d(N)
+    Qs = P.structured_hierarchy_2d(N, 2, transfer="linear")          # coarsest = 33^2 = 1089 unknowns -> BCR
+    rng = np.random.default_rng(0)
+    b, x0 = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
+    h1 = DeviceHierarchy(A, Qs, smoother="mcgs", dense_coarse_max=500)
+    assert h1.levels[-1].coarse_kind == 1
+    h1.set_rhs(b)
+    h1.set_x(x0)
+    p1 = h1.make_params(nu_pre=1, nu_post=1)
+    want = []
+    for _ in range(4):
+        h1.vcycle(p1)
+        want.append(h1.get_x().copy())
+
+    def body(fab):
+        h = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h1.colors, n_dist=1, dense_coarse_max=500,
+                                 bcr_split_min_blocks=2, region_bytes=1 << 20, timeout_s=30.0, push_exchange=True)
+        assert h.levels[-1].coarse_bcr_dist is not None
+        h.set_rhs(b)
+        h.set_x(x0)
+        p = h.make_params(nu_pre=1, nu_post=1)
+        got = []
+        for _ in range(4):
+            h.vcycle(p)
+            got.append(h.get_x().copy())
+        h.check()
+        h.close()
+        return got
+
+    prev = lib.mg_set_push_exchange(1)
+    try:
+        res = run_virtual_ranks(world, body)
+    finally:
+        lib.mg_set_push_exchange(prev)
+    for got in res:
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
