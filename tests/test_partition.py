@@ -357,12 +357,18 @@ def test_partitioned_sweeps_on_random_unstructured_graphs(seed, size):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("world,N", [(2, 16), (4, 64), (3, 40)])
+@pytest.mark.parametrize("world,N", [(2, 16), (4, 64), (3, 40), (5, 0), (8, -1)])
 def test_push_tables_reproduce_the_colour_exchange(world, N):
     """partition.push_tables (send tables of the producer-driven exchange): storing every listed row's value into slot
     `pos` of the message to peer `peer` fills each message completely, exactly once, with what the receiver's halo
-    expects; the slice mask covers the listed rows; the rows sent to a higher rank lie in the last `tail` CTAs"""
-    A = F.canonical_csr(poisson2d(N))
+    expects; the slice mask covers the listed rows; the rows sent to a higher rank lie in the last `tail` CTAs.
+    N <= 0: a random unstructured graph, where a row goes to several peers and every rank neighbours every other"""
+    if N > 0:
+        A = F.canonical_csr(poisson2d(N))
+    else:
+        n = 300 - 60 * N
+        S = sp.random(n, n, density=0.03, random_state=7 - N, format="csr")
+        A = F.canonical_csr(sp.csr_matrix(S + S.T + sp.diags(np.full(n, 9.0))))
     colors, nc = F.greedy_colors(A)
     offs, plans = plans_for(A, world, colors)
     rng = np.random.default_rng(4)
