@@ -489,7 +489,10 @@ def run_b200(a):
                                                                               len(l.color_ptr) - 1 for l in h.levels],
                            "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2), "nn_builder": NN_BUILD.get(n),
                            "residual_after_timed_steps": res_after,
-                           "ms_per_step_without_exchange_waits": ms_dry, "parallelism": ("row-partitioned x%d, levels 0..%d partitioned, %d replicated, halo exchange by peer-memory "
+                           "ms_per_step_without_exchange_waits": ms_dry,
+                           "exchange": (("producer-driven (MGB_PUSH_EXCHANGE=1)" if getattr(h, "push_exchange", False)
+                                         else "consumer-driven") if part else None),
+                           "parallelism": ("row-partitioned x%d, levels 0..%d partitioned, %d replicated, halo exchange by peer-memory "
                                            "stores over NVLink inside the cycle graph" % (world, h.n_dist - 1, a.levels - h.n_dist))
                            if part else ("replicas" if world > 1 else "single")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches_per_step * a.steps,
