@@ -442,6 +442,18 @@ int mg_host_greedy_color(int64_t n, const int32_t *h_indptr, const int32_t *h_in
 int mg_host_greedy_color_block(int64_t n_own, int64_t n_ext, const int32_t *h_indptr, const int32_t *h_indices,
                                const int32_t *h_ext_color, uint64_t *h_forbidden_lo, uint64_t *h_forbidden_hi,
                                int32_t *h_colors, int phase);
+/* The colouring of mg_host_greedy_color computed on the device (csrc/color_kernels.cu): rounds of a Jones-Plassmann
+ * sweep whose priority is the row's place in the first-fit order, on the patterns of A and A^T (device CSR index arrays).
+ * Identical colours, entry for entry.  d_work: mg_color_workspace_size(n) bytes.  A setup-time call: it synchronises the
+ * stream every 128 rounds.  MG_ERR_UNSUPPORTED if more than max_rounds rounds (long dependency chains, e.g. a 1D mesh
+ * numbered end to end: use the host helper) or more than 128 colours would be needed. */
+int64_t mg_color_workspace_size(int64_t n);
+int mg_color_first_fit(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const int32_t *d_t_indptr,
+                       const int32_t *d_t_indices, int32_t *d_colors, void *d_work, int64_t work_bytes,
+                       int64_t max_rounds, int64_t *h_rounds, void *stream);
+/* the same rounds run serially on HOST arrays with the same per-row code (CPU test-suite; not called by the product) */
+int mg_host_color_rounds(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, const int32_t *h_t_indptr,
+                         const int32_t *h_t_indices, int32_t *h_colors, void *h_work, int64_t *h_rounds);
 /* dependency level of every row for an exact index-order sweep (see mg_gs_lex_sweep_csr); returns nlevels */
 int64_t mg_host_lex_levels(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_level);
 

@@ -234,3 +234,25 @@ def build_host_hierarchy(A, Q_list, smoother, colors=None, with_sell=True):
             for k in ("A", "Q", "QT"):
                 d[k + "_sell"] = csr_to_sell(d[k])
     return levels
+
+
+def greedy_colors_by_rounds(A):
+    """The colouring of greedy_colors evaluated by dependency rounds (csrc/color_kernels.cu, host emulation of the
+    device algorithm with the same per-row code): (colours, number of colours, rounds).  Test infrastructure for the
+    device colouring; the product calls setup_device.DeviceSetup.first_fit_colors."""
+    A = canonical_csr(A)
+    n = A.shape[0]
+    T = sp.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape).T.tocsr()
+    T.sort_indices()
+    tip, tix = T.indptr.astype(np.int32), T.indices.astype(np.int32)
+    lib = _lib.load()
+    colors = np.empty(max(n, 1), dtype=np.int32)
+    work = np.zeros(int(lib.mg_color_workspace_size(n)), dtype=np.uint8)
+    import ctypes
+    rounds = ctypes.c_int64(0)
+    rc = lib.mg_host_color_rounds(n, A.indptr.ctypes.data, A.indices.ctypes.data, tip.ctypes.data, tix.ctypes.data,
+                                  colors.ctypes.data, work.ctypes.data, ctypes.byref(rounds))
+    if rc:
+        _lib.check(rc, "mg_host_color_rounds")
+    colors = colors[:n]
+    return colors, (int(colors.max()) + 1 if n else 0), int(rounds.value)

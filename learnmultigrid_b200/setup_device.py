@@ -4,6 +4,7 @@ the device buffers.  The host path (formats.build_host_hierarchy) produces the s
 what the GPU tests compare this against.
 """
 import ctypes
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -207,6 +208,23 @@ class DeviceSetup:
                    "mg_extract_dinv")
         return out
 
+    def first_fit_colors(self, A, max_rounds=400000):
+        """The colours of formats.greedy_colors computed on the device (csrc/color_kernels.cu: dependency rounds on the
+        patterns of A and A^T); returns a host int32 array.  Raises MgError (UNSUPPORTED) when the dependency chains
+        are too long for the round-based algorithm -- the caller then uses the host helper."""
+        t = self.torch
+        n = A.shape[0]
+        AT = self.transpose(A)
+        colors = self.empty(n, t.int32)
+        nb = int(self.lib.mg_color_workspace_size(n))
+        work = self.temp(nb)
+        rounds = ctypes.c_int64(0)
+        _lib.check(self.lib.mg_color_first_fit(n, A.indptr.data_ptr(), A.indices.data_ptr(), AT.indptr.data_ptr(),
+                                               AT.indices.data_ptr(), colors.data_ptr(), work.data_ptr(), nb,
+                                               int(max_rounds), ctypes.byref(rounds), self.st()), "mg_color_first_fit")
+        self.last_color_rounds = int(rounds.value)
+        return colors.cpu().numpy()
+
     def color_perm(self, colors_host):
         """device perm (new -> old, stable by colour), inverse perm, host colour offsets"""
         t = self.torch
@@ -260,9 +278,17 @@ def level_colors(S, smoother, colors, A_host0, A_nat):
             if colors is not None and colors[l] is not None:
                 col = np.ascontiguousarray(colors[l], dtype=np.int32)
             else:
-                pat = A_host0 if (l == 0 and A_host0 is not None) else F.raw_csr(
-                    A_nat[l].indptr.cpu().numpy(), A_nat[l].indices.cpu().numpy(), np.zeros(A_nat[l].nnz), A_nat[l].shape)
-                col = F.greedy_colors(pat)[0]
+                col = None
+                if os.environ.get("MGB_DEVICE_COLORS", "0") == "1":      # opt-in until it has run on a GPU
+                    try:
+                        col = S.first_fit_colors(A_nat[l])
+                    except _lib.MgError:
+                        col = None                                       # chains too long: serial helper below
+                if col is None:
+                    pat = A_host0 if (l == 0 and A_host0 is not None) else F.raw_csr(
+                        A_nat[l].indptr.cpu().numpy(), A_nat[l].indices.cpu().numpy(), np.zeros(A_nat[l].nnz),
+                        A_nat[l].shape)
+                    col = F.greedy_colors(pat)[0]
             out.append(col)
         else:
             out.append(None)

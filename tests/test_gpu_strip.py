@@ -185,3 +185,31 @@ def test_producer_driven_exchange_with_split_bcr_coarsest_level(torch_mod, world
     for got in res:
         for g, w in zip(got, want):
             assert np.array_equal(g, w)
+
+
+def test_device_first_fit_colouring_equals_the_host_helper(torch_mod):
+    """csrc/color_kernels.cu: the round-based colouring on the device gives the colours of formats.greedy_colors, entry
+    for entry (structured operator with identity rows, 7- / 19-point Galerkin levels, unstructured numbering, a random
+    unsymmetric pattern); a 1D chain exceeds the round limit and reports UNSUPPORTED"""
+    import scipy.sparse as sp
+    from learnmultigrid_b200 import _lib, formats as F, problems as P, setup_device as SD
+    torch = torch_mod
+    S = SD.DeviceSetup(torch, torch.device("cuda", 0))
+    N = 128
+    A = F.canonical_csr(P.structured_laplacian_2d(N, P.variable_coefficient))
+    mats = [A]
+    for transfer in ("linear", "quasi"):
+        Q = F.canonical_csr(P.structured_hierarchy_2d(N, 2, transfer)[0])
+        mats.append(F.canonical_csr(sp.csr_matrix(Q.T @ sp.csc_matrix(A) @ Q)))
+    mats.append(F.canonical_csr(P.irregular_p1_2d(64)["A"]))
+    mats.append(F.canonical_csr(sp.random(3000, 3000, density=0.003, random_state=1, format="csr")
+                                + sp.diags((np.arange(3000) % 5 > 0) * 1.0)))
+    for M in mats:
+        want, nc = F.greedy_colors(M)
+        got = S.first_fit_colors(S.upload(M))
+        assert np.array_equal(got, want)
+        assert S.last_color_rounds >= 1
+    chain = F.canonical_csr(sp.diags([np.ones(4999), 2 * np.ones(5000), np.ones(4999)], [-1, 0, 1], format="csr"))
+    with pytest.raises(_lib.MgError):
+        S.first_fit_colors(S.upload(chain), max_rounds=1000)
+    assert np.array_equal(S.first_fit_colors(S.upload(chain), max_rounds=6000), F.greedy_colors(chain)[0])

@@ -299,3 +299,36 @@ def test_interface_helpers_of_the_assembly_and_mesh_mirror():
     fine = Mesh1DRefinement(3, 2)
     fine.construct()
     assert fine.get_ne() == 12 and fine.get_np() == 13 and fine.get_connections().shape == (12, 2)
+
+
+def test_round_based_colouring_equals_the_serial_first_fit():
+    """csrc/color_kernels.cu (the device colouring) run as a serial host emulation with the kernels' per-row code:
+    identical colours to mg_host_greedy_color on structured operators with identity rows, Galerkin levels (7-, 19-,
+    37-point), unsymmetric random patterns, empty rows, and beyond 64 colours; the number of rounds is the length of
+    the longest dependency chain (two grid widths on a row-major grid)"""
+    from learnmultigrid_b200 import _lib, problems as P
+    N = 24
+    A = P.structured_laplacian_2d(N)
+    mats = [A]
+    for transfer in ("linear", "quasi"):
+        cur = sp.csc_matrix(A)
+        for Q in P.structured_hierarchy_2d(N, 3, transfer):
+            cur = sp.csr_matrix(Q.T @ cur @ Q)
+            mats.append(cur)
+    mats.append(sp.random(200, 200, density=0.04, random_state=3, format="csr") + sp.diags((np.arange(200) % 4 > 0) * 1.0))
+    C = sp.lil_matrix((100, 100))
+    C[:70, :70] = 1.0
+    C[70:, 3] = 1.0
+    C.setdiag(1.0)
+    C[95, :] = 0.0
+    mats.append(C.tocsr())                                        # 70 colours, one-directional couplings, an empty row
+    for M in mats:
+        M = F.canonical_csr(M)
+        want, nc = F.greedy_colors(M)
+        got, nc2, rounds = F.greedy_colors_by_rounds(M)
+        assert np.array_equal(got, want) and nc2 == nc
+        assert 1 <= rounds <= M.shape[0]
+    _, _, rounds = F.greedy_colors_by_rounds(A)
+    assert rounds <= 2 * (N + 1) + 2                              # anti-diagonal wavefronts + the identity rows
+    with pytest.raises(_lib.MgError):
+        F.greedy_colors_by_rounds(F.canonical_csr(sp.csr_matrix(np.ones((130, 130)))))
