@@ -248,7 +248,6 @@ def greedy_colors_by_rounds(A):
     lib = _lib.load()
     colors = np.empty(max(n, 1), dtype=np.int32)
     work = np.zeros(int(lib.mg_color_workspace_size(n)), dtype=np.uint8)
-    import ctypes
     rounds = ctypes.c_int64(0)
     rc = lib.mg_host_color_rounds(n, A.indptr.ctypes.data, A.indices.ctypes.data, tip.ctypes.data, tix.ctypes.data,
                                   colors.ctypes.data, work.ctypes.data, ctypes.byref(rounds))
