@@ -155,3 +155,12 @@ def emulate_vcycle(levels, smoother, nu_pre, nu_post, omega, x0, b0, zero_guess_
 
     rec(0)
     return xs[0]
+
+
+def free_port():
+    """a TCP port that is free right now (torchrun rendezvous: back-to-back runs must not collide in TIME_WAIT)"""
+    import socket
+    with socket.socket() as sock:
+        sock.bind(("127.0.0.1", 0))
+        return str(sock.getsockname()[1])
+

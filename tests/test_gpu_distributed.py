@@ -13,7 +13,7 @@ import sys
 import numpy as np
 import pytest
 
-from helpers import bilinear_P, poisson2d
+from helpers import bilinear_P, free_port, poisson2d
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -300,7 +300,7 @@ def test_two_process_torchrun_over_cuda_ipc(torch_mod):
         pytest.skip("needs >= 2 GPUs (run with gpurun --gpus 2)")
     env = dict(os.environ, OMP_NUM_THREADS="1")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
-           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "tools", "dist_check.py"), "--size", "128"]
+           "127.0.0.1", "--master-port", free_port(), os.path.join(ROOT, "tools", "dist_check.py"), "--size", "128"]
     out = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
     assert "DIST_CHECK_OK" in out.stdout, out.stdout[-4000:]
 

@@ -11,7 +11,7 @@ import scipy.sparse as sp
 
 from learnmultigrid_b200 import formats as F
 from learnmultigrid_b200 import partition as PT
-from helpers import poisson2d
+from helpers import free_port, poisson2d
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -168,7 +168,7 @@ def test_two_process_gloo_halo_exchange(tmp_path):
     script.write_text(WORKER)
     env = dict(os.environ, MGB_ROOT=ROOT, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29531", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", free_port(), str(script)],
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
     assert "PARTITION_OK" in out.stdout, out.stdout[-3000:]
 
@@ -307,7 +307,7 @@ def test_two_process_gloo_partitioned_vcycle(tmp_path):
     script.write_text(VCYCLE_WORKER)
     env = dict(os.environ, MGB_ROOT=ROOT, OMP_NUM_THREADS="1")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                          "--master-addr", "127.0.0.1", "--master-port", free_port(), str(script)],
                          env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
     assert "VCYCLE_PARTITION_OK" in out.stdout, out.stdout[-4000:]
 
