@@ -22,6 +22,8 @@ int sell_gs_rows_fused(const mg_sell *, double *, const double *, int64_t, int64
 int sell_prolong_fused(const mg_sell *, const double *, const double *, double *, const SellFuse *, cudaStream_t);
 int sell_gs_rows_push(const mg_sell *, double *, const double *, int64_t, int64_t, const SellFuse *, const SellPush *, cudaStream_t);
 int comm_launch_prepared(const ExArgs &, int, cudaStream_t);
+int sell_residual_partials(const mg_sell *, const double *, const double *, double *, int *, cudaStream_t);
+int comm_norm_allreduce(mg_comm *, const double *, int64_t, double *, double *, double *, cudaStream_t);
 int g_fused_exchange = 1;
 int g_push_exchange = 0;     // producer-driven colour exchanges (mg_set_push_exchange); off by default
 
@@ -445,8 +447,15 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     int rc = MG_OK;
     if (norm) {   // outer loop of Multigrid.solve (:62-63): ||b - A x||^2 over all row blocks
         MG_REQUIRE(norm->d_partials && norm->d_local && norm->d_slots && norm->d_norm2, "norm workspace missing");
-        rc = sell_residual_norm2(&levels[0].A, levels[0].d_x, levels[0].d_b, norm->d_partials, norm->d_local, st);
-        if (!rc) rc = mg_comm_allreduce_sum(comm, norm->d_local, norm->d_slots, norm->d_norm2, stream);
+        if (g_push_exchange && comm->world > 1 && levels[0].A.nrows > 0) {
+            // latency mode: the second stage of the norm and its all-reduce are one single-CTA kernel
+            int nblocks = 0;
+            rc = sell_residual_partials(&levels[0].A, levels[0].d_x, levels[0].d_b, norm->d_partials, &nblocks, st);
+            if (!rc) rc = comm_norm_allreduce(comm, norm->d_partials, nblocks, norm->d_local, norm->d_slots, norm->d_norm2, st);
+        } else {
+            rc = sell_residual_norm2(&levels[0].A, levels[0].d_x, levels[0].d_b, norm->d_partials, norm->d_local, st);
+            if (!rc) rc = mg_comm_allreduce_sum(comm, norm->d_local, norm->d_slots, norm->d_norm2, stream);
+        }
     }
     if (!rc && params) rc = vcycle_rec(comm, levels, nlevels, 0, *params, st);
     if (!rc) rc = flush_pending(comm, st);      // the halo of the iterate is current when the program ends

@@ -465,6 +465,11 @@ int sell_residual_norm2(const mg_sell *A, const double *x, const double *b, doub
     MG_CHECK_LAUNCH("reduce_partials");
     return MG_OK;
 }
+// first stage only: per-block partial sums of ||b - A x||^2 (the partitioned norm adds its own second stage, comm.cu)
+int sell_residual_partials(const mg_sell *A, const double *x, const double *b, double *partials, int *nblocks,
+                           cudaStream_t st) {
+    return launch_sell<RESNORM>(A, x, b, nullptr, nullptr, 0.0, partials, 0, A->nrows, st, "sell_residual_partials", nblocks);
+}
 int sell_jacobi(const mg_sell *A, const double *dinv, const double *x, const double *b, double *xo,
                 double omega, cudaStream_t st) {
     return launch_sell<JACOBI>(A, x, b, dinv, xo, omega, nullptr, 0, A->nrows, st, "sell_jacobi");

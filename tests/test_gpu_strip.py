@@ -109,8 +109,9 @@ def test_producer_driven_exchange_is_bit_identical(torch_mod, world, n_dist, use
     h.set_rhs(b)
     h.set_x(x0)
     params = h.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
-    want = []
+    want, want_norms = [], []
     for _ in range(cycles):
+        want_norms.append(h.residual_norm())
         h.vcycle(params)
         want.append(h.get_x().copy())
 
@@ -121,22 +122,25 @@ def test_producer_driven_exchange_is_bit_identical(torch_mod, world, n_dist, use
         hd.set_rhs(b)
         hd.set_x(x0)
         p = hd.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
-        xs = []
+        xs, norms = [], []
         for _ in range(cycles):
-            hd.vcycle(p, use_graph=use_graph, with_norm=True)
+            hd.vcycle(p, use_graph=use_graph, with_norm=True)       # norm + all-reduce in one kernel in this mode
+            norms.append(hd.last_norm())
             xs.append(hd.get_x().copy())
         hd.check()
         hd.close()
-        return xs
+        return xs, norms
 
     prev = lib.mg_set_push_exchange(1)
     try:
         res = run_virtual_ranks(world, body)
     finally:
         lib.mg_set_push_exchange(prev)
-    for xs in res:
+    for xs, norms in res:
         for got, w in zip(xs, want):
             assert np.array_equal(got, w)
+        np.testing.assert_allclose(norms, want_norms, rtol=1e-13)
+        assert norms == res[0][1]                                   # identical bits on every rank
 
 
 @pytest.mark.parametrize("world", [2, 3])
