@@ -542,3 +542,39 @@ def test_rectangular_strip_generators_match_the_assembly(Nx, Ny):
     offs, res = strip_run(G, Qs, 3)
     for l in range(3):
         same(sp.vstack([res[r][0][l] for r in range(3)], format="csr"), want[l])
+
+
+@pytest.mark.parametrize("seed,world", [(0, 2), (1, 3), (2, 5), (3, 7)])
+def test_strip_hierarchy_on_random_unstructured_operators(seed, world):
+    """no grid structure at all: random sparse A (unsymmetric, empty rows) and random transfers with empty rows and
+    columns; couplings cross every block boundary, some ranks fetch from all others; two levels of Galerkin products,
+    transposes and the composed setup (colours, plans) against the global computation"""
+    rng = np.random.default_rng(seed)
+    n0, n1, n2 = 230 + 17 * seed, 71 + 5 * seed, 19 + seed
+    A = sp.random(n0, n0, density=0.03, random_state=seed, format="csr") + sp.diags((np.arange(n0) % 7 > 0) * 3.0)
+    Q0 = sp.random(n0, n1, density=0.05, random_state=seed + 10, format="csr")
+    Q1 = sp.random(n1, n2, density=0.15, random_state=seed + 20, format="csr")
+    A, Qs = F.canonical_csr(A), [F.canonical_csr(Q0), F.canonical_csr(Q1)]
+    want = global_hierarchy(A, Qs)
+    offs, res = strip_run(A, Qs, world)
+    for l in range(3):
+        same(sp.vstack([res[r][0][l] for r in range(world)], format="csr"), want[l])
+    for l, Q in enumerate(Qs):
+        same(sp.vstack([res[r][1][l] for r in range(world)], format="csr"), F.canonical_csr(sp.csr_matrix(Q.T)))
+
+    def body(fab):
+        r = fab.rank
+        return PS.strip_local_setup(fab, A[offs[0][r]:offs[0][r + 1]],
+                                    [q[offs[l][r]:offs[l][r + 1]] for l, q in enumerate(Qs)], offs, 2, "mcgs")
+    QTs = [F.canonical_csr(sp.csr_matrix(q.T)) for q in Qs]
+    for r, (levs, A_rep, Q_rep) in enumerate(run_ranks(world, body)):
+        same(A_rep, want[2])
+        assert Q_rep == []
+        for l, lv in enumerate(levs):
+            colors = F.greedy_colors(want[l])[0]
+            assert np.array_equal(lv.colors, colors[offs[l][r]:offs[l][r + 1]])
+            ext = PT.level_external_columns(want[l], QTs[l], Qs[l - 1] if l else None, offs[l], offs[l + 1],
+                                            offs[l - 1] if l else None, r)
+            ref = PT.RankPlan(offs[l], r, ext, colors)
+            assert np.array_equal(lv.plan.halo_gid, ref.halo_gid) and lv.plan.seg_color == ref.seg_color
+            assert np.array_equal(lv.plan.perm, ref.perm)
