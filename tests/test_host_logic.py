@@ -332,3 +332,31 @@ def test_round_based_colouring_equals_the_serial_first_fit():
     assert rounds <= 2 * (N + 1) + 2                              # anti-diagonal wavefronts + the identity rows
     with pytest.raises(_lib.MgError):
         F.greedy_colors_by_rounds(F.canonical_csr(sp.csr_matrix(np.ones((130, 130)))))
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_sell_layout_on_ragged_and_empty_inputs(seed):
+    """SELL-32 host layout (the cross-check of the device builder) on random ragged matrices: row counts that are not
+    multiples of 32, empty rows, one empty matrix, a single row; every row sum equals CSR's in the same order, padding
+    has value 0 and a valid column"""
+    rng = np.random.default_rng(seed)
+    shapes = [(1, 5), (31, 40), (33, 7), (64, 64), (100, 90), (5, 200)]
+    for (n, m) in shapes:
+        A = sp.random(n, m, density=rng.uniform(0.02, 0.4), random_state=seed * 7 + n, format="lil")
+        for r in rng.integers(0, n, size=max(n // 5, 1)):
+            A[int(r), :] = 0                                   # empty rows
+        A = F.canonical_csr(sp.csr_matrix(A))
+        A.eliminate_zeros()
+        slice_ptr, cols, vals = F.csr_to_sell(A)
+        assert len(slice_ptr) == (n + 31) // 32 + 1 and slice_ptr[0] == 0 and np.all(np.diff(slice_ptr) % 32 == 0)
+        assert len(cols) == len(vals) == slice_ptr[-1]
+        assert np.all((cols >= 0) & (cols < m)) or slice_ptr[-1] == 0
+        assert np.count_nonzero(vals) == np.count_nonzero(A.data)
+        x = rng.standard_normal(m)
+        want = np.array([np.sum(A.data[A.indptr[i]:A.indptr[i + 1]] * x[A.indices[A.indptr[i]:A.indptr[i + 1]]]
+                                * 1.0) if A.indptr[i + 1] > A.indptr[i] else 0.0 for i in range(n)])
+        got = sell_rowsum((slice_ptr, cols, vals), n, x)
+        np.testing.assert_allclose(got, want, rtol=1e-14, atol=1e-15)
+    empty = F.canonical_csr(sp.csr_matrix((0, 4)))
+    sp0, c0, v0 = F.csr_to_sell(empty)
+    assert len(sp0) == 1 and len(c0) == 0 and len(v0) == 0
