@@ -96,9 +96,18 @@ typedef struct {
     int64_t max_slice_len;      /* longest slice (entries per row); 0 = unknown (generic kernel)           */
     int64_t uniform_len;        /* > 0: EVERY slice has exactly this many entries per row (= max_slice_len), so
                                    slice offsets are computed, not loaded; 0 = lengths vary, use d_slice_ptr */
+    const int32_t *d_slice_off; /* optional (NULL: none): [nslices][uniform_len] column offsets relative to the row
+                                   for slices in which every row has the columns row + off[j]; filled by
+                                   mg_sell_slice_offsets, used when mg_set_implied_columns(1) */
 } mg_sell;
 
 /* y = A x  (rows [row0,row1)) */
+/* Implied columns (opt-in, default 0; results identical): on a uniform matrix with <= 8 entries per row, slices whose
+ * 32 rows all have the columns row + off[j] (structured stencil levels: all slices but those holding a boundary node)
+ * read 4 bytes of offset per entry index instead of 128 bytes of column indices.  mg_sell_slice_offsets fills
+ * d_off[nslices * uniform_len] (irregular slices: d_off[s * len] = INT32_MIN); point mg_sell.d_slice_off at it. */
+int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, void *stream);
+int mg_set_implied_columns(int enabled);
 int mg_sell_spmv(const mg_sell *A, const double *d_x, double *d_y, void *stream);
 /* r = b - A x */
 int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, double *d_r, void *stream);

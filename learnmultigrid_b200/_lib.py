@@ -29,7 +29,7 @@ class MgError(RuntimeError):
 class mg_sell(ctypes.Structure):
     _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nslices", c_i64),
                 ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp), ("max_slice_len", c_i64),
-                ("uniform_len", c_i64)]
+                ("uniform_len", c_i64), ("d_slice_off", c_vp)]
 
 
 class mg_bcr(ctypes.Structure):
@@ -107,6 +107,8 @@ _SIGNATURES = {
     "mg_gs_lex_sweep_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
     "mg_prolong_correct_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_sell_spmv": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
+    "mg_sell_slice_offsets": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp]),
+    "mg_set_implied_columns": (c_int, [c_int]),
     "mg_sell_residual": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
     "mg_sell_residual_norm2": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_norm_workspace_size": (c_i64, [c_i64]),
@@ -243,6 +245,8 @@ def load():
         lib.mg_set_fused_exchange(0)
     if os.environ.get("MGB_PUSH_EXCHANGE", "0") == "1":
         lib.mg_set_push_exchange(1)
+    if os.environ.get("MGB_IMPLIED_COLUMNS", "0") == "1":
+        lib.mg_set_implied_columns(1)
     if "MGB_WIDE_MIN_LEN" in os.environ:
         lib.mg_set_wide_min_len(int(os.environ["MGB_WIDE_MIN_LEN"]))
     if "MGB_TAIL_MAX_ROWS" in os.environ:

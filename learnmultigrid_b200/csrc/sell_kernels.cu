@@ -140,6 +140,95 @@ sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, con
     sell_body<MODE, LEN, UNIFORM, true>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
 }
 
+// ---- implied columns ------------------------------------------------------------------------------------------------
+// On a structured stencil level nearly every slice is REGULAR: entry j of every one of its 32 rows has column
+// row + off[j] with ONE offset table for the slice (mg_sell_slice_offsets; formats.sell_slice_offsets is the host twin).
+// For those slices the kernel below computes the columns instead of streaming them: 4*LEN bytes of offsets per slice
+// in place of 128*LEN bytes of column indices, i.e. 64 instead of 88 bytes per 5-point row.  The values, the gathers
+// and the order of the additions are untouched, so the results are the same bits; slices that are not regular (a
+// boundary node among the rows, the ragged tail) take the ordinary path inside the same kernel.  Uniform matrices
+// with at most 8 entries per row only; opt-in (mg_set_implied_columns) until it has been measured.
+constexpr int32_t kSliceIrregular = INT32_MIN;
+static int g_implied_columns = 0;
+
+__global__ void __launch_bounds__(kBlock)
+sell_slice_offsets_kernel(int64_t nslices, int64_t nrows, int len, const int32_t *__restrict__ cols,
+                          int32_t *__restrict__ off) {
+    const int64_t w = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (w >= nslices) return;
+    const int64_t row = w * kSlice + lane;
+    bool regular = (w + 1) * kSlice <= nrows;
+    for (int j = 0; j < len; ++j) {
+        const int64_t rel = (int64_t)cols[(w * len + j) * kSlice + lane] - row;
+        const int64_t rel0 = __shfl_sync(0xffffffffu, rel, 0);
+        regular = __all_sync(0xffffffffu, rel == rel0) && regular;
+        if (lane == 0) off[w * len + j] = (int32_t)rel0;
+    }
+    if (lane == 0 && !regular) off[w * len] = kSliceIrregular;
+}
+
+template <int MODE, int LEN>
+__global__ void __launch_bounds__(kBlock)
+sell_kernel_reg(SellArgs A, const int32_t *__restrict__ soff, const double *x, const double *__restrict__ b,
+                const double *aux, double *y, double omega, double *__restrict__ partials) {
+    pdl_prologue();
+    const int64_t row = A.first_row + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const bool active = row >= A.row_begin && row < A.row_end;
+    double contrib = 0.0;
+    if (row < A.row_end) {
+        const int64_t slice = row >> 5;
+        const int lane = (int)(row & 31);
+        const int64_t base = slice * (int64_t)(kSlice * LEN);
+        const double *__restrict__ v = A.vals + base + lane;
+        const int32_t *__restrict__ o = soff + slice * LEN;
+        double sum = 0.0, diag = 0.0;
+        const int32_t o0 = __ldg(o);
+        if (o0 != kSliceIrregular) {          // warp-uniform
+            int32_t cc[LEN];
+            double vv[LEN], xx[LEN];
+#pragma unroll
+            for (int j = 0; j < LEN; ++j) vv[j] = ld_stream(v + j * kSlice);
+            cc[0] = (int32_t)row + o0;
+#pragma unroll
+            for (int j = 1; j < LEN; ++j) cc[j] = (int32_t)row + __ldg(o + j);
+#pragma unroll
+            for (int j = 0; j < LEN; ++j) xx[j] = x[cc[j]];
+#pragma unroll
+            for (int j = 0; j < LEN; ++j) {
+                if (MODE == GS) {
+                    if (cc[j] == row) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
+                } else {
+                    sum = mul_add_unfused(sum, vv[j], xx[j]);
+                }
+            }
+        } else {
+            row_chunk<MODE, LEN>(A.cols + base + lane, v, x, row, sum, diag);
+        }
+        if (active) {      // the epilogues of sell_body
+            if (MODE == SPMV) {
+                y[row] = sum;
+            } else if (MODE == RESID) {
+                y[row] = __dsub_rn(b[row], sum);
+            } else if (MODE == RESNORM) {
+                const double r = __dsub_rn(b[row], sum);
+                contrib = r * r;
+            } else if (MODE == JACOBI) {
+                const double r = __dsub_rn(b[row], sum);
+                y[row] = __dadd_rn(x[row], __dmul_rn(omega, __dmul_rn(aux[row], r)));
+            } else if (MODE == GS) {
+                if (diag != 0.0) y[row] = __ddiv_rn(__dsub_rn(b[row], sum), diag);
+            } else if (MODE == PROLONG) {
+                y[row] = __dadd_rn(aux[row], sum);
+            }
+        }
+    }
+    if (MODE == RESNORM) {
+        const double s = block_sum<kBlock>(contrib);
+        if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    }
+}
+
 // Colour sweep of a partitioned level that PUSHES its own boundary values (producer-driven exchange, exchange.cuh):
 // the compute CTAs run the rows next to the upper neighbour first (tail_first), every thread whose row is in the
 // colour's send table stores its new value straight into the peer's staging slot, and the NVLink flight overlaps the
@@ -358,6 +447,18 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     }
     const int64_t grid = (nthreads + kBlock - 1) / kBlock;
     if (grid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
+    if (g_implied_columns && !fuse && uni && A->d_slice_off && ml >= 1 && ml <= 8) {      // see sell_kernel_reg
+#define MG_REG_CASE(L) \
+    case L: launch_k(sell_kernel_reg<MODE, L>, (unsigned)grid, kBlock, st, a, A->d_slice_off, x, b, aux, y, omega, partials); break
+        switch (ml) {
+            MG_REG_CASE(1); MG_REG_CASE(2); MG_REG_CASE(3); MG_REG_CASE(4);
+            MG_REG_CASE(5); MG_REG_CASE(6); MG_REG_CASE(7); MG_REG_CASE(8);
+        }
+#undef MG_REG_CASE
+        MG_CHECK_LAUNCH(name);
+        if (nblocks_out) *nblocks_out = (int)grid;
+        return MG_OK;
+    }
 #define MG_SELL_CASE(L)                                                                                      \
     do {                                                                                                     \
         if (fuse) {                                                                                          \
@@ -512,6 +613,22 @@ int mg_sell_halo_mask(const mg_sell *A, int64_t first_halo_col, unsigned char *d
         ns, A->d_slice_ptr, A->uniform_len, A->d_cols, first_halo_col, d_mask);
     MG_CHECK_LAUNCH("sell_halo_mask");
     return MG_OK;
+}
+/* per-slice column offsets of a UNIFORM matrix (uniform_len entries per row): d_off[s * len + j]; slices that are not
+ * regular get d_off[s * len] = INT32_MIN (see sell_kernel_reg) */
+int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, void *stream) {
+    if (int rc = check_sell(A)) return rc;
+    MG_REQUIRE(d_off && A->uniform_len > 0 && A->uniform_len == A->max_slice_len, "uniform SELL matrix expected");
+    if (A->nslices == 0) return MG_OK;
+    sell_slice_offsets_kernel<<<(unsigned)((A->nslices * 32 + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        A->nslices, A->nrows, (int)A->uniform_len, A->d_cols, d_off);
+    MG_CHECK_LAUNCH("sell_slice_offsets");
+    return MG_OK;
+}
+int mg_set_implied_columns(int enabled) {
+    const int prev = g_implied_columns;
+    g_implied_columns = enabled ? 1 : 0;
+    return prev;
 }
 int64_t mg_set_wide_min_len(int64_t len) {
     const int64_t prev = g_wide_min_len;

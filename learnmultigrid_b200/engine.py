@@ -12,6 +12,7 @@ their natural order inside every row), so that each colour's sweep streams one c
 and reads/writes x contiguously.  Vectors are permuted once on the way in and out.
 """
 import ctypes
+import os
 
 import numpy as np
 import scipy.sparse as sp
@@ -41,6 +42,20 @@ class DeviceSell:
         self.struct = _lib.mg_sell(self.shape[0], self.shape[1], (self.shape[0] + 31) // 32,
                                    self.slice_ptr.data_ptr(), self.cols.data_ptr(), self.vals.data_ptr(),
                                    self.max_len, self.uniform_len)
+        self._attach_slice_offsets()
+
+    def _attach_slice_offsets(self):
+        """opt-in (MGB_IMPLIED_COLUMNS=1): per-slice column offsets of a uniform matrix with <= 8 entries per
+        row, so that regular slices compute their columns instead of loading them (mg_set_implied_columns)"""
+        self.slice_off = None
+        if os.environ.get("MGB_IMPLIED_COLUMNS", "0") != "1" or not 1 <= self.uniform_len <= 8 or self.shape[0] == 0:
+            return
+        import torch
+        nsl = (self.shape[0] + 31) // 32
+        self.slice_off = torch.empty(nsl * self.uniform_len, dtype=torch.int32, device=self.cols.device)
+        _lib.check(_lib.load().mg_sell_slice_offsets(ctypes.byref(self.struct), self.slice_off.data_ptr(),
+                                                     _lib.stream_handle(torch)), "mg_sell_slice_offsets")
+        self.struct.d_slice_off = self.slice_off.data_ptr()
 
     @classmethod
     def from_device(cls, shape, nnz, slice_ptr, cols, vals, max_len=0, uniform_len=0):
@@ -54,6 +69,7 @@ class DeviceSell:
         self.struct = _lib.mg_sell(shape[0], shape[1], (shape[0] + 31) // 32,
                                    slice_ptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), self.max_len,
                                    self.uniform_len)
+        self._attach_slice_offsets()
         return self
 
     def bytes(self):

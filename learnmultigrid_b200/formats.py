@@ -255,3 +255,25 @@ def greedy_colors_by_rounds(A):
         _lib.check(rc, "mg_host_color_rounds")
     colors = colors[:n]
     return colors, (int(colors.max()) + 1 if n else 0), int(rounds.value)
+
+
+SLICE_IRREGULAR = -2 ** 31
+
+
+def sell_slice_offsets(sell, nrows, length):
+    """Slice-relative columns of a UNIFORM SELL-32 matrix (every slice `length` entries per row): off[s, j] such that
+    entry j of EVERY row r of slice s has column r + off[s, j]; slices where that does not hold (or that hold rows
+    beyond the matrix) get off[s, 0] = SLICE_IRREGULAR.  On a structured stencil level nearly all slices are regular,
+    so a kernel can compute the columns instead of loading them: 4*length bytes per slice instead of 128*length
+    (csrc/sell_kernels.cu, mg_set_implied_columns).  Host twin of mg_sell_slice_offsets."""
+    slice_ptr, cols, _ = sell
+    nsl = len(slice_ptr) - 1
+    off = np.full((nsl, max(length, 1)), SLICE_IRREGULAR, dtype=np.int32)
+    if nsl == 0 or length <= 0:
+        return off
+    c = np.asarray(cols, dtype=np.int64).reshape(nsl, length, SLICE)          # [slice][entry][lane]
+    rows = (np.arange(nsl, dtype=np.int64) * SLICE)[:, None, None] + np.arange(SLICE, dtype=np.int64)[None, None, :]
+    rel = c - rows
+    regular = np.all(rel == rel[:, :, :1], axis=(1, 2)) & ((np.arange(nsl) + 1) * SLICE <= nrows)
+    off[regular] = rel[regular][:, :, 0].astype(np.int32)
+    return off

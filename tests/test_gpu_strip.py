@@ -217,3 +217,51 @@ def test_device_first_fit_colouring_equals_the_host_helper(torch_mod):
     with pytest.raises(_lib.MgError):
         S.first_fit_colors(S.upload(chain), max_rounds=1000)
     assert np.array_equal(S.first_fit_colors(S.upload(chain), max_rounds=6000), F.greedy_colors(chain)[0])
+
+
+def test_implied_columns_are_bit_identical(torch_mod, monkeypatch):
+    """mg_set_implied_columns(1) + per-slice offsets (MGB_IMPLIED_COLUMNS=1): regular slices compute their columns from
+    the row; the device-built offset tables equal the host twin, every SELL mode gives the same bits as the ordinary
+    kernels, and so does a whole solve (multicolour Gauss-Seidel and Jacobi)"""
+    import ctypes
+    from learnmultigrid_b200 import _lib, formats as F, problems as P
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    torch = torch_mod
+    lib = _lib.load()
+    N, levels = 256, 4
+    A = F.canonical_csr(P.structured_laplacian_2d(N, P.variable_coefficient))
+    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, "linear")]
+    b = P.structured_rhs_2d(N)
+    x0 = np.random.default_rng(2).standard_normal((A.shape[0], 1))
+
+    def run(smoother):
+        h = DeviceHierarchy(A, Qs, smoother=smoother)
+        h.set_rhs(b)
+        h.set_x(x0)
+        p = h.make_params(nu_pre=2, nu_post=1, omega=2.0 / 3.0)
+        out = []
+        for _ in range(3):
+            out.append(h.residual_norm())
+            h.vcycle(p)
+            out.append(h.get_x().copy())
+        return h, out
+
+    plain = {s: run(s)[1] for s in ("mcgs", "jacobi")}
+    monkeypatch.setenv("MGB_IMPLIED_COLUMNS", "1")
+    prev = lib.mg_set_implied_columns(1)
+    try:
+        for s in ("mcgs", "jacobi"):
+            h, got = run(s)
+            lev = h.levels[0]
+            assert lev.A.slice_off is not None and lev.A.struct.d_slice_off
+            # device-built offsets = host twin on the same (colour-blocked) matrix
+            sell = (lev.A.slice_ptr.cpu().numpy(), lev.A.cols.cpu().numpy(), lev.A.vals.cpu().numpy())
+            want = F.sell_slice_offsets(sell, lev.A.shape[0], lev.A.uniform_len)
+            dev = lev.A.slice_off.cpu().numpy().reshape(want.shape)
+            reg = want[:, 0] != F.SLICE_IRREGULAR
+            assert np.array_equal(dev[:, 0] != F.SLICE_IRREGULAR, reg) and np.array_equal(dev[reg], want[reg])
+            assert reg.mean() > 0.7
+            for g, w in zip(got, plain[s]):
+                assert np.array_equal(np.asarray(g), np.asarray(w))
+    finally:
+        lib.mg_set_implied_columns(prev)

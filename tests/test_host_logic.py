@@ -360,3 +360,52 @@ def test_sell_layout_on_ragged_and_empty_inputs(seed):
     empty = F.canonical_csr(sp.csr_matrix((0, 4)))
     sp0, c0, v0 = F.csr_to_sell(empty)
     assert len(sp0) == 1 and len(c0) == 0 and len(v0) == 0
+
+
+def test_slice_relative_columns_of_structured_levels():
+    """formats.sell_slice_offsets: on the colour-blocked structured operators nearly every slice is regular (columns =
+    row + a per-slice offset table); the columns rebuilt from the offsets equal the stored ones on exactly those slices;
+    slices with identity rows, ragged tails or unstructured rows are marked irregular"""
+    from learnmultigrid_b200 import problems as P
+    N = 128
+    A = P.structured_laplacian_2d(N, P.variable_coefficient)
+    mats = [F.canonical_csr(A)]
+    cur = sp.csc_matrix(A)
+    for Q in P.structured_hierarchy_2d(N, 2, "linear"):
+        cur = sp.csr_matrix(Q.T @ cur @ Q)
+        mats.append(F.canonical_csr(cur))
+    for l, M in enumerate(mats):
+        colors, nc = F.greedy_colors(M)
+        perm, cptr = F.color_permutation(colors)
+        Mp = F.permute_csr(M, perm, F.inverse_permutation(perm))
+        sell = F.csr_to_sell(Mp)
+        slice_ptr, cols, vals = sell
+        lens = np.diff(slice_ptr) // 32
+        assert lens.min() == lens.max()                               # uniform on structured levels
+        L = int(lens.max())
+        off = F.sell_slice_offsets(sell, Mp.shape[0], L)
+        regular = off[:, 0] != F.SLICE_IRREGULAR
+        assert l > 0 or regular.mean() > 0.45          # two slices per grid line hold a boundary node (129 wide here)
+        nsl = len(lens)
+        c = cols.reshape(nsl, L, 32)
+        rows = (np.arange(nsl) * 32)[:, None, None] + np.arange(32)[None, None, :]
+        rebuilt = rows + off[:, :, None].astype(np.int64)
+        assert np.array_equal(rebuilt[regular], c[regular])
+        assert not np.any(np.all((rebuilt == c)[~regular], axis=(1, 2)) & ((np.arange(nsl)[~regular] + 1) * 32 <= Mp.shape[0]))
+        # a slice that mixes identity (boundary) rows with stencil rows is never regular; a slice of identity rows
+        # only is (padding repeats the row's last column, i.e. the row itself: all offsets 0)
+        ident = np.bincount(np.flatnonzero(np.diff(Mp.indptr) == 1) // 32, minlength=nsl)
+        full = np.minimum(32, Mp.shape[0] - np.arange(nsl) * 32)
+        assert not np.any(regular[(ident > 0) & (ident < full)])
+    # at benchmark-like widths almost everything is regular (1 - 2 / (slices per grid line))
+    big = F.canonical_csr(P.structured_laplacian_2d(1024))
+    colors, _ = F.greedy_colors(big)
+    perm, _ = F.color_permutation(colors)
+    sell = F.csr_to_sell(F.permute_csr(big, perm, F.inverse_permutation(perm)))
+    assert (F.sell_slice_offsets(sell, big.shape[0], 5)[:, 0] != F.SLICE_IRREGULAR).mean() > 0.93
+    R = F.canonical_csr(sp.random(96, 96, density=0.1, random_state=1, format="csr") + sp.eye(96))
+    sell = F.csr_to_sell(R)
+    lens = np.diff(sell[0]) // 32
+    if lens.min() == lens.max():
+        assert not np.any(F.sell_slice_offsets(sell, 96, int(lens.max()))[:, 0] != F.SLICE_IRREGULAR)
+    assert F.sell_slice_offsets((np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0)), 0, 5).shape == (0, 5)
