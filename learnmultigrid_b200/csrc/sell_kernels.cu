@@ -185,19 +185,20 @@ sell_kernel_reg(SellArgs A, const int32_t *__restrict__ soff, const double *x, c
         double sum = 0.0, diag = 0.0;
         const int32_t o0 = __ldg(o);
         if (o0 != kSliceIrregular) {          // warp-uniform
-            int32_t cc[LEN];
+            int32_t oo[LEN];                   // the same for all 32 rows: column of entry j = row + oo[j]
             double vv[LEN], xx[LEN];
 #pragma unroll
             for (int j = 0; j < LEN; ++j) vv[j] = ld_stream(v + j * kSlice);
-            cc[0] = (int32_t)row + o0;
+            oo[0] = o0;
 #pragma unroll
-            for (int j = 1; j < LEN; ++j) cc[j] = (int32_t)row + __ldg(o + j);
+            for (int j = 1; j < LEN; ++j) oo[j] = __ldg(o + j);
+            const double *xr = x + row;
 #pragma unroll
-            for (int j = 0; j < LEN; ++j) xx[j] = x[cc[j]];
+            for (int j = 0; j < LEN; ++j) xx[j] = xr[oo[j]];
 #pragma unroll
             for (int j = 0; j < LEN; ++j) {
-                if (MODE == GS) {
-                    if (cc[j] == row) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
+                if (MODE == GS) {              // the diagonal entry is the one with offset 0
+                    if (oo[j] == 0) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
                 } else {
                     sum = mul_add_unfused(sum, vv[j], xx[j]);
                 }
