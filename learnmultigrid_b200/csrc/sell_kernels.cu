@@ -168,17 +168,19 @@ sell_slice_offsets_kernel(int64_t nslices, int64_t nrows, int len, const int32_t
     if (lane == 0 && !regular) off[w * len] = kSliceIrregular;
 }
 
-template <int MODE, int LEN>
-__global__ void __launch_bounds__(kBlock)
-sell_kernel_reg(SellArgs A, const int32_t *__restrict__ soff, const double *x, const double *__restrict__ b,
-                const double *aux, double *y, double omega, double *__restrict__ partials) {
-    pdl_prologue();
-    const int64_t row = A.first_row + (int64_t)blockIdx.x * kBlock + threadIdx.x;
+template <int MODE, int LEN, bool FUSED>
+__device__ __forceinline__ void
+sell_reg_body(const SellArgs &A, const int32_t *__restrict__ soff, const double *x, const double *__restrict__ b,
+              const double *aux, double *y, double omega, double *__restrict__ partials, int64_t bid, const ExArgs *fx,
+              const unsigned char *__restrict__ mask) {
+    const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
     const bool active = row >= A.row_begin && row < A.row_end;
     double contrib = 0.0;
     if (row < A.row_end) {
         const int64_t slice = row >> 5;
         const int lane = (int)(row & 31);
+        unsigned char hw = 0;              // fused launch: does this slice read halo columns?
+        if (FUSED) hw = mask ? mask[slice] : 1;
         const int64_t base = slice * (int64_t)(kSlice * LEN);
         const double *__restrict__ v = A.vals + base + lane;
         const int32_t *__restrict__ o = soff + slice * LEN;
@@ -192,6 +194,7 @@ sell_kernel_reg(SellArgs A, const int32_t *__restrict__ soff, const double *x, c
             oo[0] = o0;
 #pragma unroll
             for (int j = 1; j < LEN; ++j) oo[j] = __ldg(o + j);
+            if (FUSED && hw) fused_wait_ready(*fx);
             const double *xr = x + row;
 #pragma unroll
             for (int j = 0; j < LEN; ++j) xx[j] = xr[oo[j]];
@@ -204,7 +207,7 @@ sell_kernel_reg(SellArgs A, const int32_t *__restrict__ soff, const double *x, c
                 }
             }
         } else {
-            row_chunk<MODE, LEN>(A.cols + base + lane, v, x, row, sum, diag);
+            row_chunk<MODE, LEN>(A.cols + base + lane, v, x, row, sum, diag, hw, fx);
         }
         if (active) {      // the epilogues of sell_body
             if (MODE == SPMV) {
@@ -226,8 +229,31 @@ sell_kernel_reg(SellArgs A, const int32_t *__restrict__ soff, const double *x, c
     }
     if (MODE == RESNORM) {
         const double s = block_sum<kBlock>(contrib);
-        if (threadIdx.x == 0) partials[blockIdx.x] = s;
+        if (threadIdx.x == 0) partials[bid] = s;
     }
+}
+
+template <int MODE, int LEN>
+__global__ void __launch_bounds__(kBlock)
+sell_kernel_reg(SellArgs A, const int32_t *__restrict__ soff, const double *x, const double *__restrict__ b,
+                const double *aux, double *y, double omega, double *__restrict__ partials) {
+    pdl_prologue();
+    sell_reg_body<MODE, LEN, false>(A, soff, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
+}
+
+// the same carrying an exchange site as extra CTAs (see sell_kernel_fused)
+template <int MODE, int LEN>
+__global__ void __launch_bounds__(kBlock)
+sell_kernel_reg_fused(SellArgs A, const int32_t *__restrict__ soff, const double *x, const double *__restrict__ b,
+                      const double *aux, double *y, double omega, double *__restrict__ partials, const ExArgs fx,
+                      const unsigned char *__restrict__ mask) {
+    pdl_prologue();
+    const int nex = fx.npeers * fx.ctas_per_peer;
+    if ((int)blockIdx.x < nex) {
+        fused_exchange_cta(fx, (int)blockIdx.x);
+        return;
+    }
+    sell_reg_body<MODE, LEN, true>(A, soff, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
 }
 
 // Colour sweep of a partitioned level that PUSHES its own boundary values (producer-driven exchange, exchange.cuh):
@@ -448,9 +474,12 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     }
     const int64_t grid = (nthreads + kBlock - 1) / kBlock;
     if (grid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
-    if (g_implied_columns && !fuse && uni && A->d_slice_off && ml >= 1 && ml <= 8) {      // see sell_kernel_reg
-#define MG_REG_CASE(L) \
-    case L: launch_k(sell_kernel_reg<MODE, L>, (unsigned)grid, kBlock, st, a, A->d_slice_off, x, b, aux, y, omega, partials); break
+    if (g_implied_columns && uni && A->d_slice_off && ml >= 1 && ml <= 8) {      // see sell_kernel_reg
+#define MG_REG_CASE(L)                                                                                                  \
+    case L:                                                                                                             \
+        if (fuse) launch_k(sell_kernel_reg_fused<MODE, L>, (unsigned)(grid + fuse->nex), kBlock, st, a, A->d_slice_off, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
+        else launch_k(sell_kernel_reg<MODE, L>, (unsigned)grid, kBlock, st, a, A->d_slice_off, x, b, aux, y, omega, partials); \
+        break
         switch (ml) {
             MG_REG_CASE(1); MG_REG_CASE(2); MG_REG_CASE(3); MG_REG_CASE(4);
             MG_REG_CASE(5); MG_REG_CASE(6); MG_REG_CASE(7); MG_REG_CASE(8);

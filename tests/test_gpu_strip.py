@@ -265,3 +265,50 @@ def test_implied_columns_are_bit_identical(torch_mod, monkeypatch):
                 assert np.array_equal(np.asarray(g), np.asarray(w))
     finally:
         lib.mg_set_implied_columns(prev)
+
+
+def test_implied_columns_on_partitioned_levels(torch_mod, monkeypatch):
+    """the implied-columns kernels carrying an exchange site (sell_kernel_reg_fused): partitioned cycle with
+    MGB_IMPLIED_COLUMNS=1 against the ordinary single-GPU cycle, bit for bit"""
+    from learnmultigrid_b200 import _lib, formats as F, problems as P
+    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    lib = _lib.load()
+    N, levels, nu, cycles = 256, 4, 1, 3
+    A = F.canonical_csr(P.structured_laplacian_2d(N))
+    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, "linear")]
+    b = P.structured_rhs_2d(N)
+    x0 = np.random.default_rng(8).standard_normal((A.shape[0], 1))
+    h = DeviceHierarchy(A, Qs, smoother="mcgs")
+    h.set_rhs(b)
+    h.set_x(x0)
+    params = h.make_params(nu_pre=nu, nu_post=nu)
+    want = []
+    for _ in range(cycles):
+        h.vcycle(params)
+        want.append(h.get_x().copy())
+
+    def body(fab):
+        hd = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h.colors, n_dist=2, region_bytes=1 << 20,
+                                  max_sites=256, timeout_s=30.0)
+        assert hd.levels[0].A.slice_off is not None
+        hd.set_rhs(b)
+        hd.set_x(x0)
+        p = hd.make_params(nu_pre=nu, nu_post=nu)
+        xs = []
+        for _ in range(cycles):
+            hd.vcycle(p, with_norm=True)
+            xs.append(hd.get_x().copy())
+        hd.check()
+        hd.close()
+        return xs
+
+    monkeypatch.setenv("MGB_IMPLIED_COLUMNS", "1")
+    prev = lib.mg_set_implied_columns(1)
+    try:
+        res = run_virtual_ranks(2, body)
+    finally:
+        lib.mg_set_implied_columns(prev)
+    for xs in res:
+        for got, w in zip(xs, want):
+            assert np.array_equal(got, w)
