@@ -29,6 +29,8 @@ multi)
     step dist_check_push 300 env MGB_PUSH_EXCHANGE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29512 tools/dist_check.py --size 512 --levels 5 --n-dist 3
     step bench_consumer 600 run bench.py --gpus "$n" --steps 40 --no-cpu-baseline
     step bench_push 600 env MGB_PUSH_EXCHANGE=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus "$n" --steps 40 --no-cpu-baseline
+    step bench_implied 600 env MGB_IMPLIED_COLUMNS=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29514 bench.py --gpus "$n" --steps 40 --no-cpu-baseline
+    step bench_push_implied 600 env MGB_PUSH_EXCHANGE=1 MGB_IMPLIED_COLUMNS=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$n" --master-addr 127.0.0.1 --master-port 29515 bench.py --gpus "$n" --steps 40 --no-cpu-baseline
     step bench_weak 900 run tools/bench_weak.py --n 8192 --steps 20 --colors structured
     ;;
 *)
