@@ -112,12 +112,13 @@ int mg_sell_spmv(const mg_sell *A, const double *d_x, double *d_y, void *stream)
 /* r = b - A x */
 int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, double *d_r, void *stream);
 /* fused: *d_norm2 = sum_i (b - A x)_i^2 without storing r (outer loop Multigrid.py:62-63); d_partials is a
- * workspace of mg_norm_workspace_size(nrows) doubles; deterministic two-stage reduction. */
+ * workspace of mg_norm_workspace_size(nrows) = ceil(nrows/32)+1 doubles (the worst case over the kernel variants: one
+ * partial per CTA, and the warps-per-slice kernel has one CTA per slice); deterministic two-stage reduction. */
 int mg_sell_residual_norm2(const mg_sell *A, const double *d_x, const double *d_b, double *d_partials,
                            double *d_norm2, void *stream);
 int64_t mg_norm_workspace_size(int64_t n);
 /* launches that cover at least `rows` rows use the bulk-async (TMA) staged kernel; 0 = never.  Returns the
- * previous threshold (default 65536).  Both kernels give bit-identical results. */
+ * previous threshold (default 0 = off).  Both kernels give bit-identical results. */
 int64_t mg_set_tma_min_rows(int64_t rows);
 /* matrices whose longest slice has at least `len` entries per row (and at most 64) run the warps-per-slice
  * kernel: loads of a row spread over four or eight warps, products added in storage order (same bits); 0 = never.  Returns

@@ -634,7 +634,9 @@ int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, dou
     if (int rc = check_sell(A)) return rc;
     return sell_residual(A, d_x, d_b, d_r, (cudaStream_t)stream);
 }
-int64_t mg_norm_workspace_size(int64_t n) { return (n + kBlock - 1) / kBlock + 1; }
+/* worst case over the kernels that write partials: the warps-per-slice kernel with eight warps per slice has one CTA
+ * (one partial) per 32 rows */
+int64_t mg_norm_workspace_size(int64_t n) { return (n + kSlice - 1) / kSlice + 1; }
 /* rows per launch from which the bulk-async staged SELL kernel is used (0 = never); returns the old value */
 int mg_sell_halo_mask(const mg_sell *A, int64_t first_halo_col, unsigned char *d_mask, void *stream) {
     MG_REQUIRE(A && d_mask && A->nrows > 0, "null argument");

@@ -6,6 +6,19 @@ from .. import _lib
 from .Solver import IterativeSolver
 
 
+def _same_operator(P, A):
+    """True only if the preconditioner was built from THIS operator (same object, or the same CSC arrays entry for
+    entry); a multigrid built from another matrix of the same sparsity must not replace A in `A p`."""
+    if P is None:
+        return False
+    if P is A:
+        return True
+    if P.shape != A.shape or P.nnz != A.nnz or P.format != A.format:
+        return False
+    return (np.array_equal(P.indptr, A.indptr) and np.array_equal(P.indices, A.indices)
+            and np.array_equal(P.data, A.data))
+
+
 class CG(IterativeSolver):
 
     def __init__(self, matrix, rhs):
@@ -18,8 +31,8 @@ class CG(IterativeSolver):
         changes results only in the last bits.  `preconditioner(r_dev, z_dev)` applies z = M^-1 r on device
         vectors (see solvers.Multigrid.Multigrid.as_preconditioner)."""
         h = getattr(preconditioner, "hierarchy", None)
-        if (h is not None and initial_guess is None and getattr(preconditioner, "matrix", None) is not None
-                and preconditioner.matrix.shape == self.matrix.shape and preconditioner.matrix.nnz == self.matrix.nnz
+        if (h is not None and initial_guess is None and _same_operator(getattr(preconditioner, "matrix", None),
+                                                                       self.matrix)
                 and not getattr(h.levels[0], "n_halo", 0)):
             # the preconditioner's hierarchy already holds this operator on the device (SELL, level-0 ordering): run
             # the whole iteration there (engine.DeviceHierarchy.pcg) instead of uploading a second copy of the matrix

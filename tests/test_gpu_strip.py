@@ -1,17 +1,14 @@
 """GPU tests of distributed_strip.StripHierarchy (partitioned hierarchy built from row blocks only): iterates and
 residual norms bit-identical to the single-GPU hierarchy, local products on the device SpGEMM identical to SciPy's.
 
-Written at the end of round 1 with no GPU time left: NOT YET RUN on a B200, therefore skipped unless MGB_UNVERIFIED=1
-(first thing to run in the next round: MGB_UNVERIFIED=1 python -m pytest tests/test_gpu_strip.py -m gpu)."""
-import os
+Also: producer-driven exchange, device first-fit colouring, implied columns.  First run on a B200 in round 2
+(profiles/r02_pytest_gpu_unverified_first_run.log: 14 passed); the MGB_UNVERIFIED gate of round 1 is gone."""
 
 import numpy as np
 import pytest
 import scipy.sparse as sp
 
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(os.environ.get("MGB_UNVERIFIED") != "1",
-                                 reason="not yet verified on a GPU (set MGB_UNVERIFIED=1 to run)")]
+pytestmark = [pytest.mark.gpu]
 
 
 @pytest.fixture(scope="module")

@@ -16,7 +16,6 @@ case "${1:-single}" in
 single)
     step pytest_gpu 900 python -m pytest tests -m gpu -x -q
     step pytest_unverified 600 env MGB_UNVERIFIED=1 python -m pytest tests/test_gpu_strip.py -m gpu -q
-    step memcheck_push 600 env MGB_UNVERIFIED=1 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_strip.py -m gpu -q -k "producer_driven_exchange_is_bit_identical and 2-2-True"
     step bench_default 600 python bench.py
     step bench_implied_columns 600 env MGB_IMPLIED_COLUMNS=1 python bench.py --no-cpu-baseline
     step setup_host_colours 900 python tools/bench_setup_pcg.py
