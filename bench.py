@@ -47,10 +47,13 @@ def parse_args():
     ap.add_argument("--nu", type=int, default=1)
     ap.add_argument("--coefficient", default="constant", choices=["constant", "variable"])
     ap.add_argument("--cycles-per-solve", type=int, default=10)
-    ap.add_argument("--cpu-n", type=int, default=1024, help="mesh size of the bounded CPU sample")
+    ap.add_argument("--cpu-n", type=int, default=2048,
+                    help="mesh size of the bounded CPU sample (SURVEY 8d: <= 4 M DOF measured, the rest labelled extrapolated)")
     ap.add_argument("--setup", default=os.environ.get("MGB_BENCH_SETUP", "device"), choices=["host", "device"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity-check", action="store_true",
+                    help="N > 1: skip the small partitioned-vs-single-GPU bit-identity check run before the benchmark")
     ap.add_argument("--profile-step", action="store_true",
                     help="bracket ONE extra step with cudaProfilerStart/Stop (ncu --profile-from-start off)")
     ap.add_argument("--multi", default=os.environ.get("MGB_BENCH_MULTI", "partitioned"),
@@ -258,9 +261,50 @@ def run_reference(a):
             "config": {"workload": workload_name(a, a.n), "sample": sample,
                        "smoother": ("index-order Gauss-Seidel (PyAMG's sweep restated in C: what the reference runs whatever "
                                     "`smoother` says, Multigrid.py:88,121)" if a.smoother == "GaussSeidel" else "damped Jacobi")},
-            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample},
+            "extrapolated": n != a.n,
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                             "extrapolated": n != a.n},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
+
+
+def multi_rank_parity(torch, dist, fab, a):
+    """N > 1: the partitioned cycle (real ranks, real NVLink exchanges) against the single-GPU cycle every rank also
+    runs, on a small problem of the same kind: iterates must agree bit for bit, norms to rounding.  Returns a dict for
+    `config` (the driver's scaling run then carries multi-process parity)."""
+    from learnmultigrid_b200 import problems as P
+    from learnmultigrid_b200.distributed import DistributedHierarchy
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    N, levels, cycles = 512, 5, 3
+    coef = P.variable_coefficient if a.coefficient == "variable" else None
+    A = P.structured_laplacian_2d(N, coef)
+    Qs = P.structured_hierarchy_2d(N, levels, transfer="linear")
+    rng = np.random.default_rng(11)
+    n = A.shape[0]
+    b, x0 = rng.standard_normal(n), rng.standard_normal(n)
+    h1 = DeviceHierarchy(A, Qs, smoother="mcgs")
+    hd = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h1.colors, n_dist=3, timeout_s=30.0)
+    for h in (h1, hd):
+        h.set_rhs(b)
+        h.set_x(x0)
+    p1, pd = h1.make_params(nu_pre=a.nu, nu_post=a.nu), hd.make_params(nu_pre=a.nu, nu_post=a.nu)
+    same, close = True, True
+    for _ in range(cycles):
+        h1.vcycle(p1, with_norm=True)
+        hd.vcycle(pd, norm_after=True)
+        n1, nd = h1.last_norm(), hd.last_norm()
+        o0, o1 = int(hd.offsets[0][fab.rank]), int(hd.offsets[0][fab.rank + 1])
+        same = same and np.array_equal(h1.get_x()[o0:o1], hd.get_x_local())
+        close = close and abs(n1 - nd) <= 1e-12 * n1
+    hd.check()
+    t = torch.tensor([1 if same else 0, 1 if close else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    hd.close()
+    del h1, hd
+    torch.cuda.empty_cache()
+    return {"problem": "%dx%d grid, %d levels (3 partitioned), V(%d,%d), %d cycles, every rank vs its own single-GPU cycle"
+                       % (N + 1, N + 1, levels, a.nu, a.nu, cycles),
+            "iterates_bit_identical": bool(int(t[0].item())), "norms_equal_to_1e-12": bool(int(t[1].item()))}
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -284,8 +328,13 @@ def run_b200(a):
     mg = SemiGeometricMG(A, rhs, Qs)
     mg.setup = a.setup
     part = world > 1 and a.multi == "partitioned"
+    parity = None
     if part:
-        mg.distribute(min_rows_per_rank=a.min_rows_per_rank, timeout_s=30.0)
+        from learnmultigrid_b200.distributed import TorchFabric
+        fab = TorchFabric()
+        if a.smoother == "GaussSeidel" and not a.no_parity_check:
+            parity = multi_rank_parity(torch, dist, fab, a)
+        mg.distribute(fab, min_rows_per_rank=a.min_rows_per_rank, timeout_s=30.0)
         mg.local_solution = True
     t0 = time.perf_counter()
     kw = dict(levels=a.levels, smoother=a.smoother, smooth_steps=a.nu, omega=2.0 / 3.0)
@@ -309,19 +358,20 @@ def run_b200(a):
     lev0 = h.levels[0]
     st = _lib.stream_handle(torch)
 
+    # One outer iteration of Multigrid.solve in steady state = one program / one graph: the V-cycle, then the residual
+    # norm of its result (what the next iteration tests, Multigrid.py:62-63,69).  With multicolour Gauss-Seidel the
+    # last colour's share of the norm comes out of the last sweep's registers (mg_vcycle_norm / mg_dist_norm.after).
     if part:
-        def step():                  # one program / one graph: fused residual norm + all-reduce + V-cycle
-            h.vcycle(params, with_norm=True)
+        def step():
+            h.vcycle(params, norm_after=True)
     else:
         def step():
-            _lib.check(lib.mg_sell_residual_norm2(ctypes.byref(lev0.A.struct), lev0.x.data_ptr(), lev0.b.data_ptr(),
-                                                  h._norm_ws.data_ptr(), h._norm_out.data_ptr(), st))
-            h.vcycle(params)
+            h.vcycle(params, with_norm=True)
 
     for _ in range(max(a.warmup, 3)):
         step()
     torch.cuda.synchronize()
-    launches_per_step = h.last_launches if part else 2 + h.last_launches
+    launches_per_step = h.last_launches
     h.zero_x()                       # time from a fresh start so the iterate stays meaningful
     torch.cuda.synchronize()
     if world > 1:
@@ -358,12 +408,12 @@ def run_b200(a):
         h.check()                    # no exchange timed out
         # the same program with its exchange kernels launched as no-ops: kernel time without waiting for peers
         for _ in range(3):
-            h.vcycle(params, with_norm=True, dry=True)
+            h.vcycle(params, norm_after=True, dry=True)
         torch.cuda.synchronize()
         dist.barrier()
         e0.record()
         for _ in range(a.steps):
-            h.vcycle(params, with_norm=True, dry=True)
+            h.vcycle(params, norm_after=True, dry=True)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1) / a.steps], device="cuda")
@@ -402,17 +452,38 @@ def run_b200(a):
     ach = sweep_bytes / (ms_sweep * 1e-3) / 1e9
     cyc = h.cycle_bytes(a.nu, a.nu)
     cyc_gbs = cyc["total"] / (ms_step * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_gs_traffic.json")
-    if lev0.color_ptr is not None and n == 8192 and a.coefficient == "constant" and os.path.exists(tpath):
-        traffic = json.load(open(tpath))["traffic_per_launch"]      # ncu --set full capture of this kernel / config
+    # DRAM bytes per launch of that kernel from a stored `ncu --set full` capture -- only quoted for the configuration
+    # it was taken on (1 GPU, this grid, constant coefficient, the kernel variant that runs by default)
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_gs_traffic.json")
+    implied = getattr(lev0.A, "slice_off", None) is not None and os.environ.get("MGB_IMPLIED_COLUMNS", "1") != "0"
+    if os.path.exists(tpath) and world == 1 and lev0.color_ptr is not None:
+        t = json.load(open(tpath))
+        if t.get("n") == n and t.get("coefficient") == a.coefficient and bool(t.get("implied_columns")) == implied:
+            traffic = t["traffic_per_launch"]
+            traffic_src = "stored ncu --set full capture (%s), not measured in this run" % t.get("source", tpath)
+    per_gpu = world if part else 1
+    moved = h.cycle_bytes_moved(a.nu, a.nu) if hasattr(h, "cycle_bytes_moved") else None
+    nsl0 = (lev0.n + 31) // 32
+    sweep_moved = (lev0.A.stream_bytes() if hasattr(lev0.A, "stream_bytes") else S) + 24 * lev0.n
     roofline = {"bound": "hbm", "kernel": "sell_kernel<GS> (fine-level colour sweep)" if lev0.color_ptr is not None
                 else "sell_kernel<JACOBI> (fine-level sweep)",
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_source": peak_src,
-                "traffic": traffic, "bytes_per_launch": sweep_bytes / nlaunch, "launches_per_sweep": nlaunch,
+                "traffic": traffic, "traffic_source": traffic_src,
+                "bytes_per_launch": sweep_bytes / nlaunch, "launches_per_sweep": nlaunch,
                 "ms_per_launch": ms_sweep / nlaunch,
-                "cycle": {"algorithmic_bytes": cyc["total"], "achieved": cyc_gbs, "frac": cyc_gbs / peak,
-                          "frac_of_8TBps": cyc_gbs / 8000.0, "bytes_per_dof": cyc["total"] / ndof}}
+                "implied_columns": implied,
+                # what the kernel actually streams (values + columns or per-slice offsets + b, x in, x out): the
+                # algorithmic yardstick above stays the CSR bytes of SURVEY 8d, so byte-saving shows as frac > 1
+                "moved_bytes_per_launch": sweep_moved / nlaunch,
+                "moved_frac": sweep_moved / (ms_sweep * 1e-3) / 1e9 / peak,
+                # whole step; per GPU (a partitioned run moves 1/world of the global bytes on each GPU)
+                "cycle": {"algorithmic_bytes": cyc["total"], "algorithmic_bytes_per_gpu": cyc["total"] / per_gpu,
+                          "achieved": cyc_gbs / per_gpu, "frac": cyc_gbs / per_gpu / peak,
+                          "frac_of_8TBps": cyc_gbs / per_gpu / 8000.0, "bytes_per_dof": cyc["total"] / ndof,
+                          "moved_bytes_per_gpu": None if moved is None else moved["total"],
+                          "moved_frac": None if moved is None else moved["total"] / (ms_step * 1e-3) / 1e9 / peak,
+                          "moved_model": None if moved is None else moved["model"]}}
 
     # ---- SpMV per level (the metric's second half): y = A_l x on every smoothed level, algorithmic bytes
     # S(nnz, n) + 16 n over the CUDA-event time of back-to-back launches; this rank's rows when partitioned.
@@ -434,7 +505,11 @@ def run_b200(a):
             ms_l = e0.elapsed_time(e1) / reps_l
             gbs_l = bytes_l / (ms_l * 1e-3) / 1e9
             per_level.append({"level": l, "rows": int(lev.n), "nnz": int(nnz_l), "us_per_launch": round(ms_l * 1e3, 2),
-                              "gbs": round(gbs_l, 1), "frac": round(gbs_l / peak, 4)})
+                              "gbs": round(gbs_l, 1), "frac": round(gbs_l / peak, 4),
+                              # back-to-back launches on the same operands: what fits the 126 MB L2 is re-read from
+                              # there, so fractions of levels that (partly) fit are not HBM fractions
+                              "working_set_mb": round(bytes_l / 1e6, 1),
+                              "l2_resident_share": round(min(1.0, 126e6 / bytes_l), 2)})
         roofline["spmv_per_level"] = per_level
     except Exception as exc:         # pragma: no cover
         roofline["spmv_per_level"] = {"error": repr(exc)}
@@ -472,7 +547,7 @@ def run_b200(a):
     cpu = None
     if not a.no_cpu_baseline and rank == 0:
         v, per, ncyc, tset = cpu_cycle_rate(a, a.cpu_n, reference_style=False)
-        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port",
+        cpu = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "extrapolated": a.cpu_n != n,
                "sample": "%dx%d grid (%d DOF) of the same %d-level V(%d,%d) configuration, %d cycles, hierarchy built "
                          "once (setup %.1f s excluded); SciPy sparsetools + C Gauss-Seidel are single-threaded; "
                          "host has %d cores" % (a.cpu_n + 1, a.cpu_n + 1, (a.cpu_n + 1) ** 2, a.levels, a.nu, a.nu,
@@ -488,7 +563,11 @@ def run_b200(a):
                            "levels_nnz": [l.nnz_A for l in h.levels], "colors": [None if l.color_ptr is None else
                                                                               len(l.color_ptr) - 1 for l in h.levels],
                            "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2), "nn_builder": NN_BUILD.get(n),
-                           "residual_after_timed_steps": res_after,
+                           "residual_after_timed_steps": res_after, "multi_rank_parity": parity,
+                           "step": "V-cycle + residual norm of its result (one graph): steady-state outer iteration of "
+                                   "Multigrid.solve; cycle fusion %s, implied columns %s"
+                                   % ("off" if os.environ.get("MGB_CYCLE_FUSION", "1") == "0" else "on",
+                                      "on" if implied else "off"),
                            "ms_per_step_without_exchange_waits": ms_dry,
                            "exchange": (("producer-driven (MGB_PUSH_EXCHANGE=1)" if getattr(h, "push_exchange", False)
                                          else "consumer-driven") if part else None),

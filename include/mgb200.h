@@ -101,19 +101,27 @@ typedef struct {
                                    mg_sell_slice_offsets, used when mg_set_implied_columns(1) */
 } mg_sell;
 
-/* y = A x  (rows [row0,row1)) */
-/* Implied columns (opt-in, default 0; results identical): on a uniform matrix with <= 8 entries per row, slices whose
+/* Implied columns (default on; results identical): on a uniform matrix with <= 8 entries per row, slices whose
  * 32 rows all have the columns row + off[j] (structured stencil levels: all slices but those holding a boundary node)
- * read 4 bytes of offset per entry index instead of 128 bytes of column indices.  mg_sell_slice_offsets fills
- * d_off[nslices * uniform_len] (irregular slices: d_off[s * len] = INT32_MIN); point mg_sell.d_slice_off at it. */
-int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, void *stream);
+ * read 4 bytes of offset per entry index instead of 128 bytes of column indices, and the x gathers of a warp become
+ * contiguous 256-byte reads.  mg_sell_slice_offsets fills d_off[nslices * uniform_len] (irregular slices:
+ * d_off[s * len] = INT32_MIN) and adds the number of regular slices to *d_nregular (device int64, zeroed by the
+ * caller; may be NULL); point mg_sell.d_slice_off at the table when enough slices are regular. */
+int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, int64_t *d_nregular, void *stream);
 int mg_set_implied_columns(int enabled);
+/* launches of fewer rows keep loading their columns (one dependent load less on latency-bound launches); returns the
+ * previous floor (default 2^19) */
+int64_t mg_set_implied_min_rows(int64_t rows);
+/* y = A x */
 int mg_sell_spmv(const mg_sell *A, const double *d_x, double *d_y, void *stream);
-/* r = b - A x */
+/* r = b - A x; _rows: only the rows [row0,row1) of r are written */
 int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, double *d_r, void *stream);
+int mg_sell_residual_rows(const mg_sell *A, const double *d_x, const double *d_b, double *d_r, int64_t row0,
+                          int64_t row1, void *stream);
 /* fused: *d_norm2 = sum_i (b - A x)_i^2 without storing r (outer loop Multigrid.py:62-63); d_partials is a
- * workspace of mg_norm_workspace_size(nrows) = ceil(nrows/32)+1 doubles (the worst case over the kernel variants: one
- * partial per CTA, and the warps-per-slice kernel has one CTA per slice); deterministic two-stage reduction. */
+ * workspace of mg_norm_workspace_size(nrows) = ceil(nrows/32)+2 doubles (the worst case over the kernel variants: one
+ * partial per CTA, the warps-per-slice kernel has one CTA per slice, and mg_vcycle_norm writes two runs of partials);
+ * deterministic two-stage reduction. */
 int mg_sell_residual_norm2(const mg_sell *A, const double *d_x, const double *d_b, double *d_partials,
                            double *d_norm2, void *stream);
 int64_t mg_norm_workspace_size(int64_t n);
@@ -133,9 +141,24 @@ int mg_sell_jacobi(const mg_sell *A, const double *d_dinv, const double *d_x, co
 /* Gauss-Seidel update of the rows [row0,row1) in place (one colour of a colour-blocked ordering). */
 int mg_sell_gs_rows(const mg_sell *A, double *d_x, const double *d_b, int64_t row0, int64_t row1,
                     void *stream);
-/* u_out = u + Q e  (u_out may alias u) */
+/* The same sweep, which also leaves what the NEXT operation of a V-cycle needs from these rows, computed from the
+ * registers that still hold each row (no second pass over the matrix): tail = 1: d_r[i] = (b - A x)_i with the new
+ * x_i, for i in [row0,row1); tail = 2: per-CTA partial sums of (b - A x)_i^2 over these rows in d_partials,
+ * *h_nblocks of them; tail = 0: mg_sell_gs_rows.  Exact (the bits of a residual pass after the sweep) when no row of
+ * the range has a non-zero entry in the column of another row of the range -- a proper colouring.  Available for
+ * rows of at most 8 entries, or launches the warps-per-slice kernel takes: mg_sell_gs_tail_ok. */
+int mg_sell_gs_rows_tail(const mg_sell *A, double *d_x, const double *d_b, int64_t row0, int64_t row1, int tail,
+                         double *d_r, double *d_partials, int *h_nblocks, void *stream);
+int mg_sell_gs_tail_ok(const mg_sell *A, int64_t row0, int64_t row1);
+/* First colour sweep on a zero iterate without the matrix: x[0..n_vec) = 0 except x_i = b_i / d_diag[i] for i in
+ * [row0,row1) with d_diag[i] != 0 -- the bits of mg_fill(0) followed by mg_sell_gs_rows(row0,row1). */
+int mg_sell_gs_zero_first(int64_t n_vec, int64_t row0, int64_t row1, const double *d_diag, const double *d_b,
+                          double *d_x, void *stream);
+/* u_out = u + Q e  (u_out may alias u); _rows: only the rows [row0,row1) */
 int mg_sell_prolong_correct(const mg_sell *Q, const double *d_e, const double *d_u, double *d_u_out,
                             void *stream);
+int mg_sell_prolong_correct_rows(const mg_sell *Q, const double *d_e, const double *d_u, double *d_u_out, int64_t row0,
+                                 int64_t row1, void *stream);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* vector kernels (Multigrid.py:63 np.linalg.norm; CG.py:30-48 dots and updates)                     */
@@ -458,6 +481,12 @@ int mg_host_greedy_color_block(int64_t n_own, int64_t n_ext, const int32_t *h_in
  * stream every 128 rounds.  MG_ERR_UNSUPPORTED if more than max_rounds rounds (long dependency chains, e.g. a 1D mesh
  * numbered end to end: use the host helper) or more than 128 colours would be needed. */
 int64_t mg_color_workspace_size(int64_t n);
+/* Is a colouring proper for the operator, and has every row a diagonal (mg_level.flags)?  Rows [0,nrows) of a CSR block
+ * whose row i is global row row0 + i; d_color is indexed by GLOBAL row / column id.  *d_flags (device int32, zeroed by
+ * the caller) |= 1 if a row has a non-zero entry in the column of another row of its own colour, |= 2 if a row has no
+ * non-zero diagonal entry. */
+int mg_csr_coloring_flags(int64_t nrows, int64_t row0, const int32_t *d_indptr, const int32_t *d_indices,
+                          const double *d_values, const int32_t *d_color, int32_t *d_flags, void *stream);
 int mg_color_first_fit(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const int32_t *d_t_indptr,
                        const int32_t *d_t_indices, int32_t *d_colors, void *d_work, int64_t work_bytes,
                        int64_t max_rounds, int64_t *h_rounds, void *stream);
@@ -494,7 +523,20 @@ typedef struct {
     /* row-partitioned level (multi-GPU): n = OWNED rows, vectors hold n + dist->n_halo entries; NULL otherwise */
     const mg_dist_level *dist;
     const mg_bcr_dist *coarse_bcr_dist;   /* optional: split the BCR solve over the ranks (mg_vcycle_dist only)      */
+    /* what mg_level_inspect established about A and the colouring (0 = nothing: the cycle then does no work-saving
+     * fusion on this level); on partitioned levels the facts must hold for the GLOBAL operator                      */
+    uint32_t flags;                       /* MG_LEVEL_*                                                              */
+    uint32_t pad_;
+    const double *d_diag;                 /* the diagonal as the Gauss-Seidel kernel finds it (0: none); optional    */
 } mg_level;
+/* multicolour Gauss-Seidel only.  PROPER_COLORING: no row has a non-zero entry in the column of ANOTHER row of its own
+ * colour.  NONZERO_DIAG: every row has a non-zero diagonal entry (so a colour sweep overwrites every row it visits). */
+enum { MG_LEVEL_PROPER_COLORING = 1, MG_LEVEL_NONZERO_DIAG = 2 };
+/* d_diag[i] (optional) = last non-zero stored entry of row i on the diagonal (0 if none) -- what mg_sell_gs_rows divides
+ * by; *d_flags (device int32, zeroed by the caller) |= 1 if the colouring given by d_color_ptr[ncolors+1] (device) is
+ * NOT proper, |= 2 if some row has no non-zero diagonal.  ncolors = 0: only the diagonal is examined. */
+int mg_level_inspect(const mg_sell *A, int ncolors, const int64_t *d_color_ptr, double *d_diag, int32_t *d_flags,
+                     void *stream);
 
 typedef struct {
     int32_t smoother;          /* MG_SMOOTH_*                                                            */
@@ -503,11 +545,25 @@ typedef struct {
     int32_t zero_guess_skip;   /* 1: skip A*0 work on coarse levels (results identical)                  */
     int32_t reverse_post;      /* 1: multicolour post-smoothing visits the colours in reverse order, which makes
                                   the V-cycle a symmetric operator (preconditioner for CG); 0: reference order  */
+    int32_t x0_zero;           /* 1: the iterate on levels[0] is to be taken as zero (d_x need not be initialised):
+                                  z = M^-1 r of a preconditioner application without a memset and the A*0 work    */
+    int32_t pad_;
 } mg_cycle_params;
 
 /* One V-cycle starting on levels[0]: pre-smooth, residual, restrict, recurse / coarsest solve,
  * prolong + correct, post-smooth.  Launches only; capturable in a CUDA graph. */
 int mg_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, void *stream);
+/* The same cycle, then *d_norm2 = ||b - A x||_2^2 of the NEW iterate on levels[0] -- what the next outer iteration of
+ * Multigrid.solve evaluates first (Multigrid.py:62-63).  With multicolour Gauss-Seidel on a properly coloured level
+ * the last colour sweep sums the squared residuals of its own rows from registers, and only the other colours' rows
+ * are passed over again.  d_partials: mg_norm_workspace_size(n) doubles. */
+int mg_vcycle_norm(const mg_level *levels, int nlevels, const mg_cycle_params *params, double *d_partials,
+                   double *d_norm2, void *stream);
+/* 1 (default): the multicolour cycle skips work whose result is never read or is already in registers (residual of the
+ * last pre-smoothing colour from its sweep, no prolongation onto the colour the post-smoothing overwrites first, first
+ * sweep on a zero iterate without the matrix); needs mg_level.flags.  0: every operation is a pass of its own.  The
+ * results are bit-identical.  Returns the previous setting. */
+int mg_set_cycle_fusion(int enabled);
 /* The same cycle over a hierarchy whose first levels are row-partitioned across the ranks of `comm` (levels with
  * mg_level.dist set) and whose remaining levels are replicated.  Enqueues ONE program (mg_comm_begin .. mg_comm_end):
  * if `norm` is given, first the fused residual + squared 2-norm of level 0 summed over all ranks into *d_norm2 (the
@@ -517,35 +573,14 @@ typedef struct {
     double *d_local;           /* 1 double: this rank's sum of squares                                      */
     double *d_slots;           /* MG_MAX_RANKS doubles: the other ranks' sums land here                     */
     double *d_norm2;           /* 1 double: the global sum, identical bits on every rank                    */
+    int32_t after;             /* 0: the norm of the iterate the program STARTS from; 1: of the iterate the cycle
+                                  leaves (fused into the last sweep as in mg_vcycle_norm; needs params)          */
+    int32_t pad_;
 } mg_dist_norm;
 int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_cycle_params *params,
                    const mg_dist_norm *norm, void *stream);
 /* number of kernels the last mg_vcycle call on this thread launched (bench.py's gpu_launches) */
 int64_t mg_last_launch_count(void);
-/* Tail program (csrc/tail.cu; off by default).  In mg_vcycle / mg_vcycle_dist, from the first replicated level with at
- * most `rows` rows downwards, the operations of the cycle (smoothing sweeps, residual, restriction, prolongation,
- * fills) are not launched one by one but recorded and run by ONE persistent cooperative kernel per stretch -- the way
- * down to the coarsest solve, the way back up -- whose CTAs walk the record and separate dependent operations by a
- * grid barrier.  The record travels in the kernel's parameter space (<= 40 operations per launch), so the launch is
- * capturable in a CUDA graph like any other.  Same per-row arithmetic as the SELL kernels: bit-identical results.
- * Levels smoothed by index-order Gauss-Seidel are never recorded.  Returns the previous threshold (0 = off). */
-int64_t mg_set_tail_max_rows(int64_t rows);
-/* resident CTAs per SM of that kernel (default 2, clamped to what fits); returns the previous value */
-int mg_set_tail_ctas_per_sm(int ctas);
-/* incremented by the two setters above: a captured graph of the cycle is valid for one value of it */
-int64_t mg_tail_config_epoch(void);
-/* of the last mg_vcycle / mg_vcycle_dist / mg_host_tail_vcycle call on this thread: operations recorded, grid
- * barriers placed between them, cooperative launches made */
-int mg_tail_last_stats(int64_t *ops, int64_t *barriers, int64_t *launches);
-/* HOST emulation for the CPU test-suite (every pointer in `levels` is a host pointer; Jacobi or multicolour
- * Gauss-Seidel; dense coarsest inverse): the whole cycle is recorded as a tail program and executed serially with the
- * same per-row code; shuffle != 0 runs the rows of every barrier-free group of operations in a pseudo-random order,
- * which is legal exactly if the barriers are placed correctly.  Not called by the product. */
-int mg_host_tail_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, uint64_t shuffle);
-/* TEST HOOK: on != 0 removes every barrier inside a stretch (wrong on purpose), so that the test-suite can show that
- * the shuffled host execution above does detect a missing barrier.  Returns the previous setting. */
-int mg_tail_debug_drop_barriers(int on);
-
 /* CUDA-graph helpers: capture whatever is enqueued on `stream` between begin and end. */
 int mg_graph_begin(void *stream);
 int mg_graph_end(void *stream, void **graph_exec_out);

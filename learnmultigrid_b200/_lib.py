@@ -20,6 +20,7 @@ c_vp = ctypes.c_void_p
 
 MG_SMOOTH_JACOBI, MG_SMOOTH_MCGS, MG_SMOOTH_LEXGS = 0, 1, 2
 MG_COARSE_DENSE, MG_COARSE_BCR = 0, 1
+MG_LEVEL_PROPER_COLORING, MG_LEVEL_NONZERO_DIAG = 1, 2
 
 
 class MgError(RuntimeError):
@@ -72,7 +73,8 @@ class mg_bcr_dist(ctypes.Structure):
 
 
 class mg_dist_norm(ctypes.Structure):
-    _fields_ = [("d_partials", c_vp), ("d_local", c_vp), ("d_slots", c_vp), ("d_norm2", c_vp)]
+    _fields_ = [("d_partials", c_vp), ("d_local", c_vp), ("d_slots", c_vp), ("d_norm2", c_vp),
+                ("after", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
 
 class mg_level(ctypes.Structure):
@@ -83,12 +85,14 @@ class mg_level(ctypes.Structure):
                 ("Q", mg_sell), ("QT", mg_sell),
                 ("d_x", c_vp), ("d_b", c_vp), ("d_r", c_vp), ("d_tmp", c_vp),
                 ("coarse_kind", ctypes.c_int32), ("d_coarse_inv", c_vp), ("coarse_bcr", c_vp),
-                ("dist", ctypes.POINTER(mg_dist_level)), ("coarse_bcr_dist", ctypes.POINTER(mg_bcr_dist))]
+                ("dist", ctypes.POINTER(mg_dist_level)), ("coarse_bcr_dist", ctypes.POINTER(mg_bcr_dist)),
+                ("flags", ctypes.c_uint32), ("pad_", ctypes.c_uint32), ("d_diag", c_vp)]
 
 
 class mg_cycle_params(ctypes.Structure):
     _fields_ = [("smoother", ctypes.c_int32), ("nu_pre", ctypes.c_int32), ("nu_post", ctypes.c_int32),
-                ("omega", c_dbl), ("zero_guess_skip", ctypes.c_int32), ("reverse_post", ctypes.c_int32)]
+                ("omega", c_dbl), ("zero_guess_skip", ctypes.c_int32), ("reverse_post", ctypes.c_int32),
+                ("x0_zero", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
 
 # name -> (restype, argtypes).  tests/test_abi.py checks that every function declared in include/mgb200.h is
@@ -107,7 +111,17 @@ _SIGNATURES = {
     "mg_gs_lex_sweep_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_int, c_vp]),
     "mg_prolong_correct_csr": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_sell_spmv": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
-    "mg_sell_slice_offsets": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp]),
+    "mg_sell_slice_offsets": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
+    "mg_set_implied_min_rows": (c_i64, [c_i64]),
+    "mg_level_inspect": (c_int, [ctypes.POINTER(mg_sell), c_int, c_vp, c_vp, c_vp, c_vp]),
+    "mg_sell_residual_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "mg_sell_gs_rows_tail": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp,
+                                     ctypes.POINTER(c_int), c_vp]),
+    "mg_sell_gs_tail_ok": (c_int, [ctypes.POINTER(mg_sell), c_i64, c_i64]),
+    "mg_sell_gs_zero_first": (c_int, [c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_vp]),
+    "mg_sell_prolong_correct_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
+    "mg_vcycle_norm": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp, c_vp, c_vp]),
+    "mg_set_cycle_fusion": (c_int, [c_int]),
     "mg_set_implied_columns": (c_int, [c_int]),
     "mg_sell_residual": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
     "mg_sell_residual_norm2": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -116,12 +130,6 @@ _SIGNATURES = {
     "mg_sell_halo_mask": (c_int, [ctypes.POINTER(mg_sell), c_i64, c_vp, c_vp]),
     "mg_set_fused_exchange": (c_int, [c_int]),
     "mg_set_push_exchange": (c_int, [c_int]),
-    "mg_set_tail_max_rows": (c_i64, [c_i64]),
-    "mg_set_tail_ctas_per_sm": (c_int, [c_int]),
-    "mg_tail_config_epoch": (c_i64, []),
-    "mg_tail_last_stats": (c_int, [c_vp, c_vp, c_vp]),
-    "mg_host_tail_vcycle": (c_int, [c_vp, c_int, c_vp, ctypes.c_uint64]),
-    "mg_tail_debug_drop_barriers": (c_int, [c_int]),
     "mg_set_wide_min_len": (c_i64, [c_i64]),
     "mg_set_wide_max_rows": (c_i64, [c_i64]),
     "mg_sell_jacobi": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
@@ -198,6 +206,7 @@ _SIGNATURES = {
     "mg_host_greedy_color_block": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
     "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
     "mg_color_workspace_size": (c_i64, [c_i64]),
+    "mg_csr_coloring_flags": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_color_first_fit": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "mg_host_color_rounds": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),
@@ -245,12 +254,14 @@ def load():
         lib.mg_set_fused_exchange(0)
     if os.environ.get("MGB_PUSH_EXCHANGE", "0") == "1":
         lib.mg_set_push_exchange(1)
-    if os.environ.get("MGB_IMPLIED_COLUMNS", "0") == "1":
-        lib.mg_set_implied_columns(1)
+    if os.environ.get("MGB_IMPLIED_COLUMNS", "1") == "0":
+        lib.mg_set_implied_columns(0)
+    if "MGB_IMPLIED_MIN_ROWS" in os.environ:
+        lib.mg_set_implied_min_rows(int(os.environ["MGB_IMPLIED_MIN_ROWS"]))
+    if os.environ.get("MGB_CYCLE_FUSION", "1") == "0":
+        lib.mg_set_cycle_fusion(0)
     if "MGB_WIDE_MIN_LEN" in os.environ:
         lib.mg_set_wide_min_len(int(os.environ["MGB_WIDE_MIN_LEN"]))
-    if "MGB_TAIL_MAX_ROWS" in os.environ:
-        lib.mg_set_tail_max_rows(int(os.environ["MGB_TAIL_MAX_ROWS"]))
     if "MGB_WIDE_MAX_ROWS" in os.environ:
         lib.mg_set_wide_max_rows(int(os.environ["MGB_WIDE_MAX_ROWS"]))
     _lib = lib

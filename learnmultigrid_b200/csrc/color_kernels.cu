@@ -130,6 +130,26 @@ jp_round_kernel(JpView v, const int32_t *cur, int32_t *next, int32_t *counters, 
 
 using namespace mgb;
 
+namespace mgb {
+__global__ void __launch_bounds__(kBlock)
+csr_coloring_flags_kernel(int64_t nrows, int64_t row0, const int32_t *__restrict__ indptr,
+                          const int32_t *__restrict__ indices, const double *__restrict__ values,
+                          const int32_t *__restrict__ color, int32_t *__restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (i >= nrows) return;
+    const int64_t gi = row0 + i;
+    const int32_t ci = color[gi];
+    int bad = 2;
+    for (int32_t p = indptr[i]; p < indptr[i + 1]; ++p) {
+        if (values[p] == 0.0) continue;
+        const int64_t j = indices[p];
+        if (j == gi) bad &= ~2;
+        else if (color[j] == ci) bad |= 1;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+}  // namespace mgb
+
 extern "C" {
 
 static JpView jp_view(int64_t n, const int32_t *ip, const int32_t *ix, const int32_t *tip, const int32_t *tix, char *work,
@@ -186,6 +206,21 @@ int mg_color_first_fit(int64_t n, const int32_t *d_indptr, const int32_t *d_indi
         if (r >= max_rounds) return set_error(MG_ERR_UNSUPPORTED, "mg_color_first_fit", "dependency chains too long for the round-based colouring");
     }
     if (h_rounds) *h_rounds = r;
+    return MG_OK;
+}
+
+/* Is a colouring proper for the operator, and has every row a diagonal?  Rows [0,nrows) of a CSR block whose row i is
+ * global row row0 + i; d_color is indexed by GLOBAL row / column id.  *d_flags (device int32, zeroed by the caller)
+ * |= 1 if a row has a non-zero entry in the column of another row of its own colour, |= 2 if a row has no non-zero
+ * diagonal entry.  This is what mg_level_inspect finds on a colour-blocked SELL level, asked of the operator in its
+ * natural ordering -- the form in which a partitioned level can ask it about the GLOBAL colouring. */
+int mg_csr_coloring_flags(int64_t nrows, int64_t row0, const int32_t *d_indptr, const int32_t *d_indices,
+                          const double *d_values, const int32_t *d_color, int32_t *d_flags, void *stream) {
+    MG_REQUIRE(nrows >= 0 && d_indptr && d_flags && d_color, "bad argument");
+    if (nrows == 0) return MG_OK;
+    csr_coloring_flags_kernel<<<(unsigned)((nrows + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
+        nrows, row0, d_indptr, d_indices, d_values, d_color, d_flags);
+    MG_CHECK_LAUNCH("csr_coloring_flags");
     return MG_OK;
 }
 

@@ -34,7 +34,8 @@ inline int set_error(int code, const char *what, const char *detail) {
         if (!(cond)) return mgb::set_error(MG_ERR_INVALID, __func__, msg);                    \
     } while (0)
 
-enum SellMode { SPMV = 0, RESID = 1, RESNORM = 2, JACOBI = 3, GS = 4, PROLONG = 5 };
+// GS_RES / GS_NORM: colour sweep that also yields the residual / the squared residual norm of the swept rows
+enum SellMode { SPMV = 0, RESID = 1, RESNORM = 2, JACOBI = 3, GS = 4, PROLONG = 5, GS_RES = 6, GS_NORM = 7 };
 
 constexpr int kSlice = 32;      // SELL slice height = one warp
 constexpr int kBlock = 256;     // threads per CTA of the streaming kernels

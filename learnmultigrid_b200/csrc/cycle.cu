@@ -4,40 +4,31 @@
 //   -> prolong + correct (:115) -> post-smooth (:121).
 // The Galerkin product (:97-98) and the coarse factorisation (:106), which the reference repeats in every
 // cycle, are hoisted to setup; the arithmetic of a cycle is unchanged.
-#include "exchange.cuh"
-#include "tail.cuh"
+#include "sell_api.cuh"
 
 namespace mgb {
 
-struct SellFuse {          // mirrors sell_kernels.cu
-    ExArgs ex;
-    int nex;
-    const unsigned char *mask;
-};
 int comm_prepare(mg_comm *, const mg_xfer *, const double *, double *, ExArgs *, int *);
-bool sell_fusable(const mg_sell *, int64_t, int64_t);
-int sell_spmv_fused(const mg_sell *, const double *, double *, const SellFuse *, cudaStream_t);
-int sell_residual_fused(const mg_sell *, const double *, const double *, double *, const SellFuse *, cudaStream_t);
-int sell_gs_rows_fused(const mg_sell *, double *, const double *, int64_t, int64_t, const SellFuse *, cudaStream_t);
-int sell_prolong_fused(const mg_sell *, const double *, const double *, double *, const SellFuse *, cudaStream_t);
-int sell_gs_rows_push(const mg_sell *, double *, const double *, int64_t, int64_t, const SellFuse *, const SellPush *, cudaStream_t);
 int comm_launch_prepared(const ExArgs &, int, cudaStream_t);
-int sell_residual_partials(const mg_sell *, const double *, const double *, double *, int *, cudaStream_t);
 int comm_norm_allreduce(mg_comm *, const double *, int64_t, double *, double *, double *, cudaStream_t);
 int g_fused_exchange = 1;
 int g_push_exchange = 0;     // producer-driven colour exchanges (mg_set_push_exchange); off by default
+// Work the multicolour cycle does not have to do (mg_set_cycle_fusion; results are the same bits either way):
+//  * the last colour sweep of the pre-smoothing also writes the residual of its own rows, so the residual pass only
+//    covers the other colours; likewise the last sweep of the post-smoothing on level 0 yields its rows' share of
+//    ||b - A x||^2 when the caller wants the norm of the new iterate (mg_vcycle_norm);
+//  * the prolongation skips the rows of the colour the post-smoothing sweeps first: a Gauss-Seidel update does not read
+//    the row's own old value, so whatever the correction added there is overwritten unread;
+//  * the first colour sweep on a zero iterate is x = b / diag without a pass over the matrix.
+// The first two need a proper colouring (no non-zero coupling inside a colour), the second also a non-zero diagonal in
+// every row: mg_level.flags, established by mg_level_inspect on the operator as stored.
+int g_cycle_fusion = 1;
 
 thread_local char g_last_error[512] = "";
 thread_local int64_t g_launch_count = 0;
 thread_local int64_t g_last_cycle_launches = 0;
 int g_pdl = 1;
 
-int sell_spmv(const mg_sell *, const double *, double *, cudaStream_t);
-int sell_residual(const mg_sell *, const double *, const double *, double *, cudaStream_t);
-int sell_residual_norm2(const mg_sell *, const double *, const double *, double *, double *, cudaStream_t);
-int sell_jacobi(const mg_sell *, const double *, const double *, const double *, double *, double, cudaStream_t);
-int sell_gs_rows(const mg_sell *, double *, const double *, int64_t, int64_t, cudaStream_t);
-int sell_prolong(const mg_sell *, const double *, const double *, double *, cudaStream_t);
 int vec_axpby(int64_t, double, const double *, double, const double *, double *, cudaStream_t);
 int vec_fill(int64_t, double, double *, cudaStream_t);
 int vec_diag_scale(int64_t, double, const double *, const double *, double *, cudaStream_t);
@@ -53,48 +44,6 @@ int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStre
         int _rc = (expr);       \
         if (_rc) return _rc;    \
     } while (0)
-
-// ---- tail program (tail.cu): on small replicated levels the operations are recorded and run by one persistent
-// cooperative kernel instead of one launch each.  The op_* wrappers below are what the cycle calls on levels that may
-// be recorded; outside a recording they are the plain launches.
-struct TailScope {          // ends a recording on every exit path of the frame that began it
-    bool on = false;
-    ~TailScope() { if (on) tail_end(); }
-};
-
-static int op_gs_rows(const mg_sell *A, double *x, const double *b, int64_t r0, int64_t r1, cudaStream_t st) {
-    if (tail_recording()) { tail_record_sell(GS, A, x, b, nullptr, x, 0.0, r0, r1); return MG_OK; }
-    return sell_gs_rows(A, x, b, r0, r1, st);
-}
-static int op_jacobi(const mg_sell *A, const double *dinv, const double *x, const double *b, double *xo, double omega,
-                     cudaStream_t st) {
-    if (tail_recording()) { tail_record_sell(JACOBI, A, x, b, dinv, xo, omega, 0, A->nrows); return MG_OK; }
-    return sell_jacobi(A, dinv, x, b, xo, omega, st);
-}
-static int op_residual(const mg_sell *A, const double *x, const double *b, double *r, cudaStream_t st) {
-    if (tail_recording()) { tail_record_sell(RESID, A, x, b, nullptr, r, 0.0, 0, A->nrows); return MG_OK; }
-    return sell_residual(A, x, b, r, st);
-}
-static int op_spmv(const mg_sell *A, const double *x, double *y, cudaStream_t st) {
-    if (tail_recording()) { tail_record_sell(SPMV, A, x, nullptr, nullptr, y, 0.0, 0, A->nrows); return MG_OK; }
-    return sell_spmv(A, x, y, st);
-}
-static int op_prolong(const mg_sell *Q, const double *e, const double *u, double *uo, cudaStream_t st) {
-    if (tail_recording()) { tail_record_sell(PROLONG, Q, e, nullptr, u, uo, 0.0, 0, Q->nrows); return MG_OK; }
-    return sell_prolong(Q, e, u, uo, st);
-}
-static int op_fill(int64_t n, double v, double *x, cudaStream_t st) {
-    if (tail_recording()) { tail_record_vector(T_FILL, n, v, nullptr, nullptr, nullptr, x); return MG_OK; }
-    return vec_fill(n, v, x, st);
-}
-static int op_diag_scale(int64_t n, double omega, const double *dinv, const double *b, double *out, cudaStream_t st) {
-    if (tail_recording()) { tail_record_vector(T_DIAG_SCALE, n, omega, nullptr, b, dinv, out); return MG_OK; }
-    return vec_diag_scale(n, omega, dinv, b, out, st);
-}
-static int op_copy(int64_t n, const double *src, double *dst, cudaStream_t st) {
-    if (tail_recording()) { tail_record_vector(T_COPY, n, 0.0, src, nullptr, nullptr, dst); return MG_OK; }
-    return vec_axpby(n, 1.0, src, 0.0, nullptr, dst, st);
-}
 
 // Deferred exchange: with multicolour Gauss-Seidel an exchange of a level vector is not launched when it is issued
 // but handed to the next SELL kernel that gathers from that vector, which carries it as extra CTAs (sell_kernel_fused).
@@ -172,13 +121,28 @@ static inline bool can_push(const mg_level &L, int64_t r0, int64_t r1) {
            D->d_push_pos && r1 > r0 && sell_fusable(&L.A, r0, r1);
 }
 
+// What the LAST colour sweep of a smoothing call should produce besides the new values of its rows (multicolour
+// Gauss-Seidel on a properly coloured level, see g_cycle_fusion): their residual, or their share of the squared
+// residual norm.  On return `done` tells whether it did; the rows [rest0, rest1) are then what a stand-alone pass
+// still has to cover.
+struct Tail {
+    int kind = TAIL_NONE;
+    double *r_out = nullptr;
+    double *partials = nullptr;
+    bool done = false;
+    int64_t rest0 = 0, rest1 = 0;
+    int nblocks = 0;
+};
+
+static inline bool level_proper(const mg_level &L) { return g_cycle_fusion && (L.flags & MG_LEVEL_PROPER_COLORING); }
+
 // `steps` smoothing sweeps on level L.  cur points at the buffer holding the iterate and is updated
 // (Jacobi ping-pongs between d_x and d_tmp).  zero_guess: the iterate is known to be exactly zero and the
 // buffer has NOT been initialised.
 static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, int steps, double **cur, double **alt,
-                  bool zero_guess, bool reverse, cudaStream_t st) {
+                  bool zero_guess, bool reverse, cudaStream_t st, Tail *tail = nullptr) {
     if (steps <= 0) {
-        if (zero_guess) MG_TRY(op_fill(vec_len(L), 0.0, *cur, st));
+        if (zero_guess) MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
         return MG_OK;
     }
     if (P.smoother == MG_SMOOTH_JACOBI) {
@@ -186,33 +150,49 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
         if (zero_guess) {
             if (P.zero_guess_skip) {
                 // x1 = 0 + omega*(dinv*(b - A*0)) = omega*(dinv*b): same bits as a sweep on zeros, no matrix pass
-                MG_TRY(op_diag_scale(L.n, P.omega, L.d_dinv, L.d_b, *alt, st));
+                MG_TRY(vec_diag_scale(L.n, P.omega, L.d_dinv, L.d_b, *alt, st));
                 MG_TRY(halo_all(comm, L, *alt, st));
                 double *t = *cur; *cur = *alt; *alt = t;
                 s = 1;
             } else {
-                MG_TRY(op_fill(vec_len(L), 0.0, *cur, st));
+                MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
             }
         }
         for (; s < steps; ++s) {
-            MG_TRY(op_jacobi(&L.A, L.d_dinv, *cur, L.d_b, *alt, P.omega, st));
+            MG_TRY(sell_jacobi(&L.A, L.d_dinv, *cur, L.d_b, *alt, P.omega, st));
             MG_TRY(halo_all(comm, L, *alt, st));
             double *t = *cur; *cur = *alt; *alt = t;
         }
         return MG_OK;
     }
-    if (zero_guess) MG_TRY(op_fill(vec_len(L), 0.0, *cur, st));
     if (P.smoother == MG_SMOOTH_MCGS) {
         if (L.ncolors <= 0 || !L.h_color_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no colouring");
         if (L.dist && L.dist->ncolors != L.ncolors) return set_error(MG_ERR_INVALID, "mg_vcycle", "halo plan and colouring disagree");
         for (int s = 0; s < steps; ++s)
             for (int cc = 0; cc < L.ncolors; ++cc) {
                 const int c = reverse ? L.ncolors - 1 - cc : cc;
+                const int64_t r0 = L.h_color_ptr[c], r1 = L.h_color_ptr[c + 1];
+                const bool first = s == 0 && cc == 0, last = s == steps - 1 && cc == L.ncolors - 1;
+                int tk = TAIL_NONE;
+                if (last && tail && tail->kind != TAIL_NONE && level_proper(L) && sell_gs_tail_ok(&L.A, r0, r1)) tk = tail->kind;
+                if (first && zero_guess) {
+                    if (g_cycle_fusion && P.zero_guess_skip && L.d_diag && tk == TAIL_NONE && r1 > r0) {
+                        // every entry the first colour reads is zero: x = b / diag for its rows, zeros elsewhere, in
+                        // one pass over the vector and none over the matrix (the bits of fill + sweep)
+                        MG_TRY(sell_gs_zero_first(vec_len(L), r0, r1, L.d_diag, L.d_b, *cur, st));
+                        if (L.dist) MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
+                        continue;
+                    }
+                    MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
+                }
+                double *r_out = tk == TAIL_RESIDUAL ? tail->r_out : nullptr;
+                double *partials = tk == TAIL_NORM ? tail->partials : nullptr;
+                int nb = 0;
                 if (L.dist) {
                     SellFuse f;
                     bool use;
-                    const int64_t r0 = L.h_color_ptr[c], r1 = L.h_color_ptr[c + 1];
                     MG_TRY(take_pending(comm, *cur, &L.A, r0, r1, L.dist->d_mask_A, &f, &use, st));
+                    bool pushed = false;
                     if (can_push(L, r0, r1)) {
                         // producer-driven: book this colour's site now (after the carried one, so that sites are
                         // consumed in the order they were booked); the kernel below stores the boundary values into
@@ -228,31 +208,37 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
                             push.pos = D.d_push_pos + D.h_push_ptr[c];
                             push.n = (int32_t)(D.h_push_ptr[c + 1] - D.h_push_ptr[c]);
                             push.tail_first = D.h_push_tail ? (int32_t)D.h_push_tail[c] : 0;
-                            MG_TRY(sell_gs_rows_push(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, &push, st));
+                            MG_TRY(sell_gs_rows_push(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, &push, tk, r_out, partials, &nb, st));
                             g_pend.x = D.xfer_color + c;
                             g_pend.vec = *cur;
                             g_pend.prepared = true;
                             g_pend.grid = grid;
                             g_pend.ex = push.ex;
                             g_pend.ex.recv_only = 1;
-                            continue;
+                            pushed = true;
                         }
-                        // no peers on this site: nothing to push or to receive
-                        if (use) MG_TRY(sell_gs_rows_fused(&L.A, *cur, L.d_b, r0, r1, &f, st));
-                        else MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, st));
-                        continue;
+                        // grid == 0: no peers on this site, nothing to push or to receive
+                        if (!pushed) MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, tk, r_out, partials, &nb, st));
+                    } else {
+                        MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, tk, r_out, partials, &nb, st));
+                        MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
                     }
-                    if (use) MG_TRY(sell_gs_rows_fused(&L.A, *cur, L.d_b, r0, r1, &f, st));
-                    else MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, st));
-                    MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
                 } else {
-                    MG_TRY(op_gs_rows(&L.A, *cur, L.d_b, L.h_color_ptr[c], L.h_color_ptr[c + 1], st));
+                    MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, nullptr, tk, r_out, partials, &nb, st));
+                }
+                if (tk != TAIL_NONE) {
+                    tail->done = true;
+                    tail->nblocks = nb;
+                    // the swept colour is the first or the last block, what is left is one range
+                    tail->rest0 = c == 0 ? r1 : 0;
+                    tail->rest1 = c == 0 ? L.n : r0;
+                    if (c != 0 && c != L.ncolors - 1) return set_error(MG_ERR_INVALID, "mg_vcycle", "internal: tail colour in the middle");
                 }
             }
         return MG_OK;
     }
+    if (zero_guess) MG_TRY(vec_fill(vec_len(L), 0.0, *cur, st));
     if (P.smoother == MG_SMOOTH_LEXGS) {
-        if (tail_recording()) return set_error(MG_ERR_UNSUPPORTED, "mg_vcycle", "index-order Gauss-Seidel cannot be part of a tail program");
         if (L.dist) return set_error(MG_ERR_UNSUPPORTED, "mg_vcycle", "index-order Gauss-Seidel is serial across row blocks; not available on partitioned levels");
         if (!L.d_csr_indptr || !L.d_lex_level_ptr) return set_error(MG_ERR_INVALID, "mg_vcycle", "level has no lexicographic schedule");
         return csr_gs_lex(L.d_csr_indptr, L.d_csr_indices, L.d_csr_values, *cur, L.d_b, L.d_lex_level_ptr,
@@ -261,20 +247,16 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
     return set_error(MG_ERR_INVALID, "mg_vcycle", "unknown smoother");
 }
 
+// the squared residual norm of the iterate the cycle leaves on level 0, as per-CTA partial sums (mg_vcycle_norm)
+struct NormOut {
+    double *partials;
+    int nblocks;
+};
+
 static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l, const mg_cycle_params &P,
-                      cudaStream_t st) {
+                      cudaStream_t st, NormOut *norm = nullptr) {
     const mg_level &L = levels[l];
     if (l == nlevels - 1) {   // coarsest: direct solve (Multigrid.py:106)
-        MG_TRY(tail_flush(st));                                      // a recorded tail runs before the solve's own kernels
-        if (tail_host_mode()) {                                      // CPU test-suite: dense inverse applied on the host
-            if (L.coarse_kind != MG_COARSE_DENSE || !L.d_coarse_inv) return set_error(MG_ERR_UNSUPPORTED, "mg_host_tail_vcycle", "host mode needs a dense coarsest inverse");
-            for (int64_t i = 0; i < L.n; ++i) {
-                double acc = 0.0;
-                for (int64_t j = 0; j < L.n; ++j) acc += L.d_coarse_inv[i * L.n + j] * L.d_b[j];
-                L.d_x[i] = acc;
-            }
-            return MG_OK;
-        }
         if (L.coarse_kind == MG_COARSE_DENSE) {
             if (!L.d_coarse_inv) return set_error(MG_ERR_INVALID, "mg_vcycle", "coarsest level has no inverse");
             return dense_gemv(L.n, L.n, L.d_coarse_inv, L.d_b, L.d_x, st);
@@ -284,7 +266,8 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
     }
     const mg_level &C = levels[l + 1];
     const bool jac = P.smoother == MG_SMOOTH_JACOBI;
-    const bool zero_guess = l > 0;
+    const bool mcgs = P.smoother == MG_SMOOTH_MCGS;
+    const bool zero_guess = l > 0 || P.x0_zero != 0;
     double *cur = L.d_x, *alt = L.d_tmp;
     bool prolong_flip = false;
     if (jac) {
@@ -297,56 +280,75 @@ static int vcycle_rec(mg_comm *comm, const mg_level *levels, int nlevels, int l,
         }
     }
     if (!L.dist) MG_TRY(flush_pending(comm, st));                    // replicated level: nothing may be in flight
-    // from the first level that is small enough (and replicated, like everything below it) the operations are recorded
-    // into a tail program; the frame that starts the recording flushes and ends it
-    TailScope tail;
-    if (!tail_recording() && tail_max_rows() > 0 && !L.dist && L.n <= tail_max_rows() &&
-        (P.smoother == MG_SMOOTH_JACOBI || P.smoother == MG_SMOOTH_MCGS)) {
-        tail_begin(false, 0);
-        tail.on = true;
-    }
-    const bool defer = P.smoother == MG_SMOOTH_MCGS;                 // exchanges ride on the next SELL kernel
+    const bool defer = mcgs;                                         // exchanges ride on the next SELL kernel
     SellFuse f;
     bool use = false;
-    MG_TRY(smooth(comm, L, P, P.nu_pre, &cur, &alt, zero_guess, false, st));
+    // ---- pre-smoothing; its last colour sweep also writes the residual of its rows
+    Tail pre;
+    if (mcgs && P.nu_pre > 0) {
+        pre.kind = TAIL_RESIDUAL;
+        pre.r_out = L.d_r;
+    }
+    MG_TRY(smooth(comm, L, P, P.nu_pre, &cur, &alt, zero_guess, false, st, &pre));
+    int64_t q0 = 0, q1 = L.A.nrows;                                  // rows whose residual is still to be formed
+    if (pre.done) { q0 = pre.rest0; q1 = pre.rest1; }
     if (L.dist) {
         const mg_dist_level &D = *L.dist;
-        MG_TRY(take_pending(comm, cur, &L.A, 0, L.A.nrows, D.d_mask_A, &f, &use, st));
-        if (use) MG_TRY(sell_residual_fused(&L.A, cur, L.d_b, L.d_r, &f, st));       // res = rhs - A u
-        else MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, st));
+        MG_TRY(take_pending(comm, cur, &L.A, q0, q1, D.d_mask_A, &f, &use, st));
+        MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, q0, q1, use ? &f : nullptr, st));      // res = rhs - A u
         MG_TRY(issue_exchange(comm, D.xfer_all, L.d_r, defer, st));                  // the restriction reads halo rows
         // last partitioned level: restrict into the owned block of the coarse rhs, then gather it into every
         // rank's full vector (the coarse levels below are replicated)
         double *rc = D.xfer_gather ? D.d_gather_tmp : C.d_b;
         MG_TRY(take_pending(comm, L.d_r, &L.QT, 0, L.QT.nrows, D.d_mask_QT, &f, &use, st));
-        if (use) MG_TRY(sell_spmv_fused(&L.QT, L.d_r, rc, &f, st));                  // res_coarse = Q^T res (owned rows)
-        else MG_TRY(sell_spmv(&L.QT, L.d_r, rc, st));
+        MG_TRY(sell_spmv(&L.QT, L.d_r, rc, 0, L.QT.nrows, use ? &f : nullptr, st));  // res_coarse = Q^T res (owned rows)
         if (D.xfer_gather) {
             MG_TRY(vec_scatter(D.n_gather_own, D.d_gather_self_idx, D.d_gather_tmp, C.d_b, st));
             MG_TRY(comm_exchange(comm, D.xfer_gather, D.d_gather_tmp, C.d_b, st));
         }
     } else {
-        MG_TRY(op_residual(&L.A, cur, L.d_b, L.d_r, st));            // res = rhs - A u
-        MG_TRY(op_spmv(&L.QT, L.d_r, C.d_b, st));                    // res_coarse = Q^T res
+        MG_TRY(sell_residual(&L.A, cur, L.d_b, L.d_r, q0, q1, nullptr, st));         // res = rhs - A u
+        MG_TRY(sell_spmv(&L.QT, L.d_r, C.d_b, 0, L.QT.nrows, nullptr, st));          // res_coarse = Q^T res
     }
-    MG_TRY(vcycle_rec(comm, levels, nlevels, l + 1, P, st));         // u_coarse
+    mg_cycle_params Pc = P;
+    Pc.x0_zero = 0;                                                  // below level 0 the guess is zero anyway
+    MG_TRY(vcycle_rec(comm, levels, nlevels, l + 1, Pc, st));        // u_coarse
     double *out = prolong_flip ? alt : cur;                          // u = u + Q u_coarse (out of place when flipping)
+    // The colour the post-smoothing sweeps first is overwritten without being read: its rows need no correction.
+    int64_t p0 = 0, p1 = L.Q.nrows;
+    if (mcgs && P.nu_post > 0 && level_proper(L) && (L.flags & MG_LEVEL_NONZERO_DIAG) && L.ncolors > 0 && L.h_color_ptr) {
+        if (P.reverse_post) p1 = L.h_color_ptr[L.ncolors - 1];
+        else p0 = L.h_color_ptr[1];
+    }
     if (L.dist) {
         // a partitioned coarse level leaves the exchange of its last sweep pending on C.d_x
-        MG_TRY(take_pending(comm, C.d_x, &L.Q, 0, L.Q.nrows, L.dist->d_mask_Q, &f, &use, st));
-        if (use) MG_TRY(sell_prolong_fused(&L.Q, C.d_x, cur, out, &f, st));
-        else MG_TRY(sell_prolong(&L.Q, C.d_x, cur, out, st));
+        MG_TRY(take_pending(comm, C.d_x, &L.Q, p0, p1, L.dist->d_mask_Q, &f, &use, st));
+        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, out, p0, p1, use ? &f : nullptr, st));
     } else {
-        MG_TRY(op_prolong(&L.Q, C.d_x, cur, out, st));
+        MG_TRY(sell_prolong(&L.Q, C.d_x, cur, out, p0, p1, nullptr, st));
     }
     if (prolong_flip) { double *t = cur; cur = alt; alt = t; }
     // every boundary value changed.  Deferred, this exchange rides on the first post-smoothing sweep, which rewrites
     // its own colour while the values are being sent: harmless, a colour never reads itself and is sent again right
     // after its sweep.
     if (L.dist) MG_TRY(issue_exchange(comm, L.dist->xfer_all, cur, defer, st));
-    MG_TRY(smooth(comm, L, P, P.nu_post, &cur, &alt, false, P.reverse_post != 0, st));
-    if (cur != L.d_x) MG_TRY(op_copy(vec_len(L), cur, L.d_x, st));   // safety net; not reached
-    if (tail.on) MG_TRY(tail_flush(st));
+    // ---- post-smoothing; on level 0 its last colour sweep can yield its rows' share of the new residual norm
+    Tail post;
+    if (norm && mcgs && P.nu_post > 0) {
+        post.kind = TAIL_NORM;
+        post.partials = norm->partials;
+    }
+    MG_TRY(smooth(comm, L, P, P.nu_post, &cur, &alt, false, P.reverse_post != 0, st, &post));
+    if (cur != L.d_x) MG_TRY(vec_axpby(vec_len(L), 1.0, cur, 0.0, nullptr, L.d_x, st));   // safety net; not reached
+    if (norm) {
+        int64_t n0 = 0, n1 = L.A.nrows;
+        int nb = 0, nb2 = 0;
+        if (post.done) { n0 = post.rest0; n1 = post.rest1; nb = post.nblocks; }
+        use = false;
+        if (L.dist) MG_TRY(take_pending(comm, L.d_x, &L.A, n0, n1, L.dist->d_mask_A, &f, &use, st));
+        MG_TRY(sell_residual_partials(&L.A, L.d_x, L.d_b, norm->partials + nb, n0, n1, &nb2, use ? &f : nullptr, st));
+        norm->nblocks = nb + nb2;
+    }
     return MG_OK;
 }
 
@@ -380,7 +382,7 @@ using namespace mgb;
 
 extern "C" {
 
-int mg_version(void) { return 100; }
+int mg_version(void) { return 200; }
 int mg_set_fused_exchange(int enabled) {
     const int prev = g_fused_exchange;
     g_fused_exchange = enabled ? 1 : 0;
@@ -389,6 +391,11 @@ int mg_set_fused_exchange(int enabled) {
 int mg_set_push_exchange(int enabled) {
     const int prev = g_push_exchange;
     g_push_exchange = enabled ? 1 : 0;
+    return prev;
+}
+int mg_set_cycle_fusion(int enabled) {
+    const int prev = g_cycle_fusion;
+    g_cycle_fusion = enabled ? 1 : 0;
     return prev;
 }
 int mg_set_pdl(int enabled) {
@@ -426,8 +433,19 @@ int mg_device_info(int *sm, int64_t *mem, int *cc) {
 int mg_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, void *stream) {
     MG_TRY(check_levels(levels, nlevels, params, false));
     const int64_t before = g_launch_count;
-    tail_stats_reset();
     int rc = vcycle_rec(nullptr, levels, nlevels, 0, *params, (cudaStream_t)stream);
+    g_last_cycle_launches = g_launch_count - before;
+    return rc;
+}
+
+int mg_vcycle_norm(const mg_level *levels, int nlevels, const mg_cycle_params *params, double *d_partials,
+                   double *d_norm2, void *stream) {
+    MG_TRY(check_levels(levels, nlevels, params, false));
+    MG_REQUIRE(d_partials && d_norm2, "norm workspace missing");
+    const int64_t before = g_launch_count;
+    NormOut no{d_partials, 0};
+    int rc = vcycle_rec(nullptr, levels, nlevels, 0, *params, (cudaStream_t)stream, &no);
+    if (!rc) rc = sell_reduce_partials(d_partials, no.nblocks, d_norm2, (cudaStream_t)stream);
     g_last_cycle_launches = g_launch_count - before;
     return rc;
 }
@@ -440,24 +458,32 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     else MG_REQUIRE(levels && nlevels >= 1, "no level");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t before = g_launch_count;
-    tail_stats_reset();
     MG_TRY(mg_comm_begin(comm));
     g_pend.x = nullptr;
     g_pend.prepared = false;
     int rc = MG_OK;
-    if (norm) {   // outer loop of Multigrid.solve (:62-63): ||b - A x||^2 over all row blocks
-        MG_REQUIRE(norm->d_partials && norm->d_local && norm->d_slots && norm->d_norm2, "norm workspace missing");
-        if (g_push_exchange && comm->world > 1 && levels[0].A.nrows > 0) {
-            // latency mode: the second stage of the norm and its all-reduce are one single-CTA kernel
-            int nblocks = 0;
-            rc = sell_residual_partials(&levels[0].A, levels[0].d_x, levels[0].d_b, norm->d_partials, &nblocks, st);
-            if (!rc) rc = comm_norm_allreduce(comm, norm->d_partials, nblocks, norm->d_local, norm->d_slots, norm->d_norm2, st);
-        } else {
-            rc = sell_residual_norm2(&levels[0].A, levels[0].d_x, levels[0].d_b, norm->d_partials, norm->d_local, st);
-            if (!rc) rc = mg_comm_allreduce_sum(comm, norm->d_local, norm->d_slots, norm->d_norm2, stream);
-        }
+    if (norm) MG_REQUIRE(norm->d_partials && norm->d_local && norm->d_slots && norm->d_norm2, "norm workspace missing");
+    const bool after = norm && norm->after && params;
+    // second stage of a norm whose per-CTA partials are in norm->d_partials, and its all-reduce
+    auto finish_norm = [&](int nblocks) -> int {
+        if (g_push_exchange && comm->world > 1 && nblocks > 0)   // latency mode: one single-CTA kernel
+            return comm_norm_allreduce(comm, norm->d_partials, nblocks, norm->d_local, norm->d_slots, norm->d_norm2, st);
+        int r = sell_reduce_partials(norm->d_partials, nblocks, norm->d_local, st);
+        if (!r) r = mg_comm_allreduce_sum(comm, norm->d_local, norm->d_slots, norm->d_norm2, stream);
+        return r;
+    };
+    if (norm && !after) {   // outer loop of Multigrid.solve (:62-63): ||b - A x||^2 over all row blocks
+        int nblocks = 0;
+        rc = sell_residual_partials(&levels[0].A, levels[0].d_x, levels[0].d_b, norm->d_partials, 0, levels[0].A.nrows,
+                                    &nblocks, nullptr, st);
+        if (!rc) rc = finish_norm(nblocks);
     }
-    if (!rc && params) rc = vcycle_rec(comm, levels, nlevels, 0, *params, st);
+    NormOut no{norm ? norm->d_partials : nullptr, 0};
+    if (!rc && params) rc = vcycle_rec(comm, levels, nlevels, 0, *params, st, after ? &no : nullptr);
+    if (!rc && after) {     // the norm of the NEW iterate, its last colour's share already summed by the last sweep
+        rc = flush_pending(comm, st);
+        if (!rc) rc = finish_norm(no.nblocks);
+    }
     if (!rc) rc = flush_pending(comm, st);      // the halo of the iterate is current when the program ends
     g_pend.x = nullptr;
     g_pend.prepared = false;
@@ -467,23 +493,6 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
 }
 
 int64_t mg_last_launch_count(void) { return g_last_cycle_launches; }
-
-/* The V-cycle with EVERY level recorded into a tail program and executed serially on the HOST (all pointers of the
- * mg_level array are host pointers; multicolour Gauss-Seidel or Jacobi; dense coarsest inverse).  This is how the CPU
- * test-suite checks the recorder, the placement of the grid barriers (shuffle != 0: the rows of every barrier-free
- * group of operations run in a pseudo-random order) and the per-row arithmetic of tail.cu without a GPU.  Not called
- * by the product. */
-int mg_host_tail_vcycle(const mg_level *levels, int nlevels, const mg_cycle_params *params, uint64_t shuffle) {
-    MG_TRY(check_levels(levels, nlevels, params, false));
-    MG_REQUIRE(params->smoother == MG_SMOOTH_JACOBI || params->smoother == MG_SMOOTH_MCGS, "Jacobi or multicolour Gauss-Seidel only");
-    tail_stats_reset();
-    tail_begin(true, shuffle);
-    TailScope scope;
-    scope.on = true;
-    int rc = vcycle_rec(nullptr, levels, nlevels, 0, *params, nullptr);
-    if (!rc) rc = tail_flush(nullptr);
-    return rc;
-}
 
 int mg_graph_begin(void *stream) {
     MG_CHECK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));

@@ -145,6 +145,13 @@ __device__ __forceinline__ void push_row_if_listed(const SellPush &P, int64_t ro
     for (; lo < P.n && P.rows[lo] == row; ++lo) push_boundary_value(P.ex, P.peer[lo], P.pos[lo], v);
 }
 
+// an exchange site riding on a SELL launch (prepared by comm_prepare)
+struct SellFuse {
+    ExArgs ex;
+    int nex;                       // exchange CTAs in front of the compute CTAs
+    const unsigned char *mask;     // per slice of the matrix: reads halo columns (NULL: assume every slice does)
+};
+
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");

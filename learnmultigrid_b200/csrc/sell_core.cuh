@@ -1,0 +1,582 @@
+// sell_core.cuh -- the streaming hot-path kernels on the SELL-32 format (see include/mgb200.h) and their launcher.
+//
+// One thread per row, one warp per slice.  Entry k of the 32 rows of a slice is contiguous
+// (256 B of values + 128 B of columns per warp request), so the matrix streams fully coalesced; the x
+// gathers go through L1/L2, which hold the few grid lines a structured stencil touches.
+// Every kernel is HBM-bound: algorithmic bytes per row = 12*nnz_row + 4 (CSR yardstick of SURVEY 8d) plus
+// the vector traffic listed at each launcher.
+//
+// The templates are instantiated per group of modes in sell_kernels.cu / sell_modes_gs.cu / sell_modes_vec.cu (three
+// translation units so that the ~500 specialisations compile in parallel).
+#pragma once
+#include "exchange.cuh"
+#include "sell_api.cuh"
+
+namespace mgb {
+
+struct SellArgs {
+    const int64_t *__restrict__ slice_ptr;
+    const int32_t *__restrict__ cols;
+    const double *__restrict__ vals;
+    const int32_t *__restrict__ slice_off;   // implied columns (IMPL kernels): [nslices][LEN] offsets, see below
+    int64_t row_begin;   // first row this launch touches
+    int64_t row_end;     // one past the last row
+    int64_t first_row;   // row of thread 0 of block 0 (row_begin rounded down to a slice)
+    int64_t nrows;       // rows of the matrix (rows of the last slice beyond it hold no data)
+    double *r_out;       // GS_RES: where the residual of the swept rows goes
+};
+
+__host__ __device__ constexpr bool mode_is_gs(int m) { return m == GS || m == GS_RES || m == GS_NORM; }
+__host__ __device__ constexpr bool mode_has_partials(int m) { return m == RESNORM || m == GS_NORM; }
+
+// ---- implied columns ------------------------------------------------------------------------------------------------
+// On a structured stencil level nearly every slice is REGULAR: entry j of every one of its 32 rows has column
+// row + off[j] with ONE offset table for the slice (mg_sell_slice_offsets; formats.sell_slice_offsets is the host twin).
+// For those slices the IMPL kernels compute the columns instead of streaming them: 4*LEN bytes of offsets per slice
+// in place of 128*LEN bytes of column indices, i.e. 64 instead of 88 bytes per 5-point row -- and the x gathers of a
+// warp become contiguous 256-byte reads.  The values, the gathers and the order of the additions are untouched, so the
+// results are the same bits; slices that are not regular (a boundary node among the rows, the ragged tail) take the
+// ordinary path inside the same kernel.  Uniform matrices with at most 8 entries per row only.
+constexpr int32_t kSliceIrregular = INT32_MIN;
+
+// What the epilogue of a row needs besides the row sum.
+struct SellEp {
+    const double *__restrict__ b;
+    const double *aux;
+    double *y;
+    double omega;
+};
+
+// One row of at most LEN entries, everything in registers and in straight-line code: all cols/vals loads are issued
+// first, then all x gathers, then the sums in storage order (LEN*12 bytes per thread in flight at ~4 registers per
+// entry).  PRED: the slice holds len < LEN entries per row (non-uniform matrices), loads and sums are predicated on
+// j < len (warp-uniform).  IMPL: the columns are row + o[j] (regular slice of an implied-columns matrix).
+// `halo_wait` (launches carrying an exchange site): this slice reads halo columns, so between the matrix loads (which
+// do not depend on the halo and are already in flight) and the x gathers, wait until the launch's exchange CTAs have
+// unpacked it.
+// Gauss-Seidel modes: the diagonal entry is skipped in the sum and divides it (PyAMG gauss_seidel); GS_RES / GS_NORM
+// then form r = b - A x of the row WITH its new value from the registers that still hold the row -- the row's
+// residual costs no second pass over the matrix.  That is exact because a properly coloured sweep changes no other
+// entry this row reads (cycle.cu only asks for it on such levels), and it adds the products in storage order with the
+// diagonal in its place, i.e. it is the residual kernel's arithmetic.
+template <int MODE, int LEN, bool PRED, bool IMPL>
+__device__ __forceinline__ void short_row(const SellArgs &A, const int32_t *__restrict__ c, const double *__restrict__ v,
+                                          const int32_t *__restrict__ o, int32_t o0, int len, const double *x, int64_t row,
+                                          bool active, const SellEp &E, double &contrib, unsigned char halo_wait,
+                                          const ExArgs *fx) {
+    int32_t cc[LEN];
+    double vv[LEN], xx[LEN];
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) {
+        if (!PRED || j < len) {
+            vv[j] = ld_stream(v + j * kSlice);
+            if (!IMPL) cc[j] = ld_stream(c + j * kSlice);
+        }
+    }
+    if (IMPL) {
+        cc[0] = (int32_t)row + o0;
+#pragma unroll
+        for (int j = 1; j < LEN; ++j) cc[j] = (int32_t)row + __ldg(o + j);
+    }
+    if (halo_wait) fused_wait_ready(*fx);
+#pragma unroll
+    for (int j = 0; j < LEN; ++j)
+        if (!PRED || j < len) xx[j] = x[cc[j]];
+    double sum = 0.0, diag = 0.0;
+    // GS_RES / GS_NORM keep the separately rounded products (the VALUE for a diagonal entry, flagged in dmask) instead
+    // of the row itself: 2 registers per entry across the division instead of 5
+    double pp[(MODE == GS_RES || MODE == GS_NORM) ? LEN : 1];
+    unsigned dmask = 0;
+#pragma unroll
+    for (int j = 0; j < LEN; ++j) {
+        if (!PRED || j < len) {
+            if (MODE == GS) {
+                if (cc[j] == (int32_t)row) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
+            } else if (MODE == GS_RES || MODE == GS_NORM) {
+                if (cc[j] == (int32_t)row) {
+                    if (vv[j] != 0.0) diag = vv[j];
+                    pp[j] = vv[j];
+                    dmask |= 1u << j;
+                } else {
+                    pp[j] = __dmul_rn(vv[j], xx[j]);
+                    sum = __dadd_rn(sum, pp[j]);
+                }
+            } else {
+                sum = mul_add_unfused(sum, vv[j], xx[j]);
+            }
+        }
+    }
+    if (!active) return;
+    if (MODE == SPMV) {
+        E.y[row] = sum;
+    } else if (MODE == RESID) {
+        E.y[row] = __dsub_rn(E.b[row], sum);
+    } else if (MODE == RESNORM) {
+        const double r = __dsub_rn(E.b[row], sum);
+        contrib = r * r;
+    } else if (MODE == JACOBI) {
+        const double r = __dsub_rn(E.b[row], sum);
+        E.y[row] = __dadd_rn(x[row], __dmul_rn(E.omega, __dmul_rn(E.aux[row], r)));
+    } else if (MODE == PROLONG) {
+        E.y[row] = __dadd_rn(E.aux[row], sum);   // aux = u (may alias y)
+    } else {                             // Gauss-Seidel family
+        const double bv = E.b[row];
+        const bool upd = diag != 0.0;
+        double xn = 0.0;
+        if (upd) {
+            xn = __ddiv_rn(__dsub_rn(bv, sum), diag);
+            E.y[row] = xn;
+        }
+        if (MODE == GS_RES || MODE == GS_NORM) {
+            // residual of the row with its new value: the products in storage order, the diagonal entry times the new
+            // iterate in its place.  A diagonal entry of a row that was not updated is a stored zero: its product is
+            // an exact zero, and adding it would change nothing (a sum that starts at +0 never becomes -0).
+            double s2 = 0.0;
+#pragma unroll
+            for (int j = 0; j < LEN; ++j)
+                if (!PRED || j < len) {
+                    if (dmask & (1u << j)) { if (upd) s2 = __dadd_rn(s2, __dmul_rn(pp[j], xn)); }
+                    else s2 = __dadd_rn(s2, pp[j]);
+                }
+            const double r = __dsub_rn(bv, s2);
+            if (MODE == GS_RES) A.r_out[row] = r;
+            else contrib = r * r;
+        }
+    }
+}
+
+// CNT consecutive entries of a long row (LEN == 0 kernels): loads first, then gathers, then the sums
+template <int MODE, int CNT>
+__device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const double *__restrict__ v,
+                                          const double *x, int64_t row, double &sum, double &diag,
+                                          unsigned char halo_wait = 0, const ExArgs *fx = nullptr) {
+    int32_t cc[CNT];
+    double vv[CNT], xx[CNT];
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+        cc[j] = ld_stream(c + j * kSlice);
+        vv[j] = ld_stream(v + j * kSlice);
+    }
+    if (halo_wait) fused_wait_ready(*fx);
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) xx[j] = x[cc[j]];
+#pragma unroll
+    for (int j = 0; j < CNT; ++j) {
+        if (MODE == GS) {
+            if (cc[j] == row) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
+        } else {
+            sum = mul_add_unfused(sum, vv[j], xx[j]);
+        }
+    }
+}
+
+// LEN   : the matrix' longest slice when it is <= 8 (short_row), 0 for longer rows (chunks of 4 + rolled remainder;
+//         not for GS_RES / GS_NORM, which need the whole row in registers).
+// UNIFORM: every slice of the matrix has exactly LEN entries, so the slice offset is computed instead of loaded.
+// IMPL  : implied columns for the regular slices (UNIFORM matrices only).
+// The microbenchmark behind these choices is tools/sellbench.cu (profiles/r01_sellbench.log): occupancy x bytes in
+// flight per thread decides; at 32 registers and 60 B per thread the fine-level sweep reaches the DRAM limit
+// (6.8 TB/s algorithmic, ~7.1 TB/s of actual traffic), a rolled loop stays at 5.4 TB/s.
+template <int MODE, int LEN, bool UNIFORM, bool FUSED, bool IMPL>
+__device__ __forceinline__ void
+sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
+          double *__restrict__ partials, int64_t bid, const ExArgs *fx, const unsigned char *__restrict__ mask) {
+    static_assert(!IMPL || (UNIFORM && LEN > 0), "implied columns need a uniform matrix with short rows");
+    static_assert(LEN > 0 || MODE <= PROLONG, "fused residual modes need the row in registers");
+    const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
+    const bool active = row >= A.row_begin && row < A.row_end;
+    double contrib = 0.0;
+    if (row < A.row_end) {   // warp-uniform except in the last slice
+        const int64_t slice = row >> 5;
+        const int lane = (int)(row & 31);
+        unsigned char hw = 0;      // fused launch: does this slice read halo columns? (load issued now, used later)
+        if (FUSED) hw = mask ? mask[slice] : 1;
+        int64_t base;
+        int len;
+        if (UNIFORM) {
+            base = slice * (int64_t)(kSlice * LEN);
+            len = LEN;
+        } else {
+            base = A.slice_ptr[slice];
+            len = (int)((A.slice_ptr[slice + 1] - base) >> 5);
+        }
+        const double *__restrict__ v = A.vals + base + lane;
+        const int32_t *__restrict__ c = A.cols + base + lane;
+        if (LEN > 0) {
+            constexpr int L = LEN > 0 ? LEN : 1;
+            const SellEp E{b, aux, y, omega};
+            if (IMPL) {
+                const int32_t *__restrict__ o = A.slice_off + slice * L;
+                const int32_t o0 = __ldg(o);
+                if (o0 != kSliceIrregular) short_row<MODE, L, false, true>(A, c, v, o, o0, L, x, row, active, E, contrib, hw, fx);
+                else short_row<MODE, L, false, false>(A, c, v, nullptr, 0, L, x, row, active, E, contrib, hw, fx);
+            } else if (UNIFORM || len == L) {
+                short_row<MODE, L, false, false>(A, c, v, nullptr, 0, L, x, row, active, E, contrib, hw, fx);
+            } else {
+                short_row<MODE, L, true, false>(A, c, v, nullptr, 0, len, x, row, active, E, contrib, hw, fx);
+            }
+        } else {
+            double sum = 0.0, diag = 0.0;
+            int k = 0;
+            for (; k + 4 <= len; k += 4) {
+                row_chunk<MODE, 4>(c + k * kSlice, v + k * kSlice, x, row, sum, diag, hw, fx);
+                hw = 0;
+            }
+            for (; k < len; ++k) {
+                row_chunk<MODE, 1>(c + k * kSlice, v + k * kSlice, x, row, sum, diag, hw, fx);
+                hw = 0;
+            }
+            if (active) {
+                if (MODE == SPMV) {
+                    y[row] = sum;
+                } else if (MODE == RESID) {
+                    y[row] = __dsub_rn(b[row], sum);
+                } else if (MODE == RESNORM) {
+                    const double r = __dsub_rn(b[row], sum);
+                    contrib = r * r;
+                } else if (MODE == JACOBI) {
+                    const double r = __dsub_rn(b[row], sum);
+                    y[row] = __dadd_rn(x[row], __dmul_rn(omega, __dmul_rn(aux[row], r)));
+                } else if (MODE == GS) {
+                    if (diag != 0.0) y[row] = __ddiv_rn(__dsub_rn(b[row], sum), diag);
+                } else if (MODE == PROLONG) {
+                    y[row] = __dadd_rn(aux[row], sum);   // aux = u (may alias y)
+                }
+            }
+        }
+    }
+    if (mode_has_partials(MODE)) {
+        const double s = block_sum<kBlock>(contrib);
+        if (threadIdx.x == 0) partials[bid] = s;
+    }
+}
+
+// resident CTAs per SM the compiler has to leave room for: the sweeps with a fused residual keep the row's products
+// alive across the division and take 41-48 registers (5 CTAs) when left alone; capped at 40 (6 CTAs) where ptxas
+// manages that without spilling (build/sell_modes_gs.ptxas.log)
+__host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform) {
+    return (m > PROLONG && (len <= 5 || (uniform && len <= 7))) ? 6 : 1;
+}
+
+template <int MODE, int LEN, bool UNIFORM, bool IMPL>
+__global__ void __launch_bounds__(kBlock, mode_min_ctas(MODE, LEN, UNIFORM))
+sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
+            double *y, double omega, double *__restrict__ partials) {
+    pdl_prologue();
+    sell_body<MODE, LEN, UNIFORM, false, IMPL>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
+}
+
+// The same kernel carrying an exchange site (multi-GPU, csrc/comm.cu): the first npeers*ctas_per_peer CTAs push the
+// boundary values the previous kernel produced, poll for the peers' packets and unpack them into the halo of x; the
+// compute CTAs whose slice reads halo columns (mask) wait for that, all others start at once.  The exchange latency
+// (NVLink flight + polling) is hidden behind the interior rows, and the site costs no launch of its own.
+template <int MODE, int LEN, bool UNIFORM, bool IMPL>
+__global__ void __launch_bounds__(kBlock)
+sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
+                  double *__restrict__ partials, const ExArgs fx, const unsigned char *__restrict__ mask) {
+    pdl_prologue();
+    const int nex = fx.npeers * fx.ctas_per_peer;
+    if ((int)blockIdx.x < nex) {
+        fused_exchange_cta(fx, (int)blockIdx.x);
+        if (mode_has_partials(MODE)) {}      // exchange CTAs own no partial sum
+        return;
+    }
+    sell_body<MODE, LEN, UNIFORM, true, IMPL>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
+}
+
+// Colour sweep of a partitioned level that PUSHES its own boundary values (producer-driven exchange, exchange.cuh):
+// the compute CTAs run the rows next to the upper neighbour first (tail_first), every thread whose row is in the
+// colour's send table stores its new value straight into the peer's staging slot, and the NVLink flight overlaps the
+// interior rows of this very kernel.  CARRY: the launch also carries the previous site as extra CTAs, exactly like
+// sell_kernel_fused.  Same values, same packets, same receiving code (mg_set_push_exchange).
+template <int MODE, int LEN, bool UNIFORM, bool CARRY, bool IMPL>
+__global__ void __launch_bounds__(kBlock)
+sell_gs_push_kernel(SellArgs A, double *x, const double *__restrict__ b, double *__restrict__ partials, const ExArgs fx,
+                    const unsigned char *__restrict__ mask, const SellPush push) {
+    static_assert(mode_is_gs(MODE), "only colour sweeps push");
+    pdl_prologue();
+    const int nex = CARRY ? fx.npeers * fx.ctas_per_peer : 0;
+    if (CARRY && (int)blockIdx.x < nex) {
+        fused_exchange_cta(fx, (int)blockIdx.x);
+        return;
+    }
+    const int64_t nb = (int64_t)gridDim.x - nex;
+    int64_t bid = (int64_t)blockIdx.x - nex;
+    bid = bid < push.tail_first ? nb - 1 - bid : bid - push.tail_first;
+    sell_body<MODE, LEN, UNIFORM, CARRY, IMPL>(A, x, b, nullptr, x, 0.0, partials, bid, &fx, mask);
+    const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
+    if (row >= A.row_begin && row < A.row_end && !push.ex.dry && push.mask[row >> 5]) push_row_if_listed(push, row, x);
+}
+
+// ---- long rows: four warps per slice ---------------------------------------------------------------------------------
+// With 19- / 37-point Galerkin stencils (quasi-L2 transfers) one thread walking a whole row is a chain of dependent
+// (column -> x gather) round trips: ~15 us per launch however small, and half the DRAM rate on large levels.  Here
+// the four warps of a slice take every fourth entry each, issue all their loads up front, and park the separately
+// rounded products v*x in shared memory; one warp then adds them in STORAGE ORDER, so the row sums keep the oracle's
+// bits (the additions are the only order-sensitive part, and they are a few hundred cycles of shared-memory reads).
+constexpr int kWideU = 5;          // entries per warp and pass
+constexpr int kWideMaxLen = 64;    // products kept in shared memory: 64 entries x 32 rows per slice
+
+// WPS warps share one slice (kBlock/32/WPS slices per CTA); WPS*kWideU entries per pass: 4 warps cover the 19-point
+// stencil in one pass, 8 warps the 37-point one.
+template <int MODE, int WPS>
+__global__ void __launch_bounds__(kBlock)
+sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__restrict__ b, const double *aux,
+                 double *y, double omega, double *__restrict__ partials) {
+    pdl_prologue();
+    constexpr int SPC = kBlock / 32 / WPS;
+    __shared__ double prod[SPC][kWideMaxLen][kSlice];
+    __shared__ unsigned char skip[SPC][kWideMaxLen][kSlice];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int sl = warp / WPS, w = warp % WPS;
+    const int64_t slice = (A.first_row >> 5) + (int64_t)blockIdx.x * SPC + sl;
+    const int64_t row = slice * kSlice + lane;
+    int len = 0;
+    int64_t base = 0;
+    if (slice * kSlice < A.row_end && row < A.nrows) {
+        if (uniform_len > 0) {
+            base = slice * (int64_t)kSlice * uniform_len;
+            len = uniform_len;
+        } else {
+            base = A.slice_ptr[slice];
+            len = (int)((A.slice_ptr[slice + 1] - base) >> 5);
+        }
+    }
+    // the warp that will finish the rows fetches their vector entries now, under the shadow of the matrix loads
+    const bool finisher = w == 0 && row >= A.row_begin && row < A.row_end;
+    double bv = 0.0, av = 0.0;
+    if (finisher) {
+        if (MODE != SPMV && MODE != PROLONG) bv = b[row];
+        if (MODE == JACOBI || MODE == PROLONG) av = aux[row];
+    }
+    const double *__restrict__ v = A.vals + base + lane;
+    const int32_t *__restrict__ c = A.cols + base + lane;
+    for (int k0 = w; k0 < len; k0 += WPS * kWideU) {
+        int32_t cc[kWideU];
+        double vv[kWideU], xx[kWideU];
+#pragma unroll
+        for (int j = 0; j < kWideU; ++j) {
+            const int k = k0 + j * WPS;
+            if (k < len) {
+                cc[j] = ld_stream(c + (int64_t)k * kSlice);
+                vv[j] = ld_stream(v + (int64_t)k * kSlice);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < kWideU; ++j)
+            if (k0 + j * WPS < len) xx[j] = x[cc[j]];
+#pragma unroll
+        for (int j = 0; j < kWideU; ++j) {
+            const int k = k0 + j * WPS;
+            if (k < len) {
+                const bool is_diag = mode_is_gs(MODE) && cc[j] == row;
+                prod[sl][k][lane] = is_diag ? vv[j] : __dmul_rn(vv[j], xx[j]);
+                if (mode_is_gs(MODE)) skip[sl][k][lane] = is_diag ? 1 : 0;
+            }
+        }
+    }
+    double xr = 0.0;
+    if (MODE == JACOBI && finisher) xr = x[row];
+    __syncthreads();
+    double contrib = 0.0;
+    if (finisher) {
+        double sum = 0.0, diag = 0.0;
+        for (int k = 0; k < len; ++k) {
+            const double p = prod[sl][k][lane];
+            if (mode_is_gs(MODE) && skip[sl][k][lane]) { if (p != 0.0) diag = p; }
+            else sum = __dadd_rn(sum, p);
+        }
+        if (MODE == SPMV) {
+            y[row] = sum;
+        } else if (MODE == RESID) {
+            y[row] = __dsub_rn(bv, sum);
+        } else if (MODE == RESNORM) {
+            const double r = __dsub_rn(bv, sum);
+            contrib = r * r;
+        } else if (MODE == JACOBI) {
+            const double r = __dsub_rn(bv, sum);
+            y[row] = __dadd_rn(xr, __dmul_rn(omega, __dmul_rn(av, r)));
+        } else if (MODE == PROLONG) {
+            y[row] = __dadd_rn(av, sum);
+        } else {                       // Gauss-Seidel family, see short_row
+            const bool upd = diag != 0.0;
+            double xn = 0.0;
+            if (upd) {
+                xn = __ddiv_rn(__dsub_rn(bv, sum), diag);
+                y[row] = xn;
+            }
+            if (MODE != GS) {
+                // the residual of the row with its new value: the parked products in storage order, the diagonal
+                // entry (parked as its VALUE) times the new iterate in its place.  A diagonal entry that did not
+                // update the row is a stored zero: its product is an exact zero and adding it changes nothing.
+                double s2 = 0.0;
+                for (int k = 0; k < len; ++k) {
+                    const double p = prod[sl][k][lane];
+                    if (skip[sl][k][lane]) { if (upd) s2 = __dadd_rn(s2, __dmul_rn(p, xn)); }
+                    else s2 = __dadd_rn(s2, p);
+                }
+                const double r = __dsub_rn(bv, s2);
+                if (MODE == GS_RES) A.r_out[row] = r;
+                else contrib = r * r;
+            }
+        }
+    }
+    if (mode_has_partials(MODE)) {
+        const double s = block_sum<kBlock>(contrib);
+        if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    }
+}
+
+// ---- launcher ----------------------------------------------------------------------------------------------------------
+// tunables (defined in sell_kernels.cu)
+extern int64_t g_wide_min_len;      // slices at least this long use sell_wide_kernel (0 = never)
+extern int64_t g_wide_max_rows;     // ... for launches of at most this many rows
+extern int64_t g_tma_min_rows;      // rows per launch from which the bulk-async staged kernel is used; 0 disables it
+extern int g_implied_columns;       // use the offset tables of matrices that carry one
+extern int64_t g_implied_min_rows;  // ... for launches of at least this many rows
+
+template <int MODE>
+int launch_sell_tma(const mg_sell *M, int64_t max_len, const double *x, const double *b, const double *aux, double *y,
+                    double omega, double *partials, int64_t row0, int64_t row1, int *grid_out, cudaStream_t st,
+                    const char *name);
+
+inline bool sell_uses_wide(const mg_sell *A, int64_t row0, int64_t row1) {
+    const int64_t ml = A->max_slice_len;
+    return g_wide_min_len > 0 && ml >= g_wide_min_len && ml <= kWideMaxLen && row1 - row0 <= g_wide_max_rows;
+}
+// which launches can carry an exchange site: the thread-per-row kernel only
+bool sell_fusable(const mg_sell *A, int64_t row0, int64_t row1);
+// which colour sweeps can also produce the residual / the squared residual norm of their rows (GS_RES / GS_NORM)
+bool sell_gs_tail_ok(const mg_sell *A, int64_t row0, int64_t row1);
+
+inline SellArgs sell_args(const mg_sell *A, int64_t row0, int64_t row1, double *r_out) {
+    SellArgs a;
+    a.slice_ptr = A->d_slice_ptr;
+    a.cols = A->d_cols;
+    a.vals = A->d_vals;
+    a.slice_off = A->d_slice_off;
+    a.row_begin = row0;
+    a.row_end = row1;
+    a.first_row = row0 & ~(int64_t)(kSlice - 1);
+    a.nrows = A->nrows;
+    a.r_out = r_out;
+    return a;
+}
+inline bool sell_use_implied(const mg_sell *A, int64_t row0, int64_t row1) {
+    const int64_t ml = A->max_slice_len;
+    return g_implied_columns && A->d_slice_off && A->uniform_len > 0 && A->uniform_len == ml && ml >= 1 && ml <= 8 &&
+           row1 - row0 >= g_implied_min_rows;
+}
+
+template <int MODE>
+static int launch_sell(const mg_sell *A, const double *x, const double *b, const double *aux, double *y,
+                       double omega, double *partials, int64_t row0, int64_t row1, cudaStream_t st,
+                       const char *name, int *nblocks_out = nullptr, const SellFuse *fuse = nullptr,
+                       double *r_out = nullptr) {
+    if (nblocks_out) *nblocks_out = 0;
+    if (fuse && !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot carry an exchange site");
+    if (row1 <= row0) return MG_OK;
+    if (MODE > PROLONG && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
+    if constexpr (MODE <= PROLONG) {
+        if (g_tma_min_rows > 0 && row1 - row0 >= g_tma_min_rows && A->max_slice_len > 0) {
+            int grid = 0;
+            const int rc = launch_sell_tma<MODE>(A, A->max_slice_len, x, b, aux, y, omega, partials, row0, row1, &grid, st, name);
+            if (rc <= 0) {
+                if (nblocks_out) *nblocks_out = grid;
+                return rc;
+            }
+        }
+    }
+    const SellArgs a = sell_args(A, row0, row1, r_out);
+    const int64_t nthreads = row1 - a.first_row;
+    const int64_t ml = A->max_slice_len;
+    const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
+    if (sell_uses_wide(A, row0, row1)) {
+        const int wps = ml <= 4 * kWideU ? 4 : 8;
+        const int spc = kBlock / 32 / wps;                            // slices per CTA
+        const int64_t nsl = (nthreads + kSlice - 1) / kSlice;
+        const int64_t wgrid = (nsl + spc - 1) / spc;
+        if (wgrid > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
+        if (wps == 4)
+            launch_k(sell_wide_kernel<MODE, 4>, (unsigned)wgrid, kBlock, st, a, (int)(uni ? ml : 0), x, b, aux, y, omega, partials);
+        else
+            launch_k(sell_wide_kernel<MODE, 8>, (unsigned)wgrid, kBlock, st, a, (int)(uni ? ml : 0), x, b, aux, y, omega, partials);
+        MG_CHECK_LAUNCH(name);
+        if (nblocks_out) *nblocks_out = (int)wgrid;
+        return MG_OK;
+    }
+    const int64_t grid = (nthreads + kBlock - 1) / kBlock;
+    if (grid + (fuse ? fuse->nex : 0) > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
+    const bool impl = sell_use_implied(A, row0, row1);
+#define MG_SELL_LAUNCH(L, U, I)                                                                                          \
+    do {                                                                                                                 \
+        if (fuse) launch_k(sell_kernel_fused<MODE, L, U, I>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
+        else launch_k(sell_kernel<MODE, L, U, I>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);         \
+    } while (0)
+#define MG_SELL_CASE(L)                                   \
+    case L:                                               \
+        if (impl) MG_SELL_LAUNCH(L, true, true);          \
+        else if (uni) MG_SELL_LAUNCH(L, true, false);     \
+        else MG_SELL_LAUNCH(L, false, false);             \
+        break
+    switch (ml) {
+        MG_SELL_CASE(1); MG_SELL_CASE(2); MG_SELL_CASE(3); MG_SELL_CASE(4);
+        MG_SELL_CASE(5); MG_SELL_CASE(6); MG_SELL_CASE(7); MG_SELL_CASE(8);
+        default:   // long rows, or length unknown (0)
+            if constexpr (MODE <= PROLONG) MG_SELL_LAUNCH(0, false, false);
+            else return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
+    }
+#undef MG_SELL_CASE
+#undef MG_SELL_LAUNCH
+    MG_CHECK_LAUNCH(name);
+    if (nblocks_out) *nblocks_out = (int)grid;
+    return MG_OK;
+}
+
+// colour sweep that pushes its own boundary values (carry: the previous site riding along, or NULL)
+template <int MODE>
+static int launch_sell_push(const mg_sell *A, double *x, const double *b, int64_t row0, int64_t row1, const SellFuse *carry,
+                            const SellPush *push, double *r_out, double *partials, int *nblocks_out, cudaStream_t st) {
+    const char *name = "sell_gs_rows_push";
+    if (nblocks_out) *nblocks_out = 0;
+    if (!push || !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot push an exchange site");
+    if (MODE > PROLONG && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
+    const SellArgs a = sell_args(A, row0, row1, r_out);
+    const int64_t ml = A->max_slice_len;
+    const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
+    const bool impl = sell_use_implied(A, row0, row1);
+    const int64_t grid = (row1 - a.first_row + kBlock - 1) / kBlock;
+    const int nex = carry ? carry->nex : 0;
+    if (grid + nex > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
+    SellPush p = *push;
+    if (p.tail_first < 0 || p.tail_first > grid / 2) p.tail_first = 0;
+    ExArgs none;
+    memset(&none, 0, sizeof(none));
+    const ExArgs &fx = carry ? carry->ex : none;
+    const unsigned char *mask = carry ? carry->mask : nullptr;
+#define MG_PUSH_LAUNCH(L, U, I)                                                                                          \
+    do {                                                                                                                 \
+        if (carry) launch_k(sell_gs_push_kernel<MODE, L, U, true, I>, (unsigned)(grid + nex), kBlock, st, a, x, b, partials, fx, mask, p); \
+        else launch_k(sell_gs_push_kernel<MODE, L, U, false, I>, (unsigned)grid, kBlock, st, a, x, b, partials, fx, mask, p);              \
+    } while (0)
+#define MG_PUSH_CASE(L)                                   \
+    case L:                                               \
+        if (impl) MG_PUSH_LAUNCH(L, true, true);          \
+        else if (uni) MG_PUSH_LAUNCH(L, true, false);     \
+        else MG_PUSH_LAUNCH(L, false, false);             \
+        break
+    switch (ml) {
+        MG_PUSH_CASE(1); MG_PUSH_CASE(2); MG_PUSH_CASE(3); MG_PUSH_CASE(4);
+        MG_PUSH_CASE(5); MG_PUSH_CASE(6); MG_PUSH_CASE(7); MG_PUSH_CASE(8);
+        default:
+            if constexpr (MODE == GS) MG_PUSH_LAUNCH(0, false, false);
+            else return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
+    }
+#undef MG_PUSH_CASE
+#undef MG_PUSH_LAUNCH
+    MG_CHECK_LAUNCH(name);
+    if (nblocks_out) *nblocks_out = (int)grid;
+    return MG_OK;
+}
+
+}  // namespace mgb

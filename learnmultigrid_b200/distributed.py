@@ -238,11 +238,13 @@ class DistributedHierarchy(DeviceHierarchy):
         c = self.comm.struct
         c.dry_run = 1
         try:
-            for nu in (1, 2):
+            for nu, after in ((1, 0), (2, 0), (1, 1)):          # norm before / after the cycle: different kernels
                 params = self.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
+                self._norm_struct.after = after
                 _lib.check(self.lib.mg_vcycle_dist(ctypes.byref(c), self._level_structs, self.nlevels,
                                                    ctypes.byref(params), ctypes.byref(self._norm_struct), st),
                            "mg_vcycle_dist (warm-up)")
+            self._norm_struct.after = 0
             lev = self.levels[0]
             if lev.perm is not None:
                 _lib.check(self.lib.mg_gather(self.n, lev.perm.data_ptr(), self._stage.data_ptr(), lev.tmp.data_ptr(),
@@ -369,6 +371,10 @@ class DistributedHierarchy(DeviceHierarchy):
             lev.perm = None if p.perm is None else torch.from_numpy(p.perm).to(dev)
             lev.color_ptr = p.color_ptr
             lev.nnz_A, lev.nnz_Q = A_nat[l].nnz, Q_nat[l].nnz
+            if self.colors[l] is not None:
+                # what the cycle may assume (mg_level.flags) must hold for the GLOBAL operator: a row of this block may
+                # couple to a halo row of its own colour; every rank holds the global level here and gets the same answer
+                lev.flags = S.coloring_flags(A_nat[l], self.colors[l])
             blk = self._rowblock(A_nat[l], p.o0, p.o1)
             loc = SD.DevCSR((p.n_own, lev.n_vec), blk.indptr, self._remap(S, blk.indices, lays[l]), blk.values)
             Ap = S.permute(loc, lev.perm, None)
@@ -565,12 +571,15 @@ class DistributedHierarchy(DeviceHierarchy):
         parts = self.fabric.allgather(self._from_level0(lev.r).reshape(-1))
         return np.concatenate(parts).reshape(-1, 1)
 
-    def vcycle(self, params, nlevels=None, use_graph=True, with_norm=False, dry=False):
-        """One V-cycle (optionally preceded by the fused residual norm of the outer loop) as one program.  Every
-        rank must make the same call.  Captured into a CUDA graph per parameter set.  dry=True captures the program
-        with its exchanges disabled (results are meaningless; bench.py times it to separate kernel time from
-        exchange time)."""
+    def vcycle(self, params, nlevels=None, use_graph=True, with_norm=False, dry=False, norm_after=False):
+        """One V-cycle as one program, optionally with the residual norm of the outer loop: with_norm -- of the iterate
+        the program starts from, evaluated first; norm_after -- of the iterate the cycle leaves, its last colour's share
+        summed by the last sweep (mg_dist_norm.after); read it with last_norm().  Every rank must make the same call.
+        Captured into a CUDA graph per parameter set.  dry=True captures the program with its exchanges disabled
+        (results are meaningless; bench.py times it to separate kernel time from exchange time)."""
         torch = self.torch
+        with_norm = bool(with_norm or norm_after)
+        self._norm_struct.after = 1 if norm_after else 0
         if nlevels is not None and int(nlevels) != self.nlevels:
             raise ValueError("a partitioned hierarchy runs all of its levels")
         L = self.nlevels
@@ -583,7 +592,7 @@ class DistributedHierarchy(DeviceHierarchy):
             self.last_launches = int(self.lib.mg_last_launch_count())
             return
         key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip,
-               params.reverse_post, bool(with_norm), bool(dry), int(self.lib.mg_tail_config_epoch()))
+               params.reverse_post, params.x0_zero, bool(with_norm), bool(norm_after), bool(dry))
         g = self._graphs.get(key)
         if g is None:
             cap = torch.cuda.Stream(device=self.device)

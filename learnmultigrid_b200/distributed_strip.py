@@ -172,6 +172,17 @@ class StripHierarchy(DistributedHierarchy):
             lev.A = S.to_sell(Ap)
             lev.dinv = S.dinv(Ap, None)
             lev.local_nnz_A = Ap.nnz
+            if p.color_ptr is not None:
+                # mg_level.flags must hold for the GLOBAL operator and be the same on every rank (they decide the
+                # launch sequence, hence the exchange sites): this block's rows against the colours of everything they
+                # read -- own rows by colour block, halo slots by (owner, colour) segment -- then AND over the ranks
+                vcol = np.full(lev.n_vec, -1, dtype=np.int32)
+                for c in range(len(p.color_ptr) - 1):
+                    vcol[int(p.color_ptr[c]):int(p.color_ptr[c + 1])] = c
+                for (q, c), (a, b) in p.seg_color.items():
+                    vcol[p.n_own + a:p.n_own + b] = c
+                mine_flags = S.coloring_flags(Ap, vcol)
+                lev.flags = int(np.bitwise_and.reduce([int(f) for f in self.fabric.allgather(mine_flags)]))
             del blk, loc, Ap
             blk = S.upload(strip[l].Q)
             loc = SD.DevCSR((p.n_own, lays[l + 1].length), blk.indptr, self._remap(S, blk.indices, lays[l + 1]),

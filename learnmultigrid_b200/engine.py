@@ -44,18 +44,29 @@ class DeviceSell:
                                    self.max_len, self.uniform_len)
         self._attach_slice_offsets()
 
+    IMPLIED_MIN_ROWS = 1 << 19      # the kernels' floor (mg_set_implied_min_rows): smaller matrices never use a table
+
     def _attach_slice_offsets(self):
-        """opt-in (MGB_IMPLIED_COLUMNS=1): per-slice column offsets of a uniform matrix with <= 8 entries per
-        row, so that regular slices compute their columns instead of loading them (mg_set_implied_columns)"""
+        """Implied columns (sell_core.cuh): per-slice column offsets of a uniform matrix with <= 8 entries per row, so
+        that regular slices compute their columns instead of loading them.  The table is kept when at least half of
+        the slices are regular (structured stencil levels: ~99 %; unstructured numberings: none).
+        MGB_IMPLIED_COLUMNS=0 switches it off."""
         self.slice_off = None
-        if os.environ.get("MGB_IMPLIED_COLUMNS", "0") != "1" or not 1 <= self.uniform_len <= 8 or self.shape[0] == 0:
+        self.regular_slices = 0
+        floor = int(os.environ.get("MGB_IMPLIED_MIN_ROWS", self.IMPLIED_MIN_ROWS))
+        if (os.environ.get("MGB_IMPLIED_COLUMNS", "1") == "0" or not 1 <= self.uniform_len <= 8
+                or self.shape[0] < max(floor // 2, 1)):
             return
         import torch
         nsl = (self.shape[0] + 31) // 32
-        self.slice_off = torch.empty(nsl * self.uniform_len, dtype=torch.int32, device=self.cols.device)
-        _lib.check(_lib.load().mg_sell_slice_offsets(ctypes.byref(self.struct), self.slice_off.data_ptr(),
+        off = torch.empty(nsl * self.uniform_len, dtype=torch.int32, device=self.cols.device)
+        cnt = torch.zeros(1, dtype=torch.int64, device=self.cols.device)
+        _lib.check(_lib.load().mg_sell_slice_offsets(ctypes.byref(self.struct), off.data_ptr(), cnt.data_ptr(),
                                                      _lib.stream_handle(torch)), "mg_sell_slice_offsets")
-        self.struct.d_slice_off = self.slice_off.data_ptr()
+        self.regular_slices = int(cnt.item())
+        if 2 * self.regular_slices >= nsl:
+            self.slice_off = off
+            self.struct.d_slice_off = off.data_ptr()
 
     @classmethod
     def from_device(cls, shape, nnz, slice_ptr, cols, vals, max_len=0, uniform_len=0):
@@ -74,6 +85,16 @@ class DeviceSell:
 
     def bytes(self):
         return self.padded * 12 + self.slice_ptr.numel() * 8
+
+    def stream_bytes(self):
+        """bytes one pass over the matrix actually reads: values, and columns or -- for regular slices of a matrix with
+        implied columns (large launches) -- 4 bytes of offset per slice and entry index"""
+        nsl = (self.shape[0] + 31) // 32
+        if self.slice_off is None or self.shape[0] < self.IMPLIED_MIN_ROWS or nsl == 0:
+            return self.padded * 12 + (0 if self.uniform_len else self.slice_ptr.numel() * 8)
+        per_slice = 32 * self.uniform_len
+        irregular = nsl - self.regular_slices
+        return self.padded * 8 + irregular * per_slice * 4 + nsl * self.uniform_len * 4
 
 
 class Level:
@@ -182,6 +203,7 @@ class DeviceHierarchy:
             lev.b = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.r = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.tmp = torch.zeros(n, dtype=torch.float64, device=dev)
+        self._inspect_levels()
         n0 = self.levels[0].n
         self.n = n0
         self._stage = torch.zeros(n0, dtype=torch.float64, device=dev)       # natural-order staging
@@ -204,6 +226,9 @@ class DeviceHierarchy:
                     self._keep.append(cp)
                     s.ncolors = len(lev.color_ptr) - 1
                     s.h_color_ptr = ctypes.cast(cp, ctypes.POINTER(ctypes.c_int64))
+                    s.flags = int(getattr(lev, "flags", 0))
+                    if getattr(lev, "diag", None) is not None:
+                        s.d_diag = lev.diag.data_ptr()
                 if getattr(lev, "csr", None) is not None and getattr(lev, "lex_ptr", None) is not None:
                     s.d_csr_indptr, s.d_csr_indices, s.d_csr_values = (t.data_ptr() for t in lev.csr)
                     s.d_lex_level_ptr = lev.lex_ptr.data_ptr()
@@ -218,6 +243,29 @@ class DeviceHierarchy:
                     if getattr(lev, "coarse_bcr_dist", None) is not None:
                         s.coarse_bcr_dist = ctypes.pointer(lev.coarse_bcr_dist)
         self._level_structs = arr
+
+    def _inspect_levels(self):
+        """What the cycle may assume about every coloured level (mg_level.flags / d_diag, csrc/cycle.cu
+        g_cycle_fusion): the diagonal as the Gauss-Seidel kernel finds it, whether the colouring is proper and whether
+        every row has a non-zero diagonal.  Levels whose flags were already set by the builder (partitioned levels:
+        the facts must hold for the GLOBAL operator, distributed.py) only get their diagonal here."""
+        torch, dev = self.torch, self.device
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        st = _lib.stream_handle(torch)
+        for lev in self.levels:
+            if getattr(lev, "A", None) is None or lev.color_ptr is None:
+                continue
+            lev.diag = torch.empty(lev.n, dtype=torch.float64, device=dev)
+            have = getattr(lev, "flags", None) is not None
+            cp = torch.tensor([int(v) for v in lev.color_ptr], dtype=torch.int64, device=dev)
+            flag.zero_()
+            _lib.check(self.lib.mg_level_inspect(ctypes.byref(lev.A.struct), 0 if have else len(lev.color_ptr) - 1,
+                                                 cp.data_ptr(), lev.diag.data_ptr(), flag.data_ptr(), st),
+                       "mg_level_inspect")
+            if not have:
+                bad = int(flag.item())
+                lev.flags = ((0 if bad & 1 else _lib.MG_LEVEL_PROPER_COLORING)
+                             | (0 if bad & 2 else _lib.MG_LEVEL_NONZERO_DIAG))
 
     # ------------------------------------------------------------------------------------------------
     # vectors in and out (host NumPy <-> permuted device vectors)
@@ -295,29 +343,46 @@ class DeviceHierarchy:
         torch.cuda.current_stream().synchronize()
         return float(np.sqrt(self._norm_host.item()))
 
+    def last_norm(self):
+        """||b - A x||_2 left on the device by vcycle(with_norm=True): one D2H of 8 bytes."""
+        torch = self.torch
+        self._norm_host.copy_(self._norm_out, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return float(np.sqrt(self._norm_host.item()))
+
     def residual_vector(self):
         lev = self.levels[0]
         _lib.check(self.lib.mg_sell_residual(ctypes.byref(lev.A.struct), lev.x.data_ptr(), lev.b.data_ptr(),
                                              lev.r.data_ptr(), _lib.stream_handle(self.torch)), "mg_sell_residual")
         return self._from_level0(lev.r)
 
-    def make_params(self, nu_pre=1, nu_post=None, omega=1.0, zero_guess_skip=True, reverse_post=False):
+    def make_params(self, nu_pre=1, nu_post=None, omega=1.0, zero_guess_skip=True, reverse_post=False, x0_zero=False):
+        """x0_zero: the cycle starts from a zero iterate on level 0 WITHOUT reading (or needing) the contents of x --
+        a preconditioner application z = M^-1 r."""
         sm = {"jacobi": _lib.MG_SMOOTH_JACOBI, "mcgs": _lib.MG_SMOOTH_MCGS, "lexgs": _lib.MG_SMOOTH_LEXGS}[self.smoother]
         return _lib.mg_cycle_params(sm, int(nu_pre), int(nu_pre if nu_post is None else nu_post), float(omega),
-                                    1 if zero_guess_skip else 0, 1 if reverse_post else 0)
+                                    1 if zero_guess_skip else 0, 1 if reverse_post else 0, 1 if x0_zero else 0, 0)
 
-    def vcycle(self, params, nlevels=None, use_graph=True):
+    def _enqueue_cycle(self, L, params, with_norm, stream):
+        if with_norm:
+            return self.lib.mg_vcycle_norm(self._level_structs, L, ctypes.byref(params), self._norm_ws.data_ptr(),
+                                           self._norm_out.data_ptr(), stream)
+        return self.lib.mg_vcycle(self._level_structs, L, ctypes.byref(params), stream)
+
+    def vcycle(self, params, nlevels=None, use_graph=True, with_norm=False):
         """One V-cycle on the level-0 vectors (x updated in place).  The launch sequence is captured into a CUDA
-        graph the first time a parameter set is used and replayed afterwards."""
+        graph the first time a parameter set is used and replayed afterwards.
+        with_norm: the cycle also leaves ||b - A x||^2 of the NEW iterate on the device (mg_vcycle_norm: the last
+        colour sweep sums its own rows' share from registers); read it with last_norm()."""
         torch = self.torch
         L = self.nlevels if nlevels is None else int(nlevels)
         st = _lib.stream_handle(torch)
         if not use_graph or self.smoother == "lexgs":      # cooperative launches are not captured
-            _lib.check(self.lib.mg_vcycle(self._level_structs, L, ctypes.byref(params), st), "mg_vcycle")
+            _lib.check(self._enqueue_cycle(L, params, with_norm, st), "mg_vcycle")
             self.last_launches = int(self.lib.mg_last_launch_count())
             return
         key = (L, params.smoother, params.nu_pre, params.nu_post, params.omega, params.zero_guess_skip,
-               params.reverse_post, int(self.lib.mg_tail_config_epoch()))
+               params.reverse_post, params.x0_zero, bool(with_norm))
         g = self._graphs.get(key)
         if g is None:
             cap = torch.cuda.Stream(device=self.device)
@@ -325,7 +390,7 @@ class DeviceHierarchy:
             with torch.cuda.stream(cap):
                 h = cap.cuda_stream
                 _lib.check(self.lib.mg_graph_begin(h), "mg_graph_begin")
-                rc = self.lib.mg_vcycle(self._level_structs, L, ctypes.byref(params), h)
+                rc = self._enqueue_cycle(L, params, with_norm, h)
                 launches = int(self.lib.mg_last_launch_count())
                 out = ctypes.c_void_p()
                 rc2 = self.lib.mg_graph_end(h, ctypes.byref(out))
@@ -420,6 +485,55 @@ class DeviceHierarchy:
         total += coarse
         return {"total": total, "outer": S(lv[0].nnz_A, lv[0].n) + 16 * lv[0].n, "levels": per_level,
                 "coarse": coarse}
+
+    def cycle_bytes_moved(self, nu_pre, nu_post):
+        """Bytes THIS GPU has to move per outer iteration (V-cycle + norm of its result) the way the cycle is actually
+        run -- the model behind roofline.cycle.moved_frac in bench.py, next to the CSR yardstick of cycle_bytes():
+        matrix streams as stored (values; columns, or 4 B of offset per slice and entry where columns are implied),
+        every vector entry an operation reads or writes counted once per operation (gathers: the distinct entries,
+        bounded by the rows read), and the passes the multicolour cycle leaves out (cycle.cu g_cycle_fusion)."""
+        fusion = os.environ.get("MGB_CYCLE_FUSION", "1") != "0"
+        total = 0.0
+        lv = self.levels
+        for l in range(self.nlevels - 1):
+            L_ = lv[l]
+            n = L_.n
+            nc = getattr(lv[l + 1], "n", 0)
+            SA, SQ, SQT = L_.A.stream_bytes(), L_.Q.stream_bytes(), L_.QT.stream_bytes()
+            lenA = max(L_.A.max_len, 1)
+            lenQ = max(L_.Q.max_len, 1)
+
+            def rows_pass(R, write_vec, read_b=True):      # matrix share + b + output + distinct x entries gathered
+                return SA * R / max(n, 1) + (8 * R if read_b else 0) + 8 * R * write_vec + 8 * min(n, lenA * R)
+            mc = self.smoother == "mcgs" and L_.color_ptr is not None
+            fused = mc and fusion and int(getattr(L_, "flags", 0)) & 1
+            skip_prolong = fused and int(getattr(L_, "flags", 0)) & 2 and nu_post > 0
+            if mc:
+                sizes = np.diff(np.asarray(L_.color_ptr, dtype=np.int64))
+                sweep = sum(SA * c / max(n, 1) + 16 * c + 8 * min(n - c, (lenA - 1) * c) for c in sizes)
+                last, first = int(sizes[-1]), int(sizes[0])
+            else:
+                sweep = rows_pass(n, 1) + (8 * n if self.smoother == "jacobi" else 0)
+                last = first = 0
+            b = (nu_pre + nu_post) * sweep
+            if l > 0 and nu_pre > 0:
+                if mc and fusion and getattr(L_, "diag", None) is not None:
+                    b += 8 * n + 16 * first - (SA * first / max(n, 1) + 16 * first + 8 * min(n - first, (lenA - 1) * first))
+                else:
+                    b += 8 * n                                 # zero fill
+            r_rows = n - last if (fused and nu_pre > 0) else n
+            b += rows_pass(r_rows, 1) + (8 * last if (fused and nu_pre > 0) else 0)         # residual
+            b += SQT + 8 * nc + 8 * n                                                      # restriction
+            p_rows = n - first if skip_prolong else n
+            b += SQ * p_rows / max(n, 1) + 16 * p_rows + 8 * min(nc, lenQ * p_rows)        # prolongation
+            if l == 0:                                                                     # norm of the new iterate
+                nr = n - last if (fused and nu_post > 0) else n
+                b += rows_pass(nr, 0)
+            total += b
+        total += lv[-1].coarse_bytes + 16 * lv[-1].n
+        return {"total": total, "model": "bytes this GPU streams per step as run: stored matrix bytes (implied columns "
+                                         "counted as 4 B per slice and entry), vector entries once per operation, "
+                                         "skipped passes left out"}
 
     def level_matrix(self, l):
         """A_l in natural ordering as a SciPy CSR (for pattern / value parity checks)."""

@@ -225,6 +225,18 @@ class DeviceSetup:
         self.last_color_rounds = int(rounds.value)
         return colors.cpu().numpy()
 
+    def coloring_flags(self, A, colors_host, row0=0):
+        """mg_level.flags of a level from its operator in natural ordering (rows row0.. of the global matrix when A is
+        a row block with global column ids) and the GLOBAL colour array: MG_LEVEL_PROPER_COLORING if no row couples to
+        another row of its colour, MG_LEVEL_NONZERO_DIAG if every row has a non-zero diagonal."""
+        t = self.torch
+        col = t.from_numpy(np.ascontiguousarray(colors_host, dtype=np.int32)).to(self.dev)
+        self._flag.zero_()
+        _lib.check(self.lib.mg_csr_coloring_flags(A.shape[0], int(row0), *A.ptrs(), col.data_ptr(),
+                                                  self._flag.data_ptr(), self.st()), "mg_csr_coloring_flags")
+        bad = int(self._flag.item())
+        return ((0 if bad & 1 else _lib.MG_LEVEL_PROPER_COLORING) | (0 if bad & 2 else _lib.MG_LEVEL_NONZERO_DIAG))
+
     def color_perm(self, colors_host):
         """device perm (new -> old, stable by colour), inverse perm, host colour offsets"""
         t = self.torch

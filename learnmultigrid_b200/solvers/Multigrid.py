@@ -79,9 +79,13 @@ class Multigrid(IterativeSolver):
         else:
             h.set_x(self.solution)
         track_res = np.ndarray(shape=(0, 1), dtype=float)
-        for _ in range(0, max_iterations):
+        # :62-63 residual + norm.  Only the first one is a pass of its own: every cycle that is followed by another
+        # iteration also leaves the norm of its new iterate (the last colour sweep sums its rows' share from
+        # registers, engine.vcycle(with_norm=True) / mg_vcycle_norm)
+        res = h.residual_norm() if max_iterations > 0 else None
+        for it in range(0, max_iterations):
             self.iterations += 1
-            self.residual = h.residual_norm()                      # :62-63 fused residual + norm
+            self.residual = res
             if self.iterations <= 1:                               # :64-66
                 self.residual = float(np.sqrt(float(self.get_dimension())))
                 self._residual_is_ones = True
@@ -92,7 +96,13 @@ class Multigrid(IterativeSolver):
                 print("It: ", self.iterations, self.residual)
             if self.residual <= error:
                 break
-            h.vcycle(params, use_graph=use_graph)                  # :73
+            more = it + 1 < max_iterations
+            if self.fabric is not None and hasattr(h, "comm"):
+                h.vcycle(params, use_graph=use_graph, norm_after=more)             # :73
+            else:
+                h.vcycle(params, use_graph=use_graph, with_norm=more)              # :73
+            if more:
+                res = h.last_norm()
         if self.fabric is not None and getattr(self, "local_solution", False) and hasattr(h, "get_x_local"):
             self.solution = h.get_x_local(view=getattr(self, "pinned_io", False))     # this rank's row block only
         else:

@@ -27,14 +27,14 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_library_loads_and_reports_version():
     lib = _lib.load()
-    assert lib.mg_version() == 100
+    assert lib.mg_version() == 200
     assert lib.mg_last_error() is not None
 
 
 def test_struct_layouts_match_header_sizes():
-    # mg_sell: 3 x int64 + 3 pointers + 2 x int64 + 1 pointer; mg_cycle_params: 3 x int32 (+pad) + double + int32 (+pad)
+    # mg_sell: 3 x int64 + 3 pointers + 2 x int64 + 1 pointer; mg_cycle_params: 3 x int32 (+pad) + double + 3 x int32 (+pad)
     assert ctypes.sizeof(_lib.mg_sell) == 72
-    assert ctypes.sizeof(_lib.mg_cycle_params) == 32
+    assert ctypes.sizeof(_lib.mg_cycle_params) == 40
     assert ctypes.sizeof(_lib.mg_level) % 8 == 0
     lib = _lib.load()
     for which, st in enumerate((_lib.mg_sell, _lib.mg_level, _lib.mg_cycle_params, _lib.mg_bcr, _lib.mg_comm,

@@ -217,9 +217,9 @@ def test_device_first_fit_colouring_equals_the_host_helper(torch_mod):
 
 
 def test_implied_columns_are_bit_identical(torch_mod, monkeypatch):
-    """mg_set_implied_columns(1) + per-slice offsets (MGB_IMPLIED_COLUMNS=1): regular slices compute their columns from
-    the row; the device-built offset tables equal the host twin, every SELL mode gives the same bits as the ordinary
-    kernels, and so does a whole solve (multicolour Gauss-Seidel and Jacobi)"""
+    """implied columns (default on; here with the row floor lowered so that a 66 k-row level uses them): regular slices
+    compute their columns from the row; the device-built offset tables equal the host twin, every SELL mode gives the
+    same bits as the ordinary kernels, and so does a whole solve (multicolour Gauss-Seidel and Jacobi)"""
     import ctypes
     from learnmultigrid_b200 import _lib, formats as F, problems as P
     from learnmultigrid_b200.engine import DeviceHierarchy
@@ -243,10 +243,15 @@ def test_implied_columns_are_bit_identical(torch_mod, monkeypatch):
             out.append(h.get_x().copy())
         return h, out
 
-    plain = {s: run(s)[1] for s in ("mcgs", "jacobi")}
-    monkeypatch.setenv("MGB_IMPLIED_COLUMNS", "1")
-    prev = lib.mg_set_implied_columns(1)
+    monkeypatch.setenv("MGB_IMPLIED_COLUMNS", "0")
+    prev = lib.mg_set_implied_columns(0)
+    floor = lib.mg_set_implied_min_rows(1)
     try:
+        plain = {s: run(s)[1] for s in ("mcgs", "jacobi")}
+        assert run("mcgs")[0].levels[0].A.slice_off is None
+        monkeypatch.setenv("MGB_IMPLIED_COLUMNS", "1")
+        monkeypatch.setenv("MGB_IMPLIED_MIN_ROWS", "1")
+        lib.mg_set_implied_columns(1)
         for s in ("mcgs", "jacobi"):
             h, got = run(s)
             lev = h.levels[0]
@@ -262,11 +267,13 @@ def test_implied_columns_are_bit_identical(torch_mod, monkeypatch):
                 assert np.array_equal(np.asarray(g), np.asarray(w))
     finally:
         lib.mg_set_implied_columns(prev)
+        lib.mg_set_implied_min_rows(floor)
 
 
 def test_implied_columns_on_partitioned_levels(torch_mod, monkeypatch):
-    """the implied-columns kernels carrying an exchange site (sell_kernel_reg_fused): partitioned cycle with
-    MGB_IMPLIED_COLUMNS=1 against the ordinary single-GPU cycle, bit for bit"""
+    """the implied-columns kernels carrying an exchange site, and the partitioned cycle's shortcuts (fused residual of
+    the last colour, skipped prolongation rows, norm after the cycle): against the plain single-GPU cycle -- no implied
+    columns, one pass per operation -- bit for bit"""
     from learnmultigrid_b200 import _lib, formats as F, problems as P
     from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
     from learnmultigrid_b200.engine import DeviceHierarchy
@@ -276,36 +283,53 @@ def test_implied_columns_on_partitioned_levels(torch_mod, monkeypatch):
     Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, "linear")]
     b = P.structured_rhs_2d(N)
     x0 = np.random.default_rng(8).standard_normal((A.shape[0], 1))
-    h = DeviceHierarchy(A, Qs, smoother="mcgs")
-    h.set_rhs(b)
-    h.set_x(x0)
-    params = h.make_params(nu_pre=nu, nu_post=nu)
-    want = []
-    for _ in range(cycles):
-        h.vcycle(params)
-        want.append(h.get_x().copy())
+    monkeypatch.setenv("MGB_IMPLIED_COLUMNS", "0")
+    prev = lib.mg_set_implied_columns(0)
+    floor = lib.mg_set_implied_min_rows(1)
+    lib.mg_set_cycle_fusion(0)
+    try:
+        h = DeviceHierarchy(A, Qs, smoother="mcgs")
+        h.set_rhs(b)
+        h.set_x(x0)
+        params = h.make_params(nu_pre=nu, nu_post=nu)
+        want, want_norm = [], []
+        for _ in range(cycles):
+            h.vcycle(params)
+            want.append(h.get_x().copy())
+            want_norm.append(h.residual_norm())
+    finally:
+        lib.mg_set_cycle_fusion(1)
 
     def body(fab):
         hd = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h.colors, n_dist=2, region_bytes=1 << 20,
                                   max_sites=256, timeout_s=30.0)
         assert hd.levels[0].A.slice_off is not None
-        hd.set_rhs(b)
-        hd.set_x(x0)
+        assert all(int(lv.flags) == 3 for lv in hd.levels[:-1])
         p = hd.make_params(nu_pre=nu, nu_post=nu)
-        xs = []
-        for _ in range(cycles):
-            hd.vcycle(p, with_norm=True)
-            xs.append(hd.get_x().copy())
+        out = []
+        for mode in ("before", "after"):
+            hd.set_rhs(b)
+            hd.set_x(x0)
+            xs, ns = [], []
+            for _ in range(cycles):
+                hd.vcycle(p, with_norm=mode == "before", norm_after=mode == "after")
+                xs.append(hd.get_x().copy())
+                ns.append(hd.last_norm())
+            out.append((xs, ns))
         hd.check()
         hd.close()
-        return xs
+        return out
 
     monkeypatch.setenv("MGB_IMPLIED_COLUMNS", "1")
-    prev = lib.mg_set_implied_columns(1)
+    monkeypatch.setenv("MGB_IMPLIED_MIN_ROWS", "1")
     try:
+        lib.mg_set_implied_columns(1)
         res = run_virtual_ranks(2, body)
     finally:
         lib.mg_set_implied_columns(prev)
-    for xs in res:
-        for got, w in zip(xs, want):
-            assert np.array_equal(got, w)
+        lib.mg_set_implied_min_rows(floor)
+    for out in res:
+        for xs, ns in out:
+            for got, w in zip(xs, want):
+                assert np.array_equal(got, w)
+        np.testing.assert_allclose(out[1][1], want_norm, rtol=1e-12)          # the norm AFTER each cycle

@@ -174,7 +174,9 @@ A1 = sp.csr_matrix(Qs[0].T @ sp.csc_matrix(A) @ Qs[0]); A1.sort_indices()
 ok = ok and np.array_equal(levs[0].colors, col[offs[0][r]:offs[0][r + 1]]) and levs[0].ncolors == nc \
     and np.array_equal(A_rep.indices, A1.indices) and np.array_equal(A_rep.data, A1.data) \
     and (Q_rep[0] != Qs[1]).nnz == 0
-print("RANK", r, "OK" if ok else "MISMATCH", flush=True)
+import sys
+sys.stdout.write("RANK %d %s\n" % (r, "OK" if ok else "MISMATCH"))      # one write: the two ranks share the pipe
+sys.stdout.flush()
 dist.destroy_process_group()
 """
 
