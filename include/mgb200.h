@@ -96,7 +96,7 @@ typedef struct {
     int64_t max_slice_len;      /* longest slice (entries per row); 0 = unknown (generic kernel)           */
     int64_t uniform_len;        /* > 0: EVERY slice has exactly this many entries per row (= max_slice_len), so
                                    slice offsets are computed, not loaded; 0 = lengths vary, use d_slice_ptr */
-    const int32_t *d_slice_off; /* optional (NULL: none): [nslices][uniform_len] column offsets relative to the row
+    const int32_t *d_slice_off; /* optional (NULL: none): [nslices][8] column offsets relative to the row
                                    for slices in which every row has the columns row + off[j]; filled by
                                    mg_sell_slice_offsets, used when mg_set_implied_columns(1) */
 } mg_sell;
@@ -104,8 +104,8 @@ typedef struct {
 /* Implied columns (default on; results identical): on a uniform matrix with <= 8 entries per row, slices whose
  * 32 rows all have the columns row + off[j] (structured stencil levels: all slices but those holding a boundary node)
  * read 4 bytes of offset per entry index instead of 128 bytes of column indices, and the x gathers of a warp become
- * contiguous 256-byte reads.  mg_sell_slice_offsets fills d_off[nslices * uniform_len] (irregular slices:
- * d_off[s * len] = INT32_MIN) and adds the number of regular slices to *d_nregular (device int64, zeroed by the
+ * contiguous 256-byte reads.  mg_sell_slice_offsets fills d_off[nslices * 8] (one 32-byte record per slice, entries
+ * beyond uniform_len zero; the table must be 32-byte aligned; irregular slices: d_off[s * 8] = INT32_MIN) and adds the number of regular slices to *d_nregular (device int64, zeroed by the
  * caller; may be NULL); point mg_sell.d_slice_off at the table when enough slices are regular. */
 int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, int64_t *d_nregular, void *stream);
 int mg_set_implied_columns(int enabled);
@@ -132,6 +132,11 @@ int64_t mg_set_tma_min_rows(int64_t rows);
  * kernel: loads of a row spread over four or eight warps, products added in storage order (same bits); 0 = never.  Returns
  * the previous threshold (default 9: the 19- and 37-point Galerkin stencils of quasi-L2 transfers). */
 int64_t mg_set_wide_min_len(int64_t len);
+/* SpMV / prolongation with matrices of at most two entries per row (linear transfer operators): launches of at least
+ * mg_set_short_min_rows rows (default 2^18) take r in {1, 2, 4} rows per thread (default 2; 1 = the ordinary kernel), all
+ * loads of a stage issued for all of them first.  Same bits.  Both return the previous value. */
+int mg_set_short_rows_per_thread(int r);
+int64_t mg_set_short_min_rows(int64_t rows);
 /* ... and only for launches of at most `rows` rows (default 2^18): larger launches keep enough rows in flight for the
  * thread-per-row kernel, which then streams at the DRAM limit.  Returns the previous value. */
 int64_t mg_set_wide_max_rows(int64_t rows);
@@ -579,6 +584,26 @@ typedef struct {
 } mg_dist_norm;
 int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_cycle_params *params,
                    const mg_dist_norm *norm, void *stream);
+/* Conjugate gradients preconditioned by one V-cycle per iteration, statement order of learn_multigrid/solvers/CG.py:12-50
+ * (x0 = 0) with z = M^-1 r inserted (BASELINE.json configs[4]).  The residual r lives in levels[0].d_b (the caller puts
+ * the right-hand side there), z in levels[0].d_x.  All scalars stay on the device:
+ *     d_scalars[8]: [0] r.z  [1] p.Ap  [2] alpha  [3] beta  [4] r.r  [5..7] scratch
+ * mg_pcg_start: x = 0, [4] = r.r.  mg_pcg_iterate (first != 0 on the first call): z = M^-1 r (params == NULL: z = r),
+ * beta, p = z + beta p, Ap = A p together with p.Ap, alpha, x += alpha p and r -= alpha Ap together with r.r.  Launches
+ * only (one CUDA graph per value of `first`); the host reads [4] afterwards to test convergence.  comm != NULL: levels[0]
+ * is row-partitioned (d_p then holds n + n_halo entries), every call is one program and the dot products are summed over
+ * the ranks in rank order. */
+typedef struct {
+    double *d_x;          /* n: the solution being built, level-0 ordering                   */
+    double *d_p;          /* n (+ halo): search direction                                    */
+    double *d_Ap;         /* n                                                               */
+    double *d_scalars;    /* 8 doubles                                                       */
+    double *d_partials;   /* mg_norm_workspace_size(n) doubles                               */
+    double *d_slots;      /* MG_MAX_RANKS doubles (partitioned runs; NULL otherwise)         */
+} mg_pcg;
+int mg_pcg_start(mg_comm *comm, const mg_level *levels, const mg_pcg *pcg, void *stream);
+int mg_pcg_iterate(mg_comm *comm, const mg_level *levels, int nlevels, const mg_cycle_params *params, const mg_pcg *pcg,
+                   int first, void *stream);
 /* number of kernels the last mg_vcycle call on this thread launched (bench.py's gpu_launches) */
 int64_t mg_last_launch_count(void);
 /* CUDA-graph helpers: capture whatever is enqueued on `stream` between begin and end. */

@@ -77,6 +77,11 @@ class mg_dist_norm(ctypes.Structure):
                 ("after", ctypes.c_int32), ("pad_", ctypes.c_int32)]
 
 
+class mg_pcg(ctypes.Structure):
+    _fields_ = [("d_x", c_vp), ("d_p", c_vp), ("d_Ap", c_vp), ("d_scalars", c_vp), ("d_partials", c_vp),
+                ("d_slots", c_vp)]
+
+
 class mg_level(ctypes.Structure):
     _fields_ = [("n", c_i64), ("A", mg_sell), ("d_dinv", c_vp),
                 ("ncolors", ctypes.c_int32), ("h_color_ptr", ctypes.POINTER(c_i64)),
@@ -113,6 +118,8 @@ _SIGNATURES = {
     "mg_sell_spmv": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
     "mg_sell_slice_offsets": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
     "mg_set_implied_min_rows": (c_i64, [c_i64]),
+    "mg_set_short_rows_per_thread": (c_int, [c_int]),
+    "mg_set_short_min_rows": (c_i64, [c_i64]),
     "mg_level_inspect": (c_int, [ctypes.POINTER(mg_sell), c_int, c_vp, c_vp, c_vp, c_vp]),
     "mg_sell_residual_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "mg_sell_gs_rows_tail": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_i64, c_i64, c_int, c_vp, c_vp,
@@ -122,6 +129,9 @@ _SIGNATURES = {
     "mg_sell_prolong_correct_rows": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_i64, c_i64, c_vp]),
     "mg_vcycle_norm": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp, c_vp, c_vp]),
     "mg_set_cycle_fusion": (c_int, [c_int]),
+    "mg_pcg_start": (c_int, [c_vp, ctypes.POINTER(mg_level), ctypes.POINTER(mg_pcg), c_vp]),
+    "mg_pcg_iterate": (c_int, [c_vp, ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params),
+                               ctypes.POINTER(mg_pcg), c_int, c_vp]),
     "mg_set_implied_columns": (c_int, [c_int]),
     "mg_sell_residual": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp]),
     "mg_sell_residual_norm2": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -258,6 +268,8 @@ def load():
         lib.mg_set_implied_columns(0)
     if "MGB_IMPLIED_MIN_ROWS" in os.environ:
         lib.mg_set_implied_min_rows(int(os.environ["MGB_IMPLIED_MIN_ROWS"]))
+    if "MGB_SHORT_ROWS" in os.environ:
+        lib.mg_set_short_rows_per_thread(int(os.environ["MGB_SHORT_ROWS"]))
     if os.environ.get("MGB_CYCLE_FUSION", "1") == "0":
         lib.mg_set_cycle_fusion(0)
     if "MGB_WIDE_MIN_LEN" in os.environ:

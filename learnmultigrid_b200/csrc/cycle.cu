@@ -37,6 +37,10 @@ int csr_gs_lex(const int32_t *, const int32_t *, const double *, double *, const
                const int32_t *, int64_t, int64_t, int, cudaStream_t);
 int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const double *rhs, double *x, cudaStream_t st);
 int vec_scatter(int64_t, const int32_t *, const double *, double *, cudaStream_t);
+int vec_dot_partials(int64_t, const double *, const double *, double *, int *, cudaStream_t);
+int vec_pcg_direction(int64_t, const double *, double *, const double *, int, cudaStream_t);
+int vec_pcg_update(int64_t, const double *, const double *, double *, double *, const double *, double *, int *, cudaStream_t);
+int vec_pcg_scalar(int, int, double *, const double *, cudaStream_t);
 int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStream_t);
 
 #define MG_TRY(expr)            \
@@ -493,6 +497,91 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
 }
 
 int64_t mg_last_launch_count(void) { return g_last_cycle_launches; }
+
+/* ---- conjugate gradients preconditioned by one V-cycle per iteration (CG.py:12-50 + BASELINE configs[4]) -------------
+ * Everything stays on the device: the scalars live in pcg->d_scalars, every dot product is the by-product of the
+ * kernel that produces its operand where there is one (p.Ap from the SpMV, r.r from the update of x and r), and an
+ * iteration is one launch sequence (capturable in one CUDA graph) after which the host reads 8 bytes to test
+ * convergence.  comm != NULL: levels[0] is row-partitioned, the sequence is one program of the communicator and the
+ * dot products are summed over the ranks in rank order. */
+static int pcg_reduce(mg_comm *comm, const mg_pcg *S, int nblocks, int op, int first, cudaStream_t st) {
+    double *local = S->d_scalars + 6;
+    MG_TRY(sell_reduce_partials(S->d_partials, nblocks, local, st));
+    const double *in = local;
+    if (comm && comm->world > 1) {
+        MG_REQUIRE(S->d_slots, "mg_pcg.d_slots missing");
+        MG_TRY(flush_pending(comm, st));
+        MG_TRY(mg_comm_allreduce_sum(comm, local, S->d_slots, S->d_scalars + 7, st));
+        in = S->d_scalars + 7;
+    }
+    return vec_pcg_scalar(op, first, S->d_scalars, in, st);
+}
+static int check_pcg(const mg_level *levels, const mg_pcg *S) {
+    MG_REQUIRE(levels && S && S->d_x && S->d_p && S->d_Ap && S->d_scalars && S->d_partials, "mg_pcg: null member");
+    MG_REQUIRE(levels[0].n > 0 && levels[0].d_x && levels[0].d_b, "level vectors missing");
+    return MG_OK;
+}
+int mg_pcg_start(mg_comm *comm, const mg_level *levels, const mg_pcg *pcg, void *stream) {
+    MG_TRY(check_pcg(levels, pcg));
+    cudaStream_t st = (cudaStream_t)stream;
+    const mg_level &L = levels[0];
+    if (comm) {
+        MG_TRY(mg_comm_begin(comm));
+        g_pend.x = nullptr;
+        g_pend.prepared = false;
+    }
+    MG_TRY(vec_fill(L.n, 0.0, pcg->d_x, st));
+    int nb = 0;
+    MG_TRY(vec_dot_partials(L.n, L.d_b, L.d_b, pcg->d_partials, &nb, st));
+    MG_TRY(pcg_reduce(comm, pcg, nb, 0, 0, st));
+    if (comm) MG_TRY(mg_comm_end(comm, stream));
+    return MG_OK;
+}
+int mg_pcg_iterate(mg_comm *comm, const mg_level *levels, int nlevels, const mg_cycle_params *params, const mg_pcg *pcg,
+                   int first, void *stream) {
+    MG_TRY(check_pcg(levels, pcg));
+    if (params) MG_TRY(check_levels(levels, nlevels, params, comm != nullptr));
+    cudaStream_t st = (cudaStream_t)stream;
+    const mg_level &L = levels[0];
+    MG_REQUIRE(!L.dist || comm, "partitioned level without a communicator");
+    const int64_t before = g_launch_count;
+    if (comm) {
+        MG_TRY(mg_comm_begin(comm));
+        g_pend.x = nullptr;
+        g_pend.prepared = false;
+    }
+    double *r = L.d_b;
+    const double *z = r;
+    if (params) {                               // z = M^-1 r: one V-cycle on (x, b) = (0, r), z lands in d_x
+        mg_cycle_params P = *params;
+        P.x0_zero = 1;
+        MG_TRY(vcycle_rec(comm, levels, nlevels, 0, P, st));
+        MG_TRY(flush_pending(comm, st));
+        z = L.d_x;
+    }
+    int nb = 0;
+    MG_TRY(vec_dot_partials(L.n, r, z, pcg->d_partials, &nb, st));
+    MG_TRY(pcg_reduce(comm, pcg, nb, 1, first, st));                          // beta = r.z / (r.z)_old
+    MG_TRY(vec_pcg_direction(L.n, z, pcg->d_p, pcg->d_scalars, first, st));    // p = z + beta p
+    SellFuse f;
+    bool use = false;
+    if (L.dist) {
+        MG_TRY(issue_exchange(comm, L.dist->xfer_all, pcg->d_p, true, st));    // the SpMV reads halo entries of p
+        MG_TRY(take_pending(comm, pcg->d_p, &L.A, 0, L.A.nrows, L.dist->d_mask_A, &f, &use, st));
+    }
+    MG_TRY(sell_spmv_dot(&L.A, pcg->d_p, pcg->d_p, pcg->d_Ap, pcg->d_partials, &nb, use ? &f : nullptr, st));
+    MG_TRY(pcg_reduce(comm, pcg, nb, 2, 0, st));                              // alpha = r.z / p.Ap
+    MG_TRY(vec_pcg_update(L.n, pcg->d_p, pcg->d_Ap, pcg->d_x, r, pcg->d_scalars, pcg->d_partials, &nb, st));
+    MG_TRY(pcg_reduce(comm, pcg, nb, 0, 0, st));                              // r.r of the new residual
+    if (comm) {
+        MG_TRY(flush_pending(comm, st));
+        g_pend.x = nullptr;
+        g_pend.prepared = false;
+        MG_TRY(mg_comm_end(comm, stream));
+    }
+    g_last_cycle_launches = g_launch_count - before;
+    return MG_OK;
+}
 
 int mg_graph_begin(void *stream) {
     MG_CHECK_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));

@@ -10,6 +10,9 @@ enum SweepTail { TAIL_NONE = 0, TAIL_RESIDUAL = 1, TAIL_NORM = 2 };
 
 // y = A x
 int sell_spmv(const mg_sell *A, const double *x, double *y, int64_t row0, int64_t row1, const SellFuse *fuse, cudaStream_t st);
+// y = A x and per-CTA partial sums of w . y over the rows (*nblocks of them): the p . A p of conjugate gradients
+int sell_spmv_dot(const mg_sell *A, const double *x, const double *w, double *y, double *partials, int *nblocks,
+                  const SellFuse *fuse, cudaStream_t st);
 // r = b - A x
 int sell_residual(const mg_sell *A, const double *x, const double *b, double *r, int64_t row0, int64_t row1,
                   const SellFuse *fuse, cudaStream_t st);

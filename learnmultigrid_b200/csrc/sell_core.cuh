@@ -27,17 +27,19 @@ struct SellArgs {
 };
 
 __host__ __device__ constexpr bool mode_is_gs(int m) { return m == GS || m == GS_RES || m == GS_NORM; }
-__host__ __device__ constexpr bool mode_has_partials(int m) { return m == RESNORM || m == GS_NORM; }
+__host__ __device__ constexpr bool mode_has_partials(int m) { return m == RESNORM || m == GS_NORM || m == SPMV_DOT; }
+__host__ __device__ constexpr bool mode_is_tail(int m) { return m == GS_RES || m == GS_NORM; }
 
 // ---- implied columns ------------------------------------------------------------------------------------------------
 // On a structured stencil level nearly every slice is REGULAR: entry j of every one of its 32 rows has column
 // row + off[j] with ONE offset table for the slice (mg_sell_slice_offsets; formats.sell_slice_offsets is the host twin).
-// For those slices the IMPL kernels compute the columns instead of streaming them: 4*LEN bytes of offsets per slice
-// in place of 128*LEN bytes of column indices, i.e. 64 instead of 88 bytes per 5-point row -- and the x gathers of a
-// warp become contiguous 256-byte reads.  The values, the gathers and the order of the additions are untouched, so the
+// For those slices the IMPL kernels compute the columns instead of streaming them: one 32-byte record of offsets per
+// slice (kOffStride ints, two 128-bit loads issued together with the value loads) in place of 128*LEN bytes of column
+// indices, i.e. 65 instead of 88 bytes per 5-point row -- and the x gathers of a warp become contiguous 256-byte reads.  The values, the gathers and the order of the additions are untouched, so the
 // results are the same bits; slices that are not regular (a boundary node among the rows, the ragged tail) take the
 // ordinary path inside the same kernel.  Uniform matrices with at most 8 entries per row only.
 constexpr int32_t kSliceIrregular = INT32_MIN;
+constexpr int kOffStride = 8;      // ints per slice in the offset table (rows of at most 8 entries)
 
 // What the epilogue of a row needs besides the row sum.
 struct SellEp {
@@ -59,11 +61,18 @@ struct SellEp {
 // residual costs no second pass over the matrix.  That is exact because a properly coloured sweep changes no other
 // entry this row reads (cycle.cu only asks for it on such levels), and it adds the products in storage order with the
 // diagonal in its place, i.e. it is the residual kernel's arithmetic.
+// A Gauss-Seidel row whose new value is stored by the caller (GS_NORM: after the block reduction, so that the
+// reduction's barrier does not wait for the store).
+struct RowOut {
+    double xn;
+    bool store;
+};
+
 template <int MODE, int LEN, bool PRED, bool IMPL>
 __device__ __forceinline__ void short_row(const SellArgs &A, const int32_t *__restrict__ c, const double *__restrict__ v,
-                                          const int32_t *__restrict__ o, int32_t o0, int len, const double *x, int64_t row,
+                                          const int32_t *oo, int len, const double *x, int64_t row,
                                           bool active, const SellEp &E, double &contrib, unsigned char halo_wait,
-                                          const ExArgs *fx) {
+                                          const ExArgs *fx, RowOut &out) {
     int32_t cc[LEN];
     double vv[LEN], xx[LEN];
 #pragma unroll
@@ -74,14 +83,18 @@ __device__ __forceinline__ void short_row(const SellArgs &A, const int32_t *__re
         }
     }
     if (IMPL) {
-        cc[0] = (int32_t)row + o0;
 #pragma unroll
-        for (int j = 1; j < LEN; ++j) cc[j] = (int32_t)row + __ldg(o + j);
+        for (int j = 0; j < LEN; ++j) cc[j] = (int32_t)row + oo[j];
     }
+    // prolongation rows are short (few bytes in flight per thread, registers to spare): fetch u under the matrix loads
+    double av = 0.0;
+    if (MODE == PROLONG && active) av = E.aux[row];
     if (halo_wait) fused_wait_ready(*fx);
+    // A Gauss-Seidel row never uses its own old value (the diagonal entry divides, and a row that is not updated has a
+    // zero there): no gather for it -- 8 bytes per row of DRAM reads less (ncu: 65 -> 57 B per 5-point row)
 #pragma unroll
     for (int j = 0; j < LEN; ++j)
-        if (!PRED || j < len) xx[j] = x[cc[j]];
+        if (!PRED || j < len) xx[j] = (mode_is_gs(MODE) && cc[j] == (int32_t)row) ? 0.0 : x[cc[j]];
     double sum = 0.0, diag = 0.0;
     // GS_RES / GS_NORM keep the separately rounded products (the VALUE for a diagonal entry, flagged in dmask) instead
     // of the row itself: 2 registers per entry across the division instead of 5
@@ -109,6 +122,9 @@ __device__ __forceinline__ void short_row(const SellArgs &A, const int32_t *__re
     if (!active) return;
     if (MODE == SPMV) {
         E.y[row] = sum;
+    } else if (MODE == SPMV_DOT) {
+        E.y[row] = sum;
+        contrib = E.aux[row] * sum;
     } else if (MODE == RESID) {
         E.y[row] = __dsub_rn(E.b[row], sum);
     } else if (MODE == RESNORM) {
@@ -118,25 +134,31 @@ __device__ __forceinline__ void short_row(const SellArgs &A, const int32_t *__re
         const double r = __dsub_rn(E.b[row], sum);
         E.y[row] = __dadd_rn(x[row], __dmul_rn(E.omega, __dmul_rn(E.aux[row], r)));
     } else if (MODE == PROLONG) {
-        E.y[row] = __dadd_rn(E.aux[row], sum);   // aux = u (may alias y)
+        E.y[row] = __dadd_rn(av, sum);   // aux = u (may alias y)
     } else {                             // Gauss-Seidel family
         const double bv = E.b[row];
         const bool upd = diag != 0.0;
         double xn = 0.0;
         if (upd) {
             xn = __ddiv_rn(__dsub_rn(bv, sum), diag);
-            E.y[row] = xn;
+            if (MODE == GS_NORM) {
+                out.xn = xn;
+                out.store = true;
+            } else {
+                E.y[row] = xn;
+            }
         }
         if (MODE == GS_RES || MODE == GS_NORM) {
             // residual of the row with its new value: the products in storage order, the diagonal entry times the new
-            // iterate in its place.  A diagonal entry of a row that was not updated is a stored zero: its product is
-            // an exact zero, and adding it would change nothing (a sum that starts at +0 never becomes -0).
+            // iterate in its place (selects, no branches).  A diagonal entry of a row that was not updated is a stored
+            // zero: xn is 0 then and the term an exact zero, which changes nothing (a sum that starts at +0 never
+            // becomes -0).
             double s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < LEN; ++j)
                 if (!PRED || j < len) {
-                    if (dmask & (1u << j)) { if (upd) s2 = __dadd_rn(s2, __dmul_rn(pp[j], xn)); }
-                    else s2 = __dadd_rn(s2, pp[j]);
+                    const double t = ((dmask >> j) & 1u) ? __dmul_rn(pp[j], xn) : pp[j];
+                    s2 = __dadd_rn(s2, t);
                 }
             const double r = __dsub_rn(bv, s2);
             if (MODE == GS_RES) A.r_out[row] = r;
@@ -159,7 +181,7 @@ __device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const d
     }
     if (halo_wait) fused_wait_ready(*fx);
 #pragma unroll
-    for (int j = 0; j < CNT; ++j) xx[j] = x[cc[j]];
+    for (int j = 0; j < CNT; ++j) xx[j] = (MODE == GS && cc[j] == row) ? 0.0 : x[cc[j]];
 #pragma unroll
     for (int j = 0; j < CNT; ++j) {
         if (MODE == GS) {
@@ -182,10 +204,11 @@ __device__ __forceinline__ void
 sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
           double *__restrict__ partials, int64_t bid, const ExArgs *fx, const unsigned char *__restrict__ mask) {
     static_assert(!IMPL || (UNIFORM && LEN > 0), "implied columns need a uniform matrix with short rows");
-    static_assert(LEN > 0 || MODE <= PROLONG, "fused residual modes need the row in registers");
+    static_assert(LEN > 0 || !mode_is_tail(MODE), "fused residual modes need the row in registers");
     const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
     const bool active = row >= A.row_begin && row < A.row_end;
     double contrib = 0.0;
+    RowOut out{0.0, false};
     if (row < A.row_end) {   // warp-uniform except in the last slice
         const int64_t slice = row >> 5;
         const int lane = (int)(row & 31);
@@ -206,14 +229,18 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
             constexpr int L = LEN > 0 ? LEN : 1;
             const SellEp E{b, aux, y, omega};
             if (IMPL) {
-                const int32_t *__restrict__ o = A.slice_off + slice * L;
-                const int32_t o0 = __ldg(o);
-                if (o0 != kSliceIrregular) short_row<MODE, L, false, true>(A, c, v, o, o0, L, x, row, active, E, contrib, hw, fx);
-                else short_row<MODE, L, false, false>(A, c, v, nullptr, 0, L, x, row, active, E, contrib, hw, fx);
+                // the slice's offset record: two 128-bit loads, the same address for the whole warp
+                const int4 *__restrict__ o = reinterpret_cast<const int4 *>(A.slice_off + slice * kOffStride);
+                const int4 oa = __ldg(o);
+                int4 ob = make_int4(0, 0, 0, 0);
+                if (L > 4) ob = __ldg(o + 1);
+                const int32_t oo[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+                if (oa.x != kSliceIrregular) short_row<MODE, L, false, true>(A, c, v, oo, L, x, row, active, E, contrib, hw, fx, out);
+                else short_row<MODE, L, false, false>(A, c, v, nullptr, L, x, row, active, E, contrib, hw, fx, out);
             } else if (UNIFORM || len == L) {
-                short_row<MODE, L, false, false>(A, c, v, nullptr, 0, L, x, row, active, E, contrib, hw, fx);
+                short_row<MODE, L, false, false>(A, c, v, nullptr, L, x, row, active, E, contrib, hw, fx, out);
             } else {
-                short_row<MODE, L, true, false>(A, c, v, nullptr, 0, len, x, row, active, E, contrib, hw, fx);
+                short_row<MODE, L, true, false>(A, c, v, nullptr, len, x, row, active, E, contrib, hw, fx, out);
             }
         } else {
             double sum = 0.0, diag = 0.0;
@@ -229,6 +256,9 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
             if (active) {
                 if (MODE == SPMV) {
                     y[row] = sum;
+                } else if (MODE == SPMV_DOT) {
+                    y[row] = sum;
+                    contrib = aux[row] * sum;
                 } else if (MODE == RESID) {
                     y[row] = __dsub_rn(b[row], sum);
                 } else if (MODE == RESNORM) {
@@ -245,8 +275,9 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
             }
         }
     }
+    if (MODE == GS_NORM && out.store) y[row] = out.xn;
     if (mode_has_partials(MODE)) {
-        const double s = block_sum<kBlock>(contrib);
+        const double s = block_sum_last<kBlock>(contrib);
         if (threadIdx.x == 0) partials[bid] = s;
     }
 }
@@ -255,7 +286,9 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
 // alive across the division and take 41-48 registers (5 CTAs) when left alone; capped at 40 (6 CTAs) where ptxas
 // manages that without spilling (build/sell_modes_gs.ptxas.log)
 __host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform) {
-    return (m > PROLONG && (len <= 5 || (uniform && len <= 7))) ? 6 : 1;
+    if (mode_is_tail(m)) return (len <= 5 || (uniform && len <= 7)) ? 6 : 1;
+    // the plain modes fit 32 registers (full occupancy); the Gauss-Seidel sweep does up to 5 entries per row
+    return (len >= 1 && uniform && len <= (m == GS ? 5 : 7)) ? 8 : 1;
 }
 
 template <int MODE, int LEN, bool UNIFORM, bool IMPL>
@@ -264,6 +297,58 @@ sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const dou
             double *y, double omega, double *__restrict__ partials) {
     pdl_prologue();
     sell_body<MODE, LEN, UNIFORM, false, IMPL>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
+}
+
+// Very short rows (linear transfer operators: one or two entries): one row per thread keeps only ~30 bytes per thread in
+// flight behind a chain of three dependent loads (slice pointer -> column -> vector entry), and the prolongation runs at
+// 5.4 instead of 6.8 TB/s (ncu, profiles/r02_ncu_step_sell_kernels.txt).  Here a thread takes R rows, 256 apart, and
+// issues every load of a stage for all of them before the first use.  SpMV and prolongation, LEN <= 2, no exchange site.
+template <int MODE, int LEN, int R>
+__global__ void __launch_bounds__(kBlock)
+sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
+    static_assert(MODE == SPMV || MODE == PROLONG, "short-row kernel: SpMV and prolongation only");
+    pdl_prologue();
+    int64_t row[R], base[R];
+    int len[R];
+    bool act[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        row[r] = A.first_row + ((int64_t)blockIdx.x * R + r) * kBlock + threadIdx.x;
+        act[r] = row[r] >= A.row_begin && row[r] < A.row_end;
+        base[r] = 0;
+        len[r] = 0;
+        if (row[r] < A.row_end) {
+            const int64_t sl = row[r] >> 5;
+            const int64_t p0 = A.slice_ptr[sl], p1 = A.slice_ptr[sl + 1];
+            base[r] = p0 + (row[r] & 31);
+            len[r] = (int)((p1 - p0) >> 5);
+        }
+    }
+    int32_t cc[R][LEN];
+    double vv[R][LEN], xx[R][LEN], av[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+        for (int j = 0; j < LEN; ++j)
+            if (j < len[r]) {
+                cc[r][j] = ld_stream(A.cols + base[r] + j * kSlice);
+                vv[r][j] = ld_stream(A.vals + base[r] + j * kSlice);
+            }
+        av[r] = (MODE == PROLONG && act[r]) ? aux[row[r]] : 0.0;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int j = 0; j < LEN; ++j)
+            if (j < len[r]) xx[r][j] = x[cc[r][j]];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        double sum = 0.0;
+#pragma unroll
+        for (int j = 0; j < LEN; ++j)
+            if (j < len[r]) sum = mul_add_unfused(sum, vv[r][j], xx[r][j]);
+        if (act[r]) y[row[r]] = MODE == PROLONG ? __dadd_rn(av[r], sum) : sum;
+    }
 }
 
 // The same kernel carrying an exchange site (multi-GPU, csrc/comm.cu): the first npeers*ctas_per_peer CTAs push the
@@ -346,8 +431,8 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
     const bool finisher = w == 0 && row >= A.row_begin && row < A.row_end;
     double bv = 0.0, av = 0.0;
     if (finisher) {
-        if (MODE != SPMV && MODE != PROLONG) bv = b[row];
-        if (MODE == JACOBI || MODE == PROLONG) av = aux[row];
+        if (MODE != SPMV && MODE != PROLONG && MODE != SPMV_DOT) bv = b[row];
+        if (MODE == JACOBI || MODE == PROLONG || MODE == SPMV_DOT) av = aux[row];
     }
     const double *__restrict__ v = A.vals + base + lane;
     const int32_t *__restrict__ c = A.cols + base + lane;
@@ -364,7 +449,7 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
         }
 #pragma unroll
         for (int j = 0; j < kWideU; ++j)
-            if (k0 + j * WPS < len) xx[j] = x[cc[j]];
+            if (k0 + j * WPS < len) xx[j] = (mode_is_gs(MODE) && cc[j] == row) ? 0.0 : x[cc[j]];
 #pragma unroll
         for (int j = 0; j < kWideU; ++j) {
             const int k = k0 + j * WPS;
@@ -388,6 +473,9 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
         }
         if (MODE == SPMV) {
             y[row] = sum;
+        } else if (MODE == SPMV_DOT) {
+            y[row] = sum;
+            contrib = av * sum;
         } else if (MODE == RESID) {
             y[row] = __dsub_rn(bv, sum);
         } else if (MODE == RESNORM) {
@@ -412,8 +500,7 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
                 double s2 = 0.0;
                 for (int k = 0; k < len; ++k) {
                     const double p = prod[sl][k][lane];
-                    if (skip[sl][k][lane]) { if (upd) s2 = __dadd_rn(s2, __dmul_rn(p, xn)); }
-                    else s2 = __dadd_rn(s2, p);
+                    s2 = __dadd_rn(s2, skip[sl][k][lane] ? __dmul_rn(p, xn) : p);
                 }
                 const double r = __dsub_rn(bv, s2);
                 if (MODE == GS_RES) A.r_out[row] = r;
@@ -422,7 +509,7 @@ sell_wide_kernel(SellArgs A, int uniform_len, const double *x, const double *__r
         }
     }
     if (mode_has_partials(MODE)) {
-        const double s = block_sum<kBlock>(contrib);
+        const double s = block_sum_last<kBlock>(contrib);
         if (threadIdx.x == 0) partials[blockIdx.x] = s;
     }
 }
@@ -434,6 +521,8 @@ extern int64_t g_wide_max_rows;     // ... for launches of at most this many row
 extern int64_t g_tma_min_rows;      // rows per launch from which the bulk-async staged kernel is used; 0 disables it
 extern int g_implied_columns;       // use the offset tables of matrices that carry one
 extern int64_t g_implied_min_rows;  // ... for launches of at least this many rows
+extern int g_short_rows_per_thread; // rows per thread of sell_short_kernel (1 = off, 2 or 4)
+extern int64_t g_short_min_rows;    // ... for launches of at least this many rows
 
 template <int MODE>
 int launch_sell_tma(const mg_sell *M, int64_t max_len, const double *x, const double *b, const double *aux, double *y,
@@ -476,7 +565,7 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     if (nblocks_out) *nblocks_out = 0;
     if (fuse && !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot carry an exchange site");
     if (row1 <= row0) return MG_OK;
-    if (MODE > PROLONG && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
+    if (mode_is_tail(MODE) && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
     if constexpr (MODE <= PROLONG) {
         if (g_tma_min_rows > 0 && row1 - row0 >= g_tma_min_rows && A->max_slice_len > 0) {
             int grid = 0;
@@ -507,6 +596,22 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     }
     const int64_t grid = (nthreads + kBlock - 1) / kBlock;
     if (grid + (fuse ? fuse->nex : 0) > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
+    if constexpr (MODE == SPMV || MODE == PROLONG) {
+        if (!fuse && ml >= 1 && ml <= 2 && g_short_rows_per_thread > 1 && row1 - row0 >= g_short_min_rows && A->d_slice_ptr) {
+            const int R = g_short_rows_per_thread >= 4 ? 4 : 2;
+            const unsigned sg = (unsigned)((grid + R - 1) / R);
+            if (ml == 1) {
+                if (R == 4) launch_k(sell_short_kernel<MODE, 1, 4>, sg, kBlock, st, a, x, aux, y);
+                else launch_k(sell_short_kernel<MODE, 1, 2>, sg, kBlock, st, a, x, aux, y);
+            } else {
+                if (R == 4) launch_k(sell_short_kernel<MODE, 2, 4>, sg, kBlock, st, a, x, aux, y);
+                else launch_k(sell_short_kernel<MODE, 2, 2>, sg, kBlock, st, a, x, aux, y);
+            }
+            MG_CHECK_LAUNCH(name);
+            if (nblocks_out) *nblocks_out = (int)sg;
+            return MG_OK;
+        }
+    }
     const bool impl = sell_use_implied(A, row0, row1);
 #define MG_SELL_LAUNCH(L, U, I)                                                                                          \
     do {                                                                                                                 \
@@ -523,7 +628,7 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
         MG_SELL_CASE(1); MG_SELL_CASE(2); MG_SELL_CASE(3); MG_SELL_CASE(4);
         MG_SELL_CASE(5); MG_SELL_CASE(6); MG_SELL_CASE(7); MG_SELL_CASE(8);
         default:   // long rows, or length unknown (0)
-            if constexpr (MODE <= PROLONG) MG_SELL_LAUNCH(0, false, false);
+            if constexpr (!mode_is_tail(MODE)) MG_SELL_LAUNCH(0, false, false);
             else return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
     }
 #undef MG_SELL_CASE
@@ -540,7 +645,7 @@ static int launch_sell_push(const mg_sell *A, double *x, const double *b, int64_
     const char *name = "sell_gs_rows_push";
     if (nblocks_out) *nblocks_out = 0;
     if (!push || !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot push an exchange site");
-    if (MODE > PROLONG && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
+    if (mode_is_tail(MODE) && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
     const SellArgs a = sell_args(A, row0, row1, r_out);
     const int64_t ml = A->max_slice_len;
     const bool uni = A->uniform_len > 0 && A->uniform_len == ml;

@@ -15,6 +15,9 @@ int64_t g_tma_min_rows = 0;          // off by default: the register-staged kern
 // rows 11.8 -> 9.9 us, but 263 k rows 3.5 -> 4.8 us (one more dependent load in a latency-bound launch): hence the floor.
 int g_implied_columns = 1;
 int64_t g_implied_min_rows = 1 << 19;
+// rows of one or two entries (linear transfers): R rows per thread on large launches (sell_short_kernel)
+int g_short_rows_per_thread = 2;
+int64_t g_short_min_rows = 1 << 18;
 
 __global__ void __launch_bounds__(kBlock)
 sell_slice_offsets_kernel(int64_t nslices, int64_t nrows, int len, const int32_t *__restrict__ cols,
@@ -24,14 +27,17 @@ sell_slice_offsets_kernel(int64_t nslices, int64_t nrows, int len, const int32_t
     if (w >= nslices) return;
     const int64_t row = w * kSlice + lane;
     bool regular = (w + 1) * kSlice <= nrows;
-    for (int j = 0; j < len; ++j) {
-        const int64_t rel = (int64_t)cols[(w * len + j) * kSlice + lane] - row;
-        const int64_t rel0 = __shfl_sync(0xffffffffu, rel, 0);
-        regular = __all_sync(0xffffffffu, rel == rel0) && regular;
-        if (lane == 0) off[w * len + j] = (int32_t)rel0;
+    for (int j = 0; j < kOffStride; ++j) {
+        int64_t rel0 = 0;
+        if (j < len) {
+            const int64_t rel = (int64_t)cols[(w * len + j) * kSlice + lane] - row;
+            rel0 = __shfl_sync(0xffffffffu, rel, 0);
+            regular = __all_sync(0xffffffffu, rel == rel0) && regular;
+        }
+        if (lane == 0) off[w * kOffStride + j] = (int32_t)rel0;
     }
     if (lane == 0) {
-        if (!regular) off[w * len] = kSliceIrregular;
+        if (!regular) off[w * kOffStride] = kSliceIrregular;
         else if (nregular) atomicAdd(nregular, 1ull);
     }
 }
@@ -190,12 +196,14 @@ int mg_sell_halo_mask(const mg_sell *A, int64_t first_halo_col, unsigned char *d
     MG_CHECK_LAUNCH("sell_halo_mask");
     return MG_OK;
 }
-/* per-slice column offsets of a UNIFORM matrix (uniform_len entries per row): d_off[s * len + j]; slices that are not
- * regular get d_off[s * len] = INT32_MIN (see sell_core.cuh); *d_nregular (device, zeroed by the caller, may be NULL)
- * counts the regular slices */
+/* per-slice column offsets of a UNIFORM matrix (uniform_len <= 8 entries per row): one record of 8 ints per slice,
+ * d_off[s * 8 + j] (32-byte aligned: cudaMalloc'ed); slices that are not regular get d_off[s * 8] = INT32_MIN (see
+ * sell_core.cuh); *d_nregular (device, zeroed by the caller, may be NULL) counts the regular slices */
 int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, int64_t *d_nregular, void *stream) {
     if (int rc = check_sell(A)) return rc;
-    MG_REQUIRE(d_off && A->uniform_len > 0 && A->uniform_len == A->max_slice_len, "uniform SELL matrix expected");
+    MG_REQUIRE(d_off && A->uniform_len > 0 && A->uniform_len == A->max_slice_len && A->uniform_len <= kOffStride,
+               "uniform SELL matrix with at most 8 entries per row expected");
+    MG_REQUIRE(((uintptr_t)d_off & 31) == 0, "offset table must be 32-byte aligned");
     if (A->nslices == 0) return MG_OK;
     sell_slice_offsets_kernel<<<(unsigned)((A->nslices * 32 + kBlock - 1) / kBlock), kBlock, 0, (cudaStream_t)stream>>>(
         A->nslices, A->nrows, (int)A->uniform_len, A->d_cols, d_off, (unsigned long long *)d_nregular);
@@ -221,6 +229,16 @@ int mg_set_implied_columns(int enabled) {
 int64_t mg_set_implied_min_rows(int64_t rows) {
     const int64_t prev = g_implied_min_rows;
     g_implied_min_rows = rows < 0 ? 0 : rows;
+    return prev;
+}
+int mg_set_short_rows_per_thread(int r) {
+    const int prev = g_short_rows_per_thread;
+    g_short_rows_per_thread = r >= 4 ? 4 : r >= 2 ? 2 : 1;
+    return prev;
+}
+int64_t mg_set_short_min_rows(int64_t rows) {
+    const int64_t prev = g_short_min_rows;
+    g_short_min_rows = rows < 0 ? 0 : rows;
     return prev;
 }
 int64_t mg_set_wide_min_len(int64_t len) {

@@ -12,7 +12,7 @@ dot_partials_kernel(int64_t n, const double *__restrict__ x, const double *__res
     double s = 0.0;
     const int64_t stride = (int64_t)gridDim.x * kBlock;
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) s += x[i] * y[i];
-    s = block_sum<kBlock>(s);
+    s = block_sum_last<kBlock>(s);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
@@ -66,6 +66,51 @@ scatter_kernel(int64_t n, const int32_t *__restrict__ idx, const double *__restr
     for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) out[idx[i]] = in[i];
 }
 
+// ---- conjugate gradients with the scalars on the device (cycle.cu mg_pcg_*; CG.py:30-48) ----------------------------
+// scalars s[]: [0] r.z  [1] p.Ap  [2] alpha  [3] beta  [4] r.r
+// p = z + beta p  (first iteration: p = z); same rounding as mg_axpby(beta, p, 1, z, p)
+__global__ void __launch_bounds__(kBlock)
+pcg_direction_kernel(int64_t n, const double *__restrict__ z, double *__restrict__ p, const double *__restrict__ s, int first) {
+    pdl_prologue();
+    const double beta = first ? 0.0 : s[3];
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride)
+        p[i] = first ? z[i] : __dadd_rn(__dmul_rn(beta, p[i]), z[i]);
+}
+// x += alpha p, r -= alpha Ap and the per-CTA partial sums of r.r in one pass (48 B per row instead of 64 + a dot)
+__global__ void __launch_bounds__(kBlock)
+pcg_update_kernel(int64_t n, const double *__restrict__ p, const double *__restrict__ Ap, double *__restrict__ x,
+                  double *__restrict__ r, const double *__restrict__ s, double *__restrict__ partials) {
+    pdl_prologue();
+    const double alpha = s[2];
+    double acc = 0.0;
+    const int64_t stride = (int64_t)gridDim.x * kBlock;
+    for (int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x; i < n; i += stride) {
+        x[i] = __dadd_rn(__dmul_rn(alpha, p[i]), x[i]);
+        const double ri = __dadd_rn(__dmul_rn(-alpha, Ap[i]), r[i]);
+        r[i] = ri;
+        acc += ri * ri;
+    }
+    acc = block_sum_last<kBlock>(acc);
+    if (threadIdx.x == 0) partials[blockIdx.x] = acc;
+}
+// what follows a reduction: op 0: s[4] = v (r.r);  op 1: beta = v / s[0], s[0] = v (v = new r.z);  op 2: s[1] = v,
+// alpha = s[0] / v (v = p.Ap)
+__global__ void pcg_scalar_kernel(int op, int first, double *s, const double *in) {
+    pdl_prologue();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double v = *in;
+    if (op == 0) {
+        s[4] = v;
+    } else if (op == 1) {
+        s[3] = first ? 0.0 : v / s[0];
+        s[0] = v;
+    } else {
+        s[1] = v;
+        s[2] = s[0] / v;
+    }
+}
+
 static inline unsigned stream_grid(int64_t n) {
     int64_t g = (n + kBlock - 1) / kBlock;
     const int64_t cap = (int64_t)sm_count() * 8;   // 8 resident CTAs of 256 threads per SM
@@ -80,6 +125,32 @@ int vec_dot(int64_t n, const double *x, const double *y, double *partials, doubl
     MG_CHECK_LAUNCH("dot_partials");
     launch_k(reduce_partials_kernel2, (unsigned)(1), (unsigned)1024, st, partials, g, out);
     MG_CHECK_LAUNCH("reduce_partials");
+    return MG_OK;
+}
+int vec_dot_partials(int64_t n, const double *x, const double *y, double *partials, int *nblocks, cudaStream_t st) {
+    const unsigned g = stream_grid(n);
+    launch_k(dot_partials_kernel, (unsigned)(g), (unsigned)kBlock, st, n, x, y, partials);
+    MG_CHECK_LAUNCH("dot_partials");
+    *nblocks = (int)g;
+    return MG_OK;
+}
+int vec_pcg_direction(int64_t n, const double *z, double *p, const double *s, int first, cudaStream_t st) {
+    if (n <= 0) return MG_OK;
+    launch_k(pcg_direction_kernel, (unsigned)(stream_grid(n)), (unsigned)kBlock, st, n, z, p, s, first);
+    MG_CHECK_LAUNCH("pcg_direction");
+    return MG_OK;
+}
+int vec_pcg_update(int64_t n, const double *p, const double *Ap, double *x, double *r, const double *s,
+                   double *partials, int *nblocks, cudaStream_t st) {
+    const unsigned g = stream_grid(n);
+    launch_k(pcg_update_kernel, (unsigned)(g), (unsigned)kBlock, st, n, p, Ap, x, r, s, partials);
+    MG_CHECK_LAUNCH("pcg_update");
+    *nblocks = (int)g;
+    return MG_OK;
+}
+int vec_pcg_scalar(int op, int first, double *s, const double *in, cudaStream_t st) {
+    launch_k(pcg_scalar_kernel, 1u, 32u, st, op, first, s, in);
+    MG_CHECK_LAUNCH("pcg_scalar");
     return MG_OK;
 }
 int vec_axpby(int64_t n, double a, const double *x, double b, const double *y, double *out, cudaStream_t st) {

@@ -616,6 +616,9 @@ class DistributedHierarchy(DeviceHierarchy):
         _lib.check(self.lib.mg_graph_launch(g[0], st), "mg_graph_launch")
         self.last_launches = g[1]
 
+    def _comm_ptr(self):
+        return ctypes.byref(self.comm.struct)
+
     def last_norm(self):
         """sqrt of the squared residual norm the last with_norm program computed (synchronises)"""
         self._norm_host.copy_(self._norm_out, non_blocking=True)

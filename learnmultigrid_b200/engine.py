@@ -59,7 +59,7 @@ class DeviceSell:
             return
         import torch
         nsl = (self.shape[0] + 31) // 32
-        off = torch.empty(nsl * self.uniform_len, dtype=torch.int32, device=self.cols.device)
+        off = torch.empty(nsl * 8, dtype=torch.int32, device=self.cols.device)       # one 32-byte record per slice
         cnt = torch.zeros(1, dtype=torch.int64, device=self.cols.device)
         _lib.check(_lib.load().mg_sell_slice_offsets(ctypes.byref(self.struct), off.data_ptr(), cnt.data_ptr(),
                                                      _lib.stream_handle(torch)), "mg_sell_slice_offsets")
@@ -94,7 +94,7 @@ class DeviceSell:
             return self.padded * 12 + (0 if self.uniform_len else self.slice_ptr.numel() * 8)
         per_slice = 32 * self.uniform_len
         irregular = nsl - self.regular_slices
-        return self.padded * 8 + irregular * per_slice * 4 + nsl * self.uniform_len * 4
+        return self.padded * 8 + irregular * per_slice * 4 + nsl * 32
 
 
 class Level:
@@ -403,60 +403,90 @@ class DeviceHierarchy:
         self.last_launches = g[1]
 
     # ------------------------------------------------------------------------------------------------
-    def pcg(self, rhs, params, error=1e-8, max_iterations=1000):
+    def _comm_ptr(self):
+        """the communicator of a partitioned hierarchy (distributed.py overrides), or None"""
+        return None
+
+    def pcg(self, rhs, params, error=1e-8, max_iterations=1000, view=False):
         """Conjugate gradients preconditioned by one V-cycle per iteration (BASELINE.json configs[4]), entirely in
-        the level-0 ordering of this hierarchy: A p by the SELL kernel, z = M^-1 r by replaying the captured cycle on
-        (x_0, b_0) = (0, r) -- the residual LIVES in the level's right-hand-side buffer, so nothing is copied or
-        permuted per iteration.  Statement order = solvers/CG.py (the reference's CG.py:12-50 plus the
-        preconditioner).  Returns (solution (n,1) natural order, history list, iterations)."""
+        the level-0 ordering of this hierarchy and entirely on the device (mg_pcg_start / mg_pcg_iterate): the residual
+        LIVES in the level's right-hand-side buffer and z = M^-1 r in its iterate, so nothing is copied or permuted per
+        iteration; the scalars stay on the device, p.Ap comes out of the SpMV and r.r out of the update of x and r; an
+        iteration is one CUDA graph, after which the host reads 8 bytes (the convergence test).  params=None: plain CG.
+        Statement order = solvers/CG.py (the reference's CG.py:12-50 plus the preconditioner).  Works on a partitioned
+        hierarchy too (every rank makes the same call; dots are summed over the ranks in rank order).
+        Returns (solution (n,1) natural order -- this rank's block when partitioned --, history list, iterations);
+        self.last_pcg_timing holds the wall-clock split transfer in / iterations / transfer out."""
+        import time
         torch, lib = self.torch, self.lib
         lev = self.levels[0]
         n = self.n
-        if getattr(lev, "n_halo", 0):
-            raise _lib.MgError("pcg() runs on a single-GPU hierarchy")
         st = _lib.stream_handle(torch)
+        comm = self._comm_ptr()
         if getattr(self, "_cg", None) is None:
-            self._cg = [torch.zeros(n, dtype=torch.float64, device=self.device) for _ in range(3)]
-        x, p, Ap = self._cg
-        r, z = lev.b, lev.x
+            n_vec = getattr(lev, "n_vec", n)
+            x = torch.zeros(n, dtype=torch.float64, device=self.device)
+            p = torch.zeros(n_vec, dtype=torch.float64, device=self.device)
+            Ap = torch.zeros(n, dtype=torch.float64, device=self.device)
+            sc = torch.zeros(8, dtype=torch.float64, device=self.device)
+            slots = torch.zeros(_lib.MG_MAX_RANKS, dtype=torch.float64, device=self.device)
+            self._cg = (x, p, Ap, sc, slots)
+            self._cg_struct = _lib.mg_pcg(x.data_ptr(), p.data_ptr(), Ap.data_ptr(), sc.data_ptr(),
+                                          self._norm_ws.data_ptr(), slots.data_ptr())
+            self._cg_graphs = {}
+        x, p, Ap, sc, _ = self._cg
+        pcg = ctypes.byref(self._cg_struct)
+        pp = None if params is None else ctypes.byref(params)
 
-        def dot(a, b):
-            _lib.check(lib.mg_dot(n, a.data_ptr(), b.data_ptr(), self._norm_ws.data_ptr(), self._norm_out.data_ptr(), st),
-                       "mg_dot")
-            self._norm_host.copy_(self._norm_out, non_blocking=True)
+        def read_rr():
+            self._norm_host.copy_(sc[4:5], non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            return float(self._norm_host.item())
+            return float(np.sqrt(self._norm_host.item()))
 
-        def axpby(a, xx, b, yy, out):
-            _lib.check(lib.mg_axpby(n, float(a), xx.data_ptr(), float(b), yy.data_ptr(), out.data_ptr(), st), "mg_axpby")
+        def iterate(first):
+            key = (first, None if params is None else (params.smoother, params.nu_pre, params.nu_post, params.omega,
+                                                       params.zero_guess_skip, params.reverse_post))
+            g = self._cg_graphs.get(key)
+            if g is None:
+                if self.smoother == "lexgs" and params is not None:      # cooperative launches are not captured
+                    _lib.check(lib.mg_pcg_iterate(comm, self._level_structs, self.nlevels, pp, pcg, first, st),
+                               "mg_pcg_iterate")
+                    return
+                cap = torch.cuda.Stream(device=self.device)
+                cap.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(cap):
+                    h = cap.cuda_stream
+                    _lib.check(lib.mg_graph_begin(h), "mg_graph_begin")
+                    rc = lib.mg_pcg_iterate(comm, self._level_structs, self.nlevels, pp, pcg, first, h)
+                    out = ctypes.c_void_p()
+                    rc2 = lib.mg_graph_end(h, ctypes.byref(out))
+                    _lib.check(rc, "mg_pcg_iterate (capture)")
+                    _lib.check(rc2, "mg_graph_end")
+                torch.cuda.current_stream().wait_stream(cap)
+                g = self._cg_graphs[key] = out
+                self._graphs[("pcg",) + key] = (out, 0)        # destroyed with the other graphs
+            _lib.check(lib.mg_graph_launch(g, st), "mg_graph_launch")
 
-        def precondition():
-            z.zero_()
-            self.vcycle(params)
-
+        t0 = time.perf_counter()
         self.set_rhs(rhs)                      # r = b - A*0 = b
-        x.zero_()
-        track = [float(np.sqrt(dot(r, r)))]
-        precondition()
-        p.copy_(z)
-        rz = dot(r, z)
+        torch.cuda.current_stream().synchronize()
+        t1 = time.perf_counter()
+        _lib.check(lib.mg_pcg_start(comm, self._level_structs, pcg, st), "mg_pcg_start")
+        track = [read_rr()]
         its = 0
-        for _ in range(max_iterations):
+        for k in range(max_iterations):
             its += 1
-            _lib.check(lib.mg_sell_spmv(ctypes.byref(lev.A.struct), p.data_ptr(), Ap.data_ptr(), st), "mg_sell_spmv")
-            alpha = rz / dot(p, Ap)
-            axpby(alpha, p, 1.0, x, x)
-            axpby(-alpha, Ap, 1.0, r, r)
-            res = float(np.sqrt(dot(r, r)))
+            iterate(1 if k == 0 else 0)
+            res = read_rr()
             track.append(res)
             if res <= error:
                 break
-            precondition()
-            rz_new = dot(r, z)
-            beta = rz_new / rz
-            rz = rz_new
-            axpby(beta, p, 1.0, z, p)
-        return self._from_level0(x), track, its
+        t2 = time.perf_counter()
+        sol = self._from_level0(x, view)
+        t3 = time.perf_counter()
+        self.last_pcg_timing = {"transfer_in_s": t1 - t0, "iterations_s": t2 - t1, "transfer_out_s": t3 - t2,
+                                "iterations": its}
+        return sol, track, its
 
     def __del__(self):
         try:

@@ -6,12 +6,13 @@ from .. import _lib
 from .Solver import IterativeSolver
 
 
-def _same_operator(P, A):
-    """True only if the preconditioner was built from THIS operator (same object, or the same CSC arrays entry for
-    entry); a multigrid built from another matrix of the same sparsity must not replace A in `A p`."""
+def _same_operator(P, A, P_src=None, A_src=None):
+    """True only if the preconditioner was built from THIS operator (same object -- the stored matrix or the object the
+    caller constructed both solvers from -- or the same CSC arrays entry for entry); a multigrid built from another
+    matrix of the same sparsity must not replace A in `A p`."""
     if P is None:
         return False
-    if P is A:
+    if P is A or (P_src is not None and P_src is A_src):
         return True
     if P.shape != A.shape or P.nnz != A.nnz or P.format != A.format:
         return False
@@ -31,17 +32,25 @@ class CG(IterativeSolver):
         changes results only in the last bits.  `preconditioner(r_dev, z_dev)` applies z = M^-1 r on device
         vectors (see solvers.Multigrid.Multigrid.as_preconditioner)."""
         h = getattr(preconditioner, "hierarchy", None)
-        if (h is not None and initial_guess is None and _same_operator(getattr(preconditioner, "matrix", None),
-                                                                       self.matrix)
-                and not getattr(h.levels[0], "n_halo", 0)):
+        if (h is not None and initial_guess is None
+                and _same_operator(getattr(preconditioner, "matrix", None), self.matrix,
+                                   getattr(preconditioner, "matrix_src", None), getattr(self, "_matrix_src", None))):
             # the preconditioner's hierarchy already holds this operator on the device (SELL, level-0 ordering): run
-            # the whole iteration there (engine.DeviceHierarchy.pcg) instead of uploading a second copy of the matrix
+            # the whole iteration there (engine.DeviceHierarchy.pcg: scalars on the device, one CUDA graph per
+            # iteration; also on a row-partitioned hierarchy) instead of uploading a second copy of the matrix
             x, track, its = h.pcg(self.rhs, preconditioner.params, error=error, max_iterations=max_iterations)
+            r = h._from_level0(h.levels[0].b)                         # the residual lives in the level-0 rhs buffer
+            if getattr(h, "comm", None) is not None:                  # partitioned: x and r are this rank's row blocks
+                if not getattr(self, "local_solution", False):
+                    x = np.concatenate([v.reshape(-1) for v in h.fabric.allgather(x.reshape(-1))]).reshape(-1, 1)
+                    r = np.concatenate([v.reshape(-1) for v in h.fabric.allgather(r.reshape(-1))]).reshape(-1, 1)
+                h.check()
             self.iterations += its
             self.solution = x
             self.residual = track[-1]
             self.track_res = np.array(track, dtype=float).reshape(-1, 1)
-            self.residual_vector = h._from_level0(h.levels[0].b)      # the residual lives in the level-0 rhs buffer
+            self.residual_vector = r
+            self.last_timing = getattr(h, "last_pcg_timing", None)
             return
         d = self._device_csr()
         torch, lib, n = d["torch"], d["lib"], d["n"]

@@ -242,6 +242,7 @@ class Multigrid(IterativeSolver):
         apply.hierarchy = h            # solvers.CG runs the whole iteration inside the hierarchy when it sees these
         apply.params = params
         apply.matrix = self.matrix
+        apply.matrix_src = getattr(self, "_matrix_src", None)
         return apply
 
 

@@ -15,19 +15,22 @@ from .. import formats as F
 
 class Solver:
     def __init__(self, matrix, rhs):
-        # Solver.py:14-21
-        self.dim = rhs.size
-        self.residual_vector = np.empty(shape=rhs.shape)
+        # Solver.py:14-21 (rhs may also be a pinned torch tensor: it is then copied to the device without staging)
+        self.dim = int(rhs.numel()) if hasattr(rhs, "numel") else rhs.size
+        shape = tuple(rhs.shape)
+        self.residual_vector = np.empty(shape=shape)
         self.residual = 0.0
+        self._matrix_src = matrix            # the caller's object: lets two solvers recognise the same operator
         self.matrix = csc_matrix(matrix)
         self.rhs = rhs
-        self.solution = np.empty(shape=rhs.shape)
+        self.solution = np.empty(shape=shape)
         self.track_res = np.ndarray(shape=(0, 1), dtype=float)
         self._dev = None
 
     # accessors of Solver.py:23-48 (read access is generated from the table below the class)
     def set_matrix(self, matrix):
         self.matrix = matrix
+        self._matrix_src = matrix
         self._dev = None                 # the device copy belongs to the old matrix
 
     def set_rhs(self, rhs):

@@ -136,7 +136,8 @@ def test_rows_with_zero_or_missing_diagonal_keep_their_value_and_their_residual(
     bad = np.asarray(cptr, dtype=np.int64).copy()
     bad[1] = bad[2]                                # merge colours 0 and 1
     flag.zero_()
-    L.check(lib.mg_level_inspect(ctypes.byref(S.struct), nc, up(env, bad).data_ptr(), None, flag.data_ptr(), st(env)))
+    dbad = up(env, bad)
+    L.check(lib.mg_level_inspect(ctypes.byref(S.struct), nc, dbad.data_ptr(), None, flag.data_ptr(), st(env)))
     assert int(flag.item()) & 1
 
 
@@ -156,8 +157,8 @@ def test_first_sweep_on_a_zero_iterate_without_the_matrix(env):
     want = torch.zeros(n + 17, dtype=torch.float64, device=env["dev"])            # 17 halo entries behind the rows
     L.check(lib.mg_sell_gs_rows(ctypes.byref(S.struct), want.data_ptr(), db.data_ptr(), 0, int(cptr[1]), st(env)))
     got = torch.full((n + 17,), 3.0, dtype=torch.float64, device=env["dev"])
-    L.check(lib.mg_sell_gs_zero_first(n + 17, 0, int(cptr[1]), up(env, Ap.diagonal()).data_ptr(), db.data_ptr(),
-                                      got.data_ptr(), st(env)))
+    dd = up(env, Ap.diagonal())
+    L.check(lib.mg_sell_gs_zero_first(n + 17, 0, int(cptr[1]), dd.data_ptr(), db.data_ptr(), got.data_ptr(), st(env)))
     assert np.array_equal(got.cpu().numpy().view(np.int64), want.cpu().numpy().view(np.int64))    # signs of zero too
 
 
@@ -287,7 +288,88 @@ def test_norm_workspace_covers_the_wide_kernel(env):
     size = int(lib.mg_norm_workspace_size(n))
     ws = torch.full((size + 4096,), -123.0, dtype=torch.float64, device=env["dev"])
     nrm = torch.zeros(1, dtype=torch.float64, device=env["dev"])
-    L.check(lib.mg_sell_residual_norm2(ctypes.byref(S.struct), up(env, x).data_ptr(), up(env, b).data_ptr(), ws.data_ptr(),
+    dx, db = up(env, x), up(env, b)
+    L.check(lib.mg_sell_residual_norm2(ctypes.byref(S.struct), dx.data_ptr(), db.data_ptr(), ws.data_ptr(),
                                        nrm.data_ptr(), st(env)))
     np.testing.assert_allclose(np.sqrt(nrm.item()), np.linalg.norm(b - A @ x), rtol=1e-13)
     assert bool((ws[size:] == -123.0).all())
+
+
+@pytest.mark.parametrize("rpt", [2, 4])
+def test_short_row_kernel_is_bit_identical(env, rpt):
+    """transfer operators with one or two entries per row: R rows per thread (sell_short_kernel) against the oracle, whole
+    matrix and row ranges that start and end inside a slice, out of place and in place"""
+    from learnmultigrid_b200 import formats as F, problems as P
+    from learnmultigrid_b200.engine import DeviceSell
+    L, lib, torch = env["L"], env["lib"], env["torch"]
+    Q = F.canonical_csr(P.linear_P_2d(96))
+    onecol = F.canonical_csr(sp.csr_matrix((np.arange(1.0, 3001.0), (np.arange(3000), np.arange(3000) % 77)), shape=(3000, 77)))
+    old_r, old_min = lib.mg_set_short_rows_per_thread(rpt), lib.mg_set_short_min_rows(0)
+    try:
+        for M in (Q, onecol):
+            S = DeviceSell(torch, M, env["dev"])
+            assert 1 <= S.max_len <= 2
+            rng = np.random.default_rng(5)
+            e, u = rng.standard_normal(M.shape[1]), rng.standard_normal(M.shape[0])
+            de, du = up(env, e), up(env, u)
+            out = torch.empty(M.shape[0], dtype=torch.float64, device=env["dev"])
+            L.check(lib.mg_sell_spmv(ctypes.byref(S.struct), de.data_ptr(), out.data_ptr(), st(env)))
+            assert np.array_equal(out.cpu().numpy(), K.spmv(M, e))
+            L.check(lib.mg_sell_prolong_correct(ctypes.byref(S.struct), de.data_ptr(), du.data_ptr(), out.data_ptr(), st(env)))
+            want = K.prolong_correct(M, e, u)
+            assert np.array_equal(out.cpu().numpy(), want)
+            for r0, r1 in ((0, 1), (37, M.shape[0] - 45), (513, 1301), (M.shape[0] - 1, M.shape[0])):
+                part = up(env, u)                                   # in place on a row range
+                L.check(lib.mg_sell_prolong_correct_rows(ctypes.byref(S.struct), de.data_ptr(), part.data_ptr(),
+                                                         part.data_ptr(), r0, r1, st(env)))
+                got = part.cpu().numpy()
+                assert np.array_equal(got[r0:r1], want[r0:r1])
+                assert np.array_equal(got[:r0], u[:r0]) and np.array_equal(got[r1:], u[r1:])
+    finally:
+        lib.mg_set_short_rows_per_thread(old_r)
+        lib.mg_set_short_min_rows(old_min)
+
+
+def test_device_pcg_single_and_partitioned(env):
+    """BASELINE configs[4] on the device-side iteration (mg_pcg_start / mg_pcg_iterate: scalars on the device, p.Ap from
+    the SpMV, r.r from the update, one graph per iteration): against the CPU oracle's PCG, and row-partitioned over 2 and
+    3 virtual ranks against the single-GPU run (same iteration count, histories to rounding of the dot products)"""
+    from learnmultigrid_b200 import problems as P
+    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    from oracle.vcycle import OracleMultigrid, pcg_solve
+    N, L = 128, 5
+    A = P.symmetric_dirichlet(P.structured_laplacian_2d(N, P.variable_coefficient), P.boundary_nodes_2d(N))
+    rhs = P.structured_rhs_2d(N)
+    Qs = P.structured_hierarchy_2d(N, L, transfer="linear")
+    h = DeviceHierarchy(A, Qs, smoother="mcgs")
+    params = h.make_params(nu_pre=1, nu_post=1, reverse_post=True)
+    x, hist, its = h.pcg(rhs, params, error=1e-10, max_iterations=60)
+    o = OracleMultigrid(A, rhs, Qs, smoother="mcgs", colors=h.colors, hoist_setup=True, reverse_post=True)
+    o.build_hierarchy(L)
+    n = A.shape[0]
+    xo, ho, io = pcg_solve(A, rhs, lambda r: o.v_cycle(o.matrix, np.zeros((n, 1)), r, 1, L), 60, 1e-10)
+    assert its == io and its < 15
+    np.testing.assert_allclose(hist, np.asarray(ho).ravel(), rtol=1e-6)
+    np.testing.assert_allclose(x, xo, rtol=0, atol=1e-9 * np.linalg.norm(xo))
+    x2, hist2, its2 = h.pcg(rhs, params, error=1e-10, max_iterations=60)          # graphs replayed: same bits
+    assert its2 == its and hist2 == hist and np.array_equal(x, x2)
+    # plain CG through the same device iteration
+    xc, hc, ic = h.pcg(rhs, None, error=1e-8, max_iterations=2000)
+    assert ic > 5 * its and hc[-1] <= 1e-8
+    np.testing.assert_allclose(xc, xo, rtol=0, atol=1e-6 * np.linalg.norm(xo))
+
+    for world in (2, 3):
+        def body(fab):
+            hd = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h.colors, n_dist=2, region_bytes=1 << 20,
+                                      max_sites=512, timeout_s=30.0)
+            pd = hd.make_params(nu_pre=1, nu_post=1, reverse_post=True)
+            xl, hl, il = hd.pcg(rhs, pd, error=1e-10, max_iterations=60)
+            hd.check()
+            o0, o1 = int(hd.offsets[0][fab.rank]), int(hd.offsets[0][fab.rank + 1])
+            hd.close()
+            return xl, hl, il, o0, o1
+        for xl, hl, il, o0, o1 in run_virtual_ranks(world, body):
+            assert il == its
+            np.testing.assert_allclose(hl, hist, rtol=1e-7)
+            np.testing.assert_allclose(xl, x[o0:o1], rtol=0, atol=1e-10 * np.linalg.norm(x))

@@ -75,19 +75,25 @@ def main():
         pre = mg.as_preconditioner(levels=a.levels, smoother="GaussSeidel", smooth_steps=1)
         torch.cuda.synchronize()
         t_setup = time.perf_counter() - t0
-        cg = CG(A, rhs)
+        rhs_pinned = torch.from_numpy(np.ascontiguousarray(rhs.reshape(-1))).pin_memory()
+        cg = CG(A, rhs_pinned)
         cg.solve(max_iterations=3, error=0.0, preconditioner=pre)          # warm-up: graph capture, kernel loading
-        cg = CG(A, rhs)
+        cg = CG(A, rhs_pinned)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         cg.solve(max_iterations=200, error=a.tol, preconditioner=pre)
         torch.cuda.synchronize()
         t_solve = time.perf_counter() - t0
+        tm = cg.last_timing or {}
         line = {"config": "C5 setup sweep + MG-preconditioned CG", "grid": "%dx%d" % (N + 1, N + 1), "dof": n0,
                 "levels": a.levels, "transfer": a.transfer, "coefficient": a.coefficient, "generate_s": round(t_gen, 2),
                 "galerkin": galerkin, "galerkin_total_ms": sum(g["ms"] for g in galerkin),
                 "setup_total_s": round(t_setup, 3), "pcg_iterations": cg.get_iterations(), "pcg_tol": a.tol,
                 "pcg_final_residual": float(cg.track_res[-1, 0]), "pcg_solve_ms": t_solve * 1e3,
+                "pcg_split_ms": {"rhs_host_to_device": tm.get("transfer_in_s", 0) * 1e3,
+                                 "iterations": tm.get("iterations_s", 0) * 1e3,
+                                 "per_iteration": tm.get("iterations_s", 0) * 1e3 / max(cg.get_iterations(), 1),
+                                 "solution_device_to_host": tm.get("transfer_out_s", 0) * 1e3},
                 "pcg_dof_per_s": n0 / t_solve}
         print(json.dumps(line), flush=True)
         del mg, cg, pre
