@@ -50,6 +50,9 @@ def parse_args():
     ap.add_argument("--cpu-n", type=int, default=2048,
                     help="mesh size of the bounded CPU sample (SURVEY 8d: <= 4 M DOF measured, the rest labelled extrapolated)")
     ap.add_argument("--setup", default=os.environ.get("MGB_BENCH_SETUP", "device"), choices=["host", "device"])
+    ap.add_argument("--generate", default=os.environ.get("MGB_BENCH_GENERATE", "device"), choices=["device", "host"],
+                    help="device (default; structured meshes with linear transfers): the synthetic operator and transfer "
+                         "operators are generated in HBM (problems_device.py) instead of in NumPy + upload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-parity-check", action="store_true",
@@ -323,7 +326,15 @@ def run_b200(a):
     n = a.n
     ndof = (n + 1) ** 2
     t0 = time.perf_counter()
-    A, rhs, Qs = build_problem(a, n)
+    on_device = a.generate == "device" and a.mesh == "structured" and a.transfer == "linear" and a.setup == "device"
+    if on_device:
+        from learnmultigrid_b200 import problems as P, problems_device as PD
+        A = PD.structured_laplacian_2d(n, PD.variable_coefficient if a.coefficient == "variable" else None)
+        Qs = PD.structured_hierarchy_2d(n, a.levels)
+        rhs = P.structured_rhs_2d(n)            # host vector: the end-to-end leg copies it in through the API
+        torch.cuda.synchronize()
+    else:
+        A, rhs, Qs = build_problem(a, n)
     t_gen = time.perf_counter() - t0
     mg = SemiGeometricMG(A, rhs, Qs)
     mg.setup = a.setup
@@ -562,7 +573,9 @@ def run_b200(a):
                            % (cyc["total"] / 1e9), "setup": a.setup, "levels_rows": list(getattr(h, "_global_n", [l.n for l in h.levels])),
                            "levels_nnz": [l.nnz_A for l in h.levels], "colors": [None if l.color_ptr is None else
                                                                               len(l.color_ptr) - 1 for l in h.levels],
-                           "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2), "nn_builder": NN_BUILD.get(n),
+                           "generate_s": round(t_gen, 2), "generated_on": "device" if on_device else "host",
+                           "setup_s": round(t_setup, 2), "nn_builder": NN_BUILD.get(n),
+                           "setup_phases_s": {k: round(v, 3) for k, v in (getattr(h, "setup_timing", None) or {}).items()},
                            "residual_after_timed_steps": res_after, "multi_rank_parity": parity,
                            "step": "V-cycle + residual norm of its result (one graph): steady-state outer iteration of "
                                    "Multigrid.solve; cycle fusion %s, implied columns %s"

@@ -99,6 +99,11 @@ typedef struct {
     const int32_t *d_slice_off; /* optional (NULL: none): [nslices][8] column offsets relative to the row
                                    for slices in which every row has the columns row + off[j]; filled by
                                    mg_sell_slice_offsets, used when mg_set_implied_columns(1) */
+    /* optional value dictionary (NULL: none; mg_value_dict_build on d_vals): d_vals[p] == d_val_table[d_val_idx[p]] for
+     * every stored entry p, at most 256 table entries.  Kernels on rows of at most 8 entries then stream one byte per
+     * entry instead of eight (mg_set_value_dict); the doubles are the same, so are the results. */
+    const unsigned char *d_val_idx;
+    const double *d_val_table;
 } mg_sell;
 
 /* Implied columns (default on; results identical): on a uniform matrix with <= 8 entries per row, slices whose
@@ -108,6 +113,16 @@ typedef struct {
  * beyond uniform_len zero; the table must be 32-byte aligned; irregular slices: d_off[s * 8] = INT32_MIN) and adds the number of regular slices to *d_nregular (device int64, zeroed by the
  * caller; may be NULL); point mg_sell.d_slice_off at the table when enough slices are regular. */
 int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, int64_t *d_nregular, void *stream);
+/* Value dictionary (csrc/valdict.cu): finite-element operators on uniform meshes and interpolation operators hold few
+ * DISTINCT values (5-point Laplacian: 4, -1, 1, 0; linear interpolation: 1, 0.5, 0).  mg_value_dict_build looks for at
+ * most 256 distinct bit patterns among d_vals[0..n): *h_count = how many (d_table[0..count) and d_index[0..n) are
+ * written), or -1 if there are more (nothing is written; found after a few thousand entries).  d_work:
+ * mg_value_dict_workspace() bytes.  Synchronises.  mg_set_value_dict(0) makes the kernels ignore dictionaries
+ * (default 1); returns the previous setting. */
+int64_t mg_value_dict_workspace(void);
+int mg_value_dict_build(int64_t n, const double *d_vals, unsigned char *d_index, double *d_table, void *d_work,
+                        int *h_count, void *stream);
+int mg_set_value_dict(int enabled);
 int mg_set_implied_columns(int enabled);
 /* launches of fewer rows keep loading their columns (one dependent load less on latency-bound launches); returns the
  * previous floor (default 2^19) */
@@ -200,6 +215,9 @@ typedef struct {
     double *d_f, *d_x;            /* work vectors, n_pad doubles each                                          */
     int64_t tail_na;              /* blocks left after the reductions (<= 1: a single block)                   */
     double *d_tail;               /* work vector, max(tail_na,1)*m doubles                                     */
+    const int32_t *d_perm;        /* optional (NULL: identity): the factors are those of P A P^T, row i of which is row
+                                     d_perm[i] of A (a bandwidth-reducing ordering); the solve gathers rhs and
+                                     scatters x accordingly                                                    */
 } mg_bcr;
 int mg_bcr_blocks_from_csr(int64_t n, int64_t n_pad, int64_t m, const int32_t *d_indptr, const int32_t *d_indices,
                            const double *d_values, double *d_D, double *d_L, double *d_U, int32_t *d_bad,

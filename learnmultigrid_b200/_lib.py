@@ -30,14 +30,15 @@ class MgError(RuntimeError):
 class mg_sell(ctypes.Structure):
     _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nslices", c_i64),
                 ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp), ("max_slice_len", c_i64),
-                ("uniform_len", c_i64), ("d_slice_off", c_vp)]
+                ("uniform_len", c_i64), ("d_slice_off", c_vp), ("d_val_idx", c_vp), ("d_val_table", c_vp)]
 
 
 class mg_bcr(ctypes.Structure):
     _fields_ = [("n", c_i64), ("n_pad", c_i64), ("m", c_i64), ("nb", c_i64),
                 ("nlevels", ctypes.c_int32), ("pad_", ctypes.c_int32),
                 ("d_GL", c_vp * 32), ("d_GU", c_vp * 32), ("d_Dinv", c_vp * 32), ("d_HL", c_vp * 32),
-                ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp), ("tail_na", c_i64), ("d_tail", c_vp)]
+                ("d_HU", c_vp * 32), ("na", c_i64 * 32), ("d_last_inv", c_vp), ("d_f", c_vp), ("d_x", c_vp), ("tail_na", c_i64), ("d_tail", c_vp),
+                ("d_perm", c_vp)]
 
 
 MG_MAX_RANKS = 8
@@ -118,6 +119,9 @@ _SIGNATURES = {
     "mg_sell_spmv": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
     "mg_sell_slice_offsets": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
     "mg_set_implied_min_rows": (c_i64, [c_i64]),
+    "mg_value_dict_workspace": (c_i64, []),
+    "mg_value_dict_build": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_vp]),
+    "mg_set_value_dict": (c_int, [c_int]),
     "mg_set_short_rows_per_thread": (c_int, [c_int]),
     "mg_set_short_min_rows": (c_i64, [c_i64]),
     "mg_level_inspect": (c_int, [ctypes.POINTER(mg_sell), c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -268,6 +272,8 @@ def load():
         lib.mg_set_implied_columns(0)
     if "MGB_IMPLIED_MIN_ROWS" in os.environ:
         lib.mg_set_implied_min_rows(int(os.environ["MGB_IMPLIED_MIN_ROWS"]))
+    if os.environ.get("MGB_VALUE_DICT", "1") == "0":
+        lib.mg_set_value_dict(0)
     if "MGB_SHORT_ROWS" in os.environ:
         lib.mg_set_short_rows_per_thread(int(os.environ["MGB_SHORT_ROWS"]))
     if os.environ.get("MGB_CYCLE_FUSION", "1") == "0":

@@ -38,7 +38,9 @@ class DenseCoarse:
 class BcrCoarse:
     kind = _lib.MG_COARSE_BCR
 
-    def __init__(self, torch, dev, n, ip, ix, va, half_bw, min_block=64, tail_blocks=16):
+    def __init__(self, torch, dev, n, ip, ix, va, half_bw, min_block=64, tail_blocks=16, perm=None):
+        """perm (optional, host int32 array): (ip, ix, va) is P A P^T for the caller's operator A, row i of it being row
+        perm[i] of A; right-hand sides are gathered and solutions scattered accordingly inside the solve."""
         lib = _lib.load()
         st = _lib.stream_handle(torch)
         f64 = torch.float64
@@ -139,6 +141,10 @@ class BcrCoarse:
         h.tail_na = self.tail_na
         self.tail = torch.zeros(max(self.tail_na, 1) * m, dtype=f64, device=dev)
         h.d_tail = self.tail.data_ptr()
+        self.perm = None
+        if perm is not None:
+            self.perm = torch.from_numpy(np.ascontiguousarray(perm, dtype=np.int32)).to(dev)
+            h.d_perm = self.perm.data_ptr()
         self.handle = h
         self.bytes = (sum((2 * ((lv["na"] + 1) // 2) + 3 * (lv["na"] // 2)) * mm * 8 for lv in self.levels)
                       + self.tail_na * self.tail_na * mm * 8)
@@ -203,14 +209,59 @@ class BcrCoarse:
                                             _lib.stream_handle(torch)), "mg_bcr_solve")
 
 
+BCR_MAX_FACTOR_BYTES = 24 << 30     # refuse factorisations beyond this (5 n m doubles)
+
+
+def rcm_ordering(indptr, indices, n):
+    """reverse Cuthill-McKee ordering of the symmetrised pattern (host, setup time): perm[i] = old row of new row i"""
+    import scipy.sparse as sp
+    from scipy.sparse.csgraph import reverse_cuthill_mckee
+    pat = sp.csr_matrix((np.ones(len(indices), dtype=np.int8), indices, indptr), shape=(n, n))
+    return np.asarray(reverse_cuthill_mckee(sp.csr_matrix(pat + pat.T), symmetric_mode=True), dtype=np.int32)
+
+
+def permuted_half_bandwidth(indptr, indices, perm):
+    n = len(indptr) - 1
+    iperm = np.empty(n, dtype=np.int64)
+    iperm[perm] = np.arange(n, dtype=np.int64)
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(indptr))
+    return int(np.abs(iperm[indices] - iperm[rows]).max()) if len(indices) else 0
+
+
 def build_coarse_solver(torch, dev, n, ip, ix, va, dense_max, host_pattern=None):
-    """pick dense inverse or BCR for the coarsest operator given as device CSR (ip, ix, va)"""
+    """Direct solver for an operator given as device CSR (ip, ix, va) -- the coarsest level of a hierarchy
+    (Multigrid.py:106) or the system of DirectSolver (Solver.py:56-59):
+      * n <= dense_max: explicit inverse;
+      * banded as it is numbered (structured grids in natural order): block cyclic reduction;
+      * anything else: reverse Cuthill-McKee first (unstructured meshes, shuffled numberings), then block cyclic
+        reduction on P A P^T with the permutation applied inside the solve."""
     if n <= dense_max:
         return DenseCoarse(torch, dev, n, ip, ix, va)
     if host_pattern is None:
         host_pattern = (ip.cpu().numpy(), ix.cpu().numpy())
-    bw = half_bandwidth(*host_pattern)
-    if (n + max(bw, 64) - 1) // max(bw, 64) < 4:
-        raise _lib.MgError("coarsest operator (%d unknowns, half bandwidth %d) is neither small enough for a dense "
-                           "inverse nor banded enough for block cyclic reduction; use more levels" % (n, bw))
-    return BcrCoarse(torch, dev, n, ip, ix, va, bw)
+    hp, hx = host_pattern
+    bw = half_bandwidth(hp, hx)
+
+    def fits(b):
+        m = max(b, 64)
+        return (n + m - 1) // m >= 4 and 5 * n * m * 8 <= BCR_MAX_FACTOR_BYTES
+    # a structured grid in natural order has half bandwidth ~ sqrt(n): keep it (no permutation in the solve)
+    if fits(bw) and bw * bw <= 4 * n:
+        return BcrCoarse(torch, dev, n, ip, ix, va, bw)
+    perm = rcm_ordering(hp, hx, n)
+    bw_p = permuted_half_bandwidth(hp, hx, perm)
+    if bw_p >= bw and fits(bw):
+        return BcrCoarse(torch, dev, n, ip, ix, va, bw)
+    if not fits(bw_p):
+        raise _lib.MgError("direct solve: %d unknowns with half bandwidth %d (%d after reverse Cuthill-McKee) are neither "
+                           "small enough for a dense inverse nor banded enough for block cyclic reduction"
+                           % (n, bw, bw_p))
+    # P A P^T on the device: rows gathered by perm, columns relabelled by its inverse (entry order inside a row is
+    # irrelevant to the block extraction)
+    from .setup_device import DevCSR, DeviceSetup
+    S = DeviceSetup(torch, dev)
+    dperm = torch.from_numpy(perm).to(dev)
+    iperm = S.empty(n, torch.int32)
+    _lib.check(S.lib.mg_invert_permutation(n, dperm.data_ptr(), iperm.data_ptr(), S.st()), "mg_invert_permutation")
+    Ap = S.permute(DevCSR((n, n), ip, ix, va), dperm, iperm)
+    return BcrCoarse(torch, dev, n, Ap.indptr, Ap.indices, Ap.values, bw_p, perm=perm)

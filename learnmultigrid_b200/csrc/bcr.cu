@@ -23,6 +23,7 @@ struct BcrHandle {            // mirrors mg_bcr in include/mgb200.h
     double *f, *x;
     int64_t tail_na;          // blocks left after the reductions (0/1: one block); last_inv is (tail_na*m)^2
     double *tail;             // tail_na*m doubles: contiguous right-hand side of the tail system
+    const int32_t *perm;      // optional: the factors belong to the rows / columns perm[0..n) of the caller's operator
 };
 
 // ---- setup kernels -------------------------------------------------------------------------------------------
@@ -178,10 +179,11 @@ __device__ __forceinline__ double warp_row_dot(const double *__restrict__ row, c
 }
 
 __global__ void __launch_bounds__(kBlock)
-bcr_load_kernel(int64_t n, int64_t n_pad, const double *__restrict__ b, double *__restrict__ f) {
+bcr_load_kernel(int64_t n, int64_t n_pad, const double *__restrict__ b, const int32_t *__restrict__ perm,
+                double *__restrict__ f) {
     pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i < n_pad) f[i] = (i < n) ? b[i] : 0.0;
+    if (i < n_pad) f[i] = (i < n) ? b[perm ? perm[i] : i] : 0.0;
 }
 
 // level s forward: kept blocks j in [j0, j0+nk) (position p = 2j, original block p << s)
@@ -285,10 +287,10 @@ bcr_backward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nodd, const do
 }
 
 __global__ void __launch_bounds__(kBlock)
-bcr_store_kernel(int64_t n, const double *__restrict__ x, double *__restrict__ out) {
+bcr_store_kernel(int64_t n, const double *__restrict__ x, const int32_t *__restrict__ perm, double *__restrict__ out) {
     pdl_prologue();
     const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
-    if (i < n) out[i] = x[i];
+    if (i < n) out[perm ? perm[i] : i] = x[i];
 }
 
 static inline unsigned warps_grid(int64_t nwarps) { return (unsigned)((nwarps * 32 + kBlock - 1) / kBlock); }
@@ -309,7 +311,7 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
     if (!H || H->m <= 0 || H->nlevels < 0 || H->nlevels > 32) return set_error(MG_ERR_INVALID, "bcr_solve", "bad handle");
     if (dist && !comm) dist = nullptr;
     const int m = (int)H->m;
-    launch_k(bcr_load_kernel, (unsigned)((unsigned)((H->n_pad + kBlock - 1) / kBlock)), (unsigned)kBlock, st, H->n, H->n_pad, rhs, H->f);
+    launch_k(bcr_load_kernel, (unsigned)((unsigned)((H->n_pad + kBlock - 1) / kBlock)), (unsigned)kBlock, st, H->n, H->n_pad, rhs, H->perm, H->f);
     MG_CHECK_LAUNCH("bcr_load");
     for (int s = 0; s < H->nlevels; ++s) {
         const int64_t na = H->na[s], nk = (na + 1) / 2;
@@ -389,7 +391,7 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
             if (rc) return rc;
         }
     }
-    launch_k(bcr_store_kernel, (unsigned)((unsigned)((H->n + kBlock - 1) / kBlock)), (unsigned)kBlock, st, H->n, H->x, x);
+    launch_k(bcr_store_kernel, (unsigned)((unsigned)((H->n + kBlock - 1) / kBlock)), (unsigned)kBlock, st, H->n, H->x, H->perm, x);
     MG_CHECK_LAUNCH("bcr_store");
     return MG_OK;
 }

@@ -50,6 +50,7 @@ __device__ __forceinline__ double mul_add_unfused(double acc, double a, double b
 // streaming (read-once) loads of the matrix arrays: do not pollute L1, which we want for the x gathers
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
+__device__ __forceinline__ unsigned char ld_stream(const unsigned char *p) { return __ldcs(p); }
 
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
 // The V-cycle is a long chain of short dependent kernels (60-150 per cycle, many of a few microseconds on the coarse

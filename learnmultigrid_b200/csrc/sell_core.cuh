@@ -18,7 +18,9 @@ struct SellArgs {
     const int64_t *__restrict__ slice_ptr;
     const int32_t *__restrict__ cols;
     const double *__restrict__ vals;
-    const int32_t *__restrict__ slice_off;   // implied columns (IMPL kernels): [nslices][LEN] offsets, see below
+    const int32_t *__restrict__ slice_off;   // implied columns (IMPL kernels): [nslices][8] offsets, see below
+    const unsigned char *__restrict__ vidx;  // value dictionary (VAL8 kernels): one byte per entry, laid out like vals
+    const double *__restrict__ vtab;         // ... indexing this table of at most 256 doubles
     int64_t row_begin;   // first row this launch touches
     int64_t row_end;     // one past the last row
     int64_t first_row;   // row of thread 0 of block 0 (row_begin rounded down to a slice)
@@ -68,18 +70,35 @@ struct RowOut {
     bool store;
 };
 
-template <int MODE, int LEN, bool PRED, bool IMPL>
-__device__ __forceinline__ void short_row(const SellArgs &A, const int32_t *__restrict__ c, const double *__restrict__ v,
-                                          const int32_t *oo, int len, const double *x, int64_t row,
-                                          bool active, const SellEp &E, double &contrib, unsigned char halo_wait,
-                                          const ExArgs *fx, RowOut &out) {
+// VAL8: the values come from the matrix' dictionary (valdict.cu): one byte per entry from DRAM, the double from a
+// 2 KB table that stays in L1 -- the same doubles, 7 bytes per entry less.
+template <int MODE, int LEN, bool PRED, bool IMPL, bool VAL8>
+__device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, const int32_t *oo, int len, const double *x,
+                                          int64_t row, bool active, const SellEp &E, double &contrib,
+                                          unsigned char halo_wait, const ExArgs *fx, RowOut &out) {
+    const int32_t *__restrict__ c = A.cols + ent;
+    const double *__restrict__ v = A.vals + ent;
+    const unsigned char *__restrict__ vi = A.vidx + ent;
     int32_t cc[LEN];
     double vv[LEN], xx[LEN];
+    if (VAL8) {
+        unsigned char ii[LEN];
 #pragma unroll
-    for (int j = 0; j < LEN; ++j) {
-        if (!PRED || j < len) {
-            vv[j] = ld_stream(v + j * kSlice);
-            if (!IMPL) cc[j] = ld_stream(c + j * kSlice);
+        for (int j = 0; j < LEN; ++j)
+            if (!PRED || j < len) ii[j] = ld_stream(vi + j * kSlice);
+#pragma unroll
+        for (int j = 0; j < LEN; ++j)
+            if (!PRED || j < len) {
+                if (!IMPL) cc[j] = ld_stream(c + j * kSlice);
+                vv[j] = __ldg(A.vtab + ii[j]);
+            }
+    } else {
+#pragma unroll
+        for (int j = 0; j < LEN; ++j) {
+            if (!PRED || j < len) {
+                vv[j] = ld_stream(v + j * kSlice);
+                if (!IMPL) cc[j] = ld_stream(c + j * kSlice);
+            }
         }
     }
     if (IMPL) {
@@ -199,12 +218,13 @@ __device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const d
 // The microbenchmark behind these choices is tools/sellbench.cu (profiles/r01_sellbench.log): occupancy x bytes in
 // flight per thread decides; at 32 registers and 60 B per thread the fine-level sweep reaches the DRAM limit
 // (6.8 TB/s algorithmic, ~7.1 TB/s of actual traffic), a rolled loop stays at 5.4 TB/s.
-template <int MODE, int LEN, bool UNIFORM, bool FUSED, bool IMPL>
+template <int MODE, int LEN, bool UNIFORM, bool FUSED, bool IMPL, bool VAL8>
 __device__ __forceinline__ void
 sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
           double *__restrict__ partials, int64_t bid, const ExArgs *fx, const unsigned char *__restrict__ mask) {
     static_assert(!IMPL || (UNIFORM && LEN > 0), "implied columns need a uniform matrix with short rows");
     static_assert(LEN > 0 || !mode_is_tail(MODE), "fused residual modes need the row in registers");
+    static_assert(!VAL8 || LEN > 0, "the value dictionary is for short rows");
     const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
     const bool active = row >= A.row_begin && row < A.row_end;
     double contrib = 0.0;
@@ -235,12 +255,12 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
                 int4 ob = make_int4(0, 0, 0, 0);
                 if (L > 4) ob = __ldg(o + 1);
                 const int32_t oo[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
-                if (oa.x != kSliceIrregular) short_row<MODE, L, false, true>(A, c, v, oo, L, x, row, active, E, contrib, hw, fx, out);
-                else short_row<MODE, L, false, false>(A, c, v, nullptr, L, x, row, active, E, contrib, hw, fx, out);
+                if (oa.x != kSliceIrregular) short_row<MODE, L, false, true, VAL8>(A, base + lane, oo, L, x, row, active, E, contrib, hw, fx, out);
+                else short_row<MODE, L, false, false, VAL8>(A, base + lane, nullptr, L, x, row, active, E, contrib, hw, fx, out);
             } else if (UNIFORM || len == L) {
-                short_row<MODE, L, false, false>(A, c, v, nullptr, L, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, false, false, VAL8>(A, base + lane, nullptr, L, x, row, active, E, contrib, hw, fx, out);
             } else {
-                short_row<MODE, L, true, false>(A, c, v, nullptr, len, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, true, false, VAL8>(A, base + lane, nullptr, len, x, row, active, E, contrib, hw, fx, out);
             }
         } else {
             double sum = 0.0, diag = 0.0;
@@ -291,19 +311,19 @@ __host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform) {
     return (len >= 1 && uniform && len <= (m == GS ? 5 : 7)) ? 8 : 1;
 }
 
-template <int MODE, int LEN, bool UNIFORM, bool IMPL>
+template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8>
 __global__ void __launch_bounds__(kBlock, mode_min_ctas(MODE, LEN, UNIFORM))
 sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
             double *y, double omega, double *__restrict__ partials) {
     pdl_prologue();
-    sell_body<MODE, LEN, UNIFORM, false, IMPL>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
+    sell_body<MODE, LEN, UNIFORM, false, IMPL, VAL8>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
 }
 
 // Very short rows (linear transfer operators: one or two entries): one row per thread keeps only ~30 bytes per thread in
 // flight behind a chain of three dependent loads (slice pointer -> column -> vector entry), and the prolongation runs at
 // 5.4 instead of 6.8 TB/s (ncu, profiles/r02_ncu_step_sell_kernels.txt).  Here a thread takes R rows, 256 apart, and
 // issues every load of a stage for all of them before the first use.  SpMV and prolongation, LEN <= 2, no exchange site.
-template <int MODE, int LEN, int R>
+template <int MODE, int LEN, int R, bool VAL8>
 __global__ void __launch_bounds__(kBlock)
 sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
     static_assert(MODE == SPMV || MODE == PROLONG, "short-row kernel: SpMV and prolongation only");
@@ -326,15 +346,24 @@ sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
     }
     int32_t cc[R][LEN];
     double vv[R][LEN], xx[R][LEN], av[R];
+    unsigned char ii[R][LEN];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
 #pragma unroll
         for (int j = 0; j < LEN; ++j)
             if (j < len[r]) {
                 cc[r][j] = ld_stream(A.cols + base[r] + j * kSlice);
-                vv[r][j] = ld_stream(A.vals + base[r] + j * kSlice);
+                if (VAL8) ii[r][j] = ld_stream(A.vidx + base[r] + j * kSlice);
+                else vv[r][j] = ld_stream(A.vals + base[r] + j * kSlice);
             }
         av[r] = (MODE == PROLONG && act[r]) ? aux[row[r]] : 0.0;
+    }
+    if (VAL8) {
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+            for (int j = 0; j < LEN; ++j)
+                if (j < len[r]) vv[r][j] = __ldg(A.vtab + ii[r][j]);
     }
 #pragma unroll
     for (int r = 0; r < R; ++r)
@@ -355,7 +384,7 @@ sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
 // boundary values the previous kernel produced, poll for the peers' packets and unpack them into the halo of x; the
 // compute CTAs whose slice reads halo columns (mask) wait for that, all others start at once.  The exchange latency
 // (NVLink flight + polling) is hidden behind the interior rows, and the site costs no launch of its own.
-template <int MODE, int LEN, bool UNIFORM, bool IMPL>
+template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8>
 __global__ void __launch_bounds__(kBlock)
 sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
                   double *__restrict__ partials, const ExArgs fx, const unsigned char *__restrict__ mask) {
@@ -366,7 +395,7 @@ sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, con
         if (mode_has_partials(MODE)) {}      // exchange CTAs own no partial sum
         return;
     }
-    sell_body<MODE, LEN, UNIFORM, true, IMPL>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
+    sell_body<MODE, LEN, UNIFORM, true, IMPL, VAL8>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
 }
 
 // Colour sweep of a partitioned level that PUSHES its own boundary values (producer-driven exchange, exchange.cuh):
@@ -374,7 +403,7 @@ sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, con
 // colour's send table stores its new value straight into the peer's staging slot, and the NVLink flight overlaps the
 // interior rows of this very kernel.  CARRY: the launch also carries the previous site as extra CTAs, exactly like
 // sell_kernel_fused.  Same values, same packets, same receiving code (mg_set_push_exchange).
-template <int MODE, int LEN, bool UNIFORM, bool CARRY, bool IMPL>
+template <int MODE, int LEN, bool UNIFORM, bool CARRY, bool IMPL, bool VAL8>
 __global__ void __launch_bounds__(kBlock)
 sell_gs_push_kernel(SellArgs A, double *x, const double *__restrict__ b, double *__restrict__ partials, const ExArgs fx,
                     const unsigned char *__restrict__ mask, const SellPush push) {
@@ -388,7 +417,7 @@ sell_gs_push_kernel(SellArgs A, double *x, const double *__restrict__ b, double 
     const int64_t nb = (int64_t)gridDim.x - nex;
     int64_t bid = (int64_t)blockIdx.x - nex;
     bid = bid < push.tail_first ? nb - 1 - bid : bid - push.tail_first;
-    sell_body<MODE, LEN, UNIFORM, CARRY, IMPL>(A, x, b, nullptr, x, 0.0, partials, bid, &fx, mask);
+    sell_body<MODE, LEN, UNIFORM, CARRY, IMPL, VAL8>(A, x, b, nullptr, x, 0.0, partials, bid, &fx, mask);
     const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
     if (row >= A.row_begin && row < A.row_end && !push.ex.dry && push.mask[row >> 5]) push_row_if_listed(push, row, x);
 }
@@ -521,6 +550,7 @@ extern int64_t g_wide_max_rows;     // ... for launches of at most this many row
 extern int64_t g_tma_min_rows;      // rows per launch from which the bulk-async staged kernel is used; 0 disables it
 extern int g_implied_columns;       // use the offset tables of matrices that carry one
 extern int64_t g_implied_min_rows;  // ... for launches of at least this many rows
+extern int g_value_dict;            // use the value dictionaries of matrices that carry one
 extern int g_short_rows_per_thread; // rows per thread of sell_short_kernel (1 = off, 2 or 4)
 extern int64_t g_short_min_rows;    // ... for launches of at least this many rows
 
@@ -544,12 +574,18 @@ inline SellArgs sell_args(const mg_sell *A, int64_t row0, int64_t row1, double *
     a.cols = A->d_cols;
     a.vals = A->d_vals;
     a.slice_off = A->d_slice_off;
+    a.vidx = A->d_val_idx;
+    a.vtab = A->d_val_table;
     a.row_begin = row0;
     a.row_end = row1;
     a.first_row = row0 & ~(int64_t)(kSlice - 1);
     a.nrows = A->nrows;
     a.r_out = r_out;
     return a;
+}
+inline bool sell_use_dict(const mg_sell *A) {
+    const int64_t ml = A->max_slice_len;
+    return g_value_dict && A->d_val_idx && A->d_val_table && ml >= 1 && ml <= 8;
 }
 inline bool sell_use_implied(const mg_sell *A, int64_t row0, int64_t row1) {
     const int64_t ml = A->max_slice_len;
@@ -600,38 +636,52 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
         if (!fuse && ml >= 1 && ml <= 2 && g_short_rows_per_thread > 1 && row1 - row0 >= g_short_min_rows && A->d_slice_ptr) {
             const int R = g_short_rows_per_thread >= 4 ? 4 : 2;
             const unsigned sg = (unsigned)((grid + R - 1) / R);
+            const bool dict = sell_use_dict(A);
+#define MG_SHORT(L, RR)                                                                          \
+    do {                                                                                         \
+        if (dict) launch_k(sell_short_kernel<MODE, L, RR, true>, sg, kBlock, st, a, x, aux, y);  \
+        else launch_k(sell_short_kernel<MODE, L, RR, false>, sg, kBlock, st, a, x, aux, y);      \
+    } while (0)
             if (ml == 1) {
-                if (R == 4) launch_k(sell_short_kernel<MODE, 1, 4>, sg, kBlock, st, a, x, aux, y);
-                else launch_k(sell_short_kernel<MODE, 1, 2>, sg, kBlock, st, a, x, aux, y);
+                if (R == 4) MG_SHORT(1, 4);
+                else MG_SHORT(1, 2);
             } else {
-                if (R == 4) launch_k(sell_short_kernel<MODE, 2, 4>, sg, kBlock, st, a, x, aux, y);
-                else launch_k(sell_short_kernel<MODE, 2, 2>, sg, kBlock, st, a, x, aux, y);
+                if (R == 4) MG_SHORT(2, 4);
+                else MG_SHORT(2, 2);
             }
+#undef MG_SHORT
             MG_CHECK_LAUNCH(name);
             if (nblocks_out) *nblocks_out = (int)sg;
             return MG_OK;
         }
     }
     const bool impl = sell_use_implied(A, row0, row1);
-#define MG_SELL_LAUNCH(L, U, I)                                                                                          \
+    const bool dict = sell_use_dict(A);
+#define MG_SELL_LAUNCH(L, U, I, V)                                                                                       \
     do {                                                                                                                 \
-        if (fuse) launch_k(sell_kernel_fused<MODE, L, U, I>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
-        else launch_k(sell_kernel<MODE, L, U, I>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);         \
+        if (fuse) launch_k(sell_kernel_fused<MODE, L, U, I, V>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
+        else launch_k(sell_kernel<MODE, L, U, I, V>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);      \
+    } while (0)
+#define MG_SELL_VARIANT(L, V)                             \
+    do {                                                  \
+        if (impl) MG_SELL_LAUNCH(L, true, true, V);       \
+        else if (uni) MG_SELL_LAUNCH(L, true, false, V);  \
+        else MG_SELL_LAUNCH(L, false, false, V);          \
     } while (0)
 #define MG_SELL_CASE(L)                                   \
     case L:                                               \
-        if (impl) MG_SELL_LAUNCH(L, true, true);          \
-        else if (uni) MG_SELL_LAUNCH(L, true, false);     \
-        else MG_SELL_LAUNCH(L, false, false);             \
+        if (dict) MG_SELL_VARIANT(L, true);               \
+        else MG_SELL_VARIANT(L, false);                   \
         break
     switch (ml) {
         MG_SELL_CASE(1); MG_SELL_CASE(2); MG_SELL_CASE(3); MG_SELL_CASE(4);
         MG_SELL_CASE(5); MG_SELL_CASE(6); MG_SELL_CASE(7); MG_SELL_CASE(8);
         default:   // long rows, or length unknown (0)
-            if constexpr (!mode_is_tail(MODE)) MG_SELL_LAUNCH(0, false, false);
+            if constexpr (!mode_is_tail(MODE)) MG_SELL_LAUNCH(0, false, false, false);
             else return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
     }
 #undef MG_SELL_CASE
+#undef MG_SELL_VARIANT
 #undef MG_SELL_LAUNCH
     MG_CHECK_LAUNCH(name);
     if (nblocks_out) *nblocks_out = (int)grid;
@@ -650,6 +700,7 @@ static int launch_sell_push(const mg_sell *A, double *x, const double *b, int64_
     const int64_t ml = A->max_slice_len;
     const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
     const bool impl = sell_use_implied(A, row0, row1);
+    const bool dict = sell_use_dict(A);
     const int64_t grid = (row1 - a.first_row + kBlock - 1) / kBlock;
     const int nex = carry ? carry->nex : 0;
     if (grid + nex > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
@@ -659,25 +710,31 @@ static int launch_sell_push(const mg_sell *A, double *x, const double *b, int64_
     memset(&none, 0, sizeof(none));
     const ExArgs &fx = carry ? carry->ex : none;
     const unsigned char *mask = carry ? carry->mask : nullptr;
-#define MG_PUSH_LAUNCH(L, U, I)                                                                                          \
+#define MG_PUSH_LAUNCH(L, U, I, V)                                                                                       \
     do {                                                                                                                 \
-        if (carry) launch_k(sell_gs_push_kernel<MODE, L, U, true, I>, (unsigned)(grid + nex), kBlock, st, a, x, b, partials, fx, mask, p); \
-        else launch_k(sell_gs_push_kernel<MODE, L, U, false, I>, (unsigned)grid, kBlock, st, a, x, b, partials, fx, mask, p);              \
+        if (carry) launch_k(sell_gs_push_kernel<MODE, L, U, true, I, V>, (unsigned)(grid + nex), kBlock, st, a, x, b, partials, fx, mask, p); \
+        else launch_k(sell_gs_push_kernel<MODE, L, U, false, I, V>, (unsigned)grid, kBlock, st, a, x, b, partials, fx, mask, p);              \
+    } while (0)
+#define MG_PUSH_VARIANT(L, V)                             \
+    do {                                                  \
+        if (impl) MG_PUSH_LAUNCH(L, true, true, V);       \
+        else if (uni) MG_PUSH_LAUNCH(L, true, false, V);  \
+        else MG_PUSH_LAUNCH(L, false, false, V);          \
     } while (0)
 #define MG_PUSH_CASE(L)                                   \
     case L:                                               \
-        if (impl) MG_PUSH_LAUNCH(L, true, true);          \
-        else if (uni) MG_PUSH_LAUNCH(L, true, false);     \
-        else MG_PUSH_LAUNCH(L, false, false);             \
+        if (dict) MG_PUSH_VARIANT(L, true);               \
+        else MG_PUSH_VARIANT(L, false);                   \
         break
     switch (ml) {
         MG_PUSH_CASE(1); MG_PUSH_CASE(2); MG_PUSH_CASE(3); MG_PUSH_CASE(4);
         MG_PUSH_CASE(5); MG_PUSH_CASE(6); MG_PUSH_CASE(7); MG_PUSH_CASE(8);
         default:
-            if constexpr (MODE == GS) MG_PUSH_LAUNCH(0, false, false);
+            if constexpr (MODE == GS) MG_PUSH_LAUNCH(0, false, false, false);
             else return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
     }
 #undef MG_PUSH_CASE
+#undef MG_PUSH_VARIANT
 #undef MG_PUSH_LAUNCH
     MG_CHECK_LAUNCH(name);
     if (nblocks_out) *nblocks_out = (int)grid;

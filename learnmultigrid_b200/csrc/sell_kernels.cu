@@ -15,6 +15,7 @@ int64_t g_tma_min_rows = 0;          // off by default: the register-staged kern
 // rows 11.8 -> 9.9 us, but 263 k rows 3.5 -> 4.8 us (one more dependent load in a latency-bound launch): hence the floor.
 int g_implied_columns = 1;
 int64_t g_implied_min_rows = 1 << 19;
+int g_value_dict = 1;                // value dictionaries (valdict.cu) are used where a matrix carries one
 // rows of one or two entries (linear transfers): R rows per thread on large launches (sell_short_kernel)
 int g_short_rows_per_thread = 2;
 int64_t g_short_min_rows = 1 << 18;
@@ -126,14 +127,6 @@ bool sell_gs_tail_ok(const mg_sell *A, int64_t row0, int64_t row1) {
 int sell_spmv(const mg_sell *A, const double *x, double *y, int64_t row0, int64_t row1, const SellFuse *fuse, cudaStream_t st) {
     return launch_sell<SPMV>(A, x, nullptr, nullptr, y, 0.0, nullptr, row0, row1, st, "sell_spmv", nullptr, fuse);
 }
-int sell_residual(const mg_sell *A, const double *x, const double *b, double *r, int64_t row0, int64_t row1,
-                  const SellFuse *fuse, cudaStream_t st) {
-    return launch_sell<RESID>(A, x, b, nullptr, r, 0.0, nullptr, row0, row1, st, "sell_residual", nullptr, fuse);
-}
-int sell_residual_partials(const mg_sell *A, const double *x, const double *b, double *partials, int64_t row0,
-                           int64_t row1, int *nblocks, const SellFuse *fuse, cudaStream_t st) {
-    return launch_sell<RESNORM>(A, x, b, nullptr, nullptr, 0.0, partials, row0, row1, st, "sell_residual_partials", nblocks, fuse);
-}
 int sell_reduce_partials(const double *partials, int64_t n, double *out, cudaStream_t st) {
     launch_k(reduce_partials_kernel, 1u, 1024u, st, partials, n, out);
     MG_CHECK_LAUNCH("reduce_partials");
@@ -229,6 +222,11 @@ int mg_set_implied_columns(int enabled) {
 int64_t mg_set_implied_min_rows(int64_t rows) {
     const int64_t prev = g_implied_min_rows;
     g_implied_min_rows = rows < 0 ? 0 : rows;
+    return prev;
+}
+int mg_set_value_dict(int enabled) {
+    const int prev = g_value_dict;
+    g_value_dict = enabled ? 1 : 0;
     return prev;
 }
 int mg_set_short_rows_per_thread(int r) {

@@ -43,6 +43,35 @@ class DeviceSell:
                                    self.slice_ptr.data_ptr(), self.cols.data_ptr(), self.vals.data_ptr(),
                                    self.max_len, self.uniform_len)
         self._attach_slice_offsets()
+        self._attach_value_dict()
+
+    VALUE_DICT_MIN_ROWS = 1 << 16      # smaller matrices are latency-bound launches: a dictionary buys nothing there
+
+    def _attach_value_dict(self):
+        """Value dictionary (csrc/valdict.cu): if the matrix holds at most 256 distinct values and its rows have at
+        most 8 entries, keep one byte per entry next to the values; the streaming kernels then read that byte and look
+        the double up in a 2 KB table.  MGB_VALUE_DICT=0 switches it off."""
+        self.val_idx = self.val_table = None
+        self.distinct_values = None
+        floor = int(os.environ.get("MGB_VALUE_DICT_MIN_ROWS", self.VALUE_DICT_MIN_ROWS))
+        if (os.environ.get("MGB_VALUE_DICT", "1") == "0" or not 1 <= self.max_len <= 8 or self.shape[0] < floor
+                or self.vals.numel() == 0):
+            return
+        import torch
+        lib = _lib.load()
+        dev = self.vals.device
+        idx = torch.empty(self.vals.numel(), dtype=torch.uint8, device=dev)
+        table = torch.zeros(256, dtype=torch.float64, device=dev)
+        work = torch.empty(int(lib.mg_value_dict_workspace()), dtype=torch.uint8, device=dev)
+        cnt = ctypes.c_int(0)
+        _lib.check(lib.mg_value_dict_build(self.vals.numel(), self.vals.data_ptr(), idx.data_ptr(), table.data_ptr(),
+                                           work.data_ptr(), ctypes.byref(cnt), _lib.stream_handle(torch)),
+                   "mg_value_dict_build")
+        if cnt.value > 0:
+            self.distinct_values = int(cnt.value)
+            self.val_idx, self.val_table = idx, table
+            self.struct.d_val_idx = idx.data_ptr()
+            self.struct.d_val_table = table.data_ptr()
 
     IMPLIED_MIN_ROWS = 1 << 19      # the kernels' floor (mg_set_implied_min_rows): smaller matrices never use a table
 
@@ -81,6 +110,7 @@ class DeviceSell:
                                    slice_ptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), self.max_len,
                                    self.uniform_len)
         self._attach_slice_offsets()
+        self._attach_value_dict()
         return self
 
     def bytes(self):
@@ -90,11 +120,12 @@ class DeviceSell:
         """bytes one pass over the matrix actually reads: values, and columns or -- for regular slices of a matrix with
         implied columns (large launches) -- 4 bytes of offset per slice and entry index"""
         nsl = (self.shape[0] + 31) // 32
+        vbytes = 1 if (self.val_idx is not None and os.environ.get("MGB_VALUE_DICT", "1") != "0") else 8
         if self.slice_off is None or self.shape[0] < self.IMPLIED_MIN_ROWS or nsl == 0:
-            return self.padded * 12 + (0 if self.uniform_len else self.slice_ptr.numel() * 8)
+            return self.padded * (4 + vbytes) + (0 if self.uniform_len else self.slice_ptr.numel() * 8)
         per_slice = 32 * self.uniform_len
         irregular = nsl - self.regular_slices
-        return self.padded * 8 + irregular * per_slice * 4 + nsl * 32
+        return self.padded * vbytes + irregular * per_slice * 4 + nsl * 32
 
 
 class Level:
@@ -203,7 +234,12 @@ class DeviceHierarchy:
             lev.b = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.r = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.tmp = torch.zeros(n, dtype=torch.float64, device=dev)
+        import time
+        t0 = time.perf_counter()
         self._inspect_levels()
+        torch.cuda.synchronize()
+        if getattr(self, "setup_timing", None) is not None:
+            self.setup_timing["inspect (diagonal, colouring flags)"] = time.perf_counter() - t0
         n0 = self.levels[0].n
         self.n = n0
         self._stage = torch.zeros(n0, dtype=torch.float64, device=dev)       # natural-order staging

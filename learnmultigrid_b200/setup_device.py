@@ -259,7 +259,7 @@ class DeviceSetup:
         return perm, iperm, cptr
 
 
-def build_natural(S, A, Q_list):
+def build_natural(S, A, Q_list, tm=None):
     """Upload A and the transfer operators and form the Galerkin hierarchy in natural ordering on the device.
     Returns (A_host0, A_nat, Q_nat, QT_nat)."""
     L = len(Q_list) + 1
@@ -268,16 +268,24 @@ def build_natural(S, A, Q_list):
         A_nat = [A]
     else:
         A_host0 = F.solver_csr(A)                          # Solver.py:18 stores csc_matrix(matrix)
+        if tm:
+            tm.mark("host format conversion")
         A_nat = [S.upload(A_host0)]
     Q_nat, QT_nat = [], []
     for l in range(L - 1):
         Q = Q_list[l] if isinstance(Q_list[l], DevCSR) else S.upload(Q_list[l])
         if Q.shape[0] != A_nat[l].shape[0]:
             raise ValueError("Q_%d has %d rows, level operator has %d" % (l, Q.shape[0], A_nat[l].shape[0]))
+        if tm:
+            tm.mark("upload")
         QT = S.transpose(Q)
         Q_nat.append(Q)
         QT_nat.append(QT)
+        if tm:
+            tm.mark("transpose Q")
         A_nat.append(S.galerkin(A_nat[l], Q, QT))
+        if tm:
+            tm.mark("Galerkin SpGEMM")
     return A_host0, A_nat, Q_nat, QT_nat
 
 
@@ -340,15 +348,33 @@ def build_replicated_level(h, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, ipe
     return lev
 
 
+class PhaseTimer:
+    """wall-clock seconds per setup phase (the device is synchronised at every mark: setup only)"""
+
+    def __init__(self, torch):
+        import time
+        self.torch, self.time = torch, time
+        self.t = time.perf_counter()
+        self.phases = {}
+
+    def mark(self, name):
+        self.torch.cuda.synchronize()
+        now = self.time.perf_counter()
+        self.phases[name] = self.phases.get(name, 0.0) + (now - self.t)
+        self.t = now
+
+
 def setup_device(h, A, Q_list, colors, dense_coarse_max):
     """Populate `h.levels` of a DeviceHierarchy with device-built data (same contents as the host path)."""
     torch, dev = h.torch, h.device
     S = DeviceSetup(torch, dev)
     h._setup = S
     L = h.nlevels
-    A_host0, A_nat, Q_nat, QT_nat = build_natural(S, A, Q_list)
+    tm = PhaseTimer(torch)
+    A_host0, A_nat, Q_nat, QT_nat = build_natural(S, A, Q_list, tm)
     # orderings
     h.colors = level_colors(S, h.smoother, colors, A_host0, A_nat)
+    tm.mark("colouring")
     perms, iperms, cptrs = [], [], []
     for l in range(L):
         if h.colors[l] is not None:
@@ -358,8 +384,13 @@ def setup_device(h, A, Q_list, colors, dense_coarse_max):
         perms.append(p)
         iperms.append(ip)
         cptrs.append(cp)
-    h.levels = [build_replicated_level(h, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, iperms, cptrs,
-                                       dense_coarse_max) for l in range(L)]
+    tm.mark("colour permutations")
+    h.levels = []
+    for l in range(L):
+        h.levels.append(build_replicated_level(h, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, iperms, cptrs,
+                                               dense_coarse_max))
+        tm.mark("coarsest factorisation" if l == L - 1 else "permute + SELL build")
+    h.setup_timing = tm.phases
     h.host_A = None
     h.host_Q = None
     if h.keep_host:

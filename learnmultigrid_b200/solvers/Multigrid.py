@@ -163,7 +163,7 @@ class Multigrid(IterativeSolver):
         n = self.matrix.shape[0]
         for l in range(levels - 1):
             if l < len(given):
-                q = F.canonical_csr(given[l])
+                q = given[l] if hasattr(given[l], "ptrs") else F.canonical_csr(given[l])      # DevCSR: already on the device
             else:
                 q = F.geometric_interpolator_csr(n)
             if q.shape[0] != n:
@@ -200,6 +200,12 @@ class Multigrid(IterativeSolver):
             qs = self._transfer_list(levels, first_call)
         finally:
             self.matrix = save
+        # the hierarchy re-derives CSR from what the Solver holds (csc_matrix(matrix), Solver.py:18); when the caller's
+        # own object is canonical CSR that round trip is the identity and is skipped (seconds at 10^8 entries)
+        src = getattr(self, "_matrix_src", None)
+        if (A is save and src is not None and sp.isspmatrix_csr(src) and src.dtype == np.float64
+                and src.has_canonical_format):
+            A = src
         if self.fabric is not None and self.fabric.world > 1:
             from ..distributed import DistributedHierarchy
             return DistributedHierarchy(A, qs, self.fabric, smoother=kind, colors=colors, **self.dist_options)

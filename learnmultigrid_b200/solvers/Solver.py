@@ -21,7 +21,9 @@ class Solver:
         self.residual_vector = np.empty(shape=shape)
         self.residual = 0.0
         self._matrix_src = matrix            # the caller's object: lets two solvers recognise the same operator
-        self.matrix = csc_matrix(matrix)
+        # an operator that already lives in device memory (setup_device.DevCSR from assembly_device / problems_device)
+        # stays there; anything else is held as the reference holds it
+        self.matrix = matrix if hasattr(matrix, "ptrs") else csc_matrix(matrix)
         self.rhs = rhs
         self.solution = np.empty(shape=shape)
         self.track_res = np.ndarray(shape=(0, 1), dtype=float)
@@ -92,31 +94,55 @@ for _name, _attribute in (("get_matrix", "matrix"), ("get_rhs", "rhs"), ("get_so
 
 
 class DirectSolver(Solver):
-    """spsolve replacement (Solver.py:51-59): dense inverse on the device (n <= 4096)."""
+    """spsolve replacement (Solver.py:51-59) on the device, for any sparse system: explicit inverse up to 4096 unknowns,
+    block cyclic reduction beyond (after a reverse Cuthill-McKee reordering when the numbering is not banded,
+    coarse.build_coarse_solver), followed by steps of iterative refinement with the residual formed in fp64 on the
+    device until it stops shrinking."""
+
+    DENSE_MAX = 4096
+    REFINE_STEPS = 3
 
     def __init__(self, matrix, rhs):
         super().__init__(matrix, rhs)
 
     def solve(self):
+        from ..coarse import build_coarse_solver
         d = self._device_csr()
         torch, lib, n = d["torch"], d["lib"], d["n"]
-        if n > 4096:
-            raise _lib.MgError("DirectSolver: dense device solve is limited to 4096 unknowns")
         st = _lib.stream_handle(torch)
-        dense = torch.empty(n * n, dtype=torch.float64, device=d["dev"])
-        _lib.check(lib.mg_csr_to_dense(n, d["indptr"].data_ptr(), d["indices"].data_ptr(), d["values"].data_ptr(),
-                                       dense.data_ptr(), st), "mg_csr_to_dense")
-        inv = torch.empty(n * n, dtype=torch.float64, device=d["dev"])
-        work = torch.empty(int(lib.mg_dense_inverse_workspace(n)), dtype=torch.uint8, device=d["dev"])
-        _lib.check(lib.mg_dense_inverse(n, dense.data_ptr(), inv.data_ptr(), work.data_ptr(), st), "mg_dense_inverse")
+        solver = build_coarse_solver(torch, d["dev"], n, d["indptr"], d["indices"], d["values"], self.DENSE_MAX,
+                                     (d["host"].indptr, d["host"].indices))
+        self.method = "dense inverse" if solver.kind == _lib.MG_COARSE_DENSE else (
+            "block cyclic reduction" + (" after reverse Cuthill-McKee" if getattr(solver, "perm", None) is not None else ""))
+
+        def apply(rhs, out):
+            if solver.kind == _lib.MG_COARSE_DENSE:
+                _lib.check(lib.mg_dense_gemv(n, n, solver.inv.data_ptr(), rhs.data_ptr(), out.data_ptr(), st),
+                           "mg_dense_gemv")
+            else:
+                solver.solve(torch, rhs, out)
+
         b = self._upload(self.rhs)
         x = torch.empty_like(b)
-        _lib.check(lib.mg_dense_gemv(n, n, inv.data_ptr(), b.data_ptr(), x.data_ptr(), st), "mg_dense_gemv")
+        apply(b, x)
         r = torch.empty_like(b)
         self._residual(x, b, r)
+        res = self._norm(r)
+        e = torch.empty_like(b)
+        for _ in range(self.REFINE_STEPS):
+            if res == 0.0:
+                break
+            apply(r, e)
+            xn = x + e                     # one elementwise add per refinement step (setup-grade work)
+            rn = torch.empty_like(b)
+            self._residual(xn, b, rn)
+            resn = self._norm(rn)
+            if not resn < res:
+                break
+            x, r, res = xn, rn, resn
         self.solution = x.cpu().numpy().reshape(self.dim, 1)
         self.residual_vector = r.cpu().numpy().reshape(self.dim, 1)
-        self.residual = self._norm(r)
+        self.residual = res
 
 
 class IterativeSolver(Solver):

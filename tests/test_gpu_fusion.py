@@ -188,6 +188,7 @@ def test_fused_cycle_is_bit_identical_to_the_plain_cycle(env, kind, N, levels, n
     old_floor = lib.mg_set_implied_min_rows(1)
     import os
     os.environ["MGB_IMPLIED_MIN_ROWS"] = "1"
+    os.environ["MGB_VALUE_DICT_MIN_ROWS"] = "1"
     try:
         h = DeviceHierarchy(A, Qs, smoother="mcgs")
         flags = [int(getattr(lv, "flags", 0)) for lv in h.levels[:-1]]
@@ -196,10 +197,11 @@ def test_fused_cycle_is_bit_identical_to_the_plain_cycle(env, kind, N, levels, n
             assert h.levels[0].A.slice_off is not None           # structured stencil level: implied columns attached
         params = h.make_params(nu_pre=nu, nu_post=nu, reverse_post=reverse)
         results = {}
-        for fusion in (0, 1):
-            for implied in (0, 1):
+        for fusion, implied, vdict in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 0, 1), (1, 1, 1)):
+            if True:
                 lib.mg_set_cycle_fusion(fusion)
                 lib.mg_set_implied_columns(implied)
+                lib.mg_set_value_dict(vdict)
                 h._graphs = {}
                 h.set_rhs(rhs)
                 h.zero_x()
@@ -211,19 +213,24 @@ def test_fused_cycle_is_bit_identical_to_the_plain_cycle(env, kind, N, levels, n
                     np.testing.assert_allclose(norms[-1], h.residual_norm(), rtol=1e-12)
                 h.vcycle(params, use_graph=False)                # eager, without the norm
                 xs.append(h.levels[0].x.clone())
-                results[(fusion, implied)] = (xs, norms, h.last_launches)
-        base = results[(0, 0)]
+                results[(fusion, implied, vdict)] = (xs, norms, h.last_launches)
+        base = results[(0, 0, 0)]
         for key, (xs, norms, _) in results.items():
             for a, b_ in zip(xs, base[0]):
                 assert env["torch"].equal(a, b_), key
         assert norms[-1] < norms[0]
         # the fused cycle launches no more kernels than the plain one
-        assert results[(1, 1)][2] <= results[(0, 0)][2]
+        assert results[(1, 1, 1)][2] <= results[(0, 0, 0)][2]
+        if kind in ("linear", "linear-var"):                       # linear interpolation: {1, 0.5, 0} -> dictionaries
+            assert h.levels[0].Q.val_idx is not None and h.levels[0].Q.distinct_values <= 4
+            assert (h.levels[0].A.val_idx is not None) == (kind == "linear")    # variable coefficients: too many values
     finally:
         lib.mg_set_cycle_fusion(1)
         lib.mg_set_implied_columns(1)
+        lib.mg_set_value_dict(1)
         lib.mg_set_implied_min_rows(old_floor)
         os.environ.pop("MGB_IMPLIED_MIN_ROWS", None)
+        os.environ.pop("MGB_VALUE_DICT_MIN_ROWS", None)
 
 
 def test_preconditioner_application_from_an_uninitialised_iterate(env):
@@ -373,3 +380,65 @@ def test_device_pcg_single_and_partitioned(env):
             assert il == its
             np.testing.assert_allclose(hl, hist, rtol=1e-7)
             np.testing.assert_allclose(xl, x[o0:o1], rtol=0, atol=1e-10 * np.linalg.norm(x))
+
+
+def test_value_dictionary_kernels_are_bit_identical(env):
+    """csrc/valdict.cu: a matrix with few distinct values is re-encoded as one byte per entry + table, every SELL mode
+    gives the bits of the ordinary kernels (which the other tests pin to the oracle); a matrix with more than 256
+    distinct values gets no dictionary; -0.0 and +0.0 are different entries"""
+    from learnmultigrid_b200 import formats as F
+    from learnmultigrid_b200.engine import DeviceSell
+    L, lib, torch = env["L"], env["lib"], env["torch"]
+    import os
+    os.environ["MGB_VALUE_DICT_MIN_ROWS"] = "1"
+    try:
+        rng = np.random.default_rng(12)
+        for n, per_row, uniform, nvals in ((30000, 5, True, 7), (30000, 2, False, 200), (9000, 3, False, 250), (9000, 2, False, 3)):
+            A = banded(n, per_row, n + nvals, uniform)
+            pool = np.concatenate([rng.standard_normal(nvals - 2), [-0.0, 0.5]])
+            A.data[:] = pool[rng.integers(0, nvals, size=A.nnz)]
+            A = sp.csr_matrix(A)
+            A.setdiag(40.0)                                            # a diagonal that dominates (entries exist already)
+            A = F.raw_csr(A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data, A.shape)
+            colors, nc = F.greedy_colors(A)
+            perm, cptr = F.color_permutation(colors)
+            Ap = F.permute_csr(A, perm, F.inverse_permutation(perm))
+            S = DeviceSell(torch, Ap, env["dev"])
+            assert S.val_idx is not None and S.distinct_values <= 256
+            tab = S.val_table.cpu().numpy()
+            assert np.array_equal(tab[S.val_idx.cpu().numpy().astype(np.int64)].view(np.int64),
+                                  S.vals.cpu().numpy().view(np.int64))              # lossless, signs of zero included
+            x, b, u = rng.standard_normal(n), rng.standard_normal(n), rng.standard_normal(n)
+            ws = torch.zeros(int(lib.mg_norm_workspace_size(n)) + 8, dtype=torch.float64, device=env["dev"])
+            outs = {}
+            for use in (0, 1):
+                lib.mg_set_value_dict(use)
+                dx, db, du = up(env, x), up(env, b), up(env, u)
+                y = torch.empty(n, dtype=torch.float64, device=env["dev"])
+                r = torch.empty(n, dtype=torch.float64, device=env["dev"])
+                xj = torch.empty(n, dtype=torch.float64, device=env["dev"])
+                nrm = torch.zeros(1, dtype=torch.float64, device=env["dev"])
+                dd = up(env, 1.0 / Ap.diagonal())
+                L.check(lib.mg_sell_spmv(ctypes.byref(S.struct), dx.data_ptr(), y.data_ptr(), st(env)))
+                L.check(lib.mg_sell_residual(ctypes.byref(S.struct), dx.data_ptr(), db.data_ptr(), r.data_ptr(), st(env)))
+                L.check(lib.mg_sell_residual_norm2(ctypes.byref(S.struct), dx.data_ptr(), db.data_ptr(), ws.data_ptr(),
+                                                   nrm.data_ptr(), st(env)))
+                L.check(lib.mg_sell_jacobi(ctypes.byref(S.struct), dd.data_ptr(), dx.data_ptr(), db.data_ptr(),
+                                           xj.data_ptr(), 0.7, st(env)))
+                L.check(lib.mg_sell_prolong_correct(ctypes.byref(S.struct), dx.data_ptr(), du.data_ptr(), du.data_ptr(), st(env)))
+                xg = up(env, x)
+                rt = torch.zeros(n, dtype=torch.float64, device=env["dev"])
+                for c in range(nc):
+                    L.check(lib.mg_sell_gs_rows_tail(ctypes.byref(S.struct), xg.data_ptr(), db.data_ptr(), int(cptr[c]),
+                                                     int(cptr[c + 1]), 1, rt.data_ptr(), None, None, st(env)))
+                outs[use] = [t.clone() for t in (y, r, nrm, xj, du, xg, rt)]
+            lib.mg_set_value_dict(1)
+            for a_, b_ in zip(outs[0], outs[1]):
+                assert torch.equal(a_, b_)
+            assert np.array_equal(outs[1][0].cpu().numpy(), K.spmv(Ap, x))
+        many = banded(20000, 5, 3, False)                              # random values: far more than 256 distinct
+        S = DeviceSell(torch, many, env["dev"])
+        assert S.val_idx is None and not S.struct.d_val_idx
+    finally:
+        lib.mg_set_value_dict(1)
+        os.environ.pop("MGB_VALUE_DICT_MIN_ROWS", None)
