@@ -416,6 +416,18 @@ int mg_vector_from_runs(int64_t m, const int32_t *d_rows, const int32_t *d_order
  * triangle-triangle intersections (finishes the reference's 2D stub L2Projection.py:17-24 along the 1D recipe
  * CouplingOperator.py:31-69): nine contributions per candidate pair of elements (+ the overlap area, optional).
  * Fold with mg_coo_fold_sum.  The mg_host_ variant runs the same per-pair code serially on host arrays (CPU tests). */
+/* Candidate (fine, coarse) element pairs = overlapping bounding boxes, found on the device by binning both meshes on one
+ * G x G grid (lower corner h_lo, cell (p - lo) * h_inv_size): mg_tri_boxes_2d writes the boxes (and how many cells each
+ * covers), mg_tri_incidence_2d the (cell, triangle) incidences of the coarse mesh at d_ptr[t] (sort them stably by cell
+ * to get the per-cell lists), mg_tri_pairs_2d counts (d_pair_c NULL) and then writes the pairs of every fine triangle,
+ * coarse ids ascending; a pair is reported in the one cell that holds the lower-left corner of the boxes' intersection. */
+int mg_tri_boxes_2d(int64_t ne, const double *d_points, const int32_t *d_conn, const double *h_lo, const double *h_inv_size,
+                    int32_t G, double *d_box, int32_t *d_ncells, void *stream);
+int mg_tri_incidence_2d(int64_t ne, const double *d_box, const double *h_lo, const double *h_inv_size, int32_t G,
+                        const int32_t *d_ptr, int32_t *d_inc_cell, int32_t *d_inc_tri, void *stream);
+int mg_tri_pairs_2d(int64_t nf, const double *d_box_f, const double *d_box_c, const double *h_lo, const double *h_inv_size,
+                    int32_t G, const int32_t *d_cell_ptr, const int32_t *d_cell_tri, int32_t *d_count,
+                    const int32_t *d_ptr, int32_t *d_pair_f, int32_t *d_pair_c, void *stream);
 int mg_coupling_pairs_p1_2d(int64_t npairs, const int32_t *d_pair_f, const int32_t *d_pair_c, const double *d_pf,
                             const int32_t *d_tf, const double *d_pc, const int32_t *d_tc, int32_t *d_rows,
                             int32_t *d_cols, double *d_vals, double *d_area, void *stream);

@@ -80,21 +80,32 @@ class L2Projection:
         return B / B.sum(axis=1)[:, np.newaxis]
 
     # ---- 2D ------------------------------------------------------------------------------------------------
-    def compute_transfer_2d(self, P=None):
+    def compute_transfer_2d(self, P=None, B=None):
         """Q (CSR) between two P1 triangle meshes of the same domain.
         With P (the linear interpolation coarse -> fine of NESTED meshes, n_f x n_c) the coupling operator is
         B_h = M_h P -- one sparse product.  Without it B_h is integrated on the triangle-triangle
-        intersections (coupling2d.coupling_operator_2d), which works for non-nested meshes as well.
+        intersections ON THE DEVICE (coupling2d.coupling_operator_2d_native), which works for non-nested meshes as
+        well; a coupling operator computed elsewhere can be handed in as B (the CPU tests pass the NumPy model's).
         "quasi": Q = B / rowsum(B); "pseudo": Q = diag(colsum M)^-1 B; "L2": Q = M^-1 B (sparse solve, dense result:
         small meshes only), as in 1D."""
         if self.type not in self.KINDS:
             raise ValueError("unknown projection type %r" % (self.type,))
         M = MassMatrix(self.fine_mesh).compute_mass_2d(FunctionTriangle(1), Quadrature2D(3), format="csr")
-        if P is not None:
+        if B is not None:
+            B = sp.csr_matrix(B)
+        elif P is not None:
             B = sp.csr_matrix(M @ sp.csr_matrix(P))
         else:
-            from .coupling2d import coupling_operator_2d
-            B = coupling_operator_2d(self.fine_mesh, self.coarse_mesh)
+            # on the device: candidate pairs by bounding-box binning, clipping / integration per pair, fold
+            # (csrc/assembly_kernels.cu); coupling2d.coupling_operator_2d is the NumPy model the tests check it against
+            from .coupling2d import coupling_operator_2d_native
+            from ..setup_device import DeviceSetup
+            from .. import _lib
+            Bd = coupling_operator_2d_native(self.fine_mesh, self.coarse_mesh)
+            torch = _lib.require_cuda()
+            B = DeviceSetup(torch, Bd.values.device).download(Bd)
+            B = sp.csr_matrix(B)
+            B.sort_indices()
         if self.type == "L2":
             from scipy.sparse.linalg import splu
             Q = sp.csr_matrix(splu(sp.csc_matrix(M)).solve(B.toarray()))

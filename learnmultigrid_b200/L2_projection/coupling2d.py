@@ -102,28 +102,72 @@ def _barycentric(p, tri, elem, x):
     return np.stack([1.0 - l1 - l2, l1, l2], axis=1)
 
 
+def candidate_pairs_device(S, d_pf, d_tf, d_pc, d_tc, lo, hi):
+    """candidate_pairs on the GPU (csrc/assembly_kernels.cu: mg_tri_boxes_2d / mg_tri_incidence_2d / mg_tri_pairs_2d):
+    both meshes binned on one G x G grid, per-cell lists of the coarse triangles by a stable radix sort of the (cell,
+    triangle) incidences, two passes (count, fill) over the fine triangles.  Returns device int32 arrays (f, c), sorted
+    by fine id, then coarse id -- the same SET of pairs as the host function."""
+    import ctypes
+    from .. import _lib
+    torch, lib, dev = S.torch, S.lib, S.dev
+    st = S.st()
+    nf, nc = d_tf.shape[0], d_tc.shape[0]
+    G = max(1, int(np.sqrt(nc / 2.0)))
+    size = (np.asarray(hi, dtype=np.float64) - np.asarray(lo, dtype=np.float64)) / G
+    size[size == 0] = 1.0
+    h_lo = np.ascontiguousarray(lo, dtype=np.float64)
+    h_inv = np.ascontiguousarray(1.0 / size, dtype=np.float64)
+    plo, pinv = h_lo.ctypes.data_as(ctypes.c_void_p), h_inv.ctypes.data_as(ctypes.c_void_p)
+    box_f, box_c = S.empty(4 * nf, torch.float64), S.empty(4 * nc, torch.float64)
+    ncells = S.empty(nc, torch.int32)
+    _lib.check(lib.mg_tri_boxes_2d(nf, d_pf.data_ptr(), d_tf.data_ptr(), plo, pinv, G, box_f.data_ptr(), None, st),
+               "mg_tri_boxes_2d")
+    _lib.check(lib.mg_tri_boxes_2d(nc, d_pc.data_ptr(), d_tc.data_ptr(), plo, pinv, G, box_c.data_ptr(),
+                                   ncells.data_ptr(), st), "mg_tri_boxes_2d")
+    iptr, ninc = S.scan(ncells, nc)
+    inc_cell, inc_tri = S.empty(ninc, torch.int32), S.empty(ninc, torch.int32)
+    _lib.check(lib.mg_tri_incidence_2d(nc, box_c.data_ptr(), plo, pinv, G, iptr.data_ptr(), inc_cell.data_ptr(),
+                                       inc_tri.data_ptr(), st), "mg_tri_incidence_2d")
+    bits = max(1, int(np.ceil(np.log2(max(G * G, 2)))))
+    order = S.argsort_i32(inc_cell, bits)                     # stable: triangle ids stay ascending inside a cell
+    cell_tri = inc_tri[order.long()].contiguous()
+    cell_sorted = inc_cell[order.long()].contiguous()
+    cell_ptr = torch.searchsorted(cell_sorted, torch.arange(G * G + 1, dtype=torch.int32, device=dev)).to(torch.int32)
+    count = S.empty(nf, torch.int32)
+    _lib.check(lib.mg_tri_pairs_2d(nf, box_f.data_ptr(), box_c.data_ptr(), plo, pinv, G, cell_ptr.data_ptr(),
+                                   cell_tri.data_ptr(), count.data_ptr(), None, None, None, st), "mg_tri_pairs_2d")
+    pptr, K = S.scan(count, nf)
+    pair_f, pair_c = S.empty(K, torch.int32), S.empty(K, torch.int32)
+    if K:
+        _lib.check(lib.mg_tri_pairs_2d(nf, box_f.data_ptr(), box_c.data_ptr(), plo, pinv, G, cell_ptr.data_ptr(),
+                                       cell_tri.data_ptr(), None, pptr.data_ptr(), pair_f.data_ptr(), pair_c.data_ptr(),
+                                       st), "mg_tri_pairs_2d")
+    return pair_f, pair_c
+
+
 def _pair_kernel_inputs(pf, tf, pc, tc, f, c):
     return (np.ascontiguousarray(f, dtype=np.int32), np.ascontiguousarray(c, dtype=np.int32),
             np.ascontiguousarray(pf, dtype=np.float64), np.ascontiguousarray(tf, dtype=np.int32),
             np.ascontiguousarray(pc, dtype=np.float64), np.ascontiguousarray(tc, dtype=np.int32))
 
 
-def coupling_operator_2d_native(fine_mesh, coarse_mesh, where="device"):
-    """The same operator through libmgb200 (csrc/assembly_kernels.cu: one thread per candidate pair clips, triangulates
-    and integrates; runs of equal (row, col) summed by the assembly fold).  where="device": CUDA kernels, returns a
-    device CSR (setup_device.DevCSR); where="host": the same per-pair C code run serially on the host (CPU tests),
-    returns SciPy CSR.  Candidate pairs come from the host binning in both cases."""
+def coupling_operator_2d_native(fine_mesh, coarse_mesh, where="device", pairs="device"):
+    """The same operator through libmgb200 (csrc/assembly_kernels.cu: bounding boxes binned on a grid give the candidate
+    pairs; one thread per candidate pair clips, triangulates and integrates; runs of equal (row, col) summed by the
+    assembly fold).  where="device": CUDA kernels end to end, returns a device CSR (setup_device.DevCSR);
+    where="host": the same per-pair C code run serially on the host with the NumPy binning (CPU tests), returns SciPy
+    CSR."""
     import ctypes
     from .. import _lib
     pf = np.asarray(fine_mesh.get_points(), dtype=np.float64)
     tf = np.asarray(fine_mesh.get_connections(), dtype=np.int64)
     pc = np.asarray(coarse_mesh.get_points(), dtype=np.float64)
     tc = np.asarray(coarse_mesh.get_connections(), dtype=np.int64)
-    f, c = candidate_pairs(pf, tf, pc, tc)
-    hf, hc, hpf, htf, hpc, htc = _pair_kernel_inputs(pf, tf, pc, tc, f, c)
-    K = len(hf)
     lib = _lib.load()
     if where == "host":
+        f, c = candidate_pairs(pf, tf, pc, tc)
+        hf, hc, hpf, htf, hpc, htc = _pair_kernel_inputs(pf, tf, pc, tc, f, c)
+        K = len(hf)
         rows, cols = np.empty(9 * K, dtype=np.int32), np.empty(9 * K, dtype=np.int32)
         vals = np.empty(9 * K)
         ptr = lambda a: a.ctypes.data_as(ctypes.c_void_p)
@@ -139,7 +183,19 @@ def coupling_operator_2d_native(fine_mesh, coarse_mesh, where="device"):
     torch = _lib.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device())
     S = SD.DeviceSetup(torch, dev)
-    d = [torch.from_numpy(a).to(dev) for a in (hf, hc, hpf, htf, hpc, htc)]
+    # meshes to the device once; candidate pairs by binning there (pairs="host": the NumPy binning, for cross-checks)
+    d_pf, d_pc = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev) for a in (pf, pc))
+    d_tf, d_tc = (torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev) for a in (tf, tc))
+    if pairs == "host":
+        f, c = candidate_pairs(pf, tf, pc, tc)
+        d_f = torch.from_numpy(np.ascontiguousarray(f, dtype=np.int32)).to(dev)
+        d_c = torch.from_numpy(np.ascontiguousarray(c, dtype=np.int32)).to(dev)
+    else:
+        lo = np.minimum(pf.min(axis=0), pc.min(axis=0))
+        hi = np.maximum(pf.max(axis=0), pc.max(axis=0))
+        d_f, d_c = candidate_pairs_device(S, d_pf, d_tf, d_pc, d_tc, lo, hi)
+    K = int(d_f.numel())
+    d = [d_f, d_c, d_pf, d_tf, d_pc, d_tc]
     rows, cols, vals = S.empty(9 * K, torch.int32), S.empty(9 * K, torch.int32), S.empty(9 * K, torch.float64)
     st = _lib.stream_handle(torch)
     _lib.check(lib.mg_coupling_pairs_p1_2d(K, *[t.data_ptr() for t in d], rows.data_ptr(), cols.data_ptr(),

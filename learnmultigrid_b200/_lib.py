@@ -119,6 +119,9 @@ _SIGNATURES = {
     "mg_sell_spmv": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
     "mg_sell_slice_offsets": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp]),
     "mg_set_implied_min_rows": (c_i64, [c_i64]),
+    "mg_tri_boxes_2d": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, c_vp]),
+    "mg_tri_incidence_2d": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp]),
+    "mg_tri_pairs_2d": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_value_dict_workspace": (c_i64, []),
     "mg_value_dict_build": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_vp]),
     "mg_set_value_dict": (c_int, [c_int]),

@@ -217,7 +217,7 @@ def rcm_ordering(indptr, indices, n):
     import scipy.sparse as sp
     from scipy.sparse.csgraph import reverse_cuthill_mckee
     pat = sp.csr_matrix((np.ones(len(indices), dtype=np.int8), indices, indptr), shape=(n, n))
-    return np.asarray(reverse_cuthill_mckee(sp.csr_matrix(pat + pat.T), symmetric_mode=True), dtype=np.int32)
+    return np.array(reverse_cuthill_mckee(sp.csr_matrix(pat + pat.T), symmetric_mode=True), dtype=np.int32, copy=True)
 
 
 def permuted_half_bandwidth(indptr, indices, perm):

@@ -266,6 +266,86 @@ coupling_pairs_kernel(int64_t npairs, const int32_t *__restrict__ pair_f, const 
 
 static inline unsigned grid_for(int64_t n) { return (unsigned)((n + kBlock - 1) / kBlock); }
 
+// ---- candidate pairs of the coupling operator: uniform-grid binning of the triangles' bounding boxes ---------------
+// A (fine, coarse) pair is a candidate if the two bounding boxes overlap.  Both meshes are binned on one G x G grid;
+// a fine triangle walks the cells its box covers and the coarse triangles listed there, and reports a pair only in the
+// cell that holds the lower-left corner of the boxes' intersection, so every pair is reported exactly once.
+struct BinGrid {
+    double lo[2], inv[2];       // cell of a point p: floor((p - lo) * inv), clamped to [0, G)
+    int32_t G;
+};
+__device__ __forceinline__ int bin_cell(const BinGrid &g, double v, int d) {
+    int c = (int)floor((v - g.lo[d]) * g.inv[d]);
+    return c < 0 ? 0 : (c >= g.G ? g.G - 1 : c);
+}
+// box[t] = (xlo, ylo, xhi, yhi); ncells[t] = cells the box covers
+__global__ void __launch_bounds__(kBlock)
+tri_boxes_kernel(int64_t ne, const double *__restrict__ pts, const int32_t *__restrict__ conn, BinGrid g,
+                 double *__restrict__ box, int32_t *__restrict__ ncells) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= ne) return;
+    double lo[2] = {1e300, 1e300}, hi[2] = {-1e300, -1e300};
+    for (int i = 0; i < 3; ++i) {
+        const int64_t v = conn[3 * t + i];
+        for (int d = 0; d < 2; ++d) {
+            const double x = pts[2 * v + d];
+            lo[d] = fmin(lo[d], x);
+            hi[d] = fmax(hi[d], x);
+        }
+    }
+    box[4 * t] = lo[0]; box[4 * t + 1] = lo[1]; box[4 * t + 2] = hi[0]; box[4 * t + 3] = hi[1];
+    if (ncells)
+        ncells[t] = (bin_cell(g, hi[0], 0) - bin_cell(g, lo[0], 0) + 1) * (bin_cell(g, hi[1], 1) - bin_cell(g, lo[1], 1) + 1);
+}
+// (cell, triangle) incidences of the coarse mesh, triangle-major: inc_cell[ptr[t] + k], inc_tri likewise
+__global__ void __launch_bounds__(kBlock)
+tri_incidence_kernel(int64_t ne, const double *__restrict__ box, BinGrid g, const int32_t *__restrict__ ptr,
+                     int32_t *__restrict__ inc_cell, int32_t *__restrict__ inc_tri) {
+    const int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (t >= ne) return;
+    const int x0 = bin_cell(g, box[4 * t], 0), x1 = bin_cell(g, box[4 * t + 2], 0);
+    const int y0 = bin_cell(g, box[4 * t + 1], 1), y1 = bin_cell(g, box[4 * t + 3], 1);
+    int64_t o = ptr[t];
+    for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x, ++o) {
+            inc_cell[o] = y * g.G + x;
+            inc_tri[o] = (int32_t)t;
+        }
+}
+// pass 0 (pairs == NULL): count[f] = candidate pairs of fine triangle f; pass 1: write them at ptr[f], coarse ids
+// ascending (the lists of a cell are ascending, the few cells of a box are merged by insertion)
+__global__ void __launch_bounds__(kBlock)
+tri_pairs_kernel(int64_t nf, const double *__restrict__ box_f, const double *__restrict__ box_c, BinGrid g,
+                 const int32_t *__restrict__ cell_ptr, const int32_t *__restrict__ cell_tri,
+                 int32_t *__restrict__ count, const int32_t *__restrict__ ptr, int32_t *__restrict__ pair_f,
+                 int32_t *__restrict__ pair_c) {
+    const int64_t f = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    if (f >= nf) return;
+    const double fx0 = box_f[4 * f], fy0 = box_f[4 * f + 1], fx1 = box_f[4 * f + 2], fy1 = box_f[4 * f + 3];
+    const int x0 = bin_cell(g, fx0, 0), x1 = bin_cell(g, fx1, 0), y0 = bin_cell(g, fy0, 1), y1 = bin_cell(g, fy1, 1);
+    int n = 0;
+    const int64_t base = pair_c ? ptr[f] : 0;
+    for (int y = y0; y <= y1; ++y)
+        for (int x = x0; x <= x1; ++x) {
+            const int cell = y * g.G + x;
+            for (int32_t q = cell_ptr[cell]; q < cell_ptr[cell + 1]; ++q) {
+                const int32_t c = cell_tri[q];
+                const double cx0 = box_c[4 * c], cy0 = box_c[4 * c + 1], cx1 = box_c[4 * c + 2], cy1 = box_c[4 * c + 3];
+                if (!(fx0 <= cx1 && cx0 <= fx1 && fy0 <= cy1 && cy0 <= fy1)) continue;
+                // the cell of the intersection's lower-left corner owns the pair
+                if (bin_cell(g, fmax(fx0, cx0), 0) != x || bin_cell(g, fmax(fy0, cy0), 1) != y) continue;
+                if (pair_c) {
+                    int64_t k = base + n;                      // insertion keeps the coarse ids ascending
+                    while (k > base && pair_c[k - 1] > c) { pair_c[k] = pair_c[k - 1]; --k; }
+                    pair_c[k] = c;
+                    pair_f[base + n] = (int32_t)f;
+                }
+                ++n;
+            }
+        }
+    if (!pair_c) count[f] = n;
+}
+
 }  // namespace mgb
 
 using namespace mgb;
@@ -338,6 +418,37 @@ int mg_coupling_pairs_p1_2d(int64_t npairs, const int32_t *d_pair_f, const int32
     MG_REQUIRE(npairs > 0 && d_pair_f && d_pair_c && d_pf && d_tf && d_pc && d_tc && d_rows && d_cols && d_vals, "null argument");
     coupling_pairs_kernel<<<grid_for(npairs), kBlock, 0, (cudaStream_t)stream>>>(npairs, d_pair_f, d_pair_c, d_pf, d_tf, d_pc, d_tc, d_rows, d_cols, d_vals, d_area);
     MG_CHECK_LAUNCH("coupling_pairs");
+    return MG_OK;
+}
+/* Candidate pairs on the device (see the kernels above).  Boxes: d_box[4*ne]; with d_ncells the number of grid cells each
+ * box covers.  lo / inv_size / G describe the common G x G binning grid. */
+int mg_tri_boxes_2d(int64_t ne, const double *d_points, const int32_t *d_conn, const double *h_lo, const double *h_inv_size,
+                    int32_t G, double *d_box, int32_t *d_ncells, void *stream) {
+    MG_REQUIRE(ne > 0 && d_points && d_conn && h_lo && h_inv_size && G > 0 && d_box, "bad argument");
+    BinGrid g{{h_lo[0], h_lo[1]}, {h_inv_size[0], h_inv_size[1]}, G};
+    tri_boxes_kernel<<<grid_for(ne), kBlock, 0, (cudaStream_t)stream>>>(ne, d_points, d_conn, g, d_box, d_ncells);
+    MG_CHECK_LAUNCH("tri_boxes");
+    return MG_OK;
+}
+int mg_tri_incidence_2d(int64_t ne, const double *d_box, const double *h_lo, const double *h_inv_size, int32_t G,
+                        const int32_t *d_ptr, int32_t *d_inc_cell, int32_t *d_inc_tri, void *stream) {
+    MG_REQUIRE(ne > 0 && d_box && h_lo && h_inv_size && G > 0 && d_ptr && d_inc_cell && d_inc_tri, "bad argument");
+    BinGrid g{{h_lo[0], h_lo[1]}, {h_inv_size[0], h_inv_size[1]}, G};
+    tri_incidence_kernel<<<grid_for(ne), kBlock, 0, (cudaStream_t)stream>>>(ne, d_box, g, d_ptr, d_inc_cell, d_inc_tri);
+    MG_CHECK_LAUNCH("tri_incidence");
+    return MG_OK;
+}
+/* d_pair_c == NULL: d_count[f] = candidate pairs of fine triangle f.  Otherwise the pairs are written at d_ptr[f]
+ * (exclusive scan of the counts): fine id, coarse ids ascending. */
+int mg_tri_pairs_2d(int64_t nf, const double *d_box_f, const double *d_box_c, const double *h_lo, const double *h_inv_size,
+                    int32_t G, const int32_t *d_cell_ptr, const int32_t *d_cell_tri, int32_t *d_count,
+                    const int32_t *d_ptr, int32_t *d_pair_f, int32_t *d_pair_c, void *stream) {
+    MG_REQUIRE(nf > 0 && d_box_f && d_box_c && h_lo && h_inv_size && G > 0 && d_cell_ptr && d_cell_tri, "bad argument");
+    MG_REQUIRE((d_pair_c && d_pair_f && d_ptr) || (!d_pair_c && d_count), "count or fill arguments missing");
+    BinGrid g{{h_lo[0], h_lo[1]}, {h_inv_size[0], h_inv_size[1]}, G};
+    tri_pairs_kernel<<<grid_for(nf), kBlock, 0, (cudaStream_t)stream>>>(nf, d_box_f, d_box_c, g, d_cell_ptr, d_cell_tri,
+                                                                          d_count, d_ptr, d_pair_f, d_pair_c);
+    MG_CHECK_LAUNCH("tri_pairs");
     return MG_OK;
 }
 /* the same per-pair code on HOST arrays (serial), for the CPU test-suite */

@@ -268,7 +268,8 @@ class SemiGeometricMG(Multigrid):
         super().__init__(matrix, rhs)
         self.label = "SemiGeometricMG"
         if isinstance(l2_proj, (list, tuple)):
-            self.l_hierarchy = [csr_matrix(q) for q in l2_proj]     # one operator per level (extension)
+            # one operator per level (extension); operators already on the device (DevCSR) stay there
+            self.l_hierarchy = [q if hasattr(q, "ptrs") else csr_matrix(q) for q in l2_proj]
         else:
             self.l_hierarchy = [csr_matrix(l2_proj)]               # Multigrid.py:182
         self.l2_proj = self.l_hierarchy[0]

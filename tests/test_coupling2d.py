@@ -39,7 +39,7 @@ def test_nested_meshes_give_mass_times_interpolation(N):
     want.sort_indices()
     assert np.array_equal(B.indptr, want.indptr) and np.array_equal(B.indices, want.indices)
     np.testing.assert_allclose(B.data, want.data, rtol=1e-12, atol=1e-16)
-    Q = L2Projection("quasi", fine, coarse).compute_transfer_2d()
+    Q = L2Projection("quasi", fine, coarse).compute_transfer_2d(B=B)       # (without B: integrated on the device)
     np.testing.assert_allclose(Q.toarray(), P.quasi_l2_Q_2d(N).toarray(), rtol=1e-12, atol=1e-15)
 
 
@@ -59,7 +59,7 @@ def test_partition_of_unity_on_non_nested_meshes(fine, coarse):
     inter.find_intersections2d(geometric=True)
     assert len(inter.get_intersections()) == len(pairs)
     for typ in ("quasi", "pseudo"):
-        Q = L2Projection(typ, mf, mc).compute_transfer_2d()
+        Q = L2Projection(typ, mf, mc).compute_transfer_2d(B=B)
         if typ == "quasi":
             np.testing.assert_allclose(np.asarray(Q.sum(axis=1)).ravel(), 1.0, rtol=1e-13)
         assert Q.shape == (mf.get_np(), mc.get_np())
@@ -71,7 +71,7 @@ def test_two_level_cycle_converges_on_non_nested_meshes():
     from oracle.vcycle import OracleMultigrid
     pb = P.irregular_p1_2d(16, seed=4)
     coarse = Mesh2D(36)
-    Q = L2Projection("quasi", pb["mesh"], coarse).compute_transfer_2d()
+    Q = L2Projection("quasi", pb["mesh"], coarse).compute_transfer_2d(B=coupling_operator_2d(pb["mesh"], coarse))
     # coarse boundary nodes interpolate into the Dirichlet rows only: drop their columns so that Q^T A Q is regular
     pc = np.asarray(coarse.get_points())
     interior_c = np.flatnonzero((pc[:, 0] > 1e-12) & (pc[:, 0] < 1 - 1e-12) & (pc[:, 1] > 1e-12) & (pc[:, 1] < 1 - 1e-12))

@@ -130,10 +130,19 @@ def test_device_coupling_operator_on_triangle_intersections(asm):
     from learnmultigrid_b200.assembly.ShapeFunction import FunctionTriangle
     pb = P.irregular_p1_2d(32, seed=8)
     for coarse in (Mesh2D(13 * 13), Mesh2D(16 * 16)):          # unrelated and (for 16x16 parents) nested
-        Bd = asm.S.download(coupling_operator_2d_native(pb["mesh"], coarse))
+        Bd = asm.S.download(coupling_operator_2d_native(pb["mesh"], coarse))                 # pairs binned on the device
+        Bx = asm.S.download(coupling_operator_2d_native(pb["mesh"], coarse, pairs="host"))   # pairs from the NumPy binning
+        assert np.array_equal(Bd.indptr, Bx.indptr) and np.array_equal(Bd.indices, Bx.indices)
+        np.testing.assert_allclose(Bd.data, Bx.data, rtol=1e-13, atol=1e-18)
         Bh = coupling_operator_2d(pb["mesh"], coarse)
         assert np.array_equal(Bd.indptr, Bh.indptr) and np.array_equal(Bd.indices, Bh.indices)
         np.testing.assert_allclose(Bd.data, Bh.data, rtol=1e-12, atol=1e-17)
         Mc = MassMatrix(coarse).compute_mass_2d(FunctionTriangle(1), Quadrature2D(3), format="csr")
         np.testing.assert_allclose(np.asarray(Bd.sum(axis=1)).ravel(), np.asarray(pb["M"].sum(axis=1)).ravel(), rtol=1e-12)
         np.testing.assert_allclose(np.asarray(Bd.sum(axis=0)).ravel(), np.asarray(Mc.sum(axis=1)).ravel(), rtol=1e-12)
+        # the API's 2D transfer operator is built from the device coupling operator
+        from learnmultigrid_b200.L2_projection.L2Projection import L2Projection
+        Qd = L2Projection("quasi", pb["mesh"], coarse).compute_transfer_2d()
+        Qh = L2Projection("quasi", pb["mesh"], coarse).compute_transfer_2d(B=Bh)
+        assert np.array_equal(Qd.indptr, Qh.indptr) and np.array_equal(Qd.indices, Qh.indices)
+        np.testing.assert_allclose(Qd.data, Qh.data, rtol=1e-12, atol=1e-17)

@@ -393,7 +393,7 @@ def test_value_dictionary_kernels_are_bit_identical(env):
     os.environ["MGB_VALUE_DICT_MIN_ROWS"] = "1"
     try:
         rng = np.random.default_rng(12)
-        for n, per_row, uniform, nvals in ((30000, 5, True, 7), (30000, 2, False, 200), (9000, 3, False, 250), (9000, 2, False, 3)):
+        for n, per_row, uniform, nvals in ((30000, 5, True, 7), (30000, 1, False, 200), (9000, 1, False, 250), (9000, 2, True, 3)):
             A = banded(n, per_row, n + nvals, uniform)
             pool = np.concatenate([rng.standard_normal(nvals - 2), [-0.0, 0.5]])
             A.data[:] = pool[rng.integers(0, nvals, size=A.nnz)]
