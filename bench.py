@@ -467,7 +467,7 @@ def run_b200(a):
     # it was taken on (1 GPU, this grid, constant coefficient, the kernel variant that runs by default)
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "r02_gs_traffic.json")
-    implied = getattr(lev0.A, "slice_off", None) is not None and os.environ.get("MGB_IMPLIED_COLUMNS", "1") != "0"
+    implied = getattr(lev0.A, "slice_rec", None) is not None and os.environ.get("MGB_IMPLIED_COLUMNS", "1") != "0"
     if os.path.exists(tpath) and world == 1 and lev0.color_ptr is not None:
         t = json.load(open(tpath))
         if t.get("n") == n and t.get("coefficient") == a.coefficient and bool(t.get("implied_columns")) == implied:

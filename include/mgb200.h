@@ -96,9 +96,18 @@ typedef struct {
     int64_t max_slice_len;      /* longest slice (entries per row); 0 = unknown (generic kernel)           */
     int64_t uniform_len;        /* > 0: EVERY slice has exactly this many entries per row (= max_slice_len), so
                                    slice offsets are computed, not loaded; 0 = lengths vary, use d_slice_ptr */
-    const int32_t *d_slice_off; /* optional (NULL: none): [nslices][8] column offsets relative to the row
-                                   for slices in which every row has the columns row + off[j]; filled by
-                                   mg_sell_slice_offsets, used when mg_set_implied_columns(1) */
+    /* optional implied columns (NULL: none): d_slice_rec[s] = id of the offset record of slice s -- every one of its 32
+     * rows has the columns row + d_rec_table[8 * id + j] -- or 255 for a slice that is not regular (a boundary node
+     * among its rows, the ragged tail: the kernels then read its column indices).  Built from mg_sell_slice_offsets by
+     * deduplicating the records (structured levels have a handful).  h_spec_*: optional host-side hints, for launches
+     * over the rows [h_spec_row[k], h_spec_row[k+1]) the record most of those slices use is h_spec_rec[9 * k] (its id)
+     * with the offsets h_spec_rec[9 * k + 1 .. 9 * k + 8]; the launch passes it by value and the kernel gathers with
+     * it BEFORE the slice's id has arrived (n_spec = 0: record 0, the most frequent one, is assumed). */
+    const unsigned char *d_slice_rec;
+    const int32_t *d_rec_table;
+    int32_t nrec, n_spec;
+    const int64_t *h_spec_row;
+    const int32_t *h_spec_rec;
     /* optional value dictionary (NULL: none; mg_value_dict_build on d_vals): d_vals[p] == d_val_table[d_val_idx[p]] for
      * every stored entry p, at most 256 table entries.  Kernels on rows of at most 8 entries then stream one byte per
      * entry instead of eight (mg_set_value_dict); the doubles are the same, so are the results. */
@@ -110,8 +119,9 @@ typedef struct {
  * 32 rows all have the columns row + off[j] (structured stencil levels: all slices but those holding a boundary node)
  * read 4 bytes of offset per entry index instead of 128 bytes of column indices, and the x gathers of a warp become
  * contiguous 256-byte reads.  mg_sell_slice_offsets fills d_off[nslices * 8] (one 32-byte record per slice, entries
- * beyond uniform_len zero; the table must be 32-byte aligned; irregular slices: d_off[s * 8] = INT32_MIN) and adds the number of regular slices to *d_nregular (device int64, zeroed by the
- * caller; may be NULL); point mg_sell.d_slice_off at the table when enough slices are regular. */
+ * beyond uniform_len zero; irregular slices: d_off[s * 8] = INT32_MIN) -- the raw material of mg_sell.d_slice_rec /
+ * d_rec_table -- and adds the number of regular slices to *d_nregular (device int64, zeroed by the
+ * caller; may be NULL). */
 int mg_sell_slice_offsets(const mg_sell *A, int32_t *d_off, int64_t *d_nregular, void *stream);
 /* Value dictionary (csrc/valdict.cu): finite-element operators on uniform meshes and interpolation operators hold few
  * DISTINCT values (5-point Laplacian: 4, -1, 1, 0; linear interpolation: 1, 0.5, 0).  mg_value_dict_build looks for at

@@ -21,6 +21,7 @@ c_vp = ctypes.c_void_p
 MG_SMOOTH_JACOBI, MG_SMOOTH_MCGS, MG_SMOOTH_LEXGS = 0, 1, 2
 MG_COARSE_DENSE, MG_COARSE_BCR = 0, 1
 MG_LEVEL_PROPER_COLORING, MG_LEVEL_NONZERO_DIAG = 1, 2
+SLICE_IRREGULAR = -2 ** 31
 
 
 class MgError(RuntimeError):
@@ -30,7 +31,9 @@ class MgError(RuntimeError):
 class mg_sell(ctypes.Structure):
     _fields_ = [("nrows", c_i64), ("ncols", c_i64), ("nslices", c_i64),
                 ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp), ("max_slice_len", c_i64),
-                ("uniform_len", c_i64), ("d_slice_off", c_vp), ("d_val_idx", c_vp), ("d_val_table", c_vp)]
+                ("uniform_len", c_i64), ("d_slice_rec", c_vp), ("d_rec_table", c_vp),
+                ("nrec", ctypes.c_int32), ("n_spec", ctypes.c_int32), ("h_spec_row", ctypes.POINTER(c_i64)),
+                ("h_spec_rec", ctypes.POINTER(ctypes.c_int32)), ("d_val_idx", c_vp), ("d_val_table", c_vp)]
 
 
 class mg_bcr(ctypes.Structure):

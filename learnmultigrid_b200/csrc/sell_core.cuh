@@ -18,7 +18,11 @@ struct SellArgs {
     const int64_t *__restrict__ slice_ptr;
     const int32_t *__restrict__ cols;
     const double *__restrict__ vals;
-    const int32_t *__restrict__ slice_off;   // implied columns (IMPL kernels): [nslices][8] offsets, see below
+    const unsigned char *__restrict__ slice_rec;   // implied columns (IMPL kernels): record id per slice, see below
+    const int32_t *__restrict__ rec_table;         // ... [nrec][8] column offsets relative to the row
+    int32_t spec_id;                               // the record this launch expects (most of its slices use it)
+    int32_t spec_off[8];                           // ... and its offsets, by value
+    int32_t ncols_m1;                              // clamp for the speculative gathers
     const unsigned char *__restrict__ vidx;  // value dictionary (VAL8 kernels): one byte per entry, laid out like vals
     const double *__restrict__ vtab;         // ... indexing this table of at most 256 doubles
     int64_t row_begin;   // first row this launch touches
@@ -35,13 +39,18 @@ __host__ __device__ constexpr bool mode_is_tail(int m) { return m == GS_RES || m
 // ---- implied columns ------------------------------------------------------------------------------------------------
 // On a structured stencil level nearly every slice is REGULAR: entry j of every one of its 32 rows has column
 // row + off[j] with ONE offset table for the slice (mg_sell_slice_offsets; formats.sell_slice_offsets is the host twin).
-// For those slices the IMPL kernels compute the columns instead of streaming them: one 32-byte record of offsets per
-// slice (kOffStride ints, two 128-bit loads issued together with the value loads) in place of 128*LEN bytes of column
-// indices, i.e. 65 instead of 88 bytes per 5-point row -- and the x gathers of a warp become contiguous 256-byte reads.  The values, the gathers and the order of the additions are untouched, so the
+// For those slices the IMPL kernels compute the columns instead of streaming them.  A structured level has only a
+// handful of DIFFERENT offset tables (one per colour and grid-line parity), so a slice stores one byte -- the id of its
+// record in a small table -- in place of 128*LEN bytes of column indices: 57 instead of 88 bytes per 5-point row, and
+// the x gathers of a warp become contiguous 256-byte reads.  The launch carries the record most of its slices use BY
+// VALUE: the kernel gathers x with it at once, in the shadow of the load of the slice's id, and only redoes the
+// gathers for the few slices that turn out to use another record (or to be irregular: id 255, columns read from
+// memory).  Without that, every thread would pay two dependent DRAM round trips (record, then x).  The values, the gathers and the order of the additions are untouched, so the
 // results are the same bits; slices that are not regular (a boundary node among the rows, the ragged tail) take the
 // ordinary path inside the same kernel.  Uniform matrices with at most 8 entries per row only.
 constexpr int32_t kSliceIrregular = INT32_MIN;
-constexpr int kOffStride = 8;      // ints per slice in the offset table (rows of at most 8 entries)
+constexpr int kOffStride = 8;      // ints per offset record (rows of at most 8 entries)
+constexpr int kRecIrregular = 255; // d_slice_rec value of a slice whose columns are not implied
 
 // What the epilogue of a row needs besides the row sum.
 struct SellEp {
@@ -73,7 +82,7 @@ struct RowOut {
 // VAL8: the values come from the matrix' dictionary (valdict.cu): one byte per entry from DRAM, the double from a
 // 2 KB table that stays in L1 -- the same doubles, 7 bytes per entry less.
 template <int MODE, int LEN, bool PRED, bool IMPL, bool VAL8>
-__device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, const int32_t *oo, int len, const double *x,
+__device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_t slice, int len, const double *x,
                                           int64_t row, bool active, const SellEp &E, double &contrib,
                                           unsigned char halo_wait, const ExArgs *fx, RowOut &out) {
     const int32_t *__restrict__ c = A.cols + ent;
@@ -101,9 +110,11 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, const 
             }
         }
     }
+    unsigned rec = 0;
     if (IMPL) {
+        rec = __ldg(A.slice_rec + slice);          // one byte, the same for the whole warp; not waited for yet
 #pragma unroll
-        for (int j = 0; j < LEN; ++j) cc[j] = (int32_t)row + oo[j];
+        for (int j = 0; j < LEN; ++j) cc[j] = min(max((int32_t)row + A.spec_off[j], 0), A.ncols_m1);
     }
     // prolongation rows are short (few bytes in flight per thread, registers to spare): fetch u under the matrix loads
     double av = 0.0;
@@ -114,17 +125,29 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, const 
 #pragma unroll
     for (int j = 0; j < LEN; ++j)
         if (!PRED || j < len) xx[j] = (mode_is_gs(MODE) && cc[j] == (int32_t)row) ? 0.0 : x[cc[j]];
+    if (IMPL && rec != (unsigned)A.spec_id) {      // warp-uniform and rare: this slice uses another record, or none
+        if (rec == (unsigned)kRecIrregular) {
+#pragma unroll
+            for (int j = 0; j < LEN; ++j) cc[j] = ld_stream(c + j * kSlice);
+        } else {
+            const int32_t *__restrict__ o = A.rec_table + rec * kOffStride;
+#pragma unroll
+            for (int j = 0; j < LEN; ++j) cc[j] = (int32_t)row + __ldg(o + j);
+        }
+#pragma unroll
+        for (int j = 0; j < LEN; ++j) xx[j] = (mode_is_gs(MODE) && cc[j] == (int32_t)row) ? 0.0 : x[cc[j]];
+    }
     double sum = 0.0, diag = 0.0;
     // GS_RES / GS_NORM keep the separately rounded products (the VALUE for a diagonal entry, flagged in dmask) instead
     // of the row itself: 2 registers per entry across the division instead of 5
-    double pp[(MODE == GS_RES || MODE == GS_NORM) ? LEN : 1];
+    double pp[MODE == GS_RES ? LEN : 1];
     unsigned dmask = 0;
 #pragma unroll
     for (int j = 0; j < LEN; ++j) {
         if (!PRED || j < len) {
-            if (MODE == GS) {
+            if (MODE == GS || MODE == GS_NORM) {
                 if (cc[j] == (int32_t)row) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
-            } else if (MODE == GS_RES || MODE == GS_NORM) {
+            } else if (MODE == GS_RES) {
                 if (cc[j] == (int32_t)row) {
                     if (vv[j] != 0.0) diag = vv[j];
                     pp[j] = vv[j];
@@ -167,11 +190,11 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, const 
                 E.y[row] = xn;
             }
         }
-        if (MODE == GS_RES || MODE == GS_NORM) {
+        if (MODE == GS_RES) {
             // residual of the row with its new value: the products in storage order, the diagonal entry times the new
             // iterate in its place (selects, no branches).  A diagonal entry of a row that was not updated is a stored
             // zero: xn is 0 then and the term an exact zero, which changes nothing (a sum that starts at +0 never
-            // becomes -0).
+            // becomes -0).  These are the bits of the residual pass: the restriction reads them.
             double s2 = 0.0;
 #pragma unroll
             for (int j = 0; j < LEN; ++j)
@@ -179,9 +202,16 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, const 
                     const double t = ((dmask >> j) & 1u) ? __dmul_rn(pp[j], xn) : pp[j];
                     s2 = __dadd_rn(s2, t);
                 }
-            const double r = __dsub_rn(bv, s2);
-            if (MODE == GS_RES) A.r_out[row] = r;
-            else contrib = r * r;
+            A.r_out[row] = __dsub_rn(bv, s2);
+        }
+        if (MODE == GS_NORM) {
+            // The swept row's share of ||b - A x||^2.  Only the NORM is wanted here (a history value compared at
+            // 1e-12, summed in an order of its own anyway), so the row's residual is taken as (b - sum) - d x_new in one
+            // fused multiply-add instead of re-adding the products in storage order: the row has just been solved, the
+            // value is rounding noise of size eps |b| either way, and the kernel stays as light as the plain sweep
+            // (ncu: the storage-order version ran at 2.4 TB/s against 3.9 for the sweep).
+            const double r = upd ? fma(-diag, xn, __dsub_rn(bv, sum)) : __dsub_rn(bv, sum);
+            contrib = r * r;
         }
     }
 }
@@ -249,18 +279,11 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
             constexpr int L = LEN > 0 ? LEN : 1;
             const SellEp E{b, aux, y, omega};
             if (IMPL) {
-                // the slice's offset record: two 128-bit loads, the same address for the whole warp
-                const int4 *__restrict__ o = reinterpret_cast<const int4 *>(A.slice_off + slice * kOffStride);
-                const int4 oa = __ldg(o);
-                int4 ob = make_int4(0, 0, 0, 0);
-                if (L > 4) ob = __ldg(o + 1);
-                const int32_t oo[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
-                if (oa.x != kSliceIrregular) short_row<MODE, L, false, true, VAL8>(A, base + lane, oo, L, x, row, active, E, contrib, hw, fx, out);
-                else short_row<MODE, L, false, false, VAL8>(A, base + lane, nullptr, L, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, false, true, VAL8>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out);
             } else if (UNIFORM || len == L) {
-                short_row<MODE, L, false, false, VAL8>(A, base + lane, nullptr, L, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, false, false, VAL8>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out);
             } else {
-                short_row<MODE, L, true, false, VAL8>(A, base + lane, nullptr, len, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, true, false, VAL8>(A, base + lane, slice, len, x, row, active, E, contrib, hw, fx, out);
             }
         } else {
             double sum = 0.0, diag = 0.0;
@@ -306,6 +329,7 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
 // alive across the division and take 41-48 registers (5 CTAs) when left alone; capped at 40 (6 CTAs) where ptxas
 // manages that without spilling (build/sell_modes_gs.ptxas.log)
 __host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform) {
+    if (m == GS_NORM) return (len >= 1 && uniform && len <= 5) ? 8 : 1;    // as light as the plain sweep
     if (mode_is_tail(m)) return (len <= 5 || (uniform && len <= 7)) ? 6 : 1;
     // the plain modes fit 32 registers (full occupancy); the Gauss-Seidel sweep does up to 5 entries per row
     return (len >= 1 && uniform && len <= (m == GS ? 5 : 7)) ? 8 : 1;
@@ -573,7 +597,11 @@ inline SellArgs sell_args(const mg_sell *A, int64_t row0, int64_t row1, double *
     a.slice_ptr = A->d_slice_ptr;
     a.cols = A->d_cols;
     a.vals = A->d_vals;
-    a.slice_off = A->d_slice_off;
+    a.slice_rec = A->d_slice_rec;
+    a.rec_table = A->d_rec_table;
+    a.spec_id = 0;
+    for (int j = 0; j < 8; ++j) a.spec_off[j] = 0;
+    a.ncols_m1 = (int32_t)(A->ncols > 0 ? A->ncols - 1 : 0);
     a.vidx = A->d_val_idx;
     a.vtab = A->d_val_table;
     a.row_begin = row0;
@@ -589,8 +617,20 @@ inline bool sell_use_dict(const mg_sell *A) {
 }
 inline bool sell_use_implied(const mg_sell *A, int64_t row0, int64_t row1) {
     const int64_t ml = A->max_slice_len;
-    return g_implied_columns && A->d_slice_off && A->uniform_len > 0 && A->uniform_len == ml && ml >= 1 && ml <= 8 &&
-           row1 - row0 >= g_implied_min_rows;
+    return g_implied_columns && A->d_slice_rec && A->d_rec_table && A->nrec > 0 && A->uniform_len > 0 &&
+           A->uniform_len == ml && ml >= 1 && ml <= 8 && row1 - row0 >= g_implied_min_rows;
+}
+// the record a launch over [row0,row1) should expect: the hint of the block that holds row0 if the matrix carries
+// hints, else record 0 (the most frequent one), whose offsets are then unknown on the host -> no speculation possible,
+// the kernel takes the table path for every slice (spec_id = -1)
+inline void sell_pick_spec(const mg_sell *A, int64_t row0, SellArgs &a) {
+    a.spec_id = -1;
+    for (int k = 0; k < A->n_spec && A->h_spec_row && A->h_spec_rec; ++k)
+        if (row0 >= A->h_spec_row[k] && row0 < A->h_spec_row[k + 1]) {
+            a.spec_id = A->h_spec_rec[9 * k];
+            for (int j = 0; j < 8; ++j) a.spec_off[j] = A->h_spec_rec[9 * k + 1 + j];
+            return;
+        }
 }
 
 template <int MODE>
@@ -612,7 +652,8 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
             }
         }
     }
-    const SellArgs a = sell_args(A, row0, row1, r_out);
+    SellArgs a = sell_args(A, row0, row1, r_out);
+    if (sell_use_implied(A, row0, row1)) sell_pick_spec(A, row0, a);
     const int64_t nthreads = row1 - a.first_row;
     const int64_t ml = A->max_slice_len;
     const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
@@ -696,10 +737,11 @@ static int launch_sell_push(const mg_sell *A, double *x, const double *b, int64_
     if (nblocks_out) *nblocks_out = 0;
     if (!push || !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot push an exchange site");
     if (mode_is_tail(MODE) && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
-    const SellArgs a = sell_args(A, row0, row1, r_out);
+    SellArgs a = sell_args(A, row0, row1, r_out);
     const int64_t ml = A->max_slice_len;
     const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
     const bool impl = sell_use_implied(A, row0, row1);
+    if (impl) sell_pick_spec(A, row0, a);
     const bool dict = sell_use_dict(A);
     const int64_t grid = (row1 - a.first_row + kBlock - 1) / kBlock;
     const int nex = carry ? carry->nex : 0;

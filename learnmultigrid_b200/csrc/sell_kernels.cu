@@ -99,19 +99,25 @@ sell_inspect_kernel(int64_t nrows, const int64_t *__restrict__ slice_ptr, int64_
     if (bad) atomicOr(flags, bad);
 }
 
-// see sell_gs_zero_first
+// see sell_gs_zero_first: two entries per thread, 128-bit accesses where both lie inside the colour
 __global__ void __launch_bounds__(kBlock)
 gs_zero_first_kernel(int64_t n_vec, int64_t row0, int64_t row1, const double *__restrict__ diag,
                      const double *__restrict__ b, double *__restrict__ x) {
     pdl_prologue();
-    const int64_t i = (int64_t)blockIdx.x * kBlock + threadIdx.x;
+    const int64_t i = 2 * ((int64_t)blockIdx.x * kBlock + threadIdx.x);
     if (i >= n_vec) return;
-    double v = 0.0;
-    if (i >= row0 && i < row1) {
-        const double d = diag[i];
-        if (d != 0.0) v = __ddiv_rn(__dsub_rn(b[i], 0.0), d);
+    double v0 = 0.0, v1 = 0.0;
+    if (i >= row0 && i + 1 < row1) {
+        const double2 d = *reinterpret_cast<const double2 *>(diag + i);
+        const double2 r = *reinterpret_cast<const double2 *>(b + i);
+        if (d.x != 0.0) v0 = __ddiv_rn(__dsub_rn(r.x, 0.0), d.x);
+        if (d.y != 0.0) v1 = __ddiv_rn(__dsub_rn(r.y, 0.0), d.y);
+    } else {
+        if (i >= row0 && i < row1) { const double d = diag[i]; if (d != 0.0) v0 = __ddiv_rn(__dsub_rn(b[i], 0.0), d); }
+        if (i + 1 >= row0 && i + 1 < row1) { const double d = diag[i + 1]; if (d != 0.0) v1 = __ddiv_rn(__dsub_rn(b[i + 1], 0.0), d); }
     }
-    x[i] = v;
+    if (i + 1 < n_vec) *reinterpret_cast<double2 *>(x + i) = make_double2(v0, v1);
+    else x[i] = v0;
 }
 
 bool sell_fusable(const mg_sell *A, int64_t row0, int64_t row1) {
@@ -141,7 +147,8 @@ int sell_residual_norm2(const mg_sell *A, const double *x, const double *b, doub
 int sell_gs_zero_first(int64_t n_vec, int64_t row0, int64_t row1, const double *diag, const double *b, double *x,
                        cudaStream_t st) {
     if (n_vec <= 0) return MG_OK;
-    launch_k(gs_zero_first_kernel, (unsigned)((n_vec + kBlock - 1) / kBlock), kBlock, st, n_vec, row0, row1, diag, b, x);
+    if ((((uintptr_t)diag | (uintptr_t)b | (uintptr_t)x) & 15) != 0) return set_error(MG_ERR_INVALID, "gs_zero_first", "vectors must be 16-byte aligned");
+    launch_k(gs_zero_first_kernel, (unsigned)(((n_vec + 1) / 2 + kBlock - 1) / kBlock), kBlock, st, n_vec, row0, row1, diag, b, x);
     MG_CHECK_LAUNCH("gs_zero_first");
     return MG_OK;
 }

@@ -76,26 +76,80 @@ class DeviceSell:
     IMPLIED_MIN_ROWS = 1 << 19      # the kernels' floor (mg_set_implied_min_rows): smaller matrices never use a table
 
     def _attach_slice_offsets(self):
-        """Implied columns (sell_core.cuh): per-slice column offsets of a uniform matrix with <= 8 entries per row, so
-        that regular slices compute their columns instead of loading them.  The table is kept when at least half of
-        the slices are regular (structured stencil levels: ~99 %; unstructured numberings: none).
-        MGB_IMPLIED_COLUMNS=0 switches it off."""
-        self.slice_off = None
+        """Implied columns (sell_core.cuh): the per-slice column offsets of a uniform matrix with <= 8 entries per row
+        (mg_sell_slice_offsets), deduplicated: a structured level has a handful of distinct offset records, so a slice
+        keeps one byte (the id of its record, 255 = not regular) and the records sit in a small table, most frequent
+        first.  Kept when at least half of the slices are regular (structured stencil levels: ~99 %; unstructured
+        numberings: none).  MGB_IMPLIED_COLUMNS=0 switches it off."""
+        self.slice_rec = self.rec_table = None
         self.regular_slices = 0
+        self._spec_keep = None
         floor = int(os.environ.get("MGB_IMPLIED_MIN_ROWS", self.IMPLIED_MIN_ROWS))
         if (os.environ.get("MGB_IMPLIED_COLUMNS", "1") == "0" or not 1 <= self.uniform_len <= 8
                 or self.shape[0] < max(floor // 2, 1)):
             return
         import torch
         nsl = (self.shape[0] + 31) // 32
-        off = torch.empty(nsl * 8, dtype=torch.int32, device=self.cols.device)       # one 32-byte record per slice
-        cnt = torch.zeros(1, dtype=torch.int64, device=self.cols.device)
+        dev = self.cols.device
+        off = torch.empty(nsl * 8, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(1, dtype=torch.int64, device=dev)
         _lib.check(_lib.load().mg_sell_slice_offsets(ctypes.byref(self.struct), off.data_ptr(), cnt.data_ptr(),
                                                      _lib.stream_handle(torch)), "mg_sell_slice_offsets")
         self.regular_slices = int(cnt.item())
-        if 2 * self.regular_slices >= nsl:
-            self.slice_off = off
-            self.struct.d_slice_off = off.data_ptr()
+        if 2 * self.regular_slices < nsl:
+            return
+        off = off.view(nsl, 8)
+        regular = off[:, 0] != _lib.SLICE_IRREGULAR
+        recs, inverse, counts = torch.unique(off[regular], dim=0, return_inverse=True, return_counts=True)
+        order = torch.argsort(counts, descending=True)[:254]            # ids 0..253 by frequency; 255 = irregular
+        rank_of = torch.full((recs.shape[0],), 255, dtype=torch.int64, device=dev)
+        rank_of[order] = torch.arange(order.numel(), device=dev)
+        ids = torch.full((nsl,), 255, dtype=torch.uint8, device=dev)
+        ids[regular] = rank_of[inverse].to(torch.uint8)
+        self.regular_slices = int((ids != 255).sum().item())
+        self.slice_rec = ids
+        self.rec_table = recs[order].contiguous().to(torch.int32)
+        self.struct.d_slice_rec = ids.data_ptr()
+        self.struct.d_rec_table = self.rec_table.data_ptr()
+        self.struct.nrec = int(self.rec_table.shape[0])
+        self.set_spec_blocks([0, self.shape[0]])
+
+    @property
+    def slice_off(self):
+        """per-slice offset records [nslices][8] rebuilt from ids + table (tests; None without implied columns)"""
+        if self.slice_rec is None:
+            return None
+        import torch
+        out = torch.zeros(self.slice_rec.numel(), 8, dtype=torch.int32, device=self.slice_rec.device)
+        reg = self.slice_rec != 255
+        out[reg] = self.rec_table[self.slice_rec[reg].long()]
+        out[~reg, 0] = _lib.SLICE_IRREGULAR
+        return out.reshape(-1)
+
+    def set_spec_blocks(self, row_ptr):
+        """Tell the launcher which offset record the slices of each row block [row_ptr[k], row_ptr[k+1]) mostly use
+        (the colour blocks: the ranges the cycle launches over), so that a launch can carry that record by value and
+        gather with it before the slice's own id has arrived (mg_sell.h_spec_*)."""
+        if self.slice_rec is None:
+            return
+        import torch
+        row_ptr = [int(v) for v in row_ptr]
+        nb = len(row_ptr) - 1
+        table = self.rec_table.cpu().numpy()
+        rows = (ctypes.c_int64 * (nb + 1))(*row_ptr)
+        rec = (ctypes.c_int32 * (9 * max(nb, 1)))()
+        for k in range(nb):
+            s0, s1 = row_ptr[k] // 32, max((row_ptr[k + 1] + 31) // 32, row_ptr[k] // 32 + 1)
+            ids = self.slice_rec[s0:s1]
+            ids = ids[ids != 255]
+            best = int(torch.bincount(ids.long(), minlength=1).argmax().item()) if ids.numel() else 0
+            rec[9 * k] = best
+            for j in range(8):
+                rec[9 * k + 1 + j] = int(table[best, j])
+        self._spec_keep = (rows, rec)
+        self.struct.n_spec = nb
+        self.struct.h_spec_row = ctypes.cast(rows, ctypes.POINTER(ctypes.c_int64))
+        self.struct.h_spec_rec = ctypes.cast(rec, ctypes.POINTER(ctypes.c_int32))
 
     @classmethod
     def from_device(cls, shape, nnz, slice_ptr, cols, vals, max_len=0, uniform_len=0):
@@ -121,11 +175,11 @@ class DeviceSell:
         implied columns (large launches) -- 4 bytes of offset per slice and entry index"""
         nsl = (self.shape[0] + 31) // 32
         vbytes = 1 if (self.val_idx is not None and os.environ.get("MGB_VALUE_DICT", "1") != "0") else 8
-        if self.slice_off is None or self.shape[0] < self.IMPLIED_MIN_ROWS or nsl == 0:
+        if self.slice_rec is None or self.shape[0] < self.IMPLIED_MIN_ROWS or nsl == 0:
             return self.padded * (4 + vbytes) + (0 if self.uniform_len else self.slice_ptr.numel() * 8)
         per_slice = 32 * self.uniform_len
         irregular = nsl - self.regular_slices
-        return self.padded * vbytes + irregular * per_slice * 4 + nsl * 32
+        return self.padded * vbytes + irregular * per_slice * 4 + nsl
 
 
 class Level:
@@ -292,6 +346,7 @@ class DeviceHierarchy:
             if getattr(lev, "A", None) is None or lev.color_ptr is None:
                 continue
             lev.diag = torch.empty(lev.n, dtype=torch.float64, device=dev)
+            lev.A.set_spec_blocks(lev.color_ptr)          # launches run over colour blocks: one offset record each
             have = getattr(lev, "flags", None) is not None
             cp = torch.tensor([int(v) for v in lev.color_ptr], dtype=torch.int64, device=dev)
             flag.zero_()

@@ -241,8 +241,8 @@ class DeviceSetup:
         """device perm (new -> old, stable by colour), inverse perm, host colour offsets"""
         t = self.torch
         n = len(colors_host)
-        ncol = int(colors_host.max()) + 1 if n else 0
         keys = t.from_numpy(np.ascontiguousarray(colors_host, dtype=np.int32)).to(self.dev)
+        ncol = int(keys.max().item()) + 1 if n else 0
         ks = self.empty(n, t.int32)
         perm = self.empty(n, t.int32)
         iota = self.empty(n, t.int32)
@@ -255,7 +255,8 @@ class DeviceSetup:
         _lib.check(self.lib.mg_invert_permutation(n, perm.data_ptr(), iperm.data_ptr(), self.st()),
                    "mg_invert_permutation")
         cptr = np.zeros(ncol + 1, dtype=np.int64)
-        np.cumsum(np.bincount(colors_host, minlength=ncol), out=cptr[1:])
+        if n:
+            np.cumsum(t.bincount(keys.long(), minlength=ncol).cpu().numpy(), out=cptr[1:])
         return perm, iperm, cptr
 
 
@@ -299,7 +300,10 @@ def level_colors(S, smoother, colors, A_host0, A_nat):
                 col = np.ascontiguousarray(colors[l], dtype=np.int32)
             else:
                 col = None
-                if os.environ.get("MGB_DEVICE_COLORS", "0") == "1":      # opt-in until it has run on a GPU
+                # first-fit on the device by dependency rounds (csrc/color_kernels.cu: the colours of the serial
+                # helper, entry for entry; 8193^2: 0.78 s for the whole hierarchy instead of 2.3 s, profiles/
+                # r02_bench_device_colours.json); small levels and long dependency chains take the serial helper
+                if os.environ.get("MGB_DEVICE_COLORS", "1") == "1" and A_nat[l].shape[0] >= 50000:
                     try:
                         col = S.first_fit_colors(A_nat[l])
                     except _lib.MgError:

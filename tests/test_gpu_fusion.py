@@ -90,9 +90,13 @@ def test_sweep_with_fused_residual_and_norm_is_the_residual_pass(env, n, per_row
         L.check(lib.mg_sell_gs_rows_tail(ctypes.byref(S.struct), x3.data_ptr(), db.data_ptr(), r0, r1, 2, None,
                                          ws.data_ptr(), ctypes.byref(nb), st(env)))
         assert torch.equal(x1, x3) and nb.value > 0
+        # only the NORM is asked of this mode: the swept rows have just been solved, their residual is rounding noise
+        # (formed with one FMA, not in storage order), so what is checked is its share of ||b - A x||^2
         got = float(ws[:nb.value].sum().item())
-        want = float((r_ref[r0:r1] ** 2).sum().item())
-        np.testing.assert_allclose(got, want, rtol=1e-13)
+        rest = float((r_ref[:r0] ** 2).sum().item() + (r_ref[r1:] ** 2).sum().item())
+        total = float((r_ref ** 2).sum().item())
+        np.testing.assert_allclose(got + rest, total, rtol=1e-13)
+        assert 0.0 <= got <= 1e-24 * max(total, 1.0) * (r1 - r0)
         # residual of the remaining rows by the row-range entry: the two halves make the full residual
         L.check(lib.mg_sell_residual_rows(ctypes.byref(S.struct), x2.data_ptr(), db.data_ptr(), r.data_ptr(), 0, r0, st(env)))
         L.check(lib.mg_sell_residual_rows(ctypes.byref(S.struct), x2.data_ptr(), db.data_ptr(), r.data_ptr(), r1, n, st(env)))

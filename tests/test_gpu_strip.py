@@ -255,7 +255,7 @@ def test_implied_columns_are_bit_identical(torch_mod, monkeypatch):
         for s in ("mcgs", "jacobi"):
             h, got = run(s)
             lev = h.levels[0]
-            assert lev.A.slice_off is not None and lev.A.struct.d_slice_off
+            assert lev.A.slice_off is not None and lev.A.struct.d_slice_rec and lev.A.struct.nrec >= 1
             # device-built offsets = host twin on the same (colour-blocked) matrix
             sell = (lev.A.slice_ptr.cpu().numpy(), lev.A.cols.cpu().numpy(), lev.A.vals.cpu().numpy())
             want = F.sell_slice_offsets(sell, lev.A.shape[0], lev.A.uniform_len)
