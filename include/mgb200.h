@@ -425,7 +425,8 @@ int mg_vector_from_runs(int64_t m, const int32_t *d_rows, const int32_t *d_order
 /* Semi-geometric coupling operator B[f,c] = int phi_f phi_c between two P1 triangle meshes, integrated on the
  * triangle-triangle intersections (finishes the reference's 2D stub L2Projection.py:17-24 along the 1D recipe
  * CouplingOperator.py:31-69): nine contributions per candidate pair of elements (+ the overlap area, optional).
- * Fold with mg_coo_fold_sum.  The mg_host_ variant runs the same per-pair code serially on host arrays (CPU tests). */
+ * Fold with mg_coo_fold_sum.  (mg_host_coupling_pairs_p1_2d, testing library only: the same per-pair code run serially on
+ * host arrays, for the CPU tests.) */
 /* Candidate (fine, coarse) element pairs = overlapping bounding boxes, found on the device by binning both meshes on one
  * G x G grid (lower corner h_lo, cell (p - lo) * h_inv_size): mg_tri_boxes_2d writes the boxes (and how many cells each
  * covers), mg_tri_incidence_2d the (cell, triangle) incidences of the coarse mesh at d_ptr[t] (sort them stably by cell
@@ -441,9 +442,11 @@ int mg_tri_pairs_2d(int64_t nf, const double *d_box_f, const double *d_box_c, co
 int mg_coupling_pairs_p1_2d(int64_t npairs, const int32_t *d_pair_f, const int32_t *d_pair_c, const double *d_pf,
                             const int32_t *d_tf, const double *d_pc, const int32_t *d_tc, int32_t *d_rows,
                             int32_t *d_cols, double *d_vals, double *d_area, void *stream);
+#ifdef MGB_TESTING      /* libmgb200_testing.so only: not exported by the product library */
 int mg_host_coupling_pairs_p1_2d(int64_t npairs, const int32_t *h_pair_f, const int32_t *h_pair_c, const double *h_pf,
                                  const int32_t *h_tf, const double *h_pc, const int32_t *h_tc, int32_t *h_rows,
                                  int32_t *h_cols, double *h_vals, double *h_area);
+#endif
 /* A[nodes,:] = I[nodes,:] for the rows flagged in d_flag: count pass, scan, fill pass */
 int mg_csr_dirichlet_count(int64_t n, const int32_t *d_indptr, const int32_t *d_flag, int32_t *d_count, void *stream);
 int mg_csr_dirichlet_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
@@ -494,6 +497,7 @@ int mg_nn_cut_count(int64_t n, const int32_t *d_indptr, const int32_t *d_indices
 int mg_nn_cut_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const double *d_values,
                    const int32_t *d_keep, const int32_t *d_out_indptr, int32_t *d_out_indices, double *d_out_values,
                    void *stream);
+#ifdef MGB_TESTING      /* libmgb200_testing.so only: not exported by the product library */
 /* the same per-node code run serially on HOST arrays: lets the CPU test-suite check the extraction and contribution
  * logic against the reference's golden vectors without a GPU; not called by the product */
 int mg_host_nn_coarsen(int64_t n, const int32_t *h_t_indptr, const int32_t *h_t_indices, const double *h_t_values,
@@ -503,6 +507,7 @@ int mg_host_nn_extract_patches(int64_t nc, const int32_t *h_indptr, const int32_
                                const int32_t *h_cmap, const int32_t *h_clist, double *h_patches, int32_t *h_fill);
 int mg_host_nn_contributions(int64_t np_, const int32_t *h_fill, const double *h_pred, const int32_t *h_cmap,
                              int32_t unused_row, int32_t *h_rows, int32_t *h_cols, double *h_vals, int32_t *h_dneigh);
+#endif
 
 /* ------------------------------------------------------------------------------------------------ */
 /* host-side (serial, HOST pointers) setup helpers                                                    */
@@ -535,9 +540,11 @@ int mg_csr_coloring_flags(int64_t nrows, int64_t row0, const int32_t *d_indptr, 
 int mg_color_first_fit(int64_t n, const int32_t *d_indptr, const int32_t *d_indices, const int32_t *d_t_indptr,
                        const int32_t *d_t_indices, int32_t *d_colors, void *d_work, int64_t work_bytes,
                        int64_t max_rounds, int64_t *h_rounds, void *stream);
+#ifdef MGB_TESTING      /* libmgb200_testing.so only: not exported by the product library */
 /* the same rounds run serially on HOST arrays with the same per-row code (CPU test-suite; not called by the product) */
 int mg_host_color_rounds(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, const int32_t *h_t_indptr,
                          const int32_t *h_t_indices, int32_t *h_colors, void *h_work, int64_t *h_rounds);
+#endif
 /* dependency level of every row for an exact index-order sweep (see mg_gs_lex_sweep_csr); returns nlevels */
 int64_t mg_host_lex_levels(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, int32_t *h_level);
 

@@ -165,6 +165,7 @@ def coupling_operator_2d_native(fine_mesh, coarse_mesh, where="device", pairs="d
     tc = np.asarray(coarse_mesh.get_connections(), dtype=np.int64)
     lib = _lib.load()
     if where == "host":
+        lib = _lib.load_testing()                # the serial host twin of the pair kernel is test infrastructure
         f, c = candidate_pairs(pf, tf, pc, tc)
         hf, hc, hpf, htf, hpc, htc = _pair_kernel_inputs(pf, tf, pc, tc, f, c)
         K = len(hf)

@@ -205,7 +205,6 @@ _SIGNATURES = {
     "mg_coo_fold_sum": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_vector_from_runs": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_coupling_pairs_p1_2d": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mg_host_coupling_pairs_p1_2d": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_csr_dirichlet_count": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp]),
     "mg_csr_dirichlet_fill": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_nn_coarsen": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -219,16 +218,12 @@ _SIGNATURES = {
     "mg_nn_row_normalise": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "mg_nn_cut_count": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_nn_cut_fill": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mg_host_nn_coarsen": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mg_host_nn_extract_patches": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mg_host_nn_contributions": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp]),
     "mg_host_greedy_color": (c_int, [c_i64, c_vp, c_vp, c_vp]),
     "mg_host_greedy_color_block": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int]),
     "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
     "mg_color_workspace_size": (c_i64, [c_i64]),
     "mg_csr_coloring_flags": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_color_first_fit": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
-    "mg_host_color_rounds": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),
     "mg_vcycle_dist": (c_int, [ctypes.POINTER(mg_comm), ctypes.POINTER(mg_level), c_int,
                                ctypes.POINTER(mg_cycle_params), ctypes.POINTER(mg_dist_norm), c_vp]),
@@ -239,7 +234,19 @@ _SIGNATURES = {
     "mg_graph_destroy": (c_int, [c_vp]),
 }
 
+# serial host emulations of device code, exported by libmgb200_testing.so only (csrc/Makefile): the CPU test-suite checks
+# the NN patch logic, the per-pair coupling integration and the colouring rounds through them; nothing in the product
+# calls load_testing()
+_TESTING_SIGNATURES = {
+    "mg_host_coupling_pairs_p1_2d": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_host_nn_coarsen": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_host_nn_extract_patches": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "mg_host_nn_contributions": (c_int, [c_i64, c_vp, c_vp, c_vp, ctypes.c_int32, c_vp, c_vp, c_vp, c_vp]),
+    "mg_host_color_rounds": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+}
+
 _lib = None
+_testing_lib = None
 
 
 def build(force=False, verbose=False):
@@ -289,6 +296,24 @@ def load():
     if "MGB_WIDE_MAX_ROWS" in os.environ:
         lib.mg_set_wide_max_rows(int(os.environ["MGB_WIDE_MAX_ROWS"]))
     _lib = lib
+    return lib
+
+
+def load_testing():
+    """libmgb200_testing.so: the product library plus the `mg_host_*` emulations (test infrastructure)."""
+    global _testing_lib
+    if _testing_lib is not None:
+        return _testing_lib
+    path = os.path.join(os.path.dirname(LIB_PATH), "libmgb200_testing.so")
+    if not os.path.exists(path):
+        raise MgError("libmgb200_testing.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    lib = ctypes.CDLL(path)
+    for table in (_SIGNATURES, _TESTING_SIGNATURES):
+        for name, (res, args) in table.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+    _testing_lib = lib
     return lib
 
 

@@ -451,6 +451,7 @@ int mg_tri_pairs_2d(int64_t nf, const double *d_box_f, const double *d_box_c, co
     MG_CHECK_LAUNCH("tri_pairs");
     return MG_OK;
 }
+#ifdef MGB_TESTING
 /* the same per-pair code on HOST arrays (serial), for the CPU test-suite */
 int mg_host_coupling_pairs_p1_2d(int64_t npairs, const int32_t *h_pair_f, const int32_t *h_pair_c, const double *h_pf,
                                  const int32_t *h_tf, const double *h_pc, const int32_t *h_tc, int32_t *h_rows,
@@ -476,6 +477,7 @@ int mg_host_coupling_pairs_p1_2d(int64_t npairs, const int32_t *h_pair_f, const 
     }
     return MG_OK;
 }
+#endif  // MGB_TESTING
 
 /* Dirichlet rows (thesis_structured_2d.py:407-414: A[nodes,:] = I[nodes,:]): rows with d_flag != 0 become (i, 1.0).
  * Two passes around a scan of d_count. */

@@ -224,6 +224,7 @@ int mg_csr_coloring_flags(int64_t nrows, int64_t row0, const int32_t *d_indptr, 
     return MG_OK;
 }
 
+#ifdef MGB_TESTING
 /* The same rounds run serially on HOST arrays with the same per-row code (CPU test-suite; not called by the product).
  * h_work: mg_color_workspace_size(n) bytes.  *h_rounds = number of non-empty rounds. */
 int mg_host_color_rounds(int64_t n, const int32_t *h_indptr, const int32_t *h_indices, const int32_t *h_t_indptr,
@@ -259,5 +260,6 @@ int mg_host_color_rounds(int64_t n, const int32_t *h_indptr, const int32_t *h_in
     if (done != n) return set_error(MG_ERR_INVALID, "mg_host_color_rounds", "rows left uncoloured (inconsistent transpose pattern?)");
     return MG_OK;
 }
+#endif  // MGB_TESTING
 
 }  // extern "C"

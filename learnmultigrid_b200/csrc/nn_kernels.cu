@@ -594,6 +594,7 @@ int mg_nn_cut_fill(int64_t n, const int32_t *d_indptr, const int32_t *d_indices,
     return MG_OK;
 }
 
+#ifdef MGB_TESTING
 /* ---- the same per-node code on HOST arrays (serial): used by the CPU test-suite to check the extraction and the
  * contribution logic against the reference's golden vectors without a GPU.  Not called by the product. ---- */
 int mg_host_nn_coarsen(int64_t n, const int32_t *h_t_indptr, const int32_t *h_t_indices, const double *h_t_values,
@@ -639,5 +640,6 @@ int mg_host_nn_contributions(int64_t np_, const int32_t *h_fill, const double *h
     }
     return MG_OK;
 }
+#endif  // MGB_TESTING
 
 }  // extern "C"

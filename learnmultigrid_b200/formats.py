@@ -245,7 +245,7 @@ def greedy_colors_by_rounds(A):
     T = sp.csr_matrix((np.ones(A.nnz), A.indices, A.indptr), shape=A.shape).T.tocsr()
     T.sort_indices()
     tip, tix = T.indptr.astype(np.int32), T.indices.astype(np.int32)
-    lib = _lib.load()
+    lib = _lib.load_testing()                    # the host emulation lives in libmgb200_testing.so
     colors = np.empty(max(n, 1), dtype=np.int32)
     work = np.zeros(int(lib.mg_color_workspace_size(n)), dtype=np.uint8)
     rounds = ctypes.c_int64(0)

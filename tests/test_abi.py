@@ -8,9 +8,15 @@ from learnmultigrid_b200 import _lib
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_functions():
+def declared_functions(testing=False):
+    """product prototypes of mgb200.h, or (testing=True) those inside its `#ifdef MGB_TESTING` blocks"""
     text = open(os.path.join(ROOT, "include", "mgb200.h")).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    blocks = re.findall(r"#ifdef MGB_TESTING(.*?)#endif", text, flags=re.S)
+    if testing:
+        text = "\n".join(blocks)
+    else:
+        text = re.sub(r"#ifdef MGB_TESTING.*?#endif", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(mg_[a-z0-9_]+)\s*\(", text)))
 
 
@@ -23,6 +29,18 @@ def test_header_symbols_are_exported_and_bound():
         assert n in _lib._SIGNATURES, "declared in mgb200.h but not bound in _lib.py: " + n
     for n in _lib._SIGNATURES:
         assert n in names, "bound in _lib.py but not declared in mgb200.h: " + n
+
+
+def test_host_emulations_live_in_the_testing_library_only():
+    """the serial host twins of device code (mg_host_nn_*, mg_host_coupling_pairs_p1_2d, mg_host_color_rounds) are test
+    infrastructure: exported by libmgb200_testing.so, absent from the product library"""
+    twins = declared_functions(testing=True)
+    assert len(twins) == 5 and sorted(twins) == sorted(_lib._TESTING_SIGNATURES)
+    product = ctypes.CDLL(_lib.LIB_PATH)
+    testing = _lib.load_testing()
+    for n in twins:
+        assert not hasattr(product, n), "test-only symbol in the product library: " + n
+        assert hasattr(testing, n)
 
 
 def test_library_loads_and_reports_version():

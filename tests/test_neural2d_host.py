@@ -40,7 +40,7 @@ def ptr(a):
 
 
 def host_coarsen(M):
-    lib = _lib.load()
+    lib = _lib.load_testing()
     MT = sp.csr_matrix(M.T)
     MT.sort_indices()
     n = M.shape[0]
@@ -64,7 +64,7 @@ def fold_reference_rule(rows, cols, vals, n, nc, unused):
 
 @pytest.mark.parametrize("case", CASES)
 def test_coarsening_extraction_and_fill_match_the_reference(case):
-    lib = _lib.load()
+    lib = _lib.load_testing()
     g = load_golden("neural_2d_cases.npz")
     for l, d in enumerate(levels_of(g, case)):
         M = d["M"]
@@ -115,7 +115,7 @@ def star(arms):
 
 def test_variants_drop_a_sliding_window_of_the_smallest_entries():
     """a hub with 9 neighbours of increasing mass entry: variant v keeps all but the entries ranked v..v+2"""
-    lib = _lib.load()
+    lib = _lib.load_testing()
     M = star(9)
     cmap, clist = host_coarsen(M)
     assert clist[0] == 0
@@ -134,7 +134,7 @@ def test_variants_drop_a_sliding_window_of_the_smallest_entries():
 
 
 def test_more_than_twelve_neighbours_is_reported_not_worked_around():
-    lib = _lib.load()
+    lib = _lib.load_testing()
     M = star(13)
     cmap, clist = host_coarsen(M)
     ip, ix, va = M.indptr.astype(np.int32), M.indices.astype(np.int32), M.data.astype(np.float64)
@@ -147,7 +147,7 @@ def test_more_than_twelve_neighbours_is_reported_not_worked_around():
 def test_first_reference_run_with_the_stub_predictor():
     """tests/golden/neural_2d_stub.npz: the reference's NeuralMG_2D on Mesh2D(64) (SURVEY 8c probe: the 25 coarse nodes
     (2j, 2k), patches (25, 43), Q shapes (81, 25) and (25, 9))"""
-    lib = _lib.load()
+    lib = _lib.load_testing()
     g = load_golden("neural_2d_stub.npz")
     M = sp.csr_matrix((g["M_data"], (g["M_row"], g["M_col"])), shape=tuple(g["M_shape"]))
     M.sort_indices()
