@@ -144,7 +144,7 @@ int mg_sell_residual(const mg_sell *A, const double *d_x, const double *d_b, dou
 int mg_sell_residual_rows(const mg_sell *A, const double *d_x, const double *d_b, double *d_r, int64_t row0,
                           int64_t row1, void *stream);
 /* fused: *d_norm2 = sum_i (b - A x)_i^2 without storing r (outer loop Multigrid.py:62-63); d_partials is a
- * workspace of mg_norm_workspace_size(nrows) = ceil(nrows/32)+2 doubles (the worst case over the kernel variants: one
+ * workspace of mg_norm_workspace_size(nrows) = ceil(nrows/32)+66 doubles (the worst case over the kernel variants: one
  * partial per CTA, the warps-per-slice kernel has one CTA per slice, and mg_vcycle_norm writes two runs of partials);
  * deterministic two-stage reduction. */
 int mg_sell_residual_norm2(const mg_sell *A, const double *d_x, const double *d_b, double *d_partials,

@@ -133,7 +133,29 @@ bool sell_gs_tail_ok(const mg_sell *A, int64_t row0, int64_t row1) {
 int sell_spmv(const mg_sell *A, const double *x, double *y, int64_t row0, int64_t row1, const SellFuse *fuse, cudaStream_t st) {
     return launch_sell<SPMV>(A, x, nullptr, nullptr, y, 0.0, nullptr, row0, row1, st, "sell_spmv", nullptr, fuse);
 }
+// first stage of a long reduction: CTA g sums the contiguous chunk [g * chunk, (g+1) * chunk) in a fixed order
+__global__ void __launch_bounds__(1024) reduce_chunks_kernel(const double *__restrict__ partials, int64_t n, int64_t chunk,
+                                                             double *__restrict__ out) {
+    pdl_prologue();
+    const int64_t lo = (int64_t)blockIdx.x * chunk, hi = lo + chunk < n ? lo + chunk : n;
+    double s = 0.0;
+    for (int64_t i = lo + threadIdx.x; i < hi; i += 1024) s += partials[i];
+    s = block_sum_last<1024>(s);
+    if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+constexpr int kReduceChunks = 64;       // CTAs of the first stage (the workspace holds that many doubles behind the partials)
+
 int sell_reduce_partials(const double *partials, int64_t n, double *out, cudaStream_t st) {
+    if (n > 32768) {                    // one CTA would take tens of microseconds (262 k partials: 28 us)
+        double *tmp = const_cast<double *>(partials) + n;
+        const int64_t chunk = (n + kReduceChunks - 1) / kReduceChunks;
+        launch_k(reduce_chunks_kernel, (unsigned)kReduceChunks, 1024u, st, partials, n, chunk, tmp);
+        MG_CHECK_LAUNCH("reduce_chunks");
+        launch_k(reduce_partials_kernel, 1u, 1024u, st, (const double *)tmp, (int64_t)kReduceChunks, out);
+        MG_CHECK_LAUNCH("reduce_partials");
+        return MG_OK;
+    }
     launch_k(reduce_partials_kernel, 1u, 1024u, st, partials, n, out);
     MG_CHECK_LAUNCH("reduce_partials");
     return MG_OK;
@@ -186,8 +208,9 @@ int mg_sell_residual_rows(const mg_sell *A, const double *d_x, const double *d_b
     return sell_residual(A, d_x, d_b, d_r, row0, row1, nullptr, (cudaStream_t)stream);
 }
 /* worst case over the kernels that write partials: the warps-per-slice kernel with eight warps per slice has one CTA
- * (one partial) per 32 rows; a sweep with a fused norm followed by the norm of the remaining rows writes two runs */
-int64_t mg_norm_workspace_size(int64_t n) { return (n + kSlice - 1) / kSlice + 2; }
+ * (one partial) per 32 rows; a sweep with a fused norm followed by the norm of the remaining rows writes two runs;
+ * the first stage of a long second-stage reduction parks its 64 sums behind the partials */
+int64_t mg_norm_workspace_size(int64_t n) { return (n + kSlice - 1) / kSlice + 2 + kReduceChunks; }
 int mg_sell_halo_mask(const mg_sell *A, int64_t first_halo_col, unsigned char *d_mask, void *stream) {
     MG_REQUIRE(A && d_mask && A->nrows > 0, "null argument");
     const int64_t ns = A->nslices;
