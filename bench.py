@@ -582,8 +582,8 @@ def run_b200(a):
                                    % ("off" if os.environ.get("MGB_CYCLE_FUSION", "1") == "0" else "on",
                                       "on" if implied else "off"),
                            "ms_per_step_without_exchange_waits": ms_dry,
-                           "exchange": (("producer-driven (MGB_PUSH_EXCHANGE=1)" if getattr(h, "push_exchange", False)
-                                         else "consumer-driven") if part else None),
+                           "exchange": ("halo sites riding on the SELL kernel that reads the vector (peer-memory stores)"
+                                        if part else None),
                            "parallelism": ("row-partitioned x%d, levels 0..%d partitioned, %d replicated, halo exchange by peer-memory "
                                            "stores over NVLink inside the cycle graph" % (world, h.n_dist - 1, a.levels - h.n_dist))
                            if part else ("replicas" if world > 1 else "single")},

@@ -384,27 +384,12 @@ typedef struct {
      * extra CTAs in front push / poll / unpack, the compute CTAs of masked slices wait for them, all others overlap
      * the exchange.  NULL: every slice waits. */
     const unsigned char *d_mask_A, *d_mask_Q, *d_mask_QT;
-    /* Producer-driven colour exchanges (mg_set_push_exchange; all NULL: not available).  Send table of colour c =
-     * entries [h_push_ptr[c], h_push_ptr[c+1]) of d_push_row / d_push_peer / d_push_pos, sorted by row: local row
-     * d_push_row[e] is packet d_push_pos[e] of the message xfer_color[c] sends to its peer number d_push_peer[e].
-     * d_push_mask: per slice of A, 1 if the slice holds a row of any colour's table.  h_push_tail[c]: how many CTAs (of
-     * 256 rows) at the end of colour c's row range hold rows sent to a higher rank; they are run first. */
-    const int64_t *h_push_ptr;
-    const int32_t *d_push_row, *d_push_peer, *d_push_pos;
-    const unsigned char *d_push_mask;
-    const int64_t *h_push_tail;
 } mg_dist_level;
 /* d_mask[s] = 1 if slice s of the SELL matrix holds a column >= first_halo_col */
 int mg_sell_halo_mask(const mg_sell *A, int64_t first_halo_col, unsigned char *d_mask, void *stream);
 /* 1 (default): in mg_vcycle_dist with multicolour Gauss-Seidel the halo exchanges ride on the following SELL kernel
  * (see mg_dist_level); 0: every exchange is a kernel of its own.  Same results.  Returns the previous setting. */
 int mg_set_fused_exchange(int enabled);
-/* 1: on levels that carry send tables (mg_dist_level.h_push_ptr) a colour sweep of multicolour Gauss-Seidel stores its
- * boundary values into the neighbours' staging slots ITSELF, boundary rows first, so that the NVLink flight overlaps
- * the interior rows of the kernel that produced the values; the next kernel that reads the vector only polls and
- * unpacks.  0 (default): the values are pushed by extra CTAs of that next kernel.  Same packets, same results.
- * Needs mg_set_fused_exchange(1).  Returns the previous setting. */
-int mg_set_push_exchange(int enabled);
 
 /* ------------------------------------------------------------------------------------------------ */
 /* P1 assembly on the device (csrc/assembly_kernels.cu).  Replaces the per-element Python loops of

@@ -65,9 +65,7 @@ class mg_dist_level(ctypes.Structure):
     _fields_ = [("n_halo", c_i64), ("ncolors", ctypes.c_int32), ("pad_", ctypes.c_int32),
                 ("xfer_color", ctypes.POINTER(mg_xfer)), ("xfer_all", ctypes.POINTER(mg_xfer)),
                 ("xfer_gather", ctypes.POINTER(mg_xfer)), ("d_gather_tmp", c_vp), ("d_gather_self_idx", c_vp),
-                ("n_gather_own", c_i64), ("d_mask_A", c_vp), ("d_mask_Q", c_vp), ("d_mask_QT", c_vp),
-                ("h_push_ptr", ctypes.POINTER(c_i64)), ("d_push_row", c_vp), ("d_push_peer", c_vp), ("d_push_pos", c_vp),
-                ("d_push_mask", c_vp), ("h_push_tail", ctypes.POINTER(c_i64))]
+                ("n_gather_own", c_i64), ("d_mask_A", c_vp), ("d_mask_Q", c_vp), ("d_mask_QT", c_vp)]
 
 
 class mg_bcr_dist(ctypes.Structure):
@@ -149,7 +147,6 @@ _SIGNATURES = {
     "mg_set_tma_min_rows": (c_i64, [c_i64]),
     "mg_sell_halo_mask": (c_int, [ctypes.POINTER(mg_sell), c_i64, c_vp, c_vp]),
     "mg_set_fused_exchange": (c_int, [c_int]),
-    "mg_set_push_exchange": (c_int, [c_int]),
     "mg_set_wide_min_len": (c_i64, [c_i64]),
     "mg_set_wide_max_rows": (c_i64, [c_i64]),
     "mg_sell_jacobi": (c_int, [ctypes.POINTER(mg_sell), c_vp, c_vp, c_vp, c_vp, c_dbl, c_vp]),
@@ -279,8 +276,6 @@ def load():
         lib.mg_set_pdl(0)
     if os.environ.get("MGB_FUSED_EXCHANGE", "1") == "0":
         lib.mg_set_fused_exchange(0)
-    if os.environ.get("MGB_PUSH_EXCHANGE", "0") == "1":
-        lib.mg_set_push_exchange(1)
     if os.environ.get("MGB_IMPLIED_COLUMNS", "1") == "0":
         lib.mg_set_implied_columns(0)
     if "MGB_IMPLIED_MIN_ROWS" in os.environ:

@@ -205,57 +205,6 @@ bcr_forward_kernel(int m, int s, int64_t na, int64_t j0, int64_t nk, const doubl
     if (lane == 0) f[(p << s) * m + r] -= acc;
 }
 
-// The same two kernels for a level that is SPLIT over the ranks in producer-driven mode (mg_set_push_exchange): the
-// lane that stores a block-row entry also stores it into every peer's staging slot.  The all-gather message of a
-// split level lists the rank's entries block by block, row by row (coarse.py::make_dist), i.e. entry `wid` of the launch
-// is packet `wid`; the site itself then only polls and unpacks (ExArgs.recv_only).
-__global__ void __launch_bounds__(kBlock)
-bcr_forward_push_kernel(int m, int s, int64_t na, int64_t j0, int64_t nk, const double *__restrict__ GL,
-                        const double *__restrict__ GU, double *f, const ExArgs px) {
-    pdl_prologue();
-    const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wid >= nk * m) return;
-    const int64_t j = j0 + wid / m;
-    const int r = (int)(wid % m);
-    const int64_t p = 2 * j;
-    double acc = 0.0;
-    if (p >= 1) acc += warp_row_dot(GL + (j * m + r) * (int64_t)m, f + ((p - 1) << s) * m, m, lane);
-    if (p + 1 < na) acc += warp_row_dot(GU + (j * m + r) * (int64_t)m, f + ((p + 1) << s) * m, m, lane);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-        const double v = f[(p << s) * m + r] - acc;
-        f[(p << s) * m + r] = v;
-        if (!px.dry)
-            for (int k = 0; k < px.npeers; ++k) push_boundary_value(px, k, wid, v);
-    }
-}
-
-__global__ void __launch_bounds__(kBlock)
-bcr_backward_push_kernel(int m, int s, int64_t na, int64_t j0, int64_t nodd, const double *__restrict__ Dinv,
-                         const double *__restrict__ HL, const double *__restrict__ HU, const double *__restrict__ f,
-                         double *x, const ExArgs px) {
-    pdl_prologue();
-    const int64_t wid = ((int64_t)blockIdx.x * kBlock + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (wid >= nodd * m) return;
-    const int64_t j = j0 + wid / m;
-    const int r = (int)(wid % m);
-    const int64_t p = 2 * j + 1;
-    const int64_t ro = (j * m + r) * (int64_t)m;
-    double acc = warp_row_dot(Dinv + ro, f + (p << s) * m, m, lane);
-    acc -= warp_row_dot(HL + ro, x + ((p - 1) << s) * m, m, lane);
-    if (p + 1 < na) acc -= warp_row_dot(HU + ro, x + ((p + 1) << s) * m, m, lane);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-    if (lane == 0) {
-        x[(p << s) * m + r] = acc;
-        if (!px.dry)
-            for (int k = 0; k < px.npeers; ++k) push_boundary_value(px, k, wid, acc);
-    }
-}
-
 // the system left after s reduction levels (tail_na blocks at positions p << s): gather its right-hand side into a
 // contiguous vector; the dense inverse is then applied by gemv_rows (dense_kernels.cu), which scatters the result back
 __global__ void __launch_bounds__(kBlock)
@@ -296,9 +245,6 @@ bcr_store_kernel(int64_t n, const double *__restrict__ x, const int32_t *__restr
 static inline unsigned warps_grid(int64_t nwarps) { return (unsigned)((nwarps * 32 + kBlock - 1) / kBlock); }
 
 int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStream_t);
-int comm_prepare(mg_comm *, const mg_xfer *, const double *, double *, ExArgs *, int *);
-int comm_launch_prepared(const ExArgs &, int, cudaStream_t);
-extern int g_push_exchange;      // cycle.cu (mg_set_push_exchange)
 int gemv_rows(int64_t total_rows, int64_t row0, int64_t nrows, int64_t m, const double *M, const double *x, double *y,
               int64_t bm, int shift, cudaStream_t st);
 
@@ -317,23 +263,6 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
         const int64_t na = H->na[s], nk = (na + 1) / 2;
         const bool split = dist && dist->fwd_xfer[s];
         const int64_t j0 = split ? dist->fwd_j0[s] : 0, j1 = split ? dist->fwd_j1[s] : nk;
-        if (split && g_push_exchange && j1 > j0) {      // producer-driven: book the site, push from the kernel, then unpack
-            ExArgs px;
-            int grid = 0;
-            int rc = comm_prepare(comm, dist->fwd_xfer[s], H->f, H->f, &px, &grid);
-            if (rc) return rc;
-            if (grid > 0) {
-                launch_k(bcr_forward_push_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->GL[s], H->GU[s], H->f, px);
-                MG_CHECK_LAUNCH("bcr_forward_push");
-                px.recv_only = 1;
-                rc = comm_launch_prepared(px, grid, st);
-                if (rc) return rc;
-            } else {
-                launch_k(bcr_forward_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->GL[s], H->GU[s], H->f);
-                MG_CHECK_LAUNCH("bcr_forward");
-            }
-            continue;
-        }
         if (j1 > j0) {
             launch_k(bcr_forward_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->GL[s], H->GU[s], H->f);
             MG_CHECK_LAUNCH("bcr_forward");
@@ -362,25 +291,6 @@ int bcr_solve(const void *handle, const mg_bcr_dist *dist, mg_comm *comm, const 
         const int64_t na = H->na[s], nodd = na / 2;
         const bool split = dist && dist->bwd_xfer[s];
         const int64_t j0 = split ? dist->bwd_j0[s] : 0, j1 = split ? dist->bwd_j1[s] : nodd;
-        if (split && g_push_exchange && j1 > j0) {
-            ExArgs px;
-            int grid = 0;
-            int rc = comm_prepare(comm, dist->bwd_xfer[s], H->x, H->x, &px, &grid);
-            if (rc) return rc;
-            if (grid > 0) {
-                launch_k(bcr_backward_push_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->Dinv[s],
-                         H->HL[s], H->HU[s], H->f, H->x, px);
-                MG_CHECK_LAUNCH("bcr_backward_push");
-                px.recv_only = 1;
-                rc = comm_launch_prepared(px, grid, st);
-                if (rc) return rc;
-            } else {
-                launch_k(bcr_backward_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->Dinv[s],
-                         H->HL[s], H->HU[s], H->f, H->x);
-                MG_CHECK_LAUNCH("bcr_backward");
-            }
-            continue;
-        }
         if (j1 > j0) {
             launch_k(bcr_backward_kernel, (unsigned)(warps_grid((j1 - j0) * m)), (unsigned)kBlock, st, m, s, na, j0, j1 - j0, H->Dinv[s], H->HL[s],
                                                                               H->HU[s], H->f, H->x);

@@ -49,52 +49,6 @@ __global__ void sum_slots_kernel(const double *value, const double *slots, int r
     }
 }
 
-// Squared residual norm of a partitioned level, second stage and all-reduce in ONE kernel of one CTA (producer-driven
-// mode; otherwise reduce_partials_kernel + exchange_kernel + sum_slots_kernel): sum the per-block partials in the fixed
-// order of reduce_partials_kernel, store the local sum into every peer's staging slot, poll for theirs, add in rank
-// order.  Same additions in the same order as the three-kernel path, hence the same bits.
-__global__ void __launch_bounds__(1024)
-norm_allreduce_kernel(const double *__restrict__ partials, int64_t n, double *local, const ExArgs a, int rank, int world,
-                      double *slots, double *out) {
-    pdl_prologue();
-    __shared__ double mine;
-    double s = 0.0;
-    for (int64_t i = threadIdx.x; i < n; i += 1024) s += partials[i];
-    s = block_sum<1024>(s);
-    if (threadIdx.x == 0) {
-        mine = s;
-        *local = s;
-    }
-    __syncthreads();
-    if (!a.dry) {
-        if ((int)threadIdx.x < a.npeers) {
-            const int k = (int)threadIdx.x;
-            const ExPeer &P = a.p[k];
-            push_boundary_value(a, k, 0, mine);
-            const unsigned long long epoch = *a.epoch;
-            const unsigned long long tag = (epoch & 0xffffffffull) << 32;
-            const ulonglong2 *in = P.my_stage + (int64_t)(epoch & 1ull) * a.parity_stride;
-            unsigned long long w0, w1;
-            const unsigned long long t0 = global_timer_ns();
-            unsigned int spins = 0;
-            bool ok = true;
-            for (;;) {
-                ld_packet(in, w0, w1);
-                if ((w0 & 0xffffffff00000000ull) == tag && (w1 & 0xffffffff00000000ull) == tag) break;
-                if ((++spins & 1023u) == 0 && global_timer_ns() - t0 > a.timeout_ns) { ok = false; break; }
-            }
-            if (ok) slots[P.recv_off] = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
-            else atomicCAS(a.err, 0u, a.site + 1u);
-        }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) {
-        double t = 0.0;
-        for (int q = 0; q < world; ++q) t += (q == rank) ? mine : slots[q];
-        *out = t;
-    }
-}
-
 // column relabelling of a row block: global column -> local [owned (permuted) | halo] index through a lookup table:
 // slot_of[c] = halo slot (>= 0) or -1
 __global__ void __launch_bounds__(kBlock)
@@ -183,38 +137,6 @@ int comm_prepare(mg_comm *c, const mg_xfer *x, const double *src, double *dst, E
     if (cpp < 1) cpp = 1;
     a.ctas_per_peer = cpp;
     *grid_out = cpp * x->npeers;
-    return MG_OK;
-}
-
-// stand-alone launch of a site that was booked earlier (comm_prepare) -- the receiving half of a pushed exchange that
-// no SELL kernel could carry
-int comm_launch_prepared(const ExArgs &a, int grid, cudaStream_t st) {
-    if (grid <= 0) return MG_OK;
-    launch_k(exchange_kernel, (unsigned)grid, (unsigned)kBlock, st, a);
-    MG_CHECK_LAUNCH("exchange (prepared)");
-    return MG_OK;
-}
-
-// second stage of the partitioned residual norm + all-reduce as one launch (see norm_allreduce_kernel)
-int comm_norm_allreduce(mg_comm *c, const double *partials, int64_t nblocks, double *local, double *slots, double *out,
-                        cudaStream_t st) {
-    mg_xfer x;
-    memset(&x, 0, sizeof(x));
-    for (int q = 0; q < c->world; ++q) {
-        if (q == c->rank) continue;
-        const int k = x.npeers++;
-        x.peer[k] = q;
-        x.send_cnt[k] = 1;
-        x.recv_off[k] = q;
-        x.recv_cnt[k] = 1;
-    }
-    ExArgs a;
-    int grid = 0;
-    int rc = comm_prepare(c, &x, local, slots, &a, &grid);
-    if (rc) return rc;
-    if (grid == 0) a.dry = 1;                  // a world of one rank: nothing to exchange, the sum is the local value
-    launch_k(norm_allreduce_kernel, 1u, 1024u, st, partials, nblocks, local, a, (int)c->rank, (int)c->world, slots, out);
-    MG_CHECK_LAUNCH("norm_allreduce");
     return MG_OK;
 }
 

@@ -9,10 +9,7 @@
 namespace mgb {
 
 int comm_prepare(mg_comm *, const mg_xfer *, const double *, double *, ExArgs *, int *);
-int comm_launch_prepared(const ExArgs &, int, cudaStream_t);
-int comm_norm_allreduce(mg_comm *, const double *, int64_t, double *, double *, double *, cudaStream_t);
 int g_fused_exchange = 1;
-int g_push_exchange = 0;     // producer-driven colour exchanges (mg_set_push_exchange); off by default
 // Work the multicolour cycle does not have to do (mg_set_cycle_fusion; results are the same bits either way):
 //  * the last colour sweep of the pre-smoothing also writes the residual of its own rows, so the residual pass only
 //    covers the other colours; likewise the last sweep of the post-smoothing on level 0 yields its rows' share of
@@ -52,14 +49,9 @@ int comm_exchange(mg_comm *, const mg_xfer *, const double *, double *, cudaStre
 // Deferred exchange: with multicolour Gauss-Seidel an exchange of a level vector is not launched when it is issued
 // but handed to the next SELL kernel that gathers from that vector, which carries it as extra CTAs (sell_kernel_fused).
 // Anything else that needs the halo first calls flush_pending().
-// A pending exchange whose values were already PUSHED by the kernel that produced them (producer-driven mode) has its
-// site booked: `prepared` holds the receiving half (recv_only) and the number of exchange CTAs.
 struct Pending {
     const mg_xfer *x = nullptr;
     double *vec = nullptr;
-    bool prepared = false;
-    int grid = 0;
-    ExArgs ex;
 };
 static thread_local Pending g_pend;
 
@@ -68,10 +60,6 @@ static int flush_pending(mg_comm *comm, cudaStream_t st) {
     const mg_xfer *x = g_pend.x;
     double *v = g_pend.vec;
     g_pend.x = nullptr;
-    if (g_pend.prepared) {
-        g_pend.prepared = false;
-        return comm_launch_prepared(g_pend.ex, g_pend.grid, st);
-    }
     return comm_exchange(comm, x, v, v, st);
 }
 // issue an exchange of vector v: deferred if allowed, immediate otherwise
@@ -80,7 +68,6 @@ static int issue_exchange(mg_comm *comm, const mg_xfer *x, double *v, bool may_d
     if (!may_defer || !g_fused_exchange) return comm_exchange(comm, x, v, v, st);
     g_pend.x = x;
     g_pend.vec = v;
-    g_pend.prepared = false;
     return MG_OK;
 }
 // before a SELL launch that gathers from `xop` over rows [row0,row1) of M: take the pending exchange along if it is on
@@ -94,13 +81,7 @@ static int take_pending(mg_comm *comm, const double *xop, const mg_sell *M, int6
     double *v = g_pend.vec;
     g_pend.x = nullptr;
     int grid = 0;
-    if (g_pend.prepared) {          // pushed by its producer: the site is booked, only the receiving half is left
-        g_pend.prepared = false;
-        f->ex = g_pend.ex;
-        grid = g_pend.grid;
-    } else {
-        MG_TRY(comm_prepare(comm, x, v, v, &f->ex, &grid));
-    }
+    MG_TRY(comm_prepare(comm, x, v, v, &f->ex, &grid));
     if (grid == 0) return MG_OK;
     f->nex = grid;
     f->mask = mask;
@@ -116,13 +97,6 @@ static inline int64_t vec_len(const mg_level &L) { return L.n + (L.dist ? L.dist
 static inline int halo_all(mg_comm *comm, const mg_level &L, double *v, cudaStream_t st) {
     if (!L.dist) return MG_OK;
     return comm_exchange(comm, L.dist->xfer_all, v, v, st);
-}
-
-// may the colour sweep over rows [r0,r1) of a partitioned level push its own boundary values?
-static inline bool can_push(const mg_level &L, int64_t r0, int64_t r1) {
-    const mg_dist_level *D = L.dist;
-    return g_push_exchange && g_fused_exchange && D && D->h_push_ptr && D->d_push_mask && D->d_push_row && D->d_push_peer &&
-           D->d_push_pos && r1 > r0 && sell_fusable(&L.A, r0, r1);
 }
 
 // What the LAST colour sweep of a smoothing call should produce besides the new values of its rows (multicolour
@@ -196,37 +170,8 @@ static int smooth(mg_comm *comm, const mg_level &L, const mg_cycle_params &P, in
                     SellFuse f;
                     bool use;
                     MG_TRY(take_pending(comm, *cur, &L.A, r0, r1, L.dist->d_mask_A, &f, &use, st));
-                    bool pushed = false;
-                    if (can_push(L, r0, r1)) {
-                        // producer-driven: book this colour's site now (after the carried one, so that sites are
-                        // consumed in the order they were booked); the kernel below stores the boundary values into
-                        // the peers' staging slots itself and the next consumer only polls and unpacks
-                        const mg_dist_level &D = *L.dist;
-                        SellPush push;
-                        int grid = 0;
-                        MG_TRY(comm_prepare(comm, D.xfer_color + c, *cur, *cur, &push.ex, &grid));
-                        if (grid > 0) {
-                            push.mask = D.d_push_mask;
-                            push.rows = D.d_push_row + D.h_push_ptr[c];
-                            push.peer = D.d_push_peer + D.h_push_ptr[c];
-                            push.pos = D.d_push_pos + D.h_push_ptr[c];
-                            push.n = (int32_t)(D.h_push_ptr[c + 1] - D.h_push_ptr[c]);
-                            push.tail_first = D.h_push_tail ? (int32_t)D.h_push_tail[c] : 0;
-                            MG_TRY(sell_gs_rows_push(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, &push, tk, r_out, partials, &nb, st));
-                            g_pend.x = D.xfer_color + c;
-                            g_pend.vec = *cur;
-                            g_pend.prepared = true;
-                            g_pend.grid = grid;
-                            g_pend.ex = push.ex;
-                            g_pend.ex.recv_only = 1;
-                            pushed = true;
-                        }
-                        // grid == 0: no peers on this site, nothing to push or to receive
-                        if (!pushed) MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, tk, r_out, partials, &nb, st));
-                    } else {
-                        MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, tk, r_out, partials, &nb, st));
-                        MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
-                    }
+                    MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, use ? &f : nullptr, tk, r_out, partials, &nb, st));
+                    MG_TRY(issue_exchange(comm, L.dist->xfer_color + c, *cur, true, st));
                 } else {
                     MG_TRY(sell_gs_rows(&L.A, *cur, L.d_b, r0, r1, nullptr, tk, r_out, partials, &nb, st));
                 }
@@ -392,11 +337,6 @@ int mg_set_fused_exchange(int enabled) {
     g_fused_exchange = enabled ? 1 : 0;
     return prev;
 }
-int mg_set_push_exchange(int enabled) {
-    const int prev = g_push_exchange;
-    g_push_exchange = enabled ? 1 : 0;
-    return prev;
-}
 int mg_set_cycle_fusion(int enabled) {
     const int prev = g_cycle_fusion;
     g_cycle_fusion = enabled ? 1 : 0;
@@ -464,14 +404,11 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     const int64_t before = g_launch_count;
     MG_TRY(mg_comm_begin(comm));
     g_pend.x = nullptr;
-    g_pend.prepared = false;
     int rc = MG_OK;
     if (norm) MG_REQUIRE(norm->d_partials && norm->d_local && norm->d_slots && norm->d_norm2, "norm workspace missing");
     const bool after = norm && norm->after && params;
     // second stage of a norm whose per-CTA partials are in norm->d_partials, and its all-reduce
     auto finish_norm = [&](int nblocks) -> int {
-        if (g_push_exchange && comm->world > 1 && nblocks > 0)   // latency mode: one single-CTA kernel
-            return comm_norm_allreduce(comm, norm->d_partials, nblocks, norm->d_local, norm->d_slots, norm->d_norm2, st);
         int r = sell_reduce_partials(norm->d_partials, nblocks, norm->d_local, st);
         if (!r) r = mg_comm_allreduce_sum(comm, norm->d_local, norm->d_slots, norm->d_norm2, stream);
         return r;
@@ -490,7 +427,6 @@ int mg_vcycle_dist(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     }
     if (!rc) rc = flush_pending(comm, st);      // the halo of the iterate is current when the program ends
     g_pend.x = nullptr;
-    g_pend.prepared = false;
     if (!rc) rc = mg_comm_end(comm, stream);
     g_last_cycle_launches = g_launch_count - before;
     return rc;
@@ -528,8 +464,7 @@ int mg_pcg_start(mg_comm *comm, const mg_level *levels, const mg_pcg *pcg, void 
     if (comm) {
         MG_TRY(mg_comm_begin(comm));
         g_pend.x = nullptr;
-        g_pend.prepared = false;
-    }
+        }
     MG_TRY(vec_fill(L.n, 0.0, pcg->d_x, st));
     int nb = 0;
     MG_TRY(vec_dot_partials(L.n, L.d_b, L.d_b, pcg->d_partials, &nb, st));
@@ -548,8 +483,7 @@ int mg_pcg_iterate(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     if (comm) {
         MG_TRY(mg_comm_begin(comm));
         g_pend.x = nullptr;
-        g_pend.prepared = false;
-    }
+        }
     double *r = L.d_b;
     const double *z = r;
     if (params) {                               // z = M^-1 r: one V-cycle on (x, b) = (0, r), z lands in d_x
@@ -576,8 +510,7 @@ int mg_pcg_iterate(mg_comm *comm, const mg_level *levels, int nlevels, const mg_
     if (comm) {
         MG_TRY(flush_pending(comm, st));
         g_pend.x = nullptr;
-        g_pend.prepared = false;
-        MG_TRY(mg_comm_end(comm, stream));
+            MG_TRY(mg_comm_end(comm, stream));
     }
     g_last_cycle_launches = g_launch_count - before;
     return MG_OK;

@@ -36,8 +36,6 @@ struct ExArgs {
     unsigned long long timeout_ns;
     unsigned int site;
     int dry;                            // warm-up launch: do nothing
-    int recv_only;                      // the values were already stored into the peers' staging slots by the kernel
-                                        // that produced them (push_boundary_value below): only poll and unpack
     // fused into a compute kernel: the exchange CTAs count themselves in *done; the last one publishes
     // epoch * 65536 + site + 1 in *ready, which the compute CTAs that read halo columns wait for
     unsigned int *done;
@@ -71,7 +69,7 @@ __device__ __forceinline__ void exchange_role(const ExArgs &a, int bid) {
     const int64_t stride = (int64_t)a.ctas_per_peer * kBlock;
     const int64_t first = (int64_t)chunk * kBlock + threadIdx.x;
     // ---- push: never waits for anybody
-    if (!a.recv_only) {
+    {
         ulonglong2 *out = P.peer_stage + par;
         for (int64_t i = first; i < P.send_cnt; i += stride) {
             const unsigned long long bits =
@@ -109,40 +107,6 @@ __device__ __forceinline__ void exchange_role(const ExArgs &a, int bid) {
         }
     }
     if (timed_out) atomicCAS(a.err, 0u, a.site + 1u);
-}
-
-// Producer-driven variant of the push half (mg_set_push_exchange): the thread that has just computed a boundary value
-// stores it into slot `pos` of peer k's staging area itself -- same packet format, so the receiving side is
-// exchange_role with recv_only set.  The NVLink flight then overlaps the rest of the PRODUCING kernel.
-__device__ __forceinline__ void push_boundary_value(const ExArgs &a, int k, int64_t pos, double value) {
-    const unsigned long long epoch = *a.epoch;
-    const unsigned long long tag = (epoch & 0xffffffffull) << 32;
-    const unsigned long long bits = (unsigned long long)__double_as_longlong(value);
-    st_packet(a.p[k].peer_stage + (int64_t)(epoch & 1ull) * a.parity_stride + pos, (bits & 0xffffffffull) | tag,
-              (bits >> 32) | tag);
-}
-
-// What a colour sweep needs to push its own boundary values (sell_gs_push_kernel): the site booked for this colour and
-// the colour's send table -- entries sorted by local row; entry e says "row rows[e] is packet pos[e] of the message to
-// peer number peer[e] of the site".  mask: per slice of the matrix, 1 if the slice holds a row of ANY colour's table.
-struct SellPush {
-    ExArgs ex;
-    const unsigned char *mask;
-    const int32_t *rows, *peer, *pos;
-    int32_t n;                          // entries of this colour
-    int32_t tail_first;                 // this many CTAs at the END of the launch's row range run first (they hold the
-                                        // boundary rows next to the upper neighbour; the lower ones come first anyway)
-};
-
-__device__ __forceinline__ void push_row_if_listed(const SellPush &P, int64_t row, const double *x) {
-    int lo = 0, hi = P.n;               // lower bound of `row` in the sorted table
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (P.rows[mid] < row) lo = mid + 1; else hi = mid;
-    }
-    if (lo >= P.n || P.rows[lo] != row) return;
-    const double v = x[row];            // the value this thread has just written (or left alone: zero diagonal)
-    for (; lo < P.n && P.rows[lo] == row; ++lo) push_boundary_value(P.ex, P.peer[lo], P.pos[lo], v);
 }
 
 // an exchange site riding on a SELL launch (prepared by comm_prepare)

@@ -28,9 +28,6 @@ int sell_jacobi(const mg_sell *A, const double *dinv, const double *x, const dou
 // values) to r_out, or their squared residuals as per-CTA partial sums (*nblocks of them) -- see sell_gs_tail_ok.
 int sell_gs_rows(const mg_sell *A, double *x, const double *b, int64_t row0, int64_t row1, const SellFuse *fuse,
                  int tail, double *r_out, double *partials, int *nblocks, cudaStream_t st);
-// the same sweep pushing its own boundary values (producer-driven exchange); carry: the previous site, or NULL
-int sell_gs_rows_push(const mg_sell *A, double *x, const double *b, int64_t row0, int64_t row1, const SellFuse *carry,
-                      const SellPush *push, int tail, double *r_out, double *partials, int *nblocks, cudaStream_t st);
 // uo = u + Q e on the rows
 int sell_prolong(const mg_sell *Q, const double *e, const double *u, double *uo, int64_t row0, int64_t row1,
                  const SellFuse *fuse, cudaStream_t st);

@@ -422,30 +422,6 @@ sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, con
     sell_body<MODE, LEN, UNIFORM, true, IMPL, VAL8>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
 }
 
-// Colour sweep of a partitioned level that PUSHES its own boundary values (producer-driven exchange, exchange.cuh):
-// the compute CTAs run the rows next to the upper neighbour first (tail_first), every thread whose row is in the
-// colour's send table stores its new value straight into the peer's staging slot, and the NVLink flight overlaps the
-// interior rows of this very kernel.  CARRY: the launch also carries the previous site as extra CTAs, exactly like
-// sell_kernel_fused.  Same values, same packets, same receiving code (mg_set_push_exchange).
-template <int MODE, int LEN, bool UNIFORM, bool CARRY, bool IMPL, bool VAL8>
-__global__ void __launch_bounds__(kBlock)
-sell_gs_push_kernel(SellArgs A, double *x, const double *__restrict__ b, double *__restrict__ partials, const ExArgs fx,
-                    const unsigned char *__restrict__ mask, const SellPush push) {
-    static_assert(mode_is_gs(MODE), "only colour sweeps push");
-    pdl_prologue();
-    const int nex = CARRY ? fx.npeers * fx.ctas_per_peer : 0;
-    if (CARRY && (int)blockIdx.x < nex) {
-        fused_exchange_cta(fx, (int)blockIdx.x);
-        return;
-    }
-    const int64_t nb = (int64_t)gridDim.x - nex;
-    int64_t bid = (int64_t)blockIdx.x - nex;
-    bid = bid < push.tail_first ? nb - 1 - bid : bid - push.tail_first;
-    sell_body<MODE, LEN, UNIFORM, CARRY, IMPL, VAL8>(A, x, b, nullptr, x, 0.0, partials, bid, &fx, mask);
-    const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
-    if (row >= A.row_begin && row < A.row_end && !push.ex.dry && push.mask[row >> 5]) push_row_if_listed(push, row, x);
-}
-
 // ---- long rows: four warps per slice ---------------------------------------------------------------------------------
 // With 19- / 37-point Galerkin stencils (quasi-L2 transfers) one thread walking a whole row is a chain of dependent
 // (column -> x gather) round trips: ~15 us per launch however small, and half the DRAM rate on large levels.  Here
@@ -724,60 +700,6 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
 #undef MG_SELL_CASE
 #undef MG_SELL_VARIANT
 #undef MG_SELL_LAUNCH
-    MG_CHECK_LAUNCH(name);
-    if (nblocks_out) *nblocks_out = (int)grid;
-    return MG_OK;
-}
-
-// colour sweep that pushes its own boundary values (carry: the previous site riding along, or NULL)
-template <int MODE>
-static int launch_sell_push(const mg_sell *A, double *x, const double *b, int64_t row0, int64_t row1, const SellFuse *carry,
-                            const SellPush *push, double *r_out, double *partials, int *nblocks_out, cudaStream_t st) {
-    const char *name = "sell_gs_rows_push";
-    if (nblocks_out) *nblocks_out = 0;
-    if (!push || !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot push an exchange site");
-    if (mode_is_tail(MODE) && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
-    SellArgs a = sell_args(A, row0, row1, r_out);
-    const int64_t ml = A->max_slice_len;
-    const bool uni = A->uniform_len > 0 && A->uniform_len == ml;
-    const bool impl = sell_use_implied(A, row0, row1);
-    if (impl) sell_pick_spec(A, row0, a);
-    const bool dict = sell_use_dict(A);
-    const int64_t grid = (row1 - a.first_row + kBlock - 1) / kBlock;
-    const int nex = carry ? carry->nex : 0;
-    if (grid + nex > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
-    SellPush p = *push;
-    if (p.tail_first < 0 || p.tail_first > grid / 2) p.tail_first = 0;
-    ExArgs none;
-    memset(&none, 0, sizeof(none));
-    const ExArgs &fx = carry ? carry->ex : none;
-    const unsigned char *mask = carry ? carry->mask : nullptr;
-#define MG_PUSH_LAUNCH(L, U, I, V)                                                                                       \
-    do {                                                                                                                 \
-        if (carry) launch_k(sell_gs_push_kernel<MODE, L, U, true, I, V>, (unsigned)(grid + nex), kBlock, st, a, x, b, partials, fx, mask, p); \
-        else launch_k(sell_gs_push_kernel<MODE, L, U, false, I, V>, (unsigned)grid, kBlock, st, a, x, b, partials, fx, mask, p);              \
-    } while (0)
-#define MG_PUSH_VARIANT(L, V)                             \
-    do {                                                  \
-        if (impl) MG_PUSH_LAUNCH(L, true, true, V);       \
-        else if (uni) MG_PUSH_LAUNCH(L, true, false, V);  \
-        else MG_PUSH_LAUNCH(L, false, false, V);          \
-    } while (0)
-#define MG_PUSH_CASE(L)                                   \
-    case L:                                               \
-        if (dict) MG_PUSH_VARIANT(L, true);               \
-        else MG_PUSH_VARIANT(L, false);                   \
-        break
-    switch (ml) {
-        MG_PUSH_CASE(1); MG_PUSH_CASE(2); MG_PUSH_CASE(3); MG_PUSH_CASE(4);
-        MG_PUSH_CASE(5); MG_PUSH_CASE(6); MG_PUSH_CASE(7); MG_PUSH_CASE(8);
-        default:
-            if constexpr (MODE == GS) MG_PUSH_LAUNCH(0, false, false, false);
-            else return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
-    }
-#undef MG_PUSH_CASE
-#undef MG_PUSH_VARIANT
-#undef MG_PUSH_LAUNCH
     MG_CHECK_LAUNCH(name);
     if (nblocks_out) *nblocks_out = (int)grid;
     return MG_OK;

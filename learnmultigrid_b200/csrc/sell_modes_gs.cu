@@ -1,7 +1,7 @@
 // sell_modes_gs.cu -- the Gauss-Seidel modes of the SELL-32 streaming kernels (sell_core.cuh): plain colour sweep,
 // sweep + residual of the swept rows, sweep + squared residual norm of the swept rows; with or without an exchange
-// site riding along.  (The variants that push the colour's boundary values: sell_modes_push.cu; the tail modes are
-// instantiated in sell_modes_gs_tail.cu -- separate translation units so that they compile in parallel.)
+// site riding along.  (The tail modes are instantiated in sell_modes_gs_tail.cu -- a separate translation unit so that
+// they compile in parallel.)
 #include "sell_core.cuh"
 
 namespace mgb {

@@ -196,11 +196,8 @@ class DistributedHierarchy(DeviceHierarchy):
 
     def __init__(self, A, Q_list, fabric, smoother="jacobi", colors=None, device=None, min_rows_per_rank=65536,
                  n_dist=None, dense_coarse_max=DENSE_COARSE_MAX, keep_host=False, region_bytes=16 << 20,
-                 max_sites=512, timeout_s=10.0, split_coarse_solve=True, bcr_split_min_blocks=32, push_exchange=None):
+                 max_sites=512, timeout_s=10.0, split_coarse_solve=True, bcr_split_min_blocks=32):
         torch = _lib.require_cuda()
-        # producer-driven colour exchanges (mg_set_push_exchange): build the send tables; default from MGB_PUSH_EXCHANGE
-        self.push_exchange = (os.environ.get("MGB_PUSH_EXCHANGE", "0") == "1") if push_exchange is None \
-            else bool(push_exchange)
         self.split_coarse_solve = bool(split_coarse_solve)
         self.bcr_split_min_blocks = int(bcr_split_min_blocks)
         self.torch = torch
@@ -487,30 +484,8 @@ class DistributedHierarchy(DeviceHierarchy):
             d.d_gather_tmp = lev.gather_tmp.data_ptr()
             d.d_gather_self_idx = ip.data_ptr() + 4 * int(oc[rank])
             d.n_gather_own = n_own_c
-        if self.push_exchange and nc:
-            self._build_push_tables(lev, d, peers, sends)
         lev.dist_struct = d
 
-    def _build_push_tables(self, lev, d, peers, sends):
-        """send tables of a partitioned level for producer-driven colour exchanges (partition.push_tables); the library
-        uses them once mg_set_push_exchange(1) has been called"""
-        torch, dev = self.torch, self.device
-        p = lev.plan
-        host = {q: (idx.cpu().numpy(), ptr) for q, (idx, ptr) in sends.items()}
-        pptr, rows, peer, pos, mask, tail = PT.push_tables(p.n_own, p.color_ptr, peers, host, self.rank)
-        lev.push = [torch.from_numpy(a).to(dev) if len(a) else torch.zeros(1, dtype=torch.int32, device=dev)
-                    for a in (rows, peer, pos)]
-        lev.push_mask = torch.from_numpy(mask).to(dev) if len(mask) else torch.zeros(1, dtype=torch.uint8, device=dev)
-        hp = (ctypes.c_int64 * len(pptr))(*[int(v) for v in pptr])
-        ht = (ctypes.c_int64 * max(len(tail), 1))(*[int(v) for v in tail])
-        self._keep += [hp, ht]
-        d.h_push_ptr = ctypes.cast(hp, ctypes.POINTER(ctypes.c_int64))
-        d.h_push_tail = ctypes.cast(ht, ctypes.POINTER(ctypes.c_int64))
-        d.d_push_row, d.d_push_peer, d.d_push_pos = (t.data_ptr() for t in lev.push)
-        d.d_push_mask = lev.push_mask.data_ptr()
-
-    # ------------------------------------------------------------------------------------------------
-    # vectors in and out.  Host vectors are GLOBAL (n0 entries, identical on every rank) or LOCAL (owned block).
     def _host_block(self, host_vec):
         torch = self.torch
         p = self.levels[0].plan

@@ -62,14 +62,13 @@ class StripHierarchy(DistributedHierarchy):
 
     def __init__(self, A_blk, Q_blks, offsets, fabric, n_dist, smoother="jacobi", colors=None, device=None,
                  dense_coarse_max=DENSE_COARSE_MAX, region_bytes=16 << 20, max_sites=512, timeout_s=10.0,
-                 split_coarse_solve=True, bcr_split_min_blocks=32, device_products=True, push_exchange=None):
+                 split_coarse_solve=True, bcr_split_min_blocks=32, device_products=True):
         self._strip_inputs = (A_blk, list(Q_blks), [np.asarray(o, dtype=np.int64) for o in offsets])
         self._device_products = bool(device_products)
         super().__init__(None, [None] * len(Q_blks), fabric, smoother=smoother, colors=colors, device=device,
                          n_dist=n_dist, dense_coarse_max=dense_coarse_max, keep_host=False,
                          region_bytes=region_bytes, max_sites=max_sites, timeout_s=timeout_s,
-                         split_coarse_solve=split_coarse_solve, bcr_split_min_blocks=bcr_split_min_blocks,
-                         push_exchange=push_exchange)
+                         split_coarse_solve=split_coarse_solve, bcr_split_min_blocks=bcr_split_min_blocks)
 
     def _setup_dist(self, A, Q_list, colors, dense_coarse_max, min_rows, n_dist):
         torch, dev = self.torch, self.device

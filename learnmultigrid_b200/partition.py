@@ -133,53 +133,3 @@ def level_external_columns(A, QT, Q_prev, offs, offs_next, offs_prev, rank):
         f0, f1 = int(offs_prev[rank]), int(offs_prev[rank + 1])
         parts.append(external_columns(Q_prev.indptr, Q_prev.indices, f0, f1, o0, o1))
     return np.unique(np.concatenate(parts))
-
-
-def push_tables(n_own, color_ptr, peers, sends, rank, block=256, slice_rows=32):
-    """Send tables for producer-driven colour exchanges (mg_dist_level.h_push_ptr ..., csrc/exchange.cuh SellPush): the
-    kernel that sweeps colour c stores the new value of every listed row straight into the peer's staging slot.
-
-    color_ptr : colour offsets of the owned rows (colour-blocked local numbering), len ncolors + 1
-    peers     : peer ranks of the level's exchange sites, in site order (peer number k = position in this list)
-    sends[q]  : (idx, ptr) -- local rows this rank sends to q in q's halo order and the per-colour offsets into idx
-                (what DistributedHierarchy._build_xfers derives from the plans)
-    Returns (push_ptr int64[nc+1], rows int32, peer int32, pos int32, mask uint8[slices of the operator], tail int64[nc]):
-    colour c owns the entries [push_ptr[c], push_ptr[c+1]), sorted by row; entry e = "row rows[e] is packet pos[e] of the
-    message to peers[peer[e]]"; tail[c] = number of `block`-row CTAs at the end of colour c's launch that hold rows sent
-    to a HIGHER rank (run first; 0 if that would be more than half of the launch)."""
-    nc = len(color_ptr) - 1
-    rows_all, peer_all, pos_all = [], [], []
-    push_ptr = np.zeros(nc + 1, dtype=np.int64)
-    tail = np.zeros(nc, dtype=np.int64)
-    mask = np.zeros((int(n_own) + slice_rows - 1) // slice_rows, dtype=np.uint8)
-    for c in range(nc):
-        rs, ks, ps, up = [], [], [], []
-        for k, q in enumerate(peers):
-            if q not in sends:
-                continue
-            idx, ptr = sends[q]
-            seg = np.asarray(idx[int(ptr[c]):int(ptr[c + 1])], dtype=np.int64)
-            rs.append(seg)
-            ks.append(np.full(len(seg), k, dtype=np.int64))
-            ps.append(np.arange(len(seg), dtype=np.int64))
-            if q > rank:
-                up.append(seg)
-        r = np.concatenate(rs) if rs else np.zeros(0, dtype=np.int64)
-        r0, r1 = int(color_ptr[c]), int(color_ptr[c + 1])
-        if len(r) and (r.min() < r0 or r.max() >= r1):
-            raise ValueError("a row of colour %d's send list lies outside the colour block" % c)
-        order = np.argsort(r, kind="stable")
-        rows_all.append(r[order])
-        peer_all.append((np.concatenate(ks) if ks else r)[order])
-        pos_all.append((np.concatenate(ps) if ps else r)[order])
-        push_ptr[c + 1] = push_ptr[c] + len(r)
-        mask[r // slice_rows] = 1
-        upr = np.concatenate(up) if up else np.zeros(0, dtype=np.int64)
-        if len(upr) and r1 > r0:
-            first_row = r0 - r0 % slice_rows                      # the launch starts at a slice boundary
-            grid = (r1 - first_row + block - 1) // block
-            t = grid - (int(upr.min()) - first_row) // block
-            tail[c] = t if t <= grid // 2 else 0
-    cat = lambda parts: (np.concatenate(parts) if parts else np.zeros(0, dtype=np.int64)).astype(np.int32)
-    return push_ptr, cat(rows_all), cat(peer_all), cat(pos_all), mask, tail
-

@@ -1,7 +1,7 @@
 """GPU tests of distributed_strip.StripHierarchy (partitioned hierarchy built from row blocks only): iterates and
 residual norms bit-identical to the single-GPU hierarchy, local products on the device SpGEMM identical to SciPy's.
 
-Also: producer-driven exchange, device first-fit colouring, implied columns.  First run on a B200 in round 2
+Also: device first-fit colouring, implied columns.  First run on a B200 in round 2
 (profiles/r02_pytest_gpu_unverified_first_run.log: 14 passed); the MGB_UNVERIFIED gate of round 1 is gone."""
 
 import numpy as np
@@ -86,106 +86,6 @@ def test_strip_hierarchy_is_bit_identical_to_the_single_gpu_cycle(torch_mod, smo
             assert np.array_equal(got, want)                           # bit for bit
         np.testing.assert_allclose(norms, want_n, rtol=1e-13)         # blockwise sum of the squares
         assert nnz[0] == [lv.nnz_A for lv in h.levels] and nnz[1] == [lv.nnz_Q for lv in h.levels[:-1]]
-
-
-@pytest.mark.parametrize("world,n_dist,use_graph", [(2, 2, True), (4, 2, True), (3, 1, False), (4, 3, True)])
-def test_producer_driven_exchange_is_bit_identical(torch_mod, world, n_dist, use_graph):
-    """mg_set_push_exchange(1) + send tables (DistributedHierarchy(push_exchange=True)): the colour sweeps store their
-    boundary values into the peers' staging slots themselves; iterates must equal the single-GPU cycle bit for bit,
-    over several programs (epoch parity), eagerly and from the captured graph"""
-    from learnmultigrid_b200 import _lib, formats as F, problems as P
-    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
-    from learnmultigrid_b200.engine import DeviceHierarchy
-    lib = _lib.load()
-    N, levels, nu, cycles = 64, 4, 2, 4
-    A = F.canonical_csr(P.structured_laplacian_2d(N, P.variable_coefficient))
-    Qs = [F.canonical_csr(q) for q in P.structured_hierarchy_2d(N, levels, "linear")]
-    b = P.structured_rhs_2d(N)
-    x0 = np.random.default_rng(5).standard_normal((A.shape[0], 1))
-    h = DeviceHierarchy(A, Qs, smoother="mcgs")
-    h.set_rhs(b)
-    h.set_x(x0)
-    params = h.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
-    want, want_norms = [], []
-    for _ in range(cycles):
-        want_norms.append(h.residual_norm())
-        h.vcycle(params)
-        want.append(h.get_x().copy())
-
-    def body(fab):
-        hd = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h.colors, n_dist=n_dist, region_bytes=1 << 20,
-                                  max_sites=256, timeout_s=30.0, push_exchange=True)
-        assert hd.levels[0].dist_struct.h_push_ptr and hd.levels[0].dist_struct.d_push_mask
-        hd.set_rhs(b)
-        hd.set_x(x0)
-        p = hd.make_params(nu_pre=nu, nu_post=nu, omega=2.0 / 3.0)
-        xs, norms = [], []
-        for _ in range(cycles):
-            hd.vcycle(p, use_graph=use_graph, with_norm=True)       # norm + all-reduce in one kernel in this mode
-            norms.append(hd.last_norm())
-            xs.append(hd.get_x().copy())
-        hd.check()
-        hd.close()
-        return xs, norms
-
-    prev = lib.mg_set_push_exchange(1)
-    try:
-        res = run_virtual_ranks(world, body)
-    finally:
-        lib.mg_set_push_exchange(prev)
-    for xs, norms in res:
-        for got, w in zip(xs, want):
-            assert np.array_equal(got, w)
-        np.testing.assert_allclose(norms, want_norms, rtol=1e-13)
-        assert norms == res[0][1]                                   # identical bits on every rank
-
-
-@pytest.mark.parametrize("world", [2, 3])
-def test_producer_driven_exchange_with_split_bcr_coarsest_level(torch_mod, world):
-    """the split reduction levels of the block-cyclic-reduction coarsest solve push their all-gather messages from the
-    forward / backward kernels (bcr_*_push_kernel): same iterates as the single-GPU cycle, bit for bit"""
-    from learnmultigrid_b200 import _lib, problems as P
-    from learnmultigrid_b200.engine import DeviceHierarchy
-    from learnmultigrid_b200.distributed import DistributedHierarchy, run_virtual_ranks
-    lib = _lib.load()
-    N = 64
-    A = P.structured_laplacian_2d(N)
-    Qs = P.structured_hierarchy_2d(N, 2, transfer="linear")          # coarsest = 33^2 = 1089 unknowns -> BCR
-    rng = np.random.default_rng(0)
-    b, x0 = rng.standard_normal(A.shape[0]), rng.standard_normal(A.shape[0])
-    h1 = DeviceHierarchy(A, Qs, smoother="mcgs", dense_coarse_max=500)
-    assert h1.levels[-1].coarse_kind == 1
-    h1.set_rhs(b)
-    h1.set_x(x0)
-    p1 = h1.make_params(nu_pre=1, nu_post=1)
-    want = []
-    for _ in range(4):
-        h1.vcycle(p1)
-        want.append(h1.get_x().copy())
-
-    def body(fab):
-        h = DistributedHierarchy(A, Qs, fab, smoother="mcgs", colors=h1.colors, n_dist=1, dense_coarse_max=500,
-                                 bcr_split_min_blocks=2, region_bytes=1 << 20, timeout_s=30.0, push_exchange=True)
-        assert h.levels[-1].coarse_bcr_dist is not None
-        h.set_rhs(b)
-        h.set_x(x0)
-        p = h.make_params(nu_pre=1, nu_post=1)
-        got = []
-        for _ in range(4):
-            h.vcycle(p)
-            got.append(h.get_x().copy())
-        h.check()
-        h.close()
-        return got
-
-    prev = lib.mg_set_push_exchange(1)
-    try:
-        res = run_virtual_ranks(world, body)
-    finally:
-        lib.mg_set_push_exchange(prev)
-    for got in res:
-        for g, w in zip(got, want):
-            assert np.array_equal(g, w)
 
 
 def test_device_first_fit_colouring_equals_the_host_helper(torch_mod):

@@ -355,57 +355,3 @@ def test_partitioned_sweeps_on_random_unstructured_graphs(seed, size):
     for p, d in zip(plans, loc):
         got[d["g"][:p.n_own]] = d["x"][:p.n_own]
     assert np.array_equal(got, want)
-
-
-@pytest.mark.parametrize("world,N", [(2, 16), (4, 64), (3, 40), (5, 0), (8, -1)])
-def test_push_tables_reproduce_the_colour_exchange(world, N):
-    """partition.push_tables (send tables of the producer-driven exchange): storing every listed row's value into slot
-    `pos` of the message to peer `peer` fills each message completely, exactly once, with what the receiver's halo
-    expects; the slice mask covers the listed rows; the rows sent to a higher rank lie in the last `tail` CTAs.
-    N <= 0: a random unstructured graph, where a row goes to several peers and every rank neighbours every other"""
-    if N > 0:
-        A = F.canonical_csr(poisson2d(N))
-    else:
-        n = 300 - 60 * N
-        S = sp.random(n, n, density=0.03, random_state=7 - N, format="csr")
-        A = F.canonical_csr(sp.csr_matrix(S + S.T + sp.diags(np.full(n, 9.0))))
-    colors, nc = F.greedy_colors(A)
-    offs, plans = plans_for(A, world, colors)
-    rng = np.random.default_rng(4)
-    xg = rng.standard_normal(A.shape[0])
-    for s in plans:
-        # what DistributedHierarchy._build_xfers derives: who reads which of my rows, in the reader's halo order
-        sends = {}
-        for r in plans:
-            if r.rank != s.rank and s.rank in r.seg:
-                idx, ptr = s.send_indices(r)
-                sends[r.rank] = (idx, [int(v) for v in ptr])
-        peers = sorted(set(s.neighbours) | set(sends))
-        pptr, rows, peer, pos, mask, tail = PT.push_tables(s.n_own, s.color_ptr, peers, sends, s.rank)
-        assert len(pptr) == nc + 1 and pptr[-1] == len(rows) == len(peer) == len(pos)
-        xs = xg[s.gather_indices()]                                   # local vector [own (colour-blocked) | halo]
-        for c in range(nc):
-            e0, e1 = pptr[c], pptr[c + 1]
-            assert np.all(np.diff(rows[e0:e1]) >= 0)                  # sorted by row (binary search in the kernel)
-            assert np.all((rows[e0:e1] >= s.color_ptr[c]) & (rows[e0:e1] < s.color_ptr[c + 1]))
-            assert np.all(mask[rows[e0:e1] // 32] == 1)
-            for k, q in enumerate(peers):
-                if q not in sends:
-                    assert not np.any(peer[e0:e1] == k)
-                    continue
-                idx, ptr = sends[q]
-                cnt = ptr[c + 1] - ptr[c]
-                sel = np.flatnonzero(peer[e0:e1] == k) + e0
-                staged = np.full(cnt, np.nan)
-                staged[pos[sel]] = xs[rows[sel]]                      # what the producing threads store
-                assert len(sel) == cnt and not np.any(np.isnan(staged))
-                r = plans[q]
-                a, b = r.seg_color[(s.rank, c)]
-                assert np.array_equal(staged, xg[r.halo_gid[a:b]])    # what the receiver unpacks into its halo
-            up = [rows[e] for e in range(e0, e1) if peers[peer[e]] > s.rank]
-            if tail[c]:
-                r0, r1 = int(s.color_ptr[c]), int(s.color_ptr[c + 1])
-                first_row = r0 - r0 % 32
-                grid = (r1 - first_row + 255) // 256
-                assert tail[c] <= grid // 2 and min(up) >= first_row + (grid - tail[c]) * 256
-        assert mask.sum() == len(np.unique(rows // 32))

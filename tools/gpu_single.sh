@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2, call G (1 GPU): speculative implied columns, device colouring by default
+# 1-GPU check: GPU tests, bench.py (constant and variable coefficient), ncu launch list of one step with DRAM bytes.
+# Usage: gpurun --timeout 3000 -- 'bash tools/gpu_single.sh'
 set -u
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? $(tail -n 1 gpurun_out/pytest_gpu.log)"
