@@ -45,7 +45,10 @@ def parse_args():
     ap.add_argument("--smoother", default=os.environ.get("MGB_BENCH_SMOOTHER", "GaussSeidel"),
                     choices=["GaussSeidel", "Jacobi"])
     ap.add_argument("--nu", type=int, default=1)
-    ap.add_argument("--coefficient", default="constant", choices=["constant", "variable"])
+    ap.add_argument("--coefficient", default="constant", choices=["constant", "variable", "variable-symmetric"],
+                    help="variable: k = 1 + 0.9 sin(2 pi x) sin(2 pi y) (BASELINE configs[3]); variable-symmetric: the same "
+                         "with the Dirichlet couplings eliminated symmetrically (the operator of the PCG configuration; "
+                         "device generation only)")
     ap.add_argument("--cycles-per-solve", type=int, default=10)
     ap.add_argument("--cpu-n", type=int, default=2048,
                     help="mesh size of the bounded CPU sample (SURVEY 8d: <= 4 M DOF measured, the rest labelled extrapolated)")
@@ -55,6 +58,9 @@ def parse_args():
                          "operators are generated in HBM (problems_device.py) instead of in NumPy + upload")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true",
+                    help="skip config.extra: the variable-coefficient V-cycle (BASELINE configs[3]) and the MG-preconditioned "
+                         "CG solve to 1e-10 (configs[4]) measured in the same run after the headline")
     ap.add_argument("--no-parity-check", action="store_true",
                     help="N > 1: skip the small partitioned-vs-single-GPU bit-identity check run before the benchmark")
     ap.add_argument("--profile-step", action="store_true",
@@ -75,7 +81,8 @@ def parse_args():
 def workload_name(a, n):
     return "2D %s P1 %s %dx%d grid (%d DOF), %d-level V(%d,%d), %s, %s transfers" % (
         "structured" if a.mesh == "structured" else "irregularly refined (unstructured numbering)",
-        "Laplacian" if a.coefficient == "constant" else "variable-coefficient stiffness", n + 1, n + 1,
+        "Laplacian" if a.coefficient == "constant" else "variable-coefficient stiffness" + (
+            " (Dirichlet couplings eliminated symmetrically)" if a.coefficient == "variable-symmetric" else ""), n + 1, n + 1,
         (n + 1) ** 2, a.levels, a.nu, a.nu,
         ("multicolour Gauss-Seidel (greedy colouring)" if a.mesh == "irregular" else
          "multicolour (red-black on the fine level) Gauss-Seidel") if a.smoother == "GaussSeidel" else "damped Jacobi (omega=2/3)",
@@ -188,8 +195,10 @@ def build_problem(a, n):
                        "coarse_nodes": [int(q.shape[1]) for q in nmg.l_hierarchy],
                        "nnz_Q": [int(q.nnz) for q in nmg.l_hierarchy]}
         return pb["A"], pb["rhs"], nmg.l_hierarchy
-    coef = P.variable_coefficient if a.coefficient == "variable" else None
+    coef = None if a.coefficient == "constant" else P.variable_coefficient
     A = P.structured_laplacian_2d(n, coef)
+    if a.coefficient == "variable-symmetric":
+        A = P.symmetric_dirichlet(A, P.boundary_nodes_2d(n))
     rhs = P.structured_rhs_2d(n)
     Qs = P.structured_hierarchy_2d(n, a.levels, transfer=a.transfer)
     return A, rhs, Qs
@@ -310,6 +319,96 @@ def multi_rank_parity(torch, dist, fab, a):
             "iterates_bit_identical": bool(int(t[0].item())), "norms_equal_to_1e-12": bool(int(t[1].item()))}
 
 
+def extra_configs(torch, dist, a, n, Qs, rhs, fab, world, rank):
+    """config.extra: BASELINE configs[3] and [4] on the same grid, same run, same GPU count -- the variable-coefficient
+    operator k = 1 + 0.9 sin(2 pi x) sin(2 pi y) with its Dirichlet couplings eliminated symmetrically: (a) the V-cycle
+    step, (b) hierarchy setup and conjugate gradients preconditioned by one symmetric V(1,1) cycle per iteration down
+    to ||r||_2 <= 1e-10.  Informational: measured after the headline, never allowed to cost it."""
+    from learnmultigrid_b200 import problems_device as PD
+    from learnmultigrid_b200.engine import DeviceHierarchy
+    def build(symmetric):
+        t0 = time.perf_counter()
+        A2 = PD.structured_laplacian_2d(n, PD.variable_coefficient, symmetric=symmetric)
+        torch.cuda.synchronize()
+        t_gen = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        if fab is not None:
+            from learnmultigrid_b200.distributed import DistributedHierarchy
+            hh = DistributedHierarchy(A2, Qs, fab, smoother="mcgs", min_rows_per_rank=a.min_rows_per_rank, timeout_s=30.0)
+        else:
+            hh = DeviceHierarchy(A2, Qs, smoother="mcgs")
+        torch.cuda.synchronize()
+        return hh, t_gen, time.perf_counter() - t0
+
+    h2, t_gen, t_setup = build(False)
+    params = h2.make_params(nu_pre=a.nu, nu_post=a.nu)
+    h2.set_rhs(rhs)
+    h2.zero_x()
+
+    def step():
+        if fab is not None:
+            h2.vcycle(params, norm_after=True)
+        else:
+            h2.vcycle(params, with_norm=True)
+    for _ in range(3):
+        step()
+    h2.zero_x()
+    torch.cuda.synchronize()
+    if fab is not None:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / a.steps
+    if fab is not None:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ndof = (n + 1) ** 2
+    out = {"variable_coefficient_vcycle": {
+        "workload": "BASELINE configs[3]: variable-coefficient stiffness, same grid / levels / smoother",
+        "ms_per_step": ms, "dof_per_s": ndof / (ms * 1e-3),
+        "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2),
+        "setup_phases_s": {k: round(v, 3) for k, v in (getattr(h2, "setup_timing", None) or {}).items()},
+        "value_dictionary_on_A": getattr(h2.levels[0].A, "val_idx", None) is not None}}
+    if fab is not None:
+        h2.close()
+    del h2
+    torch.cuda.empty_cache()
+    h2, t_gen, t_setup = build(True)            # conjugate gradients need the symmetrically eliminated operator
+    psym = h2.make_params(nu_pre=1, nu_post=1, reverse_post=True)
+    pin = torch.from_numpy(np.ascontiguousarray(rhs.reshape(-1))).pin_memory()
+    h2.pcg(pin, psym, error=0.0, max_iterations=2)                      # warm-up: graph capture
+    torch.cuda.synchronize()
+    if fab is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    _, hist, its = h2.pcg(pin, psym, error=1e-10, max_iterations=100, view=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    tm = h2.last_pcg_timing
+    if fab is not None:
+        t = torch.tensor([dt, tm["iterations_s"]], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt, it_s = float(t[0].item()), float(t[1].item())
+        h2.check()
+    else:
+        it_s = tm["iterations_s"]
+    out["mg_preconditioned_cg"] = {
+        "workload": "BASELINE configs[4]: CG preconditioned by one symmetric V(1,1) cycle per iteration to ||r||_2 <= 1e-10, "
+                    "scalars on the device, one CUDA graph per iteration", "iterations": its, "final_residual": hist[-1],
+        "ms_per_iteration": it_s * 1e3 / max(its, 1), "solve_ms": dt * 1e3,
+        "solve_split_ms": {"rhs_host_to_device": tm["transfer_in_s"] * 1e3, "iterations": it_s * 1e3,
+                           "solution_device_to_host": tm["transfer_out_s"] * 1e3},
+        "dof_per_s_to_tolerance": ndof / dt, "hierarchy_setup_s": round(t_setup, 2)}
+    if fab is not None:
+        h2.close()
+    return out
+
+
 # ------------------------------------------------------------------------------------------------------------
 def run_b200(a):
     import torch
@@ -329,7 +428,8 @@ def run_b200(a):
     on_device = a.generate == "device" and a.mesh == "structured" and a.transfer == "linear" and a.setup == "device"
     if on_device:
         from learnmultigrid_b200 import problems as P, problems_device as PD
-        A = PD.structured_laplacian_2d(n, PD.variable_coefficient if a.coefficient == "variable" else None)
+        A = PD.structured_laplacian_2d(n, None if a.coefficient == "constant" else PD.variable_coefficient,
+                                       symmetric=a.coefficient == "variable-symmetric")
         Qs = PD.structured_hierarchy_2d(n, a.levels)
         rhs = P.structured_rhs_2d(n)            # host vector: the end-to-end leg copies it in through the API
         torch.cuda.synchronize()
@@ -340,6 +440,7 @@ def run_b200(a):
     mg.setup = a.setup
     part = world > 1 and a.multi == "partitioned"
     parity = None
+    fab = None
     if part:
         from learnmultigrid_b200.distributed import TorchFabric
         fab = TorchFabric()
@@ -555,6 +656,13 @@ def run_b200(a):
                "api": "learnmultigrid_b200.solvers.Multigrid.SemiGeometricMG.solve (pinned host rhs, host solution"
                       + ("; each rank moves its own row block)" if part else ")")}
 
+    extra = None
+    if not a.no_extra and on_device and a.smoother == "GaussSeidel" and a.coefficient == "constant":
+        try:
+            extra = extra_configs(torch, dist, a, n, Qs, rhs, fab if part else None, world, rank)
+        except Exception as exc:         # pragma: no cover
+            extra = {"error": repr(exc)}
+
     cpu = None
     if not a.no_cpu_baseline and rank == 0:
         v, per, ncyc, tset = cpu_cycle_rate(a, a.cpu_n, reference_style=False)
@@ -576,7 +684,7 @@ def run_b200(a):
                            "generate_s": round(t_gen, 2), "generated_on": "device" if on_device else "host",
                            "setup_s": round(t_setup, 2), "nn_builder": NN_BUILD.get(n),
                            "setup_phases_s": {k: round(v, 3) for k, v in (getattr(h, "setup_timing", None) or {}).items()},
-                           "residual_after_timed_steps": res_after, "multi_rank_parity": parity,
+                           "residual_after_timed_steps": res_after, "multi_rank_parity": parity, "extra": extra,
                            "step": "V-cycle + residual norm of its result (one graph): steady-state outer iteration of "
                                    "Multigrid.solve; cycle fusion %s, implied columns %s"
                                    % ("off" if os.environ.get("MGB_CYCLE_FUSION", "1") == "0" else "on",

@@ -142,7 +142,11 @@ __device__ __forceinline__ void fused_exchange_cta(const ExArgs &a, int bid) {
     }
 }
 
-// compute CTA of a fused launch whose rows read halo columns: wait until the site has been unpacked
+// compute CTA of a fused launch whose rows read halo columns: wait until the site has been unpacked.
+// Scheduling assumption: the exchange CTAs have the LOWEST block indices of the launch and CUDA dispatches the blocks
+// of a grid in index order, so they are resident (or already done) before any compute CTA can spin here; the wait is
+// bounded by timeout_ns all the same, and a time-out is raised by the host (DistributedHierarchy.check, called at the
+// end of every solve), never swallowed.
 __device__ __forceinline__ void fused_wait_ready(const ExArgs &a) {
     if (a.dry) return;
     const unsigned long long want = *a.epoch * 65536ull + a.site + 1ull;

@@ -30,11 +30,15 @@ def variable_coefficient(torch, x, y):
     return 1.0 + 0.9 * torch.sin(2 * np.pi * x) * torch.sin(2 * np.pi * y)
 
 
-def structured_laplacian_2d(N, coefficient=None, Ny=None, device=None):
-    """problems.structured_laplacian_2d as a DevCSR; coefficient: None or a callable (torch, x, y) -> k"""
+def structured_laplacian_2d(N, coefficient=None, Ny=None, device=None, symmetric=False):
+    """problems.structured_laplacian_2d as a DevCSR; coefficient: None or a callable (torch, x, y) -> k.
+    symmetric=True: problems.symmetric_dirichlet of it -- the couplings of interior rows to Dirichlet nodes are dropped
+    (their values are zero, so the solution is unchanged) and the operator is symmetric, as conjugate gradients need."""
     torch = _lib.require_cuda()
     dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     Ny = N if Ny is None else int(Ny)
+    if symmetric:
+        return _symmetric_laplacian_2d(torch, dev, N, coefficient, Ny)
     W, n, i, ix, iy = _grid(torch, dev, N, Ny)
     interior = (ix > 0) & (ix < N) & (iy > 0) & (iy < Ny)
     counts = torch.where(interior, 5, 1)
@@ -72,6 +76,40 @@ def structured_laplacian_2d(N, coefficient=None, Ny=None, device=None):
             indices[base + k] = (r + off).to(torch.int32)
             data[base + k] = v
     return DevCSR((n, n), indptr.to(torch.int32), indices, data)
+
+
+def _symmetric_laplacian_2d(torch, dev, N, coefficient, Ny):
+    """five candidate entries per interior row (south, west, centre, east, north), those that point at a boundary node
+    removed; boundary rows are identity rows.  Entry order inside a row as on the host (ascending column)."""
+    W, n, i, ix, iy = _grid(torch, dev, N, Ny)
+    interior = (ix > 0) & (ix < N) & (iy > 0) & (iy < Ny)
+    h = 1.0 / N
+    x, y = ix.to(torch.float64), iy.to(torch.float64)
+    if coefficient is None:
+        one = torch.ones(n, dtype=torch.float64, device=dev)
+        south = west = east = north = -one
+        diag = 4.0 * one
+    else:
+        def k1(sx, sy):
+            return coefficient(torch, (sx + 2.0 / 3.0) * h, (sy + 1.0 / 3.0) * h)
+
+        def k2(sx, sy):
+            return coefficient(torch, (sx + 1.0 / 3.0) * h, (sy + 2.0 / 3.0) * h)
+        east = -0.5 * (k1(x, y) + k2(x, y - 1))
+        west = -0.5 * (k1(x - 1, y) + k2(x - 1, y - 1))
+        north = -0.5 * (k2(x, y) + k1(x - 1, y))
+        south = -0.5 * (k2(x, y - 1) + k1(x - 1, y - 1))
+        diag = -(east + west + north + south)
+    # keep[k]: candidate k of the row exists -- an interior row keeps a neighbour only if that neighbour is interior
+    keep = torch.stack([interior & (iy - 1 > 0), interior & (ix - 1 > 0), torch.ones_like(interior),
+                        interior & (ix + 1 < N), interior & (iy + 1 < Ny)], dim=1)
+    cols = torch.stack([i - W, i - 1, i, i + 1, i + W], dim=1)
+    vals = torch.stack([south, west, torch.where(interior, diag, torch.ones_like(diag)), east, north], dim=1)
+    indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(keep.sum(dim=1), 0, out=indptr[1:])
+    if int(indptr[-1].item()) >= 2 ** 31:
+        raise OverflowError("nnz does not fit int32")
+    return DevCSR((n, n), indptr.to(torch.int32), cols[keep].to(torch.int32), vals[keep].contiguous())
 
 
 def structured_rhs_2d(N, f_value=-1.0, Ny=None, device=None):

@@ -103,6 +103,8 @@ class Multigrid(IterativeSolver):
                 h.vcycle(params, use_graph=use_graph, with_norm=more)              # :73
             if more:
                 res = h.last_norm()
+        if self.fabric is not None and hasattr(h, "check"):
+            h.check()          # an exchange site that timed out leaves a wrong iterate behind: raise, do not return it
         if self.fabric is not None and getattr(self, "local_solution", False) and hasattr(h, "get_x_local"):
             self.solution = h.get_x_local(view=getattr(self, "pinned_io", False))     # this rank's row block only
         else:

@@ -25,6 +25,15 @@ def test_device_generators_equal_host_generators(N, Ny):
     assert np.array_equal(V_d.indptr, V_h.indptr) and np.array_equal(V_d.indices, V_h.indices)
     np.testing.assert_allclose(V_d.data, V_h.data, rtol=1e-14, atol=1e-15)          # the device's sin(): last bits
     assert np.array_equal(PD.structured_rhs_2d(N, Ny=Ny).cpu().numpy(), P.structured_rhs_2d(N, Ny=Ny).ravel())
+    if Ny is None:                                   # the symmetrically eliminated operator of the PCG configuration
+        S_h = P.symmetric_dirichlet(P.structured_laplacian_2d(N), P.boundary_nodes_2d(N))
+        S_d = _host(PD.structured_laplacian_2d(N, symmetric=True))
+        assert np.array_equal(S_d.indptr, S_h.indptr) and np.array_equal(S_d.indices, S_h.indices)
+        assert np.array_equal(S_d.data, S_h.data)
+        Sv_h = P.symmetric_dirichlet(V_h, P.boundary_nodes_2d(N))
+        Sv_d = _host(PD.structured_laplacian_2d(N, PD.variable_coefficient, symmetric=True))
+        assert np.array_equal(Sv_d.indptr, Sv_h.indptr) and np.array_equal(Sv_d.indices, Sv_h.indices)
+        np.testing.assert_allclose(Sv_d.data, Sv_h.data, rtol=1e-14, atol=1e-15)
     ny = N if Ny is None else Ny
     for q_d, q_h in zip(PD.structured_hierarchy_2d(N, 3, Ny=Ny), P.structured_hierarchy_2d(N, 3, Ny=Ny)):
         q_d = _host(q_d)

@@ -7,8 +7,8 @@ y (domain [0,1] x [0,W]), so the per-GPU work is fixed as the GPU count W grows 
 
 No rank ever forms a global operator: each generates its own rows (problems.structured_laplacian_2d(rows=, Ny=),
 linear_P_2d(rows=, Nyf=)) and the hierarchy is built by distributed_strip.StripHierarchy.  Prints one JSON line in the
-layout of bench.py (`"scaling": "weak"`).  A step = fused residual norm + one V(nu,nu) cycle, CUDA events, max over
-ranks.  UNVERIFIED until StripHierarchy has passed tests/test_gpu_strip.py on a GPU.
+layout of bench.py (`"scaling": "weak"`).  A step = one V(nu,nu) cycle + the residual norm of its result (one graph, as
+in bench.py), CUDA events, max over ranks.
 """
 import argparse
 import json
@@ -80,7 +80,7 @@ def main():
     h.set_rhs(rhs)
     h.zero_x()
     for _ in range(max(a.warmup, 3)):
-        h.vcycle(params, with_norm=True)
+        h.vcycle(params, norm_after=True)
     torch.cuda.synchronize()
     h.zero_x()
     torch.cuda.synchronize()
@@ -88,7 +88,7 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(a.steps):
-        h.vcycle(params, with_norm=True)
+        h.vcycle(params, norm_after=True)
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
@@ -108,7 +108,8 @@ def main():
                                    % ("Laplacian" if coef is None else "variable-coefficient stiffness", W, N, N, ns[0],
                                       L, a.nu, a.nu, a.colors),
                        "levels_rows": ns, "partitioned_levels": n_dist, "generate_s": round(t_gen, 2),
-                       "setup_s": round(t_setup, 2), "residual_after_timed_steps": res},
+                       "setup_s": round(t_setup, 2), "residual_after_timed_steps": res,
+                       "dof_per_gpu": ns[0] // W},
             "roofline": {"bound": "hbm", "cycle": {"algorithmic_bytes": cyc["total"],
                                                    "achieved_gbs_per_gpu": cyc["total"] / W / (ms * 1e-3) / 1e9}},
             "gpu_launches": int(h.last_launches) * a.steps}))
