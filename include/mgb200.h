@@ -97,13 +97,13 @@ typedef struct {
     int64_t uniform_len;        /* > 0: EVERY slice has exactly this many entries per row (= max_slice_len), so
                                    slice offsets are computed, not loaded; 0 = lengths vary, use d_slice_ptr */
     /* optional implied columns (NULL: none): d_slice_rec[s] = id of the offset record of slice s -- every one of its 32
-     * rows has the columns row + d_rec_table[8 * id + j] -- or 255 for a slice that is not regular (a boundary node
+     * rows has the columns row + d_rec_table[8 * id + j] -- or 0xffff for a slice that is not regular (a boundary node
      * among its rows, the ragged tail: the kernels then read its column indices).  Built from mg_sell_slice_offsets by
-     * deduplicating the records (structured levels have a handful).  h_spec_*: optional host-side hints, for launches
+     * deduplicating the records (structured levels have a handful; at most 65534).  h_spec_*: optional host-side hints, for launches
      * over the rows [h_spec_row[k], h_spec_row[k+1]) the record most of those slices use is h_spec_rec[9 * k] (its id)
      * with the offsets h_spec_rec[9 * k + 1 .. 9 * k + 8]; the launch passes it by value and the kernel gathers with
      * it BEFORE the slice's id has arrived (n_spec = 0: record 0, the most frequent one, is assumed). */
-    const unsigned char *d_slice_rec;
+    const uint16_t *d_slice_rec;
     const int32_t *d_rec_table;
     int32_t nrec, n_spec;
     const int64_t *h_spec_row;

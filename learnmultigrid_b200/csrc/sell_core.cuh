@@ -18,7 +18,7 @@ struct SellArgs {
     const int64_t *__restrict__ slice_ptr;
     const int32_t *__restrict__ cols;
     const double *__restrict__ vals;
-    const unsigned char *__restrict__ slice_rec;   // implied columns (IMPL kernels): record id per slice, see below
+    const unsigned short *__restrict__ slice_rec;  // implied columns (IMPL kernels): record id per slice, see below
     const int32_t *__restrict__ rec_table;         // ... [nrec][8] column offsets relative to the row
     int32_t spec_id;                               // the record this launch expects (most of its slices use it)
     int32_t spec_off[8];                           // ... and its offsets, by value
@@ -40,17 +40,17 @@ __host__ __device__ constexpr bool mode_is_tail(int m) { return m == GS_RES || m
 // On a structured stencil level nearly every slice is REGULAR: entry j of every one of its 32 rows has column
 // row + off[j] with ONE offset table for the slice (mg_sell_slice_offsets; formats.sell_slice_offsets is the host twin).
 // For those slices the IMPL kernels compute the columns instead of streaming them.  A structured level has only a
-// handful of DIFFERENT offset tables (one per colour and grid-line parity), so a slice stores one byte -- the id of its
+// handful of DIFFERENT offset tables (one per colour and grid-line parity), so a slice stores two bytes -- the id of its
 // record in a small table -- in place of 128*LEN bytes of column indices: 57 instead of 88 bytes per 5-point row, and
 // the x gathers of a warp become contiguous 256-byte reads.  The launch carries the record most of its slices use BY
 // VALUE: the kernel gathers x with it at once, in the shadow of the load of the slice's id, and only redoes the
-// gathers for the few slices that turn out to use another record (or to be irregular: id 255, columns read from
+// gathers for the few slices that turn out to use another record (or to be irregular: id 0xffff, columns read from
 // memory).  Without that, every thread would pay two dependent DRAM round trips (record, then x).  The values, the gathers and the order of the additions are untouched, so the
 // results are the same bits; slices that are not regular (a boundary node among the rows, the ragged tail) take the
 // ordinary path inside the same kernel.  Uniform matrices with at most 8 entries per row only.
 constexpr int32_t kSliceIrregular = INT32_MIN;
 constexpr int kOffStride = 8;      // ints per offset record (rows of at most 8 entries)
-constexpr int kRecIrregular = 255; // d_slice_rec value of a slice whose columns are not implied
+constexpr int kRecIrregular = 0xffff; // d_slice_rec value of a slice whose columns are not implied
 
 // What the epilogue of a row needs besides the row sum.
 struct SellEp {
@@ -112,7 +112,7 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_
     }
     unsigned rec = 0;
     if (IMPL) {
-        rec = __ldg(A.slice_rec + slice);          // one byte, the same for the whole warp; not waited for yet
+        rec = __ldg(A.slice_rec + slice);          // two bytes, the same for the whole warp; not waited for yet
 #pragma unroll
         for (int j = 0; j < LEN; ++j) cc[j] = min(max((int32_t)row + A.spec_off[j], 0), A.ncols_m1);
     }
@@ -328,15 +328,17 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
 // resident CTAs per SM the compiler has to leave room for: the sweeps with a fused residual keep the row's products
 // alive across the division and take 41-48 registers (5 CTAs) when left alone; capped at 40 (6 CTAs) where ptxas
 // manages that without spilling (build/sell_modes_gs.ptxas.log)
-__host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform) {
-    if (m == GS_NORM) return (len >= 1 && uniform && len <= 5) ? 8 : 1;    // as light as the plain sweep
+__host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform, bool impl) {
+    if (m == GS_NORM || m == GS_RES) { if (len >= 1 && uniform && len <= 5) return 8; }
     if (mode_is_tail(m)) return (len <= 5 || (uniform && len <= 7)) ? 6 : 1;
-    // the plain modes fit 32 registers (full occupancy); the Gauss-Seidel sweep does up to 5 entries per row
-    return (len >= 1 && uniform && len <= (m == GS ? 5 : 7)) ? 8 : 1;
+    // the plain modes fit 32 registers (full occupancy); the Gauss-Seidel sweep and the implied-column kernels (whose
+    // offsets arrive as kernel arguments) do so up to 5 entries per row
+    if (len >= 1 && uniform && len <= ((m == GS || impl) ? 5 : 7)) return 8;
+    return (impl && len <= 7) ? 6 : 1;
 }
 
 template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8>
-__global__ void __launch_bounds__(kBlock, mode_min_ctas(MODE, LEN, UNIFORM))
+__global__ void __launch_bounds__(kBlock, mode_min_ctas(MODE, LEN, UNIFORM, IMPL))
 sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
             double *y, double omega, double *__restrict__ partials) {
     pdl_prologue();
@@ -408,8 +410,14 @@ sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
 // boundary values the previous kernel produced, poll for the peers' packets and unpack them into the halo of x; the
 // compute CTAs whose slice reads halo columns (mask) wait for that, all others start at once.  The exchange latency
 // (NVLink flight + polling) is hidden behind the interior rows, and the site costs no launch of its own.
+// (the launches that also carry an exchange site keep 40 registers for the sweeps with a fused residual: ptxas spills at 32)
+__host__ __device__ constexpr int fused_min_ctas(int m, int len, bool uniform, bool impl) {
+    if (mode_is_tail(m)) return (len <= 5 || (uniform && len <= 7)) ? 6 : 1;
+    return mode_min_ctas(m, len, uniform, impl);
+}
+
 template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, fused_min_ctas(MODE, LEN, UNIFORM, IMPL))
 sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
                   double *__restrict__ partials, const ExArgs fx, const unsigned char *__restrict__ mask) {
     pdl_prologue();

@@ -78,7 +78,7 @@ class DeviceSell:
     def _attach_slice_offsets(self):
         """Implied columns (sell_core.cuh): the per-slice column offsets of a uniform matrix with <= 8 entries per row
         (mg_sell_slice_offsets), deduplicated: a structured level has a handful of distinct offset records, so a slice
-        keeps one byte (the id of its record, 255 = not regular) and the records sit in a small table, most frequent
+        keeps two bytes (the id of its record, 0xffff = not regular) and the records sit in a table, most frequent
         first.  Kept when at least half of the slices are regular (structured stencil levels: ~99 %; unstructured
         numberings: none).  MGB_IMPLIED_COLUMNS=0 switches it off."""
         self.slice_rec = self.rec_table = None
@@ -101,12 +101,12 @@ class DeviceSell:
         off = off.view(nsl, 8)
         regular = off[:, 0] != _lib.SLICE_IRREGULAR
         recs, inverse, counts = torch.unique(off[regular], dim=0, return_inverse=True, return_counts=True)
-        order = torch.argsort(counts, descending=True)[:254]            # ids 0..253 by frequency; 255 = irregular
-        rank_of = torch.full((recs.shape[0],), 255, dtype=torch.int64, device=dev)
+        order = torch.argsort(counts, descending=True)[:32766]          # ids by frequency; -1 (0xffff) = irregular
+        rank_of = torch.full((recs.shape[0],), -1, dtype=torch.int64, device=dev)
         rank_of[order] = torch.arange(order.numel(), device=dev)
-        ids = torch.full((nsl,), 255, dtype=torch.uint8, device=dev)
-        ids[regular] = rank_of[inverse].to(torch.uint8)
-        self.regular_slices = int((ids != 255).sum().item())
+        ids = torch.full((nsl,), -1, dtype=torch.int16, device=dev)     # read as uint16 by the kernels
+        ids[regular] = rank_of[inverse].to(torch.int16)
+        self.regular_slices = int((ids >= 0).sum().item())
         self.slice_rec = ids
         self.rec_table = recs[order].contiguous().to(torch.int32)
         self.struct.d_slice_rec = ids.data_ptr()
@@ -121,7 +121,7 @@ class DeviceSell:
             return None
         import torch
         out = torch.zeros(self.slice_rec.numel(), 8, dtype=torch.int32, device=self.slice_rec.device)
-        reg = self.slice_rec != 255
+        reg = self.slice_rec >= 0
         out[reg] = self.rec_table[self.slice_rec[reg].long()]
         out[~reg, 0] = _lib.SLICE_IRREGULAR
         return out.reshape(-1)
@@ -141,7 +141,7 @@ class DeviceSell:
         for k in range(nb):
             s0, s1 = row_ptr[k] // 32, max((row_ptr[k + 1] + 31) // 32, row_ptr[k] // 32 + 1)
             ids = self.slice_rec[s0:s1]
-            ids = ids[ids != 255]
+            ids = ids[ids >= 0]
             best = int(torch.bincount(ids.long(), minlength=1).argmax().item()) if ids.numel() else 0
             rec[9 * k] = best
             for j in range(8):
@@ -179,7 +179,7 @@ class DeviceSell:
             return self.padded * (4 + vbytes) + (0 if self.uniform_len else self.slice_ptr.numel() * 8)
         per_slice = 32 * self.uniform_len
         irregular = nsl - self.regular_slices
-        return self.padded * vbytes + irregular * per_slice * 4 + nsl
+        return self.padded * vbytes + irregular * per_slice * 4 + 2 * nsl
 
 
 class Level:

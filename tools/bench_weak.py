@@ -3,7 +3,7 @@
 y (domain [0,1] x [0,W]), so the per-GPU work is fixed as the GPU count W grows and the global problem
 ((N+1) x (W N + 1) nodes, 537 M DOF at N = 8192, W = 8) is larger than the replicated setup of bench.py could hold.
 
-    torchrun --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 tools/bench_weak.py --n 8192 --steps 20
+    torchrun --nnodes=1 --nproc-per-node W --master-addr 127.0.0.1 tools/bench_weak.py --cells 8192 --steps 20
 
 No rank ever forms a global operator: each generates its own rows (problems.structured_laplacian_2d(rows=, Ny=),
 linear_P_2d(rows=, Nyf=)) and the hierarchy is built by distributed_strip.StripHierarchy.  Prints one JSON line in the
@@ -24,7 +24,7 @@ sys.path.insert(0, ROOT)
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--n", type=int, default=8192, help="cells per side of one GPU's square")
+    ap.add_argument("--cells", type=int, default=8192, dest="n", help="cells per side of one GPU's square (not --n: torchrun's parser would claim the abbreviation)")
     ap.add_argument("--levels", type=int, default=6)
     ap.add_argument("--nu", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
