@@ -571,7 +571,9 @@ def run_b200(a):
     implied = getattr(lev0.A, "slice_rec", None) is not None and os.environ.get("MGB_IMPLIED_COLUMNS", "1") != "0"
     if os.path.exists(tpath) and world == 1 and lev0.color_ptr is not None:
         t = json.load(open(tpath))
-        if t.get("n") == n and t.get("coefficient") == a.coefficient and bool(t.get("implied_columns")) == implied:
+        vdict = getattr(lev0.A, "val_idx", None) is not None and os.environ.get("MGB_VALUE_DICT", "1") != "0"
+        if (t.get("n") == n and t.get("coefficient") == a.coefficient and bool(t.get("implied_columns")) == implied
+                and bool(t.get("value_dictionary")) == vdict):
             traffic = t["traffic_per_launch"]
             traffic_src = "stored ncu --set full capture (%s), not measured in this run" % t.get("source", tpath)
     per_gpu = world if part else 1
