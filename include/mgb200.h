@@ -85,7 +85,7 @@ int mg_prolong_correct_csr(int64_t n, const int32_t *d_indptr, const int32_t *d_
  * entry k of row r sits at slice_ptr[r/32] + 32*k + r%32.  Entries keep their CSR order; padding entries
  * have value 0.0 and any valid column (the builder repeats the row's last column), so they add an exact
  * zero to every row sum and are ignored by the diagonal detection of the Gauss-Seidel kernel.  The builder pads
- * all slices to the longest one ("uniform") when that costs <= 3 % extra entries (structured grids).      */
+ * all slices to the longest one ("uniform") when that costs <= 3 % extra entries (structured grids), or <= 25 % for rows of one or two entries (linear transfer operators).      */
 typedef struct {
     int64_t nrows;
     int64_t ncols;

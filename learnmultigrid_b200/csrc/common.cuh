@@ -40,6 +40,13 @@ enum SellMode { SPMV = 0, RESID = 1, RESNORM = 2, JACOBI = 3, GS = 4, PROLONG = 
 
 constexpr int kSlice = 32;      // SELL slice height = one warp
 constexpr int kBlock = 256;     // threads per CTA of the streaming kernels
+#ifndef MGB_SELL_BLOCK
+#define MGB_SELL_BLOCK 256
+#endif
+// threads per CTA of the one-row-per-thread SELL kernels without an exchange site (sell_core.cuh: sell_kernel); the
+// occupancy bounds scale with it, so that the SM holds the same 2048 threads in more, smaller CTAs
+constexpr int kSellBlock = MGB_SELL_BLOCK;
+static_assert(kSellBlock >= 64 && kSellBlock <= kBlock && kBlock % kSellBlock == 0, "MGB_SELL_BLOCK: 64, 128 or 256");
 
 // IEEE multiply / add that the compiler may not contract into an FMA: the CPU oracle (gcc
 // -ffp-contract=off, SciPy, PyAMG) rounds the product and the sum separately and we match it bit for bit.
@@ -51,6 +58,61 @@ __device__ __forceinline__ double mul_add_unfused(double acc, double a, double b
 __device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
 __device__ __forceinline__ int32_t ld_stream(const int32_t *p) { return __ldcs(p); }
 __device__ __forceinline__ unsigned char ld_stream(const unsigned char *p) { return __ldcs(p); }
+
+// Bring a line towards the SM without holding a register for it (sell_core.cuh: the row's own vector entries).
+#ifndef MGB_ROW_OPERANDS
+#define MGB_ROW_OPERANDS 1
+#endif
+// how the one-row-per-thread kernels fetch the row's own vector entries (b, u, 1/diag, x of a Jacobi row):
+// 0 = where they are used, 1 = prefetch into L1 under the matrix loads, 2 = prefetch into L2, 3 = load into registers
+constexpr int kRowOperands = MGB_ROW_OPERANDS;
+__device__ __forceinline__ void prefetch_row_operand(const double *p) {
+    if (kRowOperands == 1) asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+    else if (kRowOperands == 2) asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// Value dictionaries in shared memory (sell_core.cuh: STAB): two instructions per lookup instead of five, at the price
+// of an asynchronous table copy and a CTA barrier in every CTA.  Measured on the 8193^2 cycle: 2.70 ms per step against
+// 2.66 ms with the table read through L1 (profiles/r02_variants_*.txt) -- the sweeps are not bound by issue slots
+// alone -- so it is off; -DMGB_SHARED_DICT=1 builds it (tools/build_variant.sh).
+#ifndef MGB_SHARED_DICT
+#define MGB_SHARED_DICT 0
+#endif
+constexpr bool kSharedDict = MGB_SHARED_DICT != 0;
+
+// dictionary index of one entry: the byte zero-extended into a 32-bit register by the load itself (a C++ unsigned char
+// makes the compiler re-mask the index before every table lookup)
+// (these loads are volatile asm: the one-row kernels rely on their loads being ISSUED in program order -- all of a row's
+// DRAM requests before the first wait, sell_core.cuh -- and ptxas otherwise sinks some of them below that wait)
+__device__ __forceinline__ unsigned ld_stream_u8(const unsigned char *p) {
+    unsigned v;
+    asm volatile("ld.global.cs.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ unsigned ld_const_u16(const unsigned short *p) {
+    unsigned v;
+    asm volatile("ld.global.nc.u16 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+// x[col], issued here
+__device__ __forceinline__ double ld_gather(const double *x, int32_t col) {
+    double v;
+    asm volatile("ld.global.f64 %0, [%1];" : "=d"(v) : "l"(x + col));
+    return v;
+}
+// x[col] unless col == skip (a Gauss-Seidel row's own entry): +0.0 then, and no memory access
+__device__ __forceinline__ double ld_gather_skip(const double *x, int32_t col, int32_t skip) {
+    double v;
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, %3;\n\tmov.f64 %0, 0d0000000000000000;\n\t@p ld.global.f64 %0, [%1];\n\t}"
+                 : "=d"(v) : "l"(x + col), "r"(col), "r"(skip));
+    return v;
+}
+// asynchronous 8-byte copy global -> shared (no register, no stall at the point of issue)
+__device__ __forceinline__ void cp_async8(void *smem, const void *gmem) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- programmatic dependent launch (PDL) --------------------------------------------------------------------------
 // The V-cycle is a long chain of short dependent kernels (60-150 per cycle, many of a few microseconds on the coarse

@@ -22,7 +22,7 @@ struct SellArgs {
     const int32_t *__restrict__ rec_table;         // ... [nrec][8] column offsets relative to the row
     int32_t spec_id;                               // the record this launch expects (most of its slices use it)
     int32_t spec_off[8];                           // ... and its offsets, by value
-    int32_t ncols_m1;                              // clamp for the speculative gathers
+    int32_t spec_lo, spec_hi;                      // rows in [lo, hi] keep every row + spec_off[j] inside the vector
     const unsigned char *__restrict__ vidx;  // value dictionary (VAL8 kernels): one byte per entry, laid out like vals
     const double *__restrict__ vtab;         // ... indexing this table of at most 256 doubles
     int64_t row_begin;   // first row this launch touches
@@ -81,25 +81,51 @@ struct RowOut {
 
 // VAL8: the values come from the matrix' dictionary (valdict.cu): one byte per entry from DRAM, the double from a
 // 2 KB table that stays in L1 -- the same doubles, 7 bytes per entry less.
-template <int MODE, int LEN, bool PRED, bool IMPL, bool VAL8>
+template <int MODE, int LEN, bool PRED, bool IMPL, bool VAL8, bool STAB>
 __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_t slice, int len, const double *x,
-                                          int64_t row, bool active, const SellEp &E, double &contrib,
-                                          unsigned char halo_wait, const ExArgs *fx, RowOut &out) {
+                                          int32_t row, bool active, const SellEp &E, double &contrib,
+                                          unsigned char halo_wait, const ExArgs *fx, RowOut &out, double *stab) {
     const int32_t *__restrict__ c = A.cols + ent;
     const double *__restrict__ v = A.vals + ent;
     const unsigned char *__restrict__ vi = A.vidx + ent;
+    // STAB: the CTA keeps the value dictionary in shared memory (two instructions per lookup instead of five: the
+    // sweeps are bound by instruction issue, ncu: 68-76 % issue-slot utilisation at 4 of 7 TB/s).  Every thread starts
+    // the asynchronous copy of one table entry now and waits for it after its own loads have been issued.
+    if (STAB) cp_async8(stab + threadIdx.x, A.vtab + threadIdx.x);
+    // The row's own vector entries (right-hand side, u of a prolongation, Jacobi's x and 1/diag, the dot product's
+    // partner) are asked for HERE, under the matrix loads.  Left to their point of use -- after the gathers have been
+    // consumed -- each is a second dependent DRAM round trip per thread (cuobjdump showed the load of b behind the last
+    // gather).  A prefetch holds no register (the sweeps sit at the 32-register limit of full occupancy; loading b early
+    // spilled it straight back to local memory), the load at the point of use then hits L1.  PROLONG rows are short and
+    // have registers to spare: their u is loaded.
+    constexpr bool kUsesB = MODE == RESID || MODE == RESNORM || MODE == JACOBI || mode_is_gs(MODE);
+    constexpr bool kUsesAux = MODE == JACOBI || MODE == SPMV_DOT;
+    constexpr bool kEarly = kRowOperands == 3;
+    double bv = 0.0, av = 0.0, xr = 0.0;
+    if (active) {
+        if (MODE == PROLONG) av = E.aux[row];
+        if (kEarly) {
+            if (kUsesB) bv = E.b[row];
+            if (kUsesAux) av = E.aux[row];
+            if (MODE == JACOBI) xr = x[row];
+        } else {
+            if (kUsesB) prefetch_row_operand(E.b + row);
+            if (kUsesAux) prefetch_row_operand(E.aux + row);
+            if (MODE == JACOBI) prefetch_row_operand(x + row);
+        }
+    }
     int32_t cc[LEN];
     double vv[LEN], xx[LEN];
+    unsigned ii[VAL8 ? LEN : 1];
     if (VAL8) {
-        unsigned char ii[LEN];
 #pragma unroll
         for (int j = 0; j < LEN; ++j)
-            if (!PRED || j < len) ii[j] = ld_stream(vi + j * kSlice);
+            if (!PRED || j < len) ii[j] = ld_stream_u8(vi + j * kSlice);
 #pragma unroll
         for (int j = 0; j < LEN; ++j)
             if (!PRED || j < len) {
                 if (!IMPL) cc[j] = ld_stream(c + j * kSlice);
-                vv[j] = __ldg(A.vtab + ii[j]);
+                if (!STAB) vv[j] = __ldg(A.vtab + ii[j]);
             }
     } else {
 #pragma unroll
@@ -112,19 +138,28 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_
     }
     unsigned rec = 0;
     if (IMPL) {
-        rec = __ldg(A.slice_rec + slice);          // two bytes, the same for the whole warp; not waited for yet
+        rec = ld_const_u16(A.slice_rec + slice);   // two bytes, the same for the whole warp; not waited for yet
+        // speculative columns: the expected record applied to the row, which is clamped ONCE so that every column stays
+        // inside the vector (a slice that really uses the record has all its rows inside [lo, hi]: the clamp is the
+        // identity there; any other slice redoes its gathers below)
+        const int32_t rs = min(max(row, A.spec_lo), A.spec_hi);
 #pragma unroll
-        for (int j = 0; j < LEN; ++j) cc[j] = min(max((int32_t)row + A.spec_off[j], 0), A.ncols_m1);
+        for (int j = 0; j < LEN; ++j) cc[j] = rs + A.spec_off[j];
     }
-    // prolongation rows are short (few bytes in flight per thread, registers to spare): fetch u under the matrix loads
-    double av = 0.0;
-    if (MODE == PROLONG && active) av = E.aux[row];
     if (halo_wait) fused_wait_ready(*fx);
     // A Gauss-Seidel row never uses its own old value (the diagonal entry divides, and a row that is not updated has a
     // zero there): no gather for it -- 8 bytes per row of DRAM reads less (ncu: 65 -> 57 B per 5-point row)
 #pragma unroll
     for (int j = 0; j < LEN; ++j)
-        if (!PRED || j < len) xx[j] = (mode_is_gs(MODE) && cc[j] == (int32_t)row) ? 0.0 : x[cc[j]];
+        if (!PRED || j < len) xx[j] = mode_is_gs(MODE) ? ld_gather_skip(x, cc[j], row) : ld_gather(x, cc[j]);
+    if (STAB) {
+        // everything this row reads from DRAM is in flight: wait for the table entry, meet the other warps, look the values up
+        cp_async_wait_all();
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < LEN; ++j)
+            if (!PRED || j < len) vv[j] = stab[ii[j]];
+    }
     if (IMPL && rec != (unsigned)A.spec_id) {      // warp-uniform and rare: this slice uses another record, or none
         if (rec == (unsigned)kRecIrregular) {
 #pragma unroll
@@ -132,53 +167,61 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_
         } else {
             const int32_t *__restrict__ o = A.rec_table + rec * kOffStride;
 #pragma unroll
-            for (int j = 0; j < LEN; ++j) cc[j] = (int32_t)row + __ldg(o + j);
+            for (int j = 0; j < LEN; ++j) cc[j] = row + __ldg(o + j);
         }
 #pragma unroll
-        for (int j = 0; j < LEN; ++j) xx[j] = (mode_is_gs(MODE) && cc[j] == (int32_t)row) ? 0.0 : x[cc[j]];
+        for (int j = 0; j < LEN; ++j) xx[j] = (mode_is_gs(MODE) && cc[j] == row) ? 0.0 : x[cc[j]];
     }
-    double sum = 0.0, diag = 0.0;
-    // GS_RES / GS_NORM keep the separately rounded products (the VALUE for a diagonal entry, flagged in dmask) instead
-    // of the row itself: 2 registers per entry across the division instead of 5
+    double sum = 0.0;
+    // GS_RES keeps the separately rounded products (the slot of the diagonal entry flagged in dmask) instead of the row
+    // itself: 2 registers per entry across the division instead of 5.
+    // Gauss-Seidel family, branch-free: the diagonal entry was "gathered" as +0.0, so its product is an exact zero, and
+    // adding a zero never changes a sum that started at +0.0 (such a sum is never -0.0): the sum has the bits of the
+    // oracle's, which skips the entry.  The diagonal VALUE is collected by OR-ing bit patterns: a row has one stored
+    // diagonal entry; padding that repeats its column carries +0.0, i.e. no bits (the old test `value != 0`).
     double pp[MODE == GS_RES ? LEN : 1];
     unsigned dmask = 0;
+    unsigned long long dbits = 0ull;
 #pragma unroll
     for (int j = 0; j < LEN; ++j) {
         if (!PRED || j < len) {
-            if (MODE == GS || MODE == GS_NORM) {
-                if (cc[j] == (int32_t)row) { if (vv[j] != 0.0) diag = vv[j]; } else sum = mul_add_unfused(sum, vv[j], xx[j]);
-            } else if (MODE == GS_RES) {
-                if (cc[j] == (int32_t)row) {
-                    if (vv[j] != 0.0) diag = vv[j];
-                    pp[j] = vv[j];
-                    dmask |= 1u << j;
-                } else {
-                    pp[j] = __dmul_rn(vv[j], xx[j]);
-                    sum = __dadd_rn(sum, pp[j]);
+            if (mode_is_gs(MODE)) {
+                const bool is_d = cc[j] == row;
+                const double p = __dmul_rn(vv[j], xx[j]);
+                sum = __dadd_rn(sum, p);
+                dbits |= is_d ? (unsigned long long)__double_as_longlong(vv[j]) : 0ull;
+                if (MODE == GS_RES) {
+                    pp[j] = p;
+                    dmask |= (is_d && vv[j] != 0.0) ? (1u << j) : 0u;
                 }
             } else {
                 sum = mul_add_unfused(sum, vv[j], xx[j]);
             }
         }
     }
+    const double diag = __longlong_as_double((long long)dbits);
     if (!active) return;
+    if (!kEarly) {
+        if (kUsesB) bv = E.b[row];
+        if (kUsesAux) av = E.aux[row];
+        if (MODE == JACOBI) xr = x[row];
+    }
     if (MODE == SPMV) {
         E.y[row] = sum;
     } else if (MODE == SPMV_DOT) {
         E.y[row] = sum;
-        contrib = E.aux[row] * sum;
+        contrib = av * sum;
     } else if (MODE == RESID) {
-        E.y[row] = __dsub_rn(E.b[row], sum);
+        E.y[row] = __dsub_rn(bv, sum);
     } else if (MODE == RESNORM) {
-        const double r = __dsub_rn(E.b[row], sum);
+        const double r = __dsub_rn(bv, sum);
         contrib = r * r;
     } else if (MODE == JACOBI) {
-        const double r = __dsub_rn(E.b[row], sum);
-        E.y[row] = __dadd_rn(x[row], __dmul_rn(E.omega, __dmul_rn(E.aux[row], r)));
+        const double r = __dsub_rn(bv, sum);
+        E.y[row] = __dadd_rn(xr, __dmul_rn(E.omega, __dmul_rn(av, r)));
     } else if (MODE == PROLONG) {
         E.y[row] = __dadd_rn(av, sum);   // aux = u (may alias y)
     } else {                             // Gauss-Seidel family
-        const double bv = E.b[row];
         const bool upd = diag != 0.0;
         double xn = 0.0;
         if (upd) {
@@ -196,10 +239,11 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_
             // zero: xn is 0 then and the term an exact zero, which changes nothing (a sum that starts at +0 never
             // becomes -0).  These are the bits of the residual pass: the restriction reads them.
             double s2 = 0.0;
+            const double dx = __dmul_rn(diag, xn);
 #pragma unroll
             for (int j = 0; j < LEN; ++j)
                 if (!PRED || j < len) {
-                    const double t = ((dmask >> j) & 1u) ? __dmul_rn(pp[j], xn) : pp[j];
+                    const double t = ((dmask >> j) & 1u) ? dx : pp[j];
                     s2 = __dadd_rn(s2, t);
                 }
             A.r_out[row] = __dsub_rn(bv, s2);
@@ -255,13 +299,23 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
     static_assert(!IMPL || (UNIFORM && LEN > 0), "implied columns need a uniform matrix with short rows");
     static_assert(LEN > 0 || !mode_is_tail(MODE), "fused residual modes need the row in registers");
     static_assert(!VAL8 || LEN > 0, "the value dictionary is for short rows");
-    const int64_t row = A.first_row + bid * kBlock + threadIdx.x;
-    const bool active = row >= A.row_begin && row < A.row_end;
+    constexpr int BLK = FUSED ? kBlock : kSellBlock;
+    // the value dictionary sits in shared memory when every warp of the CTA takes the same path to the barrier that
+    // publishes it (uniform matrices) and the CTA has one thread per table entry
+    constexpr bool STAB = kSharedDict && VAL8 && UNIFORM && LEN > 0 && BLK == 256;
+    __shared__ double stab[STAB ? 256 : 1];
+    // rows are 32-bit here (the launcher refuses matrices of 2^31 rows or more; column indices are int32 anyway): one
+    // instruction per address instead of four
+    const int32_t raw_row = (int32_t)A.first_row + (int32_t)bid * BLK + (int32_t)threadIdx.x;
+    const int32_t row_end = (int32_t)A.row_end;
+    const bool active = raw_row >= (int32_t)A.row_begin && raw_row < row_end;
+    // a CTA that shares a table meets at a barrier: its threads past the end redo the last row without storing
+    const int32_t row = STAB ? min(raw_row, row_end - 1) : raw_row;
     double contrib = 0.0;
     RowOut out{0.0, false};
-    if (row < A.row_end) {   // warp-uniform except in the last slice
+    if (row < row_end) {   // warp-uniform except in the last slice
         const int64_t slice = row >> 5;
-        const int lane = (int)(row & 31);
+        const int lane = row & 31;
         unsigned char hw = 0;      // fused launch: does this slice read halo columns? (load issued now, used later)
         if (FUSED) hw = mask ? mask[slice] : 1;
         int64_t base;
@@ -279,14 +333,19 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
             constexpr int L = LEN > 0 ? LEN : 1;
             const SellEp E{b, aux, y, omega};
             if (IMPL) {
-                short_row<MODE, L, false, true, VAL8>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, false, true, VAL8, STAB>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out, stab);
             } else if (UNIFORM || len == L) {
-                short_row<MODE, L, false, false, VAL8>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, false, false, VAL8, STAB>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out, stab);
             } else {
-                short_row<MODE, L, true, false, VAL8>(A, base + lane, slice, len, x, row, active, E, contrib, hw, fx, out);
+                short_row<MODE, L, true, false, VAL8, false>(A, base + lane, slice, len, x, row, active, E, contrib, hw, fx, out, stab);
             }
         } else {
             double sum = 0.0, diag = 0.0;
+            // the row's own vector entries first (see short_row): not one more round trip behind the last chunk
+            double bv = 0.0, av = 0.0, xr = 0.0;
+            if ((MODE == RESID || MODE == RESNORM || MODE == JACOBI || MODE == GS) && active) bv = b[row];
+            if ((MODE == PROLONG || MODE == JACOBI || MODE == SPMV_DOT) && active) av = aux[row];
+            if (MODE == JACOBI && active) xr = x[row];
             int k = 0;
             for (; k + 4 <= len; k += 4) {
                 row_chunk<MODE, 4>(c + k * kSlice, v + k * kSlice, x, row, sum, diag, hw, fx);
@@ -301,26 +360,26 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
                     y[row] = sum;
                 } else if (MODE == SPMV_DOT) {
                     y[row] = sum;
-                    contrib = aux[row] * sum;
+                    contrib = av * sum;
                 } else if (MODE == RESID) {
-                    y[row] = __dsub_rn(b[row], sum);
+                    y[row] = __dsub_rn(bv, sum);
                 } else if (MODE == RESNORM) {
-                    const double r = __dsub_rn(b[row], sum);
+                    const double r = __dsub_rn(bv, sum);
                     contrib = r * r;
                 } else if (MODE == JACOBI) {
-                    const double r = __dsub_rn(b[row], sum);
-                    y[row] = __dadd_rn(x[row], __dmul_rn(omega, __dmul_rn(aux[row], r)));
+                    const double r = __dsub_rn(bv, sum);
+                    y[row] = __dadd_rn(xr, __dmul_rn(omega, __dmul_rn(av, r)));
                 } else if (MODE == GS) {
-                    if (diag != 0.0) y[row] = __ddiv_rn(__dsub_rn(b[row], sum), diag);
+                    if (diag != 0.0) y[row] = __ddiv_rn(__dsub_rn(bv, sum), diag);
                 } else if (MODE == PROLONG) {
-                    y[row] = __dadd_rn(aux[row], sum);   // aux = u (may alias y)
+                    y[row] = __dadd_rn(av, sum);   // aux = u (may alias y)
                 }
             }
         }
     }
     if (MODE == GS_NORM && out.store) y[row] = out.xn;
     if (mode_has_partials(MODE)) {
-        const double s = block_sum_last<kBlock>(contrib);
+        const double s = block_sum_last<BLK>(contrib);
         if (threadIdx.x == 0) partials[bid] = s;
     }
 }
@@ -338,7 +397,7 @@ __host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform, bo
 }
 
 template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8>
-__global__ void __launch_bounds__(kBlock, mode_min_ctas(MODE, LEN, UNIFORM, IMPL))
+__global__ void __launch_bounds__(kSellBlock, mode_min_ctas(MODE, LEN, UNIFORM, IMPL) * (kBlock / kSellBlock))
 sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
             double *y, double omega, double *__restrict__ partials) {
     pdl_prologue();
@@ -349,7 +408,9 @@ sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const dou
 // flight behind a chain of three dependent loads (slice pointer -> column -> vector entry), and the prolongation runs at
 // 5.4 instead of 6.8 TB/s (ncu, profiles/r02_ncu_step_sell_kernels.txt).  Here a thread takes R rows, 256 apart, and
 // issues every load of a stage for all of them before the first use.  SpMV and prolongation, LEN <= 2, no exchange site.
-template <int MODE, int LEN, int R, bool VAL8>
+// UNIFORM: every slice holds exactly LEN entries per row (transfer operators are padded to that when it costs at most a
+// quarter more entries, mg_sell_layout), so the slice pointer -- the first of the three round trips -- is computed.
+template <int MODE, int LEN, int R, bool VAL8, bool UNIFORM>
 __global__ void __launch_bounds__(kBlock)
 sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
     static_assert(MODE == SPMV || MODE == PROLONG, "short-row kernel: SpMV and prolongation only");
@@ -365,9 +426,14 @@ sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
         len[r] = 0;
         if (row[r] < A.row_end) {
             const int64_t sl = row[r] >> 5;
-            const int64_t p0 = A.slice_ptr[sl], p1 = A.slice_ptr[sl + 1];
-            base[r] = p0 + (row[r] & 31);
-            len[r] = (int)((p1 - p0) >> 5);
+            if (UNIFORM) {
+                base[r] = sl * (int64_t)(kSlice * LEN) + (row[r] & 31);
+                len[r] = LEN;
+            } else {
+                const int64_t p0 = A.slice_ptr[sl], p1 = A.slice_ptr[sl + 1];
+                base[r] = p0 + (row[r] & 31);
+                len[r] = (int)((p1 - p0) >> 5);
+            }
         }
     }
     int32_t cc[R][LEN];
@@ -585,7 +651,8 @@ inline SellArgs sell_args(const mg_sell *A, int64_t row0, int64_t row1, double *
     a.rec_table = A->d_rec_table;
     a.spec_id = 0;
     for (int j = 0; j < 8; ++j) a.spec_off[j] = 0;
-    a.ncols_m1 = (int32_t)(A->ncols > 0 ? A->ncols - 1 : 0);
+    a.spec_lo = 0;
+    a.spec_hi = (int32_t)(A->ncols > 0 ? A->ncols - 1 : 0);
     a.vidx = A->d_val_idx;
     a.vtab = A->d_val_table;
     a.row_begin = row0;
@@ -611,8 +678,19 @@ inline void sell_pick_spec(const mg_sell *A, int64_t row0, SellArgs &a) {
     a.spec_id = -1;
     for (int k = 0; k < A->n_spec && A->h_spec_row && A->h_spec_rec; ++k)
         if (row0 >= A->h_spec_row[k] && row0 < A->h_spec_row[k + 1]) {
+            // rows in [lo, hi] keep row + off[j] inside [0, ncols) for every j; the kernel clamps the row to that range
+            int64_t omin = 0, omax = 0;
+            for (int j = 0; j < 8; ++j) {
+                const int64_t o = A->h_spec_rec[9 * k + 1 + j];
+                if (o < omin) omin = o;
+                if (o > omax) omax = o;
+            }
+            const int64_t lo = -omin, hi = A->ncols - 1 - omax;
+            if (hi < lo) return;                      // a matrix smaller than its stencil: no speculation
             a.spec_id = A->h_spec_rec[9 * k];
             for (int j = 0; j < 8; ++j) a.spec_off[j] = A->h_spec_rec[9 * k + 1 + j];
+            a.spec_lo = (int32_t)lo;
+            a.spec_hi = (int32_t)hi;
             return;
         }
 }
@@ -625,6 +703,7 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     if (nblocks_out) *nblocks_out = 0;
     if (fuse && !sell_fusable(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "this launch cannot carry an exchange site");
     if (row1 <= row0) return MG_OK;
+    if (A->nrows > 0x7fffffffLL || A->ncols > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "2^31 rows or more");
     if (mode_is_tail(MODE) && !sell_gs_tail_ok(A, row0, row1)) return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
     if constexpr (MODE <= PROLONG) {
         if (g_tma_min_rows > 0 && row1 - row0 >= g_tma_min_rows && A->max_slice_len > 0) {
@@ -655,17 +734,20 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
         if (nblocks_out) *nblocks_out = (int)wgrid;
         return MG_OK;
     }
-    const int64_t grid = (nthreads + kBlock - 1) / kBlock;
+    const int blk = fuse ? kBlock : kSellBlock;     // threads per CTA of the one-row-per-thread kernels
+    const int64_t grid = (nthreads + blk - 1) / blk;
     if (grid + (fuse ? fuse->nex : 0) > 0x7fffffffLL) return set_error(MG_ERR_OVERFLOW, name, "grid too large");
     if constexpr (MODE == SPMV || MODE == PROLONG) {
-        if (!fuse && ml >= 1 && ml <= 2 && g_short_rows_per_thread > 1 && row1 - row0 >= g_short_min_rows && A->d_slice_ptr) {
+        if (!fuse && ml >= 1 && ml <= 2 && g_short_rows_per_thread > 1 && row1 - row0 >= g_short_min_rows && (uni || A->d_slice_ptr)) {
             const int R = g_short_rows_per_thread >= 4 ? 4 : 2;
-            const unsigned sg = (unsigned)((grid + R - 1) / R);
+            const unsigned sg = (unsigned)(((nthreads + kBlock - 1) / kBlock + R - 1) / R);
             const bool dict = sell_use_dict(A);
-#define MG_SHORT(L, RR)                                                                          \
-    do {                                                                                         \
-        if (dict) launch_k(sell_short_kernel<MODE, L, RR, true>, sg, kBlock, st, a, x, aux, y);  \
-        else launch_k(sell_short_kernel<MODE, L, RR, false>, sg, kBlock, st, a, x, aux, y);      \
+#define MG_SHORT(L, RR)                                                                                 \
+    do {                                                                                                \
+        if (dict && uni) launch_k(sell_short_kernel<MODE, L, RR, true, true>, sg, kBlock, st, a, x, aux, y);    \
+        else if (dict) launch_k(sell_short_kernel<MODE, L, RR, true, false>, sg, kBlock, st, a, x, aux, y);    \
+        else if (uni) launch_k(sell_short_kernel<MODE, L, RR, false, true>, sg, kBlock, st, a, x, aux, y);     \
+        else launch_k(sell_short_kernel<MODE, L, RR, false, false>, sg, kBlock, st, a, x, aux, y);             \
     } while (0)
             if (ml == 1) {
                 if (R == 4) MG_SHORT(1, 4);
@@ -685,7 +767,7 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
 #define MG_SELL_LAUNCH(L, U, I, V)                                                                                       \
     do {                                                                                                                 \
         if (fuse) launch_k(sell_kernel_fused<MODE, L, U, I, V>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
-        else launch_k(sell_kernel<MODE, L, U, I, V>, (unsigned)grid, kBlock, st, a, x, b, aux, y, omega, partials);      \
+        else launch_k(sell_kernel<MODE, L, U, I, V>, (unsigned)grid, kSellBlock, st, a, x, b, aux, y, omega, partials);  \
     } while (0)
 #define MG_SELL_VARIANT(L, V)                             \
     do {                                                  \

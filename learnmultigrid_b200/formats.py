@@ -75,8 +75,9 @@ def transpose_csr(Q):
 
 
 def sell_is_uniform(max_len, sum_len, nslices):
-    """pad all slices to the longest one when that costs at most 3 % extra entries (same rule as mg_sell_layout)"""
-    return max_len > 0 and nslices * max_len * 100 <= 103 * sum_len
+    """pad all slices to the longest one when that costs at most 3 % extra entries -- 25 % for rows of one or two
+    entries, whose kernel then needs no slice pointer (same rule as mg_sell_layout)"""
+    return max_len > 0 and nslices * max_len * 100 <= (125 if max_len <= 2 else 103) * sum_len
 
 
 def csr_to_sell(A):
