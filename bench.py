@@ -373,6 +373,7 @@ def extra_configs(torch, dist, a, n, Qs, rhs, fab, world, rank):
         "ms_per_step": ms, "dof_per_s": ndof / (ms * 1e-3),
         "generate_s": round(t_gen, 2), "setup_s": round(t_setup, 2),
         "setup_phases_s": {k: round(v, 3) for k, v in (getattr(h2, "setup_timing", None) or {}).items()},
+        "setup_galerkin_per_level": getattr(h2, "setup_galerkin", None),
         "value_dictionary_on_A": getattr(h2.levels[0].A, "val_idx", None) is not None}}
     if fab is not None:
         h2.close()
@@ -691,6 +692,12 @@ def run_b200(a):
                            "generate_s": round(t_gen, 2), "generated_on": "device" if on_device else "host",
                            "setup_s": round(t_setup, 2), "nn_builder": NN_BUILD.get(n),
                            "setup_phases_s": {k: round(v, 3) for k, v in (getattr(h, "setup_timing", None) or {}).items()},
+                           # BASELINE configs[4], setup sweep: per Galerkin product Q^T A Q its wall time (first build of
+                           # the process: includes allocator / library warm-up; config.extra repeats it warm) and the
+                           # SURVEY 8(d) byte count S(a,n) + 2 S(q) + 2 S(nnz(AQ),n) + S(a_c,n_c) over it
+                           "setup_galerkin_per_level": getattr(h, "setup_galerkin", None),
+                           "pinned_staging_alloc_s": (None if getattr(h, "pinned_alloc_s", None) is None
+                                                      else round(h.pinned_alloc_s, 3)),
                            "residual_after_timed_steps": res_after, "multi_rank_parity": parity, "extra": extra,
                            "step": "V-cycle + residual norm of its result (one graph): steady-state outer iteration of "
                                    "Multigrid.solve; cycle fusion %s, implied columns %s"

@@ -5,6 +5,7 @@
             the batched inverse / GEMM entry points, solve = 2*levels+3 launches streaming the factors once.
 """
 import ctypes
+import os
 
 import numpy as np
 
@@ -38,9 +39,19 @@ class DenseCoarse:
 class BcrCoarse:
     kind = _lib.MG_COARSE_BCR
 
-    def __init__(self, torch, dev, n, ip, ix, va, half_bw, min_block=64, tail_blocks=16, perm=None):
+    # The reduction stops at this many block rows and what is left is inverted densely (one matrix-vector product in
+    # the solve instead of a chain of latency-bound levels).  The dense inverse is a Gauss-Jordan sweep over a
+    # (tail m) x (2 tail m) array per pivot: with 16 blocks of the 257^2 coarsest grid that array is 272 MB -- every one
+    # of the 4128 pivots streams it through DRAM, 0.3 s of the 0.43 s factorisation -- with 8 blocks it is 68 MB and
+    # stays in L2.  One more reduction level costs the solve two launches and saves it three quarters of the tail
+    # matrix (136 -> 34 MB).  MGB_BCR_TAIL_BLOCKS overrides.
+    TAIL_BLOCKS = 8
+
+    def __init__(self, torch, dev, n, ip, ix, va, half_bw, min_block=64, tail_blocks=None, perm=None):
         """perm (optional, host int32 array): (ip, ix, va) is P A P^T for the caller's operator A, row i of it being row
         perm[i] of A; right-hand sides are gathered and solutions scattered accordingly inside the solve."""
+        if tail_blocks is None:
+            tail_blocks = int(os.environ.get("MGB_BCR_TAIL_BLOCKS", self.TAIL_BLOCKS))
         lib = _lib.load()
         st = _lib.stream_handle(torch)
         f64 = torch.float64

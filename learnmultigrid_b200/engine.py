@@ -282,22 +282,28 @@ class DeviceHierarchy:
     def _finish_structs(self):
         torch, dev = self.torch, self.device
         L = self.nlevels
+        import time
+        t0 = time.perf_counter()
         for lev in self.levels:
             n = getattr(lev, "n_vec", lev.n)          # partitioned levels: owned entries + halo
             lev.x = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.b = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.r = torch.zeros(n, dtype=torch.float64, device=dev)
             lev.tmp = torch.zeros(n, dtype=torch.float64, device=dev)
-        import time
+        n0 = self.levels[0].n
+        self.n = n0
+        self._stage = torch.zeros(n0, dtype=torch.float64, device=dev)       # natural-order staging
+        # the pinned host staging buffer (8 n0 bytes of page-locked memory: 0.2-0.3 s at 67 M unknowns) is allocated
+        # by the first transfer that needs it -- a hierarchy fed with device-resident or pinned vectors never does
+        self._pinned_buf = None
+        torch.cuda.synchronize()
+        if getattr(self, "setup_timing", None) is not None:
+            self.setup_timing["level vectors"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         self._inspect_levels()
         torch.cuda.synchronize()
         if getattr(self, "setup_timing", None) is not None:
             self.setup_timing["inspect (diagonal, colouring flags)"] = time.perf_counter() - t0
-        n0 = self.levels[0].n
-        self.n = n0
-        self._stage = torch.zeros(n0, dtype=torch.float64, device=dev)       # natural-order staging
-        self._pinned = torch.zeros(n0, dtype=torch.float64).pin_memory()
         self._norm_ws = torch.zeros(int(self.lib.mg_norm_workspace_size(n0)) + 4096, dtype=torch.float64, device=dev)
         self._norm_out = torch.zeros(1, dtype=torch.float64, device=dev)
         self._norm_host = torch.zeros(1, dtype=torch.float64).pin_memory()
@@ -360,6 +366,15 @@ class DeviceHierarchy:
 
     # ------------------------------------------------------------------------------------------------
     # vectors in and out (host NumPy <-> permuted device vectors)
+    @property
+    def _pinned(self):
+        if self._pinned_buf is None:
+            import time
+            t0 = time.perf_counter()
+            self._pinned_buf = self.torch.empty(self.n, dtype=self.torch.float64, pin_memory=True)
+            self.pinned_alloc_s = time.perf_counter() - t0
+        return self._pinned_buf
+
     def _to_level0(self, host_vec, dst):
         torch = self.torch
         # the pinned staging buffer is reused by every transfer: wait until the previous H2D copy has read it

@@ -25,6 +25,31 @@ class DevCSR:
         return self.indptr.data_ptr(), self.indices.data_ptr(), self.values.data_ptr()
 
 
+class ColorList(list):
+    """Per-level colour arrays of a hierarchy.  Colours computed on the device stay there (the setup only needs them
+    there: permutation, flags); an entry is downloaded the first time somebody asks for it on the host (tests, the
+    oracle's colour argument, the partition plans) and is a NumPy int32 array from then on."""
+
+    def _host(self, k):
+        v = list.__getitem__(self, k)
+        if v is not None and not isinstance(v, np.ndarray):
+            v = v.cpu().numpy()
+            list.__setitem__(self, k, v)
+        return v
+
+    def __getitem__(self, k):
+        if isinstance(k, slice):
+            return [self._host(i) for i in range(*k.indices(len(self)))]
+        return self._host(k if k >= 0 else k + len(self))
+
+    def __iter__(self):
+        return (self._host(i) for i in range(len(self)))
+
+    def device(self, k):
+        """entry k as it is stored (device tensor or host array), without a download"""
+        return list.__getitem__(self, k)
+
+
 class DeviceSetup:
     def __init__(self, torch, device):
         self.torch = torch
@@ -152,12 +177,16 @@ class DeviceSetup:
                    "mg_csr_compact_nonzeros")
         return DevCSR((n, B.shape[1]), optr, oidx, oval)
 
-    def galerkin(self, A, Q, QT):
+    def galerkin(self, A, Q, QT, keep_pattern=None):
         """A_c = Q^T A Q exactly as SciPy evaluates csr_matrix(i.T @ A @ i) (Multigrid.py:97-98):
-        T = A^T Q, C = Q^T T, A_c = C^T."""
+        T = A^T Q, C = Q^T T, A_c = C^T.  keep_pattern (a list): the pattern of A^T is appended to it -- the first-fit
+        colouring of the level walks it and need not transpose A again."""
         AT = self.transpose(A)
+        if keep_pattern is not None:
+            keep_pattern.append((AT.indptr, AT.indices))
         T = self.spgemm(AT, Q)
         del AT
+        self.last_product_nnz = T.nnz              # nnz(A^T Q): the intermediate product of SURVEY 8(d)'s byte formula
         C = self.spgemm(QT, T)
         del T
         return self.transpose(C)
@@ -208,40 +237,52 @@ class DeviceSetup:
                    "mg_extract_dinv")
         return out
 
-    def first_fit_colors(self, A, max_rounds=400000):
+    def first_fit_colors(self, A, max_rounds=400000, t_pattern=None, host=True):
         """The colours of formats.greedy_colors computed on the device (csrc/color_kernels.cu: dependency rounds on the
-        patterns of A and A^T); returns a host int32 array.  Raises MgError (UNSUPPORTED) when the dependency chains
-        are too long for the round-based algorithm -- the caller then uses the host helper."""
+        patterns of A and A^T); returns a host int32 array, or the device tensor with host=False.  t_pattern: (indptr,
+        indices) of A^T on the device if the caller has them (the Galerkin product forms A^T anyway).  Raises MgError
+        (UNSUPPORTED) when the dependency chains are too long for the round-based algorithm -- the caller then uses the
+        host helper."""
         t = self.torch
         n = A.shape[0]
-        AT = self.transpose(A)
+        if t_pattern is None:
+            AT = self.transpose(A)
+            t_pattern = (AT.indptr, AT.indices)
         colors = self.empty(n, t.int32)
         nb = int(self.lib.mg_color_workspace_size(n))
         work = self.temp(nb)
         rounds = ctypes.c_int64(0)
-        _lib.check(self.lib.mg_color_first_fit(n, A.indptr.data_ptr(), A.indices.data_ptr(), AT.indptr.data_ptr(),
-                                               AT.indices.data_ptr(), colors.data_ptr(), work.data_ptr(), nb,
+        _lib.check(self.lib.mg_color_first_fit(n, A.indptr.data_ptr(), A.indices.data_ptr(), t_pattern[0].data_ptr(),
+                                               t_pattern[1].data_ptr(), colors.data_ptr(), work.data_ptr(), nb,
                                                int(max_rounds), ctypes.byref(rounds), self.st()), "mg_color_first_fit")
         self.last_color_rounds = int(rounds.value)
-        return colors.cpu().numpy()
+        return colors.cpu().numpy() if host else colors
 
     def coloring_flags(self, A, colors_host, row0=0):
         """mg_level.flags of a level from its operator in natural ordering (rows row0.. of the global matrix when A is
         a row block with global column ids) and the GLOBAL colour array: MG_LEVEL_PROPER_COLORING if no row couples to
         another row of its colour, MG_LEVEL_NONZERO_DIAG if every row has a non-zero diagonal."""
         t = self.torch
-        col = t.from_numpy(np.ascontiguousarray(colors_host, dtype=np.int32)).to(self.dev)
+        col = self._colors_on_device(colors_host)
         self._flag.zero_()
         _lib.check(self.lib.mg_csr_coloring_flags(A.shape[0], int(row0), *A.ptrs(), col.data_ptr(),
                                                   self._flag.data_ptr(), self.st()), "mg_csr_coloring_flags")
         bad = int(self._flag.item())
         return ((0 if bad & 1 else _lib.MG_LEVEL_PROPER_COLORING) | (0 if bad & 2 else _lib.MG_LEVEL_NONZERO_DIAG))
 
+    def _colors_on_device(self, colors):
+        """int32 colour array as a device tensor (host arrays are uploaded, device tensors taken as they are)"""
+        t = self.torch
+        if isinstance(colors, t.Tensor):
+            return colors if colors.dtype == t.int32 else colors.to(t.int32)
+        return t.from_numpy(np.ascontiguousarray(colors, dtype=np.int32)).to(self.dev)
+
     def color_perm(self, colors_host):
-        """device perm (new -> old, stable by colour), inverse perm, host colour offsets"""
+        """device perm (new -> old, stable by colour), inverse perm, host colour offsets; the colours may be a host
+        array or a device tensor"""
         t = self.torch
         n = len(colors_host)
-        keys = t.from_numpy(np.ascontiguousarray(colors_host, dtype=np.int32)).to(self.dev)
+        keys = self._colors_on_device(colors_host)
         ncol = int(keys.max().item()) + 1 if n else 0
         ks = self.empty(n, t.int32)
         perm = self.empty(n, t.int32)
@@ -260,9 +301,10 @@ class DeviceSetup:
         return perm, iperm, cptr
 
 
-def build_natural(S, A, Q_list, tm=None):
+def build_natural(S, A, Q_list, tm=None, t_patterns=None):
     """Upload A and the transfer operators and form the Galerkin hierarchy in natural ordering on the device.
-    Returns (A_host0, A_nat, Q_nat, QT_nat)."""
+    Returns (A_host0, A_nat, Q_nat, QT_nat).  t_patterns (a list): receives the pattern of A_l^T of every level that
+    has a coarser one (level_colors walks them)."""
     L = len(Q_list) + 1
     if isinstance(A, DevCSR):                              # already on the device (assembly_device / neural2d)
         A_host0 = None
@@ -284,16 +326,26 @@ def build_natural(S, A, Q_list, tm=None):
         QT_nat.append(QT)
         if tm:
             tm.mark("transpose Q")
-        A_nat.append(S.galerkin(A_nat[l], Q, QT))
+        A_nat.append(S.galerkin(A_nat[l], Q, QT, t_patterns))
         if tm:
-            tm.mark("Galerkin SpGEMM")
+            dt = tm.mark("Galerkin SpGEMM")
+            # SURVEY 8(d), SpGEMM row: read A, Q, Q^T once, write and read the intermediate product, write A_c
+            csr = lambda nnz, n: 12 * nnz + 4 * (n + 1)
+            a, ac = A_nat[l], A_nat[l + 1]
+            nbytes = (csr(a.nnz, a.shape[0]) + csr(Q.nnz, Q.shape[0]) + csr(QT.nnz, QT.shape[0])
+                      + 2 * csr(S.last_product_nnz, a.shape[0]) + csr(ac.nnz, ac.shape[0]))
+            tm.galerkin_levels.append({"level": l, "rows": a.shape[0], "nnz_A": a.nnz, "nnz_Q": Q.nnz,
+                                       "nnz_AQ": S.last_product_nnz, "coarse_rows": ac.shape[0], "nnz_Ac": ac.nnz,
+                                       "ms": round(dt * 1e3, 3), "algorithmic_bytes": nbytes,
+                                       "gb_per_s": round(nbytes / dt / 1e9, 1) if dt > 0 else None})
     return A_host0, A_nat, Q_nat, QT_nat
 
 
-def level_colors(S, smoother, colors, A_host0, A_nat):
-    """Per level: host colour array (or None) for multicolour Gauss-Seidel; the coarsest level is never coloured."""
+def level_colors(S, smoother, colors, A_host0, A_nat, t_patterns=None):
+    """Per level: colour array (or None) for multicolour Gauss-Seidel; the coarsest level is never coloured.  Returns a
+    ColorList: colours found on the device stay there until somebody reads them on the host."""
     L = len(A_nat)
-    out = []
+    out = ColorList()
     for l in range(L):
         if smoother == "mcgs" and l < L - 1:
             if colors is not None and colors[l] is not None:
@@ -305,7 +357,8 @@ def level_colors(S, smoother, colors, A_host0, A_nat):
                 # r02_bench_device_colours.json); small levels and long dependency chains take the serial helper
                 if os.environ.get("MGB_DEVICE_COLORS", "1") == "1" and A_nat[l].shape[0] >= 50000:
                     try:
-                        col = S.first_fit_colors(A_nat[l])
+                        col = S.first_fit_colors(A_nat[l], host=False,
+                                                 t_pattern=t_patterns[l] if t_patterns and l < len(t_patterns) else None)
                     except _lib.MgError:
                         col = None                                       # chains too long: serial helper below
                 if col is None:
@@ -360,12 +413,15 @@ class PhaseTimer:
         self.torch, self.time = torch, time
         self.t = time.perf_counter()
         self.phases = {}
+        self.galerkin_levels = []      # per level: time and SURVEY 8(d) bytes of the Galerkin product
 
     def mark(self, name):
         self.torch.cuda.synchronize()
         now = self.time.perf_counter()
-        self.phases[name] = self.phases.get(name, 0.0) + (now - self.t)
+        dt = now - self.t
+        self.phases[name] = self.phases.get(name, 0.0) + dt
         self.t = now
+        return dt
 
 
 def setup_device(h, A, Q_list, colors, dense_coarse_max):
@@ -375,14 +431,16 @@ def setup_device(h, A, Q_list, colors, dense_coarse_max):
     h._setup = S
     L = h.nlevels
     tm = PhaseTimer(torch)
-    A_host0, A_nat, Q_nat, QT_nat = build_natural(S, A, Q_list, tm)
+    t_patterns = [] if h.smoother == "mcgs" and colors is None else None
+    A_host0, A_nat, Q_nat, QT_nat = build_natural(S, A, Q_list, tm, t_patterns)
     # orderings
-    h.colors = level_colors(S, h.smoother, colors, A_host0, A_nat)
+    h.colors = level_colors(S, h.smoother, colors, A_host0, A_nat, t_patterns)
+    del t_patterns
     tm.mark("colouring")
     perms, iperms, cptrs = [], [], []
     for l in range(L):
-        if h.colors[l] is not None:
-            p, ip, cp = S.color_perm(h.colors[l])
+        if h.colors.device(l) is not None:
+            p, ip, cp = S.color_perm(h.colors.device(l))
         else:
             p = ip = cp = None
         perms.append(p)
@@ -395,6 +453,7 @@ def setup_device(h, A, Q_list, colors, dense_coarse_max):
                                                dense_coarse_max))
         tm.mark("coarsest factorisation" if l == L - 1 else "permute + SELL build")
     h.setup_timing = tm.phases
+    h.setup_galerkin = tm.galerkin_levels
     h.host_A = None
     h.host_Q = None
     if h.keep_host:

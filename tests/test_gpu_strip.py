@@ -105,15 +105,23 @@ def test_device_first_fit_colouring_equals_the_host_helper(torch_mod):
     mats.append(F.canonical_csr(P.irregular_p1_2d(64)["A"]))
     mats.append(F.canonical_csr(sp.random(3000, 3000, density=0.003, random_state=1, format="csr")
                                 + sp.diags((np.arange(3000) % 5 > 0) * 1.0)))
+    lib = _lib.load()
     for M in mats:
         want, nc = F.greedy_colors(M)
-        got = S.first_fit_colors(S.upload(M))
-        assert np.array_equal(got, want)
-        assert S.last_color_rounds >= 1
+        # work lists walked by the persistent cluster kernel (default), by one launch per round (0), and by the two in
+        # alternation (lists of more than 40 rows go to the wide grid)
+        for frontier in (None, 0, 40):
+            old = lib.mg_set_color_cluster_frontier(-1 if frontier is None else frontier)
+            try:
+                got = np.asarray(S.first_fit_colors(S.upload(M)))
+            finally:
+                lib.mg_set_color_cluster_frontier(old)
+            assert np.array_equal(got, want), frontier
+            assert S.last_color_rounds >= 1
     chain = F.canonical_csr(sp.diags([np.ones(4999), 2 * np.ones(5000), np.ones(4999)], [-1, 0, 1], format="csr"))
     with pytest.raises(_lib.MgError):
         S.first_fit_colors(S.upload(chain), max_rounds=1000)
-    assert np.array_equal(S.first_fit_colors(S.upload(chain), max_rounds=6000), F.greedy_colors(chain)[0])
+    assert np.array_equal(np.asarray(S.first_fit_colors(S.upload(chain), max_rounds=6000)), F.greedy_colors(chain)[0])
 
 
 def test_implied_columns_are_bit_identical(torch_mod, monkeypatch):
