@@ -512,14 +512,11 @@ int mg_host_greedy_color_block(int64_t n_own, int64_t n_ext, const int32_t *h_in
                                int32_t *h_colors, int phase);
 /* The colouring of mg_host_greedy_color computed on the device (csrc/color_kernels.cu): rounds of a Jones-Plassmann
  * sweep whose priority is the row's place in the first-fit order, on the patterns of A and A^T (device CSR index arrays).
- * Identical colours, entry for entry.  d_work: mg_color_workspace_size(n) bytes.  A setup-time call: it synchronises the
- * stream to look at the size of the next round's work list: lists of at most mg_set_color_cluster_frontier rows
- * (default 32768; structured grids: one anti-diagonal per round) are walked by ONE persistent thread-block cluster,
- * a cluster barrier per round, until the list outgrows it or runs dry; longer lists by 16 launches of a wide grid.
+ * Identical colours, entry for entry.  d_work: mg_color_workspace_size(n) bytes.  A round is one launch (a group of 8
+ * lanes per row, programmatic dependent launches); a setup-time call: it synchronises the stream every 128 rounds.
  * MG_ERR_UNSUPPORTED if more than max_rounds rounds (long dependency chains, e.g. a 1D mesh numbered end to end: use
  * the host helper) or more than 128 colours would be needed. */
 int64_t mg_color_workspace_size(int64_t n);
-int64_t mg_set_color_cluster_frontier(int64_t rows);   /* returns the previous value; 0 = always a launch per round */
 /* Is a colouring proper for the operator, and has every row a diagonal (mg_level.flags)?  Rows [0,nrows) of a CSR block
  * whose row i is global row row0 + i; d_color is indexed by GLOBAL row / column id.  *d_flags (device int32, zeroed by
  * the caller) |= 1 if a row has a non-zero entry in the column of another row of its own colour, |= 2 if a row has no

@@ -220,7 +220,6 @@ _SIGNATURES = {
     "mg_host_lex_levels": (c_i64, [c_i64, c_vp, c_vp, c_vp]),
     "mg_color_workspace_size": (c_i64, [c_i64]),
     "mg_csr_coloring_flags": (c_int, [c_i64, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
-    "mg_set_color_cluster_frontier": (c_i64, [c_i64]),
     "mg_color_first_fit": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_vp, c_vp]),
     "mg_vcycle": (c_int, [ctypes.POINTER(mg_level), c_int, ctypes.POINTER(mg_cycle_params), c_vp]),
     "mg_vcycle_dist": (c_int, [ctypes.POINTER(mg_comm), ctypes.POINTER(mg_level), c_int,
@@ -291,8 +290,6 @@ def load():
         lib.mg_set_wide_min_len(int(os.environ["MGB_WIDE_MIN_LEN"]))
     if "MGB_WIDE_MAX_ROWS" in os.environ:
         lib.mg_set_wide_max_rows(int(os.environ["MGB_WIDE_MAX_ROWS"]))
-    if "MGB_COLOR_CLUSTER_FRONTIER" in os.environ:      # 0: first-fit colouring with one launch per round
-        lib.mg_set_color_cluster_frontier(int(os.environ["MGB_COLOR_CLUSTER_FRONTIER"]))
     _lib = lib
     return lib
 

@@ -52,9 +52,18 @@ class BcrCoarse:
         perm[i] of A; right-hand sides are gathered and solutions scattered accordingly inside the solve."""
         if tail_blocks is None:
             tail_blocks = int(os.environ.get("MGB_BCR_TAIL_BLOCKS", self.TAIL_BLOCKS))
+        import time
         lib = _lib.load()
         st = _lib.stream_handle(torch)
         f64 = torch.float64
+        self.timing = {}           # seconds per phase of the factorisation (device synchronised at each mark: setup only)
+        t_mark = [time.perf_counter()]
+
+        def mark(name):
+            torch.cuda.synchronize()
+            now = time.perf_counter()
+            self.timing[name] = self.timing.get(name, 0.0) + now - t_mark[0]
+            t_mark[0] = now
         m = max(int(half_bw), min_block, 1)
         nb = (n + m - 1) // m
         n_pad = nb * m
@@ -70,6 +79,7 @@ class BcrCoarse:
                                               L.data_ptr(), U.data_ptr(), bad.data_ptr(), st), "mg_bcr_blocks_from_csr")
         if int(bad.item()):
             raise _lib.MgError("BCR: matrix entries outside the block-tridiagonal band (half bandwidth > block size)")
+        mark("blocks from CSR")
         sing = torch.zeros(1, dtype=torch.int32, device=dev)
         work = torch.empty(max(nb // 2, 1) * m * 2 * m, dtype=f64, device=dev)
         e = 8                       # bytes per double, for pointer arithmetic on data_ptr()
@@ -96,6 +106,7 @@ class BcrCoarse:
         while na > max(int(tail_blocks), 1):
             nodd, nk = na // 2, (na + 1) // 2
             Dinv = inverse(D.data_ptr() + mm * e, 2 * mm, nodd)
+            mark("block inverses (batched Gauss-Jordan)")
             HL, HU = zeros(nodd), zeros(nodd)
             gemm(nodd, Dinv.data_ptr(), mm, L.data_ptr() + mm * e, 2 * mm, HL.data_ptr(), mm, 1.0, 0.0)
             gemm(nodd, Dinv.data_ptr(), mm, U.data_ptr() + mm * e, 2 * mm, HU.data_ptr(), mm, 1.0, 0.0)
@@ -113,6 +124,7 @@ class BcrCoarse:
             self.levels.append({"na": na, "GL": GL, "GU": GU, "Dinv": Dinv, "HL": HL, "HU": HU})
             D, L, U = Dn, Ln, Un
             na = nk
+            mark("block products (batched GEMM)")
         self.tail_na = na
         if na == 1:
             self.last_inv = inverse(D.data_ptr(), mm, 1)
@@ -133,7 +145,7 @@ class BcrCoarse:
             _lib.check(lib.mg_dense_inverse(nt, R.data_ptr(), self.last_inv.data_ptr(), wk.data_ptr(), st),
                        "mg_dense_inverse (BCR tail)")
             del R, wk
-        torch.cuda.synchronize()
+        mark("dense inverse of the tail")
         if int(sing.item()):
             raise _lib.MgError("BCR: singular diagonal block in the coarsest operator")
         self.f = torch.zeros(n_pad, dtype=f64, device=dev)

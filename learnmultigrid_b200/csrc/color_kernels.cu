@@ -13,13 +13,9 @@
 // serial helper (round limit).  The colours are those of mg_host_greedy_color, entry for entry: the per-row code is
 // shared by the kernels and by a serial host emulation (mg_host_color_rounds), which tests/test_host_logic.py compares
 // with the serial first-fit.
-#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace mgb {
-
-// frontiers of at most this many rows are walked by the persistent cluster kernel (mg_set_color_cluster_frontier)
-int64_t g_color_cluster_frontier = 32768;
 
 struct JpView {
     int64_t n;
@@ -35,17 +31,6 @@ __host__ __device__ inline int jp_lowest_zero_bit(uint64_t w) {   // w != all on
     return __ffsll((long long)~w) - 1;
 #else
     return __builtin_ctzll(~w);
-#endif
-}
-
-// Colours and work-list entries are written by one SM and read by another INSIDE one kernel when the rounds run in the
-// persistent cluster kernel below: those loads bypass L1 (ld.global.cg), which is not coherent between SMs.
-template <typename T>
-__host__ __device__ inline T jp_load_shared(const T *p) {
-#ifdef __CUDA_ARCH__
-    return __ldcg(p);
-#else
-    return *p;
 #endif
 }
 
@@ -69,44 +54,45 @@ __host__ __device__ inline int jp_count_earlier(const JpView &v, int64_t i) {
     return w;
 }
 
-// smallest colour none of the (already coloured) neighbours has; -1: more than 128 colours would be needed
-__host__ __device__ inline int jp_first_free(const JpView &v, int64_t i) {
-    uint64_t lo = 0, hi = 0;
-    for (int32_t p = v.ip[i]; p < v.ip[i + 1]; ++p) {
-        const int32_t j = v.ix[p];
-        const int32_t c = j != i ? jp_load_shared(v.color + j) : -1;
+// The neighbours of row i are the entries of its row in A, then in A^T (with multiplicity, as jp_count_earlier counts
+// them).  The two functions below visit entries lane, lane + G, ... of that list: the kernels give a row to a group of G
+// lanes -- a serial walk is a chain of (index -> colour / priority -> atomic) round trips per neighbour, ~20 of them per
+// 5-point row, and a round is nothing but that latency -- the serial host emulation calls them with lane 0 of 1.
+// colours taken by the (already coloured) neighbours among this lane's entries: bit c of lo / bit c - 64 of hi
+__host__ __device__ inline void jp_taken_colors(const JpView &v, int64_t i, int lane, int G, uint64_t &lo, uint64_t &hi) {
+    const int32_t a0 = v.ip[i], da = v.ip[i + 1] - a0, b0 = v.tip[i], d = da + v.tip[i + 1] - b0;
+    for (int32_t k = lane; k < d; k += G) {
+        const int32_t j = k < da ? v.ix[a0 + k] : v.tix[b0 + k - da];
+        const int32_t c = j != i ? v.color[j] : -1;
         if (c >= 0) { if (c < 64) lo |= 1ull << c; else hi |= 1ull << (c - 64); }
     }
-    for (int32_t p = v.tip[i]; p < v.tip[i + 1]; ++p) {
-        const int32_t j = v.tix[p];
-        const int32_t c = j != i ? jp_load_shared(v.color + j) : -1;
-        if (c >= 0) { if (c < 64) lo |= 1ull << c; else hi |= 1ull << (c - 64); }
-    }
+}
+
+// smallest colour not in the masks; -1: more than 128 colours would be needed
+__host__ __device__ inline int jp_first_free(uint64_t lo, uint64_t hi) {
     if (~lo) return jp_lowest_zero_bit(lo);
     if (~hi) return 64 + jp_lowest_zero_bit(hi);
     return -1;
 }
 
-// row i has its colour: every later neighbour waits for one row less; those that wait for nobody any more go to `next`
-__host__ __device__ inline void jp_release(const JpView &v, int64_t i, int32_t *next, int32_t *next_cnt) {
+// row i has its colour: every later neighbour (among this lane's entries) waits for one row less; those that wait for
+// nobody any more go to `next`
+__host__ __device__ inline void jp_release(const JpView &v, int64_t i, int lane, int G, int32_t *next, int32_t *next_cnt) {
     const uint32_t me = v.prio[i];
-    for (int pass = 0; pass < 2; ++pass) {
-        const int32_t *ptr = pass ? v.tip : v.ip, *idx = pass ? v.tix : v.ix;
-        for (int32_t p = ptr[i]; p < ptr[i + 1]; ++p) {
-            const int32_t j = idx[p];
-            if (j == i || v.prio[j] <= me) continue;
+    const int32_t a0 = v.ip[i], da = v.ip[i + 1] - a0, b0 = v.tip[i], d = da + v.tip[i + 1] - b0;
+    for (int32_t k = lane; k < d; k += G) {
+        const int32_t j = k < da ? v.ix[a0 + k] : v.tix[b0 + k - da];
+        if (j == i || v.prio[j] <= me) continue;
 #ifdef __CUDA_ARCH__
-            if (atomicSub(&v.wait[j], 1) == 1) next[atomicAdd(next_cnt, 1)] = j;
+        if (atomicSub(&v.wait[j], 1) == 1) next[atomicAdd(next_cnt, 1)] = j;
 #else
-            if (--v.wait[j] == 0) next[(*next_cnt)++] = j;
+        if (--v.wait[j] == 0) next[(*next_cnt)++] = j;
 #endif
-        }
     }
 }
 
 // counters in the workspace: [0..2] work-list sizes (round r reads r % 3, fills (r+1) % 3, clears (r+2) % 3),
 // [3] rows coloured so far, [4] error flag (a row needed a 129th colour)
-// [5] rounds the last cluster launch walked, [6] the frontier it stopped at
 constexpr int kJpCounters = 8;
 
 __global__ void __launch_bounds__(kBlock) jp_priority_kernel(JpView v) {
@@ -124,67 +110,37 @@ __global__ void __launch_bounds__(kBlock) jp_wait_kernel(JpView v, int32_t *list
     if (w == 0) list0[atomicAdd(&counters[0], 1)] = (int32_t)i;
 }
 
+// One round: every row of the current work list takes its colour and releases its later neighbours.  A group of
+// kJpGroup lanes shares a row (see above); the launches of a batch are programmatic dependents of each other, so that a
+// round's launch latency hides behind the previous round.
+constexpr int kJpGroup = 8;
+
 __global__ void __launch_bounds__(kBlock)
 jp_round_kernel(JpView v, const int32_t *cur, int32_t *next, int32_t *counters, int r) {
+    pdl_prologue();
+    constexpr int G = kJpGroup;
     int32_t *cur_cnt = counters + r % 3, *next_cnt = counters + (r + 1) % 3;
     const int32_t m = *cur_cnt;
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         counters[(r + 2) % 3] = 0;                       // read in round r - 1, filled in round r + 1
         atomicAdd(&counters[3], m);
     }
-    const int64_t stride = (int64_t)gridDim.x * kBlock;
-    for (int64_t t = (int64_t)blockIdx.x * kBlock + threadIdx.x; t < m; t += stride) {
+    const int lane = threadIdx.x % G;
+    const unsigned gmask = ((1u << G) - 1u) << ((threadIdx.x & 31) / G * G);
+    const int64_t stride = (int64_t)gridDim.x * (kBlock / G);
+    for (int64_t t = (int64_t)blockIdx.x * (kBlock / G) + threadIdx.x / G; t < m; t += stride) {
         const int64_t i = cur[t];
-        int c = jp_first_free(v, i);
+        uint64_t lo = 0, hi = 0;
+        jp_taken_colors(v, i, lane, G, lo, hi);
+#pragma unroll
+        for (int o = G / 2; o > 0; o >>= 1) {
+            lo |= __shfl_xor_sync(gmask, lo, o, G);
+            hi |= __shfl_xor_sync(gmask, hi, o, G);
+        }
+        int c = jp_first_free(lo, hi);
         if (c < 0) { counters[4] = 1; c = 127; }
-        v.color[i] = c;
-        jp_release(v, i, next, next_cnt);
-    }
-}
-
-// The same rounds without a launch per round.  On a W x W grid in row-major numbering a round is one anti-diagonal --
-// at most W rows -- and there are 2 W of them per level (32 k rounds for the 8193^2 hierarchy): a launch per round is
-// all latency (18 us per round measured, 0.6 s).  Here ONE thread-block cluster of 8 x 1024 threads walks the rounds: a
-// round is one pass over the work list, then the hardware cluster barrier (barrier.cluster, a few hundred ns) in place
-// of the kernel boundary.  Everything a later round reads from an earlier one (colours, work lists, counters) is
-// written through to L2 and read with L1 bypassed (jp_load_shared / atomics), with a device-scope fence before the
-// barrier.  The kernel hands back to the host loop when the frontier outgrows it (unstructured numberings start with
-// n/6 independent rows: the wide grid of jp_round_kernel is the right tool there), when the work lists run dry, or after
-// `limit` rounds.  Round numbering, list parity and counter rotation are those of jp_round_kernel, so the two can
-// alternate.
-constexpr int kJpClusterCtas = 8;
-constexpr int kJpClusterThreads = 1024;
-
-__global__ void __cluster_dims__(kJpClusterCtas, 1, 1) __launch_bounds__(kJpClusterThreads)
-jp_cluster_rounds_kernel(JpView v, int32_t *list0, int32_t *list1, int32_t *counters, int r0, int limit, int big) {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cluster = cg::this_cluster();
-    const int tid = (int)blockIdx.x * kJpClusterThreads + (int)threadIdx.x;
-    constexpr int kThreads = kJpClusterCtas * kJpClusterThreads;
-    int done = 0, m = 0;
-    for (int r = r0; done < limit; ++r, ++done) {      // r0 is the global round number mod 6: parity and mod 3 survive
-        m = jp_load_shared(counters + r % 3);
-        if (m == 0 || m > big) break;                  // the same value in every thread: written before the last barrier
-        const int32_t *cur = (r & 1) ? list1 : list0;
-        int32_t *next = (r & 1) ? list0 : list1;
-        int32_t *next_cnt = counters + (r + 1) % 3;
-        if (tid == 0) {
-            atomicExch(counters + (r + 2) % 3, 0);     // read in round r - 1 (before its barrier), filled in round r + 1
-            atomicAdd(counters + 3, m);
-        }
-        for (int t = tid; t < m; t += kThreads) {
-            const int64_t i = jp_load_shared(cur + t);
-            int c = jp_first_free(v, i);
-            if (c < 0) { atomicExch(counters + 4, 1); c = 127; }
-            v.color[i] = c;
-            jp_release(v, i, next, next_cnt);
-        }
-        __threadfence();
-        cluster.sync();
-    }
-    if (tid == 0) {
-        counters[5] = done;
-        counters[6] = m;
+        if (lane == 0) v.color[i] = c;
+        jp_release(v, i, lane, G, next, next_cnt);
     }
 }
 
@@ -228,14 +184,6 @@ static JpView jp_view(int64_t n, const int32_t *ip, const int32_t *ix, const int
     return v;
 }
 
-/* Work lists of at most `rows` rows are walked by the persistent cluster kernel, longer ones by one launch per round
- * (default 32768; 0 = always one launch per round).  Returns the previous value. */
-int64_t mg_set_color_cluster_frontier(int64_t rows) {
-    const int64_t old = g_color_cluster_frontier;
-    if (rows >= 0) g_color_cluster_frontier = rows;
-    return old;
-}
-
 /* bytes of workspace for n rows (priorities, counters, two work lists) */
 int64_t mg_color_workspace_size(int64_t n) { return n < 0 ? -1 : 16 * n + (int64_t)sizeof(int32_t) * kJpCounters; }
 
@@ -259,38 +207,23 @@ int mg_color_first_fit(int64_t n, const int32_t *d_indptr, const int32_t *d_indi
     MG_CHECK_LAUNCH("jp_priority");
     jp_wait_kernel<<<rows_grid, kBlock, 0, st>>>(v, list[0], counters);
     MG_CHECK_LAUNCH("jp_wait");
-    int64_t cap = (int64_t)sm_count() * 4;
-    if (cap > rows_grid) cap = rows_grid;
-    const int64_t batch = 16;
-    const int64_t big = g_color_cluster_frontier < 0x7fffffffLL ? g_color_cluster_frontier : 0x7fffffffLL;
+    // kBlock / kJpGroup rows per CTA; as many CTAs as one work list can fill, a few per SM at most
+    int64_t cap = (int64_t)sm_count() * 8;
+    const int64_t want = (n + kBlock / kJpGroup - 1) / (kBlock / kJpGroup);
+    if (cap > want) cap = want;
+    const int64_t batch = 128;
     int64_t r = 0;
     int32_t host[kJpCounters];
     for (;;) {
-        // the frontier of round r decides who walks the next rounds: short work lists (structured grids: one
-        // anti-diagonal per round) go to the persistent cluster kernel, long ones to a launch per round on a wide grid
+        for (int64_t k = 0; k < batch; ++k, ++r)
+            launch_k(jp_round_kernel, (unsigned)cap, (unsigned)kBlock, st, v, (const int32_t *)list[r & 1], list[(r + 1) & 1],
+                     counters, (int)(r % 3));
+        MG_CHECK_LAUNCH("jp_round");
         MG_CHECK_CUDA(cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
         MG_CHECK_CUDA(cudaStreamSynchronize(st));
         if (host[4]) return set_error(MG_ERR_UNSUPPORTED, "mg_color_first_fit", "more than 128 colours needed");
         if (host[3] >= n) break;
         if (r >= max_rounds) return set_error(MG_ERR_UNSUPPORTED, "mg_color_first_fit", "dependency chains too long for the round-based colouring");
-        const int64_t frontier = host[r % 3];
-        if (frontier == 0)      // rows left but nobody ready: the transposed pattern does not match the pattern
-            return set_error(MG_ERR_INVALID, "mg_color_first_fit", "rows left uncoloured (inconsistent transpose pattern?)");
-        if (frontier <= big) {
-            int64_t limit = max_rounds - r;
-            if (limit > (1 << 20)) limit = 1 << 20;
-            jp_cluster_rounds_kernel<<<kJpClusterCtas, kJpClusterThreads, 0, st>>>(v, list[0], list[1], counters, (int)(r % 6),
-                                                                                  (int)limit, (int)big);
-            MG_CHECK_LAUNCH("jp_cluster_rounds");
-            ++g_launch_count;
-            MG_CHECK_CUDA(cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, st));
-            MG_CHECK_CUDA(cudaStreamSynchronize(st));
-            r += host[5];
-        } else {
-            for (int64_t k = 0; k < batch; ++k, ++r)
-                jp_round_kernel<<<(unsigned)cap, kBlock, 0, st>>>(v, list[r & 1], list[(r + 1) & 1], counters, (int)(r % 3));
-            MG_CHECK_LAUNCH("jp_round");
-        }
     }
     if (h_rounds) *h_rounds = r;
     return MG_OK;
@@ -334,11 +267,13 @@ int mg_host_color_rounds(int64_t n, const int32_t *h_indptr, const int32_t *h_in
         // the rows of a round are independent: walk them backwards to make any hidden order dependence show
         for (int32_t t = cnt - 1; t >= 0; --t) {
             const int64_t i = list[r & 1][t];
-            const int c = jp_first_free(v, i);
+            uint64_t lo = 0, hi = 0;
+            jp_taken_colors(v, i, 0, 1, lo, hi);
+            const int c = jp_first_free(lo, hi);
             if (c < 0) return set_error(MG_ERR_UNSUPPORTED, "mg_host_color_rounds", "more than 128 colours needed");
             v.color[i] = c;
         }
-        for (int32_t t = cnt - 1; t >= 0; --t) jp_release(v, list[r & 1][t], list[(r + 1) & 1], &next_cnt);
+        for (int32_t t = cnt - 1; t >= 0; --t) jp_release(v, list[r & 1][t], 0, 1, list[(r + 1) & 1], &next_cnt);
         done += cnt;
         cnt = next_cnt;
         ++r;

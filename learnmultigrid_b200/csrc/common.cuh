@@ -195,4 +195,30 @@ __device__ __forceinline__ double block_sum_last(double v) {
     return v;
 }
 
+// The same job with a quarter of the instructions: every thread parks its value in shared memory (one store), all warps
+// but the first arrive and retire, and warp 0 adds the BLOCK values in a fixed order (lane l takes l, l + 32, ..., then
+// the warp tree).  The one-row-per-thread kernels are bound by instruction issue (68-76 % of the issue slots at 4 of 7
+// TB/s): the five-step shuffle tree in EVERY warp made the sweep with a fused norm a third slower than the plain sweep
+// (ncu, level 0 of the 8193^2 step: 284 against 215 us for the same bytes).  -DMGB_PARKED_SUM=0 keeps the tree per warp.
+#ifndef MGB_PARKED_SUM
+#define MGB_PARKED_SUM 1
+#endif
+template <int BLOCK>
+__device__ __forceinline__ double block_sum_parked(double v) {
+    if (!MGB_PARKED_SUM) return block_sum_last<BLOCK>(v);
+    __shared__ double sh[BLOCK];
+    sh[threadIdx.x] = v;
+    if (threadIdx.x >= 32) {
+        asm volatile("barrier.cta.arrive 1, %0;" ::"n"(BLOCK) : "memory");
+        return 0.0;
+    }
+    asm volatile("barrier.cta.sync 1, %0;" ::"n"(BLOCK) : "memory");
+    double s = sh[threadIdx.x];
+#pragma unroll
+    for (int k = 1; k < BLOCK / 32; ++k) s = __dadd_rn(s, sh[threadIdx.x + 32 * k]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    return s;
+}
+
 }  // namespace mgb

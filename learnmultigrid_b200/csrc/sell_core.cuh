@@ -379,7 +379,7 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
     }
     if (MODE == GS_NORM && out.store) y[row] = out.xn;
     if (mode_has_partials(MODE)) {
-        const double s = block_sum_last<BLK>(contrib);
+        const double s = block_sum_parked<BLK>(contrib);
         if (threadIdx.x == 0) partials[bid] = s;
     }
 }

@@ -142,7 +142,10 @@ class DeviceSetup:
         n = A.shape[0]
         avg = B.nnz / max(B.shape[0], 1)
         counts = self.empty(n, t.int32)
-        log_t = 7
+        # the symbolic pass clears and counts a whole table per row: start from the size twice the average number of
+        # products per row asks for (at least 2^5, at most 2^7 as before) and grow on overflow
+        est = 2.0 * (A.nnz / max(n, 1)) * avg
+        log_t = min(7, max(5, int(np.ceil(np.log2(max(2.0 * est, 2.0))))))
         while True:
             g = self._group_for(avg, log_t, False)
             self._flag.zero_()
@@ -452,6 +455,8 @@ def setup_device(h, A, Q_list, colors, dense_coarse_max):
         h.levels.append(build_replicated_level(h, S, l, L, A_host0, A_nat, Q_nat, QT_nat, perms, iperms, cptrs,
                                                dense_coarse_max))
         tm.mark("coarsest factorisation" if l == L - 1 else "permute + SELL build")
+    for k, v in (getattr(getattr(h.levels[-1], "coarse", None), "timing", None) or {}).items():
+        tm.phases["coarsest: " + k] = v          # the split of "coarsest factorisation"
     h.setup_timing = tm.phases
     h.setup_galerkin = tm.galerkin_levels
     h.host_A = None

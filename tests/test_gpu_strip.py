@@ -105,19 +105,15 @@ def test_device_first_fit_colouring_equals_the_host_helper(torch_mod):
     mats.append(F.canonical_csr(P.irregular_p1_2d(64)["A"]))
     mats.append(F.canonical_csr(sp.random(3000, 3000, density=0.003, random_state=1, format="csr")
                                 + sp.diags((np.arange(3000) % 5 > 0) * 1.0)))
-    lib = _lib.load()
     for M in mats:
         want, nc = F.greedy_colors(M)
-        # work lists walked by the persistent cluster kernel (default), by one launch per round (0), and by the two in
-        # alternation (lists of more than 40 rows go to the wide grid)
-        for frontier in (None, 0, 40):
-            old = lib.mg_set_color_cluster_frontier(-1 if frontier is None else frontier)
-            try:
-                got = np.asarray(S.first_fit_colors(S.upload(M)))
-            finally:
-                lib.mg_set_color_cluster_frontier(old)
-            assert np.array_equal(got, want), frontier
-            assert S.last_color_rounds >= 1
+        got = np.asarray(S.first_fit_colors(S.upload(M)))
+        assert np.array_equal(got, want)
+        assert S.last_color_rounds >= 1
+        # the hierarchy setup keeps the colours on the device and hands the colouring the pattern of A^T it already has
+        AT = S.transpose(S.upload(M))
+        dev_col = S.first_fit_colors(S.upload(M), t_pattern=(AT.indptr, AT.indices), host=False)
+        assert dev_col.is_cuda and np.array_equal(dev_col.cpu().numpy(), want)
     chain = F.canonical_csr(sp.diags([np.ones(4999), 2 * np.ones(5000), np.ones(4999)], [-1, 0, 1], format="csr"))
     with pytest.raises(_lib.MgError):
         S.first_fit_colors(S.upload(chain), max_rounds=1000)
