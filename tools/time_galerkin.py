@@ -79,8 +79,14 @@ def main():
             assert int(S._flag.item()) == 0
         with Timed(tag + " non-zero scan"):
             optr, ototal = S.scan(nzc, n)
-        assert ototal == total, "zero pruning would run here"
-        return SD.DevCSR((n, Y.shape[1]), cptr, cidx, cval)
+        if ototal == total:
+            return SD.DevCSR((n, Y.shape[1]), cptr, cidx, cval)
+        with Timed(tag + " pruning of exact zeros"):
+            oidx = S.empty(ototal, t.int32)
+            oval = S.empty(ototal, t.float64)
+            lib.mg_csr_compact_nonzeros(n, cptr.data_ptr(), cidx.data_ptr(), cval.data_ptr(), optr.data_ptr(),
+                                        oidx.data_ptr(), oval.data_ptr(), S.st())
+        return SD.DevCSR((n, Y.shape[1]), optr, oidx, oval)
 
     t0 = time.perf_counter()
     with Timed("transpose A"):
