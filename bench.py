@@ -572,8 +572,10 @@ def run_b200(a):
     if os.path.exists(tpath) and world == 1 and lev0.color_ptr is not None:
         t = json.load(open(tpath))
         vdict = getattr(lev0.A, "val_idx", None) is not None and os.environ.get("MGB_VALUE_DICT", "1") != "0"
+        impv = (getattr(lev0.A, "rec_vals", None) is not None and implied and vdict
+                and os.environ.get("MGB_IMPLIED_VALUES", "1") != "0")
         if (t.get("n") == n and t.get("coefficient") == a.coefficient and bool(t.get("implied_columns")) == implied
-                and bool(t.get("value_dictionary")) == vdict):
+                and bool(t.get("value_dictionary")) == vdict and bool(t.get("implied_values")) == impv):
             traffic = t["traffic_per_launch"]
             traffic_src = "stored ncu --set full capture (%s), not measured in this run" % t.get("source", tpath)
     per_gpu = world if part else 1
@@ -587,6 +589,8 @@ def run_b200(a):
                 "bytes_per_launch": sweep_bytes / nlaunch, "launches_per_sweep": nlaunch,
                 "ms_per_launch": ms_sweep / nlaunch,
                 "implied_columns": implied,
+                "implied_values": getattr(lev0.A, "rec_vals", None) is not None and implied
+                and os.environ.get("MGB_IMPLIED_VALUES", "1") != "0" and os.environ.get("MGB_VALUE_DICT", "1") != "0",
                 # what the kernel actually streams (values + columns or per-slice offsets + b, x in, x out): the
                 # algorithmic yardstick above stays the CSR bytes of SURVEY 8d, so byte-saving shows as frac > 1
                 "moved_bytes_per_launch": sweep_moved / nlaunch,

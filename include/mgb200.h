@@ -113,6 +113,12 @@ typedef struct {
      * entry instead of eight (mg_set_value_dict); the doubles are the same, so are the results. */
     const unsigned char *d_val_idx;
     const double *d_val_table;
+    /* optional implied values (NULL: none; needs the two above): the 32 rows of every slice with a record id also hold
+     * the same VALUE per entry, d_rec_vals[8 * id + j] -- on a constant-coefficient stencil level the record stands for
+     * the whole slice of the matrix, and a slice that is regular in its columns but not in its values carries 0xffff.
+     * h_spec_vals[8 * k + j]: the values of the record h_spec_rec[9 * k], passed by value like its offsets. */
+    const double *d_rec_vals;
+    const double *h_spec_vals;
 } mg_sell;
 
 /* Implied columns (default on; results identical): on a uniform matrix with <= 8 entries per row, slices whose
@@ -133,6 +139,10 @@ int64_t mg_value_dict_workspace(void);
 int mg_value_dict_build(int64_t n, const double *d_vals, unsigned char *d_index, double *d_table, void *d_work,
                         int *h_count, void *stream);
 int mg_set_value_dict(int enabled);
+/* Implied values (default 1; results identical): launches over matrices that carry value records (mg_sell.d_rec_vals)
+ * read nothing per row of a regular slice but the vectors; 0: they read the dictionary bytes.  Returns the previous
+ * setting. */
+int mg_set_implied_values(int enabled);
 int mg_set_implied_columns(int enabled);
 /* launches of fewer rows keep loading their columns (one dependent load less on latency-bound launches); returns the
  * previous floor (default 2^19) */

@@ -33,7 +33,8 @@ class mg_sell(ctypes.Structure):
                 ("d_slice_ptr", c_vp), ("d_cols", c_vp), ("d_vals", c_vp), ("max_slice_len", c_i64),
                 ("uniform_len", c_i64), ("d_slice_rec", c_vp), ("d_rec_table", c_vp),
                 ("nrec", ctypes.c_int32), ("n_spec", ctypes.c_int32), ("h_spec_row", ctypes.POINTER(c_i64)),
-                ("h_spec_rec", ctypes.POINTER(ctypes.c_int32)), ("d_val_idx", c_vp), ("d_val_table", c_vp)]
+                ("h_spec_rec", ctypes.POINTER(ctypes.c_int32)), ("d_val_idx", c_vp), ("d_val_table", c_vp),
+                ("d_rec_vals", c_vp), ("h_spec_vals", ctypes.POINTER(c_dbl))]
 
 
 class mg_bcr(ctypes.Structure):
@@ -126,6 +127,7 @@ _SIGNATURES = {
     "mg_value_dict_workspace": (c_i64, []),
     "mg_value_dict_build": (c_int, [c_i64, c_vp, c_vp, c_vp, c_vp, ctypes.POINTER(c_int), c_vp]),
     "mg_set_value_dict": (c_int, [c_int]),
+    "mg_set_implied_values": (c_int, [c_int]),
     "mg_set_short_rows_per_thread": (c_int, [c_int]),
     "mg_set_short_min_rows": (c_i64, [c_i64]),
     "mg_level_inspect": (c_int, [ctypes.POINTER(mg_sell), c_int, c_vp, c_vp, c_vp, c_vp]),
@@ -282,6 +284,8 @@ def load():
         lib.mg_set_implied_min_rows(int(os.environ["MGB_IMPLIED_MIN_ROWS"]))
     if os.environ.get("MGB_VALUE_DICT", "1") == "0":
         lib.mg_set_value_dict(0)
+    if os.environ.get("MGB_IMPLIED_VALUES", "1") == "0":
+        lib.mg_set_implied_values(0)
     if "MGB_SHORT_ROWS" in os.environ:
         lib.mg_set_short_rows_per_thread(int(os.environ["MGB_SHORT_ROWS"]))
     if os.environ.get("MGB_CYCLE_FUSION", "1") == "0":

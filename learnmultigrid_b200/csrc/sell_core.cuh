@@ -9,6 +9,7 @@
 // The templates are instantiated per group of modes in sell_kernels.cu / sell_modes_gs.cu / sell_modes_vec.cu (three
 // translation units so that the ~500 specialisations compile in parallel).
 #pragma once
+#include <type_traits>
 #include "exchange.cuh"
 #include "sell_api.cuh"
 
@@ -23,6 +24,10 @@ struct SellArgs {
     int32_t spec_id;                               // the record this launch expects (most of its slices use it)
     int32_t spec_off[8];                           // ... and its offsets, by value
     int32_t spec_lo, spec_hi;                      // rows in [lo, hi] keep every row + spec_off[j] inside the vector
+    const double *__restrict__ rec_vals;           // implied values (IMPV kernels): [nrec][8] values of a record's entries
+    double spec_val[8];                            // ... those of the expected record, by value
+    double spec_diag;                              // ... its diagonal entry (the entries with offset 0, bits OR-ed)
+    uint32_t spec_dmask;                           // ... and which entries those are (bit j: offset 0, value != 0)
     const unsigned char *__restrict__ vidx;  // value dictionary (VAL8 kernels): one byte per entry, laid out like vals
     const double *__restrict__ vtab;         // ... indexing this table of at most 256 doubles
     int64_t row_begin;   // first row this launch touches
@@ -48,6 +53,12 @@ __host__ __device__ constexpr bool mode_is_tail(int m) { return m == GS_RES || m
 // memory).  Without that, every thread would pay two dependent DRAM round trips (record, then x).  The values, the gathers and the order of the additions are untouched, so the
 // results are the same bits; slices that are not regular (a boundary node among the rows, the ragged tail) take the
 // ordinary path inside the same kernel.  Uniform matrices with at most 8 entries per row only.
+// IMPLIED VALUES (IMPV, on top of implied columns and a value dictionary): on a constant-coefficient stencil level the
+// 32 rows of a regular slice also hold the same VALUE per entry, so the record stands for the whole slice of the matrix
+// (mg_sell.d_rec_vals): nothing is read per row but the vectors -- 23 instead of 28 bytes per 5-point row -- and the
+// values of the expected record are kernel parameters, i.e. operands straight from the constant bank: fifteen
+// instructions per row less in kernels that are bound by instruction issue.  Slices of another record take its values
+// from the table, irregular ones their dictionary bytes, inside the same kernel; same doubles, same order, same bits.
 constexpr int32_t kSliceIrregular = INT32_MIN;
 constexpr int kOffStride = 8;      // ints per offset record (rows of at most 8 entries)
 constexpr int kRecIrregular = 0xffff; // d_slice_rec value of a slice whose columns are not implied
@@ -81,7 +92,7 @@ struct RowOut {
 
 // VAL8: the values come from the matrix' dictionary (valdict.cu): one byte per entry from DRAM, the double from a
 // 2 KB table that stays in L1 -- the same doubles, 7 bytes per entry less.
-template <int MODE, int LEN, bool PRED, bool IMPL, bool VAL8, bool STAB>
+template <int MODE, int LEN, bool PRED, bool IMPL, bool VAL8, bool STAB, bool IMPV = false>
 __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_t slice, int len, const double *x,
                                           int32_t row, bool active, const SellEp &E, double &contrib,
                                           unsigned char halo_wait, const ExArgs *fx, RowOut &out, double *stab) {
@@ -114,10 +125,13 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_
             if (MODE == JACOBI) prefetch_row_operand(x + row);
         }
     }
+    static_assert(!IMPV || (IMPL && VAL8 && !STAB && !PRED), "implied values ride on implied columns and a dictionary");
     int32_t cc[LEN];
     double vv[LEN], xx[LEN];
     unsigned ii[VAL8 ? LEN : 1];
-    if (VAL8) {
+    if (IMPV) {
+        // nothing to load: the values are the launch's record (below) or, for the few other slices, fetched there
+    } else if (VAL8) {
 #pragma unroll
         for (int j = 0; j < LEN; ++j)
             if (!PRED || j < len) ii[j] = ld_stream_u8(vi + j * kSlice);
@@ -160,103 +174,132 @@ __device__ __forceinline__ void short_row(const SellArgs &A, int64_t ent, int64_
         for (int j = 0; j < LEN; ++j)
             if (!PRED || j < len) vv[j] = stab[ii[j]];
     }
-    if (IMPL && rec != (unsigned)A.spec_id) {      // warp-uniform and rare: this slice uses another record, or none
+    const bool other = IMPL && rec != (unsigned)A.spec_id;
+    if (other) {                                   // warp-uniform and rare: this slice uses another record, or none
         if (rec == (unsigned)kRecIrregular) {
 #pragma unroll
             for (int j = 0; j < LEN; ++j) cc[j] = ld_stream(c + j * kSlice);
+            if (IMPV) {
+#pragma unroll
+                for (int j = 0; j < LEN; ++j) ii[j] = ld_stream_u8(vi + j * kSlice);
+#pragma unroll
+                for (int j = 0; j < LEN; ++j) vv[j] = __ldg(A.vtab + ii[j]);
+            }
         } else {
             const int32_t *__restrict__ o = A.rec_table + rec * kOffStride;
 #pragma unroll
             for (int j = 0; j < LEN; ++j) cc[j] = row + __ldg(o + j);
+            if (IMPV) {
+                const double *__restrict__ rv = A.rec_vals + rec * kOffStride;
+#pragma unroll
+                for (int j = 0; j < LEN; ++j) vv[j] = __ldg(rv + j);
+            }
         }
 #pragma unroll
         for (int j = 0; j < LEN; ++j) xx[j] = (mode_is_gs(MODE) && cc[j] == row) ? 0.0 : x[cc[j]];
     }
-    double sum = 0.0;
-    // GS_RES keeps the separately rounded products (the slot of the diagonal entry flagged in dmask) instead of the row
-    // itself: 2 registers per entry across the division instead of 5.
-    // Gauss-Seidel family, branch-free: the diagonal entry was "gathered" as +0.0, so its product is an exact zero, and
-    // adding a zero never changes a sum that started at +0.0 (such a sum is never -0.0): the sum has the bits of the
-    // oracle's, which skips the entry.  The diagonal VALUE is collected by OR-ing bit patterns: a row has one stored
-    // diagonal entry; padding that repeats its column carries +0.0, i.e. no bits (the old test `value != 0`).
-    double pp[MODE == GS_RES ? LEN : 1];
-    unsigned dmask = 0;
-    unsigned long long dbits = 0ull;
+    // The rest of the row -- products, sums, epilogue -- as a function of where values, gathered entries and columns
+    // come from: the kernels with implied values run it on the launch's value record (kernel parameters: operands
+    // straight from the constant bank, no register copies) for the slices that use it and on loaded values for the
+    // others; everything else runs it once.
+    // `known`: the row belongs to a slice of the launch's record, so which entry is the diagonal and what it holds are
+    // launch constants too (spec_diag / spec_dmask) instead of five compares, ten selects and four ORs per row.
+    auto finish = [&](auto known, const double (&vv)[LEN], const double (&xx)[LEN], const int32_t (&cc)[LEN]) {
+        constexpr bool KD = decltype(known)::value;
+        double sum = 0.0;
+        // GS_RES keeps the separately rounded products (the slot of the diagonal entry flagged in dmask) instead of the row
+        // itself: 2 registers per entry across the division instead of 5.
+        // Gauss-Seidel family, branch-free: the diagonal entry was "gathered" as +0.0, so its product is an exact zero, and
+        // adding a zero never changes a sum that started at +0.0 (such a sum is never -0.0): the sum has the bits of the
+        // oracle's, which skips the entry.  The diagonal VALUE is collected by OR-ing bit patterns: a row has one stored
+        // diagonal entry; padding that repeats its column carries +0.0, i.e. no bits (the old test `value != 0`).
+        double pp[MODE == GS_RES ? LEN : 1];
+        unsigned dmask = KD ? A.spec_dmask : 0u;
+        unsigned long long dbits = 0ull;
 #pragma unroll
-    for (int j = 0; j < LEN; ++j) {
-        if (!PRED || j < len) {
-            if (mode_is_gs(MODE)) {
-                const bool is_d = cc[j] == row;
-                const double p = __dmul_rn(vv[j], xx[j]);
-                sum = __dadd_rn(sum, p);
-                dbits |= is_d ? (unsigned long long)__double_as_longlong(vv[j]) : 0ull;
-                if (MODE == GS_RES) {
-                    pp[j] = p;
-                    dmask |= (is_d && vv[j] != 0.0) ? (1u << j) : 0u;
+        for (int j = 0; j < LEN; ++j) {
+            if (!PRED || j < len) {
+                if (mode_is_gs(MODE)) {
+                    const bool is_d = cc[j] == row;
+                    const double p = __dmul_rn(vv[j], xx[j]);
+                    sum = __dadd_rn(sum, p);
+                    if (!KD) dbits |= is_d ? (unsigned long long)__double_as_longlong(vv[j]) : 0ull;
+                    if (MODE == GS_RES) {
+                        pp[j] = p;
+                        if (!KD) dmask |= (is_d && vv[j] != 0.0) ? (1u << j) : 0u;
+                    }
+                } else {
+                    sum = mul_add_unfused(sum, vv[j], xx[j]);
                 }
-            } else {
-                sum = mul_add_unfused(sum, vv[j], xx[j]);
             }
         }
-    }
-    const double diag = __longlong_as_double((long long)dbits);
-    if (!active) return;
-    if (!kEarly) {
-        if (kUsesB) bv = E.b[row];
-        if (kUsesAux) av = E.aux[row];
-        if (MODE == JACOBI) xr = x[row];
-    }
-    if (MODE == SPMV) {
-        E.y[row] = sum;
-    } else if (MODE == SPMV_DOT) {
-        E.y[row] = sum;
-        contrib = av * sum;
-    } else if (MODE == RESID) {
-        E.y[row] = __dsub_rn(bv, sum);
-    } else if (MODE == RESNORM) {
-        const double r = __dsub_rn(bv, sum);
-        contrib = r * r;
-    } else if (MODE == JACOBI) {
-        const double r = __dsub_rn(bv, sum);
-        E.y[row] = __dadd_rn(xr, __dmul_rn(E.omega, __dmul_rn(av, r)));
-    } else if (MODE == PROLONG) {
-        E.y[row] = __dadd_rn(av, sum);   // aux = u (may alias y)
-    } else {                             // Gauss-Seidel family
-        const bool upd = diag != 0.0;
-        double xn = 0.0;
-        if (upd) {
-            xn = __ddiv_rn(__dsub_rn(bv, sum), diag);
-            if (MODE == GS_NORM) {
-                out.xn = xn;
-                out.store = true;
-            } else {
-                E.y[row] = xn;
-            }
+        const double diag = KD ? A.spec_diag : __longlong_as_double((long long)dbits);
+        if (!active) return;
+        if (!kEarly) {
+            if (kUsesB) bv = E.b[row];
+            if (kUsesAux) av = E.aux[row];
+            if (MODE == JACOBI) xr = x[row];
         }
-        if (MODE == GS_RES) {
-            // residual of the row with its new value: the products in storage order, the diagonal entry times the new
-            // iterate in its place (selects, no branches).  A diagonal entry of a row that was not updated is a stored
-            // zero: xn is 0 then and the term an exact zero, which changes nothing (a sum that starts at +0 never
-            // becomes -0).  These are the bits of the residual pass: the restriction reads them.
-            double s2 = 0.0;
-            const double dx = __dmul_rn(diag, xn);
-#pragma unroll
-            for (int j = 0; j < LEN; ++j)
-                if (!PRED || j < len) {
-                    const double t = ((dmask >> j) & 1u) ? dx : pp[j];
-                    s2 = __dadd_rn(s2, t);
-                }
-            A.r_out[row] = __dsub_rn(bv, s2);
-        }
-        if (MODE == GS_NORM) {
-            // The swept row's share of ||b - A x||^2.  Only the NORM is wanted here (a history value compared at
-            // 1e-12, summed in an order of its own anyway), so the row's residual is taken as (b - sum) - d x_new in one
-            // fused multiply-add instead of re-adding the products in storage order: the row has just been solved, the
-            // value is rounding noise of size eps |b| either way, and the kernel stays as light as the plain sweep
-            // (ncu: the storage-order version ran at 2.4 TB/s against 3.9 for the sweep).
-            const double r = upd ? fma(-diag, xn, __dsub_rn(bv, sum)) : __dsub_rn(bv, sum);
+        if (MODE == SPMV) {
+            E.y[row] = sum;
+        } else if (MODE == SPMV_DOT) {
+            E.y[row] = sum;
+            contrib = av * sum;
+        } else if (MODE == RESID) {
+            E.y[row] = __dsub_rn(bv, sum);
+        } else if (MODE == RESNORM) {
+            const double r = __dsub_rn(bv, sum);
             contrib = r * r;
+        } else if (MODE == JACOBI) {
+            const double r = __dsub_rn(bv, sum);
+            E.y[row] = __dadd_rn(xr, __dmul_rn(E.omega, __dmul_rn(av, r)));
+        } else if (MODE == PROLONG) {
+            E.y[row] = __dadd_rn(av, sum);   // aux = u (may alias y)
+        } else {                             // Gauss-Seidel family
+            const bool upd = diag != 0.0;
+            double xn = 0.0;
+            if (upd) {
+                xn = __ddiv_rn(__dsub_rn(bv, sum), diag);
+                if (MODE == GS_NORM) {
+                    out.xn = xn;
+                    out.store = true;
+                } else {
+                    E.y[row] = xn;
+                }
+            }
+            if (MODE == GS_RES) {
+                // residual of the row with its new value: the products in storage order, the diagonal entry times the new
+                // iterate in its place (selects, no branches).  A diagonal entry of a row that was not updated is a stored
+                // zero: xn is 0 then and the term an exact zero, which changes nothing (a sum that starts at +0 never
+                // becomes -0).  These are the bits of the residual pass: the restriction reads them.
+                double s2 = 0.0;
+                const double dx = __dmul_rn(diag, xn);
+#pragma unroll
+                for (int j = 0; j < LEN; ++j)
+                    if (!PRED || j < len) {
+                        const double t = ((dmask >> j) & 1u) ? dx : pp[j];
+                        s2 = __dadd_rn(s2, t);
+                    }
+                A.r_out[row] = __dsub_rn(bv, s2);
+            }
+            if (MODE == GS_NORM) {
+                // The swept row's share of ||b - A x||^2.  Only the NORM is wanted here (a history value compared at
+                // 1e-12, summed in an order of its own anyway), so the row's residual is taken as (b - sum) - d x_new in one
+                // fused multiply-add instead of re-adding the products in storage order: the row has just been solved, the
+                // value is rounding noise of size eps |b| either way, and the kernel stays as light as the plain sweep
+                // (ncu: the storage-order version ran at 2.4 TB/s against 3.9 for the sweep).
+                const double r = upd ? fma(-diag, xn, __dsub_rn(bv, sum)) : __dsub_rn(bv, sum);
+                contrib = r * r;
+            }
         }
+    };
+    if (IMPV && !other) {
+        double vs[LEN];
+#pragma unroll
+        for (int j = 0; j < LEN; ++j) vs[j] = A.spec_val[j];
+        finish(std::true_type{}, vs, xx, cc);
+    } else {
+        finish(std::false_type{}, vv, xx, cc);
     }
 }
 
@@ -292,7 +335,7 @@ __device__ __forceinline__ void row_chunk(const int32_t *__restrict__ c, const d
 // The microbenchmark behind these choices is tools/sellbench.cu (profiles/r01_sellbench.log): occupancy x bytes in
 // flight per thread decides; at 32 registers and 60 B per thread the fine-level sweep reaches the DRAM limit
 // (6.8 TB/s algorithmic, ~7.1 TB/s of actual traffic), a rolled loop stays at 5.4 TB/s.
-template <int MODE, int LEN, bool UNIFORM, bool FUSED, bool IMPL, bool VAL8>
+template <int MODE, int LEN, bool UNIFORM, bool FUSED, bool IMPL, bool VAL8, bool IMPV = false>
 __device__ __forceinline__ void
 sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
           double *__restrict__ partials, int64_t bid, const ExArgs *fx, const unsigned char *__restrict__ mask) {
@@ -302,7 +345,7 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
     constexpr int BLK = FUSED ? kBlock : kSellBlock;
     // the value dictionary sits in shared memory when every warp of the CTA takes the same path to the barrier that
     // publishes it (uniform matrices) and the CTA has one thread per table entry
-    constexpr bool STAB = kSharedDict && VAL8 && UNIFORM && LEN > 0 && BLK == 256;
+    constexpr bool STAB = kSharedDict && VAL8 && UNIFORM && LEN > 0 && BLK == 256 && !IMPV;
     __shared__ double stab[STAB ? 256 : 1];
     // rows are 32-bit here (the launcher refuses matrices of 2^31 rows or more; column indices are int32 anyway): one
     // instruction per address instead of four
@@ -333,7 +376,7 @@ sell_body(const SellArgs &A, const double *x, const double *__restrict__ b, cons
             constexpr int L = LEN > 0 ? LEN : 1;
             const SellEp E{b, aux, y, omega};
             if (IMPL) {
-                short_row<MODE, L, false, true, VAL8, STAB>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out, stab);
+                short_row<MODE, L, false, true, VAL8, STAB, IMPV>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out, stab);
             } else if (UNIFORM || len == L) {
                 short_row<MODE, L, false, false, VAL8, STAB>(A, base + lane, slice, L, x, row, active, E, contrib, hw, fx, out, stab);
             } else {
@@ -396,12 +439,12 @@ __host__ __device__ constexpr int mode_min_ctas(int m, int len, bool uniform, bo
     return (impl && len <= 7) ? 6 : 1;
 }
 
-template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8>
+template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8, bool IMPV = false>
 __global__ void __launch_bounds__(kSellBlock, mode_min_ctas(MODE, LEN, UNIFORM, IMPL) * (kBlock / kSellBlock))
 sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const double *aux,
             double *y, double omega, double *__restrict__ partials) {
     pdl_prologue();
-    sell_body<MODE, LEN, UNIFORM, false, IMPL, VAL8>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
+    sell_body<MODE, LEN, UNIFORM, false, IMPL, VAL8, IMPV>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x, nullptr, nullptr);
 }
 
 // Very short rows (linear transfer operators: one or two entries): one row per thread keeps only ~30 bytes per thread in
@@ -482,7 +525,7 @@ __host__ __device__ constexpr int fused_min_ctas(int m, int len, bool uniform, b
     return mode_min_ctas(m, len, uniform, impl);
 }
 
-template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8>
+template <int MODE, int LEN, bool UNIFORM, bool IMPL, bool VAL8, bool IMPV = false>
 __global__ void __launch_bounds__(kBlock, fused_min_ctas(MODE, LEN, UNIFORM, IMPL))
 sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, const double *aux, double *y, double omega,
                   double *__restrict__ partials, const ExArgs fx, const unsigned char *__restrict__ mask) {
@@ -493,7 +536,7 @@ sell_kernel_fused(SellArgs A, const double *x, const double *__restrict__ b, con
         if (mode_has_partials(MODE)) {}      // exchange CTAs own no partial sum
         return;
     }
-    sell_body<MODE, LEN, UNIFORM, true, IMPL, VAL8>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
+    sell_body<MODE, LEN, UNIFORM, true, IMPL, VAL8, IMPV>(A, x, b, aux, y, omega, partials, (int64_t)blockIdx.x - nex, &fx, mask);
 }
 
 // ---- long rows: four warps per slice ---------------------------------------------------------------------------------
@@ -625,6 +668,7 @@ extern int64_t g_tma_min_rows;      // rows per launch from which the bulk-async
 extern int g_implied_columns;       // use the offset tables of matrices that carry one
 extern int64_t g_implied_min_rows;  // ... for launches of at least this many rows
 extern int g_value_dict;            // use the value dictionaries of matrices that carry one
+extern int g_implied_values;        // use the value records of matrices that carry them (on top of the two above)
 extern int g_short_rows_per_thread; // rows per thread of sell_short_kernel (1 = off, 2 or 4)
 extern int64_t g_short_min_rows;    // ... for launches of at least this many rows
 
@@ -655,6 +699,10 @@ inline SellArgs sell_args(const mg_sell *A, int64_t row0, int64_t row1, double *
     a.spec_hi = (int32_t)(A->ncols > 0 ? A->ncols - 1 : 0);
     a.vidx = A->d_val_idx;
     a.vtab = A->d_val_table;
+    a.rec_vals = A->d_rec_vals;
+    for (int j = 0; j < 8; ++j) a.spec_val[j] = 0.0;
+    a.spec_diag = 0.0;
+    a.spec_dmask = 0;
     a.row_begin = row0;
     a.row_end = row1;
     a.first_row = row0 & ~(int64_t)(kSlice - 1);
@@ -691,6 +739,22 @@ inline void sell_pick_spec(const mg_sell *A, int64_t row0, SellArgs &a) {
             for (int j = 0; j < 8; ++j) a.spec_off[j] = A->h_spec_rec[9 * k + 1 + j];
             a.spec_lo = (int32_t)lo;
             a.spec_hi = (int32_t)hi;
+            if (A->h_spec_vals) {
+                // the record's diagonal as the kernels find it: the entries in the row's own column, bit patterns OR-ed
+                // (a row stores one; padding that repeats the column holds +0.0)
+                unsigned long long bits = 0ull;
+                for (int j = 0; j < 8; ++j) {
+                    const double vj = A->h_spec_vals[8 * k + j];
+                    a.spec_val[j] = vj;
+                    if (j < A->uniform_len && a.spec_off[j] == 0) {
+                        unsigned long long b;
+                        memcpy(&b, &vj, sizeof(b));
+                        bits |= b;
+                        if (vj != 0.0) a.spec_dmask |= 1u << j;
+                    }
+                }
+                memcpy(&a.spec_diag, &bits, sizeof(bits));
+            }
             return;
         }
 }
@@ -764,6 +828,8 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
     }
     const bool impl = sell_use_implied(A, row0, row1);
     const bool dict = sell_use_dict(A);
+    // implied values: the launch must carry an expected record (its values travel as kernel parameters)
+    const bool impv = impl && dict && g_implied_values && A->d_rec_vals && A->h_spec_vals && a.spec_id >= 0;
 #define MG_SELL_LAUNCH(L, U, I, V)                                                                                       \
     do {                                                                                                                 \
         if (fuse) launch_k(sell_kernel_fused<MODE, L, U, I, V>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
@@ -775,9 +841,15 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
         else if (uni) MG_SELL_LAUNCH(L, true, false, V);  \
         else MG_SELL_LAUNCH(L, false, false, V);          \
     } while (0)
+#define MG_SELL_IMPV(L)                                                                                                  \
+    do {                                                                                                                 \
+        if (fuse) launch_k(sell_kernel_fused<MODE, L, true, true, true, true>, (unsigned)(grid + fuse->nex), kBlock, st, a, x, b, aux, y, omega, partials, fuse->ex, fuse->mask); \
+        else launch_k(sell_kernel<MODE, L, true, true, true, true>, (unsigned)grid, kSellBlock, st, a, x, b, aux, y, omega, partials); \
+    } while (0)
 #define MG_SELL_CASE(L)                                   \
     case L:                                               \
-        if (dict) MG_SELL_VARIANT(L, true);               \
+        if (impv) MG_SELL_IMPV(L);                        \
+        else if (dict) MG_SELL_VARIANT(L, true);          \
         else MG_SELL_VARIANT(L, false);                   \
         break
     switch (ml) {
@@ -788,6 +860,7 @@ static int launch_sell(const mg_sell *A, const double *x, const double *b, const
             else return set_error(MG_ERR_INVALID, name, "rows too long for a sweep with a fused residual");
     }
 #undef MG_SELL_CASE
+#undef MG_SELL_IMPV
 #undef MG_SELL_VARIANT
 #undef MG_SELL_LAUNCH
     MG_CHECK_LAUNCH(name);

@@ -16,6 +16,7 @@ int64_t g_tma_min_rows = 0;          // off by default: the register-staged kern
 int g_implied_columns = 1;
 int64_t g_implied_min_rows = 1 << 19;
 int g_value_dict = 1;                // value dictionaries (valdict.cu) are used where a matrix carries one
+int g_implied_values = 1;            // value records (sell_core.cuh, IMPV) are used where a matrix carries them
 // rows of one or two entries (linear transfers): R rows per thread on large launches (sell_short_kernel)
 int g_short_rows_per_thread = 2;
 int64_t g_short_min_rows = 1 << 18;
@@ -257,6 +258,11 @@ int64_t mg_set_implied_min_rows(int64_t rows) {
 int mg_set_value_dict(int enabled) {
     const int prev = g_value_dict;
     g_value_dict = enabled ? 1 : 0;
+    return prev;
+}
+int mg_set_implied_values(int enabled) {
+    const int prev = g_implied_values;
+    g_implied_values = enabled ? 1 : 0;
     return prev;
 }
 int mg_set_short_rows_per_thread(int r) {

@@ -42,8 +42,8 @@ class DeviceSell:
         self.struct = _lib.mg_sell(self.shape[0], self.shape[1], (self.shape[0] + 31) // 32,
                                    self.slice_ptr.data_ptr(), self.cols.data_ptr(), self.vals.data_ptr(),
                                    self.max_len, self.uniform_len)
-        self._attach_slice_offsets()
         self._attach_value_dict()
+        self._attach_slice_offsets()
 
     VALUE_DICT_MIN_ROWS = 1 << 16      # smaller matrices are latency-bound launches: a dictionary buys nothing there
 
@@ -81,7 +81,7 @@ class DeviceSell:
         keeps two bytes (the id of its record, 0xffff = not regular) and the records sit in a table, most frequent
         first.  Kept when at least half of the slices are regular (structured stencil levels: ~99 %; unstructured
         numberings: none).  MGB_IMPLIED_COLUMNS=0 switches it off."""
-        self.slice_rec = self.rec_table = None
+        self.slice_rec = self.rec_table = self.rec_vals = None
         self.regular_slices = 0
         self._spec_keep = None
         floor = int(os.environ.get("MGB_IMPLIED_MIN_ROWS", self.IMPLIED_MIN_ROWS))
@@ -100,7 +100,24 @@ class DeviceSell:
             return
         off = off.view(nsl, 8)
         regular = off[:, 0] != _lib.SLICE_IRREGULAR
-        recs, inverse, counts = torch.unique(off[regular], dim=0, return_inverse=True, return_counts=True)
+        # Implied values (sell_core.cuh, IMPV): with a value dictionary, look whether the 32 rows of a slice also hold
+        # the same value per entry.  On a constant-coefficient stencil level that is every slice without a boundary
+        # node; the record then carries the values as well (their dictionary indices take part in the deduplication)
+        # and a slice that is regular in its columns only counts as irregular.  Kept when that loses at most a tenth
+        # of the regular slices (variable coefficients have no dictionary to begin with).  MGB_IMPLIED_VALUES=0: off.
+        vrec = None
+        if (self.val_idx is not None and os.environ.get("MGB_IMPLIED_VALUES", "1") != "0"
+                and self.val_idx.numel() == nsl * 32 * self.uniform_len):
+            v = self.val_idx.view(nsl, self.uniform_len, 32)
+            same = (v == v[:, :, :1]).all(dim=2).all(dim=1)
+            full = regular & same
+            if 10 * int(full.sum().item()) >= 9 * self.regular_slices:
+                vrec = torch.zeros(nsl, 8, dtype=torch.int32, device=dev)
+                vrec[:, :self.uniform_len] = v[:, :, 0].to(torch.int32)
+                regular = full
+            del v, same, full
+        keys = off if vrec is None else torch.cat([off, vrec], dim=1)
+        recs, inverse, counts = torch.unique(keys[regular], dim=0, return_inverse=True, return_counts=True)
         order = torch.argsort(counts, descending=True)[:32766]          # ids by frequency; -1 (0xffff) = irregular
         rank_of = torch.full((recs.shape[0],), -1, dtype=torch.int64, device=dev)
         rank_of[order] = torch.arange(order.numel(), device=dev)
@@ -108,10 +125,13 @@ class DeviceSell:
         ids[regular] = rank_of[inverse].to(torch.int16)
         self.regular_slices = int((ids >= 0).sum().item())
         self.slice_rec = ids
-        self.rec_table = recs[order].contiguous().to(torch.int32)
+        self.rec_table = recs[order][:, :8].contiguous().to(torch.int32)
         self.struct.d_slice_rec = ids.data_ptr()
         self.struct.d_rec_table = self.rec_table.data_ptr()
         self.struct.nrec = int(self.rec_table.shape[0])
+        if vrec is not None:
+            self.rec_vals = self.val_table[recs[order][:, 8:16].long()].contiguous()      # [nrec][8] doubles
+            self.struct.d_rec_vals = self.rec_vals.data_ptr()
         self.set_spec_blocks([0, self.shape[0]])
 
     @property
@@ -136,8 +156,10 @@ class DeviceSell:
         row_ptr = [int(v) for v in row_ptr]
         nb = len(row_ptr) - 1
         table = self.rec_table.cpu().numpy()
+        vals_table = None if self.rec_vals is None else self.rec_vals.cpu().numpy()
         rows = (ctypes.c_int64 * (nb + 1))(*row_ptr)
         rec = (ctypes.c_int32 * (9 * max(nb, 1)))()
+        vals = (ctypes.c_double * (8 * max(nb, 1)))()
         for k in range(nb):
             s0, s1 = row_ptr[k] // 32, max((row_ptr[k + 1] + 31) // 32, row_ptr[k] // 32 + 1)
             ids = self.slice_rec[s0:s1]
@@ -146,10 +168,14 @@ class DeviceSell:
             rec[9 * k] = best
             for j in range(8):
                 rec[9 * k + 1 + j] = int(table[best, j])
-        self._spec_keep = (rows, rec)
+                if vals_table is not None:
+                    vals[8 * k + j] = float(vals_table[best, j])
+        self._spec_keep = (rows, rec, vals)
         self.struct.n_spec = nb
         self.struct.h_spec_row = ctypes.cast(rows, ctypes.POINTER(ctypes.c_int64))
         self.struct.h_spec_rec = ctypes.cast(rec, ctypes.POINTER(ctypes.c_int32))
+        if vals_table is not None:
+            self.struct.h_spec_vals = ctypes.cast(vals, ctypes.POINTER(ctypes.c_double))
 
     @classmethod
     def from_device(cls, shape, nnz, slice_ptr, cols, vals, max_len=0, uniform_len=0):
@@ -163,8 +189,8 @@ class DeviceSell:
         self.struct = _lib.mg_sell(shape[0], shape[1], (shape[0] + 31) // 32,
                                    slice_ptr.data_ptr(), cols.data_ptr(), vals.data_ptr(), self.max_len,
                                    self.uniform_len)
-        self._attach_slice_offsets()
         self._attach_value_dict()
+        self._attach_slice_offsets()
         return self
 
     def bytes(self):
@@ -179,6 +205,8 @@ class DeviceSell:
             return self.padded * (4 + vbytes) + (0 if self.uniform_len else self.slice_ptr.numel() * 8)
         per_slice = 32 * self.uniform_len
         irregular = nsl - self.regular_slices
+        if self.rec_vals is not None and os.environ.get("MGB_IMPLIED_VALUES", "1") != "0" and vbytes == 1:
+            return irregular * per_slice * (4 + vbytes) + 2 * nsl          # implied values: regular slices read their id
         return self.padded * vbytes + irregular * per_slice * 4 + 2 * nsl
 
 

@@ -51,7 +51,7 @@ def test_library_loads_and_reports_version():
 
 def test_struct_layouts_match_header_sizes():
     # mg_sell: 3 x int64 + 3 pointers + 2 x int64 + 2 pointers + 2 x int32 + 4 pointers; mg_cycle_params: 3 x int32 (+pad) + double + 3 x int32 (+pad)
-    assert ctypes.sizeof(_lib.mg_sell) == 120
+    assert ctypes.sizeof(_lib.mg_sell) == 136
     assert ctypes.sizeof(_lib.mg_cycle_params) == 40
     assert ctypes.sizeof(_lib.mg_level) % 8 == 0
     lib = _lib.load()

@@ -184,8 +184,9 @@ def _problem(kind, N, levels):
                                                        ("quasi", 64, 3, 1, False), ("quasi", 128, 4, 2, True),
                                                        ("irregular", 32, 3, 3, False), ("linear", 1024, 5, 1, False)])
 def test_fused_cycle_is_bit_identical_to_the_plain_cycle(env, kind, N, levels, nu, reverse):
-    """g_cycle_fusion on/off, implied columns on/off (floor lowered so that small levels use them): same iterates, bit
-    for bit, cycle after cycle; the norm the fused cycle leaves equals the stand-alone residual norm to rounding"""
+    """g_cycle_fusion on/off, implied columns on/off (floor lowered so that small levels use them), value dictionary
+    on/off, implied values on/off: same iterates, bit for bit, cycle after cycle; the norm the fused cycle leaves equals
+    the stand-alone residual norm to rounding"""
     from learnmultigrid_b200.engine import DeviceHierarchy
     lib = env["lib"]
     A, rhs, Qs = _problem(kind, N, levels)
@@ -199,13 +200,19 @@ def test_fused_cycle_is_bit_identical_to_the_plain_cycle(env, kind, N, levels, n
         assert all(f == 3 for f in flags), flags                 # proper colouring, no zero diagonal: everything fuses
         if kind.startswith("linear") and N >= 512:               # (on small grids every slice holds a boundary node)
             assert h.levels[0].A.slice_off is not None           # structured stencil level: implied columns attached
+            # ... and, the coefficient being constant, value records: the regular slices read nothing but their id
+            assert (h.levels[0].A.rec_vals is not None) == (kind == "linear")
+            if kind == "linear":
+                assert h.levels[0].A.regular_slices > 0.9 * h.levels[0].A.struct.nslices
         params = h.make_params(nu_pre=nu, nu_post=nu, reverse_post=reverse)
         results = {}
-        for fusion, implied, vdict in ((0, 0, 0), (1, 0, 0), (0, 1, 0), (1, 1, 0), (0, 0, 1), (1, 1, 1)):
+        for fusion, implied, vdict, impv in ((0, 0, 0, 1), (1, 0, 0, 1), (0, 1, 0, 1), (1, 1, 0, 1), (0, 0, 1, 1),
+                                             (1, 1, 1, 1), (1, 1, 1, 0), (0, 1, 1, 0)):
             if True:
                 lib.mg_set_cycle_fusion(fusion)
                 lib.mg_set_implied_columns(implied)
                 lib.mg_set_value_dict(vdict)
+                lib.mg_set_implied_values(impv)
                 h._graphs = {}
                 h.set_rhs(rhs)
                 h.zero_x()
@@ -217,14 +224,14 @@ def test_fused_cycle_is_bit_identical_to_the_plain_cycle(env, kind, N, levels, n
                     np.testing.assert_allclose(norms[-1], h.residual_norm(), rtol=1e-12)
                 h.vcycle(params, use_graph=False)                # eager, without the norm
                 xs.append(h.levels[0].x.clone())
-                results[(fusion, implied, vdict)] = (xs, norms, h.last_launches)
-        base = results[(0, 0, 0)]
+                results[(fusion, implied, vdict, impv)] = (xs, norms, h.last_launches)
+        base = results[(0, 0, 0, 1)]
         for key, (xs, norms, _) in results.items():
             for a, b_ in zip(xs, base[0]):
                 assert env["torch"].equal(a, b_), key
         assert norms[-1] < norms[0]
         # the fused cycle launches no more kernels than the plain one
-        assert results[(1, 1, 1)][2] <= results[(0, 0, 0)][2]
+        assert results[(1, 1, 1, 1)][2] <= results[(0, 0, 0, 1)][2]
         if kind in ("linear", "linear-var"):                       # linear interpolation: {1, 0.5, 0} -> dictionaries
             assert h.levels[0].Q.val_idx is not None and h.levels[0].Q.distinct_values <= 4
             assert (h.levels[0].A.val_idx is not None) == (kind == "linear")    # variable coefficients: too many values
@@ -232,6 +239,7 @@ def test_fused_cycle_is_bit_identical_to_the_plain_cycle(env, kind, N, levels, n
         lib.mg_set_cycle_fusion(1)
         lib.mg_set_implied_columns(1)
         lib.mg_set_value_dict(1)
+        lib.mg_set_implied_values(1)
         lib.mg_set_implied_min_rows(old_floor)
         os.environ.pop("MGB_IMPLIED_MIN_ROWS", None)
         os.environ.pop("MGB_VALUE_DICT_MIN_ROWS", None)

@@ -6,9 +6,16 @@
 # Usage: gpurun --timeout 1100 -- 'bash tools/gpu_setup_round.sh'
 set -u
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$? $(tail -n 1 gpurun_out/pytest_gpu.log)"
+timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; rc=$?; echo "pytest rc=$rc $(tail -n 1 gpurun_out/pytest_gpu.log)"
+if [ $rc -ne 0 ]; then
+  # the newest kernel variant (implied values) has a switch: is everything else still green without it?
+  tail -n 60 gpurun_out/pytest_gpu.log
+  export MGB_IMPLIED_VALUES=0
+  timeout 600 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu_without_implied_values.log 2>&1; echo "pytest (MGB_IMPLIED_VALUES=0) rc=$? $(tail -n 1 gpurun_out/pytest_gpu_without_implied_values.log)"
+fi
 timeout 600 python bench.py > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
 timeout 300 python bench.py --coefficient variable --no-cpu-baseline --no-e2e --no-extra > gpurun_out/bench_variable.log 2>&1; echo "bench variable rc=$?"
+MGB_IMPLIED_VALUES=0 timeout 300 python bench.py --no-cpu-baseline --no-e2e --no-extra > gpurun_out/bench_variant_no_implied_values.log 2>&1; echo "bench without implied values rc=$?"
 cp learnmultigrid_b200/libmgb200.so /tmp/libmgb200_shipped.so
 for lib in $(ls learnmultigrid_b200/_variants/ 2>/dev/null | sed 's/libmgb200_//; s/\.so//'); do
   cp learnmultigrid_b200/_variants/libmgb200_$lib.so learnmultigrid_b200/libmgb200.so
