@@ -454,7 +454,7 @@ sell_kernel(SellArgs A, const double *x, const double *__restrict__ b, const dou
 // UNIFORM: every slice holds exactly LEN entries per row (transfer operators are padded to that when it costs at most a
 // quarter more entries, mg_sell_layout), so the slice pointer -- the first of the three round trips -- is computed.
 template <int MODE, int LEN, int R, bool VAL8, bool UNIFORM>
-__global__ void __launch_bounds__(kBlock)
+__global__ void __launch_bounds__(kBlock, 6)
 sell_short_kernel(SellArgs A, const double *x, const double *aux, double *y) {
     static_assert(MODE == SPMV || MODE == PROLONG, "short-row kernel: SpMV and prolongation only");
     pdl_prologue();
