@@ -98,39 +98,20 @@ class DeviceSell:
         self.regular_slices = int(cnt.item())
         if 2 * self.regular_slices < nsl:
             return
-        off = off.view(nsl, 8)
-        regular = off[:, 0] != _lib.SLICE_IRREGULAR
-        # Implied values (sell_core.cuh, IMPV): with a value dictionary, look whether the 32 rows of a slice also hold
-        # the same value per entry.  On a constant-coefficient stencil level that is every slice without a boundary
-        # node; the record then carries the values as well (their dictionary indices take part in the deduplication)
-        # and a slice that is regular in its columns only counts as irregular.  Kept when that loses at most a tenth
-        # of the regular slices (variable coefficients have no dictionary to begin with).  MGB_IMPLIED_VALUES=0: off.
-        vrec = None
-        if (self.val_idx is not None and os.environ.get("MGB_IMPLIED_VALUES", "1") != "0"
-                and self.val_idx.numel() == nsl * 32 * self.uniform_len):
-            v = self.val_idx.view(nsl, self.uniform_len, 32)
-            same = (v == v[:, :, :1]).all(dim=2).all(dim=1)
-            full = regular & same
-            if 10 * int(full.sum().item()) >= 9 * self.regular_slices:
-                vrec = torch.zeros(nsl, 8, dtype=torch.int32, device=dev)
-                vrec[:, :self.uniform_len] = v[:, :, 0].to(torch.int32)
-                regular = full
-            del v, same, full
-        keys = off if vrec is None else torch.cat([off, vrec], dim=1)
-        recs, inverse, counts = torch.unique(keys[regular], dim=0, return_inverse=True, return_counts=True)
-        order = torch.argsort(counts, descending=True)[:32766]          # ids by frequency; -1 (0xffff) = irregular
-        rank_of = torch.full((recs.shape[0],), -1, dtype=torch.int64, device=dev)
-        rank_of[order] = torch.arange(order.numel(), device=dev)
-        ids = torch.full((nsl,), -1, dtype=torch.int16, device=dev)     # read as uint16 by the kernels
-        ids[regular] = rank_of[inverse].to(torch.int16)
-        self.regular_slices = int((ids >= 0).sum().item())
+        # Deduplicated records (formats.slice_records).  Implied values (sell_core.cuh, IMPV): with a value dictionary the
+        # records also carry the values where the 32 rows of a slice hold the same value per entry -- on a
+        # constant-coefficient stencil level that is every slice without a boundary node -- and a slice that is regular
+        # in its columns only then counts as irregular; kept when that loses at most a tenth of the regular slices
+        # (variable coefficients have no dictionary to begin with).  MGB_IMPLIED_VALUES=0: columns only.
+        with_values = self.val_idx is not None and os.environ.get("MGB_IMPLIED_VALUES", "1") != "0"
+        ids, self.rec_table, self.rec_vals, self.regular_slices = F.slice_records(
+            torch, off.view(nsl, 8), self.val_idx if with_values else None, self.val_table if with_values else None,
+            self.uniform_len)
         self.slice_rec = ids
-        self.rec_table = recs[order][:, :8].contiguous().to(torch.int32)
         self.struct.d_slice_rec = ids.data_ptr()
         self.struct.d_rec_table = self.rec_table.data_ptr()
         self.struct.nrec = int(self.rec_table.shape[0])
-        if vrec is not None:
-            self.rec_vals = self.val_table[recs[order][:, 8:16].long()].contiguous()      # [nrec][8] doubles
+        if self.rec_vals is not None:
             self.struct.d_rec_vals = self.rec_vals.data_ptr()
         self.set_spec_blocks([0, self.shape[0]])
 

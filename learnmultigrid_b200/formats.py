@@ -278,3 +278,43 @@ def sell_slice_offsets(sell, nrows, length):
     regular = np.all(rel == rel[:, :, :1], axis=(1, 2)) & ((np.arange(nsl) + 1) * SLICE <= nrows)
     off[regular] = rel[regular][:, :, 0].astype(np.int32)
     return off
+
+
+def slice_records(torch, off, val_idx=None, val_table=None, uniform_len=0, max_records=32766):
+    """Deduplicated slice records of a uniform SELL-32 matrix (engine.DeviceSell; sell_core.cuh IMPL / IMPV kernels).
+
+    off      : [nslices, 8] int32 tensor, the per-slice column offsets of mg_sell_slice_offsets (entries beyond
+               uniform_len zero, irregular slices flagged by SLICE_IRREGULAR in column 0)
+    val_idx  : optional uint8 tensor laid out like the matrix' values (value dictionary), val_table its <= 256 doubles
+
+    A slice keeps two bytes, the id of its record (most frequent record = 0; -1, read as 0xffff by the kernels, = the
+    slice is not regular).  With a dictionary, and if at most a tenth of the column-regular slices would be lost, a
+    record also carries the VALUES: a slice then counts as regular only if its 32 rows hold the same value per entry
+    (constant-coefficient stencil levels), and rec_vals[id] are those values.  Pure tensor code (any device): the CPU
+    suite runs it on host tensors (tests/test_host_logic.py).
+    Returns (ids int16 [nslices], rec_table int32 [nrec, 8], rec_vals float64 [nrec, 8] or None, regular_slices)."""
+    nsl = int(off.shape[0])
+    dev = off.device
+    regular = off[:, 0] != SLICE_IRREGULAR
+    n_regular = int(regular.sum().item())
+    vrec = None
+    if val_idx is not None and val_table is not None and uniform_len >= 1 and val_idx.numel() == nsl * 32 * uniform_len:
+        v = val_idx.view(nsl, uniform_len, 32)
+        same = (v == v[:, :, :1]).all(dim=2).all(dim=1)
+        full = regular & same
+        if n_regular > 0 and 10 * int(full.sum().item()) >= 9 * n_regular:
+            vrec = torch.zeros(nsl, 8, dtype=torch.int32, device=dev)
+            vrec[:, :uniform_len] = v[:, :, 0].to(torch.int32)
+            regular = full
+        del v, same, full
+    keys = off if vrec is None else torch.cat([off, vrec], dim=1)
+    recs, inverse, counts = torch.unique(keys[regular], dim=0, return_inverse=True, return_counts=True)
+    order = torch.argsort(counts, descending=True)[:max_records]       # ids by frequency
+    rank_of = torch.full((recs.shape[0],), -1, dtype=torch.int64, device=dev)
+    rank_of[order] = torch.arange(order.numel(), device=dev)
+    ids = torch.full((nsl,), -1, dtype=torch.int16, device=dev)
+    ids[regular] = rank_of[inverse].to(torch.int16)
+    rec_table = recs[order][:, :8].contiguous().to(torch.int32)
+    rec_vals = None if vrec is None else val_table[recs[order][:, 8:16].long()].contiguous()
+    return ids, rec_table, rec_vals, int((ids >= 0).sum().item())
+

@@ -409,3 +409,92 @@ def test_slice_relative_columns_of_structured_levels():
     if lens.min() == lens.max():
         assert not np.any(F.sell_slice_offsets(sell, 96, int(lens.max()))[:, 0] != F.SLICE_IRREGULAR)
     assert F.sell_slice_offsets((np.zeros(1, dtype=np.int64), np.zeros(0, dtype=np.int32), np.zeros(0)), 0, 5).shape == (0, 5)
+
+
+def _records_case(M):
+    """colour-blocked uniform SELL of M, its host-twin offsets padded to 8, a value dictionary if M has <= 256 values"""
+    import torch
+    colors, nc = F.greedy_colors(M)
+    perm, cptr = F.color_permutation(colors)
+    Mp = F.permute_csr(M, perm, F.inverse_permutation(perm))
+    sell = F.csr_to_sell(Mp)
+    slice_ptr, cols, vals = sell
+    lens = np.diff(slice_ptr) // 32
+    assert lens.min() == lens.max()
+    L, nsl = int(lens.max()), len(lens)
+    off = np.zeros((nsl, 8), dtype=np.int32)
+    off[:, :L] = F.sell_slice_offsets(sell, Mp.shape[0], L)
+    irregular = off[:, 0] == F.SLICE_IRREGULAR
+    off[irregular, 1:] = 0
+    table, idx = np.unique(vals.view(np.int64), return_inverse=True)          # distinct BIT patterns (+0 and -0 differ)
+    tt = ti = None
+    if len(table) <= 256:
+        tt = torch.from_numpy(table.view(np.float64).copy())
+        ti = torch.from_numpy(idx.astype(np.uint8))
+    return torch, Mp, cols.reshape(nsl, L, 32), vals.reshape(nsl, L, 32), L, torch.from_numpy(off), ti, tt
+
+
+def test_slice_records_rebuild_the_regular_slices_of_the_matrix():
+    """formats.slice_records (the table behind the implied-columns / implied-values kernels), on host tensors: a slice
+    with a record id has exactly the columns row + rec_table[id] and -- when the records carry values -- exactly the
+    values rec_vals[id] in all of its 32 rows; ids are ordered by frequency; a variable-coefficient operator keeps
+    column records only; an operator whose values alternate from row to row falls back to column records"""
+    from learnmultigrid_b200 import problems as P
+    N = 256                                      # (a 65-wide coarse grid has no regular slice at all)
+    A = F.canonical_csr(P.structured_laplacian_2d(N))
+    Q = P.structured_hierarchy_2d(N, 2, "linear")[0]
+    A1 = F.canonical_csr(sp.csr_matrix(Q.T @ sp.csc_matrix(A) @ Q))
+    for M, want_values in ((A, True), (A1, True), (F.canonical_csr(P.structured_laplacian_2d(N, P.variable_coefficient)), False)):
+        torch, Mp, c, v, L, off, ti, tt = _records_case(M)
+        assert (ti is not None) == want_values
+        ids, rec_table, rec_vals, nreg = F.slice_records(torch, off, ti, tt, L)
+        ids, rec_table = ids.numpy(), rec_table.numpy()
+        assert (rec_vals is not None) == want_values
+        nsl = len(ids)
+        reg = ids >= 0
+        assert nreg == reg.sum() and (not want_values or nreg > 0.4 * nsl)
+        rows = (np.arange(nsl) * 32)[:, None, None] + np.arange(32)[None, None, :]
+        rebuilt = rows + rec_table[np.maximum(ids, 0)][:, :L, None].astype(np.int64)
+        assert np.array_equal(rebuilt[reg], c[reg])
+        col_regular = off.numpy()[:, 0] != F.SLICE_IRREGULAR
+        if want_values:
+            rv = rec_vals.numpy()[np.maximum(ids, 0)][:, :L, None]
+            assert np.array_equal(np.broadcast_to(rv, v.shape)[reg].view(np.int64), v[reg].view(np.int64))   # same bits
+            # a slice lost its id only because its rows differ in a value
+            lost = col_regular & ~reg
+            assert np.all(np.any(v[lost] != v[lost][:, :, :1], axis=(1, 2)))
+            assert lost.sum() <= 0.1 * col_regular.sum()
+        else:
+            assert np.array_equal(reg, col_regular)
+        counts = np.bincount(ids[reg], minlength=len(rec_table))
+        assert np.all(np.diff(counts) <= 0) and counts.min() >= 1            # most frequent record first, none unused
+    # values that alternate from row to row: no slice is regular in its values -> the records stay column records
+    torch, Mp, c, v, L, off, ti, tt = _records_case(A)
+    lane_parity = torch.from_numpy(np.broadcast_to((np.arange(32) % 2).astype(np.uint8), c.shape).copy().reshape(-1))
+    ids2, table2, vals2, nreg2 = F.slice_records(torch, off, lane_parity, torch.tensor([1.0, 2.0], dtype=torch.float64), L)
+    assert vals2 is None and nreg2 == int((off.numpy()[:, 0] != F.SLICE_IRREGULAR).sum())
+
+
+def test_color_list_downloads_an_entry_when_it_is_read():
+    """setup_device.ColorList: colours computed on the device stay there until the host asks; entries read through the
+    list are NumPy arrays from then on, device() hands out what is stored"""
+    import torch
+    from learnmultigrid_b200.setup_device import ColorList
+
+    class Counting:
+        def __init__(self, t):
+            self.t, self.downloads = t, 0
+
+        def cpu(self):
+            self.downloads += 1
+            return self.t
+
+    dev = Counting(torch.tensor([0, 1, 0, 2], dtype=torch.int32))
+    host = np.array([1, 0], dtype=np.int32)
+    cl = ColorList([dev, host, None])
+    assert cl.device(0) is dev and dev.downloads == 0 and len(cl) == 3
+    assert cl[2] is None and cl[1] is host and cl[-2] is host
+    assert isinstance(cl[0], np.ndarray) and np.array_equal(cl[0], [0, 1, 0, 2]) and dev.downloads == 1
+    assert cl[0] is cl[0] and dev.downloads == 1                     # cached
+    assert [None if c is None else c.tolist() for c in cl] == [[0, 1, 0, 2], [1, 0], None]
+    assert [None if c is None else len(c) for c in cl[0:2]] == [4, 2]
