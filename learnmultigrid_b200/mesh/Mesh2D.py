@@ -9,6 +9,10 @@ import math
 
 import numpy as np
 
+# the reference's Mesh2D module also carries a copy of the 1D refinement mesh (Mesh2D.py:524-546; its parent there
+# has no connection_matrix, so only the Mesh1D one can be constructed): same name, the working class
+from .Mesh1D import Mesh1DRefinement  # noqa: F401
+
 
 def get_prime_factors(number):
     prime_factors = []
