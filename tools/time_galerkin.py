@@ -57,19 +57,20 @@ def main():
         n = X.shape[0]
         counts = S.empty(n, t.int32)
         avg = Y.nnz / max(Y.shape[0], 1)
-        log_t = 7
+        import numpy as np
+        est = 2.0 * (X.nnz / max(n, 1)) * avg            # as DeviceSetup.spgemm sizes its first symbolic table
+        log_t = min(7, max(5, int(np.ceil(np.log2(max(2.0 * est, 2.0))))))
         with Timed(tag + " symbolic (2^%d slots)" % log_t):
             g = S._group_for(avg, log_t, False)
             S._flag.zero_()
             lib.mg_spgemm_symbolic(n, X.indptr.data_ptr(), X.indices.data_ptr(), Y.indptr.data_ptr(),
                                    Y.indices.data_ptr(), g, log_t, counts.data_ptr(), S._flag.data_ptr(), S.st())
-            assert int(S._flag.item()) == 0
+            assert int(S._flag.item()) == 0, "table overflow: DeviceSetup.spgemm would retry with a larger one"
         with Timed(tag + " row maximum + scan"):
             max_row = int(counts.max().item())
             cptr, total = S.scan(counts, n)
         cidx = S.empty(total, t.int32)
         cval = S.empty(total, t.float64)
-        import numpy as np
         log_n = max(4, int(np.ceil(np.log2(max(2 * max_row, 2)))))
         nzc = S.empty(n, t.int32)
         with Timed(tag + " numeric (2^%d slots, group %d)" % (log_n, S._group_for(avg, log_n, True))):
