@@ -1,4 +1,4 @@
-"""Row-partitioned hierarchy built from THIS RANK'S ROW BLOCKS ONLY (DESIGN 12, weak scaling): no process ever holds
+"""Row-partitioned hierarchy built from THIS RANK'S ROW BLOCKS ONLY (DESIGN 7, weak scaling): no process ever holds
 a global operator of a partitioned level, so the problem is bounded by the memory of all GPUs together instead of one.
 
     StripHierarchy(A_blk, Q_blks, offsets, fabric, n_dist, ...)
@@ -15,10 +15,10 @@ distributed.DistributedHierarchy._setup_dist with the row blocks uploaded instea
 matrices; the result -- SELL operators, layouts, exchange descriptors -- is the same, so the cycle's iterates are
 bit-identical to DistributedHierarchy's and to the single-GPU hierarchy's.
 
-STATUS: written at the end of round 1 without GPU time left; the device part has not run on a B200 yet.  The GPU tests
-(tests/test_gpu_strip.py) are therefore skipped unless MGB_UNVERIFIED=1, and nothing else in the package uses this
-module.  _setup_dist below repeats the second half of DistributedHierarchy._setup_dist on purpose (the verified path is
-left untouched); the two are to be merged once this one has passed on the GPU.
+STATUS: verified on B200 in round 2 -- bit-identical to DistributedHierarchy on virtual ranks and on 2-8 real ranks
+(tests/test_gpu_strip.py, profiles/r02_pytest_gpu_unverified_first_run.log, profiles/r02_weak_*: 537 M unknowns on 8
+GPUs).  _setup_dist below still repeats the second half of DistributedHierarchy._setup_dist (row blocks uploaded
+instead of cut out of global device matrices); merging the two is housekeeping that has not been done.
 """
 import ctypes
 
